@@ -1,0 +1,305 @@
+/* iteres_main.c -- the `iteres` command line tool on top of libiteres_gpu.so.
+ *
+ * Same sub-commands, option letters, defaults, positional arguments and output file names as the
+ * reference drivers (iteres.c:17-29, stat.c:30-186, filter.c:30-161, cpgstat.c:16-95,
+ * cpgfilter.c:19-110), so it is a drop-in for `iteres stat | filter | cpgstat | cpgfilter`.
+ * nameStat / subfamStat are aliases (BASELINE.json's names): nameStat == filter, subfamStat == stat.
+ * The scan itself runs on the CUDA device through the C ABI of include/iteres_gpu.h; failures keep
+ * the reference's convention: message on stderr, exit status 255 (cuskent/errabort.c:166-181).
+ *
+ * Not produced by this build: the .bigWig files (Kent bwgCreate, outside the hot path; the .wig files
+ * they are made from are written and kept with -w), SAM text input (-S), -R, -B and -V.
+ */
+#define _GNU_SOURCE
+#include <getopt.h>
+#include <libgen.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include "../../include/iteres_gpu.h"
+
+#define REF_VERSION "0.3.3-r123"
+
+static void die(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
+    fputc('\n', stderr);
+    exit(-1);
+}
+static char *fmt_alloc(const char *fmt, ...) {
+    char *s = NULL; va_list ap; va_start(ap, fmt);
+    if (vasprintf(&s, fmt, ap) < 0) die("Mem Error.");
+    va_end(ap);
+    return s;
+}
+/* basename without its last extension (generic.c:7-15) */
+static char *stem(const char *path) {
+    char *tmp = strdup(path), *b = strdup(basename(tmp));
+    char *dot = strrchr(b, '.');
+    if (dot && dot != b) *dot = 0;
+    free(tmp);
+    return b;
+}
+static unsigned int uarg(const char *s) { return (unsigned int)strtol(s, 0, 0); }
+
+typedef struct { const char *flag, *text; } optline;
+static int print_usage(const char *what, const char *synopsis, const optline *o) {
+    fprintf(stderr, "\n%s\n\nUsage:   %s\n\n", what, synopsis);
+    for (int i = 0; o[i].flag; i++) fprintf(stderr, "%s -%s       %s\n", i ? "        " : "Options:", o[i].flag, o[i].text);
+    fprintf(stderr, "\n");
+    return 1;
+}
+
+static const optline STAT_OPTS[] = {
+    {"S", "input is SAM [off]"}, {"Q", "unique reads mapping Quality threshold [10]"}, {"c", "coverage threshold for overlapping [0.0001]"},
+    {"x", "discard multi-reads if mapped to different subfamily [on]"},
+    {"N", "normalized by number of (0: reads in repeats, 1: non-redundant reads, 2: mapped reads, 3: total reads) [0])"},
+    {"U", "unique reads normalized by number of (0: unique mapped reads in repeats, 1: unique mapped reads, 2: total reads) [0])"},
+    {"R", "remove redundant reads [off]"}, {"T", "treat 1 paired-end read as 2 single-end reads [off]"},
+    {"D", "discard if only one end mapped in a paired end reads [off]"}, {"w", "keep the wiggle file [off]"},
+    {"B", "output bed file of mapped reads [off]"}, {"V", "output bed file of unique mapped reads [off]"},
+    {"C", "Add 'chr' string as prefix of reference sequence [off]"}, {"E", "extend reads to represent fragment [150], specify 0 if want no extension"},
+    {"I", "Insert length threshold [500]"}, {"o", "output prefix [basename of input without extension]"}, {"h", "help message"}, {"?", "help message"}, {0, 0}};
+static const optline FILTER_OPTS[] = {
+    {"S", "input is SAM [off]"}, {"Q", "unique reads mapping Quality threshold [10]"}, {"g", "coverage threshold for overlapping [0.0001]"},
+    {"N", "normalized by number of (0: unique reads, 1: non-redundant reads, 2: mapped reads, 3: used read ends) [0]"},
+    {"n", "repName filter"}, {"c", "repClass filter"}, {"f", "repFamily filter"}, {"t", "only output repeats with at least this many reads [1]"},
+    {"r", "output the list of reads of each repeat [off]"}, {"R", "remove redundant reads [off]"},
+    {"T", "treat 1 paired-end read as 2 single-end reads [off]"}, {"D", "discard if only one end mapped in a paired end reads [off]"},
+    {"C", "Add 'chr' string as prefix of reference sequence [off]"}, {"E", "extend reads to represent fragment [150], specify 0 if want no extension"},
+    {"I", "Insert length threshold [500]"}, {"o", "output prefix [basename of input without extension]"}, {"h", "help message"}, {"?", "help message"}, {0, 0}};
+static const optline CPGSTAT_OPTS[] = {{"w", "keep the wiggle file [off]"}, {"o", "output prefix [basename of input without extension]"}, {"h", "help message"}, {"?", "help message"}, {0, 0}};
+static const optline CPGFILTER_OPTS[] = {{"n", "repName filter"}, {"c", "repClass filter"}, {"f", "repFamily filter"}, {"t", "CpG score threshold [0]"},
+    {"o", "output prefix [basename of input without extension]"}, {"h", "help message"}, {"?", "help message"}, {0, 0}};
+
+static int stat_usage(void) { return print_usage("Obtain alignment statistics for each repeat subfamily, family and class.",
+    "iteres stat [options] <chromosome size file> <repeat size file> <rmsk.txt> <bam/sam alignment file1,file2,file3...>", STAT_OPTS); }
+static int filter_usage(void) { return print_usage("Filter alignment statistics on repName, repClass or repFamily; one row per repeat locus.",
+    "iteres filter [options] <chromosome size file> <repeat size file> <rmsk.txt> <bam/sam alignment file>", FILTER_OPTS); }
+static int cpgstat_usage(void) { return print_usage("Obtain CpG statistics for each repeat subfamily, family and class.",
+    "iteres cpgstat [options] <chromosome size file> <repeat size file> <rmsk.txt> <CpG bedGraph file>", CPGSTAT_OPTS); }
+static int cpgfilter_usage(void) { return print_usage("Filter CpG statistics on repName, repClass or repFamily; one row per repeat locus.",
+    "iteres cpgfilter [options] <chromosome size file> <repeat size file> <rmsk.txt> <CpG bedGraph file>", CPGFILTER_OPTS); }
+
+static void use_device(void) {
+    const char *d = getenv("ITERES_DEVICE");
+    if (itx_device_count() <= 0) die("no CUDA device found: this build of iteres runs its hot path on the GPU only");
+    if (d && itx_set_device(atoi(d)) != ITX_OK) die("cannot use CUDA device %s", d);
+}
+static void done_in(time_t t0) { fprintf(stderr, "* Done, time used %.0f seconds.\n", difftime(time(NULL), t0)); }
+
+/* which of -n / -c / -f was given -> (rmsk column, name) as filter.c:93-113 */
+static int pick_filter(char *name, char *cls, char *fam, char **subfam) {
+    int field = 0;
+    if ((name && cls) || (name && fam) || (cls && fam)) die("Please specify only one filter, either -n, -c or -f.");
+    *subfam = strdup("ALL");
+    if (name) { *subfam = name; field = 10; } else if (cls) { *subfam = cls; field = 11; } else if (fam) { *subfam = fam; field = 12; }
+    if (strcmp(*subfam, "ALL") == 0) { fprintf(stderr, "* You didn't specify any filter, will output all repeats\n"); field = 0; }
+    return field;
+}
+
+static int main_stat(int argc, char **argv) {
+    itx_scan_opts o; itx_scan_opts_default(&o);
+    int c, keep_wig = 0, sam = 0, bed = 0, bedu = 0; unsigned int norm = 0, norm2 = 0; char *prefix = NULL;
+    time_t t0 = time(NULL);
+    while ((c = getopt(argc, argv, "SQ:c:xN:U:RTDwBVCo:E:I:h?")) >= 0) {
+        switch (c) {
+            case 'S': sam = 1; break;
+            case 'Q': o.mapQ = uarg(optarg); break;
+            case 'c': o.minCoverage = (float)atof(optarg); break;
+            case 'x': o.diffSubfam = 0; break;
+            case 'N': norm = uarg(optarg); break;
+            case 'U': norm2 = uarg(optarg); break;
+            case 'R': o.rmDup = 1; break;
+            case 'T': o.treat = 1; break;
+            case 'D': o.discardWrongEnd = 1; break;
+            case 'w': keep_wig = 1; break;
+            case 'B': bed = 1; break;
+            case 'V': bedu = 1; break;
+            case 'C': o.addChr = 1; break;
+            case 'E': o.extension = uarg(optarg); break;
+            case 'I': o.iSize = uarg(optarg); break;
+            case 'o': prefix = strdup(optarg); break;
+            case 'h': case '?': return stat_usage();
+            default: return 1;
+        }
+    }
+    if (optind + 4 > argc) return stat_usage();
+    const char *chrom_sizes = argv[optind], *rep_sizes = argv[optind + 1], *rmsk = argv[optind + 2], *bams = argv[optind + 3];
+    int nfiles = 1; for (const char *p = bams; *p; p++) if (*p == ',') nfiles++;
+    fprintf(stderr, "* Provided %i BAM/SAM file(s)\n", nfiles);
+    if (!prefix) { char *first = strdup(bams); char *comma = strchr(first, ','); if (comma) *comma = 0; prefix = stem(first); free(first); }
+    static const int NIDX[4] = {9, 8, 6, 0}, NIDX2[3] = {10, 7, 0};
+    if (norm > 3 || norm2 > 2) die("Wrong normalization method specified");
+    if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
+    if (bed || bedu) die("-B / -V bed output is not supported by this build");
+    use_device();
+    char err[ITX_ERRLEN]; uint64_t cnt[13];
+    fprintf(stderr, "* Parsing the rmsk file\n");
+    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
+    if (!ix) die("%s", err);
+    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    fprintf(stderr, "* Parsing the SAM/BAM file\n");
+    if (itx_scan_alignments(ix, bams, &o, cnt, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
+    if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Writing stats and Wig file\n");
+    char *wig = fmt_alloc("%s.iteres.wig", prefix), *wigu = fmt_alloc("%s.iteres.unique.wig", prefix);
+    char *f_sub = fmt_alloc("%s.iteres.subfamily.stat", prefix), *f_fam = fmt_alloc("%s.iteres.family.stat", prefix), *f_cla = fmt_alloc("%s.iteres.class.stat", prefix);
+    if (itx_write_stat(ix, f_sub, wig, f_fam, f_cla, wigu, cnt[NIDX[norm]], cnt[NIDX2[norm2]]) != ITX_OK) die("Can't write the stat files for prefix %s", prefix);
+    fprintf(stderr, "* bigWig files are not generated by this build%s\n", keep_wig ? "" : " (use -w to keep the wiggle files)");
+    fprintf(stderr, "* Preparing report file\n");
+    char *rep = fmt_alloc("%s.iteres.report", prefix);
+    if (itx_write_report(rep, cnt, o.mapQ, "ALL") != ITX_OK) die("Can't open %s to write", rep);
+    if (!keep_wig) { unlink(wig); unlink(wigu); }
+    itx_index_free(ix);
+    done_in(t0);
+    return 0;
+}
+
+static int main_filter(int argc, char **argv) {
+    itx_scan_opts o; itx_scan_opts_default(&o); o.filter = 1; o.diffSubfam = 0;
+    int c, sam = 0, readlist = 0, threshold = 1; unsigned int norm = 0; char *prefix = NULL, *name = NULL, *cls = NULL, *fam = NULL, *subfam;
+    time_t t0 = time(NULL);
+    while ((c = getopt(argc, argv, "SQ:g:N:n:c:t:f:rRTDCE:I:o:h?")) >= 0) {
+        switch (c) {
+            case 'S': sam = 1; break;
+            case 'Q': o.mapQ = uarg(optarg); break;
+            case 'g': o.minCoverage = (float)atof(optarg); break;
+            case 'N': norm = uarg(optarg); break;
+            case 't': threshold = (int)uarg(optarg); break;
+            case 'r': readlist = 1; break;
+            case 'R': o.rmDup = 1; break;
+            case 'T': o.treat = 1; break;
+            case 'D': o.discardWrongEnd = 1; break;
+            case 'C': o.addChr = 1; break;
+            case 'n': name = strdup(optarg); break;
+            case 'c': cls = strdup(optarg); break;
+            case 'f': fam = strdup(optarg); break;
+            case 'E': o.extension = uarg(optarg); break;
+            case 'I': o.iSize = uarg(optarg); break;
+            case 'o': prefix = strdup(optarg); break;
+            case 'h': case '?': return filter_usage();
+            default: return 1;
+        }
+    }
+    if (optind + 4 > argc) return filter_usage();
+    const char *chrom_sizes = argv[optind], *rep_sizes = argv[optind + 1], *rmsk = argv[optind + 2], *bam = argv[optind + 3];
+    int field = pick_filter(name, cls, fam, &subfam);
+    static const int NIDX[4] = {7, 8, 6, 4};
+    if (norm > 3) die("Wrong normalization method specified");
+    if (!prefix) prefix = stem(bam);
+    if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
+    if (readlist) die("-r (read name lists) is not supported by this build");
+    use_device();
+    char err[ITX_ERRLEN]; uint64_t cnt[13];
+    fprintf(stderr, "* Start to parse the rmsk file\n");
+    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
+    if (!ix) die("%s", err);
+    if (field) fprintf(stderr, "* Total %lld repeats for [%s].\n", (long long)itx_n_elem(ix), subfam);
+    else fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    fprintf(stderr, "* Start to parse the SAM/BAM file\n");
+    if (itx_scan_alignments(ix, bam, &o, cnt, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
+    if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Preparing the output file\n");
+    char *out = fmt_alloc("%s_%s.iteres.loci", prefix, subfam), *rep = fmt_alloc("%s_%s.iteres.reportloci", prefix, subfam);
+    if (itx_write_filter(ix, out, readlist, threshold, cnt[NIDX[norm]]) != ITX_OK) die("Can't open %s to write", out);
+    fprintf(stderr, "* Preparing report file\n");
+    if (itx_write_report(rep, cnt, o.mapQ, subfam) != ITX_OK) die("Can't open %s to write", rep);
+    itx_index_free(ix);
+    done_in(t0);
+    return 0;
+}
+
+static int main_cpgstat(int argc, char **argv) {
+    int c, keep_wig = 0; char *prefix = NULL; time_t t0 = time(NULL);
+    while ((c = getopt(argc, argv, "wo:h?")) >= 0) {
+        switch (c) {
+            case 'w': keep_wig = 1; break;
+            case 'o': prefix = strdup(optarg); break;
+            case 'h': case '?': return cpgstat_usage();
+            default: return 1;
+        }
+    }
+    if (optind + 4 > argc) return cpgstat_usage();
+    const char *chrom_sizes = argv[optind], *rep_sizes = argv[optind + 1], *rmsk = argv[optind + 2], *bg = argv[optind + 3];
+    if (!prefix) prefix = stem(bg);
+    use_device();
+    char err[ITX_ERRLEN]; uint32_t lines = 0, inrep = 0;
+    fprintf(stderr, "* Start to parse the rmsk file\n");
+    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
+    if (!ix) die("%s", err);
+    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    fprintf(stderr, "* Start to parse the bedGraph file\n");
+    if (itx_scan_cpg(ix, bg, 0, &lines, &inrep, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Processed CpG sites: %u\n* CpG sites in Repeats: %u\n", lines, inrep);
+    if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Writing stats and Wig file\n");
+    char *wig = fmt_alloc("%s.CpGstat.wig", prefix);
+    if (itx_write_cpg_stat(ix, fmt_alloc("%s.CpG.subfamily.stat", prefix), wig, fmt_alloc("%s.CpG.family.stat", prefix), fmt_alloc("%s.CpG.class.stat", prefix)) != ITX_OK)
+        die("Can't write the CpG stat files for prefix %s", prefix);
+    fprintf(stderr, "* bigWig files are not generated by this build%s\n", keep_wig ? "" : " (use -w to keep the wiggle file)");
+    if (!keep_wig) unlink(wig);
+    itx_index_free(ix);
+    done_in(t0);
+    return 0;
+}
+
+static int main_cpgfilter(int argc, char **argv) {
+    int c; double thr = 0; char *prefix = NULL, *name = NULL, *cls = NULL, *fam = NULL, *subfam; time_t t0 = time(NULL);
+    while ((c = getopt(argc, argv, "n:c:f:t:o:h?")) >= 0) {
+        switch (c) {
+            case 'n': name = strdup(optarg); break;
+            case 'c': cls = strdup(optarg); break;
+            case 'f': fam = strdup(optarg); break;
+            case 't': thr = strtod(optarg, NULL); break;
+            case 'o': prefix = strdup(optarg); break;
+            case 'h': case '?': return cpgfilter_usage();
+            default: return 1;
+        }
+    }
+    if (optind + 4 > argc) return cpgfilter_usage();
+    const char *chrom_sizes = argv[optind], *rep_sizes = argv[optind + 1], *rmsk = argv[optind + 2], *bg = argv[optind + 3];
+    if (!prefix) prefix = stem(bg);
+    int field = pick_filter(name, cls, fam, &subfam);
+    use_device();
+    char err[ITX_ERRLEN]; uint32_t lines = 0, inrep = 0;
+    fprintf(stderr, "* Start to parse the rmsk file\n");
+    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
+    if (!ix) die("%s", err);
+    fprintf(stderr, "* Start to parse the bedGraph file\n");
+    if (itx_scan_cpg(ix, bg, 1, &lines, &inrep, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Processed CpG sites: %u\n* CpG sites in Repeats: %u\n", lines, inrep);
+    if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
+    fprintf(stderr, "* Preparing the output file\n");
+    char *out = fmt_alloc("%s_%s.CpG.loci", prefix, subfam);
+    if (itx_write_cpg_filter(ix, out, thr) != ITX_OK) die("Can't open %s to write", out);
+    itx_index_free(ix);
+    done_in(t0);
+    return 0;
+}
+
+static int usage(void) {
+    fprintf(stderr, "\nProgram: iteres (repeat analysis utils from Wang lab; B200 build: %s)\nVersion: %s\n\n", itx_version(), REF_VERSION);
+    fprintf(stderr, "Usage:   iteres <command> [options]\n\n");
+    fprintf(stderr, "Command: stat        get repeat alignment statistics\n");
+    fprintf(stderr, "         filter      filter alignment statistic on repName/repFamily/repClass\n");
+    fprintf(stderr, "         cpgstat     generate CpG density from MRE-Seq data for repeats\n");
+    fprintf(stderr, "         cpgfilter   filter CpG statistic on repName/repFamily/repClass\n");
+    fprintf(stderr, "         subfamStat  alias of stat;  nameStat  alias of filter\n\n");
+    return 1;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return usage();
+    const char *cmd = argv[1];
+    if (!strcmp(cmd, "stat") || !strcmp(cmd, "subfamStat")) return main_stat(argc - 1, argv + 1);
+    if (!strcmp(cmd, "filter") || !strcmp(cmd, "nameStat")) return main_filter(argc - 1, argv + 1);
+    if (!strcmp(cmd, "cpgstat")) return main_cpgstat(argc - 1, argv + 1);
+    if (!strcmp(cmd, "cpgfilter")) return main_cpgfilter(argc - 1, argv + 1);
+    fprintf(stderr, "[iteres] unrecognized command '%s'\n", cmd);
+    return 1;
+}

@@ -1,0 +1,715 @@
+/* itx_gpu.cu -- device side of libiteres_gpu.so: index upload, the scan pipelines (device-resident
+ * stream, host stream through pinned staging, BGZF file through host inflate threads), result
+ * download, NCCL allreduce of the counter block.  Built for sm_100a only. */
+#include "itx_kernels.cuh"
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <errno.h>
+#include <time.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+
+#define ITX_SLACK 64
+#define ITX_MAX_EVENTS 4096
+
+struct itx_cuda {
+    int device; cudaStream_t stream, copy_stream;
+    int sm_count; size_t smem_optin;
+    /* index */
+    itx_dev_index D;
+    void *d_iv, *d_pmax, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
+    void *d_sub_len, *d_sub_bp_off, *d_sub_fold;
+    /* counter block */
+    void *d_u64; size_t n_u64;           /* cnt[16] + grp */
+    void *d_u32; size_t n_u32;           /* bp_diff, bp_diff_u, el_cnt, el_cnt_u */
+    void *d_cpg_u32; size_t n_cpg_u32;   /* grp_cpg, el_cpg */
+    void *d_cpg_f64; size_t n_cpg_f64;   /* grp_cpg_score, bp_cpg, el_cpg_score */
+    void *d_misc;                        /* tid_unknown_seen[ITX_MAX_TID_SEEN] + status[8] */
+    uint32_t *d_bp, *d_bp_u;             /* prefix-summed coverage (finalize output) */
+    /* scan workspace */
+    uint32_t C, S; uint64_t cap_chunks;
+    itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
+    long long *d_sel; int want_sel;
+    itx_trace *d_trace; uint64_t trace_cap;
+    /* staging for host streams */
+    uint8_t *d_stream; uint64_t d_stream_cap;
+    uint8_t *h_stage[2]; uint64_t h_stage_cap;
+    void *d_flush;
+    cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
+    /* NCCL (dlopen) */
+    void *nccl_lib; void *nccl_comm; int nranks, rank;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); return ITX_ENODEV; } } while (0)
+#define CKN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
+
+static int g_device = 0;
+static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
+extern "C" int itx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+extern "C" int itx_set_device(int device) { g_device = device; return cudaSetDevice(device) == cudaSuccess ? ITX_OK : ITX_ENODEV; }
+extern "C" void *itx_dev_alloc(uint64_t bytes) { void *p = NULL; cudaSetDevice(g_device); if (cudaMalloc(&p, bytes) != cudaSuccess) return NULL; return p; }
+extern "C" void itx_dev_free(void *p) { cudaFree(p); }
+extern "C" int itx_dev_upload(void *dst, const void *src, uint64_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? ITX_OK : ITX_ENODEV; }
+extern "C" void *itx_host_alloc_pinned(uint64_t bytes) { void *p = NULL; cudaSetDevice(g_device); if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL; return p; }
+extern "C" void itx_host_free_pinned(void *p) { cudaFreeHost(p); }
+extern "C" int itx_dev_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? ITX_OK : ITX_ENODEV; }
+
+template <typename T> static int upload(void **dst, const T *src, size_t n, char *err) {
+    size_t bytes = sizeof(T) * (n ? n : 1);
+    CK(cudaMalloc(dst, bytes));
+    if (n) CK(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return ITX_OK;
+}
+
+static void cuda_free_all(itx_cuda *cu) {
+    if (!cu) return;
+    cudaSetDevice(cu->device);
+    void *ptrs[] = {cu->d_iv, cu->d_pmax, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
+                    cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
+                    cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
+    for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
+    if (cu->stream) cudaStreamDestroy(cu->stream);
+    if (cu->copy_stream) cudaStreamDestroy(cu->copy_stream);
+    free(cu);
+}
+
+extern "C" void itx_index_free(itx_index *ix) {
+    if (!ix) return;
+    itx_comm_destroy(ix);
+    cuda_free_all(ix->cu);
+    itx_host_index_free(ix);
+    free(ix);
+}
+
+static int zero_counters(itx_index *ix, char *err) {
+    itx_cuda *cu = ix->cu;
+    CK(cudaMemsetAsync(cu->d_u64, 0, cu->n_u64 * 8, cu->stream));
+    CK(cudaMemsetAsync(cu->d_u32, 0, cu->n_u32 * 4, cu->stream));
+    CK(cudaMemsetAsync(cu->d_cpg_u32, 0, cu->n_cpg_u32 * 4, cu->stream));
+    CK(cudaMemsetAsync(cu->d_cpg_f64, 0, cu->n_cpg_f64 * 8, cu->stream));
+    CK(cudaMemsetAsync(cu->d_misc, 0, (ITX_MAX_TID_SEEN + 8) * 4, cu->stream));
+    CK(cudaStreamSynchronize(cu->stream));
+    return ITX_OK;
+}
+
+extern "C" void itx_index_reset_counts(itx_index *ix) {
+    char err[ITX_ERRLEN];
+    cudaSetDevice(ix->cu->device);
+    zero_counters(ix, err);
+    memset(ix->cnt, 0, sizeof ix->cnt);
+    for (int32_t i = 0; i < ix->subs.n; i++) { ix->sub[i].read_count = ix->sub[i].read_count_unique = 0; ix->sub[i].cpg_count = 0; ix->sub[i].cpg_score = 0; }
+    for (int32_t i = 0; i < ix->fams.n; i++) { ix->fam[i].read_count = ix->fam[i].read_count_unique = 0; ix->fam[i].cpg_count = 0; ix->fam[i].cpg_score = 0; }
+    for (int32_t i = 0; i < ix->clas.n; i++) { ix->cla[i].read_count = ix->cla[i].read_count_unique = 0; ix->cla[i].cpg_count = 0; ix->cla[i].cpg_score = 0; }
+    if (ix->el_names) for (long long i = 0; i < ix->n_elem; i++) { for (uint32_t k = 0; k < ix->el_names_n[i]; k++) free(ix->el_names[i][k]); ix->el_names_n[i] = 0; }
+    itx_strtab_free(&ix->warned); itx_strtab_init(&ix->warned);
+}
+
+extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk,
+                                      int filter_field, const char *filter_name, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    itx_index *ix = (itx_index *)calloc(1, sizeof(itx_index));
+    if (itx_host_index_load(ix, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err) != ITX_OK) { itx_host_index_free(ix); free(ix); return NULL; }
+    itx_cuda *cu = (itx_cuda *)calloc(1, sizeof(itx_cuda));
+    ix->cu = cu; ix->device = cu->device = g_device;
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= g_device) {
+            snprintf(err, ITX_ERRLEN, "no usable CUDA device %d (libiteres_gpu has no CPU path)", g_device);
+            goto fail;
+        }
+        CKN(cudaSetDevice(g_device));
+        cudaDeviceProp prop; CKN(cudaGetDeviceProperties(&prop, g_device));
+        cu->sm_count = prop.multiProcessorCount; cu->smem_optin = prop.sharedMemPerBlockOptin;
+        CKN(cudaStreamCreateWithFlags(&cu->stream, cudaStreamNonBlocking));
+        CKN(cudaStreamCreateWithFlags(&cu->copy_stream, cudaStreamNonBlocking));
+        const size_t ne = (size_t)ix->n_elem; const int32_t nc = ix->chroms.n, ns = ix->subs.n, nf = ix->fams.n, ncl = ix->clas.n;
+        if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_pmax, ix->pmax, ne, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
+            upload(&cu->d_meta2, ix->meta2, ne, err) || upload(&cu->d_chrom_off, ix->chrom_off, (size_t)nc + 1, err) ||
+            upload(&cu->d_chrom_size, ix->chrom_size, (size_t)nc, err) || upload(&cu->d_sub_len, ix->sub_len, (size_t)ns, err) ||
+            upload(&cu->d_sub_bp_off, ix->sub_bp_off, (size_t)ns + 1, err) || upload(&cu->d_sub_fold, ix->sub_fold, (size_t)ns, err)) goto fail;
+        /* chromosome-name table for XA lookups */
+        uint32_t nslot = 16; while (nslot < (uint32_t)nc * 2u + 2u) nslot <<= 1;
+        uint32_t *slot = (uint32_t *)calloc(nslot, 4), *noff = (uint32_t *)calloc((size_t)nc + 1, 4);
+        size_t pool = 0; for (int32_t c = 0; c < nc; c++) pool += strlen(ix->chroms.names[c]) + 1;
+        char *poolb = (char *)calloc(pool + 1, 1); size_t w = 0;
+        for (int32_t c = 0; c < nc; c++) {
+            const char *nm = ix->chroms.names[c]; size_t l = strlen(nm);
+            noff[c] = (uint32_t)w; memcpy(poolb + w, nm, l + 1); w += l + 1;
+            uint32_t i = itx_fnv1a(nm, l) & (nslot - 1);
+            while (slot[i]) i = (i + 1) & (nslot - 1);
+            slot[i] = (uint32_t)c + 1;
+        }
+        int r = upload(&cu->d_cname_slot, slot, nslot, err) || upload(&cu->d_cname_off, noff, (size_t)nc + 1, err) || upload(&cu->d_cname_pool, poolb, pool + 1, err);
+        free(slot); free(noff); free(poolb);
+        if (r) goto fail;
+        /* counter block */
+        const size_t ng = (size_t)(ns + nf + ncl);
+        cu->n_u64 = 16 + 2 * ng; cu->n_u32 = 2 * (size_t)ix->bp_len + 2 * ne;
+        cu->n_cpg_u32 = ng + ne; cu->n_cpg_f64 = ng + (size_t)ix->bp_len + ne;
+        CKN(cudaMalloc(&cu->d_u64, (cu->n_u64 ? cu->n_u64 : 1) * 8)); CKN(cudaMalloc(&cu->d_u32, (cu->n_u32 ? cu->n_u32 : 1) * 4));
+        CKN(cudaMalloc(&cu->d_cpg_u32, (cu->n_cpg_u32 ? cu->n_cpg_u32 : 1) * 4)); CKN(cudaMalloc(&cu->d_cpg_f64, (cu->n_cpg_f64 ? cu->n_cpg_f64 : 1) * 8));
+        CKN(cudaMalloc(&cu->d_misc, (ITX_MAX_TID_SEEN + 8) * 4));
+        CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
+        CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
+        itx_dev_index &D = cu->D;
+        D.iv = (const itx_iv *)cu->d_iv; D.pmax = (const int32_t *)cu->d_pmax; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
+        D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
+        D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool;
+        D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix->stat_mode;
+        D.sub_len = (const uint32_t *)cu->d_sub_len; D.sub_bp_off = (const unsigned long long *)cu->d_sub_bp_off; D.sub_fold = (const int32_t *)cu->d_sub_fold;
+        D.cnt = (unsigned long long *)cu->d_u64; D.grp = D.cnt + 16;
+        D.bp_diff = (uint32_t *)cu->d_u32; D.bp_diff_u = D.bp_diff + ix->bp_len; D.el_cnt = D.bp_diff_u + ix->bp_len; D.el_cnt_u = D.el_cnt + ne;
+        D.grp_cpg = (uint32_t *)cu->d_cpg_u32; D.el_cpg = D.grp_cpg + ng;
+        D.grp_cpg_score = (double *)cu->d_cpg_f64; D.bp_cpg = D.grp_cpg_score + ng; D.el_cpg_score = D.bp_cpg + ix->bp_len;
+        D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
+        if (zero_counters(ix, err)) goto fail;
+    }
+    ix->tune_chunk = 4096; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
+    return ix;
+fail:
+    cuda_free_all(cu); ix->cu = NULL;
+    itx_host_index_free(ix); free(ix);
+    return NULL;
+}
+
+extern "C" int itx_tune(itx_index *ix, uint32_t chunk_bytes, uint64_t window_bytes, int32_t inflate_threads) {
+    if (chunk_bytes) { if (chunk_bytes < 256 || chunk_bytes > (1u << 20) || (chunk_bytes & 63)) return ITX_EARG; ix->tune_chunk = chunk_bytes; }
+    if (window_bytes) { if (window_bytes < (1u << 16)) return ITX_EARG; ix->tune_window = window_bytes; }
+    if (inflate_threads) ix->tune_threads = inflate_threads;
+    return ITX_OK;
+}
+extern "C" int itx_trace_enable(itx_index *ix, uint64_t cap) { ix->trace_cap = cap; return ITX_OK; }
+extern "C" void itx_last_profile(const itx_index *ix, itx_profile *p) { *p = ix->prof; }
+
+/* ------------------------------------------------------------------ BAM header */
+extern "C" itx_bam_header *itx_bam_header_parse(itx_index *ix, const uint8_t *bam, uint64_t len, int addChr, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    itx_bam_header *h = (itx_bam_header *)calloc(1, sizeof *h);
+    if (itx_host_parse_bam_header(ix, bam, len, addChr, h, err) != ITX_OK) { itx_bam_header_free(h); return NULL; }
+    cudaSetDevice(ix->cu->device);
+    size_t n = (size_t)(h->n_ref ? h->n_ref : 1);
+    if (cudaMalloc((void **)&h->d_tid, n * sizeof(itx_tidinfo)) != cudaSuccess ||
+        cudaMemcpy(h->d_tid, h->tid, n * sizeof(itx_tidinfo), cudaMemcpyHostToDevice) != cudaSuccess) {
+        snprintf(err, ITX_ERRLEN, "CUDA error uploading the reference table"); itx_bam_header_free(h); return NULL;
+    }
+    return h;
+}
+extern "C" uint64_t itx_bam_header_len(const itx_bam_header *h) { return h->hdr_len; }
+extern "C" void itx_bam_header_free(itx_bam_header *h) {
+    if (!h) return;
+    if (h->names) for (int32_t i = 0; i < h->n_ref; i++) free(h->names[i]);
+    free(h->names); free(h->lens); free(h->tid);
+    if (h->d_tid) cudaFree(h->d_tid);
+    free(h);
+}
+
+/* ------------------------------------------------------------------ scan machinery */
+static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
+    itx_cuda *cu = ix->cu;
+    uint32_t C = ix->tune_chunk, S = C / 36 + 1;
+    uint64_t need = window_bytes / C + 2;
+    bool want_trace = ix->trace_cap != 0;
+    if (cu->d_tuples && cu->C == C && cu->cap_chunks >= need && (!want_trace || cu->d_rec_base) && (!cu->want_sel || cu->d_sel)) goto trace;
+    cudaFree(cu->d_tuples); cudaFree(cu->d_entry); cudaFree(cu->d_exit); cudaFree(cu->d_nrec); cudaFree(cu->d_rec_base); cudaFree(cu->d_sel);
+    cu->d_tuples = NULL; cu->d_entry = cu->d_exit = cu->d_rec_base = NULL; cu->d_nrec = NULL; cu->d_sel = NULL;
+    cu->C = C; cu->S = S; cu->cap_chunks = need;
+    CK(cudaMalloc((void **)&cu->d_tuples, need * S * sizeof(itx_tuple)));
+    CK(cudaMalloc((void **)&cu->d_entry, need * 8)); CK(cudaMalloc((void **)&cu->d_exit, need * 8)); CK(cudaMalloc((void **)&cu->d_nrec, need * 4));
+    if (want_trace) CK(cudaMalloc((void **)&cu->d_rec_base, need * 8));
+    if (cu->want_sel) CK(cudaMalloc((void **)&cu->d_sel, need * S * sizeof(long long)));
+trace:
+    if (want_trace && (!cu->d_trace || cu->trace_cap < ix->trace_cap)) {
+        cudaFree(cu->d_trace); cu->d_trace = NULL;
+        CK(cudaMalloc((void **)&cu->d_trace, ix->trace_cap * sizeof(itx_trace)));
+        cu->trace_cap = ix->trace_cap;
+    }
+    return ITX_OK;
+}
+static cudaEvent_t get_event(itx_cuda *cu, int i) {
+    while (cu->n_ev_made <= i && cu->n_ev_made < ITX_MAX_EVENTS) cudaEventCreate(&cu->ev[cu->n_ev_made++]);
+    return cu->ev[i < ITX_MAX_EVENTS ? i : ITX_MAX_EVENTS - 1];
+}
+static itx_dev_opts dev_opts(const itx_scan_opts *o) {
+    itx_dev_opts d; d.mapQ = o->mapQ; d.iSize = o->iSize; d.extension = o->extension; d.minCoverage = o->minCoverage;
+    d.filter = o->filter; d.discardWrongEnd = o->discardWrongEnd; d.treat = o->treat; d.diffSubfam = o->diffSubfam;
+    return d;
+}
+static int check_opts(const itx_scan_opts *o, char *err) {
+    if (o->rmDup) { snprintf(err, ITX_ERRLEN, "-R (remove duplicates) is order dependent and not run on the device in this build"); return ITX_ENOTSUP; }
+    return ITX_OK;
+}
+
+/* Scan context: the stream lives in one device buffer `b` of `len` bytes (plus slack); the window
+ * loop processes chunks [k_next, k_hi) once `avail` bytes are on the device. */
+typedef struct {
+    itx_index *ix; const itx_bam_header *h; const uint8_t *b; uint64_t len; itx_dev_opts o;
+    uint64_t k_first, k_end, k_next; int ev_n; int windows;
+    int n_launch;
+} scan_ctx;
+
+static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err) {
+    itx_cuda *cu = ix->cu;
+    memset(sc, 0, sizeof *sc);
+    sc->ix = ix; sc->h = h; sc->b = d_bam; sc->len = len; sc->o = dev_opts(o);
+    cu->want_sel = 0;
+    int rc = ensure_work(ix, window, err); if (rc) return rc;
+    sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
+    sc->k_next = sc->k_first;
+    unsigned long long carry = h->hdr_len;
+    CK(cudaMemcpyAsync(cu->d_carry, &carry, 8, cudaMemcpyHostToDevice, cu->stream));
+    if (ix->trace_cap) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
+    CK(cudaStreamSynchronize(cu->stream));   /* the 8-byte sources live on this stack frame */
+    return ITX_OK;
+}
+/* launch the kernels for chunks [k_next, k_hi) (k_hi <= k_end); avail = bytes valid on the device */
+static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
+    itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
+    while (sc->k_next < k_hi) {
+        uint64_t n64 = k_hi - sc->k_next; if (n64 > cu->cap_chunks - 1) n64 = cu->cap_chunks - 1;
+        uint32_t n = (uint32_t)n64;
+        itx_decode_args A;
+        A.b = sc->b; A.len = sc->len; A.avail = avail; A.k0 = sc->k_next; A.nchunks = n; A.C = cu->C; A.S = cu->S;
+        A.tid = sc->h->d_tid; A.n_ref = sc->h->n_ref; A.o = sc->o;
+        A.tuples = cu->d_tuples; A.entry = cu->d_entry; A.exit_ = cu->d_exit; A.nrec = cu->d_nrec;
+        A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status;
+        bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
+        if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
+        k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
+        k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
+        k_fixup<<<1, 32, 0, cu->stream>>>(A);
+        if (timed) cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream);
+        sc->n_launch += 3;
+        itx_overlap_args B;
+        B.D = cu->D; B.b = sc->b; B.k0 = sc->k_next; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
+        B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL;
+        if (ix->trace_cap) {
+            k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
+            B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
+        }
+        size_t hist = 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4;
+        bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
+        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
+        uint32_t need_blocks = (n + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
+        if (smem) {
+            if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
+            k_overlap<true><<<blocks, 256, hist, cu->stream>>>(B);
+        } else k_overlap<false><<<blocks, 256, 0, cu->stream>>>(B);
+        sc->n_launch++;
+        if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
+        sc->windows++;
+        sc->k_next += n;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { snprintf(err, ITX_ERRLEN, "kernel launch failed: %s", cudaGetErrorString(e)); return ITX_ENODEV; }
+    }
+    return ITX_OK;
+}
+static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
+    itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
+    unsigned long long hc[16]; uint32_t st[8];
+    CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaStreamSynchronize(cu->stream));
+    for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k];
+    if (cnt) memcpy(cnt, ix->cnt, sizeof ix->cnt);
+    itx_profile *P = &ix->prof;
+    P->decode_ms = P->overlap_ms = 0; P->total_ms = 0;
+    for (int i = 0; i + 2 < sc->ev_n + 1 && i + 2 < ITX_MAX_EVENTS; i += 3) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, cu->ev[i], cu->ev[i + 1]); cudaEventElapsedTime(&b, cu->ev[i + 1], cu->ev[i + 2]);
+        P->decode_ms += a; P->overlap_ms += b;
+    }
+    if (sc->ev_n >= 3) { float t = 0; cudaEventElapsedTime(&t, cu->ev[0], cu->ev[sc->ev_n - 1]); P->total_ms = t; }
+    P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
+    P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1];
+    P->d2h_bytes = sizeof hc + sizeof st;
+    if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
+    /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */
+    if (sc->h->n_ref > 0) {
+        int32_t nt = sc->h->n_ref < ITX_MAX_TID_SEEN ? sc->h->n_ref : ITX_MAX_TID_SEEN;
+        uint32_t *seen = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nt);
+        if (cudaMemcpy(seen, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            for (int32_t t = 0; t < nt; t++) if (seen[t]) {
+                char nm[600]; const char *raw = sc->h->names[t];
+                if (sc->h->addChr && strcasecmp(raw, "MT") == 0) snprintf(nm, sizeof nm, "chrM");
+                else if (sc->h->addChr && strncmp(raw, "chr", 3) != 0) snprintf(nm, sizeof nm, "chr%s", raw);
+                else snprintf(nm, sizeof nm, "%s", raw);
+                if (itx_strtab_find(&ix->warned, nm) < 0) {
+                    itx_strtab_add(&ix->warned, nm);
+                    fprintf(stderr, "* Warning: read ends mapped to chromosome %s will be discarded as %s not existed in the chromosome size file\n", nm, nm);
+                }
+            }
+            cudaMemsetAsync(cu->D.tid_unknown_seen, 0, sizeof(uint32_t) * (size_t)nt, cu->stream);
+        }
+        free(seen);
+    }
+    return ITX_OK;
+}
+
+extern "C" int itx_scan_bam_device(itx_index *ix, const itx_bam_header *h, const void *d_bam, uint64_t len,
+                                   const itx_scan_opts *o, uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    int rc = check_opts(o, err); if (rc) return rc;
+    CK(cudaSetDevice(ix->cu->device));
+    memset(&ix->prof, 0, sizeof ix->prof);
+    scan_ctx sc;
+    if ((rc = scan_begin(&sc, ix, h, (const uint8_t *)d_bam, len, o, ix->tune_window < len ? ix->tune_window : len, err))) return rc;
+    if ((rc = scan_window(&sc, sc.k_end, len, err))) return rc;
+    return scan_end(&sc, cnt, err);
+}
+
+/* host stream -> device: the whole uncompressed stream is kept in one device buffer (sized to the
+ * stream), filled window by window; window w is scanned once window w+1 (or the end) has landed. */
+static int ensure_stream_buffer(itx_cuda *cu, uint64_t len, char *err) {
+    if (cu->d_stream && cu->d_stream_cap >= len + ITX_SLACK) return ITX_OK;
+    cudaFree(cu->d_stream); cu->d_stream = NULL;
+    size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+    if (len + ITX_SLACK + (1ull << 30) > fr) { snprintf(err, ITX_ERRLEN, "stream of %llu bytes does not fit the device (%llu free)", (unsigned long long)len, (unsigned long long)fr); return ITX_ENOMEM; }
+    CK(cudaMalloc((void **)&cu->d_stream, len + ITX_SLACK));
+    cu->d_stream_cap = len + ITX_SLACK;
+    return ITX_OK;
+}
+static int ensure_stage(itx_cuda *cu, uint64_t bytes, char *err) {
+    if (cu->h_stage[0] && cu->h_stage_cap >= bytes) return ITX_OK;
+    for (int i = 0; i < 2; i++) { if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]); cu->h_stage[i] = NULL; }
+    for (int i = 0; i < 2; i++) CK(cudaHostAlloc((void **)&cu->h_stage[i], bytes, cudaHostAllocDefault));
+    cu->h_stage_cap = bytes;
+    return ITX_OK;
+}
+
+extern "C" int itx_scan_bam_host(itx_index *ix, const uint8_t *bam, uint64_t len, const itx_scan_opts *o,
+                                 uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    int rc = check_opts(o, err); if (rc) return rc;
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    memset(&ix->prof, 0, sizeof ix->prof);
+    itx_bam_header *h = itx_bam_header_parse(ix, bam, len, o->addChr, err);
+    if (!h) return ITX_EFORMAT;
+    uint64_t W = ix->tune_window < (256ull << 20) ? ix->tune_window : (256ull << 20);
+    W = (W / ix->tune_chunk ? W / ix->tune_chunk : 1) * (uint64_t)ix->tune_chunk;      /* whole chunks per copy */
+    scan_ctx sc;
+    if ((rc = ensure_stream_buffer(cu, len, err))) { itx_bam_header_free(h); return rc; }
+    if ((rc = scan_begin(&sc, ix, h, cu->d_stream, len, o, W, err))) { itx_bam_header_free(h); return rc; }
+    cudaPointerAttributes at; bool pinned = cudaPointerGetAttributes(&at, bam) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && (rc = ensure_stage(cu, W, err))) { itx_bam_header_free(h); return rc; }
+    cudaEvent_t done[2]; cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+    double t0 = now_ms();
+    uint64_t copied = 0; int slot = 0;
+    rc = ITX_OK;
+    while (copied < len && rc == ITX_OK) {
+        uint64_t n = len - copied < W ? len - copied : W;
+        if (pinned) {
+            if (cudaMemcpyAsync(cu->d_stream + copied, bam + copied, n, cudaMemcpyHostToDevice, cu->stream) != cudaSuccess) rc = ITX_ENODEV;
+        } else {
+            cudaEventSynchronize(done[slot]);
+            memcpy(cu->h_stage[slot], bam + copied, n);
+            if (cudaMemcpyAsync(cu->d_stream + copied, cu->h_stage[slot], n, cudaMemcpyHostToDevice, cu->stream) != cudaSuccess) rc = ITX_ENODEV;
+            cudaEventRecord(done[slot], cu->stream); slot ^= 1;
+        }
+        copied += n;
+        /* everything strictly before the window just copied can be scanned now */
+        uint64_t k_hi = copied >= len ? sc.k_end : (copied - n) / cu->C;
+        if (rc == ITX_OK && k_hi > sc.k_next) rc = scan_window(&sc, k_hi, copied, err);
+    }
+    if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, len, err);
+    if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
+    else if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError()));
+    ix->prof.h2d_bytes = len; ix->prof.h2d_ms = now_ms() - t0;
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    itx_bam_header_free(h);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ BGZF file / memory image */
+extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o,
+                                    uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    int rc = check_opts(o, err); if (rc) return rc;
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    memset(&ix->prof, 0, sizeof ix->prof);
+    itx_bgzf_block *blk = NULL; uint64_t nblk = 0, total = 0;
+    if ((rc = itx_bgzf_scan(bgzf, flen, &blk, &nblk, &total, err))) return rc;
+    if (total < 12) { free(blk); snprintf(err, ITX_ERRLEN, "invalid BAM binary header (this is not a BAM file)"); return ITX_EFORMAT; }
+    int nth = ix->tune_threads > 0 ? ix->tune_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (nth < 1) nth = 1;
+    if (nth > 256) nth = 256;
+    /* windows of whole BGZF blocks, about W uncompressed bytes each, inflated straight into pinned memory */
+    uint64_t W = ix->tune_window < (64ull << 20) ? ix->tune_window : (64ull << 20);
+    if ((rc = ensure_stream_buffer(cu, total, err)) || (rc = ensure_stage(cu, W + 65536, err))) { free(blk); return rc; }
+    cudaEvent_t done[2]; cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+    itx_bam_header *h = NULL; scan_ctx sc; bool begun = false;
+    uint8_t *hdr_copy = NULL; uint64_t hdr_have = 0;
+    double t0 = now_ms(), busy_total = 0;
+    uint64_t b = 0, copied = 0; int slot = 0;
+    while (b < nblk && rc == ITX_OK) {
+        uint64_t b1 = b, ubytes = 0;
+        while (b1 < nblk && ubytes + blk[b1].isize <= W) { ubytes += blk[b1].isize; b1++; }
+        if (b1 == b) { b1 = b + 1; ubytes = blk[b].isize; }
+        cudaEventSynchronize(done[slot]);
+        double busy = 0;
+        rc = itx_bgzf_inflate_range(bgzf, blk, b, b1, cu->h_stage[slot], nth, &busy);
+        busy_total += busy;
+        if (rc) { snprintf(err, ITX_ERRLEN, "BGZF inflate failed near compressed offset %llu", (unsigned long long)blk[b].coff); break; }
+        if (!begun) {
+            /* the BAM header may span several windows: gather until it parses */
+            hdr_copy = (uint8_t *)realloc(hdr_copy, hdr_have + ubytes); memcpy(hdr_copy + hdr_have, cu->h_stage[slot], ubytes); hdr_have += ubytes;
+            char e2[ITX_ERRLEN];
+            h = itx_bam_header_parse(ix, hdr_copy, hdr_have, o->addChr, e2);
+            if (h) {
+                if ((rc = scan_begin(&sc, ix, h, cu->d_stream, total, o, W + 65536, err))) break;
+                begun = true; free(hdr_copy); hdr_copy = NULL;
+            } else if (b1 == nblk || memcmp(hdr_copy, "BAM\1", 4) != 0) { memcpy(err, e2, ITX_ERRLEN); rc = ITX_EFORMAT; break; }
+        }
+        if (cudaMemcpyAsync(cu->d_stream + copied, cu->h_stage[slot], ubytes, cudaMemcpyHostToDevice, cu->stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+        cudaEventRecord(done[slot], cu->stream); slot ^= 1;
+        uint64_t before = copied; copied += ubytes; b = b1;
+        if (begun) {
+            uint64_t k_hi = b >= nblk ? sc.k_end : before / cu->C;
+            if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, copied, err);
+        }
+    }
+    if (rc == ITX_OK && !begun) { snprintf(err, ITX_ERRLEN, "truncated BAM header"); rc = ITX_EFORMAT; }
+    if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
+    if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
+    else { cudaStreamSynchronize(cu->stream); if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError())); }
+    ix->prof.h2d_bytes = total; ix->prof.h2d_ms = now_ms() - t0; ix->prof.inflate_ms = busy_total; ix->prof.inflate_threads = nth;
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    free(hdr_copy); free(blk); itx_bam_header_free(h);
+    return rc;
+}
+
+static int scan_one_file(itx_index *ix, const char *path, const itx_scan_opts *o, uint64_t cnt[13], char *err) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { snprintf(err, ITX_ERRLEN, "Error\n[bam file %s: %s]", path, strerror(errno)); return ITX_EIO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); snprintf(err, ITX_ERRLEN, "Error\n[bam file %s is empty or unreadable]", path); return ITX_EIO; }
+    void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { snprintf(err, ITX_ERRLEN, "mmap(%s): %s", path, strerror(errno)); return ITX_EIO; }
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    int rc = itx_scan_bgzf_memory(ix, (const uint8_t *)m, (uint64_t)st.st_size, o, cnt, err);
+    munmap(m, (size_t)st.st_size);
+    return rc;
+}
+
+extern "C" int itx_scan_alignments(itx_index *ix, const char *bam_list, const itx_scan_opts *o, uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    char *list = strdup(bam_list), *save = NULL; int rc = ITX_OK, nfile = 0;
+    itx_profile total; memset(&total, 0, sizeof total);
+    for (char *tok = strtok_r(list, ",", &save); tok && rc == ITX_OK; tok = strtok_r(NULL, ",", &save)) {
+        if (++nfile > 100) break;                       /* the reference's row[100] */
+        rc = scan_one_file(ix, tok, o, cnt, err);
+        total.decode_ms += ix->prof.decode_ms; total.overlap_ms += ix->prof.overlap_ms; total.total_ms += ix->prof.total_ms;
+        total.h2d_ms += ix->prof.h2d_ms; total.inflate_ms += ix->prof.inflate_ms; total.stream_bytes += ix->prof.stream_bytes;
+        total.h2d_bytes += ix->prof.h2d_bytes; total.d2h_bytes += ix->prof.d2h_bytes; total.n_launches += ix->prof.n_launches;
+        total.n_bad_chunks += ix->prof.n_bad_chunks; total.inflate_threads = ix->prof.inflate_threads;
+    }
+    total.n_records = ix->cnt[0] + ix->cnt[1]; total.n_fragments = ix->cnt[6];
+    ix->prof = total;
+    free(list);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ results */
+extern "C" int itx_sync_counts(itx_index *ix, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    const size_t ne = (size_t)ix->n_elem, ng = (size_t)(ix->subs.n + ix->fams.n + ix->clas.n), bl = (size_t)ix->bp_len;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, cu->stream);
+    if (ix->stat_mode && ix->subs.n) k_finalize<<<cu->sm_count * 2, 256, 0, cu->stream>>>(cu->D, cu->d_bp, cu->d_bp_u);
+    cudaEventRecord(b, cu->stream);
+    unsigned long long *u64 = (unsigned long long *)malloc((cu->n_u64 ? cu->n_u64 : 1) * 8);
+    CK(cudaMemcpyAsync(u64, cu->d_u64, cu->n_u64 * 8, cudaMemcpyDeviceToHost, cu->stream));
+    if (!ix->bp) { ix->bp = (uint32_t *)calloc(bl + 1, 4); ix->bp_u = (uint32_t *)calloc(bl + 1, 4); ix->bp_cpg = (double *)calloc(bl + 1, 8); }
+    if (!ix->el_cnt) { ix->el_cnt = (uint32_t *)calloc(ne + 1, 4); ix->el_cnt_u = (uint32_t *)calloc(ne + 1, 4); ix->el_cpg = (uint32_t *)calloc(ne + 1, 4); ix->el_cpg_score = (double *)calloc(ne + 1, 8); }
+    if (bl) { CK(cudaMemcpyAsync(ix->bp, cu->d_bp, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->bp_u, cu->d_bp_u, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); }
+    if (ne) { CK(cudaMemcpyAsync(ix->el_cnt, cu->D.el_cnt, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cnt_u, cu->D.el_cnt_u, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); }
+    uint32_t *gc = (uint32_t *)malloc((ng + 1) * 4); double *gs = (double *)malloc((ng + 1) * 8);
+    if (ng) { CK(cudaMemcpyAsync(gc, cu->D.grp_cpg, ng * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(gs, cu->D.grp_cpg_score, ng * 8, cudaMemcpyDeviceToHost, cu->stream)); }
+    if (bl) CK(cudaMemcpyAsync(ix->bp_cpg, cu->D.bp_cpg, bl * 8, cudaMemcpyDeviceToHost, cu->stream));
+    if (ne) { CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream)); }
+    CK(cudaStreamSynchronize(cu->stream));
+    float fm = 0; cudaEventElapsedTime(&fm, a, b); ix->prof.finalize_ms = fm; cudaEventDestroy(a); cudaEventDestroy(b);
+    for (int k = 0; k < 13; k++) ix->cnt[k] = u64[k];
+    const unsigned long long *g = u64 + 16;
+    const int32_t ns = ix->subs.n, nf = ix->fams.n, nc = ix->clas.n;
+    for (int32_t i = 0; i < ns; i++) { ix->sub[i].read_count = g[2 * i]; ix->sub[i].read_count_unique = g[2 * i + 1]; ix->sub[i].cpg_count = gc[i]; ix->sub[i].cpg_score = gs[i]; }
+    for (int32_t i = 0; i < nf; i++) { ix->fam[i].read_count = g[2 * (ns + i)]; ix->fam[i].read_count_unique = g[2 * (ns + i) + 1]; ix->fam[i].cpg_count = gc[ns + i]; ix->fam[i].cpg_score = gs[ns + i]; }
+    for (int32_t i = 0; i < nc; i++) { ix->cla[i].read_count = g[2 * (ns + nf + i)]; ix->cla[i].read_count_unique = g[2 * (ns + nf + i) + 1]; ix->cla[i].cpg_count = gc[ns + nf + i]; ix->cla[i].cpg_score = gs[ns + nf + i]; }
+    free(u64); free(gc); free(gs);
+    return ITX_OK;
+}
+
+extern "C" uint64_t itx_trace_fetch(itx_index *ix, itx_trace *out, uint64_t cap) {
+    itx_cuda *cu = ix->cu;
+    if (!cu->d_trace) return 0;
+    cudaSetDevice(cu->device);
+    unsigned long long n = 0;
+    cudaMemcpy(&n, cu->d_running, 8, cudaMemcpyDeviceToHost);
+    if (n > cu->trace_cap) n = cu->trace_cap;
+    if (n > cap) n = cap;
+    cudaMemcpy(out, cu->d_trace, n * sizeof(itx_trace), cudaMemcpyDeviceToHost);
+    return n;
+}
+
+extern "C" int itx_query_select(itx_index *ix, const char *chrom, const uint32_t *start, const uint32_t *end, int64_t n,
+                                float min_cov, int32_t *sel_row, int32_t *n_hits, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    int32_t c = itx_strtab_find(&ix->chroms, chrom);
+    if (c < 0 || n <= 0) { for (int64_t i = 0; i < n; i++) { sel_row[i] = -1; if (n_hits) n_hits[i] = 0; } return ITX_OK; }
+    uint32_t *ds, *de; int32_t *dr, *dh;
+    CK(cudaMalloc((void **)&ds, n * 4)); CK(cudaMalloc((void **)&de, n * 4)); CK(cudaMalloc((void **)&dr, n * 4)); CK(cudaMalloc((void **)&dh, n * 4));
+    CK(cudaMemcpy(ds, start, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(de, end, n * 4, cudaMemcpyHostToDevice));
+    k_query<<<(unsigned)((n + 127) / 128), 128, 0, cu->stream>>>(cu->D, c, ds, de, n, min_cov, dr, dh);
+    CK(cudaStreamSynchronize(cu->stream));
+    CK(cudaMemcpy(sel_row, dr, n * 4, cudaMemcpyDeviceToHost));
+    if (n_hits) CK(cudaMemcpy(n_hits, dh, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(de); cudaFree(dr); cudaFree(dh);
+    return ITX_OK;
+}
+
+extern "C" int itx_dev_flush_l2(itx_index *ix) {
+    itx_cuda *cu = ix->cu;
+    cudaSetDevice(cu->device);
+    const unsigned long long n = (256ull << 20) / 4;
+    if (!cu->d_flush && cudaMalloc(&cu->d_flush, n * 4) != cudaSuccess) return ITX_ENOMEM;
+    k_fill_u32<<<cu->sm_count * 8, 256, 0, cu->stream>>>((uint32_t *)cu->d_flush, n, 0x5a5a5a5au);
+    return cudaStreamSynchronize(cu->stream) == cudaSuccess ? ITX_OK : ITX_ENODEV;
+}
+
+/* ------------------------------------------------------------------ CpG bedGraph (cpgBedGraphOverlapRepeat) */
+extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    struct stat st;
+    FILE *f = (stat(bedgraph, &st) == 0 && S_ISDIR(st.st_mode)) ? NULL : fopen(bedgraph, "r");
+    if (!f) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
+    const size_t BATCH = 1u << 22;
+    int32_t *hc = NULL; uint32_t *hs = NULL, *he = NULL; double *hv = NULL;
+    int32_t *dc = NULL; uint32_t *ds = NULL, *de = NULL; double *dv = NULL; unsigned long long *dn = NULL;
+    int rc = ITX_OK;
+    if (cudaHostAlloc((void **)&hc, BATCH * 4, 0) || cudaHostAlloc((void **)&hs, BATCH * 4, 0) || cudaHostAlloc((void **)&he, BATCH * 4, 0) || cudaHostAlloc((void **)&hv, BATCH * 8, 0) ||
+        cudaMalloc((void **)&dc, BATCH * 4) || cudaMalloc((void **)&ds, BATCH * 4) || cudaMalloc((void **)&de, BATCH * 4) || cudaMalloc((void **)&dv, BATCH * 8) || cudaMalloc((void **)&dn, 8)) {
+        snprintf(err, ITX_ERRLEN, "CUDA allocation failed"); rc = ITX_ENOMEM;
+    }
+    unsigned long long zero = 0; uint32_t lines = 0;
+    if (rc == ITX_OK) cudaMemcpy(dn, &zero, 8, cudaMemcpyHostToDevice);
+    char *line = NULL; size_t lc = 0; size_t nb = 0; bool eof = false;
+    static const size_t IOBUF = 1 << 22; char *iobuf = (char *)malloc(IOBUF); setvbuf(f, iobuf, _IOFBF, IOBUF);
+    while (rc == ITX_OK && !eof) {
+        nb = 0;
+        while (nb < BATCH) {
+            if (getline(&line, &lc, f) < 0) { eof = true; break; }
+            char *s = line; while (*s == ' ' || (*s >= 9 && *s <= 13)) s++;
+            if (*s == 0 || *s == '#') continue;
+            char *w[20]; int nw = 0; char *q = s;
+            while (nw < 20) { while (*q == ' ' || (*q >= 9 && *q <= 13)) q++; if (!*q) break; w[nw++] = q; while (*q && !(*q == ' ' || (*q >= 9 && *q <= 13))) q++; if (!*q) break; *q++ = 0; }
+            if (nw < 4) { snprintf(err, ITX_ERRLEN, "file %s doesn't appear to be in bedGraph format. At least 4 fields required, got %d", bedgraph, nw); rc = ITX_EFORMAT; break; }
+            lines++;
+            hc[nb] = itx_strtab_find(&ix->chroms, w[0]);
+            hs[nb] = (uint32_t)strtol(w[1], NULL, 0); he[nb] = (uint32_t)strtol(w[2], NULL, 0); hv[nb] = strtod(w[3], NULL);
+            nb++;
+        }
+        if (rc != ITX_OK || nb == 0) break;
+        cudaMemcpyAsync(dc, hc, nb * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(ds, hs, nb * 4, cudaMemcpyHostToDevice, cu->stream);
+        cudaMemcpyAsync(de, he, nb * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(dv, hv, nb * 8, cudaMemcpyHostToDevice, cu->stream);
+        itx_cpg_args A; A.D = cu->D; A.chrom = dc; A.start = ds; A.end = de; A.score = dv; A.n = (long long)nb; A.filter = filter; A.in_repeat = dn;
+        k_cpg<<<(unsigned)((nb + 255) / 256), 256, 0, cu->stream>>>(A);
+        if (cudaStreamSynchronize(cu->stream) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error in the CpG kernel: %s", cudaGetErrorString(cudaGetLastError())); rc = ITX_ENODEV; }
+    }
+    unsigned long long inrep = 0;
+    if (rc == ITX_OK) cudaMemcpy(&inrep, dn, 8, cudaMemcpyDeviceToHost);
+    free(line); fclose(f); free(iobuf);
+    cudaFreeHost(hc); cudaFreeHost(hs); cudaFreeHost(he); cudaFreeHost(hv); cudaFree(dc); cudaFree(ds); cudaFree(de); cudaFree(dv); cudaFree(dn);
+    if (n_lines) *n_lines = lines;
+    if (n_in_repeat) *n_in_repeat = (uint32_t)inrep;
+    return rc;
+}
+
+/* ------------------------------------------------------------------ NCCL (resolved at run time so the library loads without it) */
+typedef struct { char internal[ITX_NCCL_ID_BYTES]; } nccl_uid;
+typedef int (*fn_uid)(nccl_uid *);
+typedef int (*fn_init)(void **, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_void)(void);
+typedef int (*fn_destroy)(void *);
+typedef const char *(*fn_errstr)(int);
+static void *nccl_open(char *err) {
+    static void *lib = NULL;
+    if (lib) return lib;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", NULL};
+    for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) snprintf(err, ITX_ERRLEN, "NCCL not found: %s", dlerror());
+    return lib;
+}
+extern "C" int itx_comm_unique_id(uint8_t id[ITX_NCCL_ID_BYTES], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    void *lib = nccl_open(err); if (!lib) return ITX_ENOTSUP;
+    fn_uid f = (fn_uid)dlsym(lib, "ncclGetUniqueId");
+    nccl_uid u; int r = f ? f(&u) : -1;
+    if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclGetUniqueId failed (%d)", r); return ITX_ENODEV; }
+    memcpy(id, u.internal, ITX_NCCL_ID_BYTES);
+    return ITX_OK;
+}
+extern "C" int itx_comm_init(itx_index *ix, const uint8_t id[ITX_NCCL_ID_BYTES], int rank, int nranks, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    itx_cuda *cu = ix->cu;
+    void *lib = nccl_open(err); if (!lib) return ITX_ENOTSUP;
+    CK(cudaSetDevice(cu->device));
+    fn_init f = (fn_init)dlsym(lib, "ncclCommInitRank");
+    nccl_uid u; memcpy(u.internal, id, ITX_NCCL_ID_BYTES);
+    int r = f ? f(&cu->nccl_comm, nranks, u, rank) : -1;
+    if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclCommInitRank failed (%d)", r); return ITX_ENODEV; }
+    cu->nccl_lib = lib; cu->rank = rank; cu->nranks = nranks;
+    return ITX_OK;
+}
+/* ONE grouped allreduce(sum) over the packed counter block: the u64 lanes (13 global counters and the
+ * subfamily/family/class pairs) and the u32 lanes (coverage difference arrays and per-locus counts,
+ * wrapping like the reference's unsigned int). */
+extern "C" int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    itx_cuda *cu = ix->cu;
+    if (!cu->nccl_comm) { snprintf(err, ITX_ERRLEN, "itx_comm_init has not been called"); return ITX_EARG; }
+    CK(cudaSetDevice(cu->device));
+    fn_allreduce ar = (fn_allreduce)dlsym(cu->nccl_lib, "ncclAllReduce");
+    fn_void gs = (fn_void)dlsym(cu->nccl_lib, "ncclGroupStart"), ge = (fn_void)dlsym(cu->nccl_lib, "ncclGroupEnd");
+    if (!ar || !gs || !ge) { snprintf(err, ITX_ERRLEN, "NCCL symbols missing"); return ITX_ENOTSUP; }
+    const int ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0;
+    int r = gs();
+    if (!r) r = ar(cu->d_u64, cu->d_u64, cu->n_u64, ncclUint64, ncclSum, cu->nccl_comm, cu->stream);
+    if (!r && cu->n_u32) r = ar(cu->d_u32, cu->d_u32, cu->n_u32, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
+    int r2 = ge(); if (!r) r = r2;
+    if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclAllReduce failed (%d)", r); return ITX_ENODEV; }
+    CK(cudaStreamSynchronize(cu->stream));
+    return ITX_OK;
+}
+extern "C" void itx_comm_destroy(itx_index *ix) {
+    itx_cuda *cu = ix ? ix->cu : NULL;
+    if (!cu || !cu->nccl_comm) return;
+    fn_destroy f = (fn_destroy)dlsym(cu->nccl_lib, "ncclCommDestroy");
+    if (f) f(cu->nccl_comm);
+    cu->nccl_comm = NULL;
+}

@@ -1,0 +1,289 @@
+/* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
+ *
+ *   k_decode    K1  record-boundary discovery + bam1_core_t unpack + fragment logic, one thread per
+ *                   stream chunk: the chunk's first record start is GUESSED structurally, the chunk is
+ *                   walked along the block_size chain with 16-byte vector loads of the core, and every
+ *                   record becomes one 16-byte tuple.         replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_verify / k_fixup  the guess of chunk i must equal the chain exit of chunk i-1; otherwise the chunk
+ *                   is re-walked from the true entry.  The tuples are therefore exactly the sequential
+ *                   chain, whatever the guesses were.
+ *   k_overlap   K2+K3  one lane per tuple: sorted-interval lower_bound + bounded backward walk in place
+ *                   of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
+ *                   counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
+ *                   global atomics, and two u32 atomics per coverage difference array.
+ *   k_finalize  prefix sums of the coverage difference arrays (one warp per subfamily).
+ *   k_cpg       K4  CpG bedGraph rows against the same table (cpgBedGraphOverlapRepeat).
+ *   k_query     overlap + selection for explicit queries (property tests).
+ */
+#ifndef ITX_KERNELS_CUH
+#define ITX_KERNELS_CUH
+#include "itx_logic.cuh"
+
+struct itx_decode_args {
+    const uint8_t *b; unsigned long long len, avail, k0;
+    uint32_t nchunks, C, S;
+    const itx_tidinfo *tid; int32_t n_ref;
+    itx_dev_opts o;
+    itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
+    unsigned long long *carry; uint32_t *winbad; uint32_t *status;
+};
+
+__device__ __forceinline__ void itx_walk_chunk(const itx_decode_args &A, uint32_t i, unsigned long long p) {
+    const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+    unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+    itx_tuple *out = A.tuples + (size_t)i * A.S;
+    uint32_t n = 0;
+    if (p < ITX_OFF_END) {
+        while (p < hi) {
+            if (p + 36 > A.len) { p = ITX_OFF_END; break; }
+            uint32_t x[9]; itx_load_core(A.b, p, x);
+            if ((int32_t)x[0] < 32 || p + 4 + (unsigned long long)x[0] > A.len) { p = ITX_OFF_END; break; }
+            if (p + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);   /* record longer than the staged window */
+            if (n < A.S) out[n] = itx_decode_record(A.b, p, x, (uint32_t)(p - lo), A.tid, A.n_ref, A.o);
+            n++;
+            p += 4 + (unsigned long long)x[0];
+        }
+    }
+    A.exit_[i] = p; A.nrec[i] = n < A.S ? n : A.S;
+}
+
+__global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.nchunks) return;
+    unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C, hi = lo + A.C;
+    if (hi > A.len) hi = A.len;
+    unsigned long long p;
+    if (i == 0) { p = *A.carry; *A.winbad = 0; }
+    else p = itx_speculate_entry(A.b, lo, hi, A.len, A.n_ref);
+    A.entry[i] = p;
+    itx_walk_chunk(A, i, p);
+}
+
+__global__ void k_verify(const itx_decode_args A) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= A.nchunks) return;
+    if (A.entry[i] != A.exit_[i - 1]) atomicAdd(A.winbad, 1u);
+}
+
+/* one warp; a no-op when every guess was right */
+__global__ void k_fixup(const itx_decode_args A) {
+    const uint32_t lane = threadIdx.x, n = A.nchunks;
+    if (*A.winbad != 0) {
+        uint32_t i = 1;
+        while (i < n) {
+            uint32_t idx = i + lane;
+            bool bad = idx < n && A.entry[idx] != A.exit_[idx - 1];
+            uint32_t m = __ballot_sync(0xffffffffu, bad);
+            if (!m) { i += 32; continue; }
+            uint32_t j = i + (uint32_t)__ffs((int)m) - 1;
+            if (lane == 0) {
+                unsigned long long e = A.exit_[j - 1];
+                A.entry[j] = e;
+                itx_walk_chunk(A, j, e);
+                atomicAdd(&A.status[1], 1u);
+                __threadfence();
+            }
+            __syncwarp();
+            i = j + 1;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *A.carry = A.exit_[n - 1];
+}
+
+/* ------------------------------------------------------------------ overlap + accumulate */
+struct itx_overlap_args {
+    itx_dev_index D;
+    const uint8_t *b; unsigned long long k0; uint32_t nchunks, C, S;
+    const itx_tuple *tuples; const uint32_t *nrec;
+    itx_dev_opts o;
+    itx_trace *trace; unsigned long long trace_cap; const unsigned long long *rec_base;   /* trace != 0: per-record trace */
+    long long *sel_out;                                                                  /* != 0: selected element per tuple slot */
+};
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
+    extern __shared__ uint32_t sh_hist[];
+    __shared__ unsigned long long sh_cnt[13];
+    const itx_dev_index &D = A.D;
+    const uint32_t nh = SMEM_HIST ? 2u * (uint32_t)(D.n_sub + D.n_fam + D.n_cla) : 0u;
+    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
+    if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
+    const uint32_t gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5), nw = gridDim.x * warps_per_block;
+    uint32_t c[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) c[k] = 0;
+    const bool stat = A.o.filter == 0 && D.stat_mode;
+    for (uint32_t i = gw; i < A.nchunks; i += nw) {
+        const uint32_t n = A.nrec[i];
+        const itx_tuple *tp = A.tuples + (size_t)i * A.S;
+        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+        for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+            const uint32_t j = j0 + lane; const bool valid = j < n;
+            itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
+            if (valid) { const uint4 v = *reinterpret_cast<const uint4 *>(tp + j); T.start = v.x; T.end = v.y; T.info = v.z; T.rec_off = v.w; }
+            const uint32_t info = T.info;
+            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+            c[0] += __popc(__ballot_sync(0xffffffffu, valid && !slot2));
+            c[1] += __popc(__ballot_sync(0xffffffffu, valid && slot2));
+            c[2] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_MAPPED) && !slot2));
+            c[3] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_MAPPED) && slot2));
+            c[4] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_USED) && !slot2));
+            c[5] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_USED) && slot2));
+            c[6] += __popc(__ballot_sync(0xffffffffu, frag));
+            const uint32_t mu = __popc(__ballot_sync(0xffffffffu, frag && uniq));
+            c[7] += mu; c[11] += mu;
+            if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
+            long long sel = -1; bool diffsub = false;
+            const uint32_t chrom = info & ITX_CHROM_MASK;
+            if (frag && chrom != ITX_CHROM_NONE) {
+                int32_t nhit; float tcov;
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov);
+                if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
+                if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
+                    const unsigned long long p = lo + T.rec_off;
+                    uint32_t x[9]; itx_load_core(A.b, p, x);
+                    uint32_t bad = 0;
+                    if (itx_mapped_to_diff_subfam(D, A.b, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) { diffsub = true; }
+                    if (bad) atomicAdd(&D.status[2], bad);
+                }
+            }
+            c[12] += __popc(__ballot_sync(0xffffffffu, diffsub));
+            const bool counted = sel >= 0 && !diffsub;
+            c[9] += __popc(__ballot_sync(0xffffffffu, counted));
+            c[10] += __popc(__ballot_sync(0xffffffffu, counted && uniq));
+            if (counted) {
+                if (stat) {
+                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+                    const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+                    if (SMEM_HIST) {
+                        atomicAdd(&sh_hist[hs], 1u); atomicAdd(&sh_hist[hf], 1u); atomicAdd(&sh_hist[hc], 1u);
+                        if (uniq) { atomicAdd(&sh_hist[hs + 1], 1u); atomicAdd(&sh_hist[hf + 1], 1u); atomicAdd(&sh_hist[hc + 1], 1u); }
+                    } else {
+                        atomicAdd(&D.grp[hs], 1ull); atomicAdd(&D.grp[hf], 1ull); atomicAdd(&D.grp[hc], 1ull);
+                        if (uniq) { atomicAdd(&D.grp[hs + 1], 1ull); atomicAdd(&D.grp[hf + 1], 1ull); atomicAdd(&D.grp[hc + 1], 1ull); }
+                    }
+                    const uint32_t L = D.sub_len[m.sub];
+                    uint32_t ja, jb;
+                    if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
+                        const unsigned long long off = D.sub_bp_off[m.sub];
+                        atomicAdd(&D.bp_diff[off + ja], 1u); atomicAdd(&D.bp_diff[off + jb], 0xffffffffu);
+                        if (uniq) { atomicAdd(&D.bp_diff_u[off + ja], 1u); atomicAdd(&D.bp_diff_u[off + jb], 0xffffffffu); }
+                    }
+                } else if (A.o.filter) {
+                    atomicAdd(&D.el_cnt[sel], 1u);
+                    if (uniq) atomicAdd(&D.el_cnt_u[sel], 1u);
+                }
+            }
+            if (A.sel_out && valid) A.sel_out[(size_t)i * A.S + j] = counted ? sel : -1;
+            if (A.trace && valid) {
+                const unsigned long long r = A.rec_base[i] + j;
+                if (r < A.trace_cap) {
+                    itx_trace t;
+                    t.start = frag ? T.start : 0; t.end = frag ? T.end : 0;
+                    t.tid = (int32_t)itx_ld_u32(A.b, lo + T.rec_off + 4);
+                    t.sel_row = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+                    t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
+                              ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
+                    A.trace[r] = t;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) if (c[k]) atomicAdd(&sh_cnt[k], (unsigned long long)c[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) atomicAdd(&D.cnt[threadIdx.x], sh_cnt[threadIdx.x]);
+    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) atomicAdd(&D.grp[t], (unsigned long long)v); }
+}
+
+/* prefix sums of the coverage difference arrays: one warp per subfamily */
+__global__ void k_finalize(const itx_dev_index D, uint32_t *bp, uint32_t *bp_u) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t s = w; s < (uint32_t)D.n_sub; s += nw) {
+        const uint32_t L = D.sub_len[s];
+        if (!L) continue;
+        const unsigned long long off = D.sub_bp_off[s];
+        uint32_t carry = 0, carry_u = 0;
+        for (uint32_t j0 = 0; j0 <= L; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            uint32_t v = j <= L ? D.bp_diff[off + j] : 0u, u = j <= L ? D.bp_diff_u[off + j] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tv = __shfl_up_sync(0xffffffffu, v, d), tu = __shfl_up_sync(0xffffffffu, u, d);
+                if (lane >= (uint32_t)d) { v += tv; u += tu; }
+            }
+            v += carry; u += carry_u;
+            if (j <= L) { bp[off + j] = v; bp_u[off + j] = u; }
+            carry = __shfl_sync(0xffffffffu, v, 31); carry_u = __shfl_sync(0xffffffffu, u, 31);
+        }
+    }
+}
+
+/* exclusive scan of nrec over one window (trace only): one block */
+__global__ void k_rec_base(const uint32_t *nrec, uint32_t n, unsigned long long *rec_base, unsigned long long *running) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t a = t * per, b = a + per < n ? a + per : n;
+    unsigned long long s = 0;
+    for (uint32_t i = a; i < b; i++) s += nrec[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) { unsigned long long acc = *running; for (uint32_t k = 0; k < blockDim.x; k++) { const unsigned long long v = part[k]; part[k] = acc; acc += v; } *running = acc; }
+    __syncthreads();
+    s = part[t];
+    for (uint32_t i = a; i < b; i++) { rec_base[i] = s; s += nrec[i]; }
+}
+
+__global__ void k_query(const itx_dev_index D, int32_t chrom, const uint32_t *start, const uint32_t *end, long long n, float min_cov,
+                        int32_t *sel_row, int32_t *n_hits) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t nh; float tcov;
+    long long sel = itx_find_select(D, chrom, start[i], end[i], &nh, &tcov);
+    if (sel >= 0 && tcov < min_cov) sel = -1;
+    sel_row[i] = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+    if (n_hits) n_hits[i] = nh;
+}
+
+/* ------------------------------------------------------------------ CpG rows */
+struct itx_cpg_args {
+    itx_dev_index D;
+    const int32_t *chrom; const uint32_t *start, *end; const double *score; long long n; int32_t filter;
+    unsigned long long *in_repeat;
+};
+__global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
+    const itx_dev_index &D = A.D;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long sel = -1; double sc = 0.0; uint32_t st = 0;
+    if (i < A.n) {
+        const int32_t c = A.chrom[i];
+        if (c >= 0) { st = A.start[i]; sel = itx_find_head(D, c, st, A.end[i]); sc = A.score[i]; }
+    }
+    const uint32_t m = __popc(__ballot_sync(0xffffffffu, sel >= 0));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(A.in_repeat, (unsigned long long)m);
+    if (sel < 0) return;
+    if (A.filter) { atomicAdd(&D.el_cpg[sel], 1u); atomicAdd(&D.el_cpg_score[sel], sc); return; }
+    if (!D.stat_mode) return;
+    const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+    const uint32_t gs = mt.sub, gf = (uint32_t)(D.n_sub + m2.fam), gc = (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+    atomicAdd(&D.grp_cpg[gs], 1u); atomicAdd(&D.grp_cpg_score[gs], sc);
+    atomicAdd(&D.grp_cpg[gf], 1u); atomicAdd(&D.grp_cpg_score[gf], sc);
+    atomicAdd(&D.grp_cpg[gc], 1u); atomicAdd(&D.grp_cpg_score[gc], sc);
+    const uint32_t L = D.sub_len[mt.sub];
+    uint32_t ja, jb;
+    if (L && itx_cov_range(st, 2u, e.start, e.end, mt.cons_start, mt.cons_end, L, &ja, &jb)) {
+        const unsigned long long off = D.sub_bp_off[mt.sub];
+        for (uint32_t j = ja; j < jb; j++) atomicAdd(&D.bp_cpg[off + j], sc);
+    }
+}
+
+__global__ void k_fill_u32(uint32_t *p, unsigned long long n, uint32_t v) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) p[i] = v;
+}
+#endif

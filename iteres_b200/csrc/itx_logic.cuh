@@ -1,0 +1,422 @@
+/* itx_logic.cuh -- the per-record / per-query device functions of the iteres hot path.
+ *
+ * Everything here is `ITX_HD` (__host__ __device__) so that the very same code can also be compiled
+ * by g++ into the test-only emulator under tests/emu/ (unit tests of the device logic on a box
+ * without a GPU).  The product library (itx_gpu.cu) only ever calls these from kernels.
+ *
+ * What is restated (reference file:line, lidaof/iteres v0.3.3-r123):
+ *   bam_read1 / core unpack   cussamtools/bam.c:179-210, bam.h:169-178
+ *   bam_calend                cussamtools/bam.c:17-27            (M, D, N only)
+ *   bam_aux_get / aux2i       cussamtools/bam_aux.c:28-48, 159-170, bam.h:754-760
+ *   per-read fragment logic   generic.c:748-905
+ *   binKeeperFind             cuskent/binRange.c:196-227         (order: level 5->0, bin high->low, row old->new)
+ *   getCov + selection        generic.c:296-301, 950-970         ("last ascent")
+ *   mapped2diffSubfam         generic.c:303-341
+ *   accumulation              generic.c:983-1024
+ */
+#ifndef ITX_LOGIC_CUH
+#define ITX_LOGIC_CUH
+#include "itx_internal.h"
+
+#if defined(__CUDACC__)
+#define ITX_HD __host__ __device__ __forceinline__
+#define ITX_HDN __host__ __device__ __noinline__
+#else
+#define ITX_HD static inline
+#define ITX_HDN static
+#endif
+
+/* ------------------------------------------------------------------ unaligned little-endian loads */
+ITX_HD uint32_t itx_ldg32(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+ITX_HD uint8_t itx_ldg8(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+ITX_HD uint32_t itx_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+/* u32 at an arbitrary byte offset; may touch up to 3 bytes past off+4 (buffers carry 64 B of slack) */
+ITX_HD uint32_t itx_ld_u32(const uint8_t *b, uint64_t off) {
+    const uint32_t *w = (const uint32_t *)(b + (off & ~3ull));
+    uint32_t sh = (uint32_t)(off & 3) * 8;
+    uint32_t lo = itx_ldg32(w);
+    if (sh == 0) return lo;
+    return itx_funnel_r(lo, itx_ldg32(w + 1), sh);
+}
+
+/* block_size + the 32-byte core of the record at byte offset p, as nine u32:
+ * x0 block_size, x1 refID, x2 pos, x3 bin<<16|mapq<<8|l_qname, x4 flag<<16|n_cigar, x5 l_seq, x6 mtid, x7 mpos, x8 isize.
+ * Four 16-byte loads of the enclosing aligned window, then a byte realignment in registers. */
+ITX_HD void itx_load_core(const uint8_t *b, uint64_t p, uint32_t x[9]) {
+    uint32_t w[16];
+    uint32_t o = (uint32_t)(p & 15);
+#if defined(__CUDA_ARCH__)
+    const uint4 *v = (const uint4 *)(b + (p & ~15ull));
+    uint4 a0 = __ldg(v), a1 = __ldg(v + 1), a2 = __ldg(v + 2), a3 = make_uint4(0, 0, 0, 0);
+    if (o > 12) a3 = __ldg(v + 3);
+    w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+    w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
+#else
+    const uint32_t *v = (const uint32_t *)(b + (p & ~15ull));
+    for (int i = 0; i < 16; i++) w[i] = (i < 12 || o > 12) ? v[i] : 0;
+#endif
+    uint32_t q = o >> 2, sh = (o & 3) * 8;
+    uint32_t t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) t[i] = itx_funnel_r(w[i], w[i + 1], sh);
+#pragma unroll
+    for (int j = 0; j < 9; j++) x[j] = q == 0 ? t[j] : (q == 1 ? t[j + 1] : (q == 2 ? t[j + 2] : t[j + 3]));
+}
+
+/* ------------------------------------------------------------------ record chain */
+/* Cheap structural test used ONLY to guess where a chunk's first record starts; the guess is checked
+ * against the real chain afterwards (k_verify / k_fixup), so a wrong answer costs time, not exactness. */
+ITX_HD bool itx_plausible(const uint8_t *b, uint64_t p, uint64_t len, int32_t n_ref, uint64_t *next) {
+    if (p + 36 > len) return false;
+    uint32_t bs = itx_ld_u32(b, p);
+    if (bs < 33u || bs > (1u << 26)) return false;
+    if (p + 4 + (uint64_t)bs > len) return false;
+    int32_t tid = (int32_t)itx_ld_u32(b, p + 4);
+    if (tid < -1 || tid >= n_ref) return false;
+    int32_t pos = (int32_t)itx_ld_u32(b, p + 8);
+    if (pos < -1) return false;
+    uint32_t lq = itx_ld_u32(b, p + 12) & 0xff;
+    if (lq == 0) return false;
+    uint32_t nc = itx_ld_u32(b, p + 16) & 0xffff;
+    int32_t ls = (int32_t)itx_ld_u32(b, p + 20);
+    if (ls < 0) return false;
+    int32_t mtid = (int32_t)itx_ld_u32(b, p + 24);
+    if (mtid < -1 || mtid >= n_ref) return false;
+    int32_t mpos = (int32_t)itx_ld_u32(b, p + 28);
+    if (mpos < -1) return false;
+    uint64_t need = 32ull + lq + 4ull * nc + (uint64_t)((ls + 1) / 2) + (uint64_t)ls;
+    if (need > bs) return false;
+    if (itx_ldg8(b + p + 36 + lq - 1) != 0) return false;          /* qname is NUL terminated */
+    *next = p + 4 + bs;
+    return true;
+}
+/* first offset in [lo, hi) that looks like a record start followed by another one (or by the end) */
+ITX_HD uint64_t itx_speculate_entry(const uint8_t *b, uint64_t lo, uint64_t hi, uint64_t len, int32_t n_ref) {
+    for (uint64_t p = lo; p < hi; p++) {
+        uint64_t nx, nx2;
+        if (!itx_plausible(b, p, len, n_ref, &nx)) continue;
+        if (nx == len || itx_plausible(b, nx, len, n_ref, &nx2)) return p;
+    }
+    return ITX_OFF_NONE;
+}
+
+/* ------------------------------------------------------------------ aux fields */
+/* bam_aux_get: returns the offset of the type byte of `tag`, or 0.  Faithful to the reference's skip
+ * rule, including its quirk that the type is upper-cased before its size is looked up (so 'f' and
+ * 'd' values are skipped as size 0).  Reads are bounded by aend. */
+ITX_HD uint64_t itx_aux_find(const uint8_t *b, uint64_t s, uint64_t aend, uint8_t t0, uint8_t t1) {
+    while (s + 1 < aend) {
+        uint8_t c0 = itx_ldg8(b + s), c1 = itx_ldg8(b + s + 1);
+        s += 2;
+        if (c0 == t0 && c1 == t1) return s;
+        if (s >= aend) break;
+        uint8_t ty = itx_ldg8(b + s);
+        if (ty >= 'a' && ty <= 'z') ty = (uint8_t)(ty - 32);
+        s += 1;
+        if (ty == 'Z' || ty == 'H') { while (s < aend && itx_ldg8(b + s) != 0) s++; s++; }
+        else if (ty == 'B') {
+            if (s + 5 > aend) break;
+            uint8_t sub = itx_ldg8(b + s);
+            uint32_t sz = (sub == 'C' || sub == 'c' || sub == 'A') ? 1u : (sub == 'S' || sub == 's') ? 2u : (sub == 'I' || sub == 'i' || sub == 'f') ? 4u : 0u;
+            uint32_t n = (uint32_t)itx_ldg8(b + s + 1) | (uint32_t)itx_ldg8(b + s + 2) << 8 | (uint32_t)itx_ldg8(b + s + 3) << 16 | (uint32_t)itx_ldg8(b + s + 4) << 24;
+            s += 5 + (uint64_t)sz * (uint64_t)(int64_t)(int32_t)n;
+        } else s += (ty == 'C' || ty == 'A') ? 1u : (ty == 'S') ? 2u : (ty == 'I') ? 4u : 0u;
+    }
+    return 0;
+}
+/* bam_aux2i on the value whose type byte sits at offset s (0 -> 0) */
+ITX_HD int32_t itx_aux2i(const uint8_t *b, uint64_t s, uint64_t aend) {
+    if (!s || s >= aend) return 0;
+    uint8_t ty = itx_ldg8(b + s); s++;
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) if (s + (uint64_t)i < aend) v |= (uint32_t)itx_ldg8(b + s + i) << (8 * i);
+    if (ty == 'c') return (int32_t)(int8_t)(v & 0xff);
+    if (ty == 'C') return (int32_t)(v & 0xff);
+    if (ty == 's') return (int32_t)(int16_t)(v & 0xffff);
+    if (ty == 'S') return (int32_t)(v & 0xffff);
+    if (ty == 'i' || ty == 'I') return (int32_t)v;
+    return 0;
+}
+/* offsets of the aux area of the record at p (x = its core) */
+ITX_HD void itx_aux_range(uint64_t p, const uint32_t x[9], uint64_t *a0, uint64_t *aend) {
+    uint32_t lq = x[3] & 0xff, nc = x[4] & 0xffff; int32_t ls = (int32_t)x[5];
+    *aend = p + 4 + (uint64_t)x[0];
+    int64_t a = (int64_t)p + 36 + lq + 4ll * nc + (int64_t)ls + (int64_t)((ls + 1) / 2);
+    *a0 = (a < (int64_t)p + 36 || (uint64_t)a > *aend) ? *aend : (uint64_t)a;
+}
+
+/* ------------------------------------------------------------------ one BAM record -> tuple */
+ITX_HD uint32_t itx_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+ITX_HD itx_tuple itx_decode_record(const uint8_t *b, uint64_t p, const uint32_t x[9], uint32_t rec_off,
+                                   const itx_tidinfo *tidtab, int32_t n_ref, const itx_dev_opts &o) {
+    itx_tuple T; T.start = 0; T.end = 0; T.info = ITX_CHROM_NONE; T.rec_off = rec_off;
+    int32_t tid = (int32_t)x[1], pos = (int32_t)x[2];
+    uint32_t mapq = (x[3] >> 8) & 0xff, lq = x[3] & 0xff, flag = x[4] >> 16, nc = x[4] & 0xffff;
+    int32_t lseq = (int32_t)x[5], mpos = (int32_t)x[7], isize = (int32_t)x[8];
+    bool paired = flag & 1, read1 = flag & 64;
+    if (paired && !read1 && !o.treat) T.info |= ITX_F_SLOT2;
+    if (flag & 4) return T;                                           /* unmapped */
+    T.info |= ITX_F_MAPPED;
+    if (tid < 0 || tid >= n_ref) return T;
+    itx_tidinfo ti = tidtab[tid];
+    if (ti.flags & ITX_TID_GLSKIP) return T;
+    if (ti.flags & ITX_TID_UNKNOWN) { T.info |= ITX_F_UNKNOWN; T.start = (uint32_t)tid; return T; }
+    T.info |= ITX_F_USED;
+    uint32_t cend = ti.cend, start = 0, end = 0; bool minus = false, se_like = false;
+    bool uniq = mapq >= o.mapQ;
+    if (o.treat) se_like = true;
+    else if (paired) {
+        if (!(flag & 8)) {
+            if (!read1) return T;
+            uint32_t ai = isize < 0 ? (uint32_t)0 - (uint32_t)isize : (uint32_t)isize;
+            if (ai > o.iSize || isize == 0) return T;
+            if (isize > 0) { start = (uint32_t)pos; end = itx_umin(cend, start + (uint32_t)isize); }
+            else { start = (uint32_t)mpos; minus = true; end = itx_umin(cend, start - (uint32_t)isize); }
+        } else { if (o.discardWrongEnd) return T; se_like = true; }
+    } else se_like = true;
+    if (se_like) {
+        start = (uint32_t)pos;
+        minus = (flag & 16) != 0;
+        uint32_t tmpend;
+        if (nc) {
+            tmpend = (uint32_t)pos;
+            /* bam_calend is only observable when the end survives the extension step */
+            if (o.extension == 0 || minus) {
+                uint64_t cp = p + 36 + lq;
+                for (uint32_t k = 0; k < nc; k++) {
+                    uint32_t cg = itx_ld_u32(b, cp + 4ull * k), op = cg & 0xf;
+                    if (op == 0 || op == 2 || op == 3) tmpend += cg >> 4;
+                }
+            }
+        } else tmpend = (uint32_t)(pos + lseq);
+        end = itx_umin(cend, tmpend);
+        if (o.extension) {
+            if (!minus) end = itx_umin(start + o.extension, cend);
+            else start = (end < o.extension) ? 0u : end - o.extension;
+        }
+    }
+    T.start = start; T.end = end;
+    T.info = (T.info & ~ITX_CHROM_MASK) | ITX_F_FRAG | (uniq ? ITX_F_UNIQ : 0u) | (minus ? ITX_F_MINUS : 0u) |
+             (ti.chrom < 0 ? ITX_CHROM_NONE : (uint32_t)ti.chrom);
+    if (o.diffSubfam && ti.chrom >= 0) {
+        uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+        if (itx_aux_find(b, a0, aend, 'X', 'A')) T.info |= ITX_F_HASXA;
+    }
+    return T;
+}
+
+/* ------------------------------------------------------------------ interval lookup */
+/* list-order key of binKeeperFind's result: level 5->0, bin high->low, rmsk row old->new */
+ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
+    int32_t a = s >> 17, z = (e - 1) >> 17; uint32_t l = 0;
+    while (a != z && l < 5) { a >>= 3; z >>= 3; l++; }
+    return ((uint64_t)(5u - l) << 48) | ((uint64_t)(0xffffu - (uint32_t)a) << 32) | (uint64_t)row;
+}
+/* index range [*first, *upper) of the chromosome's sorted table that can overlap the clamped query [fs, fe):
+ * upper = first element with start >= fe; the caller walks down while pmax > fs. */
+ITX_HD long long itx_upper(const itx_dev_index &D, long long lo, long long hi, int32_t fe) {
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (D.iv[mid].start < fe) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
+    int32_t s = (int32_t)start > es ? (int32_t)start : es, e = (int32_t)end < ee ? (int32_t)end : ee;
+    int32_t r = e - s; if (r < 0) r = 0;
+    float den = (float)(end - start);
+    return den == 0.0f ? 0.0f : (float)r / den;
+}
+/* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.
+ * Returns the sorted-table index of the selected element or -1; *n_hits = length of the hit list,
+ * *tcov = coverage of the selected element.  Exact for any number of hits: the hit list is never
+ * materialised; for n > 1 the candidates are re-walked once per list position. */
+ITX_HDN long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov) {
+    *n_hits = 0; *tcov = 0.0f;
+    int32_t fs = (int32_t)start, fe = (int32_t)end, cs = D.chrom_size[c];
+    if (fs < 0) fs = 0;
+    if (fe > cs) fe = cs;
+    if (fs >= fe) return -1;
+    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
+    long long up = itx_upper(D, lo, hi, fe);
+    int32_t n = 0; long long only = -1;
+    for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
+        itx_iv e = D.iv[i];
+        if (e.end > fs && e.start < e.end) { n++; only = i; }
+    }
+    *n_hits = n;
+    if (n == 0) return -1;
+    if (n == 1) { itx_iv e = D.iv[only]; *tcov = itx_cov(start, end, e.start, e.end); return only; }
+    uint64_t prev_key = 0; bool have_prev = false; float prev_cov = 0.0f, best_cov = 0.0f; long long sel = -1;
+    for (int32_t k = 0; k < n; k++) {
+        uint64_t bk = ~0ull; long long bi = -1;
+        for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
+            itx_iv e = D.iv[i];
+            if (e.end > fs && e.start < e.end) {
+                uint64_t key = itx_order_key(e.start, e.end, D.meta[i].row);
+                if ((!have_prev || key > prev_key) && key < bk) { bk = key; bi = i; }
+            }
+        }
+        if (bi < 0) break;
+        itx_iv e = D.iv[bi];
+        float cov = itx_cov(start, end, e.start, e.end);
+        if (cov > prev_cov) { sel = bi; best_cov = cov; }
+        prev_cov = cov; prev_key = bk; have_prev = true;
+    }
+    *tcov = best_cov;
+    return sel;
+}
+/* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
+ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end) {
+    int32_t fs = (int32_t)start, fe = (int32_t)end, cs = D.chrom_size[c];
+    if (fs < 0) fs = 0;
+    if (fe > cs) fe = cs;
+    if (fs >= fe) return -1;
+    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
+    long long up = itx_upper(D, lo, hi, fe);
+    uint64_t bk = ~0ull; long long bi = -1;
+    for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
+        itx_iv e = D.iv[i];
+        if (e.end > fs && e.start < e.end) {
+            uint64_t key = itx_order_key(e.start, e.end, D.meta[i].row);
+            if (key < bk) { bk = key; bi = i; }
+        }
+    }
+    return bi;
+}
+/* does [s, e) on chromosome c touch any element whose case-folded subfamily differs from `fold`? */
+ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, int32_t e, int32_t fold) {
+    int32_t cs = D.chrom_size[c];
+    if (s < 0) s = 0;
+    if (e > cs) e = cs;
+    if (s >= e) return false;
+    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
+    long long up = itx_upper(D, lo, hi, e);
+    for (long long i = up - 1; i >= lo && D.pmax[i] > s; i--) {
+        itx_iv v = D.iv[i];
+        if (v.end > s && v.start < v.end && D.sub_fold[D.meta[i].sub] != fold) return true;
+    }
+    return false;
+}
+
+/* ------------------------------------------------------------------ XA:Z alternates (mapped2diffSubfam) */
+/* strtol(s, 0, 0) over the bytes [s, e): white space, sign, 0x / 0 prefixes, saturating; returned as (int) */
+ITX_HD int32_t itx_strtol_int(const uint8_t *b, uint64_t s, uint64_t e) {
+    while (s < e) { uint8_t c = itx_ldg8(b + s); if (c == ' ' || (c >= 9 && c <= 13)) s++; else break; }
+    bool neg = false;
+    if (s < e) { uint8_t c = itx_ldg8(b + s); if (c == '-') { neg = true; s++; } else if (c == '+') s++; }
+    uint32_t base = 10;
+    if (s < e && itx_ldg8(b + s) == '0') {
+        uint8_t c1 = s + 1 < e ? itx_ldg8(b + s + 1) : 0, c2 = s + 2 < e ? itx_ldg8(b + s + 2) : 0;
+        bool hex2 = (c2 >= '0' && c2 <= '9') || ((c2 | 32) >= 'a' && (c2 | 32) <= 'f');
+        if ((c1 == 'x' || c1 == 'X') && hex2) { base = 16; s += 2; } else base = 8;
+    }
+    uint64_t acc = 0; bool sat = false;
+    while (s < e) {
+        uint8_t c = itx_ldg8(b + s); uint32_t d;
+        if (c >= '0' && c <= '9') d = c - '0'; else if ((c | 32) >= 'a' && (c | 32) <= 'z') d = (uint32_t)((c | 32) - 'a') + 10; else break;
+        if (d >= base) break;
+        if (acc > (0xffffffffffffffffull - d) / base) sat = true; else acc = acc * base + d;
+        s++;
+    }
+    /* LONG_MIN / LONG_MAX on overflow, like glibc; the caller's (int) cast keeps the low 32 bits */
+    uint64_t v;
+    if (neg) v = (sat || acc > 0x8000000000000000ull) ? 0x8000000000000000ull : 0ull - acc;
+    else v = (sat || acc > 0x7fffffffffffffffull) ? 0x7fffffffffffffffull : acc;
+    return (int32_t)(uint32_t)v;
+}
+ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const uint8_t *b, uint64_t s, uint64_t e) {
+    uint32_t h = 2166136261u;
+    for (uint64_t i = s; i < e; i++) { h ^= itx_ldg8(b + i); h *= 16777619u; }
+    uint32_t m = D.cname_nslot - 1, i = h & m;
+    for (;;) {
+        uint32_t v = D.cname_slot[i];
+        if (!v) return -1;
+        const char *nm = D.cname_pool + D.cname_off[v - 1];
+        uint64_t k = 0; bool same = true;
+        for (; s + k < e; k++) if ((uint8_t)nm[k] != itx_ldg8(b + s + k) || nm[k] == 0) { same = false; break; }
+        if (same && nm[k] == 0) return (int32_t)(v - 1);
+        i = (i + 1) & m;
+    }
+}
+/* record at p (core x) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start.
+ * *malformed counts alternates without 4 comma separated fields (the reference asserts there). */
+ITX_HDN bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const uint8_t *b, uint64_t p, const uint32_t x[9],
+                                       int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
+    uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+    uint64_t xa = itx_aux_find(b, a0, aend, 'X', 'A');
+    if (!xa || xa >= aend) return false;
+    uint8_t ty = itx_ldg8(b + xa);
+    if (ty != 'Z' && ty != 'H') return false;
+    int32_t nm = itx_aux2i(b, itx_aux_find(b, a0, aend, 'N', 'M'), aend);
+    uint64_t s = xa + 1, zend = s;
+    while (zend < aend && itx_ldg8(b + zend) != 0) zend++;
+    if (s == zend) return false;                                  /* chopByChar on "" gives no pieces */
+    int pieces = 0;
+    while (pieces < 100) {
+        uint64_t pe = s;
+        while (pe < zend && itx_ldg8(b + pe) != ';') pe++;
+        pieces++;
+        if (pe > s) {
+            /* up to 4 comma separated fields; the 4th stops at the next comma */
+            uint64_t fs[4], fe[4]; int nf = 0; uint64_t q = s;
+            while (nf < 4) {
+                fs[nf] = q;
+                while (q < pe && itx_ldg8(b + q) != ',') q++;
+                fe[nf] = q; nf++;
+                if (q >= pe) break;
+                q++;
+            }
+            if (nf != 4) { if (malformed) (*malformed)++; }
+            else {
+                int32_t nm2 = itx_strtol_int(b, fs[3], fe[3]);
+                if (nm2 <= nm) {
+                    int32_t st = itx_strtol_int(b, fs[1], fe[1]);
+                    if (st < 0) st = (int32_t)(0u - (uint32_t)st);
+                    int32_t en = (int32_t)((uint32_t)st + (uint32_t)qlen);
+                    int32_t c = itx_chrom_by_name(D, b, fs[0], fe[0]);
+                    if (c >= 0 && itx_any_other_subfam(D, c, st, en, sel_fold)) return true;
+                }
+            }
+        }
+        if (pe >= zend) break;
+        s = pe + 1;
+    }
+    return false;
+}
+
+/* ------------------------------------------------------------------ consensus coverage range */
+/* closed form of the loop at generic.c:990-1006: the j range [*j0, *j1) touched by a fragment
+ * (start, qlen) on element (es, ee, cs, ce) of a subfamily with consensus length L; false = nothing */
+ITX_HD bool itx_cov_range(uint32_t start, uint32_t qlen, int32_t es, int32_t ee, uint32_t cs, uint32_t ce, uint32_t L,
+                          uint32_t *j0, uint32_t *j1) {
+    uint32_t rstart = start - (uint32_t)es;
+    uint32_t rend = rstart + qlen;
+    rend = rend < (uint32_t)ee ? rend : (uint32_t)ee;
+    if (!(rstart < rend)) return false;
+    uint32_t a = rstart + cs, lim = ce < L ? ce : L;
+    if (!(a < lim)) return false;
+    uint32_t n = rend - rstart, room = lim - a;
+    *j0 = a; *j1 = a + (n < room ? n : room);
+    return true;
+}
+#endif

@@ -1,0 +1,238 @@
+/* itx_emu.cpp -- TEST-ONLY host emulation of the device logic (never part of libiteres_gpu.so).
+ *
+ * iteres_b200/csrc/itx_logic.cuh is written as __host__ __device__ code; this file compiles it with
+ * g++ and drives it the way the kernels in itx_kernels.cuh do -- chunked speculative record-boundary
+ * discovery, chain verification / repair, then one "lane" per tuple -- but sequentially.  It lets
+ * the `-m "not gpu"` suite check the per-record logic against the oracle on a box without a GPU.
+ * The product has no CPU path: nothing under iteres_b200/ links or loads this file.
+ */
+#include "../../iteres_b200/csrc/itx_logic.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+struct emu_index {
+    itx_index ix;
+    itx_dev_index D;
+    std::vector<uint32_t> cname_slot, cname_off; std::vector<char> cname_pool;
+    std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
+    std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
+    std::vector<itx_trace> trace; uint64_t n_bad;
+};
+
+extern "C" {
+
+void emu_reset(emu_index *E) {
+    std::fill(E->u64.begin(), E->u64.end(), 0ull);
+    std::fill(E->bp_diff.begin(), E->bp_diff.end(), 0u); std::fill(E->bp_diff_u.begin(), E->bp_diff_u.end(), 0u);
+    std::fill(E->el_cnt.begin(), E->el_cnt.end(), 0u); std::fill(E->el_cnt_u.begin(), E->el_cnt_u.end(), 0u);
+    std::fill(E->grp_cpg.begin(), E->grp_cpg.end(), 0u); std::fill(E->el_cpg.begin(), E->el_cpg.end(), 0u);
+    std::fill(E->grp_cpg_score.begin(), E->grp_cpg_score.end(), 0.0); std::fill(E->bp_cpg.begin(), E->bp_cpg.end(), 0.0);
+    std::fill(E->el_cpg_score.begin(), E->el_cpg_score.end(), 0.0);
+    std::fill(E->status.begin(), E->status.end(), 0u);
+    E->trace.clear(); E->n_bad = 0;
+}
+
+emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk, int filter_field, const char *filter_name, char *err) {
+    emu_index *E = new emu_index();
+    memset(&E->ix, 0, sizeof E->ix);
+    if (itx_host_index_load(&E->ix, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err) != ITX_OK) { itx_host_index_free(&E->ix); delete E; return NULL; }
+    itx_index &ix = E->ix; itx_dev_index &D = E->D;
+    const int32_t nc = ix.chroms.n, ns = ix.subs.n, nf = ix.fams.n, ncl = ix.clas.n; const size_t ne = (size_t)ix.n_elem, ng = (size_t)(ns + nf + ncl);
+    uint32_t nslot = 16; while (nslot < (uint32_t)nc * 2u + 2u) nslot <<= 1;
+    E->cname_slot.assign(nslot, 0); E->cname_off.assign((size_t)nc + 1, 0);
+    for (int32_t c = 0; c < nc; c++) {
+        const char *nm = ix.chroms.names[c]; size_t l = strlen(nm);
+        E->cname_off[c] = (uint32_t)E->cname_pool.size(); E->cname_pool.insert(E->cname_pool.end(), nm, nm + l + 1);
+        uint32_t i = itx_fnv1a(nm, l) & (nslot - 1);
+        while (E->cname_slot[i]) i = (i + 1) & (nslot - 1);
+        E->cname_slot[i] = (uint32_t)c + 1;
+    }
+    E->cname_pool.push_back(0);
+    E->u64.assign(16 + 2 * ng, 0); E->bp_diff.assign(ix.bp_len + 1, 0); E->bp_diff_u.assign(ix.bp_len + 1, 0);
+    E->el_cnt.assign(ne + 1, 0); E->el_cnt_u.assign(ne + 1, 0); E->tid_seen.assign(ITX_MAX_TID_SEEN, 0); E->status.assign(8, 0);
+    E->grp_cpg.assign(ng + 1, 0); E->el_cpg.assign(ne + 1, 0); E->grp_cpg_score.assign(ng + 1, 0.0); E->bp_cpg.assign(ix.bp_len + 1, 0.0); E->el_cpg_score.assign(ne + 1, 0.0);
+    D.iv = ix.iv; D.pmax = ix.pmax; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
+    D.n_chrom = nc; D.n_elem = ix.n_elem;
+    D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data();
+    D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix.stat_mode;
+    D.sub_len = ix.sub_len; D.sub_bp_off = ix.sub_bp_off; D.sub_fold = ix.sub_fold;
+    D.cnt = E->u64.data(); D.grp = D.cnt + 16; D.bp_diff = E->bp_diff.data(); D.bp_diff_u = E->bp_diff_u.data();
+    D.el_cnt = E->el_cnt.data(); D.el_cnt_u = E->el_cnt_u.data();
+    D.grp_cpg = E->grp_cpg.data(); D.el_cpg = E->el_cpg.data(); D.grp_cpg_score = E->grp_cpg_score.data(); D.bp_cpg = E->bp_cpg.data(); D.el_cpg_score = E->el_cpg_score.data();
+    D.tid_unknown_seen = E->tid_seen.data(); D.status = E->status.data();
+    E->n_bad = 0;
+    return E;
+}
+void emu_free(emu_index *E) { if (!E) return; itx_host_index_free(&E->ix); delete E; }
+itx_index *emu_host_index(emu_index *E) { return &E->ix; }
+
+static void walk_chunk(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, uint64_t p, const itx_bam_header &h, const itx_dev_opts &o,
+                       std::vector<itx_tuple> &out, uint64_t *exit_) {
+    uint64_t hi = lo + C; if (hi > len) hi = len;
+    out.clear();
+    if (p < ITX_OFF_END) {
+        while (p < hi) {
+            if (p + 36 > len) { p = ITX_OFF_END; break; }
+            uint32_t x[9]; itx_load_core(b, p, x);
+            if ((int32_t)x[0] < 32 || p + 4 + (uint64_t)x[0] > len) { p = ITX_OFF_END; break; }
+            out.push_back(itx_decode_record(b, p, x, (uint32_t)(p - lo), h.tid, h.n_ref, o));
+            p += 4 + (uint64_t)x[0];
+        }
+    }
+    *exit_ = p;
+}
+
+/* bam: uncompressed stream with >= 64 readable bytes after len.  want_trace: keep a per-record trace. */
+int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_scan_opts *so, uint32_t chunk, int want_trace, uint64_t cnt[13], char *err) {
+    itx_index &ix = E->ix; itx_dev_index &D = E->D;
+    itx_bam_header h;
+    if (itx_host_parse_bam_header(&ix, bam, len, so->addChr, &h, err) != ITX_OK) return ITX_EFORMAT;
+    itx_dev_opts o; o.mapQ = so->mapQ; o.iSize = so->iSize; o.extension = so->extension; o.minCoverage = so->minCoverage;
+    o.filter = so->filter; o.discardWrongEnd = so->discardWrongEnd; o.treat = so->treat; o.diffSubfam = so->diffSubfam;
+    const uint32_t C = chunk;
+    const uint64_t k0 = h.hdr_len / C, k1 = len > h.hdr_len ? (len + C - 1) / C : k0, n = k1 - k0;
+    std::vector<std::vector<itx_tuple>> tup(n);
+    std::vector<uint64_t> entry(n), exit_(n);
+    /* K1: every chunk guesses its entry independently (chunk 0 knows it) */
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t lo = (k0 + i) * C, hi = lo + C; if (hi > len) hi = len;
+        uint64_t p = i == 0 ? h.hdr_len : itx_speculate_entry(bam, lo, hi, len, h.n_ref);
+        entry[i] = p;
+        walk_chunk(bam, len, lo, C, p, h, o, tup[i], &exit_[i]);
+    }
+    /* verify + repair */
+    for (uint64_t i = 1; i < n; i++) if (entry[i] != exit_[i - 1]) {
+        E->n_bad++;
+        entry[i] = exit_[i - 1];
+        walk_chunk(bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
+    }
+    /* K2 + K3 */
+    unsigned long long *c = D.cnt;
+    const bool stat = o.filter == 0 && D.stat_mode;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t lo = (k0 + i) * C;
+        for (size_t j = 0; j < tup[i].size(); j++) {
+            const itx_tuple T = tup[i][j]; const uint32_t info = T.info;
+            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+            c[slot2 ? 1 : 0]++;
+            if (info & ITX_F_MAPPED) c[slot2 ? 3 : 2]++;
+            if (info & ITX_F_USED) c[slot2 ? 5 : 4]++;
+            if (frag) { c[6]++; if (uniq) { c[7]++; c[11]++; } }
+            if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1;
+            long long sel = -1; bool diffsub = false;
+            const uint32_t chrom = info & ITX_CHROM_MASK;
+            if (frag && chrom != ITX_CHROM_NONE) {
+                int32_t nh; float tcov;
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nh, &tcov);
+                if (sel >= 0 && tcov < o.minCoverage) sel = -1;
+                if (sel >= 0 && o.diffSubfam && (info & ITX_F_HASXA)) {
+                    const uint64_t p = lo + T.rec_off; uint32_t x[9]; itx_load_core(bam, p, x); uint32_t bad = 0;
+                    if (itx_mapped_to_diff_subfam(D, bam, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                    D.status[2] += bad;
+                }
+            }
+            if (diffsub) c[12]++;
+            const bool counted = sel >= 0 && !diffsub;
+            if (counted) {
+                c[9]++; if (uniq) c[10]++;
+                if (stat) {
+                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+                    const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+                    D.grp[hs]++; D.grp[hf]++; D.grp[hc]++;
+                    if (uniq) { D.grp[hs + 1]++; D.grp[hf + 1]++; D.grp[hc + 1]++; }
+                    const uint32_t L = D.sub_len[m.sub]; uint32_t ja, jb;
+                    if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
+                        const unsigned long long off = D.sub_bp_off[m.sub];
+                        D.bp_diff[off + ja] += 1u; D.bp_diff[off + jb] += 0xffffffffu;
+                        if (uniq) { D.bp_diff_u[off + ja] += 1u; D.bp_diff_u[off + jb] += 0xffffffffu; }
+                    }
+                } else if (o.filter) { D.el_cnt[sel]++; if (uniq) D.el_cnt_u[sel]++; }
+            }
+            if (want_trace) {
+                itx_trace t;
+                t.start = frag ? T.start : 0; t.end = frag ? T.end : 0; t.tid = (int32_t)itx_ld_u32(bam, lo + T.rec_off + 4);
+                t.sel_row = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+                t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
+                          ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
+                E->trace.push_back(t);
+            }
+        }
+    }
+    for (int k = 0; k < 13; k++) { ix.cnt[k] = c[k]; if (cnt) cnt[k] = c[k]; }
+    for (int32_t i = 0; i < h.n_ref; i++) free(h.names[i]);
+    free(h.names); free(h.lens); free(h.tid);
+    return ITX_OK;
+}
+
+/* results -> the host index (what itx_sync_counts does after the device run) */
+void emu_sync(emu_index *E) {
+    itx_index &ix = E->ix; itx_dev_index &D = E->D;
+    const size_t ne = (size_t)ix.n_elem, bl = (size_t)ix.bp_len;
+    if (!ix.bp) { ix.bp = (uint32_t *)calloc(bl + 1, 4); ix.bp_u = (uint32_t *)calloc(bl + 1, 4); ix.bp_cpg = (double *)calloc(bl + 1, 8); }
+    if (!ix.el_cnt) { ix.el_cnt = (uint32_t *)calloc(ne + 1, 4); ix.el_cnt_u = (uint32_t *)calloc(ne + 1, 4); ix.el_cpg = (uint32_t *)calloc(ne + 1, 4); ix.el_cpg_score = (double *)calloc(ne + 1, 8); }
+    for (int32_t s = 0; s < ix.subs.n; s++) {
+        uint32_t L = ix.sub_len[s]; if (!L) continue;
+        uint64_t off = ix.sub_bp_off[s]; uint32_t a = 0, u = 0;
+        for (uint32_t j = 0; j <= L; j++) { a += D.bp_diff[off + j]; u += D.bp_diff_u[off + j]; ix.bp[off + j] = a; ix.bp_u[off + j] = u; }
+    }
+    memcpy(ix.el_cnt, D.el_cnt, ne * 4); memcpy(ix.el_cnt_u, D.el_cnt_u, ne * 4);
+    memcpy(ix.el_cpg, D.el_cpg, ne * 4); memcpy(ix.el_cpg_score, D.el_cpg_score, ne * 8); memcpy(ix.bp_cpg, D.bp_cpg, bl * 8);
+    const int32_t ns = ix.subs.n, nf = ix.fams.n, nc = ix.clas.n; const unsigned long long *g = D.grp;
+    for (int32_t i = 0; i < ns; i++) { ix.sub[i].read_count = g[2 * i]; ix.sub[i].read_count_unique = g[2 * i + 1]; ix.sub[i].cpg_count = D.grp_cpg[i]; ix.sub[i].cpg_score = D.grp_cpg_score[i]; }
+    for (int32_t i = 0; i < nf; i++) { ix.fam[i].read_count = g[2 * (ns + i)]; ix.fam[i].read_count_unique = g[2 * (ns + i) + 1]; ix.fam[i].cpg_count = D.grp_cpg[ns + i]; ix.fam[i].cpg_score = D.grp_cpg_score[ns + i]; }
+    for (int32_t i = 0; i < nc; i++) { ix.cla[i].read_count = g[2 * (ns + nf + i)]; ix.cla[i].read_count_unique = g[2 * (ns + nf + i) + 1]; ix.cla[i].cpg_count = D.grp_cpg[ns + nf + i]; ix.cla[i].cpg_score = D.grp_cpg_score[ns + nf + i]; }
+}
+
+uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
+    uint64_t n = E->trace.size() < cap ? E->trace.size() : cap;
+    memcpy(out, E->trace.data(), n * sizeof(itx_trace));
+    return E->trace.size();
+}
+uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
+
+int32_t emu_query(emu_index *E, const char *chrom, uint32_t start, uint32_t end, float min_cov, int32_t *n_hits) {
+    int32_t c = itx_strtab_find(&E->ix.chroms, chrom); if (n_hits) *n_hits = 0;
+    if (c < 0) return -1;
+    int32_t nh; float tcov; long long sel = itx_find_select(E->D, c, start, end, &nh, &tcov);
+    if (n_hits) *n_hits = nh;
+    if (sel >= 0 && tcov < min_cov) sel = -1;
+    return sel >= 0 ? (int32_t)E->D.meta[sel].row : -1;
+}
+
+/* CpG rows in file order (the kernel k_cpg, sequentially) */
+int emu_scan_cpg(emu_index *E, const char *bedgraph, int filter, uint32_t *n_lines, uint32_t *n_in_repeat, char *err) {
+    itx_index &ix = E->ix; itx_dev_index &D = E->D;
+    FILE *f = fopen(bedgraph, "r"); if (!f) { snprintf(err, ITX_ERRLEN, "Couldn't open %s", bedgraph); return ITX_EIO; }
+    char *line = NULL; size_t lc = 0; uint32_t lines = 0, inrep = 0;
+    while (getline(&line, &lc, f) >= 0) {
+        char *s = line; while (*s == ' ' || (*s >= 9 && *s <= 13)) s++;
+        if (*s == 0 || *s == '#') continue;
+        char *w[20]; int nw = 0; char *q = s;
+        while (nw < 20) { while (*q == ' ' || (*q >= 9 && *q <= 13)) q++; if (!*q) break; w[nw++] = q; while (*q && !(*q == ' ' || (*q >= 9 && *q <= 13))) q++; if (!*q) break; *q++ = 0; }
+        if (nw < 4) { snprintf(err, ITX_ERRLEN, "file %s doesn't appear to be in bedGraph format. At least 4 fields required, got %d", bedgraph, nw); free(line); fclose(f); return ITX_EFORMAT; }
+        lines++;
+        int32_t c = itx_strtab_find(&ix.chroms, w[0]);
+        uint32_t st = (uint32_t)strtol(w[1], NULL, 0), en = (uint32_t)strtol(w[2], NULL, 0); double sc = strtod(w[3], NULL);
+        if (c < 0) continue;
+        long long sel = itx_find_head(D, c, st, en);
+        if (sel < 0) continue;
+        inrep++;
+        if (filter) { D.el_cpg[sel]++; D.el_cpg_score[sel] += sc; continue; }
+        if (!D.stat_mode) continue;
+        const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+        const uint32_t gs = mt.sub, gf = (uint32_t)(D.n_sub + m2.fam), gc = (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+        D.grp_cpg[gs]++; D.grp_cpg_score[gs] += sc; D.grp_cpg[gf]++; D.grp_cpg_score[gf] += sc; D.grp_cpg[gc]++; D.grp_cpg_score[gc] += sc;
+        const uint32_t L = D.sub_len[mt.sub]; uint32_t ja, jb;
+        if (L && itx_cov_range(st, 2u, e.start, e.end, mt.cons_start, mt.cons_end, L, &ja, &jb)) {
+            const unsigned long long off = D.sub_bp_off[mt.sub];
+            for (uint32_t j = ja; j < jb; j++) D.bp_cpg[off + j] += sc;
+        }
+    }
+    free(line); fclose(f);
+    if (n_lines) *n_lines = lines;
+    if (n_in_repeat) *n_in_repeat = inrep;
+    return ITX_OK;
+}
+}

@@ -92,6 +92,45 @@ def run_oracle(inp, cmd, args, outdir, prefix="out"):
         ix.close()
 
 
+def itx_opts(o):
+    from iteres_b200 import capi
+    return capi.default_opts(mapQ=o["Q"], filter=1 if o["cmd"] == "filter" else 0, rmDup=o["R"], addChr=o["C"],
+                             discardWrongEnd=o["D"], iSize=o["I"], extension=o["E"], minCoverage=o["cov"], treat=o["T"],
+                             diffSubfam=o["diff"])
+
+
+def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
+    """Same driver for the CUDA product (iteres_b200.Index) and the host emulation of its device logic
+    (emu_lib.EmuIndex).  make_index(chrom, rep, rmsk, field, name) -> index; scan(ix, bam_path, opts)."""
+    o = parse(cmd, args)
+    f = lambda n: os.path.join(inp, n)
+    p = os.path.join(outdir, prefix)
+    ix = make_index(f("chrom.sizes"), f("rep.sizes"), f("rmsk.txt"), o["field"], o["name"])
+    try:
+        if cmd == "stat":
+            scan(ix, f("reads.bam"), itx_opts(o))
+            ix.write_stat(p, o["nindex"], o["nindex2"])
+            ix.write_report(p + ".iteres.report", o["Q"], "ALL")
+        elif cmd == "filter":
+            scan(ix, f("reads.bam"), itx_opts(o))
+            ix.write_filter("%s_%s.iteres.loci" % (p, o["name"]), o["r"], o["t"], o["nindex"])
+            ix.write_report("%s_%s.iteres.reportloci" % (p, o["name"]), o["Q"], o["name"])
+        elif cmd == "cpgstat":
+            ix.scan_cpg(f("cpg.bedGraph"), 0)
+            ix.write_cpg_stat(p)
+        elif cmd == "cpgfilter":
+            ix.scan_cpg(f("cpg.bedGraph"), 1)
+            ix.write_cpg_filter("%s_%s.CpG.loci" % (p, o["name"]), o["thr"])
+        return list(ix.cnt)
+    finally:
+        ix.close()
+
+
+def needs_host_order(cmd, args):
+    """variants whose output depends on read order (not on the device yet): -R dedup, filter -r name lists"""
+    return "-R" in args or (cmd == "filter" and "-r" in args)
+
+
 SKIP = {"cmdline.txt", "stderr.txt"}
 
 

@@ -1,0 +1,139 @@
+"""The device logic (host emulation) against the oracle on generated inputs of the benchmark shapes,
+scaled down: every counter, table and coverage vector bit-exact, and the per-record trace (fragment,
+selected rmsk row, flags) identical record by record.  Also the reference binary itself against the
+oracle on the same files when it is available (the build container)."""
+import filecmp
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib as O
+import synth
+from iteres_b200 import capi
+
+CASES = [
+    # name, shape, n_rmsk, mode, n_units, opts
+    ("se50_chr1", 0, 20000, 0, 30000, {}),
+    ("se50_hg19_E0", 1, 60000, 0, 40000, dict(extension=0)),
+    ("se75_xa_hg19", 1, 60000, 1, 40000, {}),
+    ("se75_xa_nodiff", 1, 60000, 1, 20000, dict(diffSubfam=0)),
+    ("pe100_hg19", 1, 60000, 2, 20000, {}),
+    ("pe100_treat", 1, 60000, 2, 20000, dict(treat=1)),
+    ("pe100_D_I300", 1, 60000, 2, 20000, dict(discardWrongEnd=1, iSize=300)),
+    ("se50_Q30_c05", 0, 20000, 0, 20000, dict(mapQ=30, minCoverage=0.5)),
+]
+
+
+@pytest.fixture(scope="module")
+def worlds(tmp_path_factory):
+    made = {}
+
+    def get(shape, n_rmsk):
+        if (shape, n_rmsk) not in made:
+            d = str(tmp_path_factory.mktemp("synth%d" % shape))
+            s = synth.Synth(shape, n_rmsk, seed=7)
+            made[(shape, n_rmsk)] = (s, s.write_tables(d), d)
+        return made[(shape, n_rmsk)]
+    yield get
+    for s, _, _ in made.values():
+        s.close()
+
+
+def tables_equal(a, b):
+    for which in range(3):
+        assert a.table(which) == b.table(which)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_emu_matches_oracle(case, worlds):
+    name, shape, n_rmsk, mode, n_units, kw = case
+    s, (cs, rs, rm), _ = worlds(shape, n_rmsk)
+    buf, n, nrec = s.stream(mode, n_units)
+    raw = buf[:n].tobytes()
+    ora = O.OracleIndex(cs, rs, rm)
+    cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
+    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=1024)
+    cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
+    assert cnt_e == cnt_o
+    assert cnt_o[0] + cnt_o[1] == nrec and cnt_o[9] > 0
+    assert len(tr_e) == len(tr_o) == nrec
+    for f in ("start", "end", "tid", "sel_row"):
+        assert np.array_equal(tr_e[f], tr_o[f]), f
+    mask = ~np.uint32(O.lib() and 8)       # HAS_XA is reported by the oracle even where it is not evaluated
+    assert np.array_equal(tr_e["flags"] & mask, tr_o["flags"] & mask)
+    if kw.get("diffSubfam", 1) and mode == 1:
+        assert cnt_o[12] > 0
+    # group tables and coverage
+    L = O.lib()
+    import ctypes as C
+    c4 = (C.c_uint64 * 4)()
+    for which, nfun in ((0, L.ora_n_subfam), (1, L.ora_n_fam), (2, L.ora_n_class)):
+        got = emu.table(which)
+        assert len(got) == nfun(ora.h)
+        for i, row in enumerate(got):
+            L.ora_counts(ora.h, which, i, c4)
+            assert row == (L.ora_name(ora.h, which, i).decode(),) + tuple(c4)
+    for i in range(L.ora_n_subfam(ora.h)):
+        ln = L.ora_subfam_length(ora.h, i)
+        if ln:
+            for u in (0, 1):
+                want = np.ctypeslib.as_array(L.ora_subfam_bp(ora.h, i, u), shape=(ln,))
+                assert np.array_equal(emu.coverage(i, u), want)
+    ora.close()
+    emu.close()
+
+
+@pytest.mark.parametrize("chunk", [64, 448, 8192, 1 << 20])
+def test_chunk_size_never_changes_the_answer(chunk, worlds):
+    """Speculated chunk entries only cost time: any chunk size (even smaller than a record) gives the chain."""
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    buf, n, nrec = s.stream(1, 5000)
+    raw = buf[:n].tobytes()
+    ref = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
+    want = ref.scan_stream(raw, capi.default_opts())
+    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=chunk)
+    assert emu.scan_stream(raw, capi.default_opts()) == want
+    if chunk == 64:
+        assert emu.n_bad() > 0          # chunks smaller than a record: the repair path did run
+    assert emu.table(0) == ref.table(0)
+    ref.close()
+    emu.close()
+
+
+def test_truncated_stream_stops_like_the_reference(worlds):
+    """bam_read1 fails on a cut record and the reference's loop ends silently (generic.c:745)."""
+    s, (cs, rs, rm), _ = worlds(0, 20000)
+    buf, n, nrec = s.stream(0, 3000)
+    for cut in (n - 1, n - 40, n - 131, n // 2 + 3):
+        raw = buf[:cut].tobytes()
+        ora = O.OracleIndex(cs, rs, rm)
+        emu = emu_lib.EmuIndex(cs, rs, rm, chunk=512)
+        assert emu.scan_stream(raw, capi.default_opts()) == ora.scan_stream(raw, O.default_opts())
+        ora.close()
+        emu.close()
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="reference binary not built here")
+@pytest.mark.parametrize("mode,n_units,args", [(0, 20000, []), (1, 20000, []), (2, 10000, []), (1, 10000, ["-x", "-E", "0"])])
+def test_reference_binary_matches_oracle_on_synthetic_bam(mode, n_units, args, worlds, tmp_path):
+    """Pins the oracle (and with it everything compared to the oracle) to the UNMODIFIED reference on
+    inputs far larger than the known-answer files."""
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    bam = str(tmp_path / "reads.bam")
+    s.write_bam(bam, mode, n_units, level=1, threads=4)
+    rd, od = tmp_path / "ref", tmp_path / "ora"
+    rd.mkdir(); od.mkdir()
+    p = subprocess.run([O.REF_BIN, "stat", "-w", "-o", "out"] + args + [cs, rs, rm, bam], cwd=str(rd), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    import runners
+    o = runners.parse("stat", args)
+    ix = O.OracleIndex(cs, rs, rm)
+    ix.scan_file(bam, runners.ora_opts(o))
+    ix.write_stat(str(od / "out"), o["nindex"], o["nindex2"])
+    ix.write_report(str(od / "out.iteres.report"), o["Q"], "ALL")
+    ix.close()
+    for fn in ("out.iteres.subfamily.stat", "out.iteres.family.stat", "out.iteres.class.stat", "out.iteres.report", "out.iteres.wig", "out.iteres.unique.wig"):
+        assert filecmp.cmp(str(rd / fn), str(od / fn), shallow=False), fn
