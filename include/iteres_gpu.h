@@ -147,6 +147,10 @@ typedef struct itx_profile {
     int32_t inflate_threads;
 } itx_profile;
 void itx_last_profile(const itx_index *ix, itx_profile *p);
+/* device-side stopwatch on the scan stream: itx_mark records CUDA event `slot` (0..7) after everything
+ * enqueued so far; itx_elapsed_ms synchronises on both events and returns the time between them */
+int itx_mark(itx_index *ix, int slot);
+double itx_elapsed_ms(itx_index *ix, int slot_from, int slot_to);
 /* knobs (0 keeps the default): chunk bytes per decode thread, window bytes per launch group, host inflate threads */
 int itx_tune(itx_index *ix, uint32_t chunk_bytes, uint64_t window_bytes, int32_t inflate_threads);
 

@@ -53,7 +53,7 @@ itx_index_reset_counts itx_scan_alignments itx_scan_bgzf_memory itx_scan_bam_hos
 itx_bam_header_len itx_bam_header_free itx_scan_bam_device itx_scan_cpg itx_sync_counts itx_write_stat
 itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_subfam itx_n_fam itx_n_class
 itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
-itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_tune itx_comm_unique_id itx_comm_init
+itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
 itx_comm_allreduce_counts itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
 itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync""".split()
 
@@ -117,6 +117,9 @@ def lib():
         L.itx_query_select.argtypes = [vp, cp, vp, vp, C.c_int64, C.c_float, vp, vp, cp]
         L.itx_last_profile.argtypes = [vp, C.POINTER(Profile)]
         L.itx_tune.argtypes = [vp, C.c_uint32, u64, C.c_int32]
+        L.itx_mark.argtypes = [vp, C.c_int]
+        L.itx_elapsed_ms.restype = C.c_double
+        L.itx_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
         L.itx_comm_unique_id.argtypes = [vp, cp]
         L.itx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, cp]
         L.itx_comm_allreduce_counts.argtypes = [vp, cp]
@@ -291,6 +294,12 @@ class Index(IndexBase):
             if rc:
                 raise ItxError(rc, err.value.decode())
             self._dirty = False
+
+    def mark(self, slot):
+        self.L.itx_mark(self.h, slot)
+
+    def elapsed_ms(self, a, b):
+        return self.L.itx_elapsed_ms(self.h, a, b)
 
     def profile(self):
         p = Profile()

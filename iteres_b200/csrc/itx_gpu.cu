@@ -42,6 +42,7 @@ struct itx_cuda {
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
+    cudaEvent_t marks[8]; int marks_made;
     /* NCCL (dlopen) */
     void *nccl_lib; void *nccl_comm; int nranks, rank;
 };
@@ -78,6 +79,7 @@ static void cuda_free_all(itx_cuda *cu) {
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
+    if (cu->marks_made) for (int i = 0; i < 8; i++) cudaEventDestroy(cu->marks[i]);
     if (cu->stream) cudaStreamDestroy(cu->stream);
     if (cu->copy_stream) cudaStreamDestroy(cu->copy_stream);
     free(cu);
@@ -189,6 +191,22 @@ extern "C" int itx_tune(itx_index *ix, uint32_t chunk_bytes, uint64_t window_byt
     if (inflate_threads) ix->tune_threads = inflate_threads;
     return ITX_OK;
 }
+extern "C" int itx_mark(itx_index *ix, int slot) {
+    itx_cuda *cu = ix->cu;
+    if (slot < 0 || slot >= 8) return ITX_EARG;
+    cudaSetDevice(cu->device);
+    if (!cu->marks_made) { for (int i = 0; i < 8; i++) cudaEventCreate(&cu->marks[i]); cu->marks_made = 1; }
+    return cudaEventRecord(cu->marks[slot], cu->stream) == cudaSuccess ? ITX_OK : ITX_ENODEV;
+}
+extern "C" double itx_elapsed_ms(itx_index *ix, int a, int b) {
+    itx_cuda *cu = ix->cu;
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !cu->marks_made) return -1.0;
+    cudaSetDevice(cu->device);
+    if (cudaEventSynchronize(cu->marks[a]) != cudaSuccess || cudaEventSynchronize(cu->marks[b]) != cudaSuccess) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, cu->marks[a], cu->marks[b]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 extern "C" int itx_trace_enable(itx_index *ix, uint64_t cap) { ix->trace_cap = cap; return ITX_OK; }
 extern "C" void itx_last_profile(const itx_index *ix, itx_profile *p) { *p = ix->prof; }
 
@@ -299,7 +317,7 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         }
         size_t hist = 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4;
         bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
-        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
+        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 3));
         uint32_t need_blocks = (n + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
         if (smem) {
             if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
@@ -399,7 +417,8 @@ extern "C" int itx_scan_bam_host(itx_index *ix, const uint8_t *bam, uint64_t len
     itx_bam_header *h = itx_bam_header_parse(ix, bam, len, o->addChr, err);
     if (!h) return ITX_EFORMAT;
     uint64_t W = ix->tune_window < (256ull << 20) ? ix->tune_window : (256ull << 20);
-    W = (W / ix->tune_chunk ? W / ix->tune_chunk : 1) * (uint64_t)ix->tune_chunk;      /* whole chunks per copy */
+    if (W > len) W = len;
+    W = ((W + ix->tune_chunk - 1) / ix->tune_chunk) * (uint64_t)ix->tune_chunk;         /* whole chunks per copy */
     scan_ctx sc;
     if ((rc = ensure_stream_buffer(cu, len, err))) { itx_bam_header_free(h); return rc; }
     if ((rc = scan_begin(&sc, ix, h, cu->d_stream, len, o, W, err))) { itx_bam_header_free(h); return rc; }
@@ -451,6 +470,8 @@ extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t
     if (nth > 256) nth = 256;
     /* windows of whole BGZF blocks, about W uncompressed bytes each, inflated straight into pinned memory */
     uint64_t W = ix->tune_window < (64ull << 20) ? ix->tune_window : (64ull << 20);
+    if (W > total) W = total;
+    if (W < 65536) W = 65536;
     if ((rc = ensure_stream_buffer(cu, total, err)) || (rc = ensure_stage(cu, W + 65536, err))) { free(blk); return rc; }
     cudaEvent_t done[2]; cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
     itx_bam_header *h = NULL; scan_ctx sc; bool begun = false;
@@ -549,6 +570,7 @@ extern "C" int itx_sync_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     if (ne) { CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream)); }
     CK(cudaStreamSynchronize(cu->stream));
     float fm = 0; cudaEventElapsedTime(&fm, a, b); ix->prof.finalize_ms = fm; cudaEventDestroy(a); cudaEventDestroy(b);
+    ix->prof.d2h_bytes += cu->n_u64 * 8 + bl * 16 + ne * 20 + ng * 12 + bl * 8;
     for (int k = 0; k < 13; k++) ix->cnt[k] = u64[k];
     const unsigned long long *g = u64 + 16;
     const int32_t ns = ix->subs.n, nf = ix->fams.n, nc = ix->clas.n;
