@@ -70,7 +70,15 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
+
+    def wait_first(self, timeout=4.0):
+        t0 = time.perf_counter()
+        while self.p and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.p:
@@ -79,6 +87,9 @@ class ClockSampler:
                 self.p.wait(timeout=5)
             except Exception:
                 pass
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", 1e30)
+        inside = [r for r in self.rows if t0 - 0.15 <= r[-1] <= t1 + 0.15]
+        self.rows = inside or self.rows
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
         mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -156,7 +167,7 @@ def reference_baseline(wd, tables, synth_world, sample_reads, mode, procs, repea
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (BASELINE configs[1])")
@@ -270,8 +281,14 @@ def main():
     sampler = ClockSampler(lrank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+        for _ in range(2):          # keep the device busy until the sampler is running (untimed)
+            step()
+        L.itx_dev_sync()
+    barrier()
     dec = ovl = 0.0
     launches = 0
+    t_w0 = time.perf_counter()
     ix.mark(0)
     for _ in range(a.steps):
         cnt = step()
@@ -280,6 +297,7 @@ def main():
     ix.mark(1)
     L.itx_dev_sync()
     el_ms = ix.elapsed_ms(0, 1)
+    sampler.window(t_w0, time.perf_counter())
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     assert cnt[0] + cnt[1] == nrec, (cnt, nrec)
