@@ -23,7 +23,7 @@ struct itx_cuda {
     int sm_count; size_t smem_optin;
     /* index */
     itx_dev_index D;
-    void *d_iv, *d_pmax, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
+    void *d_iv, *d_bucket, *d_chrom_bucket, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
     void *d_sub_len, *d_sub_bp_off, *d_sub_fold;
     /* counter block */
     void *d_u64; size_t n_u64;           /* cnt[16] + grp */
@@ -36,6 +36,7 @@ struct itx_cuda {
     uint32_t C, S; uint64_t cap_chunks;
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
+    uint32_t *d_work; int decode_variant;   /* 0: k_decode_tiles (TMA ring), 1: k_decode (thread per chunk) */
     itx_trace *d_trace; uint64_t trace_cap;
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
@@ -72,7 +73,7 @@ template <typename T> static int upload(void **dst, const T *src, size_t n, char
 static void cuda_free_all(itx_cuda *cu) {
     if (!cu) return;
     cudaSetDevice(cu->device);
-    void *ptrs[] = {cu->d_iv, cu->d_pmax, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
+    void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush};
@@ -136,7 +137,8 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaStreamCreateWithFlags(&cu->stream, cudaStreamNonBlocking));
         CKN(cudaStreamCreateWithFlags(&cu->copy_stream, cudaStreamNonBlocking));
         const size_t ne = (size_t)ix->n_elem; const int32_t nc = ix->chroms.n, ns = ix->subs.n, nf = ix->fams.n, ncl = ix->clas.n;
-        if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_pmax, ix->pmax, ne, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
+        if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_bucket, ix->bucket, (size_t)ix->n_bucket, err) ||
+            upload(&cu->d_chrom_bucket, ix->chrom_bucket, (size_t)nc + 1, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
             upload(&cu->d_meta2, ix->meta2, ne, err) || upload(&cu->d_chrom_off, ix->chrom_off, (size_t)nc + 1, err) ||
             upload(&cu->d_chrom_size, ix->chrom_size, (size_t)nc, err) || upload(&cu->d_sub_len, ix->sub_len, (size_t)ns, err) ||
             upload(&cu->d_sub_bp_off, ix->sub_bp_off, (size_t)ns + 1, err) || upload(&cu->d_sub_fold, ix->sub_fold, (size_t)ns, err)) goto fail;
@@ -164,8 +166,10 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc(&cu->d_misc, (ITX_MAX_TID_SEEN + 8) * 4));
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
+        CKN(cudaMalloc((void **)&cu->d_work, 8)); CKN(cudaMemset(cu->d_work, 0, 8));
+        CKN(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM));
         itx_dev_index &D = cu->D;
-        D.iv = (const itx_iv *)cu->d_iv; D.pmax = (const int32_t *)cu->d_pmax; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
+        D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
         D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool;
         D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix->stat_mode;
@@ -177,7 +181,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
         if (zero_counters(ix, err)) goto fail;
     }
-    ix->tune_chunk = 4096; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
+    ix->tune_chunk = 32768; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
     return ix;
 fail:
     cuda_free_all(cu); ix->cu = NULL;
@@ -286,6 +290,12 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     sc->k_next = sc->k_first;
     unsigned long long carry = h->hdr_len;
     CK(cudaMemcpyAsync(cu->d_carry, &carry, 8, cudaMemcpyHostToDevice, cu->stream));
+    CK(cudaMemsetAsync(cu->d_work, 0, 8, cu->stream));
+    {   /* ITX_DECODE_KERNEL=thread selects the one-thread-per-chunk kernel (A/B measurement); chunks that are not whole tiles use it too */
+        const char *v = getenv("ITX_DECODE_KERNEL");
+        cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_TILE) != 0) ? 1 : 0;
+        if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
+    }
     if (ix->trace_cap) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
     CK(cudaStreamSynchronize(cu->stream));   /* the 8-byte sources live on this stack frame */
     return ITX_OK;
@@ -300,17 +310,20 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         A.b = sc->b; A.len = sc->len; A.avail = avail; A.k0 = sc->k_next; A.nchunks = n; A.C = cu->C; A.S = cu->S;
         A.tid = sc->h->d_tid; A.n_ref = sc->h->n_ref; A.o = sc->o;
         A.tuples = cu->d_tuples; A.entry = cu->d_entry; A.exit_ = cu->d_exit; A.nrec = cu->d_nrec;
-        A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status;
+        A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status; A.work = cu->d_work;
         bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
         if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
-        k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
+        if (cu->decode_variant == 0) {
+            uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)cu->sm_count * 3u;
+            k_decode_tiles<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM, cu->stream>>>(A);
+        } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
         k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
         k_fixup<<<1, 32, 0, cu->stream>>>(A);
         if (timed) cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream);
         sc->n_launch += 3;
         itx_overlap_args B;
         B.D = cu->D; B.b = sc->b; B.k0 = sc->k_next; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
-        B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL;
+        B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1;
         if (ix->trace_cap) {
             k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
             B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
@@ -351,6 +364,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
     P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1];
     P->d2h_bytes = sizeof hc + sizeof st;
+    if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA tile copy never completed (device-side time-out in k_decode_tiles)"); return ITX_ENODEV; }
     if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
     /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */
     if (sc->h->n_ref > 0) {

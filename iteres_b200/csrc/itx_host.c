@@ -249,7 +249,7 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
     int32_t nchrom = ix->chroms.n;
     size_t ne = (size_t)(nraw ? nraw : 1);
     ix->chrom_off = (long long *)calloc((size_t)nchrom + 1, sizeof(long long));
-    ix->iv = (itx_iv *)malloc(sizeof(itx_iv) * ne); ix->pmax = (int32_t *)malloc(sizeof(int32_t) * ne);
+    ix->iv = (itx_iv *)malloc(sizeof(itx_iv) * ne);
     ix->meta = (itx_meta *)malloc(sizeof(itx_meta) * ne); ix->meta2 = (itx_meta2 *)malloc(sizeof(itx_meta2) * ne);
     ix->el_chrom = (int32_t *)malloc(sizeof(int32_t) * ne);
     ix->row2el = (long long *)malloc(sizeof(long long) * (size_t)(ix->n_rows ? ix->n_rows : 1));
@@ -261,13 +261,27 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
         const raw_el *e = &raw[i];
         if (e->chrom != prevc) { prevc = e->chrom; run = INT32_MIN; }
         if (e->end > run) run = e->end;
-        ix->iv[i].start = e->start; ix->iv[i].end = e->end; ix->pmax[i] = run;
+        ix->iv[i].start = e->start; ix->iv[i].end = e->end; ix->iv[i].pmax = run; ix->iv[i].row = e->row;
         ix->meta[i].cons_start = e->cs; ix->meta[i].cons_end = e->ce; ix->meta[i].row = e->row; ix->meta[i].sub = (uint32_t)e->sub;
         ix->meta2[i].fam = e->fam; ix->meta2[i].cla = e->cla;
         ix->el_chrom[i] = e->chrom;
         ix->row2el[e->row] = i;
     }
     free(raw);
+    if (nraw >= 0xffffffffLL) { snprintf(err, ITX_ERRLEN, "more than 2^32 rmsk rows are not supported"); return ITX_ENOTSUP; }
+    /* position buckets: first element with start >= (b << ITX_BSH), per chromosome */
+    ix->chrom_bucket = (long long *)calloc((size_t)nchrom + 1, sizeof(long long));
+    for (int32_t c = 0; c < nchrom; c++) ix->chrom_bucket[c + 1] = ix->chrom_bucket[c] + ((long long)ix->chrom_size[c] >> ITX_BSH) + 2;
+    ix->n_bucket = ix->chrom_bucket[nchrom];
+    ix->bucket = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(ix->n_bucket ? ix->n_bucket : 1));
+    for (int32_t c = 0; c < nchrom; c++) {
+        long long i = ix->chrom_off[c], hi = ix->chrom_off[c + 1], nb = ix->chrom_bucket[c + 1] - ix->chrom_bucket[c];
+        for (long long b = 0; b < nb; b++) {
+            long long first = b << ITX_BSH;
+            while (i < hi && (long long)ix->iv[i].start < first) i++;
+            ix->bucket[ix->chrom_bucket[c] + b] = (uint32_t)i;
+        }
+    }
 
     /* per-subfamily consensus length, coverage array offsets, case-folded name classes */
     int32_t ns = ix->subs.n;
@@ -300,7 +314,7 @@ void itx_host_index_free(struct itx_index *ix) {
     }
     itx_strtab_free(&ix->subs); itx_strtab_free(&ix->fams); itx_strtab_free(&ix->clas); itx_strtab_free(&ix->warned);
     free(ix->sub); free(ix->fam); free(ix->cla); free(ix->sub_len); free(ix->sub_bp_off); free(ix->sub_fold);
-    free(ix->iv); free(ix->pmax); free(ix->meta); free(ix->meta2); free(ix->el_chrom); free(ix->row2el);
+    free(ix->iv); free(ix->bucket); free(ix->chrom_bucket); free(ix->meta); free(ix->meta2); free(ix->el_chrom); free(ix->row2el);
     free(ix->bp); free(ix->bp_u); free(ix->bp_cpg); free(ix->el_cnt); free(ix->el_cnt_u); free(ix->el_cpg); free(ix->el_cpg_score);
     free(ix->row_cnt); free(ix->row_cnt_u);
     free(ix->sub_order); free(ix->fam_order); free(ix->cla_order);

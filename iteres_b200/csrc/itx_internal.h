@@ -33,13 +33,17 @@ typedef struct {
 } itx_group;
 
 /* ------------------------------------------------------------------ interval table */
-/* Per chromosome the elements are ordered by (start, row); pmax = running maximum of `end`. */
-typedef struct { int32_t start, end; } itx_iv;
+/* Per chromosome the elements are ordered by (start, row); pmax = running maximum of `end` inside the
+ * chromosome; one 16-byte load per candidate.  `bucket` maps (chromosome, position >> ITX_BSH) to the
+ * first element whose start is >= the bucket's first base, so a lower_bound only searches one bucket. */
+typedef struct { int32_t start, end, pmax; uint32_t row; } itx_iv;
+#define ITX_BSH 12
 typedef struct { uint32_t cons_start, cons_end, row, sub; } itx_meta;     /* 16 B, one load */
 typedef struct { int32_t fam, cla; } itx_meta2;
 
 typedef struct {
-    const itx_iv *iv; const int32_t *pmax; const itx_meta *meta; const itx_meta2 *meta2;
+    const itx_iv *iv; const itx_meta *meta; const itx_meta2 *meta2;
+    const uint32_t *bucket; const long long *chrom_bucket;   /* bucket[chrom_bucket[c] + (pos >> ITX_BSH)], (size >> ITX_BSH) + 2 entries per chromosome */
     const long long *chrom_off;          /* n_chrom + 1 */
     const int32_t *chrom_size;           /* binKeeper maxPos (from the chrom size file) */
     int32_t n_chrom; long long n_elem;
@@ -110,7 +114,8 @@ struct itx_index {
     itx_group *sub, *fam, *cla;                                          /* counters (stat_mode only) */
     uint32_t *sub_len; unsigned long long *sub_bp_off; int32_t *sub_fold; uint64_t bp_len;
     long long n_elem, n_rows;
-    itx_iv *iv; int32_t *pmax; itx_meta *meta; itx_meta2 *meta2; int32_t *el_chrom;   /* sorted order */
+    itx_iv *iv; itx_meta *meta; itx_meta2 *meta2; int32_t *el_chrom;   /* sorted order */
+    uint32_t *bucket; long long *chrom_bucket; long long n_bucket;
     long long *row2el;                   /* rmsk row -> sorted element index or -1 */
     /* host mirrors of the device results (filled by itx_sync_counts) */
     uint64_t cnt[13];

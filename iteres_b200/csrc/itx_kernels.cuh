@@ -1,16 +1,21 @@
 /* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
  *
- *   k_decode    K1  record-boundary discovery + bam1_core_t unpack + fragment logic, one thread per
- *                   stream chunk: the chunk's first record start is GUESSED structurally, the chunk is
- *                   walked along the block_size chain with 16-byte vector loads of the core, and every
- *                   record becomes one 16-byte tuple.         replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_decode_tiles  K1  record-boundary discovery + bam1_core_t unpack + fragment logic.  The stream is
+ *                   cut into spans ("chunks"); a warp takes spans from a work counter, GUESSES the span's first
+ *                   record start with a warp-wide structural test, then streams the span through a 4 x 2 KiB
+ *                   shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier, three tiles
+ *                   in flight).  One lane walks the block_size chain in shared memory, 32 records per round;
+ *                   all lanes then decode one record each from the ring and store 32 tuples with one
+ *                   coalesced 512-byte store.                replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_decode        the same contract with one thread per chunk reading global memory directly (kept for
+ *                   A/B measurement and as the repair path's walker).
  *   k_verify / k_fixup  the guess of chunk i must equal the chain exit of chunk i-1; otherwise the chunk
  *                   is re-walked from the true entry.  The tuples are therefore exactly the sequential
  *                   chain, whatever the guesses were.
- *   k_overlap   K2+K3  one lane per tuple: sorted-interval lower_bound + bounded backward walk in place
- *                   of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
+ *   k_overlap   K2+K3  one lane per tuple: position bucket + short lower_bound + bounded backward walk in
+ *                   place of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
  *                   counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
- *                   global atomics, and two u32 atomics per coverage difference array.
+ *                   reductions, and two u32 reductions per coverage difference array.
  *   k_finalize  prefix sums of the coverage difference arrays (one warp per subfamily).
  *   k_cpg       K4  CpG bedGraph rows against the same table (cpgBedGraphOverlapRepeat).
  *   k_query     overlap + selection for explicit queries (property tests).
@@ -26,9 +31,16 @@ struct itx_decode_args {
     itx_dev_opts o;
     itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
     unsigned long long *carry; uint32_t *winbad; uint32_t *status;
+    uint32_t *work;                        /* [0] span counter of k_decode_tiles, [1] chunk counter of k_overlap; zeroed by k_fixup */
 };
 
+/* fire-and-forget reductions (RED, no return value) */
+__device__ __forceinline__ void itx_red_u32(uint32_t *p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void itx_red_u64(unsigned long long *p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+/* sequential walk of one chunk from global memory: used by k_decode and by the repair path */
 __device__ __forceinline__ void itx_walk_chunk(const itx_decode_args &A, uint32_t i, unsigned long long p) {
+    const itx_src_global G{A.b};
     const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
     unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
     itx_tuple *out = A.tuples + (size_t)i * A.S;
@@ -36,10 +48,10 @@ __device__ __forceinline__ void itx_walk_chunk(const itx_decode_args &A, uint32_
     if (p < ITX_OFF_END) {
         while (p < hi) {
             if (p + 36 > A.len) { p = ITX_OFF_END; break; }
-            uint32_t x[9]; itx_load_core(A.b, p, x);
+            uint32_t x[9]; G.core(p, x);
             if ((int32_t)x[0] < 32 || p + 4 + (unsigned long long)x[0] > A.len) { p = ITX_OFF_END; break; }
             if (p + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);   /* record longer than the staged window */
-            if (n < A.S) out[n] = itx_decode_record(A.b, p, x, (uint32_t)(p - lo), A.tid, A.n_ref, A.o);
+            if (n < A.S) out[n] = itx_decode_record(G, p, x, (uint32_t)(p - lo), A.tid, A.n_ref, A.o);
             n++;
             p += 4 + (unsigned long long)x[0];
         }
@@ -54,9 +66,170 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
     if (hi > A.len) hi = A.len;
     unsigned long long p;
     if (i == 0) { p = *A.carry; *A.winbad = 0; }
-    else p = itx_speculate_entry(A.b, lo, hi, A.len, A.n_ref);
+    else p = itx_speculate_entry(itx_src_global{A.b}, lo, hi, A.len, A.n_ref);
     A.entry[i] = p;
     itx_walk_chunk(A, i, p);
+}
+
+/* ------------------------------------------------------------------ K1, TMA ring version */
+#define ITX_TILE 2048u
+#define ITX_TILE_SH 11
+#define ITX_RING_TILES 4u
+#define ITX_RING (ITX_TILE * ITX_RING_TILES)
+#define ITX_DW 8                           /* warps per CTA */
+#define ITX_DECODE_SMEM (ITX_DW * ITX_RING + ITX_DW * ITX_RING_TILES * 8 + ITX_DW * 32 * 4)
+
+__device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void itx_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void itx_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void itx_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool itx_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* bounded wait: a tile that never lands sets status bit 4 instead of hanging the device */
+__device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uint32_t *status) {
+    for (uint32_t spin = 0; spin < (1u << 26); spin++) if (itx_mbar_try_wait(bar, parity)) return true;
+    atomicOr(&status[0], 4u);
+    return false;
+}
+
+__global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decode_args A) {
+    extern __shared__ __align__(128) uint8_t itx_smem[];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint8_t *ring = itx_smem + w * ITX_RING;
+    uint32_t *pos = reinterpret_cast<uint32_t *>(itx_smem + ITX_DW * ITX_RING + ITX_DW * ITX_RING_TILES * 8) + w * 32;
+    const uint32_t ring_s = itx_smem_addr(ring);
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * ITX_RING) + w * ITX_RING_TILES * 8;
+    if (lane == 0) {
+        for (uint32_t s = 0; s < ITX_RING_TILES; s++) itx_mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
+    uint32_t parity = 0;                                   /* bit s = phase of ring slot s's barrier */
+    const itx_src_ring R{ring, ITX_RING - 1};
+    const itx_src_global G{A.b};
+    bool dead = false;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(A.work, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.nchunks || dead) break;
+        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+        /* 1. the span's first record start: known for the window's first span, guessed otherwise */
+        unsigned long long p;
+        if (i == 0) p = *A.carry;
+        else {
+            p = ITX_OFF_NONE;
+            for (unsigned long long base = lo; base < hi; base += 32) {
+                const unsigned long long q = base + lane;
+                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
+            }
+        }
+        if (lane == 0) A.entry[i] = p;
+        /* 2. stream the span through the ring */
+        itx_tuple *out = A.tuples + (size_t)i * A.S;
+        uint32_t n_out = 0;
+        if (p < ITX_OFF_END && p < hi) {
+            unsigned long long lim = hi + ITX_TILE; if (lim > A.len) lim = A.len;
+            const unsigned long long t_limit = (lim + ITX_TILE - 1) >> ITX_TILE_SH;       /* tiles [.., t_limit) may be fetched */
+            unsigned long long t_issued = p >> ITX_TILE_SH, t_wait = t_issued;
+            while (p < hi) {
+                const unsigned long long t0 = p >> ITX_TILE_SH;
+                unsigned long long need = t0 + 2; if (need > t_limit) need = t_limit;
+                __syncwarp();                                  /* every lane is done reading the slots about to be refilled */
+                if (t0 > t_issued) {                           /* jumped over everything in flight (a record larger than the ring) */
+                    for (; t_wait < t_issued; t_wait++) {
+                        const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                        if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
+                        parity ^= 1u << s;
+                    }
+                    t_wait = t_issued = t0;
+                }
+                if (t_wait < t0) {                             /* fetched but skipped tiles: retire them in order */
+                    for (; t_wait < t0 && t_wait < t_issued; t_wait++) {
+                        const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                        if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
+                        parity ^= 1u << s;
+                    }
+                }
+                for (;;) {
+                    /* fetch ahead: tile t may replace tile t-4 once that one has landed and been consumed */
+                    unsigned long long t_to = t0 + ITX_RING_TILES; if (t_to > t_limit) t_to = t_limit;
+                    if (t_to > t_wait + ITX_RING_TILES) t_to = t_wait + ITX_RING_TILES;
+                    if (t_issued < t_to) {
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            for (unsigned long long t = t_issued; t < t_to; t++) {
+                                const uint32_t s = (uint32_t)t & (ITX_RING_TILES - 1);
+                                const unsigned long long off = t << ITX_TILE_SH;
+                                unsigned long long nb = A.len - off;
+                                if (nb > ITX_TILE) nb = ITX_TILE;
+                                const uint32_t bytes = ((uint32_t)nb + 15u) & ~15u;   /* the buffer's 64 bytes of slack cover the round-up */
+                                itx_mbar_expect_tx(bar_s + 8 * s, bytes);
+                                itx_bulk_g2s(ring_s + s * ITX_TILE, A.b + off, bytes, bar_s + 8 * s);
+                            }
+                        }
+                        t_issued = t_to;
+                    }
+                    if (t_wait >= need) break;
+                    const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                    if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
+                    parity ^= 1u << s;
+                    t_wait++;
+                }
+                if (dead) break;
+                unsigned long long F = t_wait << ITX_TILE_SH; if (F > A.len) F = A.len;   /* bytes below F are in the ring */
+                /* 3. one lane walks the block_size chain inside the ring: up to 32 record starts */
+                uint32_t n = 0, flag = 0;                      /* flag 1: chain ended, 2: record does not fit the ring */
+                unsigned long long q = p;
+                if (lane == 0) {
+                    while (n < 32 && q < hi) {
+                        if (q + 36 > A.len) { flag = 1; break; }
+                        const uint32_t bs = R.u32(q);
+                        if ((int32_t)bs < 32 || q + 4 + (unsigned long long)bs > A.len) { flag = 1; break; }
+                        if (q + 4 + (unsigned long long)bs > F) { if (n == 0) flag = 2; break; }
+                        pos[n++] = (uint32_t)(q - lo);
+                        q += 4 + (unsigned long long)bs;
+                    }
+                }
+                n = __shfl_sync(0xffffffffu, n, 0); flag = __shfl_sync(0xffffffffu, flag, 0);
+                q = __shfl_sync(0xffffffffu, q, 0);
+                __syncwarp();
+                /* 4. every lane decodes one record out of the ring; one coalesced store of the tuples */
+                if (lane < n) {
+                    const uint32_t ro = pos[lane]; const unsigned long long rp = lo + ro;
+                    uint32_t x[9]; R.core(rp, x);
+                    const itx_tuple T = itx_decode_record(R, rp, x, ro, A.tid, A.n_ref, A.o);
+                    if (n_out + lane < A.S) *reinterpret_cast<uint4 *>(out + n_out + lane) = make_uint4(T.start, T.end, T.info, T.rec_off);
+                }
+                n_out += n;
+                p = q;
+                if (flag == 2) {                               /* a record larger than what the ring holds: decode it from global memory */
+                    uint32_t x[9]; G.core(p, x);
+                    if (p + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);
+                    if (lane == 0 && n_out < A.S) out[n_out] = itx_decode_record(G, p, x, (uint32_t)(p - lo), A.tid, A.n_ref, A.o);
+                    n_out += 1;
+                    p += 4 + (unsigned long long)x[0];
+                } else if (flag == 1) { p = ITX_OFF_END; break; }
+            }
+            /* retire what is still in flight before the ring is reused by the next span */
+            __syncwarp();
+            for (; t_wait < t_issued; t_wait++) {
+                const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
+                parity ^= 1u << s;
+            }
+        }
+        if (lane == 0) { A.exit_[i] = p; A.nrec[i] = n_out < A.S ? n_out : A.S; }
+    }
 }
 
 __global__ void k_verify(const itx_decode_args A) {
@@ -88,7 +261,7 @@ __global__ void k_fixup(const itx_decode_args A) {
         }
     }
     __syncwarp();
-    if (lane == 0) *A.carry = A.exit_[n - 1];
+    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; }
 }
 
 /* ------------------------------------------------------------------ overlap + accumulate */
@@ -99,6 +272,7 @@ struct itx_overlap_args {
     itx_dev_opts o;
     itx_trace *trace; unsigned long long trace_cap; const unsigned long long *rec_base;   /* trace != 0: per-record trace */
     long long *sel_out;                                                                  /* != 0: selected element per tuple slot */
+    uint32_t *work;
 };
 
 template <bool SMEM_HIST>
@@ -110,71 +284,75 @@ __global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
     if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
-    const uint32_t gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5), nw = gridDim.x * warps_per_block;
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t c[13];
 #pragma unroll
     for (int k = 0; k < 13; k++) c[k] = 0;
     const bool stat = A.o.filter == 0 && D.stat_mode;
-    for (uint32_t i = gw; i < A.nchunks; i += nw) {
+    const itx_src_global G{A.b};
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(A.work, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.nchunks) break;
         const uint32_t n = A.nrec[i];
         const itx_tuple *tp = A.tuples + (size_t)i * A.S;
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
         for (uint32_t j0 = 0; j0 < n; j0 += 32) {
             const uint32_t j = j0 + lane; const bool valid = j < n;
             itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
-            if (valid) { const uint4 v = *reinterpret_cast<const uint4 *>(tp + j); T.start = v.x; T.end = v.y; T.info = v.z; T.rec_off = v.w; }
+            if (valid) { const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(tp + j)); T.start = v.x; T.end = v.y; T.info = v.z; T.rec_off = v.w; }
             const uint32_t info = T.info;
             const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
-            c[0] += __popc(__ballot_sync(0xffffffffu, valid && !slot2));
-            c[1] += __popc(__ballot_sync(0xffffffffu, valid && slot2));
-            c[2] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_MAPPED) && !slot2));
-            c[3] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_MAPPED) && slot2));
-            c[4] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_USED) && !slot2));
-            c[5] += __popc(__ballot_sync(0xffffffffu, (info & ITX_F_USED) && slot2));
-            c[6] += __popc(__ballot_sync(0xffffffffu, frag));
-            const uint32_t mu = __popc(__ballot_sync(0xffffffffu, frag && uniq));
+            const uint32_t m_valid = __ballot_sync(0xffffffffu, valid), m_slot2 = __ballot_sync(0xffffffffu, slot2);
+            const uint32_t m_map = __ballot_sync(0xffffffffu, info & ITX_F_MAPPED), m_used = __ballot_sync(0xffffffffu, info & ITX_F_USED);
+            const uint32_t m_frag = __ballot_sync(0xffffffffu, frag), m_uniq = __ballot_sync(0xffffffffu, uniq);
+            c[0] += __popc(m_valid & ~m_slot2); c[1] += __popc(m_slot2);
+            c[2] += __popc(m_map & ~m_slot2);   c[3] += __popc(m_map & m_slot2);
+            c[4] += __popc(m_used & ~m_slot2);  c[5] += __popc(m_used & m_slot2);
+            c[6] += __popc(m_frag);
+            const uint32_t mu = __popc(m_frag & m_uniq);
             c[7] += mu; c[11] += mu;
             if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
-            long long sel = -1; bool diffsub = false;
+            long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
             const uint32_t chrom = info & ITX_CHROM_MASK;
             if (frag && chrom != ITX_CHROM_NONE) {
                 int32_t nhit; float tcov;
-                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov);
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov, &e);
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
                 if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
                     const unsigned long long p = lo + T.rec_off;
-                    uint32_t x[9]; itx_load_core(A.b, p, x);
+                    uint32_t x[9]; G.core(p, x);
                     uint32_t bad = 0;
-                    if (itx_mapped_to_diff_subfam(D, A.b, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) { diffsub = true; }
+                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
                     if (bad) atomicAdd(&D.status[2], bad);
                 }
             }
-            c[12] += __popc(__ballot_sync(0xffffffffu, diffsub));
             const bool counted = sel >= 0 && !diffsub;
-            c[9] += __popc(__ballot_sync(0xffffffffu, counted));
-            c[10] += __popc(__ballot_sync(0xffffffffu, counted && uniq));
+            const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+            c[12] += __popc(__ballot_sync(0xffffffffu, diffsub));
+            c[9] += __popc(m_cnt); c[10] += __popc(m_cnt & m_uniq);
             if (counted) {
                 if (stat) {
-                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
                     const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
                     if (SMEM_HIST) {
                         atomicAdd(&sh_hist[hs], 1u); atomicAdd(&sh_hist[hf], 1u); atomicAdd(&sh_hist[hc], 1u);
                         if (uniq) { atomicAdd(&sh_hist[hs + 1], 1u); atomicAdd(&sh_hist[hf + 1], 1u); atomicAdd(&sh_hist[hc + 1], 1u); }
                     } else {
-                        atomicAdd(&D.grp[hs], 1ull); atomicAdd(&D.grp[hf], 1ull); atomicAdd(&D.grp[hc], 1ull);
-                        if (uniq) { atomicAdd(&D.grp[hs + 1], 1ull); atomicAdd(&D.grp[hf + 1], 1ull); atomicAdd(&D.grp[hc + 1], 1ull); }
+                        itx_red_u64(&D.grp[hs], 1ull); itx_red_u64(&D.grp[hf], 1ull); itx_red_u64(&D.grp[hc], 1ull);
+                        if (uniq) { itx_red_u64(&D.grp[hs + 1], 1ull); itx_red_u64(&D.grp[hf + 1], 1ull); itx_red_u64(&D.grp[hc + 1], 1ull); }
                     }
                     const uint32_t L = D.sub_len[m.sub];
                     uint32_t ja, jb;
                     if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
                         const unsigned long long off = D.sub_bp_off[m.sub];
-                        atomicAdd(&D.bp_diff[off + ja], 1u); atomicAdd(&D.bp_diff[off + jb], 0xffffffffu);
-                        if (uniq) { atomicAdd(&D.bp_diff_u[off + ja], 1u); atomicAdd(&D.bp_diff_u[off + jb], 0xffffffffu); }
+                        itx_red_u32(&D.bp_diff[off + ja], 1u); itx_red_u32(&D.bp_diff[off + jb], 0xffffffffu);
+                        if (uniq) { itx_red_u32(&D.bp_diff_u[off + ja], 1u); itx_red_u32(&D.bp_diff_u[off + jb], 0xffffffffu); }
                     }
                 } else if (A.o.filter) {
-                    atomicAdd(&D.el_cnt[sel], 1u);
-                    if (uniq) atomicAdd(&D.el_cnt_u[sel], 1u);
+                    itx_red_u32(&D.el_cnt[sel], 1u);
+                    if (uniq) itx_red_u32(&D.el_cnt_u[sel], 1u);
                 }
             }
             if (A.sel_out && valid) A.sel_out[(size_t)i * A.S + j] = counted ? sel : -1;
@@ -183,8 +361,8 @@ __global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
                 if (r < A.trace_cap) {
                     itx_trace t;
                     t.start = frag ? T.start : 0; t.end = frag ? T.end : 0;
-                    t.tid = (int32_t)itx_ld_u32(A.b, lo + T.rec_off + 4);
-                    t.sel_row = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+                    t.tid = (int32_t)G.u32(lo + T.rec_off + 4);
+                    t.sel_row = sel >= 0 ? (int32_t)e.row : -1;
                     t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
                               ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
                     A.trace[r] = t;
@@ -197,8 +375,8 @@ __global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
         for (int k = 0; k < 13; k++) if (c[k]) atomicAdd(&sh_cnt[k], (unsigned long long)c[k]);
     }
     __syncthreads();
-    if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) atomicAdd(&D.cnt[threadIdx.x], sh_cnt[threadIdx.x]);
-    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) atomicAdd(&D.grp[t], (unsigned long long)v); }
+    if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], sh_cnt[threadIdx.x]);
+    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) itx_red_u64(&D.grp[t], (unsigned long long)v); }
 }
 
 /* prefix sums of the coverage difference arrays: one warp per subfamily */
@@ -229,7 +407,7 @@ __global__ void k_finalize(const itx_dev_index D, uint32_t *bp, uint32_t *bp_u) 
 __global__ void k_rec_base(const uint32_t *nrec, uint32_t n, unsigned long long *rec_base, unsigned long long *running) {
     __shared__ unsigned long long part[1024];
     const uint32_t t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t a = t * per, b = a + per < n ? a + per : n;
+    const uint32_t a = t * per < n ? t * per : n, b = a + per < n ? a + per : n;
     unsigned long long s = 0;
     for (uint32_t i = a; i < b; i++) s += nrec[i];
     part[t] = s;
@@ -244,10 +422,10 @@ __global__ void k_query(const itx_dev_index D, int32_t chrom, const uint32_t *st
                         int32_t *sel_row, int32_t *n_hits) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int32_t nh; float tcov;
-    long long sel = itx_find_select(D, chrom, start[i], end[i], &nh, &tcov);
+    int32_t nh; float tcov; itx_iv e; e.row = 0;
+    long long sel = itx_find_select(D, chrom, start[i], end[i], &nh, &tcov, &e);
     if (sel >= 0 && tcov < min_cov) sel = -1;
-    sel_row[i] = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+    sel_row[i] = sel >= 0 ? (int32_t)e.row : -1;
     if (n_hits) n_hits[i] = nh;
 }
 
@@ -260,17 +438,17 @@ struct itx_cpg_args {
 __global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
     const itx_dev_index &D = A.D;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long sel = -1; double sc = 0.0; uint32_t st = 0;
+    long long sel = -1; double sc = 0.0; uint32_t st = 0; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
     if (i < A.n) {
         const int32_t c = A.chrom[i];
-        if (c >= 0) { st = A.start[i]; sel = itx_find_head(D, c, st, A.end[i]); sc = A.score[i]; }
+        if (c >= 0) { st = A.start[i]; sel = itx_find_head(D, c, st, A.end[i], &e); sc = A.score[i]; }
     }
     const uint32_t m = __popc(__ballot_sync(0xffffffffu, sel >= 0));
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(A.in_repeat, (unsigned long long)m);
     if (sel < 0) return;
     if (A.filter) { atomicAdd(&D.el_cpg[sel], 1u); atomicAdd(&D.el_cpg_score[sel], sc); return; }
     if (!D.stat_mode) return;
-    const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+    const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
     const uint32_t gs = mt.sub, gf = (uint32_t)(D.n_sub + m2.fam), gc = (uint32_t)(D.n_sub + D.n_fam + m2.cla);
     atomicAdd(&D.grp_cpg[gs], 1u); atomicAdd(&D.grp_cpg_score[gs], sc);
     atomicAdd(&D.grp_cpg[gf], 1u); atomicAdd(&D.grp_cpg_score[gf], sc);

@@ -20,27 +20,15 @@
 
 #if defined(__CUDACC__)
 #define ITX_HD __host__ __device__ __forceinline__
+#define ITX_HDM __host__ __device__ __forceinline__
 #define ITX_HDN __host__ __device__ __noinline__
 #else
 #define ITX_HD static inline
+#define ITX_HDM inline
 #define ITX_HDN static
 #endif
 
-/* ------------------------------------------------------------------ unaligned little-endian loads */
-ITX_HD uint32_t itx_ldg32(const uint32_t *p) {
-#if defined(__CUDA_ARCH__)
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
-ITX_HD uint8_t itx_ldg8(const uint8_t *p) {
-#if defined(__CUDA_ARCH__)
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
+/* ------------------------------------------------------------------ byte sources */
 ITX_HD uint32_t itx_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(lo, hi, sh);
@@ -48,73 +36,113 @@ ITX_HD uint32_t itx_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
 }
-/* u32 at an arbitrary byte offset; may touch up to 3 bytes past off+4 (buffers carry 64 B of slack) */
-ITX_HD uint32_t itx_ld_u32(const uint8_t *b, uint64_t off) {
-    const uint32_t *w = (const uint32_t *)(b + (off & ~3ull));
-    uint32_t sh = (uint32_t)(off & 3) * 8;
-    uint32_t lo = itx_ldg32(w);
-    if (sh == 0) return lo;
-    return itx_funnel_r(lo, itx_ldg32(w + 1), sh);
-}
-
-/* block_size + the 32-byte core of the record at byte offset p, as nine u32:
- * x0 block_size, x1 refID, x2 pos, x3 bin<<16|mapq<<8|l_qname, x4 flag<<16|n_cigar, x5 l_seq, x6 mtid, x7 mpos, x8 isize.
- * Four 16-byte loads of the enclosing aligned window, then a byte realignment in registers. */
-ITX_HD void itx_load_core(const uint8_t *b, uint64_t p, uint32_t x[9]) {
-    uint32_t w[16];
-    uint32_t o = (uint32_t)(p & 15);
+/* The BAM stream in global memory, addressed by stream offset.  Unaligned reads may touch up to 15 bytes
+ * past the last byte asked for (stream buffers carry 64 bytes of slack). */
+struct itx_src_global {
+    const uint8_t *b;
+    ITX_HDM uint8_t u8(uint64_t off) const {
 #if defined(__CUDA_ARCH__)
-    const uint4 *v = (const uint4 *)(b + (p & ~15ull));
-    uint4 a0 = __ldg(v), a1 = __ldg(v + 1), a2 = __ldg(v + 2), a3 = make_uint4(0, 0, 0, 0);
-    if (o > 12) a3 = __ldg(v + 3);
-    w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
-    w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
+        return __ldg(b + off);
 #else
-    const uint32_t *v = (const uint32_t *)(b + (p & ~15ull));
-    for (int i = 0; i < 16; i++) w[i] = (i < 12 || o > 12) ? v[i] : 0;
+        return b[off];
 #endif
-    uint32_t q = o >> 2, sh = (o & 3) * 8;
-    uint32_t t[12];
+    }
+    ITX_HDM uint32_t w32(uint64_t aligned_off) const {
+#if defined(__CUDA_ARCH__)
+        return __ldg(reinterpret_cast<const uint32_t *>(b + aligned_off));
+#else
+        return *reinterpret_cast<const uint32_t *>(b + aligned_off);
+#endif
+    }
+    ITX_HDM uint32_t u32(uint64_t off) const {
+        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
+        const uint32_t lo = w32(a);
+        if (sh == 0) return lo;
+        return itx_funnel_r(lo, w32(a + 4), sh);
+    }
+    /* block_size + the 32-byte core of the record at p as nine u32 (x0 block_size, x1 refID, x2 pos,
+     * x3 bin<<16|mapq<<8|l_qname, x4 flag<<16|n_cigar, x5 l_seq, x6 mtid, x7 mpos, x8 isize): four 16-byte
+     * loads of the enclosing aligned window, then a byte realignment in registers */
+    ITX_HDM void core(uint64_t p, uint32_t x[9]) const {
+        uint32_t w[16];
+        const uint32_t o = (uint32_t)(p & 15);
+#if defined(__CUDA_ARCH__)
+        const uint4 *v = reinterpret_cast<const uint4 *>(b + (p & ~15ull));
+        const uint4 a0 = __ldg(v), a1 = __ldg(v + 1), a2 = __ldg(v + 2);
+        uint4 a3 = make_uint4(0, 0, 0, 0);
+        if (o > 12) a3 = __ldg(v + 3);
+        w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+        w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
+#else
+        const uint32_t *v = reinterpret_cast<const uint32_t *>(b + (p & ~15ull));
+        for (int i = 0; i < 16; i++) w[i] = (i < 12 || o > 12) ? v[i] : 0;
+#endif
+        const uint32_t q = o >> 2, sh = (o & 3) * 8;
+        uint32_t t[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) t[i] = itx_funnel_r(w[i], w[i + 1], sh);
+        for (int i = 0; i < 12; i++) t[i] = itx_funnel_r(w[i], w[i + 1], sh);
 #pragma unroll
-    for (int j = 0; j < 9; j++) x[j] = q == 0 ? t[j] : (q == 1 ? t[j + 1] : (q == 2 ? t[j + 2] : t[j + 3]));
-}
+        for (int j = 0; j < 9; j++) x[j] = q == 0 ? t[j] : (q == 1 ? t[j + 1] : (q == 2 ? t[j + 2] : t[j + 3]));
+    }
+};
+/* A power-of-two ring (shared memory on the device) holding stream bytes at (offset & mask). */
+struct itx_src_ring {
+    const uint8_t *ring; uint32_t mask;
+    ITX_HDM uint8_t u8(uint64_t off) const { return ring[(uint32_t)off & mask]; }
+    ITX_HDM uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(ring + ((uint32_t)aligned_off & mask)); }
+    ITX_HDM uint32_t u32(uint64_t off) const {
+        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
+        return itx_funnel_r(w32(a), w32(a + 4), sh);
+    }
+    ITX_HDM void core(uint64_t p, uint32_t x[9]) const {
+        const uint64_t a = p & ~3ull; const uint32_t sh = (uint32_t)(p & 3) * 8;
+        uint32_t w[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) w[i] = w32(a + 4u * i);
+#pragma unroll
+        for (int j = 0; j < 9; j++) x[j] = itx_funnel_r(w[j], w[j + 1], sh);
+    }
+};
 
 /* ------------------------------------------------------------------ record chain */
 /* Cheap structural test used ONLY to guess where a chunk's first record starts; the guess is checked
  * against the real chain afterwards (k_verify / k_fixup), so a wrong answer costs time, not exactness. */
-ITX_HD bool itx_plausible(const uint8_t *b, uint64_t p, uint64_t len, int32_t n_ref, uint64_t *next) {
+template <class Src>
+ITX_HD bool itx_plausible(const Src &S, uint64_t p, uint64_t len, int32_t n_ref, uint64_t *next) {
     if (p + 36 > len) return false;
-    uint32_t bs = itx_ld_u32(b, p);
+    uint32_t bs = S.u32(p);
     if (bs < 33u || bs > (1u << 26)) return false;
     if (p + 4 + (uint64_t)bs > len) return false;
-    int32_t tid = (int32_t)itx_ld_u32(b, p + 4);
+    int32_t tid = (int32_t)S.u32(p + 4);
     if (tid < -1 || tid >= n_ref) return false;
-    int32_t pos = (int32_t)itx_ld_u32(b, p + 8);
+    int32_t pos = (int32_t)S.u32(p + 8);
     if (pos < -1) return false;
-    uint32_t lq = itx_ld_u32(b, p + 12) & 0xff;
+    uint32_t lq = S.u32(p + 12) & 0xff;
     if (lq == 0) return false;
-    uint32_t nc = itx_ld_u32(b, p + 16) & 0xffff;
-    int32_t ls = (int32_t)itx_ld_u32(b, p + 20);
+    uint32_t nc = S.u32(p + 16) & 0xffff;
+    int32_t ls = (int32_t)S.u32(p + 20);
     if (ls < 0) return false;
-    int32_t mtid = (int32_t)itx_ld_u32(b, p + 24);
+    int32_t mtid = (int32_t)S.u32(p + 24);
     if (mtid < -1 || mtid >= n_ref) return false;
-    int32_t mpos = (int32_t)itx_ld_u32(b, p + 28);
+    int32_t mpos = (int32_t)S.u32(p + 28);
     if (mpos < -1) return false;
     uint64_t need = 32ull + lq + 4ull * nc + (uint64_t)((ls + 1) / 2) + (uint64_t)ls;
     if (need > bs) return false;
-    if (itx_ldg8(b + p + 36 + lq - 1) != 0) return false;          /* qname is NUL terminated */
+    if (S.u8(p + 36 + lq - 1) != 0) return false;          /* qname is NUL terminated */
     *next = p + 4 + bs;
     return true;
 }
-/* first offset in [lo, hi) that looks like a record start followed by another one (or by the end) */
-ITX_HD uint64_t itx_speculate_entry(const uint8_t *b, uint64_t lo, uint64_t hi, uint64_t len, int32_t n_ref) {
-    for (uint64_t p = lo; p < hi; p++) {
-        uint64_t nx, nx2;
-        if (!itx_plausible(b, p, len, n_ref, &nx)) continue;
-        if (nx == len || itx_plausible(b, nx, len, n_ref, &nx2)) return p;
-    }
+/* a record start followed by another one (or by the end of the stream) */
+template <class Src>
+ITX_HD bool itx_plausible2(const Src &S, uint64_t p, uint64_t len, int32_t n_ref) {
+    uint64_t nx, nx2;
+    if (!itx_plausible(S, p, len, n_ref, &nx)) return false;
+    return nx == len || itx_plausible(S, nx, len, n_ref, &nx2);
+}
+/* first offset in [lo, hi) that passes itx_plausible2 */
+template <class Src>
+ITX_HD uint64_t itx_speculate_entry(const Src &S, uint64_t lo, uint64_t hi, uint64_t len, int32_t n_ref) {
+    for (uint64_t p = lo; p < hi; p++) if (itx_plausible2(S, p, len, n_ref)) return p;
     return ITX_OFF_NONE;
 }
 
@@ -122,32 +150,34 @@ ITX_HD uint64_t itx_speculate_entry(const uint8_t *b, uint64_t lo, uint64_t hi, 
 /* bam_aux_get: returns the offset of the type byte of `tag`, or 0.  Faithful to the reference's skip
  * rule, including its quirk that the type is upper-cased before its size is looked up (so 'f' and
  * 'd' values are skipped as size 0).  Reads are bounded by aend. */
-ITX_HD uint64_t itx_aux_find(const uint8_t *b, uint64_t s, uint64_t aend, uint8_t t0, uint8_t t1) {
+template <class Src>
+ITX_HD uint64_t itx_aux_find(const Src &S, uint64_t s, uint64_t aend, uint8_t t0, uint8_t t1) {
     while (s + 1 < aend) {
-        uint8_t c0 = itx_ldg8(b + s), c1 = itx_ldg8(b + s + 1);
+        uint8_t c0 = S.u8(s), c1 = S.u8(s + 1);
         s += 2;
         if (c0 == t0 && c1 == t1) return s;
         if (s >= aend) break;
-        uint8_t ty = itx_ldg8(b + s);
+        uint8_t ty = S.u8(s);
         if (ty >= 'a' && ty <= 'z') ty = (uint8_t)(ty - 32);
         s += 1;
-        if (ty == 'Z' || ty == 'H') { while (s < aend && itx_ldg8(b + s) != 0) s++; s++; }
+        if (ty == 'Z' || ty == 'H') { while (s < aend && S.u8(s) != 0) s++; s++; }
         else if (ty == 'B') {
             if (s + 5 > aend) break;
-            uint8_t sub = itx_ldg8(b + s);
+            uint8_t sub = S.u8(s);
             uint32_t sz = (sub == 'C' || sub == 'c' || sub == 'A') ? 1u : (sub == 'S' || sub == 's') ? 2u : (sub == 'I' || sub == 'i' || sub == 'f') ? 4u : 0u;
-            uint32_t n = (uint32_t)itx_ldg8(b + s + 1) | (uint32_t)itx_ldg8(b + s + 2) << 8 | (uint32_t)itx_ldg8(b + s + 3) << 16 | (uint32_t)itx_ldg8(b + s + 4) << 24;
+            uint32_t n = (uint32_t)S.u8(s + 1) | (uint32_t)S.u8(s + 2) << 8 | (uint32_t)S.u8(s + 3) << 16 | (uint32_t)S.u8(s + 4) << 24;
             s += 5 + (uint64_t)sz * (uint64_t)(int64_t)(int32_t)n;
         } else s += (ty == 'C' || ty == 'A') ? 1u : (ty == 'S') ? 2u : (ty == 'I') ? 4u : 0u;
     }
     return 0;
 }
 /* bam_aux2i on the value whose type byte sits at offset s (0 -> 0) */
-ITX_HD int32_t itx_aux2i(const uint8_t *b, uint64_t s, uint64_t aend) {
+template <class Src>
+ITX_HD int32_t itx_aux2i(const Src &S, uint64_t s, uint64_t aend) {
     if (!s || s >= aend) return 0;
-    uint8_t ty = itx_ldg8(b + s); s++;
+    uint8_t ty = S.u8(s); s++;
     uint32_t v = 0;
-    for (int i = 0; i < 4; i++) if (s + (uint64_t)i < aend) v |= (uint32_t)itx_ldg8(b + s + i) << (8 * i);
+    for (int i = 0; i < 4; i++) if (s + (uint64_t)i < aend) v |= (uint32_t)S.u8(s + i) << (8 * i);
     if (ty == 'c') return (int32_t)(int8_t)(v & 0xff);
     if (ty == 'C') return (int32_t)(v & 0xff);
     if (ty == 's') return (int32_t)(int16_t)(v & 0xffff);
@@ -166,7 +196,8 @@ ITX_HD void itx_aux_range(uint64_t p, const uint32_t x[9], uint64_t *a0, uint64_
 /* ------------------------------------------------------------------ one BAM record -> tuple */
 ITX_HD uint32_t itx_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-ITX_HD itx_tuple itx_decode_record(const uint8_t *b, uint64_t p, const uint32_t x[9], uint32_t rec_off,
+template <class Src>
+ITX_HD itx_tuple itx_decode_record(const Src &S, uint64_t p, const uint32_t x[9], uint32_t rec_off,
                                    const itx_tidinfo *tidtab, int32_t n_ref, const itx_dev_opts &o) {
     itx_tuple T; T.start = 0; T.end = 0; T.info = ITX_CHROM_NONE; T.rec_off = rec_off;
     int32_t tid = (int32_t)x[1], pos = (int32_t)x[2];
@@ -203,7 +234,7 @@ ITX_HD itx_tuple itx_decode_record(const uint8_t *b, uint64_t p, const uint32_t 
             if (o.extension == 0 || minus) {
                 uint64_t cp = p + 36 + lq;
                 for (uint32_t k = 0; k < nc; k++) {
-                    uint32_t cg = itx_ld_u32(b, cp + 4ull * k), op = cg & 0xf;
+                    uint32_t cg = S.u32(cp + 4ull * k), op = cg & 0xf;
                     if (op == 0 || op == 2 || op == 3) tmpend += cg >> 4;
                 }
             }
@@ -219,7 +250,7 @@ ITX_HD itx_tuple itx_decode_record(const uint8_t *b, uint64_t p, const uint32_t 
              (ti.chrom < 0 ? ITX_CHROM_NONE : (uint32_t)ti.chrom);
     if (o.diffSubfam && ti.chrom >= 0) {
         uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
-        if (itx_aux_find(b, a0, aend, 'X', 'A')) T.info |= ITX_F_HASXA;
+        if (itx_aux_find(S, a0, aend, 'X', 'A')) T.info |= ITX_F_HASXA;
     }
     return T;
 }
@@ -233,7 +264,20 @@ ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
 }
 /* index range [*first, *upper) of the chromosome's sorted table that can overlap the clamped query [fs, fe):
  * upper = first element with start >= fe; the caller walks down while pmax > fs. */
-ITX_HD long long itx_upper(const itx_dev_index &D, long long lo, long long hi, int32_t fe) {
+ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, long long i) {
+#if defined(__CUDA_ARCH__)
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(D.iv + i));
+    itx_iv e; e.start = v.x; e.end = v.y; e.pmax = v.z; e.row = (uint32_t)v.w;
+    return e;
+#else
+    return D.iv[i];
+#endif
+}
+/* first element of chromosome c with start >= fe (0 < fe <= chromosome size): one position bucket, then a
+ * short binary search inside it */
+ITX_HD long long itx_upper(const itx_dev_index &D, int32_t c, int32_t fe) {
+    const uint32_t *bk = D.bucket + D.chrom_bucket[c] + (fe >> ITX_BSH);
+    long long lo = bk[0], hi = bk[1];
     while (lo < hi) {
         long long mid = (lo + hi) >> 1;
         if (D.iv[mid].start < fe) lo = mid + 1; else hi = mid;
@@ -246,93 +290,106 @@ ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
     float den = (float)(end - start);
     return den == 0.0f ? 0.0f : (float)r / den;
 }
-/* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.
- * Returns the sorted-table index of the selected element or -1; *n_hits = length of the hit list,
- * *tcov = coverage of the selected element.  Exact for any number of hits: the hit list is never
- * materialised; for n > 1 the candidates are re-walked once per list position. */
-ITX_HDN long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov) {
-    *n_hits = 0; *tcov = 0.0f;
-    int32_t fs = (int32_t)start, fe = (int32_t)end, cs = D.chrom_size[c];
-    if (fs < 0) fs = 0;
-    if (fe > cs) fe = cs;
-    if (fs >= fe) return -1;
-    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
-    long long up = itx_upper(D, lo, hi, fe);
-    int32_t n = 0; long long only = -1;
-    for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
-        itx_iv e = D.iv[i];
-        if (e.end > fs && e.start < e.end) { n++; only = i; }
-    }
-    *n_hits = n;
-    if (n == 0) return -1;
-    if (n == 1) { itx_iv e = D.iv[only]; *tcov = itx_cov(start, end, e.start, e.end); return only; }
+/* clamp the query to the chromosome the way binKeeperFind does; false = empty */
+ITX_HD bool itx_clamp(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *fs, int32_t *fe) {
+    int32_t a = (int32_t)start, b = (int32_t)end, cs = D.chrom_size[c];
+    if (a < 0) a = 0;
+    if (b > cs) b = cs;
+    *fs = a; *fe = b;
+    return a < b;
+}
+/* n > 1 hits: walk the list in binKeeper order (key ascending) without materialising it -- once per list
+ * position the candidates are re-walked for the smallest key above the previous one -- and apply the
+ * "last ascent" rule.  Rare (nested / abutting repeats), so it is kept out of line. */
+ITX_HDN long long itx_select_multi(const itx_dev_index &D, long long lo, long long up, int32_t fs, uint32_t start, uint32_t end, int32_t n, float *tcov) {
     uint64_t prev_key = 0; bool have_prev = false; float prev_cov = 0.0f, best_cov = 0.0f; long long sel = -1;
     for (int32_t k = 0; k < n; k++) {
-        uint64_t bk = ~0ull; long long bi = -1;
-        for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
-            itx_iv e = D.iv[i];
+        uint64_t bk = ~0ull; long long bi = -1; itx_iv be; be.start = be.end = 0; be.pmax = 0; be.row = 0;
+        for (long long i = up - 1; i >= lo; i--) {
+            const itx_iv e = itx_ld_iv(D, i);
+            if (!(e.pmax > fs)) break;
             if (e.end > fs && e.start < e.end) {
-                uint64_t key = itx_order_key(e.start, e.end, D.meta[i].row);
-                if ((!have_prev || key > prev_key) && key < bk) { bk = key; bi = i; }
+                const uint64_t key = itx_order_key(e.start, e.end, e.row);
+                if ((!have_prev || key > prev_key) && key < bk) { bk = key; bi = i; be = e; }
             }
         }
         if (bi < 0) break;
-        itx_iv e = D.iv[bi];
-        float cov = itx_cov(start, end, e.start, e.end);
+        const float cov = itx_cov(start, end, be.start, be.end);
         if (cov > prev_cov) { sel = bi; best_cov = cov; }
         prev_cov = cov; prev_key = bk; have_prev = true;
     }
     *tcov = best_cov;
     return sel;
 }
+/* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.  Returns the
+ * sorted-table index of the selected element or -1; *n_hits = length of binKeeperFind's hit list, *tcov =
+ * coverage of the selected element, *sel_iv = the element.  Exact for any number of hits. */
+ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
+    *n_hits = 0; *tcov = 0.0f;
+    int32_t fs, fe;
+    if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
+    const long long lo = D.chrom_off[c];
+    const long long up = itx_upper(D, c, fe);
+    int32_t n = 0; long long only = -1; itx_iv oe; oe.start = oe.end = 0; oe.pmax = 0; oe.row = 0;
+    for (long long i = up - 1; i >= lo; i--) {
+        const itx_iv e = itx_ld_iv(D, i);
+        if (!(e.pmax > fs)) break;
+        if (e.end > fs && e.start < e.end) { n++; only = i; oe = e; }
+    }
+    *n_hits = n;
+    if (n == 0) return -1;
+    if (n == 1) { *tcov = itx_cov(start, end, oe.start, oe.end); *sel_iv = oe; return only; }
+    const long long sel = itx_select_multi(D, lo, up, fs, start, end, n, tcov);
+    if (sel >= 0) *sel_iv = itx_ld_iv(D, sel);
+    return sel;
+}
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
-ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end) {
-    int32_t fs = (int32_t)start, fe = (int32_t)end, cs = D.chrom_size[c];
-    if (fs < 0) fs = 0;
-    if (fe > cs) fe = cs;
-    if (fs >= fe) return -1;
-    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
-    long long up = itx_upper(D, lo, hi, fe);
+ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
+    int32_t fs, fe;
+    if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
+    const long long lo = D.chrom_off[c];
+    const long long up = itx_upper(D, c, fe);
     uint64_t bk = ~0ull; long long bi = -1;
-    for (long long i = up - 1; i >= lo && D.pmax[i] > fs; i--) {
-        itx_iv e = D.iv[i];
+    for (long long i = up - 1; i >= lo; i--) {
+        const itx_iv e = itx_ld_iv(D, i);
+        if (!(e.pmax > fs)) break;
         if (e.end > fs && e.start < e.end) {
-            uint64_t key = itx_order_key(e.start, e.end, D.meta[i].row);
-            if (key < bk) { bk = key; bi = i; }
+            const uint64_t key = itx_order_key(e.start, e.end, e.row);
+            if (key < bk) { bk = key; bi = i; *sel_iv = e; }
         }
     }
     return bi;
 }
 /* does [s, e) on chromosome c touch any element whose case-folded subfamily differs from `fold`? */
 ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, int32_t e, int32_t fold) {
-    int32_t cs = D.chrom_size[c];
-    if (s < 0) s = 0;
-    if (e > cs) e = cs;
-    if (s >= e) return false;
-    long long lo = D.chrom_off[c], hi = D.chrom_off[c + 1];
-    long long up = itx_upper(D, lo, hi, e);
-    for (long long i = up - 1; i >= lo && D.pmax[i] > s; i--) {
-        itx_iv v = D.iv[i];
-        if (v.end > s && v.start < v.end && D.sub_fold[D.meta[i].sub] != fold) return true;
+    int32_t fs, fe;
+    if (!itx_clamp(D, c, (uint32_t)s, (uint32_t)e, &fs, &fe)) return false;
+    const long long lo = D.chrom_off[c];
+    const long long up = itx_upper(D, c, fe);
+    for (long long i = up - 1; i >= lo; i--) {
+        const itx_iv v = itx_ld_iv(D, i);
+        if (!(v.pmax > fs)) break;
+        if (v.end > fs && v.start < v.end && D.sub_fold[D.meta[i].sub] != fold) return true;
     }
     return false;
 }
 
 /* ------------------------------------------------------------------ XA:Z alternates (mapped2diffSubfam) */
 /* strtol(s, 0, 0) over the bytes [s, e): white space, sign, 0x / 0 prefixes, saturating; returned as (int) */
-ITX_HD int32_t itx_strtol_int(const uint8_t *b, uint64_t s, uint64_t e) {
-    while (s < e) { uint8_t c = itx_ldg8(b + s); if (c == ' ' || (c >= 9 && c <= 13)) s++; else break; }
+template <class Src>
+ITX_HD int32_t itx_strtol_int(const Src &S, uint64_t s, uint64_t e) {
+    while (s < e) { uint8_t c = S.u8(s); if (c == ' ' || (c >= 9 && c <= 13)) s++; else break; }
     bool neg = false;
-    if (s < e) { uint8_t c = itx_ldg8(b + s); if (c == '-') { neg = true; s++; } else if (c == '+') s++; }
+    if (s < e) { uint8_t c = S.u8(s); if (c == '-') { neg = true; s++; } else if (c == '+') s++; }
     uint32_t base = 10;
-    if (s < e && itx_ldg8(b + s) == '0') {
-        uint8_t c1 = s + 1 < e ? itx_ldg8(b + s + 1) : 0, c2 = s + 2 < e ? itx_ldg8(b + s + 2) : 0;
+    if (s < e && S.u8(s) == '0') {
+        uint8_t c1 = s + 1 < e ? S.u8(s + 1) : 0, c2 = s + 2 < e ? S.u8(s + 2) : 0;
         bool hex2 = (c2 >= '0' && c2 <= '9') || ((c2 | 32) >= 'a' && (c2 | 32) <= 'f');
         if ((c1 == 'x' || c1 == 'X') && hex2) { base = 16; s += 2; } else base = 8;
     }
     uint64_t acc = 0; bool sat = false;
     while (s < e) {
-        uint8_t c = itx_ldg8(b + s); uint32_t d;
+        uint8_t c = S.u8(s); uint32_t d;
         if (c >= '0' && c <= '9') d = c - '0'; else if ((c | 32) >= 'a' && (c | 32) <= 'z') d = (uint32_t)((c | 32) - 'a') + 10; else break;
         if (d >= base) break;
         if (acc > (0xffffffffffffffffull - d) / base) sat = true; else acc = acc * base + d;
@@ -344,56 +401,61 @@ ITX_HD int32_t itx_strtol_int(const uint8_t *b, uint64_t s, uint64_t e) {
     else v = (sat || acc > 0x7fffffffffffffffull) ? 0x7fffffffffffffffull : acc;
     return (int32_t)(uint32_t)v;
 }
-ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const uint8_t *b, uint64_t s, uint64_t e) {
+template <class Src>
+ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t s, uint64_t e) {
     uint32_t h = 2166136261u;
-    for (uint64_t i = s; i < e; i++) { h ^= itx_ldg8(b + i); h *= 16777619u; }
+    for (uint64_t i = s; i < e; i++) { h ^= S.u8(i); h *= 16777619u; }
     uint32_t m = D.cname_nslot - 1, i = h & m;
     for (;;) {
         uint32_t v = D.cname_slot[i];
         if (!v) return -1;
         const char *nm = D.cname_pool + D.cname_off[v - 1];
         uint64_t k = 0; bool same = true;
-        for (; s + k < e; k++) if ((uint8_t)nm[k] != itx_ldg8(b + s + k) || nm[k] == 0) { same = false; break; }
+        for (; s + k < e; k++) if ((uint8_t)nm[k] != S.u8(s + k) || nm[k] == 0) { same = false; break; }
         if (same && nm[k] == 0) return (int32_t)(v - 1);
         i = (i + 1) & m;
     }
 }
 /* record at p (core x) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start.
  * *malformed counts alternates without 4 comma separated fields (the reference asserts there). */
-ITX_HDN bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const uint8_t *b, uint64_t p, const uint32_t x[9],
+template <class Src>
+ITX_HDN bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const Src &S, uint64_t p, const uint32_t x[9],
                                        int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
     uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
-    uint64_t xa = itx_aux_find(b, a0, aend, 'X', 'A');
+    uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
     if (!xa || xa >= aend) return false;
-    uint8_t ty = itx_ldg8(b + xa);
+    uint8_t ty = S.u8(xa);
     if (ty != 'Z' && ty != 'H') return false;
-    int32_t nm = itx_aux2i(b, itx_aux_find(b, a0, aend, 'N', 'M'), aend);
+    int32_t nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
     uint64_t s = xa + 1, zend = s;
-    while (zend < aend && itx_ldg8(b + zend) != 0) zend++;
+    while (zend < aend && S.u8(zend) != 0) zend++;
     if (s == zend) return false;                                  /* chopByChar on "" gives no pieces */
     int pieces = 0;
     while (pieces < 100) {
         uint64_t pe = s;
-        while (pe < zend && itx_ldg8(b + pe) != ';') pe++;
+        while (pe < zend && S.u8(pe) != ';') pe++;
         pieces++;
         if (pe > s) {
-            /* up to 4 comma separated fields; the 4th stops at the next comma */
-            uint64_t fs[4], fe[4]; int nf = 0; uint64_t q = s;
-            while (nf < 4) {
-                fs[nf] = q;
-                while (q < pe && itx_ldg8(b + q) != ',') q++;
-                fe[nf] = q; nf++;
-                if (q >= pe) break;
-                q++;
+            /* up to 4 comma separated fields (chr, pos, cigar, nm); the 4th stops at the next comma */
+            uint64_t f0s = 0, f0e = 0, f1s = 0, f1e = 0, f3s = 0, f3e = 0, q = s; int nf = 0; bool more = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (more) {
+                    const uint64_t b0 = q;
+                    while (q < pe && S.u8(q) != ',') q++;
+                    if (k == 0) { f0s = b0; f0e = q; } else if (k == 1) { f1s = b0; f1e = q; } else if (k == 3) { f3s = b0; f3e = q; }
+                    nf++;
+                    if (q >= pe) more = false; else q++;
+                }
             }
             if (nf != 4) { if (malformed) (*malformed)++; }
             else {
-                int32_t nm2 = itx_strtol_int(b, fs[3], fe[3]);
+                int32_t nm2 = itx_strtol_int(S, f3s, f3e);
                 if (nm2 <= nm) {
-                    int32_t st = itx_strtol_int(b, fs[1], fe[1]);
+                    int32_t st = itx_strtol_int(S, f1s, f1e);
                     if (st < 0) st = (int32_t)(0u - (uint32_t)st);
                     int32_t en = (int32_t)((uint32_t)st + (uint32_t)qlen);
-                    int32_t c = itx_chrom_by_name(D, b, fs[0], fe[0]);
+                    int32_t c = itx_chrom_by_name(D, S, f0s, f0e);
                     if (c >= 0 && itx_any_other_subfam(D, c, st, en, sel_fold)) return true;
                 }
             }

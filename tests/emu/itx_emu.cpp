@@ -18,7 +18,7 @@ struct emu_index {
     std::vector<uint32_t> cname_slot, cname_off; std::vector<char> cname_pool;
     std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
     std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
-    std::vector<itx_trace> trace; uint64_t n_bad;
+    std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch;
 };
 
 extern "C" {
@@ -31,7 +31,7 @@ void emu_reset(emu_index *E) {
     std::fill(E->grp_cpg_score.begin(), E->grp_cpg_score.end(), 0.0); std::fill(E->bp_cpg.begin(), E->bp_cpg.end(), 0.0);
     std::fill(E->el_cpg_score.begin(), E->el_cpg_score.end(), 0.0);
     std::fill(E->status.begin(), E->status.end(), 0u);
-    E->trace.clear(); E->n_bad = 0;
+    E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0;
 }
 
 emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk, int filter_field, const char *filter_name, char *err) {
@@ -53,7 +53,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     E->u64.assign(16 + 2 * ng, 0); E->bp_diff.assign(ix.bp_len + 1, 0); E->bp_diff_u.assign(ix.bp_len + 1, 0);
     E->el_cnt.assign(ne + 1, 0); E->el_cnt_u.assign(ne + 1, 0); E->tid_seen.assign(ITX_MAX_TID_SEEN, 0); E->status.assign(8, 0);
     E->grp_cpg.assign(ng + 1, 0); E->el_cpg.assign(ne + 1, 0); E->grp_cpg_score.assign(ng + 1, 0.0); E->bp_cpg.assign(ix.bp_len + 1, 0.0); E->el_cpg_score.assign(ne + 1, 0.0);
-    D.iv = ix.iv; D.pmax = ix.pmax; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
+    D.iv = ix.iv; D.bucket = ix.bucket; D.chrom_bucket = ix.chrom_bucket; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
     D.n_chrom = nc; D.n_elem = ix.n_elem;
     D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data();
     D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix.stat_mode;
@@ -62,22 +62,45 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     D.el_cnt = E->el_cnt.data(); D.el_cnt_u = E->el_cnt_u.data();
     D.grp_cpg = E->grp_cpg.data(); D.el_cpg = E->el_cpg.data(); D.grp_cpg_score = E->grp_cpg_score.data(); D.bp_cpg = E->bp_cpg.data(); D.el_cpg_score = E->el_cpg_score.data();
     D.tid_unknown_seen = E->tid_seen.data(); D.status = E->status.data();
-    E->n_bad = 0;
+    E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0;
     return E;
 }
 void emu_free(emu_index *E) { if (!E) return; itx_host_index_free(&E->ix); delete E; }
 itx_index *emu_host_index(emu_index *E) { return &E->ix; }
 
-static void walk_chunk(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, uint64_t p, const itx_bam_header &h, const itx_dev_opts &o,
+/* the ring the TMA decode kernel reads records from: 4 tiles of 2 KiB addressed by (offset & 8191) */
+static const uint32_t EMU_TILE = 2048, EMU_RING = 8192;
+static void walk_chunk(emu_index *E, const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, uint64_t p, const itx_bam_header &h, const itx_dev_opts &o,
                        std::vector<itx_tuple> &out, uint64_t *exit_) {
+    const itx_src_global G{b};
+    alignas(16) static thread_local uint8_t ring[EMU_RING];
+    const itx_src_ring R{ring, EMU_RING - 1};
+    uint64_t ring_t0 = ~0ull;
     uint64_t hi = lo + C; if (hi > len) hi = len;
     out.clear();
     if (p < ITX_OFF_END) {
         while (p < hi) {
             if (p + 36 > len) { p = ITX_OFF_END; break; }
-            uint32_t x[9]; itx_load_core(b, p, x);
+            uint32_t x[9]; G.core(p, x);
             if ((int32_t)x[0] < 32 || p + 4 + (uint64_t)x[0] > len) { p = ITX_OFF_END; break; }
-            out.push_back(itx_decode_record(b, p, x, (uint32_t)(p - lo), h.tid, h.n_ref, o));
+            const itx_tuple T = itx_decode_record(G, p, x, (uint32_t)(p - lo), h.tid, h.n_ref, o);
+            out.push_back(T);
+            /* cross-check: the same record decoded out of the shared-memory ring layout */
+            const uint64_t t0 = p / EMU_TILE, F = (t0 + 2) * EMU_TILE;
+            if (p + 4 + (uint64_t)x[0] <= F) {
+                if (t0 != ring_t0) {
+                    for (uint64_t t = t0; t < t0 + 2; t++) {
+                        const uint64_t off = t * EMU_TILE; if (off >= len + 64) break;
+                        uint64_t nb = len + 64 - off; if (nb > EMU_TILE) nb = EMU_TILE;
+                        memcpy(ring + (off & (EMU_RING - 1)), b + off, nb);
+                    }
+                    ring_t0 = t0;
+                }
+                uint32_t y[9]; R.core(p, y);
+                const itx_tuple T2 = itx_decode_record(R, p, y, (uint32_t)(p - lo), h.tid, h.n_ref, o);
+                E->ring_checked++;
+                if (memcmp(x, y, sizeof x) != 0 || memcmp(&T, &T2, sizeof T) != 0 || R.u32(p) != x[0]) E->ring_mismatch++;
+            }
             p += 4 + (uint64_t)x[0];
         }
     }
@@ -98,19 +121,20 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
     /* K1: every chunk guesses its entry independently (chunk 0 knows it) */
     for (uint64_t i = 0; i < n; i++) {
         uint64_t lo = (k0 + i) * C, hi = lo + C; if (hi > len) hi = len;
-        uint64_t p = i == 0 ? h.hdr_len : itx_speculate_entry(bam, lo, hi, len, h.n_ref);
+        uint64_t p = i == 0 ? h.hdr_len : itx_speculate_entry(itx_src_global{bam}, lo, hi, len, h.n_ref);
         entry[i] = p;
-        walk_chunk(bam, len, lo, C, p, h, o, tup[i], &exit_[i]);
+        walk_chunk(E, bam, len, lo, C, p, h, o, tup[i], &exit_[i]);
     }
     /* verify + repair */
     for (uint64_t i = 1; i < n; i++) if (entry[i] != exit_[i - 1]) {
         E->n_bad++;
         entry[i] = exit_[i - 1];
-        walk_chunk(bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
+        walk_chunk(E, bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
     }
     /* K2 + K3 */
     unsigned long long *c = D.cnt;
     const bool stat = o.filter == 0 && D.stat_mode;
+    const itx_src_global G{bam};
     for (uint64_t i = 0; i < n; i++) {
         const uint64_t lo = (k0 + i) * C;
         for (size_t j = 0; j < tup[i].size(); j++) {
@@ -121,15 +145,15 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             if (info & ITX_F_USED) c[slot2 ? 5 : 4]++;
             if (frag) { c[6]++; if (uniq) { c[7]++; c[11]++; } }
             if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1;
-            long long sel = -1; bool diffsub = false;
+            long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
             const uint32_t chrom = info & ITX_CHROM_MASK;
             if (frag && chrom != ITX_CHROM_NONE) {
                 int32_t nh; float tcov;
-                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nh, &tcov);
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nh, &tcov, &e);
                 if (sel >= 0 && tcov < o.minCoverage) sel = -1;
                 if (sel >= 0 && o.diffSubfam && (info & ITX_F_HASXA)) {
-                    const uint64_t p = lo + T.rec_off; uint32_t x[9]; itx_load_core(bam, p, x); uint32_t bad = 0;
-                    if (itx_mapped_to_diff_subfam(D, bam, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                    const uint64_t p = lo + T.rec_off; uint32_t x[9]; G.core(p, x); uint32_t bad = 0;
+                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
                     D.status[2] += bad;
                 }
             }
@@ -138,7 +162,7 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             if (counted) {
                 c[9]++; if (uniq) c[10]++;
                 if (stat) {
-                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
                     const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
                     D.grp[hs]++; D.grp[hf]++; D.grp[hc]++;
                     if (uniq) { D.grp[hs + 1]++; D.grp[hf + 1]++; D.grp[hc + 1]++; }
@@ -152,8 +176,8 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             }
             if (want_trace) {
                 itx_trace t;
-                t.start = frag ? T.start : 0; t.end = frag ? T.end : 0; t.tid = (int32_t)itx_ld_u32(bam, lo + T.rec_off + 4);
-                t.sel_row = sel >= 0 ? (int32_t)D.meta[sel].row : -1;
+                t.start = frag ? T.start : 0; t.end = frag ? T.end : 0; t.tid = (int32_t)G.u32(lo + T.rec_off + 4);
+                t.sel_row = sel >= 0 ? (int32_t)e.row : -1;
                 t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
                           ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
                 E->trace.push_back(t);
@@ -191,14 +215,16 @@ uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
     return E->trace.size();
 }
 uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
+uint64_t emu_ring_checked(emu_index *E) { return E->ring_checked; }
+uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }
 
 int32_t emu_query(emu_index *E, const char *chrom, uint32_t start, uint32_t end, float min_cov, int32_t *n_hits) {
     int32_t c = itx_strtab_find(&E->ix.chroms, chrom); if (n_hits) *n_hits = 0;
     if (c < 0) return -1;
-    int32_t nh; float tcov; long long sel = itx_find_select(E->D, c, start, end, &nh, &tcov);
+    int32_t nh; float tcov; itx_iv e; e.row = 0; long long sel = itx_find_select(E->D, c, start, end, &nh, &tcov, &e);
     if (n_hits) *n_hits = nh;
     if (sel >= 0 && tcov < min_cov) sel = -1;
-    return sel >= 0 ? (int32_t)E->D.meta[sel].row : -1;
+    return sel >= 0 ? (int32_t)e.row : -1;
 }
 
 /* CpG rows in file order (the kernel k_cpg, sequentially) */
@@ -216,12 +242,13 @@ int emu_scan_cpg(emu_index *E, const char *bedgraph, int filter, uint32_t *n_lin
         int32_t c = itx_strtab_find(&ix.chroms, w[0]);
         uint32_t st = (uint32_t)strtol(w[1], NULL, 0), en = (uint32_t)strtol(w[2], NULL, 0); double sc = strtod(w[3], NULL);
         if (c < 0) continue;
-        long long sel = itx_find_head(D, c, st, en);
+        itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
+        long long sel = itx_find_head(D, c, st, en, &e);
         if (sel < 0) continue;
         inrep++;
         if (filter) { D.el_cpg[sel]++; D.el_cpg_score[sel] += sc; continue; }
         if (!D.stat_mode) continue;
-        const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel]; const itx_iv e = D.iv[sel];
+        const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
         const uint32_t gs = mt.sub, gf = (uint32_t)(D.n_sub + m2.fam), gc = (uint32_t)(D.n_sub + D.n_fam + m2.cla);
         D.grp_cpg[gs]++; D.grp_cpg_score[gs] += sc; D.grp_cpg[gf]++; D.grp_cpg_score[gf] += sc; D.grp_cpg[gc]++; D.grp_cpg_score[gc] += sc;
         const uint32_t L = D.sub_len[mt.sub]; uint32_t ja, jb;

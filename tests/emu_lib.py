@@ -30,6 +30,9 @@ def lib():
         L.emu_trace.argtypes = [vp, vp, u64]
         L.emu_n_bad.restype = u64
         L.emu_n_bad.argtypes = [vp]
+        for f in ("emu_ring_checked", "emu_ring_mismatch"):
+            getattr(L, f).restype = u64
+            getattr(L, f).argtypes = [vp]
         L.emu_query.restype = C.c_int32
         L.emu_query.argtypes = [vp, cp, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_int32)]
         L.emu_scan_cpg.argtypes = [vp, cp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), cp]
@@ -80,6 +83,10 @@ class EmuIndex(capi.IndexBase):
 
     def n_bad(self):
         return self.L.emu_n_bad(self.e)
+
+    def ring_check(self):
+        """(records re-decoded out of the shared-memory ring layout, mismatches against the global-memory decode)"""
+        return self.L.emu_ring_checked(self.e), self.L.emu_ring_mismatch(self.e)
 
     def scan_cpg(self, path, filter=0):
         a, b = C.c_uint32(0), C.c_uint32(0)

@@ -59,6 +59,8 @@ def test_emu_matches_oracle(case, worlds):
     cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
     assert cnt_e == cnt_o
     assert cnt_o[0] + cnt_o[1] == nrec and cnt_o[9] > 0
+    checked, mism = emu.ring_check()
+    assert checked >= nrec and mism == 0          # the TMA kernel's ring addressing decodes every record identically
     assert len(tr_e) == len(tr_o) == nrec
     for f in ("start", "end", "tid", "sel_row"):
         assert np.array_equal(tr_e[f], tr_o[f]), f
@@ -137,3 +139,23 @@ def test_reference_binary_matches_oracle_on_synthetic_bam(mode, n_units, args, w
     ix.close()
     for fn in ("out.iteres.subfamily.stat", "out.iteres.family.stat", "out.iteres.class.stat", "out.iteres.report", "out.iteres.wig", "out.iteres.unique.wig"):
         assert filecmp.cmp(str(rd / fn), str(od / fn), shallow=False), fn
+
+
+@pytest.mark.parametrize("chunk", [2048, 32768])
+def test_records_of_every_size(chunk, tmp_path):
+    """records from 60 bytes to 70 KB (longer than a chunk and than the decode ring): same counters and trace"""
+    import mixed_records
+    tabs = mixed_records.tables(str(tmp_path))
+    raw, nrec = mixed_records.make()
+    for kw in ({}, dict(extension=0, treat=1)):
+        ora = O.OracleIndex(*tabs)
+        cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
+        emu = emu_lib.EmuIndex(*tabs, chunk=chunk)
+        cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
+        assert cnt_e == cnt_o and cnt_o[9] > 0 and cnt_o[0] + cnt_o[1] == nrec
+        for f in ("start", "end", "tid", "sel_row"):
+            assert np.array_equal(tr_e[f], tr_o[f]), f
+        assert np.array_equal(tr_e["flags"] & ~np.uint32(8), tr_o["flags"] & ~np.uint32(8))
+        assert emu.ring_check()[1] == 0
+        ora.close()
+        emu.close()

@@ -106,8 +106,10 @@ def assert_same_tables(ix, ora):
                 assert np.array_equal(ix.coverage(i, u), want), (i, u)
 
 
+@pytest.mark.parametrize("chunk", [1024, 2048], ids=["thread_kernel", "tma_ring_kernel"])
 @pytest.mark.parametrize("case", SYN, ids=[c[0] for c in SYN])
-def test_cuda_path_matches_oracle(case, worlds):
+def test_cuda_path_matches_oracle(case, chunk, worlds):
+    """chunk 1024 runs k_decode (one thread per chunk); chunks that are whole 2 KiB tiles run k_decode_tiles"""
     name, shape, n_rmsk, mode, n_units, kw = case
     s, (cs, rs, rm), _ = worlds(shape, n_rmsk)
     buf, n, nrec = s.stream(mode, n_units)
@@ -115,7 +117,7 @@ def test_cuda_path_matches_oracle(case, worlds):
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
     ix = capi.Index(cs, rs, rm)
-    ix.tune(chunk_bytes=1024, window_bytes=1 << 20)          # many windows: the carry between windows is on the path
+    ix.tune(chunk_bytes=chunk, window_bytes=1 << 20)         # many windows: the carry between windows is on the path
     cnt_g, tr_g = ix.scan_stream(raw, capi.default_opts(**kw), trace=True)
     assert cnt_g == cnt_o
     assert len(tr_g) == len(tr_o) == nrec
@@ -128,7 +130,7 @@ def test_cuda_path_matches_oracle(case, worlds):
     ix.close()
 
 
-@pytest.mark.parametrize("chunk,window", [(256, 1 << 16), (448, 1 << 18), (4096, 1 << 30), (65536, 1 << 22)])
+@pytest.mark.parametrize("chunk,window", [(256, 1 << 16), (448, 1 << 18), (2048, 1 << 16), (4096, 1 << 30), (32768, 1 << 20), (65536, 1 << 22)])
 def test_chunk_and_window_size_never_change_the_answer(chunk, window, worlds):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     buf, n, nrec = s.stream(1, 60000)
@@ -256,4 +258,38 @@ def test_filter_mode_counts_per_locus(worlds):
     np.add.at(want, tr_o["sel_row"][counted], 1)
     assert np.array_equal(ix.elem_counts_by_row(), want)
     ora.close()
+    ix.close()
+
+
+@pytest.mark.parametrize("chunk,window", [(1024, 1 << 18), (2048, 1 << 18), (32768, 1 << 30), (65536, 1 << 20)])
+def test_records_of_every_size(chunk, window, tmp_path):
+    """records from 60 bytes to 70 KB: longer than a chunk (chunks without any record start), than the
+    decode ring (global-memory path inside k_decode_tiles, ring restart after the jump) and straddling windows"""
+    import mixed_records
+    tabs = mixed_records.tables(str(tmp_path))
+    raw, nrec = mixed_records.make()
+    for kw in ({}, dict(extension=0, treat=1)):
+        ora = O.OracleIndex(*tabs)
+        cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
+        ix = capi.Index(*tabs)
+        ix.tune(chunk_bytes=chunk, window_bytes=window)
+        cnt_g, tr_g = ix.scan_stream(raw, capi.default_opts(**kw), trace=True)
+        assert cnt_g == cnt_o and cnt_o[0] + cnt_o[1] == nrec
+        for f in ("start", "end", "tid", "sel_row"):
+            assert np.array_equal(tr_g[f], tr_o[f]), f
+        assert np.array_equal(tr_g["flags"] & ~np.uint32(8), tr_o["flags"] & ~np.uint32(8))
+        assert_same_tables(ix, ora)
+        ora.close()
+        ix.close()
+
+
+def test_window_smaller_than_a_record_is_refused(tmp_path):
+    import mixed_records
+    tabs = mixed_records.tables(str(tmp_path))
+    raw, nrec = mixed_records.make()
+    ix = capi.Index(*tabs)
+    ix.tune(chunk_bytes=2048, window_bytes=1 << 16)          # 64 KiB windows, 70 KB records
+    with pytest.raises(capi.ItxError) as e:
+        ix.scan_stream(raw, capi.default_opts())
+    assert e.value.code == -6 and "longer than the staged window" in str(e.value)
     ix.close()
