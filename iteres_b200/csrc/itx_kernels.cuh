@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decod
                         if (q + 36 > A.len) { flag = 1; break; }
                         const uint32_t bs = R.u32(q);
                         if ((int32_t)bs < 32 || q + 4 + (unsigned long long)bs > A.len) { flag = 1; break; }
+                        if (q + 4 + (unsigned long long)bs > A.avail) atomicOr(&A.status[0], 2u);     /* record longer than the staged window */
                         if (q + 4 + (unsigned long long)bs > F) { if (n == 0) flag = 2; break; }
                         pos[n++] = (uint32_t)(q - lo);
                         q += 4 + (unsigned long long)bs;
