@@ -37,6 +37,7 @@ struct itx_cuda {
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_tiles (TMA ring), 1: k_decode (thread per chunk) */
+    int tile_sh;                            /* 10 or 11: tile size of the TMA ring */
     itx_trace *d_trace; uint64_t trace_cap;
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
@@ -167,7 +168,10 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 8)); CKN(cudaMemset(cu->d_work, 0, 8));
-        CKN(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM));
+        CKN(cudaFuncSetAttribute(k_decode_tiles<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM(10)));
+        CKN(cudaFuncSetAttribute(k_decode_tiles<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM(11)));
+        CKN(cudaFuncSetAttribute(k_decode_tiles<10>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CKN(cudaFuncSetAttribute(k_decode_tiles<11>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
@@ -293,7 +297,9 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     CK(cudaMemsetAsync(cu->d_work, 0, 8, cu->stream));
     {   /* ITX_DECODE_KERNEL=thread selects the one-thread-per-chunk kernel (A/B measurement); chunks that are not whole tiles use it too */
         const char *v = getenv("ITX_DECODE_KERNEL");
-        cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_TILE) != 0) ? 1 : 0;
+        const char *ts = getenv("ITX_TILE_SH");
+        cu->tile_sh = (ts && atoi(ts) == 10) ? 10 : 11;
+        cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % (1u << cu->tile_sh)) != 0 || cu->C > (1u << 20)) ? 1 : 0;
         if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
     }
     if (ix->trace_cap) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
@@ -314,8 +320,9 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
         if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
         if (cu->decode_variant == 0) {
-            uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)cu->sm_count * 3u;
-            k_decode_tiles<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM, cu->stream>>>(A);
+            uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)cu->sm_count * (cu->tile_sh == 10 ? 4u : 3u);
+            if (cu->tile_sh == 10) k_decode_tiles<10><<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM(10), cu->stream>>>(A);
+            else k_decode_tiles<11><<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM(11), cu->stream>>>(A);
         } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
         k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
         k_fixup<<<1, 32, 0, cu->stream>>>(A);

@@ -72,12 +72,9 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
 }
 
 /* ------------------------------------------------------------------ K1, TMA ring version */
-#define ITX_TILE 2048u
-#define ITX_TILE_SH 11
 #define ITX_RING_TILES 4u
-#define ITX_RING (ITX_TILE * ITX_RING_TILES)
 #define ITX_DW 8                           /* warps per CTA */
-#define ITX_DECODE_SMEM (ITX_DW * ITX_RING + ITX_DW * ITX_RING_TILES * 8 + ITX_DW * 32 * 4)
+#define ITX_DECODE_SMEM(TILE_SH) (ITX_DW * (ITX_RING_TILES << (TILE_SH)) + ITX_DW * ITX_RING_TILES * 8 + ITX_DW * 32 * 4)
 
 __device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void itx_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -91,19 +88,27 @@ __device__ __forceinline__ bool itx_mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 /* bounded wait: a tile that never lands sets status bit 4 instead of hanging the device */
-__device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uint32_t *status) {
-    for (uint32_t spin = 0; spin < (1u << 26); spin++) if (itx_mbar_try_wait(bar, parity)) return true;
+__device__ __noinline__ bool itx_mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t *status) {
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) if (itx_mbar_try_wait(bar, parity)) return true;
     atomicOr(&status[0], 4u);
     return false;
 }
+__device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uint32_t *status) {
+    if (itx_mbar_try_wait(bar, parity)) return true;
+    return itx_mbar_wait_slow(bar, parity, status);
+}
 
-__global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decode_args A) {
+/* TILE_SH: log2 of the tile size (10 or 11); the ring holds 4 tiles per warp.  All offsets inside a span
+ * are 32-bit and relative to the span start `lo` (spans are at most 1 MiB). */
+template <uint32_t TILE_SH>
+__global__ void __launch_bounds__(ITX_DW * 32, TILE_SH == 10 ? 4 : 3) k_decode_tiles(const itx_decode_args A) {
+    constexpr uint32_t TILE = 1u << TILE_SH, RING = TILE * ITX_RING_TILES;
     extern __shared__ __align__(128) uint8_t itx_smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint8_t *ring = itx_smem + w * ITX_RING;
-    uint32_t *pos = reinterpret_cast<uint32_t *>(itx_smem + ITX_DW * ITX_RING + ITX_DW * ITX_RING_TILES * 8) + w * 32;
+    uint8_t *ring = itx_smem + w * RING;
+    uint32_t *pos = reinterpret_cast<uint32_t *>(itx_smem + ITX_DW * RING + ITX_DW * ITX_RING_TILES * 8) + w * 32;
     const uint32_t ring_s = itx_smem_addr(ring);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * ITX_RING) + w * ITX_RING_TILES * 8;
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * RING) + w * ITX_RING_TILES * 8;
     if (lane == 0) {
         for (uint32_t s = 0; s < ITX_RING_TILES; s++) itx_mbar_init(bar_s + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decod
     __syncwarp();
     if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
     uint32_t parity = 0;                                   /* bit s = phase of ring slot s's barrier */
-    const itx_src_ring R{ring, ITX_RING - 1};
+    const itx_src_ring R{ring, RING - 1};
     const itx_src_global G{A.b};
     bool dead = false;
     for (;;) {
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decod
         if (lane == 0) i = atomicAdd(A.work, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= A.nchunks || dead) break;
-        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;      /* a multiple of TILE */
         unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
         /* 1. the span's first record start: known for the window's first span, guessed otherwise */
         unsigned long long p;
@@ -138,67 +143,73 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decod
         itx_tuple *out = A.tuples + (size_t)i * A.S;
         uint32_t n_out = 0;
         if (p < ITX_OFF_END && p < hi) {
-            unsigned long long lim = hi + ITX_TILE; if (lim > A.len) lim = A.len;
-            const unsigned long long t_limit = (lim + ITX_TILE - 1) >> ITX_TILE_SH;       /* tiles [.., t_limit) may be fetched */
-            unsigned long long t_issued = p >> ITX_TILE_SH, t_wait = t_issued;
-            while (p < hi) {
-                const unsigned long long t0 = p >> ITX_TILE_SH;
-                unsigned long long need = t0 + 2; if (need > t_limit) need = t_limit;
+            /* span-relative 32-bit quantities */
+            const uint32_t hi32 = (uint32_t)(hi - lo), lo32 = (uint32_t)lo;                   /* ring addresses use the low bits of the stream offset */
+            const uint32_t tb = (uint32_t)(lo >> TILE_SH) & (ITX_RING_TILES - 1);             /* ring slot of the span's tile 0 */
+            const unsigned long long rest = A.len - lo, av = A.avail > lo ? A.avail - lo : 0;
+            const uint32_t len32 = rest > 0x7fffffffull ? 0x7fffffffu : (uint32_t)rest;     /* bytes of stream after lo (capped) */
+            const uint32_t av32 = av > 0x7fffffffull ? 0x7fffffffu : (uint32_t)av;
+            const bool capped = rest > 0x7fffffffull;
+            uint32_t lim = hi32 + TILE; if (lim > len32) lim = len32;
+            const uint32_t t_limit = (lim + TILE - 1) >> TILE_SH;                          /* tiles [.., t_limit) may be fetched */
+            uint32_t q32 = (uint32_t)(p - lo);
+            uint32_t t_issued = q32 >> TILE_SH, t_wait = t_issued;
+            for (;;) {
+                if (q32 >= hi32) { p = lo + q32; break; }
+                const uint32_t t0 = q32 >> TILE_SH;
+                uint32_t need = t0 + 2; if (need > t_limit) need = t_limit;
                 __syncwarp();                                  /* every lane is done reading the slots about to be refilled */
                 if (t0 > t_issued) {                           /* jumped over everything in flight (a record larger than the ring) */
                     for (; t_wait < t_issued; t_wait++) {
-                        const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                        const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
                         if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
                         parity ^= 1u << s;
                     }
                     t_wait = t_issued = t0;
                 }
-                if (t_wait < t0) {                             /* fetched but skipped tiles: retire them in order */
-                    for (; t_wait < t0 && t_wait < t_issued; t_wait++) {
-                        const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
-                        if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
-                        parity ^= 1u << s;
-                    }
+                for (; t_wait < t0 && t_wait < t_issued; t_wait++) {       /* fetched but skipped tiles: retire them in order */
+                    const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
+                    if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
+                    parity ^= 1u << s;
                 }
                 for (;;) {
                     /* fetch ahead: tile t may replace tile t-4 once that one has landed and been consumed */
-                    unsigned long long t_to = t0 + ITX_RING_TILES; if (t_to > t_limit) t_to = t_limit;
+                    uint32_t t_to = t0 + ITX_RING_TILES; if (t_to > t_limit) t_to = t_limit;
                     if (t_to > t_wait + ITX_RING_TILES) t_to = t_wait + ITX_RING_TILES;
                     if (t_issued < t_to) {
                         if (lane == 0) {
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            for (unsigned long long t = t_issued; t < t_to; t++) {
-                                const uint32_t s = (uint32_t)t & (ITX_RING_TILES - 1);
-                                const unsigned long long off = t << ITX_TILE_SH;
-                                unsigned long long nb = A.len - off;
-                                if (nb > ITX_TILE) nb = ITX_TILE;
-                                const uint32_t bytes = ((uint32_t)nb + 15u) & ~15u;   /* the buffer's 64 bytes of slack cover the round-up */
+                            for (uint32_t t = t_issued; t < t_to; t++) {
+                                const uint32_t s = (t + tb) & (ITX_RING_TILES - 1), off = t << TILE_SH;
+                                uint32_t nb = len32 - off; if (nb > TILE) nb = TILE;
+                                const uint32_t bytes = (nb + 15u) & ~15u;         /* the buffer's 64 bytes of slack cover the round-up */
                                 itx_mbar_expect_tx(bar_s + 8 * s, bytes);
-                                itx_bulk_g2s(ring_s + s * ITX_TILE, A.b + off, bytes, bar_s + 8 * s);
+                                itx_bulk_g2s(ring_s + s * TILE, A.b + lo + off, bytes, bar_s + 8 * s);
                             }
                         }
                         t_issued = t_to;
                     }
                     if (t_wait >= need) break;
-                    const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                    const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
                     if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
                     parity ^= 1u << s;
                     t_wait++;
                 }
                 if (dead) break;
-                unsigned long long F = t_wait << ITX_TILE_SH; if (F > A.len) F = A.len;   /* bytes below F are in the ring */
+                uint32_t F = t_wait << TILE_SH; if (F > len32) F = len32;       /* span-relative bytes below F are in the ring */
                 /* 3. one lane walks the block_size chain inside the ring: up to 32 record starts */
                 uint32_t n = 0, flag = 0;                      /* flag 1: chain ended, 2: record does not fit the ring */
-                unsigned long long q = p;
+                uint32_t q = q32;
                 if (lane == 0) {
-                    while (n < 32 && q < hi) {
-                        if (q + 36 > A.len) { flag = 1; break; }
-                        const uint32_t bs = R.u32(q);
-                        if ((int32_t)bs < 32 || q + 4 + (unsigned long long)bs > A.len) { flag = 1; break; }
-                        if (q + 4 + (unsigned long long)bs > A.avail) atomicOr(&A.status[0], 2u);     /* record longer than the staged window */
-                        if (q + 4 + (unsigned long long)bs > F) { if (n == 0) flag = 2; break; }
-                        pos[n++] = (uint32_t)(q - lo);
-                        q += 4 + (unsigned long long)bs;
+                    while (n < 32 && q < hi32) {
+                        if (q + 36 > len32) { flag = capped ? 2 : 1; break; }
+                        const uint32_t bs = R.u32(lo32 + q);
+                        const uint32_t e = q + 4 + bs;
+                        if ((int32_t)bs < 32 || e < q || e > len32) { flag = (capped && (int32_t)bs >= 32) ? 2 : 1; break; }
+                        if (e > av32) atomicOr(&A.status[0], 2u);                /* record longer than the staged window */
+                        if (e > F) { if (n == 0) flag = 2; break; }
+                        pos[n++] = q;
+                        q = e;
                     }
                 }
                 n = __shfl_sync(0xffffffffu, n, 0); flag = __shfl_sync(0xffffffffu, flag, 0);
@@ -206,25 +217,30 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tiles(const itx_decod
                 __syncwarp();
                 /* 4. every lane decodes one record out of the ring; one coalesced store of the tuples */
                 if (lane < n) {
-                    const uint32_t ro = pos[lane]; const unsigned long long rp = lo + ro;
-                    uint32_t x[9]; R.core(rp, x);
-                    const itx_tuple T = itx_decode_record(R, rp, x, ro, A.tid, A.n_ref, A.o);
-                    if (n_out + lane < A.S) *reinterpret_cast<uint4 *>(out + n_out + lane) = make_uint4(T.start, T.end, T.info, T.rec_off);
+                    const uint32_t ro = pos[lane];
+                    uint32_t x[9]; R.core(lo32 + ro, x);
+                    const itx_tuple T = itx_decode_record(R, lo32 + ro, x, ro, A.tid, A.n_ref, A.o);
+                    if (n_out + lane < A.S) __stcs(reinterpret_cast<uint4 *>(out + n_out + lane), make_uint4(T.start, T.end, T.info, T.rec_off));
                 }
                 n_out += n;
-                p = q;
+                q32 = q;
                 if (flag == 2) {                               /* a record larger than what the ring holds: decode it from global memory */
-                    uint32_t x[9]; G.core(p, x);
-                    if (p + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);
-                    if (lane == 0 && n_out < A.S) out[n_out] = itx_decode_record(G, p, x, (uint32_t)(p - lo), A.tid, A.n_ref, A.o);
+                    const unsigned long long pp = lo + q32;
+                    if (pp + 36 > A.len) { p = ITX_OFF_END; break; }
+                    uint32_t x[9]; G.core(pp, x);
+                    if ((int32_t)x[0] < 32 || pp + 4 + (unsigned long long)x[0] > A.len) { p = ITX_OFF_END; break; }
+                    if (pp + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);
+                    if (lane == 0 && n_out < A.S) out[n_out] = itx_decode_record(G, pp, x, q32, A.tid, A.n_ref, A.o);
                     n_out += 1;
-                    p += 4 + (unsigned long long)x[0];
+                    const unsigned long long nx = pp + 4 + (unsigned long long)x[0];
+                    if (nx - lo >= 0x7fffffffull || nx >= hi) { p = nx; break; }
+                    q32 = (uint32_t)(nx - lo);
                 } else if (flag == 1) { p = ITX_OFF_END; break; }
             }
             /* retire what is still in flight before the ring is reused by the next span */
             __syncwarp();
             for (; t_wait < t_issued; t_wait++) {
-                const uint32_t s = (uint32_t)t_wait & (ITX_RING_TILES - 1);
+                const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
                 if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
                 parity ^= 1u << s;
             }
