@@ -37,7 +37,7 @@ typedef struct {
  * chromosome; one 16-byte load per candidate.  `bucket` maps (chromosome, position >> ITX_BSH) to the
  * first element whose start is >= the bucket's first base, so a lower_bound only searches one bucket. */
 typedef struct { int32_t start, end, pmax; uint32_t row; } itx_iv;
-#define ITX_BSH 12
+#define ITX_BSH 10
 typedef struct { uint32_t cons_start, cons_end, row, sub; } itx_meta;     /* 16 B, one load */
 typedef struct { int32_t fam, cla; } itx_meta2;
 

@@ -1,21 +1,21 @@
 /* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
  *
- *   k_decode_tiles  K1  record-boundary discovery + bam1_core_t unpack + fragment logic.  The stream is
- *                   cut into spans ("chunks"); a warp takes spans from a work counter, GUESSES the span's first
- *                   record start with a warp-wide structural test, then streams the span through a 4 x 2 KiB
- *                   shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier, three tiles
- *                   in flight).  One lane walks the block_size chain in shared memory, 32 records per round;
- *                   all lanes then decode one record each from the ring and store 32 tuples with one
- *                   coalesced 512-byte store.                replaces bam_read1 / bam_calend / bam_aux_get
- *   k_decode        the same contract with one thread per chunk reading global memory directly (kept for
- *                   A/B measurement and as the repair path's walker).
- *   k_verify / k_fixup  the guess of chunk i must equal the chain exit of chunk i-1; otherwise the chunk
- *                   is re-walked from the true entry.  The tuples are therefore exactly the sequential
- *                   chain, whatever the guesses were.
+ *   k_chain      K1a  record-boundary discovery: the stream is cut into chunks; one thread per chunk GUESSES the
+ *                    first record start in its chunk with a structural test and walks the block_size prefix
+ *                    chain to the chunk end, storing every record offset.  Only the 4-byte block_size words are
+ *                    touched, so thousands of independent chains per SM hide the HBM latency.
+ *   k_verify / k_fixup  the guess of chunk i must equal the chain exit of chunk i-1; otherwise the chunk is
+ *                    re-walked from its true entry.  The offsets are therefore exactly the sequential chain,
+ *                    whatever the guesses were.
+ *   k_decode_pos K1b  bam1_core_t unpack + fragment logic: a warp per chunk stages the chunk (+1 KiB margin) in
+ *                    shared memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier), then every lane
+ *                    decodes one record out of shared memory and the warp stores 32 tuples with one coalesced
+ *                    512-byte store.                          replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_decode         K1a+K1b in one thread-per-chunk kernel reading global memory (A/B measurement only).
  *   k_overlap   K2+K3  one lane per tuple: position bucket + short lower_bound + bounded backward walk in
- *                   place of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
- *                   counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
- *                   reductions, and two u32 reductions per coverage difference array.
+ *                    place of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
+ *                    counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
+ *                    reductions, and two u32 reductions per coverage difference array.
  *   k_finalize  prefix sums of the coverage difference arrays (one warp per subfamily).
  *   k_cpg       K4  CpG bedGraph rows against the same table (cpgBedGraphOverlapRepeat).
  *   k_query     overlap + selection for explicit queries (property tests).
@@ -30,8 +30,9 @@ struct itx_decode_args {
     const itx_tidinfo *tid; int32_t n_ref;
     itx_dev_opts o;
     itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
+    uint32_t *pos;                         /* record offsets inside each chunk (S slots per chunk), written by k_chain */
     unsigned long long *carry; uint32_t *winbad; uint32_t *status;
-    uint32_t *work;                        /* [0] span counter of k_decode_tiles, [1] chunk counter of k_overlap; zeroed by k_fixup */
+    uint32_t *work;                        /* [0] k_chain, [1] k_overlap, [2] k_decode_pos chunk counters; zeroed by k_fixup / k_decode_pos */
 };
 
 /* fire-and-forget reductions (RED, no return value) */
@@ -71,10 +72,54 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
     itx_walk_chunk(A, i, p);
 }
 
-/* ------------------------------------------------------------------ K1, TMA ring version */
-#define ITX_RING_TILES 4u
+/* ------------------------------------------------------------------ K1a: the record chain */
+/* walk chunk i's chain from p: record offsets (relative to the chunk start) into pos, exit and count */
+__device__ __forceinline__ void itx_chain_chunk(const itx_decode_args &A, uint32_t i, unsigned long long p) {
+    const itx_src_global G{A.b};
+    const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+    unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+    uint32_t *out = A.pos + (size_t)i * A.S;
+    uint32_t n = 0;
+    if (p < ITX_OFF_END) {
+        while (p < hi) {
+            if (p + 36 > A.len) { p = ITX_OFF_END; break; }
+            const uint32_t bs = G.u32(p);
+            const unsigned long long e = p + 4 + (unsigned long long)bs;
+            if ((int32_t)bs < 32 || e > A.len) { p = ITX_OFF_END; break; }
+            if (e > A.avail) atomicOr(&A.status[0], 2u);                 /* record longer than the staged window */
+            if (n < A.S) out[n] = (uint32_t)(p - lo);
+            n++;
+            p = e;
+        }
+    }
+    A.exit_[i] = p; A.nrec[i] = n < A.S ? n : A.S;
+}
+/* persistent: a warp claims 32 consecutive chunks at a time */
+__global__ void __launch_bounds__(256) k_chain(const itx_decode_args A) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&A.work[0], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= A.nchunks) break;
+        const uint32_t i = base + lane;
+        if (i < A.nchunks) {
+            const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+            unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+            unsigned long long p;
+            if (i == 0) p = *A.carry;
+            else p = itx_speculate_entry(itx_src_global{A.b}, lo, hi, A.len, A.n_ref);
+            A.entry[i] = p;
+            itx_chain_chunk(A, i, p);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ K1b: decode out of TMA-staged shared memory */
 #define ITX_DW 8                           /* warps per CTA */
-#define ITX_DECODE_SMEM(TILE_SH) (ITX_DW * (ITX_RING_TILES << (TILE_SH)) + ITX_DW * ITX_RING_TILES * 8 + ITX_DW * 32 * 4)
+#define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
+#define ITX_DECODE_SMEM(C) (ITX_DW * ((C) + ITX_MARGIN) + ITX_DW * 8)
 
 __device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void itx_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -87,9 +132,9 @@ __device__ __forceinline__ bool itx_mbar_try_wait(uint32_t bar, uint32_t parity)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-/* bounded wait: a tile that never lands sets status bit 4 instead of hanging the device */
+/* bounded wait with back-off: a copy that never lands sets status bit 4 instead of hanging the device */
 __device__ __noinline__ bool itx_mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t *status) {
-    for (uint32_t spin = 0; spin < (1u << 24); spin++) if (itx_mbar_try_wait(bar, parity)) return true;
+    for (uint32_t spin = 0; spin < (1u << 22); spin++) { if (itx_mbar_try_wait(bar, parity)) return true; __nanosleep(64); }
     atomicOr(&status[0], 4u);
     return false;
 }
@@ -97,155 +142,83 @@ __device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uin
     if (itx_mbar_try_wait(bar, parity)) return true;
     return itx_mbar_wait_slow(bar, parity, status);
 }
+/* bytes [base32, base32 + n) of the stream, staged linearly in shared memory */
+struct itx_src_stage {
+    const uint8_t *buf; uint32_t base32;
+    __device__ __forceinline__ uint8_t u8(uint64_t off) const { return buf[(uint32_t)off - base32]; }
+    __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(buf + ((uint32_t)aligned_off - base32)); }
+    __device__ __forceinline__ uint32_t u32(uint64_t off) const {
+        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
+        return itx_funnel_r(w32(a), w32(a + 4), sh);
+    }
+    __device__ __forceinline__ void core(uint64_t p, uint32_t x[9]) const {
+        const uint64_t a = p & ~3ull; const uint32_t sh = (uint32_t)(p & 3) * 8;
+        uint32_t w[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) w[i] = w32(a + 4u * i);
+#pragma unroll
+        for (int j = 0; j < 9; j++) x[j] = itx_funnel_r(w[j], w[j + 1], sh);
+    }
+};
 
-/* TILE_SH: log2 of the tile size (10 or 11); the ring holds 4 tiles per warp.  All offsets inside a span
- * are 32-bit and relative to the span start `lo` (spans are at most 1 MiB). */
-template <uint32_t TILE_SH>
-__global__ void __launch_bounds__(ITX_DW * 32, TILE_SH == 10 ? 4 : 3) k_decode_tiles(const itx_decode_args A) {
-    constexpr uint32_t TILE = 1u << TILE_SH, RING = TILE * ITX_RING_TILES;
+__global__ void __launch_bounds__(ITX_DW * 32) k_decode_pos(const itx_decode_args A) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint8_t *ring = itx_smem + w * RING;
-    uint32_t *pos = reinterpret_cast<uint32_t *>(itx_smem + ITX_DW * RING + ITX_DW * ITX_RING_TILES * 8) + w * 32;
-    const uint32_t ring_s = itx_smem_addr(ring);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * RING) + w * ITX_RING_TILES * 8;
+    const uint32_t stage_bytes = A.C + ITX_MARGIN;
+    uint8_t *buf = itx_smem + w * stage_bytes;
+    const uint32_t buf_s = itx_smem_addr(buf);
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * stage_bytes) + w * 8;
     if (lane == 0) {
-        for (uint32_t s = 0; s < ITX_RING_TILES; s++) itx_mbar_init(bar_s + 8 * s, 1);
+        itx_mbar_init(bar_s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
-    uint32_t parity = 0;                                   /* bit s = phase of ring slot s's barrier */
-    const itx_src_ring R{ring, RING - 1};
+    uint32_t parity = 0;
     const itx_src_global G{A.b};
-    bool dead = false;
     for (;;) {
         uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(A.work, 1u);
+        if (lane == 0) i = atomicAdd(&A.work[2], 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= A.nchunks || dead) break;
-        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;      /* a multiple of TILE */
-        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-        /* 1. the span's first record start: known for the window's first span, guessed otherwise */
-        unsigned long long p;
-        if (i == 0) p = *A.carry;
-        else {
-            p = ITX_OFF_NONE;
-            for (unsigned long long base = lo; base < hi; base += 32) {
-                const unsigned long long q = base + lane;
-                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
-            }
+        if (i >= A.nchunks) break;
+        const uint32_t n = A.nrec[i];
+        if (n == 0) continue;
+        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+        /* stage [lo, lo + C + margin) (clipped to the stream, rounded up to 16 inside the buffer's slack) */
+        unsigned long long rest = A.len - lo;
+        uint32_t nb = rest > stage_bytes ? stage_bytes : (uint32_t)rest;
+        const uint32_t bytes = (nb + 15u) & ~15u;
+        __syncwarp();                                      /* every lane is done reading the previous chunk */
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            itx_mbar_expect_tx(bar_s, bytes);
+            itx_bulk_g2s(buf_s, A.b + lo, bytes, bar_s);
         }
-        if (lane == 0) A.entry[i] = p;
-        /* 2. stream the span through the ring */
+        const uint32_t *pp = A.pos + (size_t)i * A.S;
         itx_tuple *out = A.tuples + (size_t)i * A.S;
-        uint32_t n_out = 0;
-        if (p < ITX_OFF_END && p < hi) {
-            /* span-relative 32-bit quantities */
-            const uint32_t hi32 = (uint32_t)(hi - lo), lo32 = (uint32_t)lo;                   /* ring addresses use the low bits of the stream offset */
-            const uint32_t tb = (uint32_t)(lo >> TILE_SH) & (ITX_RING_TILES - 1);             /* ring slot of the span's tile 0 */
-            const unsigned long long rest = A.len - lo, av = A.avail > lo ? A.avail - lo : 0;
-            const uint32_t len32 = rest > 0x7fffffffull ? 0x7fffffffu : (uint32_t)rest;     /* bytes of stream after lo (capped) */
-            const uint32_t av32 = av > 0x7fffffffull ? 0x7fffffffu : (uint32_t)av;
-            const bool capped = rest > 0x7fffffffull;
-            uint32_t lim = hi32 + TILE; if (lim > len32) lim = len32;
-            const uint32_t t_limit = (lim + TILE - 1) >> TILE_SH;                          /* tiles [.., t_limit) may be fetched */
-            uint32_t q32 = (uint32_t)(p - lo);
-            uint32_t t_issued = q32 >> TILE_SH, t_wait = t_issued;
-            for (;;) {
-                if (q32 >= hi32) { p = lo + q32; break; }
-                const uint32_t t0 = q32 >> TILE_SH;
-                uint32_t need = t0 + 2; if (need > t_limit) need = t_limit;
-                __syncwarp();                                  /* every lane is done reading the slots about to be refilled */
-                if (t0 > t_issued) {                           /* jumped over everything in flight (a record larger than the ring) */
-                    for (; t_wait < t_issued; t_wait++) {
-                        const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
-                        if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
-                        parity ^= 1u << s;
-                    }
-                    t_wait = t_issued = t0;
+        uint32_t ro = lane < n ? __ldcs(pp + lane) : 0u;   /* the first offsets travel while the tile lands */
+        if (!itx_mbar_wait(bar_s, parity, A.status)) break;
+        parity ^= 1u;
+        const itx_src_stage R{buf, (uint32_t)lo};
+        for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            if (j0) ro = j < n ? __ldcs(pp + j) : 0u;
+            if (j < n) {
+                itx_tuple T;
+                bool staged = false;
+                if (ro + 40u <= nb) {
+                    const uint32_t bs = R.u32((uint32_t)lo + ro);
+                    staged = (unsigned long long)ro + 4ull + bs <= nb;
                 }
-                for (; t_wait < t0 && t_wait < t_issued; t_wait++) {       /* fetched but skipped tiles: retire them in order */
-                    const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
-                    if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
-                    parity ^= 1u << s;
+                if (staged) {
+                    uint32_t x[9]; R.core((uint32_t)lo + ro, x);
+                    T = itx_decode_record(R, (uint32_t)lo + ro, x, ro, A.tid, A.n_ref, A.o);
+                } else {                                   /* the record runs past the staged bytes: read it from global memory */
+                    uint32_t x[9]; G.core(lo + ro, x);
+                    T = itx_decode_record(G, lo + ro, x, ro, A.tid, A.n_ref, A.o);
                 }
-                for (;;) {
-                    /* fetch ahead: tile t may replace tile t-4 once that one has landed and been consumed */
-                    uint32_t t_to = t0 + ITX_RING_TILES; if (t_to > t_limit) t_to = t_limit;
-                    if (t_to > t_wait + ITX_RING_TILES) t_to = t_wait + ITX_RING_TILES;
-                    if (t_issued < t_to) {
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            for (uint32_t t = t_issued; t < t_to; t++) {
-                                const uint32_t s = (t + tb) & (ITX_RING_TILES - 1), off = t << TILE_SH;
-                                uint32_t nb = len32 - off; if (nb > TILE) nb = TILE;
-                                const uint32_t bytes = (nb + 15u) & ~15u;         /* the buffer's 64 bytes of slack cover the round-up */
-                                itx_mbar_expect_tx(bar_s + 8 * s, bytes);
-                                itx_bulk_g2s(ring_s + s * TILE, A.b + lo + off, bytes, bar_s + 8 * s);
-                            }
-                        }
-                        t_issued = t_to;
-                    }
-                    if (t_wait >= need) break;
-                    const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
-                    if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
-                    parity ^= 1u << s;
-                    t_wait++;
-                }
-                if (dead) break;
-                uint32_t F = t_wait << TILE_SH; if (F > len32) F = len32;       /* span-relative bytes below F are in the ring */
-                /* 3. one lane walks the block_size chain inside the ring: up to 32 record starts */
-                uint32_t n = 0, flag = 0;                      /* flag 1: chain ended, 2: record does not fit the ring */
-                uint32_t q = q32;
-                if (lane == 0) {
-                    while (n < 32 && q < hi32) {
-                        if (q + 36 > len32) { flag = capped ? 2 : 1; break; }
-                        const uint32_t bs = R.u32(lo32 + q);
-                        const uint32_t e = q + 4 + bs;
-                        if ((int32_t)bs < 32 || e < q || e > len32) { flag = (capped && (int32_t)bs >= 32) ? 2 : 1; break; }
-                        if (e > av32) atomicOr(&A.status[0], 2u);                /* record longer than the staged window */
-                        if (e > F) { if (n == 0) flag = 2; break; }
-                        pos[n++] = q;
-                        q = e;
-                    }
-                }
-                n = __shfl_sync(0xffffffffu, n, 0); flag = __shfl_sync(0xffffffffu, flag, 0);
-                q = __shfl_sync(0xffffffffu, q, 0);
-                __syncwarp();
-                /* 4. every lane decodes one record out of the ring; one coalesced store of the tuples */
-                if (lane < n) {
-                    const uint32_t ro = pos[lane];
-                    uint32_t x[9]; R.core(lo32 + ro, x);
-                    const itx_tuple T = itx_decode_record(R, lo32 + ro, x, ro, A.tid, A.n_ref, A.o);
-                    if (n_out + lane < A.S) __stcs(reinterpret_cast<uint4 *>(out + n_out + lane), make_uint4(T.start, T.end, T.info, T.rec_off));
-                }
-                n_out += n;
-                q32 = q;
-                if (flag == 2) {                               /* a record larger than what the ring holds: decode it from global memory */
-                    const unsigned long long pp = lo + q32;
-                    if (pp + 36 > A.len) { p = ITX_OFF_END; break; }
-                    uint32_t x[9]; G.core(pp, x);
-                    if ((int32_t)x[0] < 32 || pp + 4 + (unsigned long long)x[0] > A.len) { p = ITX_OFF_END; break; }
-                    if (pp + 4 + (unsigned long long)x[0] > A.avail) atomicOr(&A.status[0], 2u);
-                    if (lane == 0 && n_out < A.S) out[n_out] = itx_decode_record(G, pp, x, q32, A.tid, A.n_ref, A.o);
-                    n_out += 1;
-                    const unsigned long long nx = pp + 4 + (unsigned long long)x[0];
-                    if (nx - lo >= 0x7fffffffull || nx >= hi) { p = nx; break; }
-                    q32 = (uint32_t)(nx - lo);
-                } else if (flag == 1) { p = ITX_OFF_END; break; }
-            }
-            /* retire what is still in flight before the ring is reused by the next span */
-            __syncwarp();
-            for (; t_wait < t_issued; t_wait++) {
-                const uint32_t s = (t_wait + tb) & (ITX_RING_TILES - 1);
-                if (!itx_mbar_wait(bar_s + 8 * s, (parity >> s) & 1u, A.status)) dead = true;
-                parity ^= 1u << s;
+                __stcs(reinterpret_cast<uint4 *>(out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
             }
         }
-        if (lane == 0) { A.exit_[i] = p; A.nrec[i] = n_out < A.S ? n_out : A.S; }
     }
 }
 
@@ -269,7 +242,7 @@ __global__ void k_fixup(const itx_decode_args A) {
             if (lane == 0) {
                 unsigned long long e = A.exit_[j - 1];
                 A.entry[j] = e;
-                itx_walk_chunk(A, j, e);
+                if (A.pos) itx_chain_chunk(A, j, e); else itx_walk_chunk(A, j, e);
                 atomicAdd(&A.status[1], 1u);
                 __threadfence();
             }
@@ -278,7 +251,7 @@ __global__ void k_fixup(const itx_decode_args A) {
         }
     }
     __syncwarp();
-    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; }
+    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; A.work[2] = 0; }
 }
 
 /* ------------------------------------------------------------------ overlap + accumulate */

@@ -256,14 +256,22 @@ ITX_HD itx_tuple itx_decode_record(const Src &S, uint64_t p, const uint32_t x[9]
 }
 
 /* ------------------------------------------------------------------ interval lookup */
-/* list-order key of binKeeperFind's result: level 5->0, bin high->low, rmsk row old->new */
-ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
-    int32_t a = s >> 17, z = (e - 1) >> 17; uint32_t l = 0;
-    while (a != z && l < 5) { a >>= 3; z >>= 3; l++; }
-    return ((uint64_t)(5u - l) << 48) | ((uint64_t)(0xffffu - (uint32_t)a) << 32) | (uint64_t)row;
+/* list-order key of binKeeperFind's result: level 5->0, bin high->low, rmsk row old->new.  The level is
+ * the smallest l with (s >> (17+3l)) == ((e-1) >> (17+3l)), i.e. ceil(bitlength((s ^ (e-1)) >> 17) / 3). */
+ITX_HD uint32_t itx_clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
 }
-/* index range [*first, *upper) of the chromosome's sorted table that can overlap the clamped query [fs, fe):
- * upper = first element with start >= fe; the caller walks down while pmax > fs. */
+ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
+    const uint32_t x = ((uint32_t)s ^ (uint32_t)(e - 1)) >> 17;
+    uint32_t l = (32u - itx_clz32(x) + 2u) / 3u;
+    if (l > 5u) l = 5u;
+    const uint32_t a = (uint32_t)s >> (17u + 3u * l);
+    return ((uint64_t)(5u - l) << 48) | ((uint64_t)(0xffffu - a) << 32) | (uint64_t)row;
+}
 ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, long long i) {
 #if defined(__CUDA_ARCH__)
     const int4 v = __ldg(reinterpret_cast<const int4 *>(D.iv + i));
@@ -323,25 +331,53 @@ ITX_HDN long long itx_select_multi(const itx_dev_index &D, long long lo, long lo
 }
 /* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.  Returns the
  * sorted-table index of the selected element or -1; *n_hits = length of binKeeperFind's hit list, *tcov =
- * coverage of the selected element, *sel_iv = the element.  Exact for any number of hits. */
+ * coverage of the selected element, *sel_iv = the element.  Up to four hits are kept in registers and
+ * visited in list order (order key ascending); longer lists take itx_select_multi.  Exact for any n. */
 ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     *n_hits = 0; *tcov = 0.0f;
     int32_t fs, fe;
     if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
     const long long lo = D.chrom_off[c];
     const long long up = itx_upper(D, c, fe);
-    int32_t n = 0; long long only = -1; itx_iv oe; oe.start = oe.end = 0; oe.pmax = 0; oe.row = 0;
+    int32_t n = 0; long long i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    itx_iv e0, e1, e2, e3; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0; e2 = e0; e3 = e0;
     for (long long i = up - 1; i >= lo; i--) {
         const itx_iv e = itx_ld_iv(D, i);
         if (!(e.pmax > fs)) break;
-        if (e.end > fs && e.start < e.end) { n++; only = i; oe = e; }
+        if (e.end > fs && e.start < e.end) {
+            if (n == 0) { i0 = i; e0 = e; } else if (n == 1) { i1 = i; e1 = e; } else if (n == 2) { i2 = i; e2 = e; } else if (n == 3) { i3 = i; e3 = e; }
+            n++;
+        }
     }
     *n_hits = n;
     if (n == 0) return -1;
-    if (n == 1) { *tcov = itx_cov(start, end, oe.start, oe.end); *sel_iv = oe; return only; }
-    const long long sel = itx_select_multi(D, lo, up, fs, start, end, n, tcov);
-    if (sel >= 0) *sel_iv = itx_ld_iv(D, sel);
-    return sel;
+    if (n == 1) { *tcov = itx_cov(start, end, e0.start, e0.end); *sel_iv = e0; return i0; }
+    if (n > 4) {
+        const long long sel = itx_select_multi(D, lo, up, fs, start, end, n, tcov);
+        if (sel >= 0) *sel_iv = itx_ld_iv(D, sel);
+        return sel;
+    }
+    const uint64_t NOKEY = ~0ull;
+    uint64_t k0 = itx_order_key(e0.start, e0.end, e0.row), k1 = itx_order_key(e1.start, e1.end, e1.row);
+    uint64_t k2 = n > 2 ? itx_order_key(e2.start, e2.end, e2.row) : NOKEY, k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
+    const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
+    const float c2 = n > 2 ? itx_cov(start, end, e2.start, e2.end) : 0.0f, c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
+    float prev = 0.0f, best = 0.0f; int32_t sel = -1;
+    for (int32_t step = 0; step < n; step++) {
+        /* the unvisited hit with the smallest key */
+        int32_t j = 0; uint64_t km = k0;
+        if (k1 < km) { km = k1; j = 1; }
+        if (k2 < km) { km = k2; j = 2; }
+        if (k3 < km) { km = k3; j = 3; }
+        const float cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+        if (cj > prev) { sel = j; best = cj; }
+        prev = cj;
+        if (j == 0) k0 = NOKEY; else if (j == 1) k1 = NOKEY; else if (j == 2) k2 = NOKEY; else k3 = NOKEY;
+    }
+    *tcov = best;
+    if (sel < 0) return -1;
+    *sel_iv = sel == 0 ? e0 : (sel == 1 ? e1 : (sel == 2 ? e2 : e3));
+    return sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3));
 }
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
 ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
