@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) k_chain(const itx_decode_args A) {
 
 /* ------------------------------------------------------------------ K1b: decode out of TMA-staged shared memory */
 #define ITX_DW 8                           /* warps per CTA */
+#define ITX_CLAIM 16u                      /* chunks claimed per atomic on the work counters */
 #define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
 #define ITX_DECODE_SMEM(C) (ITX_DW * ((C) + ITX_MARGIN) + ITX_DW * 8)
 
@@ -175,13 +176,14 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_pos(const itx_decode_arg
     __syncwarp();
     uint32_t parity = 0;
     const itx_src_global G{A.b};
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(&A.work[2], 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= A.nchunks) break;
-        const uint32_t n = A.nrec[i];
-        if (n == 0) continue;
+    uint32_t i = 0, i_end = 0;
+    for (;; i++) {
+        if (i >= i_end) {                                  /* claim a batch of chunks: one atomic per ITX_CLAIM chunks */
+            if (lane == 0) i = atomicAdd(&A.work[2], ITX_CLAIM);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= A.nchunks) break;
+            i_end = i + ITX_CLAIM < A.nchunks ? i + ITX_CLAIM : A.nchunks;
+        }
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
         /* stage [lo, lo + C + margin) (clipped to the stream, rounded up to 16 inside the buffer's slack) */
         unsigned long long rest = A.len - lo;
@@ -193,9 +195,11 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_pos(const itx_decode_arg
             itx_mbar_expect_tx(bar_s, bytes);
             itx_bulk_g2s(buf_s, A.b + lo, bytes, bar_s);
         }
+        /* the record count and the first offsets travel while the tile lands */
+        const uint32_t n = A.nrec[i];
         const uint32_t *pp = A.pos + (size_t)i * A.S;
         itx_tuple *out = A.tuples + (size_t)i * A.S;
-        uint32_t ro = lane < n ? __ldcs(pp + lane) : 0u;   /* the first offsets travel while the tile lands */
+        uint32_t ro = lane < n ? __ldcs(pp + lane) : 0u;
         if (!itx_mbar_wait(bar_s, parity, A.status)) break;
         parity ^= 1u;
         const itx_src_stage R{buf, (uint32_t)lo};
@@ -280,11 +284,14 @@ __global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
     for (int k = 0; k < 13; k++) c[k] = 0;
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const itx_src_global G{A.b};
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(A.work, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= A.nchunks) break;
+    uint32_t i = 0, i_end = 0;
+    for (;; i++) {
+        if (i >= i_end) {                                  /* claim a batch of chunks: one atomic per ITX_CLAIM chunks */
+            if (lane == 0) i = atomicAdd(A.work, ITX_CLAIM);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= A.nchunks) break;
+            i_end = i + ITX_CLAIM < A.nchunks ? i + ITX_CLAIM : A.nchunks;
+        }
         const uint32_t n = A.nrec[i];
         const itx_tuple *tp = A.tuples + (size_t)i * A.S;
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;

@@ -142,7 +142,20 @@ ITX_HD bool itx_plausible2(const Src &S, uint64_t p, uint64_t len, int32_t n_ref
 /* first offset in [lo, hi) that passes itx_plausible2 */
 template <class Src>
 ITX_HD uint64_t itx_speculate_entry(const Src &S, uint64_t lo, uint64_t hi, uint64_t len, int32_t n_ref) {
-    for (uint64_t p = lo; p < hi; p++) if (itx_plausible2(S, p, len, n_ref)) return p;
+    /* slide over aligned words: every word is loaded once, the candidate block_size at each of its four
+     * byte offsets comes out of a funnel shift, and only values in range go through the full test */
+    uint64_t a = lo & ~3ull;
+    uint32_t w0 = S.w32(a);
+    for (; a < hi; a += 4) {
+        const uint32_t w1 = S.w32(a + 4);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint64_t p = a + k;
+            const uint32_t bs = itx_funnel_r(w0, w1, 8u * k);
+            if (bs - 33u <= (1u << 26) - 33u && p >= lo && p < hi && itx_plausible2(S, p, len, n_ref)) return p;
+        }
+        w0 = w1;
+    }
     return ITX_OFF_NONE;
 }
 
