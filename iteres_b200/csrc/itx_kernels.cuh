@@ -1,17 +1,15 @@
 /* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
  *
- *   k_chain      K1a  record-boundary discovery: the stream is cut into chunks; one thread per chunk GUESSES the
- *                    first record start in its chunk with a structural test and walks the block_size prefix
- *                    chain to the chunk end, storing every record offset.  Only the 4-byte block_size words are
- *                    touched, so thousands of independent chains per SM hide the HBM latency.
- *   k_verify / k_fixup  the guess of chunk i must equal the chain exit of chunk i-1; otherwise the chunk is
- *                    re-walked from its true entry.  The offsets are therefore exactly the sequential chain,
- *                    whatever the guesses were.
- *   k_decode_pos K1b  bam1_core_t unpack + fragment logic: a warp per chunk stages the chunk (+1 KiB margin) in
- *                    shared memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier), then every lane
- *                    decodes one record out of shared memory and the warp stores 32 tuples with one coalesced
- *                    512-byte store.                          replaces bam_read1 / bam_calend / bam_aux_get
- *   k_decode         K1a+K1b in one thread-per-chunk kernel reading global memory (A/B measurement only).
+ *   k_decode_tile K1  record boundaries + bam1_core_t unpack + fragment logic in ONE streaming pass: a warp per
+ *                    chunk stages the chunk (+1 KiB margin) in shared memory with a 1-D TMA bulk copy
+ *                    (cp.async.bulk + mbarrier); the 32 lanes guess and walk 32 pieces of the block_size chain
+ *                    in parallel out of shared memory and chain the pieces with shuffles; then every lane decodes
+ *                    one record per round and the warp stores 32 tuples with one coalesced 512-byte store.
+ *                                                             replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_verify / k_fixup  the entry a chunk assumed must equal the chain exit of the previous chunk; otherwise the
+ *                    chunk is re-walked from its true entry.  The tuples are therefore exactly the sequential
+ *                    chain, whatever the guesses were.
+ *   k_decode         the same contract, one thread per chunk reading global memory (A/B measurement, odd sizes).
  *   k_overlap   K2+K3  one lane per tuple: position bucket + short lower_bound + bounded backward walk in
  *                    place of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
  *                    counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
@@ -30,9 +28,8 @@ struct itx_decode_args {
     const itx_tidinfo *tid; int32_t n_ref;
     itx_dev_opts o;
     itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
-    uint32_t *pos;                         /* record offsets inside each chunk (S slots per chunk), written by k_chain */
     unsigned long long *carry; uint32_t *winbad; uint32_t *status;
-    uint32_t *work;                        /* [0] k_chain, [1] k_overlap, [2] k_decode_pos chunk counters; zeroed by k_fixup / k_decode_pos */
+    uint32_t *work;                        /* [0] k_decode_tile, [1] k_overlap chunk counters; zeroed by k_fixup */
 };
 
 /* fire-and-forget reductions (RED, no return value) */
@@ -72,55 +69,11 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
     itx_walk_chunk(A, i, p);
 }
 
-/* ------------------------------------------------------------------ K1a: the record chain */
-/* walk chunk i's chain from p: record offsets (relative to the chunk start) into pos, exit and count */
-__device__ __forceinline__ void itx_chain_chunk(const itx_decode_args &A, uint32_t i, unsigned long long p) {
-    const itx_src_global G{A.b};
-    const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-    unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-    uint32_t *out = A.pos + (size_t)i * A.S;
-    uint32_t n = 0;
-    if (p < ITX_OFF_END) {
-        while (p < hi) {
-            if (p + 36 > A.len) { p = ITX_OFF_END; break; }
-            const uint32_t bs = G.u32(p);
-            const unsigned long long e = p + 4 + (unsigned long long)bs;
-            if ((int32_t)bs < 32 || e > A.len) { p = ITX_OFF_END; break; }
-            if (e > A.avail) atomicOr(&A.status[0], 2u);                 /* record longer than the staged window */
-            if (n < A.S) out[n] = (uint32_t)(p - lo);
-            n++;
-            p = e;
-        }
-    }
-    A.exit_[i] = p; A.nrec[i] = n < A.S ? n : A.S;
-}
-/* persistent: a warp claims 32 consecutive chunks at a time */
-__global__ void __launch_bounds__(256) k_chain(const itx_decode_args A) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&A.work[0], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= A.nchunks) break;
-        const uint32_t i = base + lane;
-        if (i < A.nchunks) {
-            const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-            unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-            unsigned long long p;
-            if (i == 0) p = *A.carry;
-            else p = itx_speculate_entry(itx_src_global{A.b}, lo, hi, A.len, A.n_ref);
-            A.entry[i] = p;
-            itx_chain_chunk(A, i, p);
-        }
-    }
-}
-
-/* ------------------------------------------------------------------ K1b: decode out of TMA-staged shared memory */
+/* ------------------------------------------------------------------ K1: one pass, TMA-staged, lane-parallel chain */
 #define ITX_DW 8                           /* warps per CTA */
-#define ITX_CLAIM 16u                      /* chunks claimed per atomic on the work counters */
+#define ITX_CLAIM 8u                       /* chunks claimed per atomic on the work counters */
 #define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
-#define ITX_DECODE_SMEM(C) (ITX_DW * ((C) + ITX_MARGIN) + ITX_DW * 8)
+#define ITX_DECODE_SMEM(C, S) (ITX_DW * ((C) + ITX_MARGIN) + ITX_DW * (((S) * 2u + 15u) & ~15u) + ITX_DW * 8)
 
 __device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void itx_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -143,11 +96,17 @@ __device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uin
     if (itx_mbar_try_wait(bar, parity)) return true;
     return itx_mbar_wait_slow(bar, parity, status);
 }
-/* bytes [base32, base32 + n) of the stream, staged linearly in shared memory */
+/* stream bytes [base, base + nb) staged linearly in shared memory; anything beyond comes from global memory */
 struct itx_src_stage {
-    const uint8_t *buf; uint32_t base32;
-    __device__ __forceinline__ uint8_t u8(uint64_t off) const { return buf[(uint32_t)off - base32]; }
-    __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(buf + ((uint32_t)aligned_off - base32)); }
+    const uint8_t *buf; const uint8_t *g; unsigned long long base; uint32_t nb;
+    __device__ __forceinline__ uint8_t u8(uint64_t off) const {
+        const unsigned long long d = off - base;
+        return d < nb ? buf[(uint32_t)d] : __ldg(g + off);
+    }
+    __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const {
+        const unsigned long long d = aligned_off - base;
+        return d + 4 <= nb ? *reinterpret_cast<const uint32_t *>(buf + (uint32_t)d) : __ldg(reinterpret_cast<const uint32_t *>(g + aligned_off));
+    }
     __device__ __forceinline__ uint32_t u32(uint64_t off) const {
         const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
         return itx_funnel_r(w32(a), w32(a + 4), sh);
@@ -155,74 +114,128 @@ struct itx_src_stage {
     __device__ __forceinline__ void core(uint64_t p, uint32_t x[9]) const {
         const uint64_t a = p & ~3ull; const uint32_t sh = (uint32_t)(p & 3) * 8;
         uint32_t w[10];
+        if (a - base + 40 <= nb) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(buf + (uint32_t)(a - base));
 #pragma unroll
-        for (int i = 0; i < 10; i++) w[i] = w32(a + 4u * i);
+            for (int i = 0; i < 10; i++) w[i] = q[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 10; i++) w[i] = w32(a + 4u * i);
+        }
 #pragma unroll
         for (int j = 0; j < 9; j++) x[j] = itx_funnel_r(w[j], w[j + 1], sh);
     }
 };
 
-__global__ void __launch_bounds__(ITX_DW * 32) k_decode_pos(const itx_decode_args A) {
+/* records that start in [p, s1): count, and the first record start >= s1 (ITX_OFF_END when the chain ends) */
+__device__ __forceinline__ void itx_sub_walk(const itx_src_stage &S, const itx_decode_args &A, unsigned long long p, unsigned long long s1,
+                                             uint32_t *n_out, unsigned long long *x_out, uint16_t *pos, uint32_t pos_base, unsigned long long lo) {
+    uint32_t n = 0;
+    if (p < ITX_OFF_END) {
+        while (p < s1) {
+            if (p + 36 > A.len) { p = ITX_OFF_END; break; }
+            const uint32_t bs = S.u32(p);
+            const unsigned long long e = p + 4 + (unsigned long long)bs;
+            if ((int32_t)bs < 32 || e > A.len) { p = ITX_OFF_END; break; }
+            if (pos) { if (e > A.avail) atomicOr(&A.status[0], 2u); pos[pos_base + n] = (uint16_t)(p - lo); }
+            n++;
+            p = e;
+        }
+    }
+    *n_out = n; *x_out = p;
+}
+
+/* A warp per chunk.  The chunk (+ margin) is staged with one TMA bulk copy; lane l owns the sub-range
+ * [lo + l*B, lo + (l+1)*B), B = C/32: it GUESSES the first record start in its sub-range and walks the
+ * block_size chain to the sub-range end.  The lanes' pieces are then chained: lane l's piece must begin where
+ * lane l-1's ended; a lane whose guess was wrong re-walks from the true position until nothing changes (exact
+ * for any input given the chunk entry, which k_verify / k_fixup check against the previous chunk).  The record
+ * offsets go through shared memory so that the decode is balanced: lane j decodes record j, j+32, ... and the
+ * warp stores 32 tuples with one coalesced 512-byte store. */
+__global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tile(const itx_decode_args A) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t stage_bytes = A.C + ITX_MARGIN;
+    const uint32_t stage_bytes = A.C + ITX_MARGIN, pos_bytes = (A.S * 2u + 15u) & ~15u, B = A.C >> 5;
     uint8_t *buf = itx_smem + w * stage_bytes;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * stage_bytes + w * pos_bytes);
     const uint32_t buf_s = itx_smem_addr(buf);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * stage_bytes) + w * 8;
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * (stage_bytes + pos_bytes)) + w * 8;
     if (lane == 0) {
         itx_mbar_init(bar_s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
     uint32_t parity = 0;
-    const itx_src_global G{A.b};
     uint32_t i = 0, i_end = 0;
     for (;; i++) {
         if (i >= i_end) {                                  /* claim a batch of chunks: one atomic per ITX_CLAIM chunks */
-            if (lane == 0) i = atomicAdd(&A.work[2], ITX_CLAIM);
+            if (lane == 0) i = atomicAdd(&A.work[0], ITX_CLAIM);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= A.nchunks) break;
             i_end = i + ITX_CLAIM < A.nchunks ? i + ITX_CLAIM : A.nchunks;
         }
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        /* stage [lo, lo + C + margin) (clipped to the stream, rounded up to 16 inside the buffer's slack) */
-        unsigned long long rest = A.len - lo;
-        uint32_t nb = rest > stage_bytes ? stage_bytes : (uint32_t)rest;
-        const uint32_t bytes = (nb + 15u) & ~15u;
+        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+        const unsigned long long rest = A.len - lo;
+        const uint32_t nb = rest > stage_bytes ? stage_bytes : (uint32_t)rest;
+        const uint32_t bytes = (nb + 15u) & ~15u;          /* the buffer's 64 bytes of slack cover the round-up */
         __syncwarp();                                      /* every lane is done reading the previous chunk */
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             itx_mbar_expect_tx(bar_s, bytes);
             itx_bulk_g2s(buf_s, A.b + lo, bytes, bar_s);
         }
-        /* the record count and the first offsets travel while the tile lands */
-        const uint32_t n = A.nrec[i];
-        const uint32_t *pp = A.pos + (size_t)i * A.S;
-        itx_tuple *out = A.tuples + (size_t)i * A.S;
-        uint32_t ro = lane < n ? __ldcs(pp + lane) : 0u;
+        unsigned long long carry = ITX_OFF_NONE;
+        if (i == 0) carry = *A.carry;                      /* the window's first chunk knows its entry */
         if (!itx_mbar_wait(bar_s, parity, A.status)) break;
         parity ^= 1u;
-        const itx_src_stage R{buf, (uint32_t)lo};
-        for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            if (j0) ro = j < n ? __ldcs(pp + j) : 0u;
-            if (j < n) {
-                itx_tuple T;
-                bool staged = false;
-                if (ro + 40u <= nb) {
-                    const uint32_t bs = R.u32((uint32_t)lo + ro);
-                    staged = (unsigned long long)ro + 4ull + bs <= nb;
-                }
-                if (staged) {
-                    uint32_t x[9]; R.core((uint32_t)lo + ro, x);
-                    T = itx_decode_record(R, (uint32_t)lo + ro, x, ro, A.tid, A.n_ref, A.o);
-                } else {                                   /* the record runs past the staged bytes: read it from global memory */
-                    uint32_t x[9]; G.core(lo + ro, x);
-                    T = itx_decode_record(G, lo + ro, x, ro, A.tid, A.n_ref, A.o);
-                }
-                __stcs(reinterpret_cast<uint4 *>(out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
+        const itx_src_stage S{buf, A.b, lo, nb};
+        /* 1. every lane guesses the first record start of its sub-range */
+        unsigned long long s0 = lo + (unsigned long long)lane * B, s1 = s0 + B;
+        if (s1 > hi) s1 = hi;
+        unsigned long long cand = ITX_OFF_NONE;
+        if (i == 0 && lane == 0) cand = carry;
+        else if (s0 < s1) cand = itx_speculate_entry(S, s0, s1, A.len, A.n_ref);
+        if (s0 > hi) s0 = hi;
+        /* 2. walk each piece, then chain the pieces: lane l must start where the previous piece stopped.  A lane
+         *    without any plausible start in its sub-range (a record covers it) is transparent: it passes its
+         *    predecessor's position on, and a lane behind an all-transparent prefix keeps its own guess. */
+        const unsigned long long guess = cand;
+        uint32_t n, n_g; unsigned long long X, X_g;
+        itx_sub_walk(S, A, guess, s1, &n_g, &X_g, nullptr, 0, lo);
+        n = n_g; X = X_g;
+        for (uint32_t it = 0; it < 34; it++) {
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, X, 1);
+            const unsigned long long want = (lane == 0 || prev == ITX_OFF_NONE) ? guess : prev;
+            const bool change = want != cand;
+            if (!__any_sync(0xffffffffu, change)) break;
+            if (change) {
+                cand = want;
+                if (want == guess) { n = n_g; X = X_g; } else itx_sub_walk(S, A, cand, s1, &n, &X, nullptr, 0, lo);
             }
         }
+        /* the entry this chunk assumed: the first lane that has a position at all */
+        const uint32_t has = __ballot_sync(0xffffffffu, cand != ITX_OFF_NONE);
+        const unsigned long long entry0 = __shfl_sync(0xffffffffu, cand, has ? (__ffs((int)has) - 1) : 0);
+        /* 3. record offsets in file order through shared memory */
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > A.S) total = A.S;
+        { uint32_t n2; unsigned long long x2; if (incl <= A.S) itx_sub_walk(S, A, cand, s1, &n2, &x2, pos, incl - n, lo); }
+        const unsigned long long exitX = __shfl_sync(0xffffffffu, X, 31);
+        __syncwarp();
+        /* 4. balanced decode: lane j takes record j, j + 32, ...; one coalesced store per 32 tuples */
+        itx_tuple *out = A.tuples + (size_t)i * A.S;
+        for (uint32_t j = lane; j < total; j += 32) {
+            const uint32_t ro = pos[j];
+            uint32_t x[9]; S.core(lo + ro, x);
+            const itx_tuple T = itx_decode_record(S, lo + ro, x, ro, A.tid, A.n_ref, A.o);
+            __stcs(reinterpret_cast<uint4 *>(out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
+        }
+        if (lane == 0) { A.entry[i] = entry0; A.exit_[i] = exitX; A.nrec[i] = total; }
     }
 }
 
@@ -246,7 +259,7 @@ __global__ void k_fixup(const itx_decode_args A) {
             if (lane == 0) {
                 unsigned long long e = A.exit_[j - 1];
                 A.entry[j] = e;
-                if (A.pos) itx_chain_chunk(A, j, e); else itx_walk_chunk(A, j, e);
+                itx_walk_chunk(A, j, e);
                 atomicAdd(&A.status[1], 1u);
                 __threadfence();
             }
@@ -255,7 +268,7 @@ __global__ void k_fixup(const itx_decode_args A) {
         }
     }
     __syncwarp();
-    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; A.work[2] = 0; }
+    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; }
 }
 
 /* ------------------------------------------------------------------ overlap + accumulate */

@@ -18,7 +18,7 @@ struct emu_index {
     std::vector<uint32_t> cname_slot, cname_off; std::vector<char> cname_pool;
     std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
     std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
-    std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch;
+    std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch, tile_checked, tile_mismatch, tile_entry_miss;
 };
 
 extern "C" {
@@ -31,7 +31,7 @@ void emu_reset(emu_index *E) {
     std::fill(E->grp_cpg_score.begin(), E->grp_cpg_score.end(), 0.0); std::fill(E->bp_cpg.begin(), E->bp_cpg.end(), 0.0);
     std::fill(E->el_cpg_score.begin(), E->el_cpg_score.end(), 0.0);
     std::fill(E->status.begin(), E->status.end(), 0u);
-    E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0;
+    E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0;
 }
 
 emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk, int filter_field, const char *filter_name, char *err) {
@@ -62,7 +62,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     D.el_cnt = E->el_cnt.data(); D.el_cnt_u = E->el_cnt_u.data();
     D.grp_cpg = E->grp_cpg.data(); D.el_cpg = E->el_cpg.data(); D.grp_cpg_score = E->grp_cpg_score.data(); D.bp_cpg = E->bp_cpg.data(); D.el_cpg_score = E->el_cpg_score.data();
     D.tid_unknown_seen = E->tid_seen.data(); D.status = E->status.data();
-    E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0;
+    E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0;
     return E;
 }
 void emu_free(emu_index *E) { if (!E) return; itx_host_index_free(&E->ix); delete E; }
@@ -107,6 +107,51 @@ static void walk_chunk(emu_index *E, const uint8_t *b, uint64_t len, uint64_t lo
     *exit_ = p;
 }
 
+/* The lane-parallel chain resolution of k_decode_tile, simulated: 32 sub-ranges of a chunk each guess their
+ * first record start and walk their piece; pieces are chained with the kernel's synchronous update rule
+ * (transparent lanes, own guess behind an all-transparent prefix).  Returns the record starts and the exit. */
+static void sub_walk(const itx_src_global &G, uint64_t len, uint64_t p, uint64_t s1, std::vector<uint64_t> *out, uint64_t *x) {
+    if (out) out->clear();
+    if (p < ITX_OFF_END) {
+        while (p < s1) {
+            if (p + 36 > len) { p = ITX_OFF_END; break; }
+            const uint32_t bs = G.u32(p); const uint64_t e = p + 4 + (uint64_t)bs;
+            if ((int32_t)bs < 32 || e > len) { p = ITX_OFF_END; break; }
+            if (out) out->push_back(p);
+            p = e;
+        }
+    }
+    *x = p;
+}
+static void tile_chain(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, int32_t n_ref, bool first, uint64_t carry,
+                       uint64_t *entry0, std::vector<uint64_t> *starts, uint64_t *exitX) {
+    const itx_src_global G{b};
+    uint64_t hi = lo + C; if (hi > len) hi = len;
+    const uint32_t B = C / 32;
+    uint64_t guess[32], cand[32], X[32], Xg[32], s1v[32];
+    for (uint32_t l = 0; l < 32; l++) {
+        uint64_t s0 = lo + (uint64_t)l * B, s1 = s0 + B; if (s1 > hi) s1 = hi;
+        s1v[l] = s1;
+        uint64_t c = ITX_OFF_NONE;
+        if (first && l == 0) c = carry; else if (s0 < s1) c = itx_speculate_entry(G, s0, s1, len, n_ref);
+        guess[l] = cand[l] = c;
+        sub_walk(G, len, c, s1, NULL, &Xg[l]); X[l] = Xg[l];
+    }
+    for (int it = 0; it < 34; it++) {
+        uint64_t want[32]; bool any = false;
+        for (uint32_t l = 0; l < 32; l++) { const uint64_t prev = l ? X[l - 1] : 0; want[l] = (l == 0 || prev == ITX_OFF_NONE) ? guess[l] : prev; if (want[l] != cand[l]) any = true; }
+        if (!any) break;
+        uint64_t nX[32];
+        for (uint32_t l = 0; l < 32; l++) { nX[l] = X[l]; if (want[l] != cand[l]) { cand[l] = want[l]; if (want[l] == guess[l]) nX[l] = Xg[l]; else sub_walk(G, len, cand[l], s1v[l], NULL, &nX[l]); } }
+        for (uint32_t l = 0; l < 32; l++) X[l] = nX[l];
+    }
+    *entry0 = ITX_OFF_NONE;
+    for (uint32_t l = 0; l < 32; l++) if (cand[l] != ITX_OFF_NONE) { *entry0 = cand[l]; break; }
+    starts->clear();
+    for (uint32_t l = 0; l < 32; l++) { std::vector<uint64_t> v; uint64_t x; sub_walk(G, len, cand[l], s1v[l], &v, &x); starts->insert(starts->end(), v.begin(), v.end()); }
+    *exitX = X[31];
+}
+
 /* bam: uncompressed stream with >= 64 readable bytes after len.  want_trace: keep a per-record trace. */
 int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_scan_opts *so, uint32_t chunk, int want_trace, uint64_t cnt[13], char *err) {
     itx_index &ix = E->ix; itx_dev_index &D = E->D;
@@ -130,6 +175,18 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
         E->n_bad++;
         entry[i] = exit_[i - 1];
         walk_chunk(E, bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
+    }
+    /* the warp kernel's lane-parallel chain, chunk by chunk, against the sequential chain */
+    if ((C & 127u) == 0 && C >= 2048u) {
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t e0, ex; std::vector<uint64_t> st;
+            tile_chain(bam, len, (k0 + i) * C, C, h.n_ref, i == 0, h.hdr_len, &e0, &st, &ex);
+            E->tile_checked++;
+            if (e0 != entry[i]) { E->tile_entry_miss++; continue; }     /* a wrong chunk guess: the repair path's business */
+            bool same = ex == exit_[i] && st.size() == tup[i].size();
+            for (size_t j = 0; same && j < st.size(); j++) same = (uint32_t)(st[j] - (k0 + i) * C) == tup[i][j].rec_off;
+            if (!same) E->tile_mismatch++;
+        }
     }
     /* K2 + K3 */
     unsigned long long *c = D.cnt;
@@ -217,6 +274,9 @@ uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
 uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
 uint64_t emu_ring_checked(emu_index *E) { return E->ring_checked; }
 uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }
+uint64_t emu_tile_checked(emu_index *E) { return E->tile_checked; }
+uint64_t emu_tile_mismatch(emu_index *E) { return E->tile_mismatch; }
+uint64_t emu_tile_entry_miss(emu_index *E) { return E->tile_entry_miss; }
 
 int32_t emu_query(emu_index *E, const char *chrom, uint32_t start, uint32_t end, float min_cov, int32_t *n_hits) {
     int32_t c = itx_strtab_find(&E->ix.chroms, chrom); if (n_hits) *n_hits = 0;

@@ -30,7 +30,7 @@ def lib():
         L.emu_trace.argtypes = [vp, vp, u64]
         L.emu_n_bad.restype = u64
         L.emu_n_bad.argtypes = [vp]
-        for f in ("emu_ring_checked", "emu_ring_mismatch"):
+        for f in ("emu_ring_checked", "emu_ring_mismatch", "emu_tile_checked", "emu_tile_mismatch", "emu_tile_entry_miss"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [vp]
         L.emu_query.restype = C.c_int32
@@ -87,6 +87,11 @@ class EmuIndex(capi.IndexBase):
     def ring_check(self):
         """(records re-decoded out of the shared-memory ring layout, mismatches against the global-memory decode)"""
         return self.L.emu_ring_checked(self.e), self.L.emu_ring_mismatch(self.e)
+
+    def tile_check(self):
+        """(chunks put through the warp kernel's lane-parallel chain, chunks whose record list differed from the
+        sequential chain although the entry was right, chunks whose entry guess was wrong)"""
+        return self.L.emu_tile_checked(self.e), self.L.emu_tile_mismatch(self.e), self.L.emu_tile_entry_miss(self.e)
 
     def scan_cpg(self, path, filter=0):
         a, b = C.c_uint32(0), C.c_uint32(0)

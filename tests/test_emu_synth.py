@@ -55,12 +55,14 @@ def test_emu_matches_oracle(case, worlds):
     raw = buf[:n].tobytes()
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
-    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=1024)
+    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=2048)
     cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
     assert cnt_e == cnt_o
     assert cnt_o[0] + cnt_o[1] == nrec and cnt_o[9] > 0
     checked, mism = emu.ring_check()
-    assert checked >= nrec and mism == 0          # the TMA kernel's ring addressing decodes every record identically
+    assert checked >= nrec and mism == 0          # ring addressing decodes every record identically
+    tc, tm, te = emu.tile_check()
+    assert tc > 0 and tm == 0 and te == emu.n_bad()   # k_decode_tile's lane-parallel chain == the sequential chain
     assert len(tr_e) == len(tr_o) == nrec
     for f in ("start", "end", "tid", "sel_row"):
         assert np.array_equal(tr_e[f], tr_o[f]), f
@@ -157,5 +159,7 @@ def test_records_of_every_size(chunk, tmp_path):
             assert np.array_equal(tr_e[f], tr_o[f]), f
         assert np.array_equal(tr_e["flags"] & ~np.uint32(8), tr_o["flags"] & ~np.uint32(8))
         assert emu.ring_check()[1] == 0
+        tc, tm, te = emu.tile_check()
+        assert tc > 0 and tm == 0                 # entry misses (te) are allowed here: records longer than a chunk
         ora.close()
         emu.close()
