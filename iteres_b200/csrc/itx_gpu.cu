@@ -36,8 +36,8 @@ struct itx_cuda {
     uint32_t C, S; uint64_t cap_chunks;
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
-    uint32_t *d_work; int decode_variant;   /* 0: k_decode_tile (TMA staged, lane-parallel chain), 1: k_decode (thread per chunk) */
-    int decode_ctas;                        /* resident CTAs per SM of k_decode_tile at the current chunk size */
+    uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
+    int decode_ctas;                        /* resident CTAs per SM of k_decode_span */
     itx_trace *d_trace; uint64_t trace_cap;
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
@@ -168,7 +168,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
-        CKN(cudaFuncSetAttribute(k_decode_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
@@ -182,7 +182,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
         if (zero_counters(ix, err)) goto fail;
     }
-    ix->tune_chunk = 8192; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
+    ix->tune_chunk = 65536; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
     return ix;
 fail:
     cuda_free_all(cu); ix->cu = NULL;
@@ -249,10 +249,10 @@ static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
     cu->C = C; cu->S = S; cu->cap_chunks = need;
     CK(cudaMalloc((void **)&cu->d_tuples, need * S * sizeof(itx_tuple)));
     CK(cudaMalloc((void **)&cu->d_entry, need * 8)); CK(cudaMalloc((void **)&cu->d_exit, need * 8)); CK(cudaMalloc((void **)&cu->d_nrec, need * 4));
-    if (C <= 16384u) {
-        CK(cudaFuncSetAttribute(k_decode_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM(C, S)));
+    {
+        CK(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_tile, ITX_DW * 32, ITX_DECODE_SMEM(C, S)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_span, ITX_DW * 32, ITX_DECODE_SMEM));
         cu->decode_ctas = nb > 0 ? nb : 1;
     }
     if (want_trace) CK(cudaMalloc((void **)&cu->d_rec_base, need * 8));
@@ -300,7 +300,7 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     CK(cudaMemsetAsync(cu->d_work, 0, 16, cu->stream));
     {   /* ITX_DECODE_KERNEL=thread selects the one-thread-per-chunk kernel (A/B measurement); chunks that are not whole tiles use it too */
         const char *v = getenv("ITX_DECODE_KERNEL");
-        cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C & 127u) != 0 || cu->C < 2048u || cu->C > 16384u) ? 1 : 0;
+        cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_STAGE) != 0 || cu->C > (1u << 20)) ? 1 : 0;
         if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
     }
     if (ix->trace_cap) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
@@ -322,7 +322,7 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
         if (cu->decode_variant == 0) {
             uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)(cu->sm_count * cu->decode_ctas);
-            k_decode_tile<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM(cu->C, cu->S), cu->stream>>>(A);
+            k_decode_span<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM, cu->stream>>>(A);
         } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
         k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
         k_fixup<<<1, 32, 0, cu->stream>>>(A);
@@ -371,7 +371,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
     P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1];
     P->d2h_bytes = sizeof hc + sizeof st;
-    if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA bulk copy never completed (device-side time-out in k_decode_tile)"); return ITX_ENODEV; }
+    if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA bulk copy never completed (device-side time-out in k_decode_span)"); return ITX_ENODEV; }
     if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
     /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */
     if (sc->h->n_ref > 0) {

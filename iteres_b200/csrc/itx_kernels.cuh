@@ -1,13 +1,14 @@
 /* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
  *
- *   k_decode_tile K1  record boundaries + bam1_core_t unpack + fragment logic in ONE streaming pass: a warp per
- *                    chunk stages the chunk (+1 KiB margin) in shared memory with a 1-D TMA bulk copy
- *                    (cp.async.bulk + mbarrier); the 32 lanes guess and walk 32 pieces of the block_size chain
- *                    in parallel out of shared memory and chain the pieces with shuffles; then every lane decodes
- *                    one record per round and the warp stores 32 tuples with one coalesced 512-byte store.
- *                                                             replaces bam_read1 / bam_calend / bam_aux_get
- *   k_verify / k_fixup  the entry a chunk assumed must equal the chain exit of the previous chunk; otherwise the
- *                    chunk is re-walked from its true entry.  The tuples are therefore exactly the sequential
+ *   k_decode_span K1  record boundaries + bam1_core_t unpack + fragment logic in ONE streaming pass.  The stream
+ *                    is cut into spans; a warp takes a span, GUESSES its first record start with a warp-wide
+ *                    structural test, then carries the block_size chain through the span stage by stage: each
+ *                    4 KiB stage (+1 KiB margin) lands in shared memory through one 1-D TMA bulk copy
+ *                    (cp.async.bulk + mbarrier), lane 0 walks the chain of the stage out of shared memory, and
+ *                    every lane decodes one record per round and the warp stores 32 tuples with one coalesced
+ *                    512-byte store.                           replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_verify / k_fixup  the entry a span assumed must equal the chain exit of the previous span; otherwise the
+ *                    span is re-walked from its true entry.  The tuples are therefore exactly the sequential
  *                    chain, whatever the guesses were.
  *   k_decode         the same contract, one thread per chunk reading global memory (A/B measurement, odd sizes).
  *   k_overlap   K2+K3  one lane per tuple: position bucket + short lower_bound + bounded backward walk in
@@ -29,7 +30,7 @@ struct itx_decode_args {
     itx_dev_opts o;
     itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
     unsigned long long *carry; uint32_t *winbad; uint32_t *status;
-    uint32_t *work;                        /* [0] k_decode_tile, [1] k_overlap chunk counters; zeroed by k_fixup */
+    uint32_t *work;                        /* [0] k_decode_span, [1] k_overlap chunk counters; zeroed by k_fixup */
 };
 
 /* fire-and-forget reductions (RED, no return value) */
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
 #define ITX_DW 8                           /* warps per CTA */
 #define ITX_CLAIM 8u                       /* chunks claimed per atomic on the work counters */
 #define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
-#define ITX_DECODE_SMEM(C, S) (ITX_DW * ((C) + ITX_MARGIN) + ITX_DW * (((S) * 2u + 15u) & ~15u) + ITX_DW * 8)
+#define ITX_DECODE_SMEM 0
 
 __device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void itx_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -127,39 +128,25 @@ struct itx_src_stage {
     }
 };
 
-/* records that start in [p, s1): count, and the first record start >= s1 (ITX_OFF_END when the chain ends) */
-__device__ __forceinline__ void itx_sub_walk(const itx_src_stage &S, const itx_decode_args &A, unsigned long long p, unsigned long long s1,
-                                             uint32_t *n_out, unsigned long long *x_out, uint16_t *pos, uint32_t pos_base, unsigned long long lo) {
-    uint32_t n = 0;
-    if (p < ITX_OFF_END) {
-        while (p < s1) {
-            if (p + 36 > A.len) { p = ITX_OFF_END; break; }
-            const uint32_t bs = S.u32(p);
-            const unsigned long long e = p + 4 + (unsigned long long)bs;
-            if ((int32_t)bs < 32 || e > A.len) { p = ITX_OFF_END; break; }
-            if (pos) { if (e > A.avail) atomicOr(&A.status[0], 2u); pos[pos_base + n] = (uint16_t)(p - lo); }
-            n++;
-            p = e;
-        }
-    }
-    *n_out = n; *x_out = p;
-}
+/* A warp per span (= "chunk" of the bookkeeping, A.C bytes, a multiple of ITX_STAGE).  Only the span's first
+ * record start is GUESSED (warp-wide structural test, checked against the previous span by k_verify / k_fixup);
+ * inside the span the chain is carried from one 4 KiB stage to the next.  Each stage (+1 KiB margin) arrives
+ * in shared memory through one TMA bulk copy; lane 0 walks the block_size chain of the stage out of shared
+ * memory (11 instructions per record), then every lane decodes one record per round out of shared memory and
+ * the warp stores 32 tuples with one coalesced 512-byte store. */
+#define ITX_STAGE 4096u
+#define ITX_POS_SLOTS 128u                 /* > ITX_STAGE / 36 record starts per stage */
+#undef ITX_DECODE_SMEM
+#define ITX_DECODE_SMEM (ITX_DW * (ITX_STAGE + ITX_MARGIN) + ITX_DW * ITX_POS_SLOTS * 2u + ITX_DW * 8)
 
-/* A warp per chunk.  The chunk (+ margin) is staged with one TMA bulk copy; lane l owns the sub-range
- * [lo + l*B, lo + (l+1)*B), B = C/32: it GUESSES the first record start in its sub-range and walks the
- * block_size chain to the sub-range end.  The lanes' pieces are then chained: lane l's piece must begin where
- * lane l-1's ended; a lane whose guess was wrong re-walks from the true position until nothing changes (exact
- * for any input given the chunk entry, which k_verify / k_fixup check against the previous chunk).  The record
- * offsets go through shared memory so that the decode is balanced: lane j decodes record j, j+32, ... and the
- * warp stores 32 tuples with one coalesced 512-byte store. */
-__global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tile(const itx_decode_args A) {
+__global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_args A) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t stage_bytes = A.C + ITX_MARGIN, pos_bytes = (A.S * 2u + 15u) & ~15u, B = A.C >> 5;
-    uint8_t *buf = itx_smem + w * stage_bytes;
-    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * stage_bytes + w * pos_bytes);
+    constexpr uint32_t STG = ITX_STAGE + ITX_MARGIN;
+    uint8_t *buf = itx_smem + w * STG;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * STG) + w * ITX_POS_SLOTS;
     const uint32_t buf_s = itx_smem_addr(buf);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * (stage_bytes + pos_bytes)) + w * 8;
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * STG + ITX_DW * ITX_POS_SLOTS * 2u) + w * 8;
     if (lane == 0) {
         itx_mbar_init(bar_s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,75 +154,81 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_decode_tile(const itx_decode
     __syncwarp();
     if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
     uint32_t parity = 0;
-    uint32_t i = 0, i_end = 0;
-    for (;; i++) {
-        if (i >= i_end) {                                  /* claim a batch of chunks: one atomic per ITX_CLAIM chunks */
-            if (lane == 0) i = atomicAdd(&A.work[0], ITX_CLAIM);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (i >= A.nchunks) break;
-            i_end = i + ITX_CLAIM < A.nchunks ? i + ITX_CLAIM : A.nchunks;
-        }
+    const itx_src_global G{A.b};
+    bool dead = false;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&A.work[0], 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.nchunks || dead) break;
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
         unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-        const unsigned long long rest = A.len - lo;
-        const uint32_t nb = rest > stage_bytes ? stage_bytes : (uint32_t)rest;
-        const uint32_t bytes = (nb + 15u) & ~15u;          /* the buffer's 64 bytes of slack cover the round-up */
-        __syncwarp();                                      /* every lane is done reading the previous chunk */
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            itx_mbar_expect_tx(bar_s, bytes);
-            itx_bulk_g2s(buf_s, A.b + lo, bytes, bar_s);
-        }
-        unsigned long long carry = ITX_OFF_NONE;
-        if (i == 0) carry = *A.carry;                      /* the window's first chunk knows its entry */
-        if (!itx_mbar_wait(bar_s, parity, A.status)) break;
-        parity ^= 1u;
-        const itx_src_stage S{buf, A.b, lo, nb};
-        /* 1. every lane guesses the first record start of its sub-range */
-        unsigned long long s0 = lo + (unsigned long long)lane * B, s1 = s0 + B;
-        if (s1 > hi) s1 = hi;
-        unsigned long long cand = ITX_OFF_NONE;
-        if (i == 0 && lane == 0) cand = carry;
-        else if (s0 < s1) cand = itx_speculate_entry(S, s0, s1, A.len, A.n_ref);
-        if (s0 > hi) s0 = hi;
-        /* 2. walk each piece, then chain the pieces: lane l must start where the previous piece stopped.  A lane
-         *    without any plausible start in its sub-range (a record covers it) is transparent: it passes its
-         *    predecessor's position on, and a lane behind an all-transparent prefix keeps its own guess. */
-        const unsigned long long guess = cand;
-        uint32_t n, n_g; unsigned long long X, X_g;
-        itx_sub_walk(S, A, guess, s1, &n_g, &X_g, nullptr, 0, lo);
-        n = n_g; X = X_g;
-        for (uint32_t it = 0; it < 34; it++) {
-            const unsigned long long prev = __shfl_up_sync(0xffffffffu, X, 1);
-            const unsigned long long want = (lane == 0 || prev == ITX_OFF_NONE) ? guess : prev;
-            const bool change = want != cand;
-            if (!__any_sync(0xffffffffu, change)) break;
-            if (change) {
-                cand = want;
-                if (want == guess) { n = n_g; X = X_g; } else itx_sub_walk(S, A, cand, s1, &n, &X, nullptr, 0, lo);
+        /* the span's first record start: known for the window's first span, guessed otherwise */
+        unsigned long long p;
+        if (i == 0) p = *A.carry;
+        else {
+            p = ITX_OFF_NONE;
+            for (unsigned long long base = lo; base < hi; base += 32) {
+                const unsigned long long q = base + lane;
+                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
             }
         }
-        /* the entry this chunk assumed: the first lane that has a position at all */
-        const uint32_t has = __ballot_sync(0xffffffffu, cand != ITX_OFF_NONE);
-        const unsigned long long entry0 = __shfl_sync(0xffffffffu, cand, has ? (__ffs((int)has) - 1) : 0);
-        /* 3. record offsets in file order through shared memory */
-        uint32_t incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total > A.S) total = A.S;
-        { uint32_t n2; unsigned long long x2; if (incl <= A.S) itx_sub_walk(S, A, cand, s1, &n2, &x2, pos, incl - n, lo); }
-        const unsigned long long exitX = __shfl_sync(0xffffffffu, X, 31);
-        __syncwarp();
-        /* 4. balanced decode: lane j takes record j, j + 32, ...; one coalesced store per 32 tuples */
+        if (lane == 0) A.entry[i] = p;
         itx_tuple *out = A.tuples + (size_t)i * A.S;
-        for (uint32_t j = lane; j < total; j += 32) {
-            const uint32_t ro = pos[j];
-            uint32_t x[9]; S.core(lo + ro, x);
-            const itx_tuple T = itx_decode_record(S, lo + ro, x, ro, A.tid, A.n_ref, A.o);
-            __stcs(reinterpret_cast<uint4 *>(out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
+        uint32_t n_out = 0;
+        while (p < hi) {                                   /* ITX_OFF_END / ITX_OFF_NONE are above any hi */
+            const unsigned long long c_lo = lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
+            unsigned long long c_hi = c_lo + ITX_STAGE; if (c_hi > hi) c_hi = hi;
+            const unsigned long long rest = A.len - c_lo;
+            const uint32_t nb = rest > STG ? STG : (uint32_t)rest;
+            const uint32_t bytes = (nb + 15u) & ~15u;      /* the buffer's 64 bytes of slack cover the round-up */
+            __syncwarp();                                  /* every lane is done reading the previous stage */
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                itx_mbar_expect_tx(bar_s, bytes);
+                itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+            }
+            if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
+            parity ^= 1u;
+            /* lane 0 walks the chain of this stage; every block_size word it reads lies inside the staged bytes */
+            uint32_t n = 0, ended = 0;
+            uint32_t q = (uint32_t)(p - c_lo);
+            if (lane == 0) {
+                const uint32_t qh = (uint32_t)(c_hi - c_lo);
+                const unsigned long long room = A.len - c_lo;                     /* record end must be <= room */
+                const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
+                const uint32_t av32 = A.avail > c_lo ? (A.avail - c_lo > 0x7fffffffull ? 0x7fffffffu : (uint32_t)(A.avail - c_lo)) : 0u;
+                while (q < qh) {
+                    if (q + 36u > room32) { ended = 1; break; }
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
+                    const uint32_t bs = itx_funnel_r(wp[0], wp[1], (q & 3u) * 8u);
+                    const uint32_t e = q + 4u + bs;
+                    if ((int32_t)bs < 32 || e < q || e > room32) {
+                        ended = 1; break;
+                    }
+                    if (e > av32) atomicOr(&A.status[0], 2u);                     /* record longer than the staged window */
+                    if (n < ITX_POS_SLOTS) pos[n] = (uint16_t)q;
+                    n++;
+                    q = e;
+                }
+            }
+            n = __shfl_sync(0xffffffffu, n, 0); ended = __shfl_sync(0xffffffffu, ended, 0);
+            q = __shfl_sync(0xffffffffu, q, 0);
+            __syncwarp();
+            const itx_src_stage S{buf, A.b, c_lo, nb};
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint32_t ro = pos[j];
+                uint32_t x[9]; S.core(c_lo + ro, x);
+                const itx_tuple T = itx_decode_record(S, c_lo + ro, x, (uint32_t)(c_lo - lo) + ro, A.tid, A.n_ref, A.o);
+                if (n_out + j < A.S) __stcs(reinterpret_cast<uint4 *>(out + n_out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
+            }
+            n_out += n;
+            if (ended) { p = ITX_OFF_END; break; }
+            p = c_lo + q;
         }
-        if (lane == 0) { A.entry[i] = entry0; A.exit_[i] = exitX; A.nrec[i] = total; }
+        if (lane == 0) { A.exit_[i] = p; A.nrec[i] = n_out < A.S ? n_out : A.S; }
     }
 }
 

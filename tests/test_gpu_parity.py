@@ -106,10 +106,10 @@ def assert_same_tables(ix, ora):
                 assert np.array_equal(ix.coverage(i, u), want), (i, u)
 
 
-@pytest.mark.parametrize("chunk", [1024, 2048], ids=["thread_kernel", "tma_ring_kernel"])
+@pytest.mark.parametrize("chunk", [1024, 8192], ids=["thread_kernel", "tma_span_kernel"])
 @pytest.mark.parametrize("case", SYN, ids=[c[0] for c in SYN])
 def test_cuda_path_matches_oracle(case, chunk, worlds):
-    """chunk 1024 runs k_decode (one thread per chunk); chunks that are whole 2 KiB tiles run k_decode_tiles"""
+    """chunk 1024 runs k_decode (one thread per chunk); chunks that are whole 4 KiB stages run k_decode_span"""
     name, shape, n_rmsk, mode, n_units, kw = case
     s, (cs, rs, rm), _ = worlds(shape, n_rmsk)
     buf, n, nrec = s.stream(mode, n_units)
@@ -130,7 +130,7 @@ def test_cuda_path_matches_oracle(case, chunk, worlds):
     ix.close()
 
 
-@pytest.mark.parametrize("chunk,window", [(256, 1 << 16), (448, 1 << 18), (2048, 1 << 16), (4096, 1 << 30), (32768, 1 << 20), (65536, 1 << 22)])
+@pytest.mark.parametrize("chunk,window", [(256, 1 << 16), (448, 1 << 18), (4096, 1 << 16), (4096, 1 << 30), (32768, 1 << 20), (65536, 1 << 22), (1 << 20, 1 << 23)])
 def test_chunk_and_window_size_never_change_the_answer(chunk, window, worlds):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     buf, n, nrec = s.stream(1, 60000)
@@ -261,7 +261,7 @@ def test_filter_mode_counts_per_locus(worlds):
     ix.close()
 
 
-@pytest.mark.parametrize("chunk,window", [(1024, 1 << 18), (2048, 1 << 18), (32768, 1 << 30), (65536, 1 << 20)])
+@pytest.mark.parametrize("chunk,window", [(1024, 1 << 18), (4096, 1 << 18), (32768, 1 << 30), (65536, 1 << 20)])
 def test_records_of_every_size(chunk, window, tmp_path):
     """records from 60 bytes to 70 KB: longer than a chunk (chunks without any record start), than the
     decode ring (global-memory path inside k_decode_tiles, ring restart after the jump) and straddling windows"""
@@ -288,7 +288,7 @@ def test_window_smaller_than_a_record_is_refused(tmp_path):
     tabs = mixed_records.tables(str(tmp_path))
     raw, nrec = mixed_records.make()
     ix = capi.Index(*tabs)
-    ix.tune(chunk_bytes=2048, window_bytes=1 << 16)          # 64 KiB windows, 70 KB records
+    ix.tune(chunk_bytes=4096, window_bytes=1 << 16)          # 64 KiB windows, 70 KB records
     with pytest.raises(capi.ItxError) as e:
         ix.scan_stream(raw, capi.default_opts())
     assert e.value.code == -6 and "longer than the staged window" in str(e.value)
