@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
 
 /* ------------------------------------------------------------------ K1: one pass, TMA-staged, lane-parallel chain */
 #define ITX_DW 8                           /* warps per CTA */
-#define ITX_CLAIM 8u                       /* chunks claimed per atomic on the work counters */
+#define ITX_CLAIM 8u                       /* work units claimed per atomic on the work counters */
+#define ITX_PART 128u                      /* tuple slots per k_overlap work unit */
 #define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
 #define ITX_DECODE_SMEM 0
 
@@ -192,30 +193,37 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
             }
             if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
             parity ^= 1u;
-            /* lane 0 walks the chain of this stage; every block_size word it reads lies inside the staged bytes */
+            /* the chain of this stage, out of shared memory.  Reads usually have one length, so instead of one
+             * record per step the warp tests 32 predicted starts at once: lane k looks at q + k * size and the run
+             * of lanes that find the same block_size there is accepted in one step (a run of 1 is the plain walk).
+             * Every block_size word read lies inside the staged bytes (the margin is larger than a core). */
             uint32_t n = 0, ended = 0;
             uint32_t q = (uint32_t)(p - c_lo);
-            if (lane == 0) {
+            {
                 const uint32_t qh = (uint32_t)(c_hi - c_lo);
-                const unsigned long long room = A.len - c_lo;                     /* record end must be <= room */
+                const unsigned long long room = A.len - c_lo;                     /* a record must end at or before room */
                 const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
                 const uint32_t av32 = A.avail > c_lo ? (A.avail - c_lo > 0x7fffffffull ? 0x7fffffffu : (uint32_t)(A.avail - c_lo)) : 0u;
                 while (q < qh) {
                     if (q + 36u > room32) { ended = 1; break; }
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
-                    const uint32_t bs = itx_funnel_r(wp[0], wp[1], (q & 3u) * 8u);
-                    const uint32_t e = q + 4u + bs;
-                    if ((int32_t)bs < 32 || e < q || e > room32) {
-                        ended = 1; break;
+                    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
+                    const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
+                    const uint32_t sz = bs0 + 4u;
+                    if ((int32_t)bs0 < 32 || q + sz < q || q + sz > room32) { ended = 1; break; }
+                    const unsigned long long pk = (unsigned long long)q + (unsigned long long)lane * sz;
+                    bool same = false;
+                    if (pk < qh && pk + sz <= room32) {
+                        const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + ((uint32_t)pk & ~3u));
+                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) == bs0;
                     }
-                    if (e > av32) atomicOr(&A.status[0], 2u);                     /* record longer than the staged window */
-                    if (n < ITX_POS_SLOTS) pos[n] = (uint16_t)q;
-                    n++;
-                    q = e;
+                    const uint32_t m = __ballot_sync(0xffffffffu, same);           /* bit 0 is always set */
+                    const uint32_t run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
+                    if (lane < run && n + lane < ITX_POS_SLOTS) pos[n + lane] = (uint16_t)pk;
+                    n += run;
+                    q += run * sz;
+                    if (q > av32 && lane == 0) atomicOr(&A.status[0], 2u);         /* record longer than the staged window */
                 }
             }
-            n = __shfl_sync(0xffffffffu, n, 0); ended = __shfl_sync(0xffffffffu, ended, 0);
-            q = __shfl_sync(0xffffffffu, q, 0);
             __syncwarp();
             const itx_src_stage S{buf, A.b, c_lo, nb};
             for (uint32_t j = lane; j < n; j += 32) {
@@ -290,18 +298,23 @@ __global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
     for (int k = 0; k < 13; k++) c[k] = 0;
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const itx_src_global G{A.b};
-    uint32_t i = 0, i_end = 0;
-    for (;; i++) {
-        if (i >= i_end) {                                  /* claim a batch of chunks: one atomic per ITX_CLAIM chunks */
-            if (lane == 0) i = atomicAdd(A.work, ITX_CLAIM);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (i >= A.nchunks) break;
-            i_end = i + ITX_CLAIM < A.nchunks ? i + ITX_CLAIM : A.nchunks;
+    /* work unit = ITX_PART consecutive tuple slots of one chunk; a warp claims ITX_CLAIM units per atomic */
+    const uint32_t ppc = (A.S + ITX_PART - 1) / ITX_PART, n_units = A.nchunks * ppc;
+    uint32_t u = 0, u_end = 0;
+    for (;; u++) {
+        if (u >= u_end) {
+            if (lane == 0) u = atomicAdd(A.work, ITX_CLAIM);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_units) break;
+            u_end = u + ITX_CLAIM < n_units ? u + ITX_CLAIM : n_units;
         }
-        const uint32_t n = A.nrec[i];
+        const uint32_t i = u / ppc, part = u - i * ppc;
+        const uint32_t nr = A.nrec[i];
+        if (part * ITX_PART >= nr) { u += ppc - part - 1; continue; }       /* the rest of this chunk's units are empty */
+        const uint32_t n = nr < (part + 1) * ITX_PART ? nr : (part + 1) * ITX_PART;
         const itx_tuple *tp = A.tuples + (size_t)i * A.S;
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        for (uint32_t j0 = part * ITX_PART; j0 < n; j0 += 32) {
             const uint32_t j = j0 + lane; const bool valid = j < n;
             itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
             if (valid) { const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(tp + j)); T.start = v.x; T.end = v.y; T.info = v.z; T.rec_off = v.w; }
