@@ -337,8 +337,8 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         }
         size_t hist = 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4;
         bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
-        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 3));
-        uint32_t need_blocks = (n + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
+        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
+        uint32_t need_blocks = (n * ((cu->S + ITX_PART - 1) / ITX_PART) + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
         if (smem) {
             if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
             k_overlap<true><<<blocks, 256, hist, cu->stream>>>(B);

@@ -284,7 +284,7 @@ struct itx_overlap_args {
 };
 
 template <bool SMEM_HIST>
-__global__ void __launch_bounds__(256) k_overlap(const itx_overlap_args A) {
+__global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
     extern __shared__ uint32_t sh_hist[];
     __shared__ unsigned long long sh_cnt[13];
     const itx_dev_index &D = A.D;

@@ -285,7 +285,7 @@ ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
     const uint32_t a = (uint32_t)s >> (17u + 3u * l);
     return ((uint64_t)(5u - l) << 48) | ((uint64_t)(0xffffu - a) << 32) | (uint64_t)row;
 }
-ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, long long i) {
+ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, uint32_t i) {
 #if defined(__CUDA_ARCH__)
     const int4 v = __ldg(reinterpret_cast<const int4 *>(D.iv + i));
     itx_iv e; e.start = v.x; e.end = v.y; e.pmax = v.z; e.row = (uint32_t)v.w;
@@ -296,11 +296,11 @@ ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, long long i) {
 }
 /* first element of chromosome c with start >= fe (0 < fe <= chromosome size): one position bucket, then a
  * short binary search inside it */
-ITX_HD long long itx_upper(const itx_dev_index &D, int32_t c, int32_t fe) {
+ITX_HD uint32_t itx_upper(const itx_dev_index &D, int32_t c, int32_t fe) {
     const uint32_t *bk = D.bucket + D.chrom_bucket[c] + (fe >> ITX_BSH);
-    long long lo = bk[0], hi = bk[1];
+    uint32_t lo = bk[0], hi = bk[1];
     while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
+        const uint32_t mid = (lo + hi) >> 1;
         if (D.iv[mid].start < fe) lo = mid + 1; else hi = mid;
     }
     return lo;
@@ -308,6 +308,7 @@ ITX_HD long long itx_upper(const itx_dev_index &D, int32_t c, int32_t fe) {
 ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
     int32_t s = (int32_t)start > es ? (int32_t)start : es, e = (int32_t)end < ee ? (int32_t)end : ee;
     int32_t r = e - s; if (r < 0) r = 0;
+    if (r != 0 && (uint32_t)r == end - start) return 1.0f;            /* fragment inside the element: x / x == 1 exactly */
     float den = (float)(end - start);
     return den == 0.0f ? 0.0f : (float)r / den;
 }
@@ -322,11 +323,11 @@ ITX_HD bool itx_clamp(const itx_dev_index &D, int32_t c, uint32_t start, uint32_
 /* n > 1 hits: walk the list in binKeeper order (key ascending) without materialising it -- once per list
  * position the candidates are re-walked for the smallest key above the previous one -- and apply the
  * "last ascent" rule.  Rare (nested / abutting repeats), so it is kept out of line. */
-ITX_HDN long long itx_select_multi(const itx_dev_index &D, long long lo, long long up, int32_t fs, uint32_t start, uint32_t end, int32_t n, float *tcov) {
+ITX_HDN long long itx_select_multi(const itx_dev_index &D, uint32_t lo, uint32_t up, int32_t fs, uint32_t start, uint32_t end, int32_t n, float *tcov) {
     uint64_t prev_key = 0; bool have_prev = false; float prev_cov = 0.0f, best_cov = 0.0f; long long sel = -1;
     for (int32_t k = 0; k < n; k++) {
         uint64_t bk = ~0ull; long long bi = -1; itx_iv be; be.start = be.end = 0; be.pmax = 0; be.row = 0;
-        for (long long i = up - 1; i >= lo; i--) {
+        for (uint32_t i = up; i-- > lo;) {
             const itx_iv e = itx_ld_iv(D, i);
             if (!(e.pmax > fs)) break;
             if (e.end > fs && e.start < e.end) {
@@ -350,11 +351,11 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
     *n_hits = 0; *tcov = 0.0f;
     int32_t fs, fe;
     if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
-    const long long lo = D.chrom_off[c];
-    const long long up = itx_upper(D, c, fe);
-    int32_t n = 0; long long i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    const uint32_t lo = (uint32_t)D.chrom_off[c];
+    const uint32_t up = itx_upper(D, c, fe);
+    int32_t n = 0; uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
     itx_iv e0, e1, e2, e3; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0; e2 = e0; e3 = e0;
-    for (long long i = up - 1; i >= lo; i--) {
+    for (uint32_t i = up; i-- > lo;) {
         const itx_iv e = itx_ld_iv(D, i);
         if (!(e.pmax > fs)) break;
         if (e.end > fs && e.start < e.end) {
@@ -364,17 +365,28 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
     }
     *n_hits = n;
     if (n == 0) return -1;
-    if (n == 1) { *tcov = itx_cov(start, end, e0.start, e0.end); *sel_iv = e0; return i0; }
+    if (n == 1) { *tcov = itx_cov(start, end, e0.start, e0.end); *sel_iv = e0; return (long long)i0; }
+    if (n == 2) {
+        /* list order = key order; the second is taken only if it covers more than the first */
+        const bool first0 = itx_order_key(e0.start, e0.end, e0.row) < itx_order_key(e1.start, e1.end, e1.row);
+        const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
+        const float ca = first0 ? c0 : c1, cb = first0 ? c1 : c0;
+        const bool take_b = cb > ca;                        /* ca > 0 always, so the first is taken before */
+        const bool pick0 = first0 != take_b;
+        *tcov = take_b ? cb : ca;
+        *sel_iv = pick0 ? e0 : e1;
+        return (long long)(pick0 ? i0 : i1);
+    }
     if (n > 4) {
         const long long sel = itx_select_multi(D, lo, up, fs, start, end, n, tcov);
-        if (sel >= 0) *sel_iv = itx_ld_iv(D, sel);
+        if (sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)sel);
         return sel;
     }
     const uint64_t NOKEY = ~0ull;
     uint64_t k0 = itx_order_key(e0.start, e0.end, e0.row), k1 = itx_order_key(e1.start, e1.end, e1.row);
-    uint64_t k2 = n > 2 ? itx_order_key(e2.start, e2.end, e2.row) : NOKEY, k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
+    uint64_t k2 = itx_order_key(e2.start, e2.end, e2.row), k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
     const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
-    const float c2 = n > 2 ? itx_cov(start, end, e2.start, e2.end) : 0.0f, c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
+    const float c2 = itx_cov(start, end, e2.start, e2.end), c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
     float prev = 0.0f, best = 0.0f; int32_t sel = -1;
     for (int32_t step = 0; step < n; step++) {
         /* the unvisited hit with the smallest key */
@@ -390,16 +402,16 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
     *tcov = best;
     if (sel < 0) return -1;
     *sel_iv = sel == 0 ? e0 : (sel == 1 ? e1 : (sel == 2 ? e2 : e3));
-    return sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3));
+    return (long long)(sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3)));
 }
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
 ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
     int32_t fs, fe;
     if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
-    const long long lo = D.chrom_off[c];
-    const long long up = itx_upper(D, c, fe);
+    const uint32_t lo = (uint32_t)D.chrom_off[c];
+    const uint32_t up = itx_upper(D, c, fe);
     uint64_t bk = ~0ull; long long bi = -1;
-    for (long long i = up - 1; i >= lo; i--) {
+    for (uint32_t i = up; i-- > lo;) {
         const itx_iv e = itx_ld_iv(D, i);
         if (!(e.pmax > fs)) break;
         if (e.end > fs && e.start < e.end) {
@@ -413,9 +425,9 @@ ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start
 ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, int32_t e, int32_t fold) {
     int32_t fs, fe;
     if (!itx_clamp(D, c, (uint32_t)s, (uint32_t)e, &fs, &fe)) return false;
-    const long long lo = D.chrom_off[c];
-    const long long up = itx_upper(D, c, fe);
-    for (long long i = up - 1; i >= lo; i--) {
+    const uint32_t lo = (uint32_t)D.chrom_off[c];
+    const uint32_t up = itx_upper(D, c, fe);
+    for (uint32_t i = up; i-- > lo;) {
         const itx_iv v = itx_ld_iv(D, i);
         if (!(v.pmax > fs)) break;
         if (v.end > fs && v.start < v.end && D.sub_fold[D.meta[i].sub] != fold) return true;
