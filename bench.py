@@ -282,9 +282,10 @@ def main():
     if rank == 0:
         sampler.start()
         sampler.wait_first()
-        for _ in range(2):          # keep the device busy until the sampler is running (untimed)
-            step()
-        L.itx_dev_sync()
+    barrier()
+    for _ in range(2):              # every rank: keep the devices busy until the sampler is running (untimed)
+        step()
+    L.itx_dev_sync()
     barrier()
     dec = ovl = 0.0
     launches = 0
