@@ -269,10 +269,11 @@ def main():
 
     def step():
         ix.reset()
-        cnt = ix.scan_bam_device(h, dbuf, n, opts)
+        cnt = ix.scan_bam_device(h, dbuf, n, opts)     # this rank's counters
         if world > 1:
-            ix.allreduce_counts()
+            step.global_cnt = ix.allreduce_counts()    # the job's counters after the one allreduce
         return cnt
+    step.global_cnt = None
 
     for _ in range(a.warmup):
         step()
@@ -310,6 +311,7 @@ def main():
         tot = torch.tensor([float(nrec)], dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         total_rec = int(tot[0])
+        assert step.global_cnt[0] + step.global_cnt[1] == total_rec, (step.global_cnt, total_rec)   # the allreduce summed every shard
     else:
         total_rec = nrec
     value = total_rec * a.steps / (el_ms * 1e-3)
@@ -319,8 +321,6 @@ def main():
     # roofline of the dominant kernel (per step, this rank)
     peak, peak_src = peaks()
     R, F, H, HU = cnt[0] + cnt[1], cnt[6], cnt[9] + cnt[12], cnt[10]
-    if world > 1:   # counts were allreduced: per-rank share for the per-launch arithmetic
-        R, F, H, HU = nrec, F // world, H // world, HU // world
     k1_bytes = n + 16 * R
     k2_bytes = 16 * R + 16 * F + 16 * H + (4 + 8) * H + 8 * HU
     dec_ms, ovl_ms = dec / a.steps, ovl / a.steps

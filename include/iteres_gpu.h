@@ -160,7 +160,8 @@ int itx_tune(itx_index *ix, uint32_t chunk_bytes, uint64_t window_bytes, int32_t
 #define ITX_NCCL_ID_BYTES 128
 int itx_comm_unique_id(uint8_t id[ITX_NCCL_ID_BYTES], char err[ITX_ERRLEN]);
 int itx_comm_init(itx_index *ix, const uint8_t id[ITX_NCCL_ID_BYTES], int rank, int nranks, char err[ITX_ERRLEN]);
-int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]);
+int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]);   /* afterwards itx_get_counters returns the global sums */
+void itx_get_counters(const itx_index *ix, uint64_t cnt[13]);
 void itx_comm_destroy(itx_index *ix);
 
 /* ---- raw device helpers for benchmarks (so a harness needs no other CUDA binding) ---- */

@@ -54,7 +54,7 @@ itx_bam_header_len itx_bam_header_free itx_scan_bam_device itx_scan_cpg itx_sync
 itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_subfam itx_n_fam itx_n_class
 itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
 itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
-itx_comm_allreduce_counts itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
+itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
 itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync""".split()
 
 _lib = None
@@ -123,6 +123,7 @@ def lib():
         L.itx_comm_unique_id.argtypes = [vp, cp]
         L.itx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, cp]
         L.itx_comm_allreduce_counts.argtypes = [vp, cp]
+        L.itx_get_counters.argtypes = [vp, C.POINTER(u64)]
         L.itx_comm_destroy.argtypes = [vp]
         L.itx_dev_alloc.restype = vp
         L.itx_dev_alloc.argtypes = [u64]
@@ -338,3 +339,5 @@ class Index(IndexBase):
     def allreduce_counts(self):
         err = C.create_string_buffer(ERRLEN)
         self._ck(self.L.itx_comm_allreduce_counts(self.h, err), err)
+        self.L.itx_get_counters(self.h, self.cnt)
+        return list(self.cnt)

@@ -23,7 +23,7 @@ struct itx_cuda {
     int sm_count; size_t smem_optin;
     /* index */
     itx_dev_index D;
-    void *d_iv, *d_bucket, *d_chrom_bucket, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
+    void *d_iv, *d_bucket, *d_chrom_bucket, *d_cinfo, *d_sinfo, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
     void *d_sub_len, *d_sub_bp_off, *d_sub_fold;
     /* counter block */
     void *d_u64; size_t n_u64;           /* cnt[16] + grp */
@@ -74,7 +74,7 @@ template <typename T> static int upload(void **dst, const T *src, size_t n, char
 static void cuda_free_all(itx_cuda *cu) {
     if (!cu) return;
     cudaSetDevice(cu->device);
-    void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
+    void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush};
@@ -139,7 +139,8 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaStreamCreateWithFlags(&cu->copy_stream, cudaStreamNonBlocking));
         const size_t ne = (size_t)ix->n_elem; const int32_t nc = ix->chroms.n, ns = ix->subs.n, nf = ix->fams.n, ncl = ix->clas.n;
         if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_bucket, ix->bucket, (size_t)ix->n_bucket, err) ||
-            upload(&cu->d_chrom_bucket, ix->chrom_bucket, (size_t)nc + 1, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
+            upload(&cu->d_chrom_bucket, ix->chrom_bucket, (size_t)nc + 1, err) || upload(&cu->d_cinfo, ix->cinfo, (size_t)nc, err) ||
+            upload(&cu->d_sinfo, ix->sinfo, (size_t)ns, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
             upload(&cu->d_meta2, ix->meta2, ne, err) || upload(&cu->d_chrom_off, ix->chrom_off, (size_t)nc + 1, err) ||
             upload(&cu->d_chrom_size, ix->chrom_size, (size_t)nc, err) || upload(&cu->d_sub_len, ix->sub_len, (size_t)ns, err) ||
             upload(&cu->d_sub_bp_off, ix->sub_bp_off, (size_t)ns + 1, err) || upload(&cu->d_sub_fold, ix->sub_fold, (size_t)ns, err)) goto fail;
@@ -170,7 +171,8 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
-        D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
+        D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
+        D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
         D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool;
         D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix->stat_mode;
@@ -746,9 +748,13 @@ extern "C" int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     if (!r && cu->n_u32) r = ar(cu->d_u32, cu->d_u32, cu->n_u32, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
     int r2 = ge(); if (!r) r = r2;
     if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclAllReduce failed (%d)", r); return ITX_ENODEV; }
+    unsigned long long hc[16];
+    CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaStreamSynchronize(cu->stream));
+    for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k];
     return ITX_OK;
 }
+extern "C" void itx_get_counters(const itx_index *ix, uint64_t cnt[13]) { memcpy(cnt, ix->cnt, sizeof ix->cnt); }
 extern "C" void itx_comm_destroy(itx_index *ix) {
     itx_cuda *cu = ix ? ix->cu : NULL;
     if (!cu || !cu->nccl_comm) return;

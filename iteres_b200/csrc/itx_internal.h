@@ -40,9 +40,14 @@ typedef struct { int32_t start, end, pmax; uint32_t row; } itx_iv;
 #define ITX_BSH 10
 typedef struct { uint32_t cons_start, cons_end, row, sub; } itx_meta;     /* 16 B, one load */
 typedef struct { int32_t fam, cla; } itx_meta2;
+/* per chromosome: first element, first bucket, size -- one 16-byte load per query */
+typedef struct { uint32_t off, bucket; int32_t size; uint32_t n; } itx_chrominfo;
+/* per subfamily: consensus length (0 = no coverage vector), offset of its difference array, case-folded name id */
+typedef struct { uint32_t len; int32_t fold; unsigned long long bp_off; } itx_subinfo;
 
 typedef struct {
     const itx_iv *iv; const itx_meta *meta; const itx_meta2 *meta2;
+    const itx_chrominfo *cinfo; const itx_subinfo *sinfo;
     const uint32_t *bucket; const long long *chrom_bucket;   /* bucket[chrom_bucket[c] + (pos >> ITX_BSH)], (size >> ITX_BSH) + 2 entries per chromosome */
     const long long *chrom_off;          /* n_chrom + 1 */
     const int32_t *chrom_size;           /* binKeeper maxPos (from the chrom size file) */
@@ -116,6 +121,7 @@ struct itx_index {
     long long n_elem, n_rows;
     itx_iv *iv; itx_meta *meta; itx_meta2 *meta2; int32_t *el_chrom;   /* sorted order */
     uint32_t *bucket; long long *chrom_bucket; long long n_bucket;
+    itx_chrominfo *cinfo; itx_subinfo *sinfo;
     long long *row2el;                   /* rmsk row -> sorted element index or -1 */
     /* host mirrors of the device results (filled by itx_sync_counts) */
     uint64_t cnt[13];

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
                     const unsigned long long p = lo + T.rec_off;
                     uint32_t x[9]; G.core(p, x);
                     uint32_t bad = 0;
-                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
                     if (bad) atomicAdd(&D.status[2], bad);
                 }
             }
@@ -359,10 +359,11 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
                         itx_red_u64(&D.grp[hs], 1ull); itx_red_u64(&D.grp[hf], 1ull); itx_red_u64(&D.grp[hc], 1ull);
                         if (uniq) { itx_red_u64(&D.grp[hs + 1], 1ull); itx_red_u64(&D.grp[hf + 1], 1ull); itx_red_u64(&D.grp[hc + 1], 1ull); }
                     }
-                    const uint32_t L = D.sub_len[m.sub];
+                    const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(D.sinfo + m.sub));      /* {len, fold, bp_off} */
+                    const uint32_t L = sv.x;
                     uint32_t ja, jb;
                     if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
-                        const unsigned long long off = D.sub_bp_off[m.sub];
+                        const unsigned long long off = (unsigned long long)sv.z | ((unsigned long long)sv.w << 32);
                         itx_red_u32(&D.bp_diff[off + ja], 1u); itx_red_u32(&D.bp_diff[off + jb], 0xffffffffu);
                         if (uniq) { itx_red_u32(&D.bp_diff_u[off + ja], 1u); itx_red_u32(&D.bp_diff_u[off + jb], 0xffffffffu); }
                     }

@@ -294,16 +294,24 @@ ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, uint32_t i) {
     return D.iv[i];
 #endif
 }
-/* first element of chromosome c with start >= fe (0 < fe <= chromosome size): one position bucket, then a
- * short binary search inside it */
-ITX_HD uint32_t itx_upper(const itx_dev_index &D, int32_t c, int32_t fe) {
-    const uint32_t *bk = D.bucket + D.chrom_bucket[c] + (fe >> ITX_BSH);
-    uint32_t lo = bk[0], hi = bk[1];
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (D.iv[mid].start < fe) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+/* The candidates of the clamped query [fs, fe) on a chromosome are walked DOWNWARD from the end of fe's
+ * position bucket: elements above that have start >= fe; the walk skips the few in the bucket itself that
+ * still start at or after fe and stops as soon as the running maximum of `end` drops to fs or below. */
+struct itx_query { int32_t fs, fe; uint32_t lo, top; };      /* walk i = top-1 .. lo */
+ITX_HD bool itx_query_open(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_query *q) {
+#if defined(__CUDA_ARCH__)
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(D.cinfo + c));
+    const uint32_t off = (uint32_t)v.x, bucket = (uint32_t)v.y; const int32_t size = v.z;
+#else
+    const uint32_t off = D.cinfo[c].off, bucket = D.cinfo[c].bucket; const int32_t size = D.cinfo[c].size;
+#endif
+    int32_t a = (int32_t)start, b = (int32_t)end;
+    if (a < 0) a = 0;
+    if (b > size) b = size;
+    if (!(a < b)) return false;
+    q->fs = a; q->fe = b; q->lo = off;
+    q->top = D.bucket[bucket + ((uint32_t)b >> ITX_BSH) + 1];
+    return true;
 }
 ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
     int32_t s = (int32_t)start > es ? (int32_t)start : es, e = (int32_t)end < ee ? (int32_t)end : ee;
@@ -312,25 +320,18 @@ ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
     float den = (float)(end - start);
     return den == 0.0f ? 0.0f : (float)r / den;
 }
-/* clamp the query to the chromosome the way binKeeperFind does; false = empty */
-ITX_HD bool itx_clamp(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *fs, int32_t *fe) {
-    int32_t a = (int32_t)start, b = (int32_t)end, cs = D.chrom_size[c];
-    if (a < 0) a = 0;
-    if (b > cs) b = cs;
-    *fs = a; *fe = b;
-    return a < b;
-}
 /* n > 1 hits: walk the list in binKeeper order (key ascending) without materialising it -- once per list
  * position the candidates are re-walked for the smallest key above the previous one -- and apply the
  * "last ascent" rule.  Rare (nested / abutting repeats), so it is kept out of line. */
-ITX_HDN long long itx_select_multi(const itx_dev_index &D, uint32_t lo, uint32_t up, int32_t fs, uint32_t start, uint32_t end, int32_t n, float *tcov) {
+ITX_HDN long long itx_select_multi(const itx_dev_index &D, const itx_query &Q, uint32_t start, uint32_t end, int32_t n, float *tcov) {
+    const int32_t fs = Q.fs, fe = Q.fe;
     uint64_t prev_key = 0; bool have_prev = false; float prev_cov = 0.0f, best_cov = 0.0f; long long sel = -1;
     for (int32_t k = 0; k < n; k++) {
         uint64_t bk = ~0ull; long long bi = -1; itx_iv be; be.start = be.end = 0; be.pmax = 0; be.row = 0;
-        for (uint32_t i = up; i-- > lo;) {
+        for (uint32_t i = Q.top; i-- > Q.lo;) {
             const itx_iv e = itx_ld_iv(D, i);
             if (!(e.pmax > fs)) break;
-            if (e.end > fs && e.start < e.end) {
+            if (e.end > fs && e.start < fe && e.start < e.end) {
                 const uint64_t key = itx_order_key(e.start, e.end, e.row);
                 if ((!have_prev || key > prev_key) && key < bk) { bk = key; bi = i; be = e; }
             }
@@ -349,16 +350,15 @@ ITX_HDN long long itx_select_multi(const itx_dev_index &D, uint32_t lo, uint32_t
  * visited in list order (order key ascending); longer lists take itx_select_multi.  Exact for any n. */
 ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     *n_hits = 0; *tcov = 0.0f;
-    int32_t fs, fe;
-    if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
-    const uint32_t lo = (uint32_t)D.chrom_off[c];
-    const uint32_t up = itx_upper(D, c, fe);
+    itx_query Q;
+    if (!itx_query_open(D, c, start, end, &Q)) return -1;
+    const int32_t fs = Q.fs, fe = Q.fe;
     int32_t n = 0; uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
     itx_iv e0, e1, e2, e3; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0; e2 = e0; e3 = e0;
-    for (uint32_t i = up; i-- > lo;) {
+    for (uint32_t i = Q.top; i-- > Q.lo;) {
         const itx_iv e = itx_ld_iv(D, i);
         if (!(e.pmax > fs)) break;
-        if (e.end > fs && e.start < e.end) {
+        if (e.end > fs && e.start < fe && e.start < e.end) {
             if (n == 0) { i0 = i; e0 = e; } else if (n == 1) { i1 = i; e1 = e; } else if (n == 2) { i2 = i; e2 = e; } else if (n == 3) { i3 = i; e3 = e; }
             n++;
         }
@@ -378,7 +378,7 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
         return (long long)(pick0 ? i0 : i1);
     }
     if (n > 4) {
-        const long long sel = itx_select_multi(D, lo, up, fs, start, end, n, tcov);
+        const long long sel = itx_select_multi(D, Q, start, end, n, tcov);
         if (sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)sel);
         return sel;
     }
@@ -406,15 +406,14 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
 }
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
 ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
-    int32_t fs, fe;
-    if (!itx_clamp(D, c, start, end, &fs, &fe)) return -1;
-    const uint32_t lo = (uint32_t)D.chrom_off[c];
-    const uint32_t up = itx_upper(D, c, fe);
+    itx_query Q;
+    if (!itx_query_open(D, c, start, end, &Q)) return -1;
+    const int32_t fs = Q.fs, fe = Q.fe;
     uint64_t bk = ~0ull; long long bi = -1;
-    for (uint32_t i = up; i-- > lo;) {
+    for (uint32_t i = Q.top; i-- > Q.lo;) {
         const itx_iv e = itx_ld_iv(D, i);
         if (!(e.pmax > fs)) break;
-        if (e.end > fs && e.start < e.end) {
+        if (e.end > fs && e.start < fe && e.start < e.end) {
             const uint64_t key = itx_order_key(e.start, e.end, e.row);
             if (key < bk) { bk = key; bi = i; *sel_iv = e; }
         }
@@ -423,14 +422,13 @@ ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start
 }
 /* does [s, e) on chromosome c touch any element whose case-folded subfamily differs from `fold`? */
 ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, int32_t e, int32_t fold) {
-    int32_t fs, fe;
-    if (!itx_clamp(D, c, (uint32_t)s, (uint32_t)e, &fs, &fe)) return false;
-    const uint32_t lo = (uint32_t)D.chrom_off[c];
-    const uint32_t up = itx_upper(D, c, fe);
-    for (uint32_t i = up; i-- > lo;) {
+    itx_query Q;
+    if (!itx_query_open(D, c, (uint32_t)s, (uint32_t)e, &Q)) return false;
+    const int32_t fs = Q.fs, fe = Q.fe;
+    for (uint32_t i = Q.top; i-- > Q.lo;) {
         const itx_iv v = itx_ld_iv(D, i);
         if (!(v.pmax > fs)) break;
-        if (v.end > fs && v.start < v.end && D.sub_fold[D.meta[i].sub] != fold) return true;
+        if (v.end > fs && v.start < fe && v.start < v.end && D.sinfo[D.meta[i].sub].fold != fold) return true;
     }
     return false;
 }

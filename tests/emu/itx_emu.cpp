@@ -57,7 +57,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     D.n_chrom = nc; D.n_elem = ix.n_elem;
     D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data();
     D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix.stat_mode;
-    D.sub_len = ix.sub_len; D.sub_bp_off = ix.sub_bp_off; D.sub_fold = ix.sub_fold;
+    D.sub_len = ix.sub_len; D.sub_bp_off = ix.sub_bp_off; D.sub_fold = ix.sub_fold; D.cinfo = ix.cinfo; D.sinfo = ix.sinfo;
     D.cnt = E->u64.data(); D.grp = D.cnt + 16; D.bp_diff = E->bp_diff.data(); D.bp_diff_u = E->bp_diff_u.data();
     D.el_cnt = E->el_cnt.data(); D.el_cnt_u = E->el_cnt_u.data();
     D.grp_cpg = E->grp_cpg.data(); D.el_cpg = E->el_cpg.data(); D.grp_cpg_score = E->grp_cpg_score.data(); D.bp_cpg = E->bp_cpg.data(); D.el_cpg_score = E->el_cpg_score.data();
@@ -210,7 +210,7 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
                 if (sel >= 0 && tcov < o.minCoverage) sel = -1;
                 if (sel >= 0 && o.diffSubfam && (info & ITX_F_HASXA)) {
                     const uint64_t p = lo + T.rec_off; uint32_t x[9]; G.core(p, x); uint32_t bad = 0;
-                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sub_fold[D.meta[sel].sub], (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
                     D.status[2] += bad;
                 }
             }
