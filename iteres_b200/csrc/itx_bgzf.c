@@ -47,6 +47,7 @@ typedef struct {
     pthread_t *th; int nth; int generation, pending, stop;
     /* the current job */
     const uint8_t *file; const itx_bgzf_block *blk; uint64_t b0, b1; uint8_t *dst; uint64_t next; int failed;
+    int mode;                            /* 0: inflate blocks [b0,b1)   1: copy bytes [b0,b1) of file to dst in 1 MiB pieces */
     double busy_max;
 } pool_t;
 static pool_t g_pool; static int g_pool_init = 0; static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -65,6 +66,15 @@ static void *worker(void *arg) {
         seen = P->generation;
         pthread_mutex_unlock(&P->mu);
         double t0 = mono_ms(); int failed = !zinit;
+        if (P->mode == 1) {
+            failed = 0;
+            for (;;) {
+                uint64_t o = __atomic_fetch_add(&P->next, (uint64_t)1 << 20, __ATOMIC_RELAXED);
+                if (o >= P->b1) break;
+                uint64_t e = o + ((uint64_t)1 << 20) < P->b1 ? o + ((uint64_t)1 << 20) : P->b1;
+                memcpy(P->dst + (o - P->b0), P->file + o, (size_t)(e - o));
+            }
+        } else
         for (;;) {
             uint64_t i = __atomic_fetch_add(&P->next, 4, __ATOMIC_RELAXED);   /* four blocks per grab */
             if (i >= P->b1) break;
@@ -103,7 +113,15 @@ static void pool_stop(void) {
     free(P->th); P->th = NULL; P->nth = 0;
 }
 
+static int pool_run(int mode, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms);
 int itx_bgzf_inflate_range(const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms) {
+    return pool_run(0, file, blocks, b0, b1, dst, nth, busy_ms);
+}
+/* dst[0 .. o1-o0) = file[o0 .. o1) with nth threads (staging a compressed window into pinned memory) */
+int itx_parallel_copy(const uint8_t *file, uint64_t o0, uint64_t o1, uint8_t *dst, int nth) {
+    return pool_run(1, file, NULL, o0, o1, dst, nth, NULL);
+}
+static int pool_run(int mode, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms) {
     if (b1 <= b0) return ITX_OK;
     pthread_mutex_lock(&g_pool_mu);
     if (g_pool_init && g_pool.nth != nth) { pool_stop(); g_pool_init = 0; }
@@ -111,7 +129,7 @@ int itx_bgzf_inflate_range(const uint8_t *file, const itx_bgzf_block *blocks, ui
     pool_t *P = &g_pool;
     if (P->nth == 0) { pthread_mutex_unlock(&g_pool_mu); return ITX_ENOMEM; }
     pthread_mutex_lock(&P->mu);
-    P->file = file; P->blk = blocks; P->b0 = b0; P->b1 = b1; P->dst = dst; P->next = b0; P->failed = 0; P->busy_max = 0;
+    P->file = file; P->blk = blocks; P->b0 = b0; P->b1 = b1; P->dst = dst; P->next = b0; P->failed = 0; P->busy_max = 0; P->mode = mode;
     P->pending = P->nth; P->generation++;
     pthread_cond_broadcast(&P->cv_work);
     while (P->pending) pthread_cond_wait(&P->cv_done, &P->mu);

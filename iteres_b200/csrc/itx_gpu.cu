@@ -41,6 +41,7 @@ struct itx_cuda {
     itx_trace *d_trace; uint64_t trace_cap;
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
+    uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
@@ -77,7 +78,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
@@ -170,6 +171,8 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITX_INF_THREADS * ITX_T_CELLS * 2)));
+        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
@@ -477,6 +480,93 @@ extern "C" int itx_scan_bam_host(itx_index *ix, const uint8_t *bam, uint64_t len
 }
 
 /* ------------------------------------------------------------------ BGZF file / memory image */
+/* BGZF -> HBM with the inflate on the device: the compressed file image travels over PCIe (about half the
+ * bytes of the stream), k_inflate decodes one BGZF block per thread straight into the stream buffer, and the
+ * scan kernels follow window by window.  Host threads only stage the compressed bytes into pinned memory. */
+static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o, uint64_t cnt[13], char *err,
+                                    const itx_bgzf_block *blk, uint64_t nblk, uint64_t total, int nth) {
+    itx_cuda *cu = ix->cu;
+    int rc = ITX_OK;
+    /* the BAM header is parsed on the host: inflate leading blocks until it is complete */
+    itx_bam_header *h = NULL;
+    {
+        uint8_t *hb = NULL; char e2[ITX_ERRLEN]; e2[0] = 0;
+        for (uint64_t nb = 1; nb <= nblk && !h; nb = nb < 4 ? nb + 1 : nb * 2) {
+            uint64_t n1 = nb < nblk ? nb : nblk, ub = blk[n1 - 1].uoff + blk[n1 - 1].isize;
+            hb = (uint8_t *)realloc(hb, ub + 64);
+            if (itx_bgzf_inflate_range(bgzf, blk, 0, n1, hb, nth, NULL) != ITX_OK) { snprintf(err, ITX_ERRLEN, "BGZF inflate failed in the header blocks"); free(hb); return ITX_EFORMAT; }
+            h = itx_bam_header_parse(ix, hb, ub, o->addChr, e2);
+            if (!h && (n1 == nblk || memcmp(hb, "BAM\1", 4) != 0)) break;
+        }
+        free(hb);
+        if (!h) { snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : "truncated BAM header"); return ITX_EFORMAT; }
+    }
+    uint64_t Wc = 64ull << 20;                               /* compressed bytes per copy window */
+    if (Wc > flen) Wc = flen;
+    if (Wc < (1u << 20)) Wc = 1u << 20;
+    cudaEvent_t slot_free[2] = {NULL, NULL};
+    enum { MAXW = 1024 }; static cudaEvent_t wev[2 * MAXW]; static int wev_made = 0; int nw = 0;
+    scan_ctx sc; bool begun = false;
+    double inflate_ms = 0, wall0 = now_ms();
+    do {
+        if ((rc = ensure_stream_buffer(cu, total, err)) || (rc = ensure_stage(cu, Wc + 65536, err))) break;
+        if (!cu->d_comp || cu->d_comp_cap < flen + ITX_SLACK) {
+            cudaFree(cu->d_comp); cu->d_comp = NULL;
+            if (cudaMalloc((void **)&cu->d_comp, flen + ITX_SLACK) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate %llu bytes for the compressed image", (unsigned long long)flen); rc = ITX_ENOMEM; break; }
+            cu->d_comp_cap = flen + ITX_SLACK;
+        }
+        if (!cu->d_blk || cu->d_blk_cap < nblk) {
+            cudaFree(cu->d_blk); cu->d_blk = NULL;
+            if (cudaMalloc((void **)&cu->d_blk, nblk * sizeof(itx_bgzf_block)) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the block table"); rc = ITX_ENOMEM; break; }
+            cu->d_blk_cap = nblk;
+        }
+        if (cudaMemcpyAsync(cu->d_blk, blk, nblk * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+        for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
+        if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
+        if ((rc = scan_begin(&sc, ix, h, cu->d_stream, total, o, ix->tune_window < total ? ix->tune_window : total, err))) break;
+        begun = true;
+        uint64_t b = 0; int slot = 0;
+        while (b < nblk && rc == ITX_OK) {
+            uint64_t b1 = b + 1;
+            while (b1 < nblk && blk[b1].coff + blk[b1].csize - blk[b].coff <= Wc) b1++;
+            const uint64_t c0 = blk[b].coff, c1 = blk[b1 - 1].coff + blk[b1 - 1].csize;
+            cudaEventSynchronize(slot_free[slot]);                             /* the previous copy out of this slot is done */
+            if (itx_parallel_copy(bgzf, c0, c1, cu->h_stage[slot], nth) != ITX_OK) { rc = ITX_ENOMEM; break; }
+            if (cudaMemcpyAsync(cu->d_comp + c0, cu->h_stage[slot], c1 - c0, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+            cudaEventRecord(slot_free[slot], cu->copy_stream);
+            cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);
+            slot ^= 1;
+            itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = b; IA.nblk = b1 - b; IA.out = cu->d_stream; IA.status = cu->D.status;
+            const unsigned nb = (unsigned)((b1 - b + ITX_INF_THREADS - 1) / ITX_INF_THREADS);
+            if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
+            k_inflate<<<nb, ITX_INF_THREADS, ITX_INF_THREADS * ITX_T_CELLS * 2, cu->stream>>>(IA);
+            if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
+            sc.n_launch++;
+            const uint64_t avail = b1 < nblk ? blk[b1].uoff : total;
+            const uint64_t k_hi = b1 >= nblk ? sc.k_end : blk[b].uoff / cu->C;
+            if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, avail, err);
+            b = b1;
+        }
+        if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
+        if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
+        else cudaStreamSynchronize(cu->stream);
+        if (rc == ITX_OK) {
+            uint32_t st[8];
+            if (cudaMemcpy(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[5]) {
+                snprintf(err, ITX_ERRLEN, "BGZF inflate failed on %u block(s), e.g. block %u at compressed offset %llu", st[5], st[6], (unsigned long long)(st[6] < nblk ? blk[st[6]].coff : 0));
+                rc = ITX_EFORMAT;
+            }
+        }
+        for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[2 * i], wev[2 * i + 1]) == cudaSuccess) inflate_ms += ms; }
+    } while (0);
+    if (rc != ITX_OK && !err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError()));
+    (void)begun;
+    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is k_inflate's device time */
+    for (int i = 0; i < 2; i++) if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    itx_bam_header_free(h);
+    return rc;
+}
+
 extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o,
                                     uint64_t cnt[13], char err[ITX_ERRLEN]) {
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
@@ -491,6 +581,14 @@ extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t
     int nth = ix->tune_threads > 0 ? ix->tune_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (nth < 1) nth = 1;
     if (nth > 256) nth = 256;
+    {   /* ITX_INFLATE=host keeps zlib on the host threads; the default inflates on the device */
+        const char *m = getenv("ITX_INFLATE");
+        if (!(m && strcmp(m, "host") == 0)) {
+            rc = scan_bgzf_device_inflate(ix, bgzf, flen, o, cnt, err, blk, nblk, total, nth);
+            free(blk);
+            return rc;
+        }
+    }
     /* windows of whole BGZF blocks, about W uncompressed bytes each, inflated straight into pinned memory */
     uint64_t W = ix->tune_window < (64ull << 20) ? ix->tune_window : (64ull << 20);
     if (W > total) W = total;

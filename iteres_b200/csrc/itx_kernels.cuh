@@ -22,6 +22,7 @@
 #ifndef ITX_KERNELS_CUH
 #define ITX_KERNELS_CUH
 #include "itx_logic.cuh"
+#include "itx_inflate.cuh"
 
 struct itx_decode_args {
     const uint8_t *b; unsigned long long len, avail, k0;
@@ -476,6 +477,35 @@ __global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
         const unsigned long long off = D.sub_bp_off[mt.sub];
         for (uint32_t j = ja; j < jb; j++) atomicAdd(&D.bp_cpg[off + j], sc);
     }
+}
+
+/* ------------------------------------------------------------------ BGZF inflate on the device */
+/* one thread per BGZF block; the thread's Huffman tables live in shared memory, cell j of thread t at
+ * cells[j * blockDim.x + t] so that lanes reading the same cell index hit different banks */
+struct itx_tab_smem {
+    uint16_t *base; uint32_t stride;
+    __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return base[j * stride]; }
+    __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { base[j * stride] = v; }
+};
+struct itx_inflate_args {
+    const uint8_t *file;                 /* the compressed file image on the device */
+    const itx_bgzf_block *blk;           /* coff, csize, isize, uoff per block */
+    unsigned long long b0, nblk;         /* blocks [b0, b0 + nblk) */
+    uint8_t *out;                        /* uncompressed stream: block b goes to out + blk[b].uoff */
+    uint32_t *status;                    /* [5] number of blocks that failed, [6] index of one of them */
+};
+#define ITX_INF_THREADS 192
+__global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
+    extern __shared__ uint16_t itx_inf_cells[];
+    const unsigned long long b = A.b0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= A.b0 + A.nblk) return;
+    const itx_bgzf_block B = A.blk[b];
+    itx_inflater<itx_tab_smem> I;
+    I.tab.base = itx_inf_cells + threadIdx.x; I.tab.stride = blockDim.x;
+    I.in = A.file + B.coff + 18; I.in_len = B.csize - 18 - 8;            /* header 18, footer CRC32 + ISIZE */
+    I.out = A.out + B.uoff; I.out_cap = B.isize; I.err = 0;
+    const uint32_t rc = I.run(B.isize);
+    if (rc != ITX_INF_OK) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
 }
 
 __global__ void k_fill_u32(uint32_t *p, unsigned long long n, uint32_t v) {

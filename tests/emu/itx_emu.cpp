@@ -7,6 +7,7 @@
  * The product has no CPU path: nothing under iteres_b200/ links or loads this file.
  */
 #include "../../iteres_b200/csrc/itx_logic.cuh"
+#include "../../iteres_b200/csrc/itx_inflate.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -321,5 +322,21 @@ int emu_scan_cpg(emu_index *E, const char *bedgraph, int filter, uint32_t *n_lin
     if (n_lines) *n_lines = lines;
     if (n_in_repeat) *n_in_repeat = inrep;
     return ITX_OK;
+}
+
+/* the device inflater (itx_inflate.cuh) on one raw-deflate stream, with a plain array as its table store */
+struct emu_tab {
+    uint16_t *cells;
+    uint16_t operator()(uint32_t j) const { return cells[j]; }
+    void set(uint32_t j, uint16_t v) const { cells[j] = v; }
+};
+int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, uint32_t expect, uint32_t *produced) {
+    uint16_t cells[ITX_T_CELLS]; memset(cells, 0, sizeof cells);
+    std::vector<uint8_t> padded(in, in + in_len); padded.resize(in_len + 16, 0);
+    itx_inflater<emu_tab> I;
+    I.tab.cells = cells; I.in = padded.data(); I.in_len = in_len; I.out = out; I.out_cap = out_cap; I.err = 0;
+    const uint32_t rc = I.run(expect);
+    if (produced) *produced = I.out_pos;
+    return (int)rc;
 }
 }

@@ -24,9 +24,12 @@ CASES = [(k, v) for k in kats.KATS for v in kats.KATS[k]["variants"]
          if not runners.needs_host_order(*kats.KATS[k]["variants"][v])]
 
 
+@pytest.mark.parametrize("inflate", ["device", "host"])
 @pytest.mark.parametrize("kat,variant", CASES)
-def test_cuda_path_matches_reference_output(kat, variant, tmp_path):
-    """BGZF file -> host inflate -> device kernels -> tables, against what the reference printed."""
+def test_cuda_path_matches_reference_output(kat, variant, inflate, tmp_path, monkeypatch):
+    """BGZF file -> inflate (k_inflate on the device, or zlib on host threads) -> device kernels -> tables,
+    against what the reference printed."""
+    monkeypatch.setenv("ITX_INFLATE", inflate)
     cmd, args = kats.KATS[kat]["variants"][variant]
     vdir = os.path.join(GOLD, kat, variant)
     scan = lambda ix, bam, opts: ix.scan_alignments(bam, opts)
@@ -157,6 +160,40 @@ def test_truncated_stream_stops_like_the_reference(worlds):
         ix.tune(chunk_bytes=512, window_bytes=1 << 18)
         assert ix.scan_stream(raw, capi.default_opts()) == ora.scan_stream(raw, O.default_opts())
         ora.close()
+        ix.close()
+
+
+@pytest.mark.parametrize("level", [0, 1, 6])
+def test_device_inflate_matches_host_inflate(level, worlds, tmp_path, monkeypatch):
+    """every BGZF block through k_inflate (one thread per block) gives the stream zlib gives"""
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    bam = str(tmp_path / "reads.bam")
+    s.write_bam(bam, 1, 80000, level=level, threads=4)
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_file(bam, O.default_opts())
+    for mode in ("device", "host"):
+        monkeypatch.setenv("ITX_INFLATE", mode)
+        ix = capi.Index(cs, rs, rm)
+        assert ix.scan_alignments(bam, capi.default_opts()) == want, mode
+        assert_same_tables(ix, ora)
+        ix.close()
+    ora.close()
+
+
+def test_damaged_bgzf_block_is_reported(worlds, tmp_path, monkeypatch):
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    bam = str(tmp_path / "reads.bam")
+    s.write_bam(bam, 0, 30000, level=6, threads=4)
+    raw = bytearray(open(bam, "rb").read())
+    for k in range(40000, 40400):
+        raw[k] ^= 0x5a
+    open(bam, "wb").write(raw)
+    for mode in ("device", "host"):
+        monkeypatch.setenv("ITX_INFLATE", mode)
+        ix = capi.Index(cs, rs, rm)
+        with pytest.raises(capi.ItxError) as e:
+            ix.scan_alignments(bam, capi.default_opts())
+        assert e.value.code == -2 and "inflate failed" in str(e.value)
         ix.close()
 
 
