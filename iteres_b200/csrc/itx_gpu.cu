@@ -525,7 +525,10 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
         if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
         if ((rc = scan_begin(&sc, ix, h, cu->d_stream, total, o, ix->tune_window < total ? ix->tune_window : total, err))) break;
         begun = true;
-        uint64_t b = 0; int slot = 0;
+        /* copies go window by window; k_inflate is launched over groups of about one resident wave of blocks
+         * (a thread decodes a whole 64 KiB block, so small launches would leave most SMs idle) */
+        const uint64_t GROUP = (uint64_t)cu->sm_count * ITX_INF_THREADS;
+        uint64_t b = 0, gb0 = 0; int slot = 0;
         while (b < nblk && rc == ITX_OK) {
             uint64_t b1 = b + 1;
             while (b1 < nblk && blk[b1].coff + blk[b1].csize - blk[b].coff <= Wc) b1++;
@@ -534,18 +537,21 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
             if (itx_parallel_copy(bgzf, c0, c1, cu->h_stage[slot], nth) != ITX_OK) { rc = ITX_ENOMEM; break; }
             if (cudaMemcpyAsync(cu->d_comp + c0, cu->h_stage[slot], c1 - c0, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
             cudaEventRecord(slot_free[slot], cu->copy_stream);
-            cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);
-            slot ^= 1;
-            itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = b; IA.nblk = b1 - b; IA.out = cu->d_stream; IA.status = cu->D.status;
-            const unsigned nb = (unsigned)((b1 - b + ITX_INF_THREADS - 1) / ITX_INF_THREADS);
-            if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
-            k_inflate<<<nb, ITX_INF_THREADS, ITX_INF_THREADS * ITX_T_CELLS * 2, cu->stream>>>(IA);
-            if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
-            sc.n_launch++;
-            const uint64_t avail = b1 < nblk ? blk[b1].uoff : total;
-            const uint64_t k_hi = b1 >= nblk ? sc.k_end : blk[b].uoff / cu->C;
-            if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, avail, err);
             b = b1;
+            if (b - gb0 >= GROUP || b == nblk) {
+                cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);           /* copies are in order: the last one covers the group */
+                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = b - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
+                const unsigned nb = (unsigned)((b - gb0 + ITX_INF_THREADS - 1) / ITX_INF_THREADS);
+                if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
+                k_inflate<<<nb, ITX_INF_THREADS, ITX_INF_THREADS * ITX_T_CELLS * 2, cu->stream>>>(IA);
+                if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
+                sc.n_launch++;
+                const uint64_t avail = b < nblk ? blk[b].uoff : total;
+                const uint64_t k_hi = b >= nblk ? sc.k_end : blk[gb0].uoff / cu->C;
+                if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, avail, err);
+                gb0 = b;
+            }
+            slot ^= 1;
         }
         if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
         if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);

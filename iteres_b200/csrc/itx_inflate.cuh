@@ -34,15 +34,18 @@ struct itx_inflater {
     Tab tab;
     uint32_t err;
 
+    /* four bytes at a time; reads may run a few bytes past the stream (buffers carry slack), the bits are never used */
     ITX_HDM void refill() {
-        while (bitcnt <= 56) {
-            uint64_t b = in_pos < in_len ? (uint64_t)in[in_pos] : 0ull;   /* zeros past the end; an over-run is caught by in_pos */
-            in_pos++;
-            bitbuf |= b << bitcnt; bitcnt += 8;
+        if (bitcnt <= 32) {
+            const uint8_t *q = in + in_pos;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3) * 8;
+            const uint32_t v = sh ? itx_funnel_r(w[0], w[1], sh) : w[0];
+            bitbuf |= (uint64_t)v << bitcnt; bitcnt += 32; in_pos += 4;
         }
     }
     ITX_HDM uint32_t bits(uint32_t n) {                 /* n <= 16 */
-        if (bitcnt < n) refill();
+        refill();
         const uint32_t v = (uint32_t)bitbuf & ((1u << n) - 1u);
         bitbuf >>= n; bitcnt -= n;
         return v;
@@ -54,7 +57,7 @@ struct itx_inflater {
     }
     /* canonical Huffman decode, one bit at a time: cnt = cell of count[0], sym = cell of symbol[0] */
     ITX_HDM int32_t decode(uint32_t cnt, uint32_t sym) {
-        if (bitcnt < 15) refill();
+        refill();
         int32_t code = 0, first = 0, index = 0;
         uint32_t buf = (uint32_t)bitbuf;
         for (uint32_t len = 1; len <= 15; len++) {
@@ -96,25 +99,26 @@ struct itx_inflater {
     static ITX_HDM uint32_t lbase(uint32_t s) { return s < 8 ? 3 + s : (s == 28 ? 258u : 3 + ((4 + (s & 3)) << ((s - 4) >> 2))); }
     static ITX_HDM uint32_t dext(uint32_t d) { return d < 4 ? 0u : (d - 2) >> 1; }
     static ITX_HDM uint32_t dbase(uint32_t d) { return d < 4 ? 1 + d : 1 + ((2 + (d & 1)) << ((d - 2) >> 1)); }
-    ITX_HDM bool codes() {
-        for (;;) {
-            if (out_pos > out_cap || in_pos > in_len + 8) return false;
-            int32_t s = decode(ITX_T_LCNT, ITX_T_LSYM);
-            if (s < 0) return false;
-            if (s < 256) { put((uint8_t)s); continue; }
-            if (s == 256) return true;
-            s -= 257;
-            if (s >= 29) return false;
-            const uint32_t len = lbase((uint32_t)s) + bits(lext((uint32_t)s));
-            const int32_t d = decode(ITX_T_DCNT, ITX_T_DSYM);
-            if (d < 0 || d >= 30) return false;
-            const uint32_t dist = dbase((uint32_t)d) + bits(dext((uint32_t)d));
-            if (dist > out_pos) return false;
-            if (out_pos + len > out_cap) { out_pos += len; return false; }
-            uint8_t *o = out + out_pos; const uint8_t *f = o - dist;
-            for (uint32_t k = 0; k < len; k++) o[k] = f[k];       /* byte-wise: overlapping copies replicate, as LZ77 requires */
-            out_pos += len;
-        }
+    /* one literal / length-distance pair / end-of-block; false = invalid data */
+    ITX_HDM bool symbol(bool *end_of_block) {
+        *end_of_block = false;
+        if (out_pos > out_cap || in_pos > in_len + 8) return false;
+        int32_t s = decode(ITX_T_LCNT, ITX_T_LSYM);
+        if (s < 0) return false;
+        if (s < 256) { put((uint8_t)s); return true; }
+        if (s == 256) { *end_of_block = true; return true; }
+        s -= 257;
+        if (s >= 29) return false;
+        const uint32_t len = lbase((uint32_t)s) + bits(lext((uint32_t)s));
+        const int32_t d = decode(ITX_T_DCNT, ITX_T_DSYM);
+        if (d < 0 || d >= 30) return false;
+        const uint32_t dist = dbase((uint32_t)d) + bits(dext((uint32_t)d));
+        if (dist > out_pos) return false;
+        if (out_pos + len > out_cap) { out_pos += len; return false; }
+        uint8_t *o = out + out_pos; const uint8_t *f = o - dist;
+        for (uint32_t k = 0; k < len; k++) o[k] = f[k];           /* byte-wise: overlapping copies replicate, as LZ77 requires */
+        out_pos += len;
+        return true;
     }
     ITX_HDM bool stored() {
         bitbuf >>= (bitcnt & 7); bitcnt -= (bitcnt & 7);          /* to the next byte boundary */
@@ -129,7 +133,7 @@ struct itx_inflater {
         construct(ITX_T_LCNT, ITX_T_LSYM, 288, [self](uint32_t s) { return self->get_len(s); });
         for (uint32_t s = 0; s < 30; s++) set_len(s, 5);
         construct(ITX_T_DCNT, ITX_T_DSYM, 30, [self](uint32_t s) { return self->get_len(s); });
-        return codes();
+        return true;
     }
     ITX_HDM bool dynamic() {
         /* order of the code-length code lengths: 16 17 18 0 8 7 9 6 10 5 11 4 | 12 3 13 2 14 1 15, five bits each */
@@ -162,19 +166,33 @@ struct itx_inflater {
         if (e != 0 && (e < 0 || nlen != (uint32_t)(tab(ITX_T_LCNT) + tab(ITX_T_LCNT + 1)))) return false;
         e = construct(ITX_T_DCNT, ITX_T_DSYM, ndist, [self, nlen](uint32_t s) { return self->get_len(nlen + s); });
         if (e != 0 && (e < 0 || ndist != (uint32_t)(tab(ITX_T_DCNT) + tab(ITX_T_DCNT + 1)))) return false;
-        return codes();
+        return true;
+    }
+    /* The decoder is a small state machine so that the 32 lanes of a warp (32 different BGZF blocks) can be
+     * stepped together: every call of advance() does ONE unit of work -- a block header (with its table build)
+     * or one symbol -- and the kernel re-converges the warp between calls. */
+    uint32_t state, last, expect;                /* state: 0 header, 1 symbols, 2 done, 3 error */
+    ITX_HDM void begin(uint32_t expect_) { bitbuf = 0; bitcnt = 0; in_pos = 0; out_pos = 0; state = 0; last = 0; expect = expect_; err = ITX_INF_OK; }
+    ITX_HDM void advance() {
+        if (state == 1) {
+            bool eob;
+            if (!symbol(&eob)) { state = 3; err = ITX_INF_EDATA; }
+            else if (eob) state = last ? 2u : 0u;
+        } else if (state == 0) {
+            last = bits(1);
+            const uint32_t type = bits(2);
+            bool ok;
+            if (type == 0) { ok = stored(); state = last ? 2u : 0u; }
+            else { ok = type == 1 ? fixed() : (type == 2 ? dynamic() : false); state = 1; }
+            if (!ok || in_pos > in_len + 8) { state = 3; err = ITX_INF_EDATA; }
+        }
+        if (state == 2 && out_pos != expect) { state = 3; err = ITX_INF_ESIZE; }
     }
     /* one whole raw-deflate stream; returns ITX_INF_* */
-    ITX_HDM uint32_t run(uint32_t expect) {
-        bitbuf = 0; bitcnt = 0; in_pos = 0; out_pos = 0;
-        for (;;) {
-            const uint32_t last = bits(1), type = bits(2);
-            bool ok = type == 0 ? stored() : (type == 1 ? fixed() : (type == 2 ? dynamic() : false));
-            if (!ok) return ITX_INF_EDATA;
-            if (in_pos > in_len + 8) return ITX_INF_EDATA;
-            if (last) break;
-        }
-        return out_pos == expect ? ITX_INF_OK : ITX_INF_ESIZE;
+    ITX_HDM uint32_t run(uint32_t expect_) {
+        begin(expect_);
+        while (state < 2) advance();
+        return err;
     }
 };
 #endif

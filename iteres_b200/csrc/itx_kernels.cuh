@@ -498,14 +498,23 @@ struct itx_inflate_args {
 __global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
     extern __shared__ uint16_t itx_inf_cells[];
     const unsigned long long b = A.b0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= A.b0 + A.nblk) return;
-    const itx_bgzf_block B = A.blk[b];
+    const bool mine = b < A.b0 + A.nblk;
     itx_inflater<itx_tab_smem> I;
     I.tab.base = itx_inf_cells + threadIdx.x; I.tab.stride = blockDim.x;
-    I.in = A.file + B.coff + 18; I.in_len = B.csize - 18 - 8;            /* header 18, footer CRC32 + ISIZE */
-    I.out = A.out + B.uoff; I.out_cap = B.isize; I.err = 0;
-    const uint32_t rc = I.run(B.isize);
-    if (rc != ITX_INF_OK) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
+    I.in = A.file; I.in_len = 0; I.out = A.out; I.out_cap = 0;
+    I.begin(0);
+    I.state = 2;
+    if (mine) {
+        const itx_bgzf_block B = A.blk[b];
+        I.in = A.file + B.coff + 18; I.in_len = B.csize - 18 - 8;        /* header 18, footer CRC32 + ISIZE */
+        I.out = A.out + B.uoff; I.out_cap = B.isize;
+        I.begin(B.isize);
+    }
+    /* the warp's 32 blocks step together: a header (table build) or one symbol per round */
+    while (__any_sync(0xffffffffu, I.state < 2)) {
+        if (I.state < 2) I.advance();
+    }
+    if (mine && I.err != ITX_INF_OK) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
 }
 
 __global__ void k_fill_u32(uint32_t *p, unsigned long long n, uint32_t v) {
