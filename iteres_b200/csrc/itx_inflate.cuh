@@ -55,7 +55,28 @@ struct itx_inflater {
         const uint32_t c = tab(ITX_T_LENS + (i >> 1));
         tab.set(ITX_T_LENS + (i >> 1), (uint16_t)((i & 1) ? ((c & 0x00ff) | (v << 8)) : ((c & 0xff00) | v)));
     }
-    /* canonical Huffman decode, one bit at a time: cnt = cell of count[0], sym = cell of symbol[0] */
+    /* canonical Huffman decode, one bit at a time.  The 15 per-length code counts of a table sit in eight
+     * registers (two 16-bit counts each, loaded by load_counts after a table is built), so the only memory
+     * access of a decode is the final symbol lookup. */
+    uint32_t lc[8], dc[8];
+    ITX_HDM void load_counts(uint32_t cnt, uint32_t c[8]) {
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) c[k] = (uint32_t)tab(cnt + 2 * k) | ((uint32_t)tab(cnt + 2 * k + 1) << 16);
+    }
+    ITX_HDM int32_t decode_regs(const uint32_t c[8], uint32_t sym) {
+        refill();
+        int32_t code = 0, first = 0, index = 0;
+        uint32_t buf = (uint32_t)bitbuf;
+#pragma unroll
+        for (uint32_t len = 1; len <= 15; len++) {
+            code |= (int32_t)(buf & 1u); buf >>= 1;
+            const int32_t count = (int32_t)((len & 1) ? (c[len >> 1] >> 16) : (c[len >> 1] & 0xffffu));
+            if (code - count < first) { bitbuf >>= len; bitcnt -= len; return (int32_t)tab(sym + (uint32_t)(index + (code - first))); }
+            index += count; first += count; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+    /* the same with the counts read from the table store (code-length code of a dynamic header) */
     ITX_HDM int32_t decode(uint32_t cnt, uint32_t sym) {
         refill();
         int32_t code = 0, first = 0, index = 0;
@@ -103,20 +124,27 @@ struct itx_inflater {
     ITX_HDM bool symbol(bool *end_of_block) {
         *end_of_block = false;
         if (out_pos > out_cap || in_pos > in_len + 8) return false;
-        int32_t s = decode(ITX_T_LCNT, ITX_T_LSYM);
+        int32_t s = decode_regs(lc, ITX_T_LSYM);
         if (s < 0) return false;
         if (s < 256) { put((uint8_t)s); return true; }
         if (s == 256) { *end_of_block = true; return true; }
         s -= 257;
         if (s >= 29) return false;
         const uint32_t len = lbase((uint32_t)s) + bits(lext((uint32_t)s));
-        const int32_t d = decode(ITX_T_DCNT, ITX_T_DSYM);
+        const int32_t d = decode_regs(dc, ITX_T_DSYM);
         if (d < 0 || d >= 30) return false;
         const uint32_t dist = dbase((uint32_t)d) + bits(dext((uint32_t)d));
         if (dist > out_pos) return false;
         if (out_pos + len > out_cap) { out_pos += len; return false; }
         uint8_t *o = out + out_pos; const uint8_t *f = o - dist;
-        for (uint32_t k = 0; k < len; k++) o[k] = f[k];           /* byte-wise: overlapping copies replicate, as LZ77 requires */
+        uint32_t k = 0;
+        if (dist >= 8) {                                             /* eight independent loads in flight per round */
+            for (; k + 8 <= len; k += 8) {
+                const uint8_t t0 = f[k], t1 = f[k + 1], t2 = f[k + 2], t3 = f[k + 3], t4 = f[k + 4], t5 = f[k + 5], t6 = f[k + 6], t7 = f[k + 7];
+                o[k] = t0; o[k + 1] = t1; o[k + 2] = t2; o[k + 3] = t3; o[k + 4] = t4; o[k + 5] = t5; o[k + 6] = t6; o[k + 7] = t7;
+            }
+        }
+        for (; k < len; k++) o[k] = f[k];                            /* byte-wise: overlapping copies replicate, as LZ77 requires */
         out_pos += len;
         return true;
     }
@@ -133,6 +161,7 @@ struct itx_inflater {
         construct(ITX_T_LCNT, ITX_T_LSYM, 288, [self](uint32_t s) { return self->get_len(s); });
         for (uint32_t s = 0; s < 30; s++) set_len(s, 5);
         construct(ITX_T_DCNT, ITX_T_DSYM, 30, [self](uint32_t s) { return self->get_len(s); });
+        load_counts(ITX_T_LCNT, lc); load_counts(ITX_T_DCNT, dc);
         return true;
     }
     ITX_HDM bool dynamic() {
@@ -166,6 +195,7 @@ struct itx_inflater {
         if (e != 0 && (e < 0 || nlen != (uint32_t)(tab(ITX_T_LCNT) + tab(ITX_T_LCNT + 1)))) return false;
         e = construct(ITX_T_DCNT, ITX_T_DSYM, ndist, [self, nlen](uint32_t s) { return self->get_len(nlen + s); });
         if (e != 0 && (e < 0 || ndist != (uint32_t)(tab(ITX_T_DCNT) + tab(ITX_T_DCNT + 1)))) return false;
+        load_counts(ITX_T_LCNT, lc); load_counts(ITX_T_DCNT, dc);
         return true;
     }
     /* The decoder is a small state machine so that the 32 lanes of a warp (32 different BGZF blocks) can be
