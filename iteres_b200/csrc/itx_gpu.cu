@@ -42,6 +42,7 @@ struct itx_cuda {
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
     uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
+    uint16_t *d_tabs; uint64_t d_tabs_threads;   /* Huffman table store of k_inflate */
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
@@ -78,7 +79,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
@@ -171,8 +172,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITX_INF_THREADS * ITX_T_CELLS * 2)));
-        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
@@ -527,23 +527,34 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
         begun = true;
         /* copies go window by window; k_inflate is launched over groups of about one resident wave of blocks
          * (a thread decodes a whole 64 KiB block, so small launches would leave most SMs idle) */
-        const uint64_t GROUP = (uint64_t)cu->sm_count * ITX_INF_THREADS;
+        int inf_ctas = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inf_ctas, k_inflate, ITX_INF_THREADS, 0);
+        if (inf_ctas < 1) inf_ctas = 1;
+        const uint64_t GROUP = (uint64_t)cu->sm_count * ITX_INF_THREADS * (uint64_t)inf_ctas;     /* one resident wave of threads */
+        {
+            const uint64_t need_thr = ((GROUP + Wc / 8192 + 4096 + 31) / 32) * 32;                   /* a group overshoots by at most one copy window of blocks */
+            if (!cu->d_tabs || cu->d_tabs_threads < need_thr) {
+                cudaFree(cu->d_tabs); cu->d_tabs = NULL;
+                if (cudaMalloc((void **)&cu->d_tabs, need_thr * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
+                cu->d_tabs_threads = need_thr;
+            }
+        }
         uint64_t b = 0, gb0 = 0; int slot = 0;
         while (b < nblk && rc == ITX_OK) {
             uint64_t b1 = b + 1;
-            while (b1 < nblk && blk[b1].coff + blk[b1].csize - blk[b].coff <= Wc) b1++;
+            while (b1 < nblk && blk[b1].coff + blk[b1].csize - blk[b].coff <= Wc && b1 - gb0 < cu->d_tabs_threads) b1++;
             const uint64_t c0 = blk[b].coff, c1 = blk[b1 - 1].coff + blk[b1 - 1].csize;
             cudaEventSynchronize(slot_free[slot]);                             /* the previous copy out of this slot is done */
             if (itx_parallel_copy(bgzf, c0, c1, cu->h_stage[slot], nth) != ITX_OK) { rc = ITX_ENOMEM; break; }
             if (cudaMemcpyAsync(cu->d_comp + c0, cu->h_stage[slot], c1 - c0, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
             cudaEventRecord(slot_free[slot], cu->copy_stream);
             b = b1;
-            if (b - gb0 >= GROUP || b == nblk) {
+            if (b - gb0 >= GROUP || b - gb0 >= cu->d_tabs_threads || b == nblk) {
                 cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);           /* copies are in order: the last one covers the group */
-                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = b - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
+                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = b - gb0; IA.out = cu->d_stream; IA.status = cu->D.status; IA.tabs = cu->d_tabs;
+                if (b - gb0 > cu->d_tabs_threads) { snprintf(err, ITX_ERRLEN, "inflate group larger than its table store"); rc = ITX_ENOMEM; break; }
                 const unsigned nb = (unsigned)((b - gb0 + ITX_INF_THREADS - 1) / ITX_INF_THREADS);
                 if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
-                k_inflate<<<nb, ITX_INF_THREADS, ITX_INF_THREADS * ITX_T_CELLS * 2, cu->stream>>>(IA);
+                k_inflate<<<nb, ITX_INF_THREADS, 0, cu->stream>>>(IA);
                 if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
                 sc.n_launch++;
                 const uint64_t avail = b < nblk ? blk[b].uoff : total;

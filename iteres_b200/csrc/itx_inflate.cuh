@@ -138,6 +138,23 @@ struct itx_inflater {
         if (out_pos + len > out_cap) { out_pos += len; return false; }
         uint8_t *o = out + out_pos; const uint8_t *f = o - dist;
         uint32_t k = 0;
+        if (dist >= 36) {
+            /* 32 bytes per round out of nine aligned words: the loads of a round are independent of each other and
+             * of the round's stores (the source lies at least 36 bytes behind), so one memory latency moves 32 bytes */
+            for (; k + 32 <= len; k += 32) {
+                const uint8_t *q = f + k;
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3) * 8;
+                uint32_t v[9];
+#pragma unroll
+                for (int j = 0; j < 9; j++) v[j] = w[j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t x = sh ? itx_funnel_r(v[j], v[j + 1], sh) : v[j];
+                    o[k + 4 * j] = (uint8_t)x; o[k + 4 * j + 1] = (uint8_t)(x >> 8); o[k + 4 * j + 2] = (uint8_t)(x >> 16); o[k + 4 * j + 3] = (uint8_t)(x >> 24);
+                }
+            }
+        }
         if (dist >= 8) {                                             /* eight independent loads in flight per round */
             for (; k + 8 <= len; k += 8) {
                 const uint8_t t0 = f[k], t1 = f[k + 1], t2 = f[k + 2], t3 = f[k + 3], t4 = f[k + 4], t5 = f[k + 5], t6 = f[k + 6], t7 = f[k + 7];

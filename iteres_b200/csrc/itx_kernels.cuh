@@ -480,12 +480,13 @@ __global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
 }
 
 /* ------------------------------------------------------------------ BGZF inflate on the device */
-/* one thread per BGZF block; the thread's Huffman tables live in shared memory, cell j of thread t at
- * cells[j * blockDim.x + t] so that lanes reading the same cell index hit different banks */
-struct itx_tab_smem {
-    uint16_t *base; uint32_t stride;
-    __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return base[j * stride]; }
-    __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { base[j * stride] = v; }
+/* one thread per BGZF block; the thread's Huffman tables (~1 KiB) live in global memory, interleaved inside
+ * the warp -- cell j of lane l at tabs[warp][j * 32 + l] -- so that lanes reading the same cell index make one
+ * coalesced request; they stay L1 / L2 resident and cost no shared memory, which lets 20 warps run per SM */
+struct itx_tab_glob {
+    uint16_t *base;
+    __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return base[j * 32u]; }
+    __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { base[j * 32u] = v; }
 };
 struct itx_inflate_args {
     const uint8_t *file;                 /* the compressed file image on the device */
@@ -493,14 +494,15 @@ struct itx_inflate_args {
     unsigned long long b0, nblk;         /* blocks [b0, b0 + nblk) */
     uint8_t *out;                        /* uncompressed stream: block b goes to out + blk[b].uoff */
     uint32_t *status;                    /* [5] number of blocks that failed, [6] index of one of them */
+    uint16_t *tabs;                      /* ITX_T_CELLS cells per thread of the launch */
 };
-#define ITX_INF_THREADS 192
+#define ITX_INF_THREADS 128
 __global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
-    extern __shared__ uint16_t itx_inf_cells[];
-    const unsigned long long b = A.b0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long b = A.b0 + gid;
     const bool mine = b < A.b0 + A.nblk;
-    itx_inflater<itx_tab_smem> I;
-    I.tab.base = itx_inf_cells + threadIdx.x; I.tab.stride = blockDim.x;
+    itx_inflater<itx_tab_glob> I;
+    I.tab.base = A.tabs + (gid >> 5) * (32ull * ITX_T_CELLS) + (gid & 31);
     I.in = A.file; I.in_len = 0; I.out = A.out; I.out_cap = 0;
     I.begin(0);
     I.state = 2;
