@@ -497,7 +497,7 @@ struct itx_inflate_args {
     uint16_t *tabs;                      /* ITX_T_CELLS cells per thread of the launch */
 };
 #define ITX_INF_THREADS 128
-__global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
+__global__ void __launch_bounds__(ITX_INF_THREADS, 8) k_inflate(const itx_inflate_args A) {
     const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long b = A.b0 + gid;
     const bool mine = b < A.b0 + A.nblk;
