@@ -355,11 +355,14 @@ def main():
             barrier()
             t0 = time.perf_counter()
             ix.reset()
+            t_a = time.perf_counter()
             c2 = ix.scan_alignments(bam, opts)
+            t_b = time.perf_counter()
             if world > 1:
                 ix.allreduce_counts()
             ix.sync()                                   # counter tables + coverage vectors back on the host
             dt = time.perf_counter() - t0
+            log("e2e step %d: reset %.1f ms, scan %.1f ms, allreduce+sync %.1f ms" % (i, 1e3 * (t_a - t0), 1e3 * (t_b - t_a), 1e3 * (t0 + dt - t_b)))
             if dist:
                 import torch
                 tt = torch.tensor([dt], dtype=torch.float64)

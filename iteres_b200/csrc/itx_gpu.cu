@@ -501,6 +501,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
         free(hb);
         if (!h) { snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : "truncated BAM header"); return ITX_EFORMAT; }
     }
+    const bool timing = getenv("ITX_TIMING") != NULL; const double tm0 = now_ms();
     uint64_t Wc = 64ull << 20;                               /* compressed bytes per copy window */
     if (Wc > flen) Wc = flen;
     if (Wc < (1u << 20)) Wc = 1u << 20;
@@ -525,6 +526,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
         if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
         if ((rc = scan_begin(&sc, ix, h, cu->d_stream, total, o, ix->tune_window < total ? ix->tune_window : total, err))) break;
         begun = true;
+        if (timing) fprintf(stderr, "[itx timing] header+alloc+begin %.1f ms\n", now_ms() - tm0);
         /* copies go window by window; k_inflate is launched over groups of about one resident wave of blocks
          * (a thread decodes a whole 64 KiB block, so small launches would leave most SMs idle) */
         int inf_ctas = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inf_ctas, k_inflate, ITX_INF_THREADS, 0);
@@ -565,8 +567,10 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
             slot ^= 1;
         }
         if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
+        if (timing) fprintf(stderr, "[itx timing] copies staged and everything enqueued at %.1f ms\n", now_ms() - tm0);
         if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
         else cudaStreamSynchronize(cu->stream);
+        if (timing) fprintf(stderr, "[itx timing] device done at %.1f ms\n", now_ms() - tm0);
         if (rc == ITX_OK) {
             uint32_t st[8];
             if (cudaMemcpy(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[5]) {
