@@ -171,6 +171,8 @@ int itx_dev_upload(void *dst, const void *src, uint64_t bytes);
 void *itx_host_alloc_pinned(uint64_t bytes);
 void itx_host_free_pinned(void *p);
 int itx_dev_flush_l2(itx_index *ix);           /* writes a 256 MiB scratch buffer */
+/* test hook: the uncompressed BAM stream the last host/BGZF scan left on the device (what the device inflate produced); returns the bytes copied */
+uint64_t itx_stream_fetch(itx_index *ix, uint8_t *out, uint64_t cap);
 int itx_dev_sync(void);
 
 #ifdef __cplusplus

@@ -55,7 +55,7 @@ itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_
 itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
 itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
 itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
-itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync""".split()
+itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch""".split()
 
 _lib = None
 
@@ -133,6 +133,8 @@ def lib():
         L.itx_host_alloc_pinned.argtypes = [u64]
         L.itx_host_free_pinned.argtypes = [vp]
         L.itx_dev_flush_l2.argtypes = [vp]
+        L.itx_stream_fetch.restype = u64
+        L.itx_stream_fetch.argtypes = [vp, vp, u64]
         _lib = L
     return _lib
 
@@ -301,6 +303,13 @@ class Index(IndexBase):
 
     def elapsed_ms(self, a, b):
         return self.L.itx_elapsed_ms(self.h, a, b)
+
+    def stream_fetch(self, nbytes):
+        """test hook: the uncompressed stream the last BGZF / host scan left on the device, as bytes"""
+        import numpy as np
+        a = np.empty(max(int(nbytes), 1), dtype=np.uint8)
+        n = self.L.itx_stream_fetch(self.h, a.ctypes.data, int(nbytes))
+        return a[:n].tobytes()
 
     def profile(self):
         p = Profile()

@@ -15,9 +15,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include <zlib.h>
 
-static int header_ok(const uint8_t *h) {
+int itx_bgzf_header_ok(const uint8_t *h) {
     return h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
 }
 
@@ -27,7 +28,7 @@ int itx_bgzf_scan(const uint8_t *file, uint64_t len, itx_bgzf_block **blocks, ui
     if (!b) { snprintf(err, ITX_ERRLEN, "out of memory"); return ITX_ENOMEM; }
     while (off + 18 <= len) {
         const uint8_t *h = file + off;
-        if (!header_ok(h)) break;
+        if (!itx_bgzf_header_ok(h)) break;
         uint32_t bsize = ((uint32_t)h[16] | (uint32_t)h[17] << 8) + 1;
         if (bsize < 26 || off + bsize > len) break;                    /* short read: the stream ends here */
         uint32_t isize; memcpy(&isize, h + bsize - 4, 4);
@@ -47,7 +48,8 @@ typedef struct {
     pthread_t *th; int nth; int generation, pending, stop;
     /* the current job */
     const uint8_t *file; const itx_bgzf_block *blk; uint64_t b0, b1; uint8_t *dst; uint64_t next; int failed;
-    int mode;                            /* 0: inflate blocks [b0,b1)   1: copy bytes [b0,b1) of file to dst in 1 MiB pieces */
+    int mode;                            /* 0: inflate blocks [b0,b1)   1: copy bytes [b0,b1) of file to dst in 1 MiB pieces   2: the same with pread(fd) */
+    int fd;
     double busy_max;
 } pool_t;
 static pool_t g_pool; static int g_pool_init = 0; static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -66,13 +68,20 @@ static void *worker(void *arg) {
         seen = P->generation;
         pthread_mutex_unlock(&P->mu);
         double t0 = mono_ms(); int failed = !zinit;
-        if (P->mode == 1) {
+        if (P->mode == 1 || P->mode == 2) {
             failed = 0;
             for (;;) {
                 uint64_t o = __atomic_fetch_add(&P->next, (uint64_t)1 << 20, __ATOMIC_RELAXED);
                 if (o >= P->b1) break;
                 uint64_t e = o + ((uint64_t)1 << 20) < P->b1 ? o + ((uint64_t)1 << 20) : P->b1;
-                memcpy(P->dst + (o - P->b0), P->file + o, (size_t)(e - o));
+                if (P->mode == 1) memcpy(P->dst + (o - P->b0), P->file + o, (size_t)(e - o));
+                else {
+                    while (o < e) {
+                        ssize_t r = pread(P->fd, P->dst + (o - P->b0), (size_t)(e - o), (off_t)o);
+                        if (r <= 0) { failed = 1; break; }
+                        o += (uint64_t)r;
+                    }
+                }
             }
         } else
         for (;;) {
@@ -113,15 +122,19 @@ static void pool_stop(void) {
     free(P->th); P->th = NULL; P->nth = 0;
 }
 
-static int pool_run(int mode, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms);
+static int pool_run(int mode, int fd, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms);
 int itx_bgzf_inflate_range(const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms) {
-    return pool_run(0, file, blocks, b0, b1, dst, nth, busy_ms);
+    return pool_run(0, -1, file, blocks, b0, b1, dst, nth, busy_ms);
 }
 /* dst[0 .. o1-o0) = file[o0 .. o1) with nth threads (staging a compressed window into pinned memory) */
 int itx_parallel_copy(const uint8_t *file, uint64_t o0, uint64_t o1, uint8_t *dst, int nth) {
-    return pool_run(1, file, NULL, o0, o1, dst, nth, NULL);
+    return pool_run(1, -1, file, NULL, o0, o1, dst, nth, NULL);
 }
-static int pool_run(int mode, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms) {
+/* the same straight from a file descriptor: no mapping, so no page faults -- the kernel copies out of the page cache */
+int itx_parallel_pread(int fd, uint64_t o0, uint64_t o1, uint8_t *dst, int nth) {
+    return pool_run(2, fd, NULL, NULL, o0, o1, dst, nth, NULL);
+}
+static int pool_run(int mode, int fd, const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1, uint8_t *dst, int nth, double *busy_ms) {
     if (b1 <= b0) return ITX_OK;
     pthread_mutex_lock(&g_pool_mu);
     if (g_pool_init && g_pool.nth != nth) { pool_stop(); g_pool_init = 0; }
@@ -130,7 +143,7 @@ static int pool_run(int mode, const uint8_t *file, const itx_bgzf_block *blocks,
     if (P->nth == 0) { pthread_mutex_unlock(&g_pool_mu); return ITX_ENOMEM; }
     pthread_mutex_lock(&P->mu);
     P->file = file; P->blk = blocks; P->b0 = b0; P->b1 = b1; P->dst = dst; P->next = b0; P->failed = 0; P->busy_max = 0; P->mode = mode;
-    P->pending = P->nth; P->generation++;
+    P->fd = fd; P->pending = P->nth; P->generation++;
     pthread_cond_broadcast(&P->cv_work);
     while (P->pending) pthread_cond_wait(&P->cv_done, &P->mu);
     int failed = P->failed; if (busy_ms) *busy_ms = P->busy_max;

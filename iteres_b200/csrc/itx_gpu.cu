@@ -42,7 +42,8 @@ struct itx_cuda {
     /* staging for host streams */
     uint8_t *d_stream; uint64_t d_stream_cap;
     uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
-    uint16_t *d_tabs; uint64_t d_tabs_threads;   /* Huffman table store of k_inflate */
+    uint16_t *d_tabs; uint64_t d_tabs_threads;   /* symbol arrays of k_inflate's long codes */
+    uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists of one inflate group */
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
@@ -79,7 +80,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
@@ -172,7 +173,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
@@ -480,96 +481,168 @@ extern "C" int itx_scan_bam_host(itx_index *ix, const uint8_t *bam, uint64_t len
 }
 
 /* ------------------------------------------------------------------ BGZF file / memory image */
-/* BGZF -> HBM with the inflate on the device: the compressed file image travels over PCIe (about half the
- * bytes of the stream), k_inflate decodes one BGZF block per thread straight into the stream buffer, and the
- * scan kernels follow window by window.  Host threads only stage the compressed bytes into pinned memory. */
-static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o, uint64_t cnt[13], char *err,
-                                    const itx_bgzf_block *blk, uint64_t nblk, uint64_t total, int nth) {
+/* where the compressed bytes come from: a file descriptor (pread, no mapping and so no page faults) or memory */
+typedef struct { int fd; const uint8_t *mem; uint64_t len; } itx_bgzf_src;
+static int src_read(const itx_bgzf_src *S, uint64_t o0, uint64_t o1, uint8_t *dst, int nth) {
+    return S->fd >= 0 ? itx_parallel_pread(S->fd, o0, o1, dst, nth) : itx_parallel_copy(S->mem, o0, o1, dst, nth);
+}
+/* grow a device buffer, keeping its first `keep` bytes; both streams are drained first (kernels in flight hold the old pointer) */
+static int grow_device(itx_cuda *cu, void **p, uint64_t *cap, uint64_t need, uint64_t keep, const char *what, char *err) {
+    if (*p && *cap >= need) return ITX_OK;
+    cudaStreamSynchronize(cu->stream); cudaStreamSynchronize(cu->copy_stream);
+    void *q = NULL;
+    if (!keep && *p) { cudaFree(*p); *p = NULL; *cap = 0; }
+    if (cudaMalloc(&q, need) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate %llu bytes on the device for %s", (unsigned long long)need, what); return ITX_ENOMEM; }
+    if (*p && keep && cudaMemcpy(q, *p, keep, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaFree(q); snprintf(err, ITX_ERRLEN, "device copy failed while growing %s", what); return ITX_ENODEV; }
+    cudaFree(*p); *p = q; *cap = need;
+    return ITX_OK;
+}
+
+/* BGZF -> HBM in ONE pass, the inflate on the device.  Host threads read the compressed file window by window
+ * into pinned memory (two slots); the main thread walks the block headers of the window just read (BSIZE at byte
+ * 16, ISIZE in the footer: bgzf.c:401-411, 471-521), which gives every block its place in the uncompressed stream,
+ * and sends window and block table over PCIe on the copy stream.  Per group of about one resident wave of blocks
+ * the scan stream runs k_inflate (Huffman decoding, literals, match lists), k_lz_resolve (match copies) and then
+ * the scan kernels over everything that lies before the group.  The stream's total size is only known at the
+ * end: the stream buffer is sized from the first window's compression ratio and grown if that was too small. */
+static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth) {
     itx_cuda *cu = ix->cu;
+    const uint64_t flen = S->len;
     int rc = ITX_OK;
-    /* the BAM header is parsed on the host: inflate leading blocks until it is complete */
-    itx_bam_header *h = NULL;
-    {
-        uint8_t *hb = NULL; char e2[ITX_ERRLEN]; e2[0] = 0;
-        for (uint64_t nb = 1; nb <= nblk && !h; nb = nb < 4 ? nb + 1 : nb * 2) {
-            uint64_t n1 = nb < nblk ? nb : nblk, ub = blk[n1 - 1].uoff + blk[n1 - 1].isize;
-            hb = (uint8_t *)realloc(hb, ub + 64);
-            if (itx_bgzf_inflate_range(bgzf, blk, 0, n1, hb, nth, NULL) != ITX_OK) { snprintf(err, ITX_ERRLEN, "BGZF inflate failed in the header blocks"); free(hb); return ITX_EFORMAT; }
-            h = itx_bam_header_parse(ix, hb, ub, o->addChr, e2);
-            if (!h && (n1 == nblk || memcmp(hb, "BAM\1", 4) != 0)) break;
-        }
-        free(hb);
-        if (!h) { snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : "truncated BAM header"); return ITX_EFORMAT; }
-    }
     const bool timing = getenv("ITX_TIMING") != NULL; const double tm0 = now_ms();
-    uint64_t Wc = 64ull << 20;                               /* compressed bytes per copy window */
+    uint64_t Wc = 64ull << 20;                               /* compressed bytes per read / copy window */
     if (Wc > flen) Wc = flen;
     if (Wc < (1u << 20)) Wc = 1u << 20;
     cudaEvent_t slot_free[2] = {NULL, NULL};
-    enum { MAXW = 1024 }; static cudaEvent_t wev[2 * MAXW]; static int wev_made = 0; int nw = 0;
+    enum { MAXW = 256 }; static cudaEvent_t wev[2 * MAXW]; static int wev_made = 0; int nw = 0;
+    itx_bgzf_block *blk = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;
+    itx_bam_header *h = NULL;
     scan_ctx sc; bool begun = false;
     double inflate_ms = 0, wall0 = now_ms();
     do {
-        if ((rc = ensure_stream_buffer(cu, total, err)) || (rc = ensure_stage(cu, Wc + 65536, err))) break;
-        if (!cu->d_comp || cu->d_comp_cap < flen + ITX_SLACK) {
-            cudaFree(cu->d_comp); cu->d_comp = NULL;
-            if (cudaMalloc((void **)&cu->d_comp, flen + ITX_SLACK) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate %llu bytes for the compressed image", (unsigned long long)flen); rc = ITX_ENOMEM; break; }
-            cu->d_comp_cap = flen + ITX_SLACK;
-        }
-        if (!cu->d_blk || cu->d_blk_cap < nblk) {
-            cudaFree(cu->d_blk); cu->d_blk = NULL;
-            if (cudaMalloc((void **)&cu->d_blk, nblk * sizeof(itx_bgzf_block)) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the block table"); rc = ITX_ENOMEM; break; }
-            cu->d_blk_cap = nblk;
-        }
-        if (cudaMemcpyAsync(cu->d_blk, blk, nblk * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+        if ((rc = ensure_stage(cu, Wc + 65536, err))) break;
+        if ((rc = grow_device(cu, (void **)&cu->d_comp, &cu->d_comp_cap, flen + ITX_SLACK, 0, "the compressed image", err))) break;
         for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
         if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
-        if ((rc = scan_begin(&sc, ix, h, cu->d_stream, total, o, ix->tune_window < total ? ix->tune_window : total, err))) break;
-        begun = true;
-        if (timing) fprintf(stderr, "[itx timing] header+alloc+begin %.1f ms\n", now_ms() - tm0);
-        /* copies go window by window; k_inflate is launched over groups of about one resident wave of blocks
-         * (a thread decodes a whole 64 KiB block, so small launches would leave most SMs idle) */
-        int inf_ctas = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inf_ctas, k_inflate, ITX_INF_THREADS, 0);
+        int inf_ctas = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inf_ctas, k_inflate, ITX_INF_THREADS, ITX_INF_SMEM);
         if (inf_ctas < 1) inf_ctas = 1;
-        const uint64_t GROUP = (uint64_t)cu->sm_count * ITX_INF_THREADS * (uint64_t)inf_ctas;     /* one resident wave of threads */
-        {
-            const uint64_t need_thr = ((GROUP + Wc / 8192 + 4096 + 31) / 32) * 32;                   /* a group overshoots by at most one copy window of blocks */
-            if (!cu->d_tabs || cu->d_tabs_threads < need_thr) {
-                cudaFree(cu->d_tabs); cu->d_tabs = NULL;
-                if (cudaMalloc((void **)&cu->d_tabs, need_thr * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
-                cu->d_tabs_threads = need_thr;
-            }
+        const uint64_t inf_grid = (uint64_t)cu->sm_count * (uint64_t)inf_ctas;                    /* resident warps */
+        uint64_t GROUP = inf_grid * ITX_INF_THREADS;                                                /* one resident wave of threads */
+        {   /* small files: no more list slots than the file can have blocks (a data block is never below ~100 compressed bytes in practice;
+             * should a file beat the estimate, groups simply close earlier) */
+            const uint64_t est = flen / 2048 + 64;
+            if (GROUP > est) GROUP = (est + 31) / 32 * 32;
         }
-        uint64_t b = 0, gb0 = 0; int slot = 0;
-        while (b < nblk && rc == ITX_OK) {
-            uint64_t b1 = b + 1;
-            while (b1 < nblk && blk[b1].coff + blk[b1].csize - blk[b].coff <= Wc && b1 - gb0 < cu->d_tabs_threads) b1++;
-            const uint64_t c0 = blk[b].coff, c1 = blk[b1 - 1].coff + blk[b1 - 1].csize;
+        if (!cu->d_tabs || cu->d_tabs_threads < inf_grid * ITX_INF_THREADS) {
+            cudaFree(cu->d_tabs); cu->d_tabs = NULL;
+            if (cudaMalloc((void **)&cu->d_tabs, inf_grid * ITX_INF_THREADS * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
+            cu->d_tabs_threads = inf_grid * ITX_INF_THREADS;
+        }
+        int lz_ctas = 2;                                                                             /* CTAs of k_lz_resolve per SM: bounds the blocks whose history must stay in L2 */
+        { const char *v = getenv("ITX_LZ_CTAS"); if (v && atoi(v) > 0) lz_ctas = atoi(v); }
+        if (!cu->d_mpl || cu->d_m_slots < GROUP) {
+            cudaFree(cu->d_mpl); cudaFree(cu->d_md); cudaFree(cu->d_mn); cu->d_mpl = NULL; cu->d_md = NULL; cu->d_mn = NULL;
+            if (cudaMalloc((void **)&cu->d_mpl, GROUP * ITX_M_WORST * 4) != cudaSuccess || cudaMalloc((void **)&cu->d_md, GROUP * ITX_M_WORST * 2) != cudaSuccess ||
+                cudaMalloc((void **)&cu->d_mn, GROUP * 4) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate the match lists (%llu blocks)", (unsigned long long)GROUP); rc = ITX_ENOMEM; break; }
+            cu->d_m_slots = GROUP;
+        }
+        uint64_t fo = 0, gb0 = 0; int slot = 0; bool ended = false;
+        const uint64_t MARGIN = (64ull << 20) + 65536;      /* a record is at most 2^26 bytes long: chunks this far behind the inflated front are safe to scan */
+        while (!ended && rc == ITX_OK) {
+            const uint64_t n = flen - fo < Wc ? flen - fo : Wc;
+            const bool more_in_file = fo + n < flen;
             cudaEventSynchronize(slot_free[slot]);                             /* the previous copy out of this slot is done */
-            if (itx_parallel_copy(bgzf, c0, c1, cu->h_stage[slot], nth) != ITX_OK) { rc = ITX_ENOMEM; break; }
-            if (cudaMemcpyAsync(cu->d_comp + c0, cu->h_stage[slot], c1 - c0, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+            uint8_t *hs = cu->h_stage[slot];
+            if (n && src_read(S, fo, fo + n, hs, nth) != ITX_OK) { snprintf(err, ITX_ERRLEN, "read error in the BAM file at offset %llu", (unsigned long long)fo); rc = ITX_EIO; break; }
+            /* the blocks that lie completely inside this window */
+            const uint64_t nb_before = nblk; uint64_t off = 0;
+            for (;;) {
+                if (nblk - gb0 >= GROUP) break;                                        /* the group is full: the rest is read again for the next one */
+                if (off + 18 > n) { if (!more_in_file) ended = true; break; }
+                const uint8_t *hd = hs + off;
+                if (!itx_bgzf_header_ok(hd)) { ended = true; break; }                  /* a bad header ends the stream silently (bgzf_read) */
+                const uint32_t bsize = ((uint32_t)hd[16] | (uint32_t)hd[17] << 8) + 1;
+                if (bsize < 26) { ended = true; break; }
+                if (off + bsize > n) { if (!more_in_file) ended = true; break; }      /* continues in the next window, or the file is cut short */
+                uint32_t isize; memcpy(&isize, hd + bsize - 4, 4);
+                if (isize == 0 || isize > 65536) { ended = true; break; }              /* an empty block ends the data (bgzf.c:539-546) */
+                if (nblk == blk_cap) { blk_cap = blk_cap ? blk_cap * 2 : 4096; blk = (itx_bgzf_block *)realloc(blk, sizeof(itx_bgzf_block) * blk_cap); }
+                blk[nblk].coff = fo + off; blk[nblk].csize = bsize; blk[nblk].isize = isize; blk[nblk].uoff = total;
+                nblk++; total += isize; off += bsize;
+            }
+            if (off == 0 && nblk - gb0 < GROUP) ended = true;                          /* no progress is possible */
+            if (!begun) {
+                /* the BAM header is parsed on the host out of the first blocks of the first window */
+                uint8_t *hb = NULL; char e2[ITX_ERRLEN]; e2[0] = 0;
+                for (uint64_t nb = 1; nb <= nblk && !h; nb = nb < 4 ? nb + 1 : nb * 2) {
+                    const uint64_t n1 = nb < nblk ? nb : nblk, ub = blk[n1 - 1].uoff + blk[n1 - 1].isize;
+                    hb = (uint8_t *)realloc(hb, ub + 64);
+                    if (itx_bgzf_inflate_range(hs, blk, 0, n1, hb, nth, NULL) != ITX_OK) { snprintf(e2, ITX_ERRLEN, "BGZF inflate failed in the header blocks"); break; }
+                    h = itx_bam_header_parse(ix, hb, ub, o->addChr, e2);
+                    if (!h && (n1 == nblk || memcmp(hb, "BAM\1", 4) != 0)) break;
+                }
+                free(hb);
+                if (!h) { snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : (nblk ? "truncated BAM header" : "invalid BAM binary header (this is not a BAM file)")); rc = ITX_EFORMAT; break; }
+                /* first guess of the stream size: this window's ratio over the whole file, with a margin */
+                uint64_t guess = total;
+                if (!ended) {
+                    guess = (uint64_t)((double)flen * ((double)total / (double)off) * 1.08) + (64ull << 20);
+                    if (!(cu->d_stream && cu->d_stream_cap >= guess + ITX_SLACK)) {
+                        size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+                        const uint64_t room = (uint64_t)fr + (cu->d_stream ? cu->d_stream_cap : 0);      /* the old buffer is released first */
+                        if (guess + ITX_SLACK + (1ull << 30) > room && room > (2ull << 30)) guess = room - (1ull << 30) - ITX_SLACK;
+                    }
+                }
+                if (!(cu->d_stream && cu->d_stream_cap >= guess + ITX_SLACK)) { cudaStreamSynchronize(cu->stream); cudaFree(cu->d_stream); cu->d_stream = NULL; cu->d_stream_cap = 0; }
+                if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, guess + ITX_SLACK, 0, "the uncompressed stream", err))) break;
+                if ((rc = scan_begin(&sc, ix, h, cu->d_stream, 1ull << 62, o, guess < ix->tune_window ? guess : ix->tune_window, err))) break;
+                begun = true;
+                if (timing) fprintf(stderr, "[itx timing] first window read, header parsed, buffers ready at %.1f ms\n", now_ms() - tm0);
+            }
+            if (total + ITX_SLACK > cu->d_stream_cap) {
+                /* the guess was too small: grow, keeping what has been inflated (everything before the open group) */
+                const uint64_t want = total + total / 2 + (256ull << 20);
+                if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, want + ITX_SLACK, blk[gb0].uoff, "the uncompressed stream", err))) break;
+                sc.b = cu->d_stream;
+            }
+            if (nblk > cu->d_blk_cap) {
+                const uint64_t want = nblk * 2 + 65536;
+                void *pb = cu->d_blk; uint64_t capb = cu->d_blk_cap * sizeof(itx_bgzf_block);
+                rc = grow_device(cu, &pb, &capb, want * sizeof(itx_bgzf_block), nb_before * sizeof(itx_bgzf_block), "the block table", err);
+                cu->d_blk = (itx_bgzf_block *)pb; cu->d_blk_cap = capb / sizeof(itx_bgzf_block);
+                if (rc) break;
+            }
+            if (off) {
+                if (cudaMemcpyAsync(cu->d_comp + fo, hs, off, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess ||
+                    cudaMemcpyAsync(cu->d_blk + nb_before, blk + nb_before, (nblk - nb_before) * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+            }
             cudaEventRecord(slot_free[slot], cu->copy_stream);
-            b = b1;
-            if (b - gb0 >= GROUP || b - gb0 >= cu->d_tabs_threads || b == nblk) {
+            fo += off;
+            if (nblk > gb0 && (nblk - gb0 >= GROUP || ended)) {
                 cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);           /* copies are in order: the last one covers the group */
-                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = b - gb0; IA.out = cu->d_stream; IA.status = cu->D.status; IA.tabs = cu->d_tabs;
-                if (b - gb0 > cu->d_tabs_threads) { snprintf(err, ITX_ERRLEN, "inflate group larger than its table store"); rc = ITX_ENOMEM; break; }
-                const unsigned nb = (unsigned)((b - gb0 + ITX_INF_THREADS - 1) / ITX_INF_THREADS);
+                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = nblk - gb0; IA.out = cu->d_stream; IA.status = cu->D.status; IA.tabs = cu->d_tabs;
+                IA.m_pl = cu->d_mpl; IA.m_d = cu->d_md; IA.m_n = cu->d_mn; IA.m_cap = ITX_M_WORST;
+                uint64_t nb = (IA.nblk + ITX_INF_THREADS - 1) / ITX_INF_THREADS; if (nb > inf_grid) nb = inf_grid;
                 if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
-                k_inflate<<<nb, ITX_INF_THREADS, 0, cu->stream>>>(IA);
+                k_inflate<<<(unsigned)nb, ITX_INF_THREADS, ITX_INF_SMEM, cu->stream>>>(IA);
+                uint64_t lzb = (IA.nblk + ITX_LZ_WARPS - 1) / ITX_LZ_WARPS, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
+                k_lz_resolve<<<(unsigned)lzb, ITX_LZ_WARPS * 32, 0, cu->stream>>>(IA);
                 if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
-                sc.n_launch++;
-                const uint64_t avail = b < nblk ? blk[b].uoff : total;
-                const uint64_t k_hi = b >= nblk ? sc.k_end : blk[gb0].uoff / cu->C;
-                if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, avail, err);
-                gb0 = b;
+                sc.n_launch += 2;
+                gb0 = nblk;
+                if (!ended) {
+                    const uint64_t k_hi = total > MARGIN ? (total - MARGIN) / cu->C : 0;
+                    if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, total, err);
+                }
             }
             slot ^= 1;
         }
-        if (rc == ITX_OK && sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
-        if (timing) fprintf(stderr, "[itx timing] copies staged and everything enqueued at %.1f ms\n", now_ms() - tm0);
+        if (rc != ITX_OK) break;
+        if (!begun) { snprintf(err, ITX_ERRLEN, "invalid BAM binary header (this is not a BAM file)"); rc = ITX_EFORMAT; break; }
+        sc.len = total; sc.k_end = total > h->hdr_len ? (total + cu->C - 1) / cu->C : sc.k_first;
+        if (sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
+        if (timing) fprintf(stderr, "[itx timing] file read, copies and kernels enqueued at %.1f ms (%llu blocks, %llu bytes)\n", now_ms() - tm0, (unsigned long long)nblk, (unsigned long long)total);
         if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
-        else cudaStreamSynchronize(cu->stream);
         if (timing) fprintf(stderr, "[itx timing] device done at %.1f ms\n", now_ms() - tm0);
         if (rc == ITX_OK) {
             uint32_t st[8];
@@ -580,12 +653,21 @@ static int scan_bgzf_device_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t
         }
         for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[2 * i], wev[2 * i + 1]) == cudaSuccess) inflate_ms += ms; }
     } while (0);
-    if (rc != ITX_OK && !err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError()));
-    (void)begun;
-    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is k_inflate's device time */
+    if (rc != ITX_OK) { cudaStreamSynchronize(cu->stream); cudaStreamSynchronize(cu->copy_stream); if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError())); }
+    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time (k_inflate + k_lz_resolve) */
     for (int i = 0; i < 2; i++) if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    free(blk);
     itx_bam_header_free(h);
     return rc;
+}
+
+static bool inflate_on_host(void) { const char *m = getenv("ITX_INFLATE"); return m && strcmp(m, "host") == 0; }   /* A/B switch: zlib on the host threads */
+static int scan_bgzf_host_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth);
+static int inflate_thread_count(const itx_index *ix) {
+    int nth = ix->tune_threads > 0 ? ix->tune_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (nth < 1) nth = 1;
+    if (nth > 256) nth = 256;
+    return nth;
 }
 
 extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o,
@@ -596,20 +678,19 @@ extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t
     itx_cuda *cu = ix->cu;
     CK(cudaSetDevice(cu->device));
     memset(&ix->prof, 0, sizeof ix->prof);
+    const int nth = inflate_thread_count(ix);
+    if (inflate_on_host()) return scan_bgzf_host_inflate(ix, bgzf, flen, o, cnt, err, nth);
+    itx_bgzf_src S; S.fd = -1; S.mem = bgzf; S.len = flen;
+    return scan_bgzf_device_inflate(ix, &S, o, cnt, err, nth);
+}
+
+/* the A/B path: block table from a walk over the whole image, zlib on the host threads, uncompressed windows over PCIe */
+static int scan_bgzf_host_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth) {
+    itx_cuda *cu = ix->cu;
+    int rc;
     itx_bgzf_block *blk = NULL; uint64_t nblk = 0, total = 0;
     if ((rc = itx_bgzf_scan(bgzf, flen, &blk, &nblk, &total, err))) return rc;
     if (total < 12) { free(blk); snprintf(err, ITX_ERRLEN, "invalid BAM binary header (this is not a BAM file)"); return ITX_EFORMAT; }
-    int nth = ix->tune_threads > 0 ? ix->tune_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
-    if (nth < 1) nth = 1;
-    if (nth > 256) nth = 256;
-    {   /* ITX_INFLATE=host keeps zlib on the host threads; the default inflates on the device */
-        const char *m = getenv("ITX_INFLATE");
-        if (!(m && strcmp(m, "host") == 0)) {
-            rc = scan_bgzf_device_inflate(ix, bgzf, flen, o, cnt, err, blk, nblk, total, nth);
-            free(blk);
-            return rc;
-        }
-    }
     /* windows of whole BGZF blocks, about W uncompressed bytes each, inflated straight into pinned memory */
     uint64_t W = ix->tune_window < (64ull << 20) ? ix->tune_window : (64ull << 20);
     if (W > total) W = total;
@@ -662,12 +743,23 @@ static int scan_one_file(itx_index *ix, const char *path, const itx_scan_opts *o
     if (fd < 0) { snprintf(err, ITX_ERRLEN, "Error\n[bam file %s: %s]", path, strerror(errno)); return ITX_EIO; }
     struct stat st;
     if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); snprintf(err, ITX_ERRLEN, "Error\n[bam file %s is empty or unreadable]", path); return ITX_EIO; }
-    void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    int rc;
+    if (inflate_on_host()) {
+        void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) { snprintf(err, ITX_ERRLEN, "mmap(%s): %s", path, strerror(errno)); return ITX_EIO; }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        rc = itx_scan_bgzf_memory(ix, (const uint8_t *)m, (uint64_t)st.st_size, o, cnt, err);
+        munmap(m, (size_t)st.st_size);
+        return rc;
+    }
+    if ((rc = check_opts(o, err))) { close(fd); return rc; }
+    if (cudaSetDevice(ix->cu->device) != cudaSuccess) { close(fd); snprintf(err, ITX_ERRLEN, "cudaSetDevice failed"); return ITX_ENODEV; }
+    memset(&ix->prof, 0, sizeof ix->prof);
+    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    itx_bgzf_src S; S.fd = fd; S.mem = NULL; S.len = (uint64_t)st.st_size;
+    rc = scan_bgzf_device_inflate(ix, &S, o, cnt, err, inflate_thread_count(ix));
     close(fd);
-    if (m == MAP_FAILED) { snprintf(err, ITX_ERRLEN, "mmap(%s): %s", path, strerror(errno)); return ITX_EIO; }
-    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
-    int rc = itx_scan_bgzf_memory(ix, (const uint8_t *)m, (uint64_t)st.st_size, o, cnt, err);
-    munmap(m, (size_t)st.st_size);
     return rc;
 }
 
@@ -732,6 +824,16 @@ extern "C" uint64_t itx_trace_fetch(itx_index *ix, itx_trace *out, uint64_t cap)
     if (n > cu->trace_cap) n = cu->trace_cap;
     if (n > cap) n = cap;
     cudaMemcpy(out, cu->d_trace, n * sizeof(itx_trace), cudaMemcpyDeviceToHost);
+    return n;
+}
+
+extern "C" uint64_t itx_stream_fetch(itx_index *ix, uint8_t *out, uint64_t cap) {
+    itx_cuda *cu = ix->cu;
+    if (!cu->d_stream) return 0;
+    cudaSetDevice(cu->device);
+    uint64_t n = ix->prof.stream_bytes < cu->d_stream_cap ? ix->prof.stream_bytes : cu->d_stream_cap;
+    if (n > cap) n = cap;
+    if (n && cudaMemcpy(out, cu->d_stream, n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
 }
 

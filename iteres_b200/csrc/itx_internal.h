@@ -153,6 +153,8 @@ int itx_bgzf_scan(const uint8_t *file, uint64_t len, itx_bgzf_block **blocks, ui
                   char err[ITX_ERRLEN]);
 /* inflate blocks [b0,b1) into dst + (uoff - uoff[b0]) with nth threads; returns 0 or ITX_EFORMAT */
 int itx_parallel_copy(const uint8_t *file, uint64_t o0, uint64_t o1, uint8_t *dst, int nth);
+int itx_parallel_pread(int fd, uint64_t o0, uint64_t o1, uint8_t *dst, int nth);
+int itx_bgzf_header_ok(const uint8_t *h18);
 int itx_bgzf_inflate_range(const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1,
                            uint8_t *dst, int nth, double *busy_ms);
 

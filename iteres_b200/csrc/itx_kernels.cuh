@@ -480,13 +480,17 @@ __global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
 }
 
 /* ------------------------------------------------------------------ BGZF inflate on the device */
-/* one thread per BGZF block; the thread's Huffman tables (~1 KiB) live in global memory, interleaved inside
- * the warp -- cell j of lane l at tabs[warp][j * 32 + l] -- so that lanes reading the same cell index make one
- * coalesced request; they stay L1 / L2 resident and cost no shared memory, which lets 20 warps run per SM */
-struct itx_tab_glob {
-    uint16_t *base;
-    __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return base[j * 32u]; }
-    __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { base[j * 32u] = v; }
+/* One thread per BGZF block, one warp per CTA, the warp's 32 blocks decoded in lock step.  A thread's look-up
+ * tables (ITX_LUT_CELLS 16-bit cells) live in shared memory as 32-bit words interleaved across the lanes -- word
+ * w of lane l at index w * 32 + l -- so every lane owns a bank whatever cell it reads; 20 KiB per warp, ten warps
+ * per SM.  The symbol arrays of the long codes live in global memory, interleaved the same way (cell j of lane l
+ * at tabs[warp][j * 32 + l]).  A warp takes the groups of 32 blocks blockIdx.x, blockIdx.x + gridDim.x, ... */
+struct itx_tab_dev {
+    uint16_t *g, *s;
+    __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return g[j * 32u]; }
+    __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { g[j * 32u] = v; }
+    __device__ __forceinline__ uint16_t lut(uint32_t j) const { return s[((j >> 1) << 6) | (j & 1u)]; }
+    __device__ __forceinline__ void lut_set(uint32_t j, uint16_t v) const { s[((j >> 1) << 6) | (j & 1u)] = v; }
 };
 struct itx_inflate_args {
     const uint8_t *file;                 /* the compressed file image on the device */
@@ -494,29 +498,73 @@ struct itx_inflate_args {
     unsigned long long b0, nblk;         /* blocks [b0, b0 + nblk) */
     uint8_t *out;                        /* uncompressed stream: block b goes to out + blk[b].uoff */
     uint32_t *status;                    /* [5] number of blocks that failed, [6] index of one of them */
-    uint16_t *tabs;                      /* ITX_T_CELLS cells per thread of the launch */
+    uint16_t *tabs;                      /* ITX_T_CELLS cells per thread of the grid */
+    /* deferred matches: block g0 of the launch owns m_pl[g0 * m_cap ..] / m_d[g0 * m_cap ..]; m_n[g0] = entries or ITX_M_NONE */
+    uint32_t *m_pl; uint16_t *m_d; uint32_t *m_n; uint32_t m_cap;
 };
-#define ITX_INF_THREADS 128
-__global__ void __launch_bounds__(ITX_INF_THREADS, 8) k_inflate(const itx_inflate_args A) {
-    const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long b = A.b0 + gid;
-    const bool mine = b < A.b0 + A.nblk;
-    itx_inflater<itx_tab_glob> I;
-    I.tab.base = A.tabs + (gid >> 5) * (32ull * ITX_T_CELLS) + (gid & 31);
-    I.in = A.file; I.in_len = 0; I.out = A.out; I.out_cap = 0;
-    I.begin(0);
-    I.state = 2;
-    if (mine) {
-        const itx_bgzf_block B = A.blk[b];
-        I.in = A.file + B.coff + 18; I.in_len = B.csize - 18 - 8;        /* header 18, footer CRC32 + ISIZE */
-        I.out = A.out + B.uoff; I.out_cap = B.isize;
-        I.begin(B.isize);
+#define ITX_INF_THREADS 32
+#define ITX_INF_SMEM (ITX_LUT_CELLS * 2u * ITX_INF_THREADS)
+/* First pass over every block of the launch: Huffman decoding, literals stored, matches listed (m_cap != 0) or
+ * copied in line (m_cap == 0).  The host sizes the lists for the worst case (ITX_M_WORST entries: a match is at
+ * least three bytes long), so a list cannot overflow. */
+#define ITX_M_WORST 21848u
+__global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
+    extern __shared__ __align__(16) uint8_t itx_inf_smem[];
+    const uint32_t lane = threadIdx.x;
+    itx_inflater<itx_tab_dev> I;
+    I.tab.g = A.tabs + (size_t)blockIdx.x * (32u * ITX_T_CELLS) + lane;
+    I.tab.s = reinterpret_cast<uint16_t *>(itx_inf_smem) + lane * 2u;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * 32u; g0 < A.nblk; g0 += (unsigned long long)gridDim.x * 32u) {
+        const unsigned long long g = g0 + lane, b = A.b0 + g;
+        const bool mine = g < A.nblk;
+        I.state = ITX_ST_DONE; I.err = ITX_INF_OK; I.m_cap = 0; I.n_match = 0;
+        if (mine) {
+            const itx_bgzf_block B = A.blk[b];
+            I.out = A.out + B.uoff; I.out_cap = B.isize;
+            if (A.m_cap) { I.m_cap = A.m_cap; I.m_pl = A.m_pl + g * A.m_cap; I.m_d = A.m_d + g * A.m_cap; }
+            I.begin(A.file + B.coff + 18, B.csize - 18 - 8, B.isize);          /* header 18, footer CRC32 + ISIZE */
+        }
+        /* the warp's 32 blocks step together: a header (table build), one symbol or one copy step per round */
+        while (__any_sync(0xffffffffu, I.running())) {
+            if (I.running()) I.advance();
+        }
+        if (mine) {
+            if (A.m_cap) A.m_n[g] = I.state == ITX_ST_DONE ? I.n_match : ITX_M_NONE;
+            if (I.state != ITX_ST_DONE) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
+        }
+        __syncwarp();
     }
-    /* the warp's 32 blocks step together: a header (table build) or one symbol per round */
-    while (__any_sync(0xffffffffu, I.state < 2)) {
-        if (I.state < 2) I.advance();
+}
+
+/* Second pass: a warp per block copies the block's listed matches, 32 entries at a time.  Only a few thousand
+ * blocks are in flight, so the 32 KiB of history a copy may reach back into stay in L2 (the first pass has tens
+ * of thousands of blocks in flight and would go to DRAM for every match). */
+#define ITX_LZ_WARPS 4
+__global__ void __launch_bounds__(ITX_LZ_WARPS * 32) k_lz_resolve(const itx_inflate_args A) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * ITX_LZ_WARPS + (threadIdx.x >> 5), nw = (unsigned long long)gridDim.x * ITX_LZ_WARPS;
+    for (unsigned long long g = w0; g < A.nblk; g += nw) {
+        const uint32_t n = A.m_n[g];
+        if (n == ITX_M_NONE || n == 0) continue;
+        uint8_t *base = A.out + A.blk[A.b0 + g].uoff;
+        const uint32_t *pl = A.m_pl + g * A.m_cap; const uint16_t *md = A.m_d + g * A.m_cap;
+        uint32_t e_next = lane < n ? __ldcs(pl + lane) : 0u, d_next = lane < n ? (uint32_t)__ldcs(md + lane) : 0u;
+        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+            const uint32_t e = e_next, dist = d_next;
+            const uint32_t kn = k0 + 32 + lane;
+            if (kn < n) { e_next = __ldcs(pl + kn); d_next = (uint32_t)__ldcs(md + kn); }      /* the next batch's entries are on their way */
+            const uint32_t pos = e & 0xffffu, len = e >> 16;
+            uint32_t undone = __ballot_sync(0xffffffffu, k0 + lane < n);
+            while (undone) {
+                const uint32_t m = (uint32_t)__ffs((int)undone) - 1u;
+                const uint32_t pm = __shfl_sync(0xffffffffu, pos, (int)m);
+                const bool go = ((undone >> lane) & 1u) && itx_lz_ready(pos, len, dist, lane == m, pm);
+                if (go) itx_lz_copy(base + pos, len, dist);
+                __syncwarp();
+                undone &= ~__ballot_sync(0xffffffffu, go);
+            }
+        }
     }
-    if (mine && I.err != ITX_INF_OK) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
 }
 
 __global__ void k_fill_u32(uint32_t *p, unsigned long long n, uint32_t v) {

@@ -324,19 +324,50 @@ int emu_scan_cpg(emu_index *E, const char *bedgraph, int filter, uint32_t *n_lin
     return ITX_OK;
 }
 
-/* the device inflater (itx_inflate.cuh) on one raw-deflate stream, with a plain array as its table store */
+/* the device inflater (itx_inflate.cuh) on one raw-deflate stream, with plain arrays as its table stores */
 struct emu_tab {
-    uint16_t *cells;
+    uint16_t *cells, *luts;
     uint16_t operator()(uint32_t j) const { return cells[j]; }
     void set(uint32_t j, uint16_t v) const { cells[j] = v; }
+    uint16_t lut(uint32_t j) const { return luts[j]; }
+    void lut_set(uint32_t j, uint16_t v) const { luts[j] = v; }
 };
-int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, uint32_t expect, uint32_t *produced) {
-    uint16_t cells[ITX_T_CELLS]; memset(cells, 0, sizeof cells);
-    std::vector<uint8_t> padded(in, in + in_len); padded.resize(in_len + 16, 0);
+/* defer = 0: matches copied in line.  defer = 1: the two-pass mode of the device -- matches listed by the decoder,
+ * then resolved in batches of 32 list entries exactly as the lanes of k_lz_resolve do (an entry goes once its
+ * source ends before the first unfinished entry's output; entries of one round never depend on each other). */
+int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, uint32_t expect, uint32_t *produced, int defer) {
+    uint16_t cells[ITX_T_CELLS], luts[ITX_LUT_CELLS]; memset(cells, 0, sizeof cells); memset(luts, 0, sizeof luts);
+    /* the decoder reads whole aligned words, a few of them past the end: give the stream an odd alignment and slack */
+    std::vector<uint8_t> padded(in_len + 64, 0);
+    const uint32_t skew = in_len % 4;
+    if (in_len) memcpy(padded.data() + 4 + skew, in, in_len);
+    const uint32_t cap = 21848;
+    std::vector<uint32_t> mpl(defer ? cap : 1); std::vector<uint16_t> md(defer ? cap : 1);
     itx_inflater<emu_tab> I;
-    I.tab.cells = cells; I.in = padded.data(); I.in_len = in_len; I.out = out; I.out_cap = out_cap; I.err = 0;
-    const uint32_t rc = I.run(expect);
+    I.tab.cells = cells; I.tab.luts = luts; I.out = out; I.out_cap = out_cap; I.err = 0;
+    I.m_cap = defer ? cap : 0; I.m_pl = mpl.data(); I.m_d = md.data();
+    const uint32_t rc = I.run(padded.data() + 4 + skew, in_len, expect);
     if (produced) *produced = I.out_pos;
+    if (I.state == ITX_ST_OVERFLOW) return 99;
+    if (defer && rc == ITX_INF_OK) {
+        const uint32_t n = I.n_match;
+        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+            uint32_t undone = 0;
+            for (uint32_t l = 0; l < 32 && k0 + l < n; l++) undone |= 1u << l;
+            while (undone) {
+                const uint32_t m = (uint32_t)__builtin_ctz(undone);
+                const uint32_t pm = mpl[k0 + m] & 0xffffu;
+                uint32_t go = 0;
+                for (uint32_t l = 0; l < 32; l++) if ((undone >> l) & 1u) {
+                    const uint32_t e = mpl[k0 + l];
+                    if (itx_lz_ready(e & 0xffffu, e >> 16, md[k0 + l] ? md[k0 + l] : 65536u, l == m, pm)) go |= 1u << l;
+                }
+                /* in reverse lane order: if two entries of a round depended on each other the result would be wrong */
+                for (int l = 31; l >= 0; l--) if ((go >> l) & 1u) { const uint32_t e = mpl[k0 + l]; itx_lz_copy(out + (e & 0xffffu), e >> 16, md[k0 + l]); }
+                undone &= ~go;
+            }
+        }
+    }
     return (int)rc;
 }
 }

@@ -35,7 +35,7 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.emu_query.restype = C.c_int32
         L.emu_query.argtypes = [vp, cp, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_int32)]
-        L.emu_inflate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.emu_inflate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int]
         L.emu_scan_cpg.argtypes = [vp, cp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), cp]
         _lib = L
     return _lib
@@ -109,11 +109,12 @@ class EmuIndex(capi.IndexBase):
         return sel, n.value
 
 
-def inflate(raw_deflate, expect_len, cap=None):
-    """one raw-deflate stream through the device inflater (host build) -> (status, bytes)"""
+def inflate(raw_deflate, expect_len, cap=None, defer=1):
+    """one raw-deflate stream through the device inflater (host build) -> (status, bytes).  defer=1 is the
+    two-pass mode the device runs (matches listed, then resolved in warp-sized batches), defer=0 copies in line."""
     cap = expect_len if cap is None else cap
     src = np.frombuffer(bytes(raw_deflate), dtype=np.uint8)
     dst = np.zeros(max(cap, 1), dtype=np.uint8)
     got = C.c_uint32(0)
-    rc = lib().emu_inflate(src.ctypes.data if len(src) else None, len(src), dst.ctypes.data, cap, expect_len, C.byref(got))
+    rc = lib().emu_inflate(src.ctypes.data if len(src) else None, len(src), dst.ctypes.data, cap, expect_len, C.byref(got), defer)
     return rc, dst[: min(got.value, cap)].tobytes()

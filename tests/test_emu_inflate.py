@@ -28,6 +28,8 @@ def samples():
         "text": (b"the quick brown fox jumps over the lazy dog, " * 1400)[:65000],
         "lowent": bytes(rnd.choice(b"ACGT") for _ in range(65280)),
         "ramp": bytes(range(256)) * 250,
+        "short_periods": b"".join(bytes([65 + i % 26]) * (3 + i % 7) + b"xyz" * (2 + i % 5) + b"abcdefg" * 3 for i in range(2500))[:65000],
+        "triples": bytes(rnd.choice(b"ab") for _ in range(65000)),       # dense 3..6-byte matches: long match lists
     }
     s = synth.Synth(0, 2000, seed=5)
     for mode in (0, 1, 2):
@@ -41,11 +43,12 @@ def samples():
 SAMPLES = samples()
 
 
+@pytest.mark.parametrize("defer", [0, 1])
 @pytest.mark.parametrize("level", [0, 1, 6, 9])
 @pytest.mark.parametrize("name", sorted(SAMPLES))
-def test_matches_zlib(name, level):
+def test_matches_zlib(name, level, defer):
     data = SAMPLES[name]
-    rc, got = emu_lib.inflate(deflate(data, level), len(data))
+    rc, got = emu_lib.inflate(deflate(data, level), len(data), defer=defer)
     assert rc == 0 and got == data
 
 

@@ -180,6 +180,57 @@ def test_device_inflate_matches_host_inflate(level, worlds, tmp_path, monkeypatc
     ora.close()
 
 
+@pytest.mark.parametrize("mode,level", [(0, 1), (1, 6), (2, 9), (2, 0)])
+def test_device_inflate_reproduces_the_stream_byte_for_byte(mode, level, worlds, tmp_path, monkeypatch):
+    """k_inflate + k_lz_resolve against the bytes the generator compressed (file entry and memory-image entry)"""
+    monkeypatch.delenv("ITX_INFLATE", raising=False)
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    bam = str(tmp_path / "reads.bam")
+    n, nrec = s.write_bam(bam, mode, 50000, level=level, threads=4)
+    buf, n2, _ = s.stream(mode, 50000)
+    assert n2 == n
+    ix = capi.Index(cs, rs, rm)
+    want = ix.scan_bam_host(buf.ctypes.data, n, capi.default_opts())
+    ix.reset()
+    assert ix.scan_alignments(bam, capi.default_opts()) == want
+    assert ix.stream_fetch(n + 100) == buf[:n].tobytes()
+    ix.reset()
+    img = np.fromfile(bam, dtype=np.uint8)
+    assert ix.scan_bgzf_memory(img.ctypes.data, len(img), capi.default_opts()) == want
+    assert ix.stream_fetch(n + 100) == buf[:n].tobytes()
+    ix.close()
+
+
+def test_bytes_after_the_eof_block_and_cut_files_end_the_stream_silently(worlds, tmp_path, monkeypatch):
+    """bgzf_read stops at an empty block, a bad header or a short block; whatever came before still counts"""
+    monkeypatch.delenv("ITX_INFLATE", raising=False)
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    bam = str(tmp_path / "reads.bam")
+    s.write_bam(bam, 0, 40000, level=1, threads=4)
+    raw = open(bam, "rb").read()
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_file(bam, O.default_opts())
+    ora.close()
+    junk = str(tmp_path / "junk.bam")
+    open(junk, "wb").write(raw + b"not a gzip member at all" * 3)
+    ix = capi.Index(cs, rs, rm)
+    assert ix.scan_alignments(junk, capi.default_opts()) == want
+    ix.close()
+    # cut inside a block: the blocks before it are the stream
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[: len(raw) * 2 // 3])
+    for inflate in ("device", "host"):
+        monkeypatch.setenv("ITX_INFLATE", inflate)
+        ix = capi.Index(cs, rs, rm)
+        got = ix.scan_alignments(cut, capi.default_opts())
+        if inflate == "device":
+            first = got
+        else:
+            assert got == first
+        assert 0 < got[0] < want[0]
+        ix.close()
+
+
 def test_damaged_bgzf_block_is_reported(worlds, tmp_path, monkeypatch):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bam = str(tmp_path / "reads.bam")
