@@ -17,6 +17,7 @@
 
 #define ITX_SLACK 64
 #define ITX_MAX_EVENTS 4096
+#define ITX_INF_STREAMS 8                  /* inflate groups in flight: copy, Huffman pass, match pass and scan of different groups overlap */
 
 struct itx_cuda {
     int device; cudaStream_t stream, copy_stream;
@@ -43,7 +44,8 @@ struct itx_cuda {
     uint8_t *d_stream; uint64_t d_stream_cap;
     uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
     uint16_t *d_tabs; uint64_t d_tabs_threads;   /* symbol arrays of k_inflate's long codes */
-    uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists of one inflate group */
+    uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists: ITX_INF_STREAMS groups in flight */
+    cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
@@ -85,6 +87,7 @@ static void cuda_free_all(itx_cuda *cu) {
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
     if (cu->marks_made) for (int i = 0; i < 8; i++) cudaEventDestroy(cu->marks[i]);
+    if (cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) { cudaStreamDestroy(cu->inf_stream[i]); cudaEventDestroy(cu->inf_done[i]); }
     if (cu->stream) cudaStreamDestroy(cu->stream);
     if (cu->copy_stream) cudaStreamDestroy(cu->copy_stream);
     free(cu);
@@ -174,6 +177,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
@@ -304,6 +308,7 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     unsigned long long carry = h->hdr_len;
     CK(cudaMemcpyAsync(cu->d_carry, &carry, 8, cudaMemcpyHostToDevice, cu->stream));
     CK(cudaMemsetAsync(cu->d_work, 0, 16, cu->stream));
+    CK(cudaMemsetAsync(cu->D.status, 0, 8 * sizeof(uint32_t), cu->stream));      /* per-scan flags and failure counts */
     {   /* ITX_DECODE_KERNEL=thread selects the one-thread-per-chunk kernel (A/B measurement); chunks that are not whole tiles use it too */
         const char *v = getenv("ITX_DECODE_KERNEL");
         cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_STAGE) != 0 || cu->C > (1u << 20)) ? 1 : 0;
@@ -513,7 +518,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     uint64_t Wc = 64ull << 20;                               /* compressed bytes per read / copy window */
     if (Wc > flen) Wc = flen;
     if (Wc < (1u << 20)) Wc = 1u << 20;
-    cudaEvent_t slot_free[2] = {NULL, NULL};
+    cudaEvent_t slot_free[2] = {NULL, NULL}, begin_ev = NULL;
     enum { MAXW = 256 }; static cudaEvent_t wev[2 * MAXW]; static int wev_made = 0; int nw = 0;
     itx_bgzf_block *blk = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;
     itx_bam_header *h = NULL;
@@ -523,30 +528,40 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         if ((rc = ensure_stage(cu, Wc + 65536, err))) break;
         if ((rc = grow_device(cu, (void **)&cu->d_comp, &cu->d_comp_cap, flen + ITX_SLACK, 0, "the compressed image", err))) break;
         for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&begin_ev, cudaEventDisableTiming);
         if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
-        int inf_ctas = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inf_ctas, k_inflate, ITX_INF_THREADS, ITX_INF_SMEM);
-        if (inf_ctas < 1) inf_ctas = 1;
-        const uint64_t inf_grid = (uint64_t)cu->sm_count * (uint64_t)inf_ctas;                    /* resident warps */
-        uint64_t GROUP = inf_grid * ITX_INF_THREADS;                                                /* one resident wave of threads */
-        {   /* small files: no more list slots than the file can have blocks (a data block is never below ~100 compressed bytes in practice;
-             * should a file beat the estimate, groups simply close earlier) */
+        /* a group = a run of consecutive blocks handed to the device as one k_inflate + k_lz_resolve pair on one of
+         * ITX_INF_STREAMS streams.  A thread needs tens of milliseconds for its block whatever the launch size, so groups
+         * are kept to a fraction of the resident threads and several are in flight: the file's copy, the two inflate
+         * passes and the scan of successive groups overlap. */
+        if (!cu->inf_made) {
+            for (int i = 0; i < ITX_INF_STREAMS; i++) { cudaStreamCreateWithFlags(&cu->inf_stream[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&cu->inf_done[i], cudaEventDisableTiming); }
+            cu->inf_made = 1;
+        }
+        uint64_t GROUP = 8192;
+        { const char *v = getenv("ITX_INF_GROUP"); if (v && atoll(v) >= 32) GROUP = (uint64_t)atoll(v) / 32 * 32; }
+        {   /* small files: no more slots than the file can have blocks (should a file beat the estimate, groups simply close earlier) */
             const uint64_t est = flen / 2048 + 64;
             if (GROUP > est) GROUP = (est + 31) / 32 * 32;
         }
-        if (!cu->d_tabs || cu->d_tabs_threads < inf_grid * ITX_INF_THREADS) {
+        if (!cu->d_tabs || cu->d_tabs_threads < GROUP * ITX_INF_STREAMS) {
             cudaFree(cu->d_tabs); cu->d_tabs = NULL;
-            if (cudaMalloc((void **)&cu->d_tabs, inf_grid * ITX_INF_THREADS * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
-            cu->d_tabs_threads = inf_grid * ITX_INF_THREADS;
+            if (cudaMalloc((void **)&cu->d_tabs, GROUP * ITX_INF_STREAMS * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
+            cu->d_tabs_threads = GROUP * ITX_INF_STREAMS;
         }
-        int lz_ctas = 2;                                                                             /* CTAs of k_lz_resolve per SM: bounds the blocks whose history must stay in L2 */
-        { const char *v = getenv("ITX_LZ_CTAS"); if (v && atoi(v) > 0) lz_ctas = atoi(v); }
-        if (!cu->d_mpl || cu->d_m_slots < GROUP) {
+        int lz_ctas = 1;
+        cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ_SMEM);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_ctas, k_lz_resolve, ITX_LZ_THREADS, ITX_LZ_SMEM);
+        if (lz_ctas < 1) lz_ctas = 1;
+        if (!cu->d_mpl || cu->d_m_slots < GROUP * ITX_INF_STREAMS) {
             cudaFree(cu->d_mpl); cudaFree(cu->d_md); cudaFree(cu->d_mn); cu->d_mpl = NULL; cu->d_md = NULL; cu->d_mn = NULL;
-            if (cudaMalloc((void **)&cu->d_mpl, GROUP * ITX_M_WORST * 4) != cudaSuccess || cudaMalloc((void **)&cu->d_md, GROUP * ITX_M_WORST * 2) != cudaSuccess ||
-                cudaMalloc((void **)&cu->d_mn, GROUP * 4) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate the match lists (%llu blocks)", (unsigned long long)GROUP); rc = ITX_ENOMEM; break; }
-            cu->d_m_slots = GROUP;
+            const uint64_t ns = GROUP * ITX_INF_STREAMS;
+            cudaStreamSynchronize(cu->stream);
+            if (cudaMalloc((void **)&cu->d_mpl, ns * ITX_M_WORST * 4) != cudaSuccess || cudaMalloc((void **)&cu->d_md, ns * ITX_M_WORST * 2) != cudaSuccess ||
+                cudaMalloc((void **)&cu->d_mn, ns * 4) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate the match lists (%llu blocks)", (unsigned long long)ns); rc = ITX_ENOMEM; break; }
+            cu->d_m_slots = ns;
         }
-        uint64_t fo = 0, gb0 = 0; int slot = 0; bool ended = false;
+        uint64_t fo = 0, gb0 = 0, n_groups = 0; int slot = 0; bool ended = false;
         const uint64_t MARGIN = (64ull << 20) + 65536;      /* a record is at most 2^26 bytes long: chunks this far behind the inflated front are safe to scan */
         while (!ended && rc == ITX_OK) {
             const uint64_t n = flen - fo < Wc ? flen - fo : Wc;
@@ -597,6 +612,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, guess + ITX_SLACK, 0, "the uncompressed stream", err))) break;
                 if ((rc = scan_begin(&sc, ix, h, cu->d_stream, 1ull << 62, o, guess < ix->tune_window ? guess : ix->tune_window, err))) break;
                 begun = true;
+                cudaEventRecord(begin_ev, cu->stream);
                 if (timing) fprintf(stderr, "[itx timing] first window read, header parsed, buffers ready at %.1f ms\n", now_ms() - tm0);
             }
             if (total + ITX_SLACK > cu->d_stream_cap) {
@@ -619,17 +635,22 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             cudaEventRecord(slot_free[slot], cu->copy_stream);
             fo += off;
             if (nblk > gb0 && (nblk - gb0 >= GROUP || ended)) {
-                cudaStreamWaitEvent(cu->stream, slot_free[slot], 0);           /* copies are in order: the last one covers the group */
-                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = nblk - gb0; IA.out = cu->d_stream; IA.status = cu->D.status; IA.tabs = cu->d_tabs;
-                IA.m_pl = cu->d_mpl; IA.m_d = cu->d_md; IA.m_n = cu->d_mn; IA.m_cap = ITX_M_WORST;
-                uint64_t nb = (IA.nblk + ITX_INF_THREADS - 1) / ITX_INF_THREADS; if (nb > inf_grid) nb = inf_grid;
-                if (nw < MAXW) cudaEventRecord(wev[2 * nw], cu->stream);
-                k_inflate<<<(unsigned)nb, ITX_INF_THREADS, ITX_INF_SMEM, cu->stream>>>(IA);
-                uint64_t lzb = (IA.nblk + ITX_LZ_WARPS - 1) / ITX_LZ_WARPS, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
-                k_lz_resolve<<<(unsigned)lzb, ITX_LZ_WARPS * 32, 0, cu->stream>>>(IA);
-                if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], cu->stream); nw++; }
+                const int gs = (int)(n_groups % ITX_INF_STREAMS); cudaStream_t st = cu->inf_stream[gs];
+                cudaStreamWaitEvent(st, slot_free[slot], 0);                   /* copies are in order: the last one covers the group */
+                if (n_groups == 0) cudaStreamWaitEvent(st, begin_ev, 0);       /* the status words are zeroed on the scan stream */
+                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = nblk - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
+                IA.tabs = cu->d_tabs + (size_t)gs * GROUP * ITX_T_CELLS;
+                IA.m_pl = cu->d_mpl + (size_t)gs * GROUP * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * GROUP * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * GROUP; IA.m_cap = ITX_M_WORST;
+                const uint64_t nb = (IA.nblk + ITX_INF_THREADS - 1) / ITX_INF_THREADS;
+                if (nw < MAXW) cudaEventRecord(wev[2 * nw], st);
+                k_inflate<<<(unsigned)nb, ITX_INF_THREADS, ITX_INF_SMEM, st>>>(IA);
+                uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
+                k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
+                if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], st); nw++; }
+                cudaEventRecord(cu->inf_done[gs], st);
+                cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0);          /* the scan stream has now waited for every group so far */
                 sc.n_launch += 2;
-                gb0 = nblk;
+                gb0 = nblk; n_groups++;
                 if (!ended) {
                     const uint64_t k_hi = total > MARGIN ? (total - MARGIN) / cu->C : 0;
                     if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, total, err);
@@ -655,7 +676,9 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     } while (0);
     if (rc != ITX_OK) { cudaStreamSynchronize(cu->stream); cudaStreamSynchronize(cu->copy_stream); if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError())); }
     ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time (k_inflate + k_lz_resolve) */
+    if (rc != ITX_OK && cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) cudaStreamSynchronize(cu->inf_stream[i]);
     for (int i = 0; i < 2; i++) if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    if (begin_ev) cudaEventDestroy(begin_ev);
     free(blk);
     itx_bam_header_free(h);
     return rc;

@@ -43,7 +43,10 @@
 #define ITX_ST_ERROR 3u
 #define ITX_ST_COPY 4u         /* a match is being copied, ITX_COPY_STEP bytes per round (in-line mode only) */
 #define ITX_ST_OVERFLOW 5u     /* deferred mode: the block has more matches than its list holds */
+#define ITX_ST_LPEND 6u        /* a long literal/length code: its symbol is on its way from the symbol array */
+#define ITX_ST_DPEND 7u        /* the same for a long distance code (the match length waits in pend_len) */
 #define ITX_COPY_STEP 8u
+#define ITX_BURST 3u           /* literals decoded ahead of the general symbol of a round */
 #define ITX_M_NONE 0xffffffffu /* match count of a block that overflowed or failed */
 
 ITX_HD uint32_t itx_brev32(uint32_t x) {
@@ -61,15 +64,16 @@ ITX_HD uint32_t itx_brev32(uint32_t x) {
 
 template <class Tab>
 struct itx_inflater {
-    /* input: aligned 32-bit words, two of them always in flight ahead of the bit buffer */
-    const uint32_t *inw, *in_lim;          /* next word to load; words at or past in_lim + 3 mean the stream overran */
-    uint32_t next0, next1;
+    /* input: aligned 32-bit words, three of them always in flight ahead of the bit buffer */
+    const uint32_t *inw, *in_lim;          /* next word to load; the word after the last one of the stream */
+    uint32_t next0, next1, next2;
     uint64_t bitbuf; uint32_t bitcnt;
     uint8_t *out; uint32_t out_cap, out_pos;
     Tab tab;
     uint32_t err;
     uint32_t state, last, expect;
-    uint32_t pend_len, pend_dist;          /* ITX_ST_COPY */
+    uint32_t pend_len, pend_dist;          /* ITX_ST_COPY, ITX_ST_DPEND */
+    uint32_t pend_sym;                     /* ITX_ST_LPEND / ITX_ST_DPEND: the symbol loaded in the previous round */
     /* deferred mode (m_cap != 0): literals go to their final place, matches are only LISTED -- entry k is
      * (output position | length << 16, distance) -- and a second pass (k_lz_resolve) copies them while the block's
      * history is cache resident; a decoder that copies in line waits on a DRAM read of its own history every round */
@@ -84,7 +88,7 @@ struct itx_inflater {
         return *p;
 #endif
     }
-    /* `in` may have any alignment; reads run up to 12 bytes past in + in_len (buffers carry slack) and never before
+    /* `in` may have any alignment; reads run up to 28 bytes past in + in_len (buffers carry slack) and never before
      * the aligned word holding in[0] */
     ITX_HDM void set_input(const uint8_t *in, uint32_t in_len) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(in);
@@ -92,16 +96,16 @@ struct itx_inflater {
         in_lim = reinterpret_cast<const uint32_t *>((a + in_len + 3) & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(a & 3) * 8;
         bitbuf = (uint64_t)(ldw(inw) >> sh); bitcnt = 32 - sh;
-        next0 = ldw(inw + 1); next1 = ldw(inw + 2); inw += 3;
+        next0 = ldw(inw + 1); next1 = ldw(inw + 2); next2 = ldw(inw + 3); inw += 4;
     }
     /* at least 32 valid bits afterwards */
     ITX_HDM void refill() {
         if (bitcnt <= 32) {
             bitbuf |= (uint64_t)next0 << bitcnt; bitcnt += 32;
-            next0 = next1; next1 = ldw(inw); inw++;
+            next0 = next1; next1 = next2; next2 = ldw(inw); inw++;
         }
     }
-    ITX_HDM bool overrun() const { return inw > in_lim + 4; }      /* more words loaded than the stream has (+ the 3 in flight) */
+    ITX_HDM bool overrun() const { return inw > in_lim + 5; }      /* more words loaded than the stream has (+ the three in flight and the bit buffer) */
     ITX_HDM void consume(uint32_t n) { bitbuf >>= n; bitcnt -= n; }
     ITX_HDM uint32_t take(uint32_t n) { const uint32_t v = (uint32_t)bitbuf & ((1u << n) - 1u); consume(n); return v; }   /* no refill: the caller knows the bits are there */
     ITX_HDM uint32_t bits(uint32_t n) { refill(); return take(n); }                                                    /* n <= 16 */
@@ -168,8 +172,10 @@ struct itx_inflater {
         }
         return left;
     }
-    /* codes longer than the table index: canonical bit-serial walk from length `from` + 1 */
-    ITX_HDM int32_t decode_long(const uint32_t c[8], uint32_t sym_base, uint32_t from, uint32_t first0, uint32_t index0) {
+    /* codes longer than the table index: canonical bit-serial walk from length `from` + 1.  Returns the slot of
+     * the symbol in the (global-memory) symbol array, or -1; the caller loads it and uses it one round later, so
+     * that the load's latency is spent on the other lanes' next symbols instead of stalling the warp. */
+    ITX_HDM int32_t walk_long(const uint32_t c[8], uint32_t from, uint32_t first0, uint32_t index0) {
         uint32_t buf = (uint32_t)bitbuf;
         int32_t code = (int32_t)((itx_brev32(buf) >> (32 - from)) << 1), first = (int32_t)first0, index = (int32_t)index0;
         buf >>= from;
@@ -178,22 +184,11 @@ struct itx_inflater {
             if (len > from) {
                 code |= (int32_t)(buf & 1u); buf >>= 1;
                 const int32_t count = (int32_t)((len & 1) ? (c[len >> 1] >> 16) : (c[len >> 1] & 0xffffu));
-                if (code - count < first) { consume(len); return (int32_t)tab(sym_base + (uint32_t)(index + (code - first))); }
+                if (code - count < first) { consume(len); return index + (code - first); }
                 index += count; first += count; first <<= 1; code <<= 1;
             }
         }
         return -1;
-    }
-    /* one literal/length symbol; at least 15 bits must be in the buffer */
-    ITX_HDM int32_t decode_l() {
-        const uint32_t e = tab.lut(ITX_LUT_L + ((uint32_t)bitbuf & ((1u << ITX_LB) - 1u)));
-        if (e & 15u) { consume(e & 15u); return (int32_t)(e >> 4); }
-        return decode_long(lc, ITX_T_LSYM, ITX_LB, lfirst, lindex);
-    }
-    ITX_HDM int32_t decode_d() {
-        const uint32_t e = tab.lut(ITX_LUT_D + ((uint32_t)bitbuf & ((1u << ITX_DB) - 1u)));
-        if (e & 15u) { consume(e & 15u); return (int32_t)(e >> 4); }
-        return decode_long(dc, ITX_T_DSYM, ITX_DB, dfirst, dindex);
     }
 
     ITX_HDM void put(uint8_t b) { if (out_pos < out_cap) out[out_pos] = b; out_pos++; }
@@ -220,31 +215,61 @@ struct itx_inflater {
         out_pos += n; pend_len -= n;
         state = pend_len ? ITX_ST_COPY : ITX_ST_SYMBOL;
     }
-    /* one literal / length-distance pair / end-of-block; false = invalid data */
-    ITX_HDM bool symbol() {
-        if (out_pos > out_cap || overrun()) return false;
-        refill();
-        int32_t s = decode_l();
-        if (s < 0) return false;
-        if (s < 256) { put((uint8_t)s); return true; }
-        if (s == 256) { state = last ? ITX_ST_DONE : ITX_ST_HEADER; return true; }
-        s -= 257;
-        if (s >= 29) return false;
-        const uint32_t len = lbase((uint32_t)s) + take(lext((uint32_t)s));      /* <= 15 + 5 of the >= 32 bits are gone */
-        refill();
-        const int32_t d = decode_d();
-        if (d < 0 || d >= 30) return false;
-        const uint32_t dist = dbase((uint32_t)d) + take(dext((uint32_t)d));      /* <= 15 + 13 */
-        if (dist > out_pos) return false;
-        if (out_pos + len > out_cap) { out_pos += len; return false; }
-        if (m_cap) {
-            if (n_match >= m_cap) { state = ITX_ST_OVERFLOW; return true; }
-            m_pl[n_match] = out_pos | (len << 16); m_d[n_match] = (uint16_t)dist; n_match++;
-            out_pos += len;
-            return true;
+    /* One round of the symbol states.  The phases are written so that the lanes of a warp re-converge before each
+     * of them: (1) a literal/length symbol -- out of the table, or the one a long code asked for in the previous
+     * round; (2) what the symbol means, down to the distance symbol; (3) the match.  false = invalid data. */
+    ITX_HDM bool symbol_round() {
+        uint32_t s = 0, d = 0, len = 0; bool have_s = false, have_d = false;
+        if (state == ITX_ST_SYMBOL) {
+            if (out_pos > out_cap || overrun()) return false;
+            refill();
+            uint32_t e = tab.lut(ITX_LUT_L + ((uint32_t)bitbuf & ((1u << ITX_LB) - 1u)));
+            /* most symbols of a BAM stream are literals with short codes: up to ITX_BURST of them go out right here,
+             * before the general symbol of the round (3 x 8 of the >= 32 bits at most, so every index is made of real bits) */
+#pragma unroll
+            for (uint32_t b = 0; b < ITX_BURST; b++) {
+                if ((e & 15u) && e < (256u << 4)) {
+                    consume(e & 15u); put((uint8_t)(e >> 4));
+                    e = tab.lut(ITX_LUT_L + ((uint32_t)bitbuf & ((1u << ITX_LB) - 1u)));
+                }
+            }
+            refill();                                                      /* only adds high bits: e stays valid */
+            if (e & 15u) { consume(e & 15u); s = e >> 4; have_s = true; }
+            else {
+                const int32_t slot = walk_long(lc, ITX_LB, lfirst, lindex);
+                if (slot < 0) return false;
+                pend_sym = tab(ITX_T_LSYM + (uint32_t)slot); state = ITX_ST_LPEND;
+            }
+        } else if (state == ITX_ST_LPEND) { s = pend_sym; have_s = true; state = ITX_ST_SYMBOL; }
+        else if (state == ITX_ST_DPEND) { d = pend_sym; len = pend_len; have_d = true; state = ITX_ST_SYMBOL; }
+        if (have_s) {
+            if (s < 256) put((uint8_t)s);
+            else if (s == 256) state = last ? ITX_ST_DONE : ITX_ST_HEADER;
+            else {
+                s -= 257;
+                if (s >= 29) return false;
+                len = lbase(s) + take(lext(s));                            /* <= 15 + 5 of the >= 32 bits are gone */
+                refill();
+                const uint32_t e = tab.lut(ITX_LUT_D + ((uint32_t)bitbuf & ((1u << ITX_DB) - 1u)));
+                if (e & 15u) { consume(e & 15u); d = e >> 4; have_d = true; }
+                else {
+                    const int32_t slot = walk_long(dc, ITX_DB, dfirst, dindex);
+                    if (slot < 0) return false;
+                    pend_sym = tab(ITX_T_DSYM + (uint32_t)slot); pend_len = len; state = ITX_ST_DPEND;
+                }
+            }
         }
-        pend_len = len; pend_dist = dist;
-        copy_step();
+        if (have_d) {
+            if (d >= 30) return false;
+            const uint32_t dist = dbase(d) + take(dext(d));                /* <= 15 + 13 of the >= 32 bits */
+            if (dist > out_pos) return false;
+            if (out_pos + len > out_cap) { out_pos += len; return false; }
+            if (m_cap) {
+                if (n_match >= m_cap) { state = ITX_ST_OVERFLOW; return true; }
+                m_pl[n_match] = out_pos | (len << 16); m_d[n_match] = (uint16_t)dist; n_match++;
+                out_pos += len;
+            } else { pend_len = len; pend_dist = dist; copy_step(); }
+        }
         return true;
     }
     ITX_HDM bool stored() {
@@ -322,7 +347,7 @@ struct itx_inflater {
      * one symbol, or one step of a long match copy -- and the kernel re-converges the warp between calls. */
     ITX_HDM void begin(const uint8_t *in, uint32_t in_len, uint32_t expect_) {
         set_input(in, in_len);
-        out_pos = 0; state = ITX_ST_HEADER; last = 0; expect = expect_; err = ITX_INF_OK; pend_len = pend_dist = 0; n_match = 0;
+        out_pos = 0; state = ITX_ST_HEADER; last = 0; expect = expect_; err = ITX_INF_OK; pend_len = pend_dist = 0; pend_sym = 0; n_match = 0;
         lfirst = lindex = dfirst = dindex = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) { lc[k] = 0; dc[k] = 0; }
@@ -330,8 +355,8 @@ struct itx_inflater {
     }
     ITX_HDM bool running() const { return state != ITX_ST_DONE && state != ITX_ST_ERROR && state != ITX_ST_OVERFLOW; }
     ITX_HDM void advance() {
-        if (state == ITX_ST_SYMBOL) {
-            if (!symbol()) { state = ITX_ST_ERROR; err = ITX_INF_EDATA; }
+        if (state == ITX_ST_SYMBOL || state == ITX_ST_LPEND || state == ITX_ST_DPEND) {
+            if (!symbol_round()) { state = ITX_ST_ERROR; err = ITX_INF_EDATA; }
         } else if (state == ITX_ST_COPY) {
             copy_step();
         } else if (state == ITX_ST_HEADER) {
@@ -354,13 +379,14 @@ struct itx_inflater {
 /* ------------------------------------------------------------------ second pass of the deferred mode */
 /* copy one match: o[0, len) = o[-d, len - d), bytes replicating when d < len as LZ77 requires.  Eight independent
  * loads per step (one memory latency per eight bytes); periods shorter than eight are replicated out of registers. */
-ITX_HD uint8_t itx_ld_l2(const uint8_t *p) {
+template <bool VIA_L2>
+ITX_HD uint8_t itx_lz_ld(const uint8_t *p) {
 #if defined(__CUDA_ARCH__)
-    return __ldcg(p);                    /* the bytes may have been written by another lane a moment ago: read them where stores land */
-#else
-    return *p;
+    if (VIA_L2) return __ldcg(p);        /* global memory: the bytes may have been stored by another lane a moment ago -- read them where stores land */
 #endif
+    return *p;
 }
+template <bool VIA_L2>
 ITX_HD void itx_lz_copy(uint8_t *o, uint32_t len, uint32_t d) {
     const uint8_t *f = o - d;
     if (d >= 8u || d >= len) {
@@ -368,14 +394,14 @@ ITX_HD void itx_lz_copy(uint8_t *o, uint32_t len, uint32_t d) {
             const uint32_t n = len - k < 8u ? len - k : 8u;
             uint8_t t[8];
 #pragma unroll
-            for (uint32_t j = 0; j < 8u; j++) t[j] = j < n ? itx_ld_l2(f + k + j) : (uint8_t)0;
+            for (uint32_t j = 0; j < 8u; j++) t[j] = j < n ? itx_lz_ld<VIA_L2>(f + k + j) : (uint8_t)0;
 #pragma unroll
             for (uint32_t j = 0; j < 8u; j++) if (j < n) o[k + j] = t[j];
         }
     } else {
         uint8_t t[8];
 #pragma unroll
-        for (uint32_t j = 0; j < 8u; j++) t[j] = j < d ? itx_ld_l2(f + j) : (uint8_t)0;
+        for (uint32_t j = 0; j < 8u; j++) t[j] = j < d ? itx_lz_ld<VIA_L2>(f + j) : (uint8_t)0;
         uint32_t idx = 0;
         for (uint32_t k = 0; k < len; k++) {
             uint8_t b = t[0];

@@ -508,7 +508,7 @@ struct itx_inflate_args {
  * copied in line (m_cap == 0).  The host sizes the lists for the worst case (ITX_M_WORST entries: a match is at
  * least three bytes long), so a list cannot overflow. */
 #define ITX_M_WORST 21848u
-__global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_args A) {
+__global__ void __launch_bounds__(ITX_INF_THREADS, 10) k_inflate(const itx_inflate_args A) {
     extern __shared__ __align__(16) uint8_t itx_inf_smem[];
     const uint32_t lane = threadIdx.x;
     itx_inflater<itx_tab_dev> I;
@@ -536,34 +536,81 @@ __global__ void __launch_bounds__(ITX_INF_THREADS) k_inflate(const itx_inflate_a
     }
 }
 
-/* Second pass: a warp per block copies the block's listed matches, 32 entries at a time.  Only a few thousand
- * blocks are in flight, so the 32 KiB of history a copy may reach back into stay in L2 (the first pass has tens
- * of thousands of blocks in flight and would go to DRAM for every match). */
-#define ITX_LZ_WARPS 4
-__global__ void __launch_bounds__(ITX_LZ_WARPS * 32) k_lz_resolve(const itx_inflate_args A) {
-    const uint32_t lane = threadIdx.x & 31;
-    const unsigned long long w0 = (unsigned long long)blockIdx.x * ITX_LZ_WARPS + (threadIdx.x >> 5), nw = (unsigned long long)gridDim.x * ITX_LZ_WARPS;
-    for (unsigned long long g = w0; g < A.nblk; g += nw) {
+/* Second pass: a CTA per block.  The block (literals in place, holes where matches go) is read into shared memory
+ * with 16-byte loads, warp 0 copies the listed matches there -- 32 list entries at a time, a few cycles per byte of
+ * history instead of a trip to L2 or DRAM -- and the finished block goes back with 16-byte stores.  Meanwhile the
+ * other warps pull the next block's list and bytes into L2. */
+#define ITX_LZ_THREADS 128
+#define ITX_LZ_SMEM (65536u + 32u)
+#define ITX_LZ_NB 4                        /* list batches (of 32 entries) kept in registers ahead of the copy loop */
+__device__ __forceinline__ void itx_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__global__ void __launch_bounds__(ITX_LZ_THREADS) k_lz_resolve(const itx_inflate_args A) {
+    extern __shared__ __align__(16) uint8_t itx_lz_buf[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (unsigned long long g = blockIdx.x; g < A.nblk; g += gridDim.x) {
         const uint32_t n = A.m_n[g];
-        if (n == ITX_M_NONE || n == 0) continue;
-        uint8_t *base = A.out + A.blk[A.b0 + g].uoff;
+        if (n == ITX_M_NONE || n == 0) continue;                       /* failed (reported by k_inflate) or nothing to copy */
+        const itx_bgzf_block B = A.blk[A.b0 + g];
+        uint8_t *base = A.out + B.uoff;
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 15u);
+        const uint8_t *a0 = base - skew;                               /* 16-byte aligned; never before the stream buffer */
+        const uint32_t span = (skew + B.isize + 15u) & ~15u;           /* <= 65536 + 16; the stream buffer carries slack past its end */
         const uint32_t *pl = A.m_pl + g * A.m_cap; const uint16_t *md = A.m_d + g * A.m_cap;
-        uint32_t e_next = lane < n ? __ldcs(pl + lane) : 0u, d_next = lane < n ? (uint32_t)__ldcs(md + lane) : 0u;
-        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-            const uint32_t e = e_next, dist = d_next;
-            const uint32_t kn = k0 + 32 + lane;
-            if (kn < n) { e_next = __ldcs(pl + kn); d_next = (uint32_t)__ldcs(md + kn); }      /* the next batch's entries are on their way */
-            const uint32_t pos = e & 0xffffu, len = e >> 16;
-            uint32_t undone = __ballot_sync(0xffffffffu, k0 + lane < n);
-            while (undone) {
-                const uint32_t m = (uint32_t)__ffs((int)undone) - 1u;
-                const uint32_t pm = __shfl_sync(0xffffffffu, pos, (int)m);
-                const bool go = ((undone >> lane) & 1u) && itx_lz_ready(pos, len, dist, lane == m, pm);
-                if (go) itx_lz_copy(base + pos, len, dist);
-                __syncwarp();
-                undone &= ~__ballot_sync(0xffffffffu, go);
+        for (uint32_t i = tid * 16u; i < span; i += ITX_LZ_THREADS * 16u) *reinterpret_cast<uint4 *>(itx_lz_buf + i) = __ldcs(reinterpret_cast<const uint4 *>(a0 + i));
+        __syncthreads();
+        if (warp == 0) {
+            uint8_t *sm = itx_lz_buf + skew;
+            uint32_t e_nx[ITX_LZ_NB], d_nx[ITX_LZ_NB];
+#pragma unroll
+            for (uint32_t b = 0; b < ITX_LZ_NB; b++) { const uint32_t k = 32u * b + lane; e_nx[b] = k < n ? __ldcs(pl + k) : 0u; d_nx[b] = k < n ? (uint32_t)__ldcs(md + k) : 0u; }
+            for (uint32_t c0 = 0; c0 < n; c0 += 32u * ITX_LZ_NB) {
+                uint32_t e_cu[ITX_LZ_NB], d_cu[ITX_LZ_NB];
+#pragma unroll
+                for (uint32_t b = 0; b < ITX_LZ_NB; b++) {
+                    e_cu[b] = e_nx[b]; d_cu[b] = d_nx[b];
+                    const uint32_t k = c0 + 32u * (ITX_LZ_NB + b) + lane;                      /* the next chunk's entries are on their way */
+                    if (k < n) { e_nx[b] = __ldcs(pl + k); d_nx[b] = (uint32_t)__ldcs(md + k); }
+                }
+#pragma unroll
+                for (uint32_t b = 0; b < ITX_LZ_NB; b++) {
+                    const uint32_t k0 = c0 + 32u * b;
+                    if (k0 < n) {
+                        const uint32_t pos = e_cu[b] & 0xffffu, len = e_cu[b] >> 16, dist = d_cu[b];
+                        uint32_t undone = __ballot_sync(0xffffffffu, k0 + lane < n);
+                        while (undone) {
+                            const uint32_t m = (uint32_t)__ffs((int)undone) - 1u;
+                            const uint32_t pm = __shfl_sync(0xffffffffu, pos, (int)m);
+                            const bool go = ((undone >> lane) & 1u) && itx_lz_ready(pos, len, dist, lane == m, pm);
+                            if (go) itx_lz_copy<false>(sm + pos, len, dist);
+                            __syncwarp();
+                            undone &= ~__ballot_sync(0xffffffffu, go);
+                        }
+                    }
+                }
+            }
+        } else {
+            /* the next block of this CTA: its list and its bytes towards L2 */
+            const unsigned long long g2 = g + gridDim.x;
+            if (g2 < A.nblk) {
+                const uint32_t n2 = A.m_n[g2];
+                if (n2 != ITX_M_NONE && n2 != 0) {
+                    const uint8_t *q0 = reinterpret_cast<const uint8_t *>(A.m_pl + g2 * A.m_cap), *q1 = reinterpret_cast<const uint8_t *>(A.m_d + g2 * A.m_cap);
+                    const itx_bgzf_block B2 = A.blk[A.b0 + g2];
+                    const uint8_t *q2 = A.out + B2.uoff;
+                    const uint32_t t = tid - 32u, nt = ITX_LZ_THREADS - 32u;
+                    for (uint32_t i = t * 128u; i < n2 * 4u; i += nt * 128u) itx_prefetch_l2(q0 + i);
+                    for (uint32_t i = t * 128u; i < n2 * 2u; i += nt * 128u) itx_prefetch_l2(q1 + i);
+                    for (uint32_t i = t * 128u; i < B2.isize; i += nt * 128u) itx_prefetch_l2(q2 + i);
+                }
             }
         }
+        __syncthreads();
+        const uint32_t lo = skew, hi = skew + B.isize;
+        for (uint32_t i = tid * 16u; i < span; i += ITX_LZ_THREADS * 16u) {
+            if (i >= lo && i + 16u <= hi) *reinterpret_cast<uint4 *>(const_cast<uint8_t *>(a0) + i) = *reinterpret_cast<const uint4 *>(itx_lz_buf + i);
+            else for (uint32_t j = 0; j < 16u; j++) if (i + j >= lo && i + j < hi) const_cast<uint8_t *>(a0)[i + j] = itx_lz_buf[i + j];
+        }
+        __syncthreads();
     }
 }
 

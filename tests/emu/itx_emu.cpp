@@ -363,7 +363,7 @@ int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_c
                     if (itx_lz_ready(e & 0xffffu, e >> 16, md[k0 + l] ? md[k0 + l] : 65536u, l == m, pm)) go |= 1u << l;
                 }
                 /* in reverse lane order: if two entries of a round depended on each other the result would be wrong */
-                for (int l = 31; l >= 0; l--) if ((go >> l) & 1u) { const uint32_t e = mpl[k0 + l]; itx_lz_copy(out + (e & 0xffffu), e >> 16, md[k0 + l]); }
+                for (int l = 31; l >= 0; l--) if ((go >> l) & 1u) { const uint32_t e = mpl[k0 + l]; itx_lz_copy<false>(out + (e & 0xffffu), e >> 16, md[k0 + l]); }
                 undone &= ~go;
             }
         }
