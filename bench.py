@@ -7,9 +7,10 @@ when N > 1) -> the 13 global counters back on the host.
 
   value      reads/s with the uncompressed BAM stream already resident in HBM (kernels only)
   e2e        the same metric through the public C-ABI call a user makes, itx_scan_alignments() on a
-             BGZF .bam file: host threads stage the compressed bytes in pinned memory -> cudaMemcpyAsync
-             -> k_inflate (BGZF blocks inflated on the device; ITX_INFLATE=host keeps zlib on the host
-             threads) -> scan kernels -> counter tables back on the host, all inside the timed region
+             BGZF .bam file: host threads pread() the compressed file into pinned memory window by window
+             -> cudaMemcpyAsync -> k_inflate + k_lz_resolve (BGZF blocks inflated on the device in groups
+             pipelined over several streams; ITX_INFLATE=host keeps zlib on the host threads) -> scan
+             kernels -> counter tables back on the host, all inside the timed region
   roofline   the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/iteres stat) on the box's host cores,
              on a bounded sample of the same workload (reference is single threaded by construction;
@@ -377,9 +378,9 @@ def main():
         e2e_t = sum(times) / len(times)
         e2e = {"value": total_rec / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(pe["h2d_bytes"]), "d2h_bytes_per_step": int(pe["d2h_bytes"]),
                "s_per_step": e2e_t, "steps": len(times), "api": "itx_scan_alignments(BGZF .bam, deflate level 1) + itx_sync_counts",
-               "inflate": ("host zlib threads" if pe["inflate_threads"] else "device, k_inflate (one thread per BGZF block)"),
+               "inflate": ("host zlib threads" if pe["inflate_threads"] else "device: k_inflate (Huffman pass, one thread per BGZF block) + k_lz_resolve (match copies, one CTA per block), groups of 8192 blocks on 8 streams"),
                "inflate_threads": int(pe["inflate_threads"]), "inflate_ms": pe["inflate_ms"],
-               "scan_kernel_ms": pe["decode_ms"] + pe["overlap_ms"],
+               "scan_stream_ms": pe["decode_ms"] + pe["overlap_ms"],      # event time on the scan stream: includes its waits on the inflate streams
                "bam_bytes": os.path.getsize(bam)}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)

@@ -45,6 +45,7 @@ struct itx_cuda {
     uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
     uint16_t *d_tabs; uint64_t d_tabs_threads;   /* symbol arrays of k_inflate's long codes */
     uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists: ITX_INF_STREAMS groups in flight */
+    int used_el, used_cpg, host_el, host_cpg;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
@@ -116,6 +117,7 @@ extern "C" void itx_index_reset_counts(itx_index *ix) {
     char err[ITX_ERRLEN];
     cudaSetDevice(ix->cu->device);
     zero_counters(ix, err);
+    ix->cu->used_el = ix->cu->used_cpg = 0;
     memset(ix->cnt, 0, sizeof ix->cnt);
     for (int32_t i = 0; i < ix->subs.n; i++) { ix->sub[i].read_count = ix->sub[i].read_count_unique = 0; ix->sub[i].cpg_count = 0; ix->sub[i].cpg_score = 0; }
     for (int32_t i = 0; i < ix->fams.n; i++) { ix->fam[i].read_count = ix->fam[i].read_count_unique = 0; ix->fam[i].cpg_count = 0; ix->fam[i].cpg_score = 0; }
@@ -301,6 +303,7 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     itx_cuda *cu = ix->cu;
     memset(sc, 0, sizeof *sc);
     sc->ix = ix; sc->h = h; sc->b = d_bam; sc->len = len; sc->o = dev_opts(o);
+    if (o->filter) cu->used_el = 1;
     cu->want_sel = 0;
     int rc = ensure_work(ix, window, err); if (rc) return rc;
     sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
@@ -672,10 +675,11 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 rc = ITX_EFORMAT;
             }
         }
-        for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[2 * i], wev[2 * i + 1]) == cudaSuccess) inflate_ms += ms; }
+        /* groups overlap: report the span from the first group's launch to the last group's end */
+        for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[0], wev[2 * i + 1]) == cudaSuccess && ms > inflate_ms) inflate_ms = ms; }
     } while (0);
     if (rc != ITX_OK) { cudaStreamSynchronize(cu->stream); cudaStreamSynchronize(cu->copy_stream); if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError())); }
-    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time (k_inflate + k_lz_resolve) */
+    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time, first k_inflate launch to last k_lz_resolve end */
     if (rc != ITX_OK && cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) cudaStreamSynchronize(cu->inf_stream[i]);
     for (int i = 0; i < 2; i++) if (slot_free[i]) cudaEventDestroy(slot_free[i]);
     if (begin_ev) cudaEventDestroy(begin_ev);
@@ -819,15 +823,27 @@ extern "C" int itx_sync_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     CK(cudaMemcpyAsync(u64, cu->d_u64, cu->n_u64 * 8, cudaMemcpyDeviceToHost, cu->stream));
     if (!ix->bp) { ix->bp = (uint32_t *)calloc(bl + 1, 4); ix->bp_u = (uint32_t *)calloc(bl + 1, 4); ix->bp_cpg = (double *)calloc(bl + 1, 8); }
     if (!ix->el_cnt) { ix->el_cnt = (uint32_t *)calloc(ne + 1, 4); ix->el_cnt_u = (uint32_t *)calloc(ne + 1, 4); ix->el_cpg = (uint32_t *)calloc(ne + 1, 4); ix->el_cpg_score = (double *)calloc(ne + 1, 8); }
-    if (bl) { CK(cudaMemcpyAsync(ix->bp, cu->d_bp, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->bp_u, cu->d_bp_u, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); }
-    if (ne) { CK(cudaMemcpyAsync(ix->el_cnt, cu->D.el_cnt, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cnt_u, cu->D.el_cnt_u, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); }
-    uint32_t *gc = (uint32_t *)malloc((ng + 1) * 4); double *gs = (double *)malloc((ng + 1) * 8);
-    if (ng) { CK(cudaMemcpyAsync(gc, cu->D.grp_cpg, ng * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(gs, cu->D.grp_cpg_score, ng * 8, cudaMemcpyDeviceToHost, cu->stream)); }
-    if (bl) CK(cudaMemcpyAsync(ix->bp_cpg, cu->D.bp_cpg, bl * 8, cudaMemcpyDeviceToHost, cu->stream));
-    if (ne) { CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream)); }
+    /* only what a scan has touched since the last reset crosses PCIe: the per-locus counters belong to filter mode, the
+     * CpG block to the bedGraph scan; untouched host copies are zero (or are zeroed here if an earlier sync filled them) */
+    const bool el = cu->used_el != 0, cpg = cu->used_cpg != 0;
+    uint64_t moved = cu->n_u64 * 8;
+    if (bl) { CK(cudaMemcpyAsync(ix->bp, cu->d_bp, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->bp_u, cu->d_bp_u, bl * 4, cudaMemcpyDeviceToHost, cu->stream)); moved += bl * 8; }
+    if (ne && el) { CK(cudaMemcpyAsync(ix->el_cnt, cu->D.el_cnt, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cnt_u, cu->D.el_cnt_u, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); moved += ne * 8; cu->host_el = 1; }
+    else if (ne && cu->host_el) { memset(ix->el_cnt, 0, ne * 4); memset(ix->el_cnt_u, 0, ne * 4); cu->host_el = 0; }
+    uint32_t *gc = (uint32_t *)calloc(ng + 1, 4); double *gs = (double *)calloc(ng + 1, 8);
+    if (cpg) {
+        if (ng) { CK(cudaMemcpyAsync(gc, cu->D.grp_cpg, ng * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(gs, cu->D.grp_cpg_score, ng * 8, cudaMemcpyDeviceToHost, cu->stream)); }
+        if (bl) CK(cudaMemcpyAsync(ix->bp_cpg, cu->D.bp_cpg, bl * 8, cudaMemcpyDeviceToHost, cu->stream));
+        if (ne) { CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream)); }
+        moved += ng * 12 + bl * 8 + ne * 12; cu->host_cpg = 1;
+    } else if (cu->host_cpg) {
+        if (bl) memset(ix->bp_cpg, 0, bl * 8);
+        if (ne) { memset(ix->el_cpg, 0, ne * 4); memset(ix->el_cpg_score, 0, ne * 8); }
+        cu->host_cpg = 0;
+    }
     CK(cudaStreamSynchronize(cu->stream));
     float fm = 0; cudaEventElapsedTime(&fm, a, b); ix->prof.finalize_ms = fm; cudaEventDestroy(a); cudaEventDestroy(b);
-    ix->prof.d2h_bytes += cu->n_u64 * 8 + bl * 16 + ne * 20 + ng * 12 + bl * 8;
+    ix->prof.d2h_bytes += moved;
     for (int k = 0; k < 13; k++) ix->cnt[k] = u64[k];
     const unsigned long long *g = u64 + 16;
     const int32_t ns = ix->subs.n, nf = ix->fams.n, nc = ix->clas.n;
@@ -893,6 +909,7 @@ extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uin
     err[0] = 0;
     itx_cuda *cu = ix->cu;
     CK(cudaSetDevice(cu->device));
+    cu->used_cpg = 1;
     struct stat st;
     FILE *f = (stat(bedgraph, &st) == 0 && S_ISDIR(st.st_mode)) ? NULL : fopen(bedgraph, "r");
     if (!f) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }

@@ -524,9 +524,16 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, 10) k_inflate(const itx_infla
             if (A.m_cap) { I.m_cap = A.m_cap; I.m_pl = A.m_pl + g * A.m_cap; I.m_d = A.m_d + g * A.m_cap; }
             I.begin(A.file + B.coff + 18, B.csize - 18 - 8, B.isize);          /* header 18, footer CRC32 + ISIZE */
         }
-        /* the warp's 32 blocks step together: a header (table build), one symbol or one copy step per round */
-        while (__any_sync(0xffffffffu, I.running())) {
-            if (I.running()) I.advance();
+        /* the warp's 32 blocks step together, one round (a few symbols, or a header with its table build) per lane per
+         * iteration.  A table build is thousands of instructions: a lane that reaches a header waits there until most
+         * of the others have reached theirs, so that the builds run side by side instead of one after the other
+         * (blocks written by the same compressor change tables after about the same number of symbols). */
+        for (;;) {
+            const bool run = I.running(), hdr = run && I.state == ITX_ST_HEADER;
+            const uint32_t m_run = __ballot_sync(0xffffffffu, run), m_hdr = __ballot_sync(0xffffffffu, hdr);
+            if (!m_run) break;
+            const bool hdr_go = m_hdr == m_run || __popc(m_hdr) >= 24;
+            if (run && (!hdr || hdr_go)) I.advance();
         }
         if (mine) {
             if (A.m_cap) A.m_n[g] = I.state == ITX_ST_DONE ? I.n_match : ITX_M_NONE;
