@@ -34,7 +34,7 @@ typedef struct itx_index itx_index;
 typedef struct itx_scan_opts {
     uint32_t mapQ;             /* -Q  (10)   unique <=> MAPQ >= mapQ                     generic.c:817 */
     int32_t  filter;           /* 0: stat (subfamily/family/class counters)  1: filter (per-locus counters) */
-    int32_t  rmDup;            /* -R  (0)    order-dependent; ITX_ENOTSUP on the device for now */
+    int32_t  rmDup;            /* -R  (0)    first read of a chr:start:end:strand key wins, in file order   generic.c:907-919 */
     int32_t  addChr;           /* -C  (0)    GL* skipped, MT->chrM, chr prefix           generic.c:781-791 */
     int32_t  discardWrongEnd;  /* -D  (0)                                                generic.c:862 */
     uint32_t iSize;            /* -I  (500)                                              generic.c:839 */
@@ -124,6 +124,7 @@ const uint32_t *itx_elem_counts_by_row(itx_index *ix, int unique);
 #define ITX_T_HAS_XA   8u
 #define ITX_T_DIFFSUB  16u
 #define ITX_T_COUNTED  32u
+#define ITX_T_DUP      64u   /* -R: dropped as a duplicate (generic.c:907-919) */
 typedef struct itx_trace { uint32_t start, end; int32_t tid; int32_t sel_row; uint32_t flags; } itx_trace;
 int itx_trace_enable(itx_index *ix, uint64_t cap);
 uint64_t itx_trace_fetch(itx_index *ix, itx_trace *out, uint64_t cap);

@@ -45,6 +45,7 @@ struct itx_cuda {
     uint8_t *d_comp; uint64_t d_comp_cap; itx_bgzf_block *d_blk; uint64_t d_blk_cap;   /* compressed file image + block table (device inflate) */
     uint16_t *d_tabs; uint64_t d_tabs_threads;   /* symbol arrays of k_inflate's long codes */
     uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists: ITX_INF_STREAMS groups in flight */
+    itx_k128 *d_dup_keys; unsigned long long *d_dup_ords, *d_dup_mins; uint64_t dup_cap, dup_ord_base;   /* -R: key table, state persists across the files of a run */
     int used_el, used_cpg, host_el, host_cpg;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
@@ -83,7 +84,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
@@ -118,6 +119,11 @@ extern "C" void itx_index_reset_counts(itx_index *ix) {
     cudaSetDevice(ix->cu->device);
     zero_counters(ix, err);
     ix->cu->used_el = ix->cu->used_cpg = 0;
+    if (ix->cu->d_dup_keys) {        /* forget the reads of the previous run */
+        cudaMemset(ix->cu->d_dup_keys, 0xff, ix->cu->dup_cap * sizeof(itx_k128)); cudaMemset(ix->cu->d_dup_ords, 0xff, ix->cu->dup_cap * 8);
+        cudaMemset(ix->cu->d_dup_mins, 0xff, 16); cudaMemset(ix->cu->d_dup_mins + 2, 0, 8);
+    }
+    ix->cu->dup_ord_base = 0;
     memset(ix->cnt, 0, sizeof ix->cnt);
     for (int32_t i = 0; i < ix->subs.n; i++) { ix->sub[i].read_count = ix->sub[i].read_count_unique = 0; ix->sub[i].cpg_count = 0; ix->sub[i].cpg_score = 0; }
     for (int32_t i = 0; i < ix->fams.n; i++) { ix->fam[i].read_count = ix->fam[i].read_count_unique = 0; ix->fam[i].cpg_count = 0; ix->fam[i].cpg_score = 0; }
@@ -286,8 +292,31 @@ static itx_dev_opts dev_opts(const itx_scan_opts *o) {
     d.filter = o->filter; d.discardWrongEnd = o->discardWrongEnd; d.treat = o->treat; d.diffSubfam = o->diffSubfam;
     return d;
 }
-static int check_opts(const itx_scan_opts *o, char *err) {
-    if (o->rmDup) { snprintf(err, ITX_ERRLEN, "-R (remove duplicates) is order dependent and not run on the device in this build"); return ITX_ENOTSUP; }
+static int check_opts(const itx_scan_opts *o, char *err) { (void)o; (void)err; return ITX_OK; }
+
+/* -R: room for `extra` more keys in the table (load kept below 0.7); a full table moves into one twice the size */
+static int ensure_dup_table(itx_cuda *cu, uint64_t extra, char *err) {
+    unsigned long long have = 0;
+    if (cu->d_dup_mins) { CK(cudaStreamSynchronize(cu->stream)); CK(cudaMemcpy(&have, cu->d_dup_mins + 2, 8, cudaMemcpyDeviceToHost)); }
+    else {
+        CK(cudaMalloc((void **)&cu->d_dup_mins, 24));
+        CK(cudaMemset(cu->d_dup_mins, 0xff, 16)); CK(cudaMemset(cu->d_dup_mins + 2, 0, 8));
+    }
+    if (cu->d_dup_keys && (have + extra) * 10 <= cu->dup_cap * 7) return ITX_OK;
+    uint64_t cap = 1ull << 20; while (cap * 7 < (have + extra) * 10 * 2) cap <<= 1;
+    itx_k128 *nk = NULL; unsigned long long *no = NULL;
+    if (cudaMalloc((void **)&nk, cap * sizeof(itx_k128)) != cudaSuccess || cudaMalloc((void **)&no, cap * 8) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(nk); snprintf(err, ITX_ERRLEN, "cannot allocate the -R key table (%llu entries)", (unsigned long long)cap); return ITX_ENOMEM;
+    }
+    CK(cudaMemsetAsync(nk, 0xff, cap * sizeof(itx_k128), cu->stream)); CK(cudaMemsetAsync(no, 0xff, cap * 8, cu->stream));
+    if (cu->d_dup_keys) {
+        CK(cudaMemsetAsync(cu->d_dup_mins + 2, 0, 8, cu->stream));
+        itx_dedup_args A; memset(&A, 0, sizeof A); A.keys = nk; A.ords = no; A.mask = cap - 1; A.mins = cu->d_dup_mins; A.status = cu->D.status;
+        k_dedup_rehash<<<cu->sm_count * 8, 256, 0, cu->stream>>>(cu->d_dup_keys, cu->d_dup_ords, cu->dup_cap, A);
+        CK(cudaStreamSynchronize(cu->stream));
+        cudaFree(cu->d_dup_keys); cudaFree(cu->d_dup_ords);
+    }
+    cu->d_dup_keys = nk; cu->d_dup_ords = no; cu->dup_cap = cap;
     return ITX_OK;
 }
 
@@ -297,6 +326,7 @@ typedef struct {
     itx_index *ix; const itx_bam_header *h; const uint8_t *b; uint64_t len; itx_dev_opts o;
     uint64_t k_first, k_end, k_next; int ev_n; int windows;
     int n_launch;
+    int rmdup;
 } scan_ctx;
 
 static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err) {
@@ -304,6 +334,7 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     memset(sc, 0, sizeof *sc);
     sc->ix = ix; sc->h = h; sc->b = d_bam; sc->len = len; sc->o = dev_opts(o);
     if (o->filter) cu->used_el = 1;
+    sc->rmdup = o->rmDup != 0;
     cu->want_sel = 0;
     int rc = ensure_work(ix, window, err); if (rc) return rc;
     sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
@@ -340,6 +371,16 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
         k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
         k_fixup<<<1, 32, 0, cu->stream>>>(A);
+        if (sc->rmdup) {
+            int rcd = ensure_dup_table(cu, (uint64_t)n * cu->C / 37 + 64, err); if (rcd) return rcd;
+            itx_dedup_args R; R.b = sc->b; R.k0 = sc->k_next; R.nchunks = n; R.C = cu->C; R.S = cu->S; R.tuples = cu->d_tuples; R.nrec = cu->d_nrec;
+            R.tid = sc->h->d_tid; R.n_ref = sc->h->n_ref; R.ord_base = cu->dup_ord_base;
+            R.keys = cu->d_dup_keys; R.ords = cu->d_dup_ords; R.mask = cu->dup_cap - 1; R.mins = cu->d_dup_mins; R.status = cu->D.status;
+            const unsigned gb = (n + 7) / 8 < (unsigned)cu->sm_count * 8u ? (n + 7) / 8 : (unsigned)cu->sm_count * 8u;
+            k_dedup<false><<<gb, 256, 0, cu->stream>>>(R);
+            k_dedup<true><<<gb, 256, 0, cu->stream>>>(R);
+            sc->n_launch += 2;
+        }
         if (timed) cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream);
         sc->n_launch += 3;
         itx_overlap_args B;
@@ -385,6 +426,8 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
     P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1];
     P->d2h_bytes = sizeof hc + sizeof st;
+    if (sc->rmdup) cu->dup_ord_base += (sc->k_end + 1) * (uint64_t)cu->S;           /* the next file's reads come after this file's */
+    if (st[4]) { snprintf(err, ITX_ERRLEN, "the -R key table overflowed"); return ITX_ENOMEM; }
     if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA bulk copy never completed (device-side time-out in k_decode_span)"); return ITX_ENODEV; }
     if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
     /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */

@@ -350,7 +350,7 @@ int itx_host_parse_bam_header(struct itx_index *ix, const uint8_t *bam, uint64_t
         memcpy(&h->lens[i], bam + p, 4); p += 4;
         /* the chromosome name the reference would look up (generic.c:781-791) */
         const char *nm = h->names[i]; char buf[512];
-        itx_tidinfo *t = &h->tid[i]; t->flags = 0; t->chrom = -1; t->cend = 0;
+        itx_tidinfo *t = &h->tid[i]; t->flags = 0; t->chrom = -1; t->cend = 0; t->csid = -1;
         if (addChr) {
             if (strncmp(nm, "GL", 2) == 0) { t->flags |= ITX_TID_GLSKIP; continue; }
             else if (strcasecmp(nm, "MT") == 0) { snprintf(buf, sizeof buf, "chrM"); nm = buf; }
@@ -361,6 +361,7 @@ int itx_host_parse_bam_header(struct itx_index *ix, const uint8_t *bam, uint64_t
         if (cend == 1) { t->flags |= ITX_TID_UNKNOWN; continue; }
         t->cend = cend;
         t->chrom = itx_strtab_find(&ix->chroms, nm);
+        t->csid = itx_strtab_find(&ix->chromsize, nm);
     }
     h->hdr_len = p;
     return ITX_OK;

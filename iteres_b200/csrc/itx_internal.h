@@ -74,6 +74,7 @@ typedef struct {
     uint32_t cend;                       /* chromSize - 1 */
     int32_t  chrom;                      /* index into the rmsk chromosome table or -1 */
     uint32_t flags;
+    int32_t  csid;                       /* index of the (renamed) chromosome in the chrom-size table: the identity -R keys on, stable across files */
 } itx_tidinfo;
 #define ITX_TID_UNKNOWN 1u               /* not in the chrom size file: warn once, discard (generic.c:796-801) */
 #define ITX_TID_GLSKIP  2u               /* -C and the name starts with GL (generic.c:783) */
@@ -88,6 +89,7 @@ struct itx_bam_header {
 
 /* decode tuple: 16 bytes per BAM record, file order inside a chunk */
 typedef struct { uint32_t start, end, info, rec_off; } itx_tuple;
+#define ITX_F_DUP     (1u << 23)         /* -R: an earlier read has the same chr:start:end:strand key (set by k_dedup) */
 #define ITX_F_FRAG    (1u << 24)
 #define ITX_F_UNIQ    (1u << 25)
 #define ITX_F_MINUS   (1u << 26)
@@ -96,8 +98,8 @@ typedef struct { uint32_t start, end, info, rec_off; } itx_tuple;
 #define ITX_F_MAPPED  (1u << 29)
 #define ITX_F_USED    (1u << 30)
 #define ITX_F_UNKNOWN (1u << 31)
-#define ITX_CHROM_MASK 0x00ffffffu
-#define ITX_CHROM_NONE 0x00ffffffu
+#define ITX_CHROM_MASK 0x007fffffu
+#define ITX_CHROM_NONE 0x007fffffu
 
 #define ITX_OFF_END  0xfffffffffffffffeULL   /* the record chain ended here (truncated / corrupt record) */
 #define ITX_OFF_NONE 0xffffffffffffffffULL   /* speculation found no plausible record start */

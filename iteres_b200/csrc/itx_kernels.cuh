@@ -273,6 +273,93 @@ __global__ void k_fixup(const itx_decode_args A) {
     if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; }
 }
 
+/* ------------------------------------------------------------------ -R: duplicate removal */
+/* An open-addressing table of 128-bit keys (claimed with one 128-bit compare-and-swap) beside an array with the
+ * smallest file-order ordinal seen for each key.  Per window, k_dedup<false> enters every unique fragment, then
+ * k_dedup<true> sets ITX_F_DUP on the fragments that are not their key's first: windows are processed in file
+ * order and a later window can only bring larger ordinals, so a window's verdicts are final when it is marked. */
+struct __align__(16) itx_k128 { unsigned long long lo, hi; };
+__device__ __forceinline__ itx_k128 itx_cas128(itx_k128 *p, itx_k128 cmp, itx_k128 val) {
+    itx_k128 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi) : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(p) : "memory");
+    return old;
+}
+#define ITX_DUP_EMPTY 0xffffffffffffffffull
+struct itx_dedup_args {
+    const uint8_t *b; unsigned long long k0; uint32_t nchunks, C, S;
+    itx_tuple *tuples; const uint32_t *nrec; const itx_tidinfo *tid; int32_t n_ref;
+    unsigned long long ord_base;                     /* ordinal of slot 0 of chunk 0 of this file */
+    itx_k128 *keys; unsigned long long *ords; unsigned long long mask;      /* capacity - 1 (a power of two) */
+    unsigned long long *mins;                        /* [0] smallest ordinal of a unique fragment, [1] of any other fragment, [2] keys in the table */
+    uint32_t *status;                                /* [4] set when the table is full */
+};
+__device__ __forceinline__ bool itx_dup_enter(const itx_dedup_args &A, unsigned long long lo, unsigned long long hi, unsigned long long ord) {
+    unsigned long long h = itx_dup_hash(lo, hi) & A.mask;
+    const itx_k128 key{lo, hi}, empty{ITX_DUP_EMPTY, ITX_DUP_EMPTY};
+    for (unsigned long long probes = 0; probes <= A.mask; probes++, h = (h + 1) & A.mask) {
+        const itx_k128 old = itx_cas128(A.keys + h, empty, key);
+        const bool fresh = old.lo == ITX_DUP_EMPTY && old.hi == ITX_DUP_EMPTY;
+        if (fresh) atomicAdd(A.mins + 2, 1ull);
+        if (fresh || (old.lo == lo && old.hi == hi)) { atomicMin(A.ords + h, ord); return true; }
+    }
+    return false;
+}
+__device__ __forceinline__ unsigned long long itx_dup_first(const itx_dedup_args &A, unsigned long long lo, unsigned long long hi) {
+    unsigned long long h = itx_dup_hash(lo, hi) & A.mask;
+    for (unsigned long long probes = 0; probes <= A.mask; probes++, h = (h + 1) & A.mask) {
+        const itx_k128 k = A.keys[h];
+        if (k.lo == lo && k.hi == hi) return A.ords[h];
+        if (k.lo == ITX_DUP_EMPTY && k.hi == ITX_DUP_EMPTY) break;
+    }
+    return ITX_DUP_EMPTY;
+}
+template <bool MARK>
+__global__ void __launch_bounds__(256) k_dedup(const itx_dedup_args A) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const itx_src_global G{A.b};
+    unsigned long long mu = ITX_DUP_EMPTY, mn = ITX_DUP_EMPTY;
+    if (MARK) { mu = A.mins[0]; mn = A.mins[1]; }
+    for (uint32_t i = w0; i < A.nchunks; i += nw) {
+        const uint32_t nr = A.nrec[i];
+        const unsigned long long lo_b = (A.k0 + i) * (unsigned long long)A.C;
+        itx_tuple *tp = A.tuples + (size_t)i * A.S;
+        for (uint32_t j = lane; j < nr; j += 32) {
+            const itx_tuple T = tp[j];
+            if (!(T.info & ITX_F_FRAG)) continue;
+            const unsigned long long ord = A.ord_base + (A.k0 + i) * (unsigned long long)A.S + j;
+            if (T.info & ITX_F_UNIQ) {
+                const int32_t t = (int32_t)G.u32(lo_b + T.rec_off + 4);
+                const int32_t csid = (t >= 0 && t < A.n_ref) ? A.tid[t].csid : -1;
+                unsigned long long klo, khi; itx_dup_key(csid, (T.info & ITX_F_MINUS) != 0, T.start, T.end, &klo, &khi);
+                if (!MARK) { if (!itx_dup_enter(A, klo, khi, ord)) atomicOr(&A.status[4], 1u); if (ord < mu) mu = ord; }
+                else if (itx_dup_first(A, klo, khi) != ord) tp[j].info = T.info | ITX_F_DUP;
+            } else {
+                if (!MARK) { if (ord < mn) mn = ord; }
+                else if (!itx_dup_nonunique_kept(ord, mu, mn)) tp[j].info = T.info | ITX_F_DUP;
+            }
+        }
+    }
+    if (!MARK) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, mu, d), c = __shfl_xor_sync(0xffffffffu, mn, d);
+            if (a < mu) mu = a;
+            if (c < mn) mn = c;
+        }
+        if (lane == 0) { if (mu != ITX_DUP_EMPTY) atomicMin(A.mins, mu); if (mn != ITX_DUP_EMPTY) atomicMin(A.mins + 1, mn); }
+    }
+}
+/* move every key of a full table into a larger one */
+__global__ void k_dedup_rehash(const itx_k128 *old_keys, const unsigned long long *old_ords, unsigned long long old_cap, itx_dedup_args A) {
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < old_cap; s += (unsigned long long)gridDim.x * blockDim.x) {
+        const itx_k128 k = old_keys[s];
+        if (k.lo == ITX_DUP_EMPTY && k.hi == ITX_DUP_EMPTY) continue;
+        if (!itx_dup_enter(A, k.lo, k.hi, old_ords[s])) atomicOr(&A.status[4], 1u);
+    }
+}
+
 /* ------------------------------------------------------------------ overlap + accumulate */
 struct itx_overlap_args {
     itx_dev_index D;
@@ -320,7 +407,7 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
             itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
             if (valid) { const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(tp + j)); T.start = v.x; T.end = v.y; T.info = v.z; T.rec_off = v.w; }
             const uint32_t info = T.info;
-            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ, live = frag && !(info & ITX_F_DUP);
             const uint32_t m_valid = __ballot_sync(0xffffffffu, valid), m_slot2 = __ballot_sync(0xffffffffu, slot2);
             const uint32_t m_map = __ballot_sync(0xffffffffu, info & ITX_F_MAPPED), m_used = __ballot_sync(0xffffffffu, info & ITX_F_USED);
             const uint32_t m_frag = __ballot_sync(0xffffffffu, frag), m_uniq = __ballot_sync(0xffffffffu, uniq);
@@ -328,12 +415,12 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
             c[2] += __popc(m_map & ~m_slot2);   c[3] += __popc(m_map & m_slot2);
             c[4] += __popc(m_used & ~m_slot2);  c[5] += __popc(m_used & m_slot2);
             c[6] += __popc(m_frag);
-            const uint32_t mu = __popc(m_frag & m_uniq);
-            c[7] += mu; c[11] += mu;
+            c[7] += __popc(m_frag & m_uniq);
+            c[11] += __popc(__ballot_sync(0xffffffffu, live) & m_uniq);       /* unique reads that survive -R (generic.c:921-922) */
             if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
             long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
             const uint32_t chrom = info & ITX_CHROM_MASK;
-            if (frag && chrom != ITX_CHROM_NONE) {
+            if (live && chrom != ITX_CHROM_NONE) {
                 int32_t nhit; float tcov;
                 sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov, &e);
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
@@ -378,11 +465,12 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
                 const unsigned long long r = A.rec_base[i] + j;
                 if (r < A.trace_cap) {
                     itx_trace t;
-                    t.start = frag ? T.start : 0; t.end = frag ? T.end : 0;
+                    t.start = live ? T.start : 0; t.end = live ? T.end : 0;
                     t.tid = (int32_t)G.u32(lo + T.rec_off + 4);
                     t.sel_row = sel >= 0 ? (int32_t)e.row : -1;
-                    t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
-                              ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
+                    t.flags = (live ? ITX_T_FRAGMENT : 0u) | (live && uniq ? ITX_T_UNIQ : 0u) | ((live && (info & ITX_F_MINUS)) ? ITX_T_MINUS : 0u) |
+                              ((live && (info & ITX_F_HASXA)) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u) |
+                              ((info & ITX_F_DUP) ? ITX_T_DUP : 0u);
                     A.trace[r] = t;
                 }
             }

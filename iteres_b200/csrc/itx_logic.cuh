@@ -540,4 +540,25 @@ ITX_HD bool itx_cov_range(uint32_t start, uint32_t qlen, int32_t es, int32_t ee,
     *j0 = a; *j1 = a + (n < room ? n : room);
     return true;
 }
+/* ------------------------------------------------------------------ -R duplicate removal (generic.c:907-919) */
+/* The reference keeps a hash of "chr:start:end:strand" strings and drops a read whose key is already there.  The
+ * key is only re-formatted for unique reads (MAPQ >= -Q); any other read re-uses the key left by the last unique
+ * read before it -- which is in the hash by then -- so it is dropped, except while no unique read has been seen
+ * yet: then the key is still the empty string, which the first such read adds.  In terms of the file-order
+ * ordinal of a fragment:
+ *   unique read      kept <=> no unique read with the same key has a smaller ordinal
+ *   any other read   kept <=> it is the first non-unique read of the run and precedes every unique read
+ * State persists across the files of a run.  The key is (chromosome identity, strand, start, end). */
+ITX_HD void itx_dup_key(int32_t csid, bool minus, uint32_t start, uint32_t end, unsigned long long *lo, unsigned long long *hi) {
+    *lo = (unsigned long long)start | ((unsigned long long)end << 32);
+    *hi = (((unsigned long long)(uint32_t)(csid + 1)) << 1) | (minus ? 1ull : 0ull);
+}
+ITX_HD bool itx_dup_nonunique_kept(unsigned long long ord, unsigned long long min_unique, unsigned long long min_nonunique) {
+    return ord == min_nonunique && ord < min_unique;
+}
+ITX_HD unsigned long long itx_dup_hash(unsigned long long lo, unsigned long long hi) {
+    unsigned long long x = lo ^ (hi * 0x9E3779B97F4A7C15ull);
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+    return x;
+}
 #endif

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <vector>
 
 struct emu_index {
@@ -20,6 +21,9 @@ struct emu_index {
     std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
     std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
     std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch, tile_checked, tile_mismatch, tile_entry_miss;
+    /* -R: smallest ordinal per key, of the unique and of the other fragments; persists across the files of a run */
+    std::map<std::pair<unsigned long long, unsigned long long>, unsigned long long> dup_first;
+    unsigned long long dup_min_unique = ~0ull, dup_min_other = ~0ull, dup_ord_base = 0;
 };
 
 extern "C" {
@@ -32,6 +36,7 @@ void emu_reset(emu_index *E) {
     std::fill(E->grp_cpg_score.begin(), E->grp_cpg_score.end(), 0.0); std::fill(E->bp_cpg.begin(), E->bp_cpg.end(), 0.0);
     std::fill(E->el_cpg_score.begin(), E->el_cpg_score.end(), 0.0);
     std::fill(E->status.begin(), E->status.end(), 0u);
+    E->dup_first.clear(); E->dup_min_unique = E->dup_min_other = ~0ull; E->dup_ord_base = 0;
     E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0;
 }
 
@@ -189,6 +194,31 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             if (!same) E->tile_mismatch++;
         }
     }
+    /* -R: the two passes of k_dedup (enter every unique fragment's key, then flag what is not its key's first) */
+    if (so->rmDup) {
+        const uint64_t S = C / 36 + 1;
+        auto key_of = [&](uint64_t i, const itx_tuple &T) {
+            const int32_t t = (int32_t)itx_src_global{bam}.u32((k0 + i) * C + T.rec_off + 4);
+            unsigned long long lo, hi; itx_dup_key((t >= 0 && t < h.n_ref) ? h.tid[t].csid : -1, (T.info & ITX_F_MINUS) != 0, T.start, T.end, &lo, &hi);
+            return std::make_pair(lo, hi);
+        };
+        for (uint64_t i = 0; i < n; i++) for (size_t j = 0; j < tup[i].size(); j++) {
+            const itx_tuple &T = tup[i][j]; if (!(T.info & ITX_F_FRAG)) continue;
+            const unsigned long long ord = E->dup_ord_base + (k0 + i) * S + j;
+            if (T.info & ITX_F_UNIQ) {
+                auto it = E->dup_first.insert(std::make_pair(key_of(i, T), ord)).first;
+                if (ord < it->second) it->second = ord;
+                if (ord < E->dup_min_unique) E->dup_min_unique = ord;
+            } else if (ord < E->dup_min_other) E->dup_min_other = ord;
+        }
+        for (uint64_t i = 0; i < n; i++) for (size_t j = 0; j < tup[i].size(); j++) {
+            itx_tuple &T = tup[i][j]; if (!(T.info & ITX_F_FRAG)) continue;
+            const unsigned long long ord = E->dup_ord_base + (k0 + i) * S + j;
+            const bool keep = (T.info & ITX_F_UNIQ) ? E->dup_first[key_of(i, T)] == ord : itx_dup_nonunique_kept(ord, E->dup_min_unique, E->dup_min_other);
+            if (!keep) T.info |= ITX_F_DUP;
+        }
+        E->dup_ord_base += (k1 + 1) * S;
+    }
     /* K2 + K3 */
     unsigned long long *c = D.cnt;
     const bool stat = o.filter == 0 && D.stat_mode;
@@ -197,15 +227,15 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
         const uint64_t lo = (k0 + i) * C;
         for (size_t j = 0; j < tup[i].size(); j++) {
             const itx_tuple T = tup[i][j]; const uint32_t info = T.info;
-            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+            const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ, live = frag && !(info & ITX_F_DUP);
             c[slot2 ? 1 : 0]++;
             if (info & ITX_F_MAPPED) c[slot2 ? 3 : 2]++;
             if (info & ITX_F_USED) c[slot2 ? 5 : 4]++;
-            if (frag) { c[6]++; if (uniq) { c[7]++; c[11]++; } }
+            if (frag) { c[6]++; if (uniq) { c[7]++; if (live) c[11]++; } }
             if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1;
             long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
             const uint32_t chrom = info & ITX_CHROM_MASK;
-            if (frag && chrom != ITX_CHROM_NONE) {
+            if (live && chrom != ITX_CHROM_NONE) {
                 int32_t nh; float tcov;
                 sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nh, &tcov, &e);
                 if (sel >= 0 && tcov < o.minCoverage) sel = -1;
@@ -234,10 +264,11 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             }
             if (want_trace) {
                 itx_trace t;
-                t.start = frag ? T.start : 0; t.end = frag ? T.end : 0; t.tid = (int32_t)G.u32(lo + T.rec_off + 4);
+                t.start = live ? T.start : 0; t.end = live ? T.end : 0; t.tid = (int32_t)G.u32(lo + T.rec_off + 4);
                 t.sel_row = sel >= 0 ? (int32_t)e.row : -1;
-                t.flags = (frag ? ITX_T_FRAGMENT : 0u) | (frag && uniq ? ITX_T_UNIQ : 0u) | ((info & ITX_F_MINUS) ? ITX_T_MINUS : 0u) |
-                          ((info & ITX_F_HASXA) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u);
+                t.flags = (live ? ITX_T_FRAGMENT : 0u) | (live && uniq ? ITX_T_UNIQ : 0u) | ((live && (info & ITX_F_MINUS)) ? ITX_T_MINUS : 0u) |
+                          ((live && (info & ITX_F_HASXA)) ? ITX_T_HAS_XA : 0u) | (diffsub ? ITX_T_DIFFSUB : 0u) | (counted ? ITX_T_COUNTED : 0u) |
+                          ((info & ITX_F_DUP) ? ITX_T_DUP : 0u);
                 E->trace.push_back(t);
             }
         }

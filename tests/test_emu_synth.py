@@ -24,6 +24,8 @@ CASES = [
     ("pe100_treat", 1, 60000, 2, 20000, dict(treat=1)),
     ("pe100_D_I300", 1, 60000, 2, 20000, dict(discardWrongEnd=1, iSize=300)),
     ("se50_Q30_c05", 0, 20000, 0, 20000, dict(mapQ=30, minCoverage=0.5)),
+    ("se50_chrM_R", 2, 3000, 0, 60000, dict(rmDup=1)),
+    ("pe100_R", 1, 60000, 2, 20000, dict(rmDup=1)),
 ]
 
 
@@ -66,7 +68,7 @@ def test_emu_matches_oracle(case, worlds):
     assert len(tr_e) == len(tr_o) == nrec
     for f in ("start", "end", "tid", "sel_row"):
         assert np.array_equal(tr_e[f], tr_o[f]), f
-    mask = ~np.uint32(8)                    # HAS_XA is reported by the oracle even where it is not evaluated
+    mask = ~np.uint32(8 | 64)               # HAS_XA is reported by the oracle even where it is not evaluated; DUP is the product's own flag
     assert np.array_equal(tr_e["flags"] & mask, tr_o["flags"] & mask)
     if kw.get("diffSubfam", 1) and mode == 1:
         assert cnt_o[12] > 0

@@ -74,6 +74,8 @@ SYN = [
     ("pe100_D_I300", 1, 60000, 2, 50000, dict(discardWrongEnd=1, iSize=300)),
     ("se50_Q30_c05", 0, 20000, 0, 50000, dict(mapQ=30, minCoverage=0.5)),
     ("se50_addChr", 1, 60000, 0, 50000, dict(addChr=1)),
+    ("se50_chrM_R", 2, 3000, 0, 200000, dict(rmDup=1)),
+    ("pe100_R", 1, 60000, 2, 100000, dict(rmDup=1)),
 ]
 
 
@@ -126,7 +128,7 @@ def test_cuda_path_matches_oracle(case, chunk, worlds):
     assert len(tr_g) == len(tr_o) == nrec
     for f in ("start", "end", "tid", "sel_row"):
         assert np.array_equal(tr_g[f], tr_o[f]), f
-    mask = ~np.uint32(8)                                      # HAS_XA: the oracle reports it even where it is not evaluated
+    mask = ~np.uint32(8 | 64)                                 # HAS_XA: the oracle reports it even where it is not evaluated; DUP is the product's own flag
     assert np.array_equal(tr_g["flags"] & mask, tr_o["flags"] & mask)
     assert_same_tables(ix, ora)
     ora.close()
@@ -229,6 +231,26 @@ def test_bytes_after_the_eof_block_and_cut_files_end_the_stream_silently(worlds,
             assert got == first
         assert 0 < got[0] < want[0]
         ix.close()
+
+
+def test_rmdup_keys_persist_across_the_files_of_a_run(worlds, tmp_path):
+    """-R: the key hash lives for the whole run (generic.c:700-745), so every read of a second copy of the file is a
+    duplicate; a reset starts a new run.  Small windows: the key table is grown and re-hashed on the way."""
+    s, (cs, rs, rm), _ = worlds(2, 3000)
+    bam = str(tmp_path / "reads.bam")
+    s.write_bam(bam, 0, 150000, level=1, threads=4)
+    ora = O.OracleIndex(cs, rs, rm)
+    o1 = ora.scan_file(bam, O.default_opts(rmDup=1))
+    o2 = ora.scan_file(bam, O.default_opts(rmDup=1))
+    assert o2[11] == o1[11] and o2[6] == 2 * o1[6] and o1[11] < o1[7]
+    ix = capi.Index(cs, rs, rm)
+    ix.tune(chunk_bytes=4096, window_bytes=1 << 20)
+    assert ix.scan_alignments(bam + "," + bam, capi.default_opts(rmDup=1)) == o2
+    assert_same_tables(ix, ora)
+    ix.reset()
+    assert ix.scan_alignments(bam, capi.default_opts(rmDup=1)) == o1
+    ora.close()
+    ix.close()
 
 
 def test_damaged_bgzf_block_is_reported(worlds, tmp_path, monkeypatch):

@@ -83,6 +83,9 @@ typedef struct {
 
 static const char *CHR1_NAMES[1] = {"chr1"};
 static const uint32_t CHR1_LENS[1] = {249250621};
+/* shape 2: two small chromosomes, so that a few tens of thousands of reads pile up on the same coordinates (-R tests) */
+static const char *SMALL_NAMES[2] = {"chr1", "chrM"};
+static const uint32_t SMALL_LENS[2] = {400000, 16571};
 
 static int cmp_row(const void *a, const void *b) {
     const srow_t *x = a, *y = b;
@@ -95,6 +98,7 @@ void *synth_new(int shape, uint64_t n_rmsk, int n_subfam, int n_fam, int n_cla, 
     synth_t *S = calloc(1, sizeof(*S));
     S->shape = shape; S->seed = seed;
     if (shape == 0) { S->n_chrom = 1; S->names = CHR1_NAMES; S->lens = CHR1_LENS; }
+    else if (shape == 2) { S->n_chrom = 2; S->names = SMALL_NAMES; S->lens = SMALL_LENS; }
     else { S->n_chrom = 25; S->names = HG19_NAMES; S->lens = HG19_LENS; }
     S->cum[0] = 0;
     for (int i = 0; i < S->n_chrom; i++) S->cum[i + 1] = S->cum[i] + S->lens[i];
