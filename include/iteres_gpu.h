@@ -42,6 +42,10 @@ typedef struct itx_scan_opts {
     float    minCoverage;      /* -c  (1e-4f)                                            generic.c:961 */
     int32_t  treat;            /* -T  (0)                                                generic.c:815 */
     int32_t  diffSubfam;       /* !-x (1 for stat, 0 for filter)                         generic.c:972 */
+    /* order-dependent side outputs, written by a host pass over the device's per-record verdicts in file order */
+    int32_t  readNames;        /* filter -r: keep the read names of every counted read per locus   generic.c:662-666 */
+    const char *outbed;        /* -B: bed line per fragment that survives -R (NULL: none)           generic.c:925-931 */
+    const char *outbed_unique; /* -V: the same for unique reads only                                generic.c:932-936 */
 } itx_scan_opts;
 void itx_scan_opts_default(itx_scan_opts *o);
 

@@ -21,7 +21,8 @@ class ScanOpts(C.Structure):
     """itx_scan_opts == the scalar arguments of samFiles2nodupRepbedFileNew (generic.c:700)."""
     _fields_ = [("mapQ", C.c_uint32), ("filter", C.c_int32), ("rmDup", C.c_int32), ("addChr", C.c_int32),
                 ("discardWrongEnd", C.c_int32), ("iSize", C.c_uint32), ("extension", C.c_uint32),
-                ("minCoverage", C.c_float), ("treat", C.c_int32), ("diffSubfam", C.c_int32)]
+                ("minCoverage", C.c_float), ("treat", C.c_int32), ("diffSubfam", C.c_int32),
+                ("readNames", C.c_int32), ("outbed", C.c_char_p), ("outbed_unique", C.c_char_p)]
 
 
 class Trace(C.Structure):
@@ -41,7 +42,7 @@ class Profile(C.Structure):
 
 
 def default_opts(**kw):
-    o = ScanOpts(10, 0, 0, 0, 0, 500, 150, 1e-4, 0, 1)
+    o = ScanOpts(10, 0, 0, 0, 0, 500, 150, 1e-4, 0, 1, 0, None, None)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

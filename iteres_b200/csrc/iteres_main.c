@@ -134,7 +134,8 @@ static int main_stat(int argc, char **argv) {
     static const int NIDX[4] = {9, 8, 6, 0}, NIDX2[3] = {10, 7, 0};
     if (norm > 3 || norm2 > 2) die("Wrong normalization method specified");
     if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
-    if (bed || bedu) die("-B / -V bed output is not supported by this build");
+    if (bed) o.outbed = fmt_alloc("%s.iteres.bed", prefix);
+    if (bedu) o.outbed_unique = fmt_alloc("%s.iteres.unique.bed", prefix);
     use_device();
     char err[ITX_ERRLEN]; uint64_t cnt[13];
     fprintf(stderr, "* Parsing the rmsk file\n");
@@ -192,7 +193,7 @@ static int main_filter(int argc, char **argv) {
     if (norm > 3) die("Wrong normalization method specified");
     if (!prefix) prefix = stem(bam);
     if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
-    if (readlist) die("-r (read name lists) is not supported by this build");
+    o.readNames = readlist;
     use_device();
     char err[ITX_ERRLEN]; uint64_t cnt[13];
     fprintf(stderr, "* Start to parse the rmsk file\n");

@@ -2,6 +2,7 @@
  * stream, host stream through pinned staging, BGZF file through host inflate threads), result
  * download, NCCL allreduce of the counter block.  Built for sm_100a only. */
 #include "itx_kernels.cuh"
+#include "itx_ordered.h"
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <pthread.h>
@@ -46,6 +47,10 @@ struct itx_cuda {
     uint16_t *d_tabs; uint64_t d_tabs_threads;   /* symbol arrays of k_inflate's long codes */
     uint32_t *d_mpl; uint16_t *d_md; uint32_t *d_mn; uint64_t d_m_slots;   /* match lists: ITX_INF_STREAMS groups in flight */
     itx_k128 *d_dup_keys; unsigned long long *d_dup_ords, *d_dup_mins; uint64_t dup_cap, dup_ord_base;   /* -R: key table, state persists across the files of a run */
+    /* order-dependent side outputs (-B / -V bed files, filter -r read names): host pass per launch group */
+    FILE *bed_f, *bed_uf; int bed_owner;             /* opened by the outermost entry point of the run */
+    uint64_t ord_cap;                                /* trace entries one launch group may need (0: not in ordered mode) */
+    itx_trace *h_ord_trace; uint64_t h_ord_trace_cap; uint8_t *h_ord_buf; uint64_t h_ord_buf_cap;
     int used_el, used_cpg, host_el, host_cpg;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
@@ -260,7 +265,8 @@ static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
     itx_cuda *cu = ix->cu;
     uint32_t C = ix->tune_chunk, S = C / 36 + 1;
     uint64_t need = window_bytes / C + 2;
-    bool want_trace = ix->trace_cap != 0;
+    bool want_trace = ix->trace_cap != 0 || cu->ord_cap != 0;
+    const uint64_t trace_need = ix->trace_cap > cu->ord_cap ? ix->trace_cap : cu->ord_cap;
     if (cu->d_tuples && cu->C == C && cu->cap_chunks >= need && (!want_trace || cu->d_rec_base) && (!cu->want_sel || cu->d_sel)) goto trace;
     cudaFree(cu->d_tuples); cudaFree(cu->d_entry); cudaFree(cu->d_exit); cudaFree(cu->d_nrec); cudaFree(cu->d_rec_base); cudaFree(cu->d_sel);
     cu->d_tuples = NULL; cu->d_entry = cu->d_exit = cu->d_rec_base = NULL; cu->d_nrec = NULL; cu->d_sel = NULL;
@@ -276,10 +282,10 @@ static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
     if (want_trace) CK(cudaMalloc((void **)&cu->d_rec_base, need * 8));
     if (cu->want_sel) CK(cudaMalloc((void **)&cu->d_sel, need * S * sizeof(long long)));
 trace:
-    if (want_trace && (!cu->d_trace || cu->trace_cap < ix->trace_cap)) {
+    if (want_trace && (!cu->d_trace || cu->trace_cap < trace_need)) {
         cudaFree(cu->d_trace); cu->d_trace = NULL;
-        CK(cudaMalloc((void **)&cu->d_trace, ix->trace_cap * sizeof(itx_trace)));
-        cu->trace_cap = ix->trace_cap;
+        CK(cudaMalloc((void **)&cu->d_trace, trace_need * sizeof(itx_trace)));
+        cu->trace_cap = trace_need;
     }
     return ITX_OK;
 }
@@ -322,12 +328,74 @@ static int ensure_dup_table(itx_cuda *cu, uint64_t extra, char *err) {
 
 /* Scan context: the stream lives in one device buffer `b` of `len` bytes (plus slack); the window
  * loop processes chunks [k_next, k_hi) once `avail` bytes are on the device. */
-typedef struct {
+typedef struct scan_ctx_s {
     itx_index *ix; const itx_bam_header *h; const uint8_t *b; uint64_t len; itx_dev_opts o;
     uint64_t k_first, k_end, k_next; int ev_n; int windows;
     int n_launch;
     int rmdup;
+    /* ordered mode */
+    int ordered, names; uint32_t mapQ; uint64_t p_cur; char **tname;
 } scan_ctx;
+
+/* ------------------------------------------------------------------ ordered mode: -B / -V bed lines, filter -r read names */
+/* These outputs follow the reads in file order and need their names and aux strings, so they are produced on the
+ * host -- but from the device's verdicts: every launch group leaves one trace entry per record (fragment, flags,
+ * selected rmsk row); the host pulls the entries and the group's bytes of the stream, walks the records once and
+ * prints.  Nothing about a read is decided on the host. */
+static int ordered_open_files(itx_cuda *cu, const itx_scan_opts *o, char *err) {
+    if (cu->bed_owner) return ITX_OK;                  /* an outer entry point of the same run holds them */
+    if (cu->bed_f) { fclose(cu->bed_f); cu->bed_f = NULL; }             /* left behind by a scan that failed */
+    if (cu->bed_uf) { fclose(cu->bed_uf); cu->bed_uf = NULL; }
+    if (o->outbed && !cu->bed_f && !(cu->bed_f = fopen(o->outbed, "w"))) { snprintf(err, ITX_ERRLEN, "Can't open %s to write: %s", o->outbed, strerror(errno)); return ITX_EIO; }
+    if (o->outbed_unique && !cu->bed_uf && !(cu->bed_uf = fopen(o->outbed_unique, "w"))) { snprintf(err, ITX_ERRLEN, "Can't open %s to write: %s", o->outbed_unique, strerror(errno)); return ITX_EIO; }
+    return ITX_OK;
+}
+static void ordered_close_files(itx_cuda *cu) {
+    if (cu->bed_f) { fclose(cu->bed_f); cu->bed_f = NULL; }
+    if (cu->bed_uf) { fclose(cu->bed_uf); cu->bed_uf = NULL; }
+    cu->bed_owner = 0;
+}
+static int ordered_begin(scan_ctx *sc, const itx_scan_opts *o, char *err) {
+    itx_index *ix = sc->ix; itx_cuda *cu = ix->cu; const itx_bam_header *h = sc->h;
+    int rc = ordered_open_files(cu, o, err); if (rc) return rc;
+    sc->p_cur = h->hdr_len;
+    sc->tname = itx_ordered_tnames(h);
+    if (sc->names) itx_ordered_names_init(ix);
+    return ITX_OK;
+}
+static void ordered_end(scan_ctx *sc) {
+    if (!sc->ordered) return;
+    if (sc->tname) { for (int32_t t = 0; t < sc->h->n_ref; t++) free(sc->tname[t]); free(sc->tname); sc->tname = NULL; }
+    itx_cuda *cu = sc->ix->cu;
+    if (!cu->bed_owner) ordered_close_files(cu);
+    if (cu->bed_f) fflush(cu->bed_f);
+    if (cu->bed_uf) fflush(cu->bed_uf);
+}
+/* the launch group just enqueued: wait for it, fetch its trace entries and its bytes, walk its records */
+static int ordered_drain(scan_ctx *sc, uint64_t avail, char *err) {
+    itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
+    unsigned long long n_w = 0, carry = 0;
+    CK(cudaStreamSynchronize(cu->stream));
+    CK(cudaMemcpy(&n_w, cu->d_running, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&carry, cu->d_carry, 8, cudaMemcpyDeviceToHost));
+    if (n_w == 0) return ITX_OK;
+    if (n_w > cu->trace_cap) { snprintf(err, ITX_ERRLEN, "internal: %llu records in a launch group, room for %llu trace entries", n_w, (unsigned long long)cu->trace_cap); return ITX_ENOMEM; }
+    uint64_t p_end = carry;                                            /* the next group's first record, or past the end of a cut stream */
+    const uint64_t lim = avail < sc->len ? avail : sc->len;
+    if (p_end > lim) p_end = lim;
+    if (p_end < sc->p_cur) p_end = sc->p_cur;
+    if (cu->h_ord_trace_cap < n_w) { free(cu->h_ord_trace); cu->h_ord_trace = (itx_trace *)malloc(n_w * sizeof(itx_trace)); cu->h_ord_trace_cap = n_w; }
+    const uint64_t nbytes = p_end - sc->p_cur;
+    if (cu->h_ord_buf_cap < nbytes + ITX_SLACK) { free(cu->h_ord_buf); cu->h_ord_buf = (uint8_t *)malloc(nbytes + ITX_SLACK); cu->h_ord_buf_cap = nbytes + ITX_SLACK; }
+    if (!cu->h_ord_trace || !cu->h_ord_buf) { snprintf(err, ITX_ERRLEN, "out of host memory in the ordered pass"); return ITX_ENOMEM; }
+    CK(cudaMemcpy(cu->h_ord_trace, cu->d_trace, n_w * sizeof(itx_trace), cudaMemcpyDeviceToHost));
+    if (nbytes) CK(cudaMemcpy(cu->h_ord_buf, sc->b + sc->p_cur, nbytes, cudaMemcpyDeviceToHost));
+    memset(cu->h_ord_buf + nbytes, 0, ITX_SLACK);
+    itx_ordered_sink K; K.bed = cu->bed_f; K.bed_u = cu->bed_uf; K.names = sc->names; K.mapQ = sc->mapQ; K.tname = sc->tname; K.n_ref = sc->h->n_ref; K.ix = ix;
+    const uint64_t p = itx_ordered_walk(K, cu->h_ord_buf, nbytes, cu->h_ord_trace, n_w);
+    sc->p_cur += p;
+    return ITX_OK;
+}
 
 static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err) {
     itx_cuda *cu = ix->cu;
@@ -336,7 +404,13 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     if (o->filter) cu->used_el = 1;
     sc->rmdup = o->rmDup != 0;
     cu->want_sel = 0;
+    sc->ordered = (o->outbed || o->outbed_unique || o->readNames) ? 1 : 0; sc->names = o->readNames != 0; sc->mapQ = o->mapQ;
+    if (sc->ordered) {
+        if (window > (256ull << 20)) window = 256ull << 20;         /* the host pass buffers one launch group */
+        cu->ord_cap = window / 37 + (uint64_t)ix->tune_chunk / 37 * 4 + 4096;    /* a record is at least 37 bytes long */
+    } else cu->ord_cap = 0;
     int rc = ensure_work(ix, window, err); if (rc) return rc;
+    if (sc->ordered && (rc = ordered_begin(sc, o, err))) return rc;
     sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
     sc->k_next = sc->k_first;
     unsigned long long carry = h->hdr_len;
@@ -348,7 +422,7 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
         cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_STAGE) != 0 || cu->C > (1u << 20)) ? 1 : 0;
         if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
     }
-    if (ix->trace_cap) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
+    if (ix->trace_cap || sc->ordered) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
     CK(cudaStreamSynchronize(cu->stream));   /* the 8-byte sources live on this stack frame */
     return ITX_OK;
 }
@@ -386,7 +460,8 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         itx_overlap_args B;
         B.D = cu->D; B.b = sc->b; B.k0 = sc->k_next; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
         B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1;
-        if (ix->trace_cap) {
+        if (ix->trace_cap || sc->ordered) {
+            if (sc->ordered) cudaMemsetAsync(cu->d_running, 0, 8, cu->stream);          /* the group's records are traced from slot 0 */
             k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
             B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
         }
@@ -404,11 +479,13 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         sc->k_next += n;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { snprintf(err, ITX_ERRLEN, "kernel launch failed: %s", cudaGetErrorString(e)); return ITX_ENODEV; }
+        if (sc->ordered) { int rco = ordered_drain(sc, avail, err); if (rco) return rco; }
     }
     return ITX_OK;
 }
 static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
+    ordered_end(sc);
     unsigned long long hc[16]; uint32_t st[8];
     CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
@@ -838,6 +915,9 @@ extern "C" int itx_scan_alignments(itx_index *ix, const char *bam_list, const it
     err[0] = 0;
     char *list = strdup(bam_list), *save = NULL; int rc = ITX_OK, nfile = 0;
     itx_profile total; memset(&total, 0, sizeof total);
+    /* the bed files span the whole list (generic.c:716-727): opened here, appended to by every file's scan */
+    if ((o->outbed || o->outbed_unique) && (rc = ordered_open_files(ix->cu, o, err))) { free(list); return rc; }
+    ix->cu->bed_owner = (o->outbed || o->outbed_unique) ? 1 : 0;
     for (char *tok = strtok_r(list, ",", &save); tok && rc == ITX_OK; tok = strtok_r(NULL, ",", &save)) {
         if (++nfile > 100) break;                       /* the reference's row[100] */
         rc = scan_one_file(ix, tok, o, cnt, err);
@@ -848,6 +928,7 @@ extern "C" int itx_scan_alignments(itx_index *ix, const char *bam_list, const it
     }
     total.n_records = ix->cnt[0] + ix->cnt[1]; total.n_fragments = ix->cnt[6];
     ix->prof = total;
+    ordered_close_files(ix->cu);
     free(list);
     return rc;
 }

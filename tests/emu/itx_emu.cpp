@@ -8,6 +8,7 @@
  */
 #include "../../iteres_b200/csrc/itx_logic.cuh"
 #include "../../iteres_b200/csrc/itx_inflate.cuh"
+#include "../../iteres_b200/csrc/itx_ordered.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -219,6 +220,10 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
         }
         E->dup_ord_base += (k1 + 1) * S;
     }
+    /* ordered side outputs: the same host pass as the product, fed by this run's trace */
+    const bool ordered = so->outbed || so->outbed_unique || so->readNames;
+    const size_t trace0 = E->trace.size();
+    if (ordered) want_trace = 1;
     /* K2 + K3 */
     unsigned long long *c = D.cnt;
     const bool stat = o.filter == 0 && D.stat_mode;
@@ -272,6 +277,16 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
                 E->trace.push_back(t);
             }
         }
+    }
+    if (ordered) {
+        itx_ordered_sink K; K.bed = so->outbed ? fopen(so->outbed, "w") : NULL; K.bed_u = so->outbed_unique ? fopen(so->outbed_unique, "w") : NULL;
+        K.names = so->readNames != 0; K.mapQ = so->mapQ; K.tname = itx_ordered_tnames(&h); K.n_ref = h.n_ref; K.ix = &ix;
+        if (K.names) itx_ordered_names_init(&ix);
+        itx_ordered_walk(K, bam + h.hdr_len, len - h.hdr_len, E->trace.data() + trace0, E->trace.size() - trace0);
+        if (K.bed) fclose(K.bed);
+        if (K.bed_u) fclose(K.bed_u);
+        for (int32_t i = 0; i < h.n_ref; i++) free(K.tname[i]);
+        free(K.tname);
     }
     for (int k = 0; k < 13; k++) { ix.cnt[k] = c[k]; if (cnt) cnt[k] = c[k]; }
     for (int32_t i = 0; i < h.n_ref; i++) free(h.names[i]);

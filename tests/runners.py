@@ -92,11 +92,17 @@ def run_oracle(inp, cmd, args, outdir, prefix="out"):
         ix.close()
 
 
-def itx_opts(o):
+def itx_opts(o, prefix=None):
     from iteres_b200 import capi
+    kw = {}
+    if o["cmd"] == "stat" and prefix:                  # -B / -V: bed files next to the tables (stat.c:101-111)
+        if o["B"]: kw["outbed"] = (prefix + ".iteres.bed").encode()
+        if o["V"]: kw["outbed_unique"] = (prefix + ".iteres.unique.bed").encode()
+    if o["cmd"] == "filter" and o["r"]:
+        kw["readNames"] = 1
     return capi.default_opts(mapQ=o["Q"], filter=1 if o["cmd"] == "filter" else 0, rmDup=o["R"], addChr=o["C"],
                              discardWrongEnd=o["D"], iSize=o["I"], extension=o["E"], minCoverage=o["cov"], treat=o["T"],
-                             diffSubfam=o["diff"])
+                             diffSubfam=o["diff"], **kw)
 
 
 def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
@@ -108,7 +114,7 @@ def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
     ix = make_index(f("chrom.sizes"), f("rep.sizes"), f("rmsk.txt"), o["field"], o["name"])
     try:
         if cmd == "stat":
-            scan(ix, f("reads.bam"), itx_opts(o))
+            scan(ix, f("reads.bam"), itx_opts(o, p))
             ix.write_stat(p, o["nindex"], o["nindex2"])
             ix.write_report(p + ".iteres.report", o["Q"], "ALL")
         elif cmd == "filter":
@@ -127,15 +133,15 @@ def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
 
 
 def needs_host_order(cmd, args):
-    """variants the host emulation of the device logic does not produce: filter -r read-name lists (the product makes
-    them in a host pass over the device's per-record verdicts; see test_cli / test_gpu_parity)"""
-    return cmd == "filter" and "-r" in args
+    """every variant is produced now: -R on the device, bed lines and filter -r name lists by the host pass over the
+    device's per-record verdicts"""
+    return False
 
 
 SKIP = {"cmdline.txt", "stderr.txt"}
 
 
-def expected_files(vdir, skip_bed=True):
+def expected_files(vdir, skip_bed=False):
     out = []
     for fn in sorted(os.listdir(vdir)):
         if fn in SKIP or (skip_bed and fn.endswith(".bed")):

@@ -17,7 +17,7 @@ def test_oracle_matches_reference_output(kat, variant, tmp_path):
     cmd, args = kats.KATS[kat]["variants"][variant]
     vdir = os.path.join(GOLD, kat, variant)
     runners.run_oracle(os.path.join(GOLD, kat, "input"), cmd, args, str(tmp_path))
-    files = runners.expected_files(vdir)
+    files = runners.expected_files(vdir, skip_bed=True)      # the oracle restates the counting path; bed lines are the product's host pass
     assert files, "golden directory is empty"
     for fn in files:
         got = os.path.join(str(tmp_path), fn)
