@@ -104,6 +104,10 @@ int itx_write_report(const char *path, const uint64_t cnt[13], uint32_t mapQ, co
 int itx_write_filter(itx_index *ix, const char *path, int readlist, int threshold, uint64_t reads_num);
 int itx_write_cpg_stat(itx_index *ix, const char *subfam_stat, const char *wig, const char *fam_stat, const char *class_stat);
 int itx_write_cpg_filter(itx_index *ix, const char *path, double score_threshold);
+/* wiggle -> bigWig = bigWigFileCreate(wig, rep_size_file, 256, 1024, 0, 1, bigWig) (stat.c:157-158, cpgstat.c:75;
+ * cuskent/bwgCreate.c:1088-1112): byte-identical files for the fixedStep wiggles itx_write_stat / itx_write_cpg_stat
+ * make.  Host only.  An empty wiggle is an error ("... is empty of data"), as in the reference. */
+int itx_wig_to_bigwig(const char *wig, const char *chrom_sizes, const char *bigwig, char err[ITX_ERRLEN]);
 
 /* ---- plain accessors (tests, bindings).  which: 0 subfamily, 1 family, 2 class; i in output-row
  *      order (the reference's hash iteration order, cuskent/hash.c:511-551). ---- */

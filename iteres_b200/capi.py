@@ -56,7 +56,7 @@ itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_
 itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
 itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
 itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
-itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch""".split()
+itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch itx_wig_to_bigwig""".split()
 
 _lib = None
 
@@ -134,6 +134,7 @@ def lib():
         L.itx_host_alloc_pinned.argtypes = [u64]
         L.itx_host_free_pinned.argtypes = [vp]
         L.itx_dev_flush_l2.argtypes = [vp]
+        L.itx_wig_to_bigwig.argtypes = [cp, cp, cp, cp]
         L.itx_stream_fetch.restype = u64
         L.itx_stream_fetch.argtypes = [vp, vp, u64]
         _lib = L

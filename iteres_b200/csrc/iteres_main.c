@@ -7,8 +7,7 @@
  * The scan itself runs on the CUDA device through the C ABI of include/iteres_gpu.h; failures keep
  * the reference's convention: message on stderr, exit status 255 (cuskent/errabort.c:166-181).
  *
- * Not produced by this build: the .bigWig files (Kent bwgCreate, outside the hot path; the .wig files
- * they are made from are written and kept with -w), SAM text input (-S), -R, -B and -V.
+ * Not accepted by this build: SAM text input (-S); convert to BAM first.
  */
 #define _GNU_SOURCE
 #include <getopt.h>
@@ -150,7 +149,9 @@ static int main_stat(int argc, char **argv) {
     char *wig = fmt_alloc("%s.iteres.wig", prefix), *wigu = fmt_alloc("%s.iteres.unique.wig", prefix);
     char *f_sub = fmt_alloc("%s.iteres.subfamily.stat", prefix), *f_fam = fmt_alloc("%s.iteres.family.stat", prefix), *f_cla = fmt_alloc("%s.iteres.class.stat", prefix);
     if (itx_write_stat(ix, f_sub, wig, f_fam, f_cla, wigu, cnt[NIDX[norm]], cnt[NIDX2[norm2]]) != ITX_OK) die("Can't write the stat files for prefix %s", prefix);
-    fprintf(stderr, "* bigWig files are not generated by this build%s\n", keep_wig ? "" : " (use -w to keep the wiggle files)");
+    fprintf(stderr, "* Generating bigWig files\n");
+    if (itx_wig_to_bigwig(wig, rep_sizes, fmt_alloc("%s.iteres.bigWig", prefix), err) != ITX_OK) die("%s", err);
+    if (itx_wig_to_bigwig(wigu, rep_sizes, fmt_alloc("%s.iteres.unique.bigWig", prefix), err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Preparing report file\n");
     char *rep = fmt_alloc("%s.iteres.report", prefix);
     if (itx_write_report(rep, cnt, o.mapQ, "ALL") != ITX_OK) die("Can't open %s to write", rep);
@@ -242,7 +243,8 @@ static int main_cpgstat(int argc, char **argv) {
     char *wig = fmt_alloc("%s.CpGstat.wig", prefix);
     if (itx_write_cpg_stat(ix, fmt_alloc("%s.CpG.subfamily.stat", prefix), wig, fmt_alloc("%s.CpG.family.stat", prefix), fmt_alloc("%s.CpG.class.stat", prefix)) != ITX_OK)
         die("Can't write the CpG stat files for prefix %s", prefix);
-    fprintf(stderr, "* bigWig files are not generated by this build%s\n", keep_wig ? "" : " (use -w to keep the wiggle file)");
+    fprintf(stderr, "* Generating bigWig files\n");
+    if (itx_wig_to_bigwig(wig, rep_sizes, fmt_alloc("%s.CpGstat.bigWig", prefix), err) != ITX_OK) die("%s", err);
     if (!keep_wig) unlink(wig);
     itx_index_free(ix);
     done_in(t0);

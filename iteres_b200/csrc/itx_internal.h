@@ -149,6 +149,9 @@ void itx_host_index_free(struct itx_index *ix);
 int itx_host_parse_bam_header(struct itx_index *ix, const uint8_t *bam, uint64_t len, int addChr,
                               struct itx_bam_header *h, char err[ITX_ERRLEN]);
 
+/* bigWig (itx_bigwig.c) */
+int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, const char *name), void *ctx, const char *out_path, char err[ITX_ERRLEN]);
+
 /* BGZF (itx_bgzf.c) */
 typedef struct { uint64_t coff; uint32_t csize, isize; uint64_t uoff; } itx_bgzf_block;
 int itx_bgzf_scan(const uint8_t *file, uint64_t len, itx_bgzf_block **blocks, uint64_t *n_blocks, uint64_t *total_u,

@@ -55,9 +55,6 @@ def main():
                 f.write("iteres %s %s\nexit=%d\n" % (cmd, " ".join(args), p.returncode))
             with open(os.path.join(vd, "stderr.txt"), "w") as f:
                 f.write(p.stderr)
-            for fn in os.listdir(vd):          # bigWig is binary and produced by code outside the hot path
-                if fn.endswith(".bigWig"):
-                    os.remove(os.path.join(vd, fn))
             print(name, vname, "exit", p.returncode, sorted(os.listdir(vd)))
 
 
