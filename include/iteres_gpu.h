@@ -44,6 +44,7 @@ typedef struct itx_scan_opts {
     int32_t  diffSubfam;       /* !-x (1 for stat, 0 for filter)                         generic.c:972 */
     /* order-dependent side outputs, written by a host pass over the device's per-record verdicts in file order */
     int32_t  readNames;        /* filter -r: keep the read names of every counted read per locus   generic.c:662-666 */
+    int32_t  isSam;            /* -S: the files are SAM text (plain or gzip), converted on the host    sam.c:39-65, bam_import.c:237-456 */
     const char *outbed;        /* -B: bed line per fragment that survives -R (NULL: none)           generic.c:925-931 */
     const char *outbed_unique; /* -V: the same for unique reads only                                generic.c:932-936 */
 } itx_scan_opts;
@@ -108,6 +109,10 @@ int itx_write_cpg_filter(itx_index *ix, const char *path, double score_threshold
  * cuskent/bwgCreate.c:1088-1112): byte-identical files for the fixedStep wiggles itx_write_stat / itx_write_cpg_stat
  * make.  Host only.  An empty wiggle is an error ("... is empty of data"), as in the reference. */
 int itx_wig_to_bigwig(const char *wig, const char *chrom_sizes, const char *bigwig, char err[ITX_ERRLEN]);
+/* the SAM text front end on its own (what a scan with isSam does first): SAM (plain or gzip) -> the uncompressed BAM
+ * stream samtools 0.1.18 would have built record by record (bam_import.c:237-456).  *bam is released with itx_free. */
+int itx_sam_to_bam(const char *sam, uint8_t **bam, uint64_t *len, char err[ITX_ERRLEN]);
+void itx_free(void *p);
 
 /* ---- plain accessors (tests, bindings).  which: 0 subfamily, 1 family, 2 class; i in output-row
  *      order (the reference's hash iteration order, cuskent/hash.c:511-551). ---- */

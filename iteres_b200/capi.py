@@ -22,7 +22,7 @@ class ScanOpts(C.Structure):
     _fields_ = [("mapQ", C.c_uint32), ("filter", C.c_int32), ("rmDup", C.c_int32), ("addChr", C.c_int32),
                 ("discardWrongEnd", C.c_int32), ("iSize", C.c_uint32), ("extension", C.c_uint32),
                 ("minCoverage", C.c_float), ("treat", C.c_int32), ("diffSubfam", C.c_int32),
-                ("readNames", C.c_int32), ("outbed", C.c_char_p), ("outbed_unique", C.c_char_p)]
+                ("readNames", C.c_int32), ("isSam", C.c_int32), ("outbed", C.c_char_p), ("outbed_unique", C.c_char_p)]
 
 
 class Trace(C.Structure):
@@ -42,7 +42,7 @@ class Profile(C.Structure):
 
 
 def default_opts(**kw):
-    o = ScanOpts(10, 0, 0, 0, 0, 500, 150, 1e-4, 0, 1, 0, None, None)
+    o = ScanOpts(10, 0, 0, 0, 0, 500, 150, 1e-4, 0, 1, 0, 0, None, None)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -56,7 +56,7 @@ itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_
 itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
 itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
 itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
-itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch itx_wig_to_bigwig""".split()
+itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch itx_wig_to_bigwig itx_sam_to_bam itx_free""".split()
 
 _lib = None
 
@@ -135,6 +135,9 @@ def lib():
         L.itx_host_free_pinned.argtypes = [vp]
         L.itx_dev_flush_l2.argtypes = [vp]
         L.itx_wig_to_bigwig.argtypes = [cp, cp, cp, cp]
+        L.itx_sam_to_bam.argtypes = [cp, C.POINTER(C.c_void_p), C.POINTER(u64), cp]
+        L.itx_free.argtypes = [C.c_void_p]
+        L.itx_free.restype = None
         L.itx_stream_fetch.restype = u64
         L.itx_stream_fetch.argtypes = [vp, vp, u64]
         _lib = L

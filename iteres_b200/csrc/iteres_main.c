@@ -7,7 +7,7 @@
  * The scan itself runs on the CUDA device through the C ABI of include/iteres_gpu.h; failures keep
  * the reference's convention: message on stderr, exit status 255 (cuskent/errabort.c:166-181).
  *
- * Not accepted by this build: SAM text input (-S); convert to BAM first.
+ * Every option of the reference drivers is accepted.
  */
 #define _GNU_SOURCE
 #include <getopt.h>
@@ -132,7 +132,7 @@ static int main_stat(int argc, char **argv) {
     if (!prefix) { char *first = strdup(bams); char *comma = strchr(first, ','); if (comma) *comma = 0; prefix = stem(first); free(first); }
     static const int NIDX[4] = {9, 8, 6, 0}, NIDX2[3] = {10, 7, 0};
     if (norm > 3 || norm2 > 2) die("Wrong normalization method specified");
-    if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
+    o.isSam = sam;
     if (bed) o.outbed = fmt_alloc("%s.iteres.bed", prefix);
     if (bedu) o.outbed_unique = fmt_alloc("%s.iteres.unique.bed", prefix);
     use_device();
@@ -193,7 +193,7 @@ static int main_filter(int argc, char **argv) {
     static const int NIDX[4] = {7, 8, 6, 4};
     if (norm > 3) die("Wrong normalization method specified");
     if (!prefix) prefix = stem(bam);
-    if (sam) die("SAM text input (-S) is not supported by this build: convert to BAM");
+    o.isSam = sam;
     o.readNames = readlist;
     use_device();
     char err[ITX_ERRLEN]; uint64_t cnt[13];

@@ -886,6 +886,14 @@ static int scan_bgzf_host_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t f
 }
 
 static int scan_one_file(itx_index *ix, const char *path, const itx_scan_opts *o, uint64_t cnt[13], char *err) {
+    if (o->isSam) {
+        /* -S: the text is turned into the BAM records samtools would have built, then takes the same path */
+        uint8_t *bam = NULL; uint64_t len = 0;
+        int rcs = itx_sam_to_bam_stream(path, &bam, &len, err);
+        if (rcs == ITX_OK) rcs = itx_scan_bam_host(ix, bam, len, o, cnt, err);
+        free(bam);
+        return rcs;
+    }
     int fd = open(path, O_RDONLY);
     if (fd < 0) { snprintf(err, ITX_ERRLEN, "Error\n[bam file %s: %s]", path, strerror(errno)); return ITX_EIO; }
     struct stat st;

@@ -149,6 +149,9 @@ void itx_host_index_free(struct itx_index *ix);
 int itx_host_parse_bam_header(struct itx_index *ix, const uint8_t *bam, uint64_t len, int addChr,
                               struct itx_bam_header *h, char err[ITX_ERRLEN]);
 
+/* SAM text -> uncompressed BAM stream (itx_sam.c); the caller frees *out_bam */
+int itx_sam_to_bam_stream(const char *path, uint8_t **out_bam, uint64_t *out_len, char err[ITX_ERRLEN]);
+
 /* bigWig (itx_bigwig.c) */
 int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, const char *name), void *ctx, const char *out_path, char err[ITX_ERRLEN]);
 

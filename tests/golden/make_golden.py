@@ -47,7 +47,7 @@ def main():
         for vname, (cmd, args) in k["variants"].items():
             vd = os.path.join(d, vname)
             os.makedirs(vd)
-            data = "cpg.bedGraph" if cmd.startswith("cpg") else "reads.bam"
+            data = "cpg.bedGraph" if cmd.startswith("cpg") else ("reads.sam" if "-S" in args else "reads.bam")
             argv = [REF, cmd] + args + ["-o", "out"] + [os.path.join("..", "input", x) for x in
                                                          ("chrom.sizes", "rep.sizes", "rmsk.txt", data)]
             p = subprocess.run(argv, cwd=vd, capture_output=True, text=True)

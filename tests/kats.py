@@ -34,7 +34,8 @@ KATS = {}
 KATS["kat1_basic"] = dict(
     chrom=CHR1M, rep=REP1, rmsk=ANNOT1, refs=CHR1M,
     reads=[se("r1", 0, 1050, 37), se("r2", 16, 5100, 5), se("r3", 0, 5880, 30), se("r4", 4, 0, 0), se("r5", 0, 989, 30)],
-    variants={"default": ("stat", ["-w"]), "E0": ("stat", ["-w", "-E", "0"]), "Q31": ("stat", ["-w", "-Q", "31"]),
+    variants={"default": ("stat", ["-w"]), "S": ("stat", ["-w", "-S"]), "filter_S": ("filter", ["-S", "-r"]),
+              "E0": ("stat", ["-w", "-E", "0"]), "Q31": ("stat", ["-w", "-Q", "31"]),
               "N2U1": ("stat", ["-w", "-N", "2", "-U", "1"]), "N3U2": ("stat", ["-w", "-N", "3", "-U", "2"]),
               "N1": ("stat", ["-w", "-N", "1"]),
               "filter": ("filter", []), "filter_r": ("filter", ["-r"]), "filter_nAluY": ("filter", ["-n", "AluY", "-r"]),
@@ -64,7 +65,7 @@ KATS["kat4_paired_xa"] = dict(
            pe("p2", 83, 5200, 5, 5000, -236), pe("p2", 163, 5000, 5, 5200, 236),
            pe("p3", 73, 1100, 30, 1100, 0), pe("p4", 99, 1050, 30, 1714, 700),
            se("r6", 0, 1050, 37, aux=XA1), se("r7", 0, 1050, 37, aux=XA2), se("r8", 16, 1250, 37, cigar="10M5D26M")],
-    variants={"default": ("stat", ["-w"]), "B": ("stat", ["-w", "-B", "-V"]), "T": ("stat", ["-w", "-T"]),
+    variants={"default": ("stat", ["-w"]), "S_B": ("stat", ["-w", "-S", "-B", "-V"]), "B": ("stat", ["-w", "-B", "-V"]), "T": ("stat", ["-w", "-T"]),
               "x": ("stat", ["-w", "-x"]), "D": ("stat", ["-w", "-D"]), "E0": ("stat", ["-w", "-E", "0"]),
               "I150": ("stat", ["-w", "-I", "150"]), "R": ("stat", ["-w", "-R"]),
               "filter_r": ("filter", ["-r"]), "filter_t2": ("filter", ["-t", "2"]), "filter_T": ("filter", ["-T", "-r"])})

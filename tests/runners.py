@@ -10,7 +10,7 @@ import oracle_lib as O
 def parse(cmd, args):
     """-> dict of options in the reference's own vocabulary."""
     o = dict(cmd=cmd, Q=10, cov=1e-4, diff=1, N=0, U=0, R=0, T=0, D=0, C=0, E=150, I=500, t=1, r=0, field=0, name="ALL",
-             thr=0.0, B=0, V=0)
+             thr=0.0, B=0, V=0, S=1 if "-S" in args else 0)
     if cmd == "stat":
         opts, _ = getopt.getopt(args, "SQ:c:xN:U:RTDwBVCo:E:I:h?")
         for k, v in opts:
@@ -100,6 +100,8 @@ def itx_opts(o, prefix=None):
         if o["V"]: kw["outbed_unique"] = (prefix + ".iteres.unique.bed").encode()
     if o["cmd"] == "filter" and o["r"]:
         kw["readNames"] = 1
+    if o["S"]:
+        kw["isSam"] = 1
     return capi.default_opts(mapQ=o["Q"], filter=1 if o["cmd"] == "filter" else 0, rmDup=o["R"], addChr=o["C"],
                              discardWrongEnd=o["D"], iSize=o["I"], extension=o["E"], minCoverage=o["cov"], treat=o["T"],
                              diffSubfam=o["diff"], **kw)
@@ -112,15 +114,16 @@ def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
     f = lambda n: os.path.join(inp, n)
     p = os.path.join(outdir, prefix)
     ix = make_index(f("chrom.sizes"), f("rep.sizes"), f("rmsk.txt"), o["field"], o["name"])
+    reads = f("reads.sam") if o["S"] else f("reads.bam")
     try:
         if cmd == "stat":
-            scan(ix, f("reads.bam"), itx_opts(o, p))
+            scan(ix, reads, itx_opts(o, p))
             ix.write_stat(p, o["nindex"], o["nindex2"])
             wig_to_bigwig(p + ".iteres.wig", f("rep.sizes"), p + ".iteres.bigWig")
             wig_to_bigwig(p + ".iteres.unique.wig", f("rep.sizes"), p + ".iteres.unique.bigWig")
             ix.write_report(p + ".iteres.report", o["Q"], "ALL")
         elif cmd == "filter":
-            scan(ix, f("reads.bam"), itx_opts(o))
+            scan(ix, reads, itx_opts(o))
             ix.write_filter("%s_%s.iteres.loci" % (p, o["name"]), o["r"], o["t"], o["nindex"])
             ix.write_report("%s_%s.iteres.reportloci" % (p, o["name"]), o["Q"], o["name"])
         elif cmd == "cpgstat":
@@ -133,6 +136,21 @@ def run_itx(make_index, scan, inp, cmd, args, outdir, prefix="out"):
         return list(ix.cnt)
     finally:
         ix.close()
+
+
+def sam_to_bam_bytes(path):
+    """what -S scans: the product's SAM text front end (host C in libiteres_gpu.so; needs no device)"""
+    import ctypes as C
+    from iteres_b200 import capi
+    L = capi.lib()
+    err = C.create_string_buffer(capi.ERRLEN)
+    p, n = C.c_void_p(), C.c_uint64()
+    rc = L.itx_sam_to_bam(path.encode(), C.byref(p), C.byref(n), err)
+    if rc:
+        raise capi.ItxError(rc, err.value.decode())
+    data = C.string_at(p, n.value)
+    L.itx_free(p)
+    return data
 
 
 def wig_to_bigwig(wig, sizes, out):

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(capi.ScanOpts) == 64 and C.sizeof(capi.Trace) == 20      # 10 scalars, readNames, pad, two path pointers
+    assert C.sizeof(capi.ScanOpts) == 64 and C.sizeof(capi.Trace) == 20      # 10 scalars, readNames, isSam, two path pointers
     o = capi.ScanOpts()
     capi.lib().itx_scan_opts_default(C.byref(o))
     assert (o.mapQ, o.iSize, o.extension, o.diffSubfam, o.filter, o.readNames, o.outbed, o.outbed_unique) == (10, 500, 150, 1, 0, 0, None, None)

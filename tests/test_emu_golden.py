@@ -23,7 +23,7 @@ def test_device_logic_matches_reference_output(kat, variant, chunk, tmp_path):
     cmd, args = kats.KATS[kat]["variants"][variant]
     vdir = os.path.join(GOLD, kat, variant)
     mk = lambda *a: emu_lib.EmuIndex(*a, chunk=chunk)
-    scan = lambda ix, bam, opts: ix.scan_stream(oracle_lib.inflate_bam(bam), opts)
+    scan = lambda ix, bam, opts: ix.scan_stream(runners.sam_to_bam_bytes(bam) if bam.endswith(".sam") else oracle_lib.inflate_bam(bam), opts)
     runners.run_itx(mk, scan, os.path.join(GOLD, kat, "input"), cmd, args, str(tmp_path))
     files = runners.expected_files(vdir)
     assert files

@@ -403,3 +403,26 @@ def test_window_smaller_than_a_record_is_refused(tmp_path):
         ix.scan_stream(raw, capi.default_opts())
     assert e.value.code == -6 and "longer than the staged window" in str(e.value)
     ix.close()
+
+
+@pytest.mark.parametrize("kat,variant", [("kat1_basic", "default"), ("kat1_basic", "S"), ("kat4_paired_xa", "B"), ("kat4_paired_xa", "S_B"),
+                                         ("kat4_paired_xa", "R"), ("kat1_basic", "filter_r"), ("kat5_cpg", "cpgstat"), ("kat5_cpg", "cpgfilter")])
+def test_command_line_tool_is_a_drop_in(kat, variant, tmp_path):
+    """the `iteres` binary with the reference's own command line: same files, same bytes (stderr is not compared)"""
+    import subprocess
+    cmd, args = kats.KATS[kat]["variants"][variant]
+    inp = os.path.join(GOLD, kat, "input")
+    data = "cpg.bedGraph" if cmd.startswith("cpg") else ("reads.sam" if "-S" in args else "reads.bam")
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "iteres_b200", "csrc", "iteres")
+    p = subprocess.run([cli, cmd] + args + ["-o", "out"] + [os.path.join(inp, x) for x in ("chrom.sizes", "rep.sizes", "rmsk.txt", data)],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    vdir = os.path.join(GOLD, kat, variant)
+    want = runners.expected_files(vdir)
+    assert sorted(os.listdir(str(tmp_path))) == want
+    for fn in want:
+        a, b = os.path.join(str(tmp_path), fn), os.path.join(vdir, fn)
+        if cmd.startswith("cpg") and not fn.endswith(".bigWig"):
+            assert close_text(a, b), fn
+        else:
+            assert filecmp.cmp(a, b, shallow=False), fn
