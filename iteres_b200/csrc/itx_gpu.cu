@@ -18,6 +18,7 @@
 
 #define ITX_SLACK 64
 #define ITX_MAX_EVENTS 4096
+#define ITX_MAX_WINDOWS 65536              /* launch groups of one scan that k_scan can log (more: the tuple path takes over) */
 #define ITX_INF_STREAMS 8                  /* inflate groups in flight: copy, Huffman pass, match pass and scan of different groups overlap */
 
 struct itx_cuda {
@@ -38,6 +39,8 @@ struct itx_cuda {
     uint32_t C, S; uint64_t cap_chunks;
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
+    unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
+    int scan_ctas[2];                                         /* resident CTAs per SM of k_scan<false>, k_scan<true> */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
     int decode_ctas;                        /* resident CTAs per SM of k_decode_span */
     itx_trace *d_trace; uint64_t trace_cap;
@@ -89,7 +92,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
@@ -188,6 +191,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
+        CKN(cudaMalloc((void **)&cu->d_carry_log, ITX_MAX_WINDOWS * 8)); CKN(cudaMalloc((void **)&cu->d_fused, 8));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -333,6 +337,8 @@ typedef struct scan_ctx_s {
     uint64_t k_first, k_end, k_next; int ev_n; int windows;
     int n_launch;
     int rmdup;
+    /* fused mode: k_scan instead of the tuple path; the windows are logged so that a failed chain check can be replayed */
+    int fused; uint32_t n_win, wins_cap; struct scan_win { uint64_t k0; uint32_t n; uint64_t avail, len; } *wins;
     /* ordered mode */
     int ordered, names; uint32_t mapQ; uint64_t p_cur; char **tname;
 } scan_ctx;
@@ -423,7 +429,90 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
         if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
     }
     if (ix->trace_cap || sc->ordered) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
+    {   /* one fused kernel per launch group unless something needs the tuples (-R, the ordered outputs, traces, ITX_FUSED=0) */
+        const char *v = getenv("ITX_FUSED");
+        sc->fused = !(v && strcmp(v, "0") == 0) && cu->decode_variant == 0 && !sc->rmdup && !sc->ordered && !ix->trace_cap && !cu->want_sel;
+        if (sc->fused) { CK(cudaMemsetAsync(cu->d_fused, 0xff, 4, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 1, 0, 4, cu->stream)); }
+    }
     CK(cudaStreamSynchronize(cu->stream));   /* the 8-byte sources live on this stack frame */
+    return ITX_OK;
+}
+static itx_decode_args decode_args(const scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len) {
+    itx_cuda *cu = sc->ix->cu;
+    itx_decode_args A;
+    A.b = sc->b; A.len = len; A.avail = avail; A.k0 = k0; A.nchunks = n; A.C = cu->C; A.S = cu->S;
+    A.tid = sc->h->d_tid; A.n_ref = sc->h->n_ref; A.o = sc->o;
+    A.tuples = cu->d_tuples; A.entry = cu->d_entry; A.exit_ = cu->d_exit; A.nrec = cu->d_nrec;
+    A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status; A.work = cu->d_work;
+    return A;
+}
+static size_t hist_bytes(const itx_cuda *cu) { return 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4; }
+/* the tuple path for chunks [k0, k0 + n): k_decode_span (or k_decode) -> k_verify -> k_fixup -> [k_dedup x2] -> k_overlap */
+static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, char *err) {
+    itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
+    const itx_decode_args A = decode_args(sc, k0, n, avail, len);
+    bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
+    if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
+    if (cu->decode_variant == 0) {
+        uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)(cu->sm_count * cu->decode_ctas);
+        k_decode_span<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM, cu->stream>>>(A);
+    } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
+    k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
+    k_fixup<<<1, 32, 0, cu->stream>>>(A);
+    if (sc->rmdup) {
+        int rcd = ensure_dup_table(cu, (uint64_t)n * cu->C / 37 + 64, err); if (rcd) return rcd;
+        itx_dedup_args R; R.b = sc->b; R.k0 = k0; R.nchunks = n; R.C = cu->C; R.S = cu->S; R.tuples = cu->d_tuples; R.nrec = cu->d_nrec;
+        R.tid = sc->h->d_tid; R.n_ref = sc->h->n_ref; R.ord_base = cu->dup_ord_base;
+        R.keys = cu->d_dup_keys; R.ords = cu->d_dup_ords; R.mask = cu->dup_cap - 1; R.mins = cu->d_dup_mins; R.status = cu->D.status;
+        const unsigned gb = (n + 7) / 8 < (unsigned)cu->sm_count * 8u ? (n + 7) / 8 : (unsigned)cu->sm_count * 8u;
+        k_dedup<false><<<gb, 256, 0, cu->stream>>>(R);
+        k_dedup<true><<<gb, 256, 0, cu->stream>>>(R);
+        sc->n_launch += 2;
+    }
+    if (timed) cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream);
+    sc->n_launch += 3;
+    itx_overlap_args B;
+    B.D = cu->D; B.b = sc->b; B.k0 = k0; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
+    B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1;
+    if (ix->trace_cap || sc->ordered) {
+        if (sc->ordered) cudaMemsetAsync(cu->d_running, 0, 8, cu->stream);          /* the group's records are traced from slot 0 */
+        k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
+        B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
+    }
+    const size_t hist = hist_bytes(cu);
+    bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
+    int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
+    uint32_t need_blocks = (n * ((cu->S + ITX_PART - 1) / ITX_PART) + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
+    if (smem) {
+        if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
+        k_overlap<true><<<blocks, 256, hist, cu->stream>>>(B);
+    } else k_overlap<false><<<blocks, 256, 0, cu->stream>>>(B);
+    sc->n_launch++;
+    if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
+    return ITX_OK;
+}
+/* the fused path: ONE kernel per launch group (k_scan); sign -1 takes a group's counts back */
+static bool fused_smem_hist(const scan_ctx *sc) {
+    const itx_cuda *cu = sc->ix->cu;
+    return (sc->o.filter == 0 && cu->D.stat_mode) && ITX_DECODE_SMEM + hist_bytes(cu) + 1024 <= cu->smem_optin;
+}
+static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, int sign) {
+    itx_cuda *cu = sc->ix->cu;
+    itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len); P.D = cu->D; P.sign = sign; P.window = window;
+    P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused; P.ticket = cu->d_fused + 1;
+    const bool sh = fused_smem_hist(sc);
+    const size_t smem = ITX_DECODE_SMEM + (sh ? hist_bytes(cu) : 0);
+    if (!cu->scan_ctas[sh]) {
+        if (sh) { cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+        else { cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+        int nb = 0;
+        if (sh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<true>, ITX_DW * 32, smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<false>, ITX_DW * 32, smem);
+        cu->scan_ctas[sh] = nb > 0 ? nb : 1;
+    }
+    const uint32_t want = (n + ITX_DW - 1) / ITX_DW, most = (uint32_t)(cu->sm_count * cu->scan_ctas[sh]);
+    const uint32_t grid = want < most ? want : most;
+    if (sh) k_scan<true><<<grid, ITX_DW * 32, smem, cu->stream>>>(P); else k_scan<false><<<grid, ITX_DW * 32, smem, cu->stream>>>(P);
+    sc->n_launch++;
     return ITX_OK;
 }
 /* launch the kernels for chunks [k_next, k_hi) (k_hi <= k_end); avail = bytes valid on the device */
@@ -432,49 +521,18 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
     while (sc->k_next < k_hi) {
         uint64_t n64 = k_hi - sc->k_next; if (n64 > cu->cap_chunks - 1) n64 = cu->cap_chunks - 1;
         uint32_t n = (uint32_t)n64;
-        itx_decode_args A;
-        A.b = sc->b; A.len = sc->len; A.avail = avail; A.k0 = sc->k_next; A.nchunks = n; A.C = cu->C; A.S = cu->S;
-        A.tid = sc->h->d_tid; A.n_ref = sc->h->n_ref; A.o = sc->o;
-        A.tuples = cu->d_tuples; A.entry = cu->d_entry; A.exit_ = cu->d_exit; A.nrec = cu->d_nrec;
-        A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status; A.work = cu->d_work;
-        bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
-        if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
-        if (cu->decode_variant == 0) {
-            uint32_t db = (n + ITX_DW - 1) / ITX_DW, dmax = (uint32_t)(cu->sm_count * cu->decode_ctas);
-            k_decode_span<<<db < dmax ? db : dmax, ITX_DW * 32, ITX_DECODE_SMEM, cu->stream>>>(A);
-        } else k_decode<<<(n + 127) / 128, 128, 0, cu->stream>>>(A);
-        k_verify<<<(n + 255) / 256, 256, 0, cu->stream>>>(A);
-        k_fixup<<<1, 32, 0, cu->stream>>>(A);
-        if (sc->rmdup) {
-            int rcd = ensure_dup_table(cu, (uint64_t)n * cu->C / 37 + 64, err); if (rcd) return rcd;
-            itx_dedup_args R; R.b = sc->b; R.k0 = sc->k_next; R.nchunks = n; R.C = cu->C; R.S = cu->S; R.tuples = cu->d_tuples; R.nrec = cu->d_nrec;
-            R.tid = sc->h->d_tid; R.n_ref = sc->h->n_ref; R.ord_base = cu->dup_ord_base;
-            R.keys = cu->d_dup_keys; R.ords = cu->d_dup_ords; R.mask = cu->dup_cap - 1; R.mins = cu->d_dup_mins; R.status = cu->D.status;
-            const unsigned gb = (n + 7) / 8 < (unsigned)cu->sm_count * 8u ? (n + 7) / 8 : (unsigned)cu->sm_count * 8u;
-            k_dedup<false><<<gb, 256, 0, cu->stream>>>(R);
-            k_dedup<true><<<gb, 256, 0, cu->stream>>>(R);
-            sc->n_launch += 2;
+        if (sc->fused && sc->n_win >= ITX_MAX_WINDOWS) { snprintf(err, ITX_ERRLEN, "more than %d launch groups in one scan: raise the window with itx_tune", ITX_MAX_WINDOWS); return ITX_ENOTSUP; }
+        if (sc->fused) {
+            if (sc->n_win == sc->wins_cap) { sc->wins_cap = sc->wins_cap ? sc->wins_cap * 2 : 64; sc->wins = (scan_ctx::scan_win *)realloc(sc->wins, sc->wins_cap * sizeof(*sc->wins)); }
+            sc->wins[sc->n_win].k0 = sc->k_next; sc->wins[sc->n_win].n = n; sc->wins[sc->n_win].avail = avail; sc->wins[sc->n_win].len = sc->len;
+            bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
+            if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
+            launch_fused(sc, sc->n_win, sc->k_next, n, avail, sc->len, +1);
+            if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream); cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
+            sc->n_win++;
+        } else {
+            int rc = launch_tuple_path(sc, sc->k_next, n, avail, sc->len, err); if (rc) return rc;
         }
-        if (timed) cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream);
-        sc->n_launch += 3;
-        itx_overlap_args B;
-        B.D = cu->D; B.b = sc->b; B.k0 = sc->k_next; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
-        B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1;
-        if (ix->trace_cap || sc->ordered) {
-            if (sc->ordered) cudaMemsetAsync(cu->d_running, 0, 8, cu->stream);          /* the group's records are traced from slot 0 */
-            k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
-            B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
-        }
-        size_t hist = 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4;
-        bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
-        int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
-        uint32_t need_blocks = (n * ((cu->S + ITX_PART - 1) / ITX_PART) + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
-        if (smem) {
-            if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
-            k_overlap<true><<<blocks, 256, hist, cu->stream>>>(B);
-        } else k_overlap<false><<<blocks, 256, 0, cu->stream>>>(B);
-        sc->n_launch++;
-        if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
         sc->windows++;
         sc->k_next += n;
         cudaError_t e = cudaGetLastError();
@@ -483,9 +541,30 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
     }
     return ITX_OK;
 }
+/* a chain check failed in window `first` (a span's guessed first record was not where the previous span ended): take back
+ * what k_scan counted from that window on and count those windows again through the tuple path, which repairs guesses */
+static int fused_replay(scan_ctx *sc, uint32_t first, char *err) {
+    itx_cuda *cu = sc->ix->cu;
+    for (uint32_t w = first; w < sc->n_win; w++) launch_fused(sc, w, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, -1);
+    CK(cudaMemcpyAsync(cu->d_carry, cu->d_carry_log + first, 8, cudaMemcpyDeviceToDevice, cu->stream));
+    for (uint32_t w = first; w < sc->n_win; w++) { int rc = launch_tuple_path(sc, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, err); if (rc) return rc; }
+    return ITX_OK;
+}
 static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
     ordered_end(sc);
+    if (sc->fused) {
+        uint32_t first_bad = 0xffffffffu;
+        CK(cudaMemcpyAsync(&first_bad, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
+        CK(cudaStreamSynchronize(cu->stream));
+        if (first_bad == 0xffffffffu && sc->n_win && getenv("ITX_FUSED_TEST_REPLAY")) first_bad = 0;      /* test hook: replay everything */
+        if (first_bad != 0xffffffffu) {
+            int rc = fused_replay(sc, first_bad, err);
+            if (rc) { free(sc->wins); sc->wins = NULL; return rc; }
+            ix->prof.n_replayed_windows = sc->n_win - first_bad;
+        }
+        free(sc->wins); sc->wins = NULL;
+    }
     unsigned long long hc[16]; uint32_t st[8];
     CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
@@ -501,7 +580,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     }
     if (sc->ev_n >= 3) { float t = 0; cudaEventElapsedTime(&t, cu->ev[0], cu->ev[sc->ev_n - 1]); P->total_ms = t; }
     P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
-    P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1];
+    P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1]; P->fused = sc->fused;
     P->d2h_bytes = sizeof hc + sizeof st;
     if (sc->rmdup) cu->dup_ord_base += (sc->k_end + 1) * (uint64_t)cu->S;           /* the next file's reads come after this file's */
     if (st[4]) { snprintf(err, ITX_ERRLEN, "the -R key table overflowed"); return ITX_ENOMEM; }
@@ -933,6 +1012,7 @@ extern "C" int itx_scan_alignments(itx_index *ix, const char *bam_list, const it
         total.h2d_ms += ix->prof.h2d_ms; total.inflate_ms += ix->prof.inflate_ms; total.stream_bytes += ix->prof.stream_bytes;
         total.h2d_bytes += ix->prof.h2d_bytes; total.d2h_bytes += ix->prof.d2h_bytes; total.n_launches += ix->prof.n_launches;
         total.n_bad_chunks += ix->prof.n_bad_chunks; total.inflate_threads = ix->prof.inflate_threads;
+        total.fused = ix->prof.fused; total.n_replayed_windows += ix->prof.n_replayed_windows;
     }
     total.n_records = ix->cnt[0] + ix->cnt[1]; total.n_fragments = ix->cnt[6];
     ix->prof = total;

@@ -31,7 +31,7 @@ struct itx_decode_args {
     itx_dev_opts o;
     itx_tuple *tuples; unsigned long long *entry, *exit_; uint32_t *nrec;
     unsigned long long *carry; uint32_t *winbad; uint32_t *status;
-    uint32_t *work;                        /* [0] k_decode_span, [1] k_overlap chunk counters; zeroed by k_fixup */
+    uint32_t *work;                        /* [0] k_decode_span, [1] k_overlap (both zeroed by k_fixup), [2] k_scan (zeroed by its last CTA) */
 };
 
 /* fire-and-forget reductions (RED, no return value) */
@@ -483,6 +483,212 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
     __syncthreads();
     if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], sh_cnt[threadIdx.x]);
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) itx_red_u64(&D.grp[t], (unsigned long long)v); }
+}
+
+/* ------------------------------------------------------------------ K1+K2+K3 in one pass */
+/* k_scan: the span kernel's streaming walk (TMA-staged stages, run-predicted chain) with every decoded record going
+ * straight into overlap / selection / accumulation, so no tuple ever leaves the SM: the stream is read once and
+ * nothing but counters is written.  A span's first record start is still a guess, and a wrong guess would by now
+ * have been counted; so the spans' entries and exits are logged, the LAST CTA to finish checks the chain
+ * (entry[i] == exit[i-1]) and notes the first window that fails, and the host -- at the end of the scan, when it
+ * reads the counters anyway -- replays every window from the first bad one with sign = -1 (the same guesses, the
+ * same additions, negated: integer sums, so the undo is exact) and runs the tuple path (k_decode_span, k_verify,
+ * k_fixup, k_overlap) over them instead.  No guess has failed on any stream tested; the path exists for exactness. */
+struct itx_scan_args {
+    itx_decode_args A;                   /* stream, spans, reference table, options, entry / exit logs, carry, status, work[2] */
+    itx_dev_index D;
+    int32_t sign;                        /* +1: count; -1: take back what the same call counted */
+    uint32_t window;                     /* index of this launch in the scan */
+    unsigned long long *carry_log;       /* [window] the carry the window started from (the undo pass starts from it too) */
+    uint32_t *first_bad;                 /* smallest window index whose chain check failed */
+    uint32_t *ticket;                    /* CTAs done */
+};
+#define ITX_SCAN_SMEM_BASE ITX_DECODE_SMEM
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) {
+    extern __shared__ __align__(128) uint8_t itx_smem[];
+    __shared__ unsigned long long sh_cnt[13];
+    __shared__ uint32_t sh_last;
+    const itx_decode_args &A = P.A; const itx_dev_index &D = P.D;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr uint32_t STG = ITX_STAGE + ITX_MARGIN;
+    uint8_t *buf = itx_smem + w * STG;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * STG) + w * ITX_POS_SLOTS;
+    const uint32_t buf_s = itx_smem_addr(buf);
+    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * STG + ITX_DW * ITX_POS_SLOTS * 2u) + w * 8;
+    uint32_t *sh_hist = reinterpret_cast<uint32_t *>(itx_smem + ITX_SCAN_SMEM_BASE);
+    const uint32_t nh = SMEM_HIST ? 2u * (uint32_t)(D.n_sub + D.n_fam + D.n_cla) : 0u;
+    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
+    if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
+    if (lane == 0) { itx_mbar_init(bar_s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const bool neg = P.sign < 0;
+    const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
+    const unsigned long long one64 = neg ? ~0ull : 1ull;
+    const bool stat = A.o.filter == 0 && D.stat_mode;
+    uint32_t c[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) c[k] = 0;
+    uint32_t parity = 0;
+    const itx_src_global G{A.b};
+    bool dead = false;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&A.work[2], 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= A.nchunks || dead) break;
+        const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
+        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+        unsigned long long p;
+        if (i == 0) {
+            if (neg) p = P.carry_log[P.window];
+            else { p = *A.carry; if (lane == 0) P.carry_log[P.window] = p; }
+        } else {
+            p = ITX_OFF_NONE;
+            for (unsigned long long base = lo; base < hi; base += 32) {
+                const unsigned long long q = base + lane;
+                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
+            }
+        }
+        if (lane == 0) A.entry[i] = p;
+        while (p < hi) {
+            const unsigned long long c_lo = lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
+            unsigned long long c_hi = c_lo + ITX_STAGE; if (c_hi > hi) c_hi = hi;
+            const unsigned long long rest = A.len - c_lo;
+            const uint32_t nb = rest > STG ? STG : (uint32_t)rest;
+            const uint32_t bytes = (nb + 15u) & ~15u;
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                itx_mbar_expect_tx(bar_s, bytes);
+                itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+            }
+            if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
+            parity ^= 1u;
+            uint32_t n = 0, ended = 0;
+            uint32_t q = (uint32_t)(p - c_lo);
+            {
+                const uint32_t qh = (uint32_t)(c_hi - c_lo);
+                const unsigned long long room = A.len - c_lo;
+                const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
+                const uint32_t av32 = A.avail > c_lo ? (A.avail - c_lo > 0x7fffffffull ? 0x7fffffffu : (uint32_t)(A.avail - c_lo)) : 0u;
+                while (q < qh) {
+                    if (q + 36u > room32) { ended = 1; break; }
+                    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
+                    const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
+                    const uint32_t sz = bs0 + 4u;
+                    if ((int32_t)bs0 < 32 || q + sz < q || q + sz > room32) { ended = 1; break; }
+                    const unsigned long long pk = (unsigned long long)q + (unsigned long long)lane * sz;
+                    bool same = false;
+                    if (pk < qh && pk + sz <= room32) {
+                        const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + ((uint32_t)pk & ~3u));
+                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) == bs0;
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, same);
+                    const uint32_t run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
+                    if (lane < run && n + lane < ITX_POS_SLOTS) pos[n + lane] = (uint16_t)pk;
+                    n += run;
+                    q += run * sz;
+                    if (q > av32 && lane == 0) atomicOr(&A.status[0], 2u);
+                }
+            }
+            __syncwarp();
+            const itx_src_stage S{buf, A.b, c_lo, nb};
+            for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+                const uint32_t j = j0 + lane; const bool valid = j < n;
+                itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
+                unsigned long long rp = 0;
+                if (valid) {
+                    rp = c_lo + pos[j];
+                    uint32_t x[9]; S.core(rp, x);
+                    T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, A.o);
+                }
+                const uint32_t info = T.info;
+                const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+                const uint32_t m_valid = __ballot_sync(0xffffffffu, valid), m_slot2 = __ballot_sync(0xffffffffu, slot2);
+                const uint32_t m_map = __ballot_sync(0xffffffffu, info & ITX_F_MAPPED), m_used = __ballot_sync(0xffffffffu, info & ITX_F_USED);
+                const uint32_t m_frag = __ballot_sync(0xffffffffu, frag), m_uniq = __ballot_sync(0xffffffffu, uniq);
+                c[0] += __popc(m_valid & ~m_slot2); c[1] += __popc(m_slot2);
+                c[2] += __popc(m_map & ~m_slot2);   c[3] += __popc(m_map & m_slot2);
+                c[4] += __popc(m_used & ~m_slot2);  c[5] += __popc(m_used & m_slot2);
+                c[6] += __popc(m_frag);
+                const uint32_t mu = __popc(m_frag & m_uniq);
+                c[7] += mu; c[11] += mu;
+                if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
+                long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
+                const uint32_t chrom = info & ITX_CHROM_MASK;
+                if (frag && chrom != ITX_CHROM_NONE) {
+                    int32_t nhit; float tcov;
+                    sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov, &e);
+                    if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
+                    if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
+                        uint32_t x[9]; S.core(rp, x);
+                        uint32_t bad = 0;
+                        if (itx_mapped_to_diff_subfam(D, S, rp, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+                    }
+                }
+                const bool counted = sel >= 0 && !diffsub;
+                const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+                c[12] += __popc(__ballot_sync(0xffffffffu, diffsub));
+                c[9] += __popc(m_cnt); c[10] += __popc(m_cnt & m_uniq);
+                if (counted) {
+                    if (stat) {
+                        const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
+                        const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+                        if (SMEM_HIST) {
+                            atomicAdd(&sh_hist[hs], 1u); atomicAdd(&sh_hist[hf], 1u); atomicAdd(&sh_hist[hc], 1u);
+                            if (uniq) { atomicAdd(&sh_hist[hs + 1], 1u); atomicAdd(&sh_hist[hf + 1], 1u); atomicAdd(&sh_hist[hc + 1], 1u); }
+                        } else {
+                            itx_red_u64(&D.grp[hs], one64); itx_red_u64(&D.grp[hf], one64); itx_red_u64(&D.grp[hc], one64);
+                            if (uniq) { itx_red_u64(&D.grp[hs + 1], one64); itx_red_u64(&D.grp[hf + 1], one64); itx_red_u64(&D.grp[hc + 1], one64); }
+                        }
+                        const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(D.sinfo + m.sub));
+                        const uint32_t L = sv.x;
+                        uint32_t ja, jb;
+                        if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
+                            const unsigned long long off = (unsigned long long)sv.z | ((unsigned long long)sv.w << 32);
+                            itx_red_u32(&D.bp_diff[off + ja], one); itx_red_u32(&D.bp_diff[off + jb], minus_one);
+                            if (uniq) { itx_red_u32(&D.bp_diff_u[off + ja], one); itx_red_u32(&D.bp_diff_u[off + jb], minus_one); }
+                        }
+                    } else if (A.o.filter) {
+                        itx_red_u32(&D.el_cnt[sel], one);
+                        if (uniq) itx_red_u32(&D.el_cnt_u[sel], one);
+                    }
+                }
+            }
+            if (ended) { p = ITX_OFF_END; break; }
+            p = c_lo + q;
+        }
+        if (lane == 0) A.exit_[i] = p;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) if (c[k]) atomicAdd(&sh_cnt[k], (unsigned long long)c[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], neg ? 0ull - sh_cnt[threadIdx.x] : sh_cnt[threadIdx.x]);
+    for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) itx_red_u64(&D.grp[t], neg ? 0ull - (unsigned long long)v : (unsigned long long)v); }
+    /* the last CTA out checks the chain of the whole window and hands the carry on */
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (sh_last) {
+        __threadfence();
+        uint32_t bad = 0;
+        for (uint32_t i = 1 + threadIdx.x; i < A.nchunks; i += blockDim.x) bad |= __ldcg(A.entry + i) != __ldcg(A.exit_ + i - 1) ? 1u : 0u;
+        bad = __syncthreads_or((int)bad) ? 1u : 0u;
+        if (threadIdx.x == 0) {
+            if (!neg) {
+                if (bad) atomicMin(P.first_bad, P.window);
+                *A.carry = __ldcg(A.exit_ + A.nchunks - 1);
+            }
+            A.work[2] = 0; *P.ticket = 0;
+        }
+    }
 }
 
 /* prefix sums of the coverage difference arrays: one warp per subfamily */

@@ -264,6 +264,33 @@ def test_rmdup_keys_persist_across_the_files_of_a_run(worlds, tmp_path):
     ix.close()
 
 
+@pytest.mark.parametrize("mode", ["fused", "tuple_path", "fused_replayed"])
+@pytest.mark.parametrize("case", [SYN[1], SYN[2], SYN[4], SYN[7]], ids=lambda c: c[0])
+def test_fused_and_tuple_paths_count_the_same(case, mode, worlds, monkeypatch):
+    """k_scan (one kernel per launch group), the tuple path it falls back to, and the replay of a scan whose chain
+    check is declared failed (take everything back with sign -1, count again through the tuple path) all give
+    the oracle's numbers"""
+    name, shape, n_rmsk, rmode, n_units, kw = case
+    if mode == "tuple_path":
+        monkeypatch.setenv("ITX_FUSED", "0")
+    if mode == "fused_replayed":
+        monkeypatch.setenv("ITX_FUSED_TEST_REPLAY", "1")
+    s, (cs, rs, rm), _ = worlds(shape, n_rmsk)
+    buf, n, nrec = s.stream(rmode, n_units)
+    raw = buf[:n].tobytes()
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_stream(raw, O.default_opts(**kw))
+    ix = capi.Index(cs, rs, rm)
+    ix.tune(chunk_bytes=8192, window_bytes=1 << 20)           # several launch groups: the carry crosses them
+    assert ix.scan_stream(raw, capi.default_opts(**kw)) == want
+    pr = ix.profile()
+    assert pr["fused"] == (0 if mode == "tuple_path" else 1)
+    assert (pr["n_replayed_windows"] > 0) == (mode == "fused_replayed")
+    assert_same_tables(ix, ora)
+    ora.close()
+    ix.close()
+
+
 def test_damaged_bgzf_block_is_reported(worlds, tmp_path, monkeypatch):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bam = str(tmp_path / "reads.bam")
