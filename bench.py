@@ -166,7 +166,25 @@ def reference_baseline(wd, tables, synth_world, sample_reads, mode, procs, repea
                       "fixed cost (rmsk parse + wig/bigWig, header-only BAM) of %.1f s subtracted" % (procs, sample_reads, "SE-50 hg19-shaped", fixed)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    # libraries (NCCL prints its version banner with some NCCL_DEBUG settings) must not add lines to stdout: everything
+    # written to fd 1 during the run goes to stderr; the JSON line is written to a duplicate of the original stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -209,7 +227,7 @@ def main():
                 vals.append(res["sample_reads"] / res["loop_s"][0])
         v = sum(vals) / len(vals)
         ms = 1e3 * res["sample_reads"] / v
-        print(json.dumps({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        emit(({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer (f32 coverage ratio)",
                           "data": "synthetic", "config": {"workload": workload, "step": "bounded sample: " + res["sample"]},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": res["kind"], "sample": res["sample"]},
@@ -242,6 +260,8 @@ def main():
     ix = itx.Index(*tables, device=lrank)
     if a.chunk or a.window:
         ix.tune(chunk_bytes=a.chunk, window_bytes=a.window)
+    if world > 1:
+        ix.tune(inflate_threads=max(2, (os.cpu_count() or 16) // world))      # the ranks of a box share its host cores
     log("index: %d intervals, %d subfamilies (%.1f s)" % (L.itx_n_elem(ix.h), ix.n(0), time.perf_counter() - t_setup))
     if world > 1:
         uid = [ix.comm_unique_id() if rank == 0 else None]
@@ -422,7 +442,7 @@ def main():
                           "repaired_chunk_entries": int(bad)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "counters": {"records": int(cnt[0] + cnt[1]), "fragments": int(cnt[6]), "in_repeats": int(cnt[9]), "unique_in_repeats": int(cnt[10])}}
-        print(json.dumps(out))
+        emit(out)
     L.itx_bam_header_free(h)
     L.itx_dev_free(dbuf)
     L.itx_host_free_pinned(hbuf)
