@@ -874,6 +874,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 rc = ITX_EFORMAT;
             }
         }
+        if (timing) for (int i = 0; i < nw; i++) { float a = 0, b = 0; cudaEventElapsedTime(&a, wev[0], wev[2 * i]); cudaEventElapsedTime(&b, wev[0], wev[2 * i + 1]); fprintf(stderr, "[itx timing] inflate group %d: %.1f .. %.1f ms after the first launch\n", i, a, b); }
         /* groups overlap: report the span from the first group's launch to the last group's end */
         for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[0], wev[2 * i + 1]) == cudaSuccess && ms > inflate_ms) inflate_ms = ms; }
     } while (0);
