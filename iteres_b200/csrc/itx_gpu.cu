@@ -54,7 +54,7 @@ struct itx_cuda {
     FILE *bed_f, *bed_uf; int bed_owner;             /* opened by the outermost entry point of the run */
     uint64_t ord_cap;                                /* trace entries one launch group may need (0: not in ordered mode) */
     itx_trace *h_ord_trace; uint64_t h_ord_trace_cap; uint8_t *h_ord_buf; uint64_t h_ord_buf_cap;
-    int used_el, used_cpg, host_el, host_cpg;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
+    int used_el, used_cpg, used_cpg_el, host_el, host_cpg, host_cpg_el;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
     void *d_flush;
@@ -126,7 +126,7 @@ extern "C" void itx_index_reset_counts(itx_index *ix) {
     char err[ITX_ERRLEN];
     cudaSetDevice(ix->cu->device);
     zero_counters(ix, err);
-    ix->cu->used_el = ix->cu->used_cpg = 0;
+    ix->cu->used_el = ix->cu->used_cpg = ix->cu->used_cpg_el = 0;
     if (ix->cu->d_dup_keys) {        /* forget the reads of the previous run */
         cudaMemset(ix->cu->d_dup_keys, 0xff, ix->cu->dup_cap * sizeof(itx_k128)); cudaMemset(ix->cu->d_dup_ords, 0xff, ix->cu->dup_cap * 8);
         cudaMemset(ix->cu->d_dup_mins, 0xff, 16); cudaMemset(ix->cu->d_dup_mins + 2, 0, 8);
@@ -1047,13 +1047,15 @@ extern "C" int itx_sync_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     if (cpg) {
         if (ng) { CK(cudaMemcpyAsync(gc, cu->D.grp_cpg, ng * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(gs, cu->D.grp_cpg_score, ng * 8, cudaMemcpyDeviceToHost, cu->stream)); }
         if (bl) CK(cudaMemcpyAsync(ix->bp_cpg, cu->D.bp_cpg, bl * 8, cudaMemcpyDeviceToHost, cu->stream));
-        if (ne) { CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream)); }
-        moved += ng * 12 + bl * 8 + ne * 12; cu->host_cpg = 1;
+        moved += ng * 12 + bl * 8; cu->host_cpg = 1;
     } else if (cu->host_cpg) {
         if (bl) memset(ix->bp_cpg, 0, bl * 8);
-        if (ne) { memset(ix->el_cpg, 0, ne * 4); memset(ix->el_cpg_score, 0, ne * 8); }
         cu->host_cpg = 0;
     }
+    if (ne && cu->used_cpg_el) {       /* the per-locus CpG counters belong to cpgfilter */
+        CK(cudaMemcpyAsync(ix->el_cpg, cu->D.el_cpg, ne * 4, cudaMemcpyDeviceToHost, cu->stream)); CK(cudaMemcpyAsync(ix->el_cpg_score, cu->D.el_cpg_score, ne * 8, cudaMemcpyDeviceToHost, cu->stream));
+        moved += ne * 12; cu->host_cpg_el = 1;
+    } else if (ne && cu->host_cpg_el) { memset(ix->el_cpg, 0, ne * 4); memset(ix->el_cpg_score, 0, ne * 8); cu->host_cpg_el = 0; }
     CK(cudaStreamSynchronize(cu->stream));
     float fm = 0; cudaEventElapsedTime(&fm, a, b); ix->prof.finalize_ms = fm; cudaEventDestroy(a); cudaEventDestroy(b);
     ix->prof.d2h_bytes += moved;
@@ -1117,53 +1119,152 @@ extern "C" int itx_dev_flush_l2(itx_index *ix) {
 }
 
 /* ------------------------------------------------------------------ CpG bedGraph (cpgBedGraphOverlapRepeat) */
+/* rows already parsed on the host (the lines the device left over) through k_cpg */
+typedef struct { int32_t *hc, *dc; uint32_t *hs, *he, *ds, *de; double *hv, *dv; size_t cap, n; } cpg_rows;
+static void cpg_rows_free(cpg_rows *R) { cudaFreeHost(R->hc); cudaFreeHost(R->hs); cudaFreeHost(R->he); cudaFreeHost(R->hv); cudaFree(R->dc); cudaFree(R->ds); cudaFree(R->de); cudaFree(R->dv); memset(R, 0, sizeof *R); }
+static int cpg_rows_init(cpg_rows *R, size_t cap) {
+    memset(R, 0, sizeof *R); R->cap = cap;
+    if (cudaHostAlloc((void **)&R->hc, cap * 4, 0) || cudaHostAlloc((void **)&R->hs, cap * 4, 0) || cudaHostAlloc((void **)&R->he, cap * 4, 0) || cudaHostAlloc((void **)&R->hv, cap * 8, 0) ||
+        cudaMalloc((void **)&R->dc, cap * 4) || cudaMalloc((void **)&R->ds, cap * 4) || cudaMalloc((void **)&R->de, cap * 4) || cudaMalloc((void **)&R->dv, cap * 8)) { cpg_rows_free(R); return ITX_ENOMEM; }
+    return ITX_OK;
+}
+static int cpg_rows_flush(itx_index *ix, cpg_rows *R, int filter, unsigned long long *d_in_repeat) {
+    itx_cuda *cu = ix->cu;
+    if (!R->n) return ITX_OK;
+    cudaMemcpyAsync(R->dc, R->hc, R->n * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(R->ds, R->hs, R->n * 4, cudaMemcpyHostToDevice, cu->stream);
+    cudaMemcpyAsync(R->de, R->he, R->n * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(R->dv, R->hv, R->n * 8, cudaMemcpyHostToDevice, cu->stream);
+    itx_cpg_args A; A.D = cu->D; A.chrom = R->dc; A.start = R->ds; A.end = R->de; A.score = R->dv; A.n = (long long)R->n; A.filter = filter; A.in_repeat = d_in_repeat;
+    k_cpg<<<(unsigned)((R->n + 255) / 256), 256, 0, cu->stream>>>(A);
+    R->n = 0;
+    return cudaStreamSynchronize(cu->stream) == cudaSuccess ? ITX_OK : ITX_ENODEV;
+}
+/* one text line [s, e) the reference's way (lineFileNextReal + chopByWhite + strtol / strtod, generic.c:1069-1076):
+ * 0 = blank or comment, -k = only k < 4 fields, 1 = a row was appended */
+static int cpg_parse_line_host(itx_index *ix, const char *s, const char *e, cpg_rows *R) {
+    while (s < e && (*s == ' ' || (*s >= 9 && *s <= 13))) s++;
+    if (s >= e || *s == '#') return 0;
+    char tmp[4][64]; const char *ws[20], *we[20]; int nw = 0; const char *q = s;
+    while (nw < 20 && q < e) { ws[nw] = q; while (q < e && !(*q == ' ' || (*q >= 9 && *q <= 13))) q++; we[nw] = q; nw++; while (q < e && (*q == ' ' || (*q >= 9 && *q <= 13))) q++; }
+    if (nw < 4) return -nw - 100;
+    char *name = strndup(ws[0], (size_t)(we[0] - ws[0]));
+    for (int k = 1; k < 4; k++) { size_t l = (size_t)(we[k] - ws[k]); if (l > 63) l = 63; memcpy(tmp[k], ws[k], l); tmp[k][l] = 0; }
+    R->hc[R->n] = itx_strtab_find(&ix->chroms, name); free(name);
+    R->hs[R->n] = (uint32_t)strtol(tmp[1], NULL, 0); R->he[R->n] = (uint32_t)strtol(tmp[2], NULL, 0); R->hv[R->n] = strtod(tmp[3], NULL);
+    R->n++;
+    return 1;
+}
+
+/* The bedGraph text is parsed ON THE DEVICE: host threads pread() the file window by window into pinned memory (whole
+ * lines per window; a cut last line moves to the next window), the text crosses PCIe as it is and k_bedgraph finds
+ * the lines, parses them and accumulates.  The host only sees what the device hands back: the first line with fewer
+ * than four fields (an error, as in the reference) and the rare lines whose score needs the full strtod.
+ * ITX_CPG_PARSE=host keeps the whole parse on the host (A/B). */
 extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]) {
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
     err[0] = 0;
     itx_cuda *cu = ix->cu;
     CK(cudaSetDevice(cu->device));
     cu->used_cpg = 1;
+    if (filter) cu->used_cpg_el = 1;
     struct stat st;
-    FILE *f = (stat(bedgraph, &st) == 0 && S_ISDIR(st.st_mode)) ? NULL : fopen(bedgraph, "r");
-    if (!f) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
-    const size_t BATCH = 1u << 22;
-    int32_t *hc = NULL; uint32_t *hs = NULL, *he = NULL; double *hv = NULL;
-    int32_t *dc = NULL; uint32_t *ds = NULL, *de = NULL; double *dv = NULL; unsigned long long *dn = NULL;
-    int rc = ITX_OK;
-    if (cudaHostAlloc((void **)&hc, BATCH * 4, 0) || cudaHostAlloc((void **)&hs, BATCH * 4, 0) || cudaHostAlloc((void **)&he, BATCH * 4, 0) || cudaHostAlloc((void **)&hv, BATCH * 8, 0) ||
-        cudaMalloc((void **)&dc, BATCH * 4) || cudaMalloc((void **)&ds, BATCH * 4) || cudaMalloc((void **)&de, BATCH * 4) || cudaMalloc((void **)&dv, BATCH * 8) || cudaMalloc((void **)&dn, 8)) {
-        snprintf(err, ITX_ERRLEN, "CUDA allocation failed"); rc = ITX_ENOMEM;
+    int fd = (stat(bedgraph, &st) == 0 && S_ISDIR(st.st_mode)) ? -1 : open(bedgraph, O_RDONLY);
+    if (fd < 0) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
+    if (fstat(fd, &st) != 0) { close(fd); snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
+    const uint64_t flen = (uint64_t)st.st_size;
+    const bool host_parse = getenv("ITX_CPG_PARSE") && strcmp(getenv("ITX_CPG_PARSE"), "host") == 0;
+    const int nth = inflate_thread_count(ix);
+    const uint64_t W = 64ull << 20, CAPW = 2 * W + 4096;                   /* a window holds a cut line of the previous one in front */
+    uint8_t *hbuf[2] = {NULL, NULL}, *dbuf[2] = {NULL, NULL}; uint32_t *dfall[2] = {NULL, NULL}; unsigned long long *dcnt = NULL;
+    cudaEvent_t done[2] = {NULL, NULL};
+    cpg_rows R; int rc = cpg_rows_init(&R, 1u << 20);
+    uint64_t used[2] = {0, 0}; bool inflight[2] = {false, false};
+    unsigned long long lines = 0, inrep = 0;
+    const uint64_t fall_cap = CAPW / 8 + 16;
+    for (int i = 0; i < 2 && rc == ITX_OK; i++) {
+        if (cudaHostAlloc((void **)&hbuf[i], CAPW + 64, 0) != cudaSuccess || cudaMalloc((void **)&dbuf[i], CAPW + 64) != cudaSuccess ||
+            cudaMalloc((void **)&dfall[i], fall_cap * 4) != cudaSuccess || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) rc = ITX_ENOMEM;
     }
-    unsigned long long zero = 0; uint32_t lines = 0;
-    if (rc == ITX_OK) cudaMemcpy(dn, &zero, 8, cudaMemcpyHostToDevice);
-    char *line = NULL; size_t lc = 0; size_t nb = 0; bool eof = false;
-    static const size_t IOBUF = 1 << 22; char *iobuf = (char *)malloc(IOBUF); setvbuf(f, iobuf, _IOFBF, IOBUF);
-    while (rc == ITX_OK && !eof) {
-        nb = 0;
-        while (nb < BATCH) {
-            if (getline(&line, &lc, f) < 0) { eof = true; break; }
-            char *s = line; while (*s == ' ' || (*s >= 9 && *s <= 13)) s++;
-            if (*s == 0 || *s == '#') continue;
-            char *w[20]; int nw = 0; char *q = s;
-            while (nw < 20) { while (*q == ' ' || (*q >= 9 && *q <= 13)) q++; if (!*q) break; w[nw++] = q; while (*q && !(*q == ' ' || (*q >= 9 && *q <= 13))) q++; if (!*q) break; *q++ = 0; }
-            if (nw < 4) { snprintf(err, ITX_ERRLEN, "file %s doesn't appear to be in bedGraph format. At least 4 fields required, got %d", bedgraph, nw); rc = ITX_EFORMAT; break; }
-            lines++;
-            hc[nb] = itx_strtab_find(&ix->chroms, w[0]);
-            hs[nb] = (uint32_t)strtol(w[1], NULL, 0); he[nb] = (uint32_t)strtol(w[2], NULL, 0); hv[nb] = strtod(w[3], NULL);
-            nb++;
+    if (rc == ITX_OK && cudaMalloc((void **)&dcnt, 2 * 4 * 8 + 8) != cudaSuccess) rc = ITX_ENOMEM;
+    if (rc != ITX_OK) snprintf(err, ITX_ERRLEN, "CUDA allocation failed");
+    unsigned long long *d_inrep_rows = dcnt ? dcnt + 8 : NULL;             /* k_cpg's own counter */
+    if (rc == ITX_OK) cudaMemsetAsync(d_inrep_rows, 0, 8, cu->stream);
+    /* what window `i` left for the host: its counters, the malformed line, the lines with a hard score */
+    auto settle = [&](int i) -> int {
+        if (!inflight[i]) return ITX_OK;
+        inflight[i] = false;
+        unsigned long long c[4];
+        if (cudaEventSynchronize(done[i]) != cudaSuccess || cudaMemcpy(c, dcnt + 4 * i, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error in the bedGraph kernel: %s", cudaGetErrorString(cudaGetLastError())); return ITX_ENODEV; }
+        lines += c[0]; inrep += c[1];
+        const char *tb = (const char *)hbuf[i];
+        if (c[2] != ~0ull) {
+            const char *s = tb + c[2], *e = s; while (e < tb + used[i] && *e != '\n') e++;
+            int k = cpg_parse_line_host(ix, s, e, &R);
+            snprintf(err, ITX_ERRLEN, "file %s doesn't appear to be in bedGraph format. At least 4 fields required, got %d", bedgraph, k < 0 ? -k - 100 : 0);
+            return ITX_EFORMAT;
         }
-        if (rc != ITX_OK || nb == 0) break;
-        cudaMemcpyAsync(dc, hc, nb * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(ds, hs, nb * 4, cudaMemcpyHostToDevice, cu->stream);
-        cudaMemcpyAsync(de, he, nb * 4, cudaMemcpyHostToDevice, cu->stream); cudaMemcpyAsync(dv, hv, nb * 8, cudaMemcpyHostToDevice, cu->stream);
-        itx_cpg_args A; A.D = cu->D; A.chrom = dc; A.start = ds; A.end = de; A.score = dv; A.n = (long long)nb; A.filter = filter; A.in_repeat = dn;
-        k_cpg<<<(unsigned)((nb + 255) / 256), 256, 0, cu->stream>>>(A);
-        if (cudaStreamSynchronize(cu->stream) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error in the CpG kernel: %s", cudaGetErrorString(cudaGetLastError())); rc = ITX_ENODEV; }
+        if (c[3]) {
+            uint32_t *off = (uint32_t *)malloc((size_t)c[3] * 4);
+            if (cudaMemcpy(off, dfall[i], (size_t)c[3] * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { free(off); return ITX_ENODEV; }
+            for (unsigned long long k = 0; k < c[3]; k++) {
+                const char *s = tb + off[k], *e = s; while (e < tb + used[i] && *e != '\n') e++;
+                if (cpg_parse_line_host(ix, s, e, &R) == 1) lines++;
+                if (R.n == R.cap) { int r2 = cpg_rows_flush(ix, &R, filter, d_inrep_rows); if (r2) { free(off); return r2; } }
+            }
+            free(off);
+        }
+        return ITX_OK;
+    };
+    uint64_t fo = 0, carry = 0; int slot = 0;
+    uint8_t *carrybuf = (uint8_t *)malloc(W + 64);
+    const bool timing = getenv("ITX_TIMING") != NULL; double t_read = 0, t_settle = 0; const double t_all0 = now_ms();
+    while (rc == ITX_OK && (fo < flen || carry)) {
+        { const double t0 = now_ms(); rc = settle(slot); t_settle += now_ms() - t0; }      /* the slot's previous window is done with */
+        if (rc) break;
+        uint8_t *hb = hbuf[slot];
+        if (carry) memcpy(hb, carrybuf, carry);
+        const double t_r0 = now_ms();
+        const uint64_t n = flen - fo < W ? flen - fo : W;
+        if (n && itx_parallel_pread(fd, fo, fo + n, hb + carry, nth) != ITX_OK) { snprintf(err, ITX_ERRLEN, "read error in %s", bedgraph); rc = ITX_EIO; break; }
+        fo += n; t_read += now_ms() - t_r0;
+        uint64_t have = carry + n, use = have;
+        if (fo < flen) {                                                   /* whole lines only; the cut one goes to the next window */
+            while (use && hb[use - 1] != '\n') use--;
+        }
+        carry = have - use;
+        if (carry > W) { snprintf(err, ITX_ERRLEN, "a line of %s is longer than %llu bytes", bedgraph, (unsigned long long)W); rc = ITX_EFORMAT; break; }
+        if (carry) memcpy(carrybuf, hb + use, carry);
+        if (use) {
+            if (host_parse) {
+                const char *s = (const char *)hb, *end = s + use;
+                while (s < end && rc == ITX_OK) {
+                    const char *e = (const char *)memchr(s, '\n', (size_t)(end - s)); if (!e) e = end;
+                    int k = cpg_parse_line_host(ix, s, e, &R);
+                    if (k < 0) { snprintf(err, ITX_ERRLEN, "file %s doesn't appear to be in bedGraph format. At least 4 fields required, got %d", bedgraph, -k - 100); rc = ITX_EFORMAT; break; }
+                    if (k == 1) lines++;
+                    if (R.n == R.cap) rc = cpg_rows_flush(ix, &R, filter, d_inrep_rows);
+                    s = e + 1;
+                }
+            } else {
+                used[slot] = use;
+                cudaMemcpyAsync(dbuf[slot], hb, use, cudaMemcpyHostToDevice, cu->stream);
+                cudaMemsetAsync(dcnt + 4 * slot, 0, 32, cu->stream); cudaMemsetAsync(dcnt + 4 * slot + 2, 0xff, 8, cu->stream);
+                itx_bedgraph_args A; A.D = cu->D; A.text = dbuf[slot]; A.n = use; A.filter = filter; A.counts = dcnt + 4 * slot; A.fallback = dfall[slot]; A.fallback_cap = fall_cap;
+                k_bedgraph<<<(unsigned)((use + ITX_BG_TILE - 1) / ITX_BG_TILE), 256, 0, cu->stream>>>(A);
+                cudaEventRecord(done[slot], cu->stream);
+                inflight[slot] = true;
+            }
+        }
+        slot ^= 1;
     }
-    unsigned long long inrep = 0;
-    if (rc == ITX_OK) cudaMemcpy(&inrep, dn, 8, cudaMemcpyDeviceToHost);
-    free(line); fclose(f); free(iobuf);
-    cudaFreeHost(hc); cudaFreeHost(hs); cudaFreeHost(he); cudaFreeHost(hv); cudaFree(dc); cudaFree(ds); cudaFree(de); cudaFree(dv); cudaFree(dn);
-    if (n_lines) *n_lines = lines;
+    for (int i = 0; i < 2 && rc == ITX_OK; i++) rc = settle(i);
+    if (rc == ITX_OK) rc = cpg_rows_flush(ix, &R, filter, d_inrep_rows);
+    if (rc == ITX_OK) { unsigned long long x = 0; cudaMemcpy(&x, d_inrep_rows, 8, cudaMemcpyDeviceToHost); inrep += x; }
+    else cudaStreamSynchronize(cu->stream);
+    if (timing) fprintf(stderr, "[itx timing] bedGraph: %.1f ms in all, %.1f ms reading, %.1f ms waiting for the device\n", now_ms() - t_all0, t_read, t_settle);
+    close(fd); free(carrybuf);
+    for (int i = 0; i < 2; i++) { if (hbuf[i]) cudaFreeHost(hbuf[i]); cudaFree(dbuf[i]); cudaFree(dfall[i]); if (done[i]) cudaEventDestroy(done[i]); }
+    cudaFree(dcnt); cpg_rows_free(&R);
+    if (n_lines) *n_lines = (uint32_t)lines;
     if (n_in_repeat) *n_in_repeat = (uint32_t)inrep;
     return rc;
 }

@@ -773,6 +773,101 @@ __global__ void __launch_bounds__(256) k_cpg(const itx_cpg_args A) {
     }
 }
 
+/* ------------------------------------------------------------------ CpG bedGraph text on the device */
+/* k_bedgraph: the text of a bedGraph file, whole lines, in device memory.  A thread per byte: the thread whose byte
+ * starts a line parses it (v2: a CTA per 4 KiB tile lists its line starts first, then a thread per line) -- skip blank and '#' lines, chop on white space, chromosome by name, strtol start / end,
+ * strtod score (lineFileNextReal + chopByWhite + generic.c:1069-1076) -- and counts it exactly as k_cpg does.  Lines
+ * with fewer than four fields (the reference aborts at the first one) and scores outside the exact fast path of
+ * itx_strtod_fast are reported by file offset for the host. */
+#define ITX_BG_SH 512u                     /* families + classes gathered per CTA in shared memory */
+struct itx_bedgraph_args {
+    itx_dev_index D;
+    const uint8_t *text; unsigned long long n;
+    int32_t filter;
+    unsigned long long *counts;          /* [0] lines, [1] CpG sites in repeats, [2] smallest offset of a malformed line, [3] lines left to the host */
+    uint32_t *fallback; unsigned long long fallback_cap;      /* offsets (in this text) of the lines whose score the host must parse */
+};
+#define ITX_BG_TILE 4096u                  /* text bytes per CTA */
+__global__ void __launch_bounds__(256) k_bedgraph(const itx_bedgraph_args A) {
+    /* family and class sums are a few dozen addresses hit by every row: they are gathered per CTA in shared memory first */
+    __shared__ double sh_sc[ITX_BG_SH]; __shared__ uint32_t sh_cn[ITX_BG_SH];
+    __shared__ uint16_t sh_start[ITX_BG_TILE + 1]; __shared__ uint32_t sh_n, sh_lines, sh_inrep;
+    const itx_dev_index &D = A.D;
+    const uint32_t n_fc = (uint32_t)(D.n_fam + D.n_cla);
+    const bool sh_ok = !A.filter && D.stat_mode && n_fc <= ITX_BG_SH;
+    if (sh_ok) for (uint32_t t = threadIdx.x; t < n_fc; t += blockDim.x) { sh_sc[t] = 0.0; sh_cn[t] = 0; }
+    if (threadIdx.x == 0) { sh_n = 0; sh_lines = 0; sh_inrep = 0; }
+    __syncthreads();
+    /* pass 1: the tile's line feeds, 16 bytes per thread; the line after each of them is this CTA's (it may run into the
+     * next tile: the parse reads global memory), and the first CTA also owns the line at offset 0 */
+    const unsigned long long base = (unsigned long long)blockIdx.x * ITX_BG_TILE;
+    {
+        const unsigned long long q0 = base + threadIdx.x * 16ull;
+        if (q0 < A.n) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (q0 + 16 <= A.n) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(A.text + q0)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+            else for (uint32_t j = 0; q0 + j < A.n; j++) w[j >> 2] |= (uint32_t)A.text[q0 + j] << (8 * (j & 3));
+#pragma unroll
+            for (uint32_t j = 0; j < 16; j++)
+                if (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) == '\n' && q0 + j + 1 < A.n) sh_start[atomicAdd(&sh_n, 1u)] = (uint16_t)(threadIdx.x * 16u + j + 1u);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && A.n) sh_start[atomicAdd(&sh_n, 1u)] = 0;
+    }
+    __syncthreads();
+    const itx_src_global G{A.text};
+    /* pass 2: a thread per line */
+    for (uint32_t k = threadIdx.x; k < sh_n; k += blockDim.x) {
+        const unsigned long long p = base + sh_start[k];
+        unsigned long long q = p, le = p;
+        while (le < A.n && A.text[le] != '\n') le++;
+        while (q < le && itx_is_space(A.text[q])) q++;
+        if (q >= le || A.text[q] == '#') continue;
+        /* up to four words; a fifth and later ones do not matter */
+        unsigned long long ws[4], we[4]; int nw = 0;
+        while (nw < 4 && q < le) {
+            ws[nw] = q; while (q < le && !itx_is_space(A.text[q])) q++;
+            we[nw] = q; nw++;
+            while (q < le && itx_is_space(A.text[q])) q++;
+        }
+        if (nw < 4) { atomicMin(A.counts + 2, p); continue; }
+        bool exact;
+        const double sc = itx_strtod_fast(G, ws[3], we[3], &exact);
+        if (!exact) {
+            const unsigned long long f = atomicAdd(A.counts + 3, 1ull);
+            if (f < A.fallback_cap) A.fallback[f] = (uint32_t)p;
+            continue;
+        }
+        atomicAdd(&sh_lines, 1u);
+        const uint32_t st = (uint32_t)itx_strtol_int(G, ws[1], we[1]), en = (uint32_t)itx_strtol_int(G, ws[2], we[2]);
+        const int32_t c = itx_chrom_by_name(D, G, ws[0], we[0]);
+        itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
+        const long long sel = c >= 0 ? itx_find_head(D, c, st, en, &e) : -1;
+        if (sel < 0) continue;
+        atomicAdd(&sh_inrep, 1u);
+        if (A.filter) { atomicAdd(&D.el_cpg[sel], 1u); atomicAdd(&D.el_cpg_score[sel], sc); continue; }
+        if (!D.stat_mode) continue;
+        const itx_meta mt = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
+        const uint32_t gs = mt.sub, gf = (uint32_t)(D.n_sub + m2.fam), gc = (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+        atomicAdd(&D.grp_cpg[gs], 1u); atomicAdd(&D.grp_cpg_score[gs], sc);
+        if (sh_ok) {
+            atomicAdd(&sh_cn[m2.fam], 1u); atomicAdd(&sh_sc[m2.fam], sc);
+            atomicAdd(&sh_cn[D.n_fam + m2.cla], 1u); atomicAdd(&sh_sc[D.n_fam + m2.cla], sc);
+        } else {
+            atomicAdd(&D.grp_cpg[gf], 1u); atomicAdd(&D.grp_cpg_score[gf], sc);
+            atomicAdd(&D.grp_cpg[gc], 1u); atomicAdd(&D.grp_cpg_score[gc], sc);
+        }
+        const uint32_t L = D.sub_len[mt.sub];
+        uint32_t ja, jb;
+        if (L && itx_cov_range(st, 2u, e.start, e.end, mt.cons_start, mt.cons_end, L, &ja, &jb)) {
+            const unsigned long long off = D.sub_bp_off[mt.sub];
+            for (uint32_t j = ja; j < jb; j++) atomicAdd(&D.bp_cpg[off + j], sc);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (sh_lines) atomicAdd(A.counts, (unsigned long long)sh_lines); if (sh_inrep) atomicAdd(A.counts + 1, (unsigned long long)sh_inrep); }
+    if (sh_ok) for (uint32_t t = threadIdx.x; t < n_fc; t += blockDim.x) if (sh_cn[t]) { atomicAdd(&D.grp_cpg[D.n_sub + t], sh_cn[t]); atomicAdd(&D.grp_cpg_score[D.n_sub + t], sh_sc[t]); }
+}
+
 /* ------------------------------------------------------------------ BGZF inflate on the device */
 /* One thread per BGZF block, one warp per CTA, the warp's 32 blocks decoded in lock step.  A thread's look-up
  * tables (ITX_LUT_CELLS 16-bit cells) live in shared memory as 32-bit words interleaved across the lanes -- word

@@ -561,4 +561,46 @@ ITX_HD unsigned long long itx_dup_hash(unsigned long long lo, unsigned long long
     x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
     return x;
 }
+/* ------------------------------------------------------------------ bedGraph text (cpgBedGraphOverlapRepeat, generic.c:1069-1076) */
+ITX_HD bool itx_is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+/* strtod over [s, e) for the plain decimal forms [sign] digits [. digits] [e|E [sign] digits]: at most 19 significant
+ * digits gathered exactly in 64 bits; when the integer fits 53 bits and the power of ten is at most 22, ONE IEEE
+ * multiplication or division of two exact doubles gives the correctly rounded value -- the value glibc's strtod
+ * returns.  Anything else (longer mantissas, huge exponents, inf / nan / hex floats) sets *exact = false and the
+ * caller hands the line to the host's strtod.  Trailing characters stop the parse like strtod(s, NULL). */
+ITX_HD double itx_pow10_exact(uint32_t k) {       /* 10^k, k <= 22: all exactly representable */
+    double r = 1.0;
+    const double t[5] = {1e1, 1e2, 1e4, 1e8, 1e16};
+#pragma unroll
+    for (int b = 0; b < 5; b++) if (k & (1u << b)) r *= t[b];          /* products of exact powers below 2^53 * 2^k stay exact up to 1e22 */
+    return r;
+}
+template <class Src>
+ITX_HD double itx_strtod_fast(const Src &S, uint64_t s, uint64_t e, bool *exact) {
+    *exact = true;
+    while (s < e && itx_is_space(S.u8(s))) s++;
+    bool neg = false;
+    if (s < e) { const uint8_t c = S.u8(s); if (c == '-') { neg = true; s++; } else if (c == '+') s++; }
+    uint64_t m = 0; int32_t e10 = 0; uint32_t nd = 0; bool any = false, dropped = false;
+    while (s < e) { const uint8_t c = S.u8(s); if (c < '0' || c > '9') break; any = true; if (nd < 19) { m = m * 10 + (c - '0'); if (m) nd++; } else { e10++; if (c != '0') dropped = true; } s++; }
+    if (s < e && S.u8(s) == '.') {
+        s++;
+        while (s < e) { const uint8_t c = S.u8(s); if (c < '0' || c > '9') break; any = true; if (nd < 19) { m = m * 10 + (c - '0'); if (m) nd++; e10--; } else if (c != '0') dropped = true; s++; }
+    }
+    if (!any) { *exact = false; return 0.0; }                       /* inf, nan, garbage: the host decides */
+    if (s < e && (S.u8(s) == 'e' || S.u8(s) == 'E')) {
+        uint64_t q = s + 1; bool en = false;
+        if (q < e && (S.u8(q) == '-' || S.u8(q) == '+')) { en = S.u8(q) == '-'; q++; }
+        if (q < e && S.u8(q) >= '0' && S.u8(q) <= '9') {
+            int32_t x = 0;
+            while (q < e && S.u8(q) >= '0' && S.u8(q) <= '9') { if (x < 100000) x = x * 10 + (S.u8(q) - '0'); q++; }
+            e10 += en ? -x : x;
+        }
+    } else if (s < e && (S.u8(s) == 'x' || S.u8(s) == 'X') && m == 0) { *exact = false; return 0.0; }      /* 0x...: a hex float */
+    if (m == 0) return neg ? -0.0 : 0.0;
+    if (dropped || m >= (1ull << 53) || e10 > 22 || e10 < -22) { *exact = false; return 0.0; }
+    double v = (double)m;
+    v = e10 >= 0 ? v * itx_pow10_exact((uint32_t)e10) : v / itx_pow10_exact((uint32_t)(-e10));
+    return neg ? -v : v;
+}
 #endif

@@ -416,4 +416,14 @@ int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_c
     }
     return (int)rc;
 }
+
+/* itx_strtod_fast on a C string: returns the value, *exact = 0 where the device leaves the line to the host */
+double emu_strtod(const char *str, int *exact) {
+    const size_t n = strlen(str);
+    std::vector<uint8_t> buf(n + 64, 0); memcpy(buf.data(), str, n);
+    bool ex = false;
+    const double v = itx_strtod_fast(itx_src_global{buf.data()}, 0, n, &ex);
+    *exact = ex ? 1 : 0;
+    return v;
+}
 }

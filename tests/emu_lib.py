@@ -36,6 +36,8 @@ def lib():
         L.emu_query.restype = C.c_int32
         L.emu_query.argtypes = [vp, cp, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_int32)]
         L.emu_inflate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int]
+        L.emu_strtod.restype = C.c_double
+        L.emu_strtod.argtypes = [cp, C.POINTER(C.c_int)]
         L.emu_scan_cpg.argtypes = [vp, cp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), cp]
         _lib = L
     return _lib
@@ -118,3 +120,10 @@ def inflate(raw_deflate, expect_len, cap=None, defer=1):
     got = C.c_uint32(0)
     rc = lib().emu_inflate(src.ctypes.data if len(src) else None, len(src), dst.ctypes.data, cap, expect_len, C.byref(got), defer)
     return rc, dst[: min(got.value, cap)].tobytes()
+
+
+def strtod_fast(text):
+    """the device's score parser (host build) -> (value, exact)"""
+    ex = C.c_int(0)
+    v = lib().emu_strtod(text.encode(), C.byref(ex))
+    return v, bool(ex.value)

@@ -460,3 +460,48 @@ def test_command_line_tool_is_a_drop_in(kat, variant, tmp_path):
     assert sorted(os.listdir(str(tmp_path))) == want
     for fn in want:
         assert same_output(cmd, os.path.join(str(tmp_path), fn), os.path.join(vdir, fn)), fn
+
+
+@pytest.mark.parametrize("parse", ["device", "host"])
+def test_bedgraph_text_oddities(parse, worlds, tmp_path, monkeypatch):
+    """k_bedgraph parses the text itself: blank and comment lines, leading blanks, CRLF, extra columns, hexadecimal
+    and octal coordinates, exponents, and scores that only the host's strtod can do (handed back by offset)"""
+    if parse == "host":
+        monkeypatch.setenv("ITX_CPG_PARSE", "host")
+    s, (cs, rs, rm), d = worlds(1, 60000)
+    src = str(tmp_path / "base.bedGraph")
+    s.write_bedgraph(src, 3000)
+    rows = [l.split() for l in open(src)]
+    rnd = np.random.RandomState(5)
+    out = ["# a comment", "", "   ", "track type=bedGraph"[0:0]]
+    for i, (c, a, b, v) in enumerate(rows):
+        k = i % 9
+        if k == 0: out.append("  %s\t%s\t%s\t%s" % (c, a, b, v))
+        elif k == 1: out.append("%s %s %s %s extra columns here" % (c, a, b, v))
+        elif k == 2: out.append("%s\t0x%x\t%s\t%s\r" % (c, int(a), b, v))
+        elif k == 3: out.append("%s\t%s\t%s\t%se0" % (c, a, b, v))
+        elif k == 4: out.append("%s\t%s\t%s\t%s" % (c, a, b, "0.1234567890123456789012"))      # more digits than 64 bits hold: host
+        elif k == 5: out.append("%s\t%s\t%s\t%s" % (c, a, b, "1e-30"))                          # power of ten beyond the exact range: host
+        elif k == 6: out.append("#%s\t%s\t%s\t%s" % (c, a, b, v))
+        elif k == 7: out.append("%s\t%s\t%s\t%.3e" % (c, a, b, float(v)))
+        else: out.append("%s\t%s\t%s\t%s" % (c, a, b, v))
+    odd = str(tmp_path / "odd.bedGraph")
+    open(odd, "w").write("\n".join(out))                       # no newline after the last line
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_cpg(odd, 0)
+    ix = capi.Index(cs, rs, rm)
+    assert ix.scan_cpg(odd, 0) == want
+    a, b = str(tmp_path / "g"), str(tmp_path / "o")
+    ix.write_cpg_stat(a); ora.write_cpg_stat(b)
+    for nme in (".CpG.subfamily.stat", ".CpGstat.wig", ".CpG.family.stat", ".CpG.class.stat"):
+        assert close_text(a + nme, b + nme), nme
+    assert want[0] == sum(1 for i in range(len(rows)) if i % 9 != 6) and want[1] > 0
+    ora.close()
+    ix.close()
+    bad = str(tmp_path / "bad.bedGraph")
+    open(bad, "w").write("\n".join(out[:50] + ["chr1\t5\t7"] + out[50:]) + "\n")
+    ix = capi.Index(cs, rs, rm)
+    with pytest.raises(capi.ItxError) as e:
+        ix.scan_cpg(bad, 0)
+    assert "At least 4 fields required, got 3" in str(e.value)
+    ix.close()
