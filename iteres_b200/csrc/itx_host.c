@@ -19,6 +19,10 @@
 #include <ctype.h>
 #include <errno.h>
 #include <sys/stat.h>
+#include <fcntl.h>
+#include <time.h>
+#include <pthread.h>
+#include <unistd.h>
 
 /* ------------------------------------------------------------------ string tables */
 uint32_t itx_fnv1a(const char *s, size_t n) {
@@ -166,6 +170,195 @@ static int bin_level(int32_t s, int32_t e, int32_t *bin) {
     return -1;
 }
 
+/* one piece of rmsk.txt */
+typedef struct {
+    char *buf; size_t lo, hi;
+    const struct itx_index *ix; int filter_field; const char *filter_name, *path;
+    long long row_base; long line_base;                 /* rows / lines before this piece (known after the counting pass) */
+    long long n_rows; long n_lines;                     /* counting pass */
+    raw_el *raw; long long nraw, rawcap, kept;          /* parsing pass: elements with LOCAL chromosome / subfamily / family / class ids */
+    itx_strtab chroms, subs, fams, clas; int32_t *chrom_size; int32_t chromcap;
+    itx_group *sub, *fam, *cla; int32_t subcap, famcap, clacap;
+    int rc; char err[ITX_ERRLEN];
+    int pass;
+} rmsk_piece;
+static void *rmsk_worker(void *arg) {
+    rmsk_piece *P = (rmsk_piece *)arg;
+    char *s = P->buf + P->lo, *end = P->buf + P->hi;
+    if (P->pass == 0) {
+        /* rows = lines that are neither comments nor blank (rmsk2binKeeperHash numbers them before it filters) */
+        long long rows = 0; long lines = 0;
+        while (s < end) {
+            char *e = (char *)memchr(s, '\n', (size_t)(end - s)); if (!e) e = end;
+            lines++;
+            if (*s != '#') { char *q = s; while (q < e && isspace((unsigned char)*q)) q++; if (q < e) rows++; }
+            s = e + 1;
+        }
+        P->n_rows = rows; P->n_lines = lines;
+        return NULL;
+    }
+    const struct itx_index *ix = P->ix;
+    itx_strtab_init(&P->chroms); itx_strtab_init(&P->subs); itx_strtab_init(&P->fams); itx_strtab_init(&P->clas);
+    long long row = P->row_base - 1; long ln = P->line_base;
+    while (s < end) {
+        char *e = (char *)memchr(s, '\n', (size_t)(end - s)); if (!e) e = end;
+        char *line = s; s = e + 1;
+        *e = 0;                                          /* the buffer is ours; one byte past the file is allocated too */
+        ln++;
+        if (line[0] == '#') continue;
+        char *w[17]; int nw = split_white(line, w, 17);
+        if (nw == 0) continue;
+        if (nw < 17) { snprintf(P->err, ITX_ERRLEN, "Expecting 17 words line %ld of %s got %d", ln, P->path, nw); P->rc = ITX_EFORMAT; return NULL; }
+        row++;
+        if (P->filter_field != 0 && strcmp(P->filter_name, w[P->filter_field]) != 0) continue;
+        P->kept++;
+        raw_el el;
+        el.cs = (uint32_t)strtol(w[9][0] == '+' ? w[13] : w[15], NULL, 0);
+        el.ce = (uint32_t)strtol(w[14], NULL, 0);
+        el.start = (int32_t)(uint32_t)strtol(w[6], NULL, 0);
+        el.end = (int32_t)(uint32_t)strtol(w[7], NULL, 0);
+        el.row = (uint32_t)row;
+        int32_t c = itx_strtab_find(&P->chroms, w[5]);
+        if (c < 0) {
+            int size = name_int_or(&ix->chromsize, ix->chromsize_val, w[5], 0);
+            if (size == 0) continue;                       /* chromosome not in the size file: row dropped */
+            if (size < 0) { snprintf(P->err, ITX_ERRLEN, "bad range %d,%d in binKeeperNew", 0, size); P->rc = ITX_EFORMAT; return NULL; }
+            c = itx_strtab_add(&P->chroms, w[5]);
+            if (c >= P->chromcap) { P->chromcap = P->chromcap ? P->chromcap * 2 : 64; P->chrom_size = (int32_t *)realloc(P->chrom_size, sizeof(int32_t) * (size_t)P->chromcap); }
+            P->chrom_size[c] = size;
+        }
+        int32_t bin;
+        if (el.start < 0 || el.end > P->chrom_size[c] || el.start > el.end) {
+            snprintf(P->err, ITX_ERRLEN, "(%d %d) out of range (%d %d) in binKeeperAdd", el.start, el.end, 0, P->chrom_size[c]); P->rc = ITX_EFORMAT; return NULL;
+        }
+        if (bin_level(el.start, el.end, &bin) < 0) { snprintf(P->err, ITX_ERRLEN, "start %d, end %d out of range in findBin (max is 2Gb)", el.start, el.end); P->rc = ITX_EFORMAT; return NULL; }
+        el.chrom = c;
+        int32_t ns0 = P->subs.n, nf0 = P->fams.n;
+        el.sub = itx_strtab_intern(&P->subs, w[10]);
+        el.cla = itx_strtab_intern(&P->clas, w[11]);
+        el.fam = itx_strtab_intern(&P->fams, w[12]);
+        P->sub = grow_groups(P->sub, &P->subcap, P->subs.n);
+        P->fam = grow_groups(P->fam, &P->famcap, P->fams.n);
+        P->cla = grow_groups(P->cla, &P->clacap, P->clas.n);
+        if (P->subs.n != ns0) { P->sub[el.sub].first_fam = el.fam; P->sub[el.sub].first_cla = el.cla; }
+        if (P->fams.n != nf0) { P->fam[el.fam].first_cla = el.cla; }
+        if (ix->stat_mode) {
+            uint64_t len = (uint32_t)(el.end - el.start);
+            P->sub[el.sub].genome_count++; P->sub[el.sub].total_length += len;
+            P->fam[el.fam].genome_count++; P->fam[el.fam].total_length += len;
+            P->cla[el.cla].genome_count++; P->cla[el.cla].total_length += len;
+        }
+        if (P->nraw == P->rawcap) { P->rawcap = P->rawcap ? P->rawcap * 2 : (1 << 14); P->raw = (raw_el *)realloc(P->raw, sizeof(raw_el) * (size_t)P->rawcap); }
+        P->raw[P->nraw++] = el;
+    }
+    return NULL;
+}
+typedef struct { int fd; char *buf; size_t lo, hi; int failed; } rmsk_read_job;
+static void *rmsk_read_worker(void *arg) {
+    rmsk_read_job *J = (rmsk_read_job *)arg;
+    size_t o = J->lo;
+    while (o < J->hi) { ssize_t r = pread(J->fd, J->buf + o, J->hi - o, (off_t)o); if (r <= 0) { J->failed = 1; break; } o += (size_t)r; }
+    return NULL;
+}
+static int rmsk_parse_parallel(struct itx_index *ix, const char *rmsk, int filter_field, const char *filter_name,
+                               raw_el **raw_out, long long *nraw_out, long long *last_row, long long *kept_out, char *err) {
+    int fd = is_directory(rmsk) ? -1 : open(rmsk, O_RDONLY);
+    if (fd < 0) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", rmsk, strerror(errno)); return ITX_EIO; }
+    int T = (int)sysconf(_SC_NPROCESSORS_ONLN); if (T < 1) T = 1; if (T > 64) T = 64;
+    size_t n = 0; char *buf = NULL;
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+        /* a regular file: every thread reads (and so first touches) its own share of the buffer */
+        n = (size_t)st.st_size; buf = (char *)malloc(n + 1);
+        if (n < ((size_t)1 << 20)) T = 1;
+        rmsk_read_job *J = (rmsk_read_job *)calloc((size_t)T, sizeof(rmsk_read_job)); pthread_t *rt = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+        for (int t = 0; t < T; t++) {
+            J[t].fd = fd; J[t].buf = buf; J[t].lo = n / (size_t)T * (size_t)t; J[t].hi = t == T - 1 ? n : n / (size_t)T * (size_t)(t + 1);
+            if (T == 1 || pthread_create(&rt[t], NULL, rmsk_read_worker, &J[t]) != 0) { rmsk_read_worker(&J[t]); rt[t] = 0; }
+        }
+        int bad = 0;
+        for (int t = 0; t < T; t++) { if (rt[t]) pthread_join(rt[t], NULL); bad |= J[t].failed; }
+        free(J); free(rt);
+        if (bad) { close(fd); free(buf); snprintf(err, ITX_ERRLEN, "read error in %s", rmsk); return ITX_EIO; }
+    } else {
+        /* pipes and the like are read to their end */
+        size_t cap = 1 << 24; buf = (char *)malloc(cap + 1);
+        for (;;) { if (n == cap) { cap *= 2; buf = (char *)realloc(buf, cap + 1); } ssize_t r = read(fd, buf + n, cap - n); if (r <= 0) break; n += (size_t)r; }
+        if (n < ((size_t)1 << 20)) T = 1;
+    }
+    close(fd);
+    buf[n] = 0;
+    rmsk_piece *P = (rmsk_piece *)calloc((size_t)T, sizeof(rmsk_piece));
+    size_t at = 0;
+    for (int t = 0; t < T; t++) {
+        size_t hi = t == T - 1 ? n : n / (size_t)T * (size_t)(t + 1);
+        if (hi < at) hi = at;
+        while (hi < n && hi > 0 && buf[hi - 1] != '\n') hi++;             /* pieces end after a line feed */
+        P[t].buf = buf; P[t].lo = at; P[t].hi = hi; P[t].ix = ix; P[t].filter_field = filter_field; P[t].filter_name = filter_name; P[t].path = rmsk;
+        at = hi;
+    }
+    pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+    const int timing = getenv("ITX_TIMING") != NULL; struct timespec tp0; clock_gettime(CLOCK_MONOTONIC, &tp0);
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) { long long r = 0; long l = 0; for (int t = 0; t < T; t++) { P[t].row_base = r; P[t].line_base = l; r += P[t].n_rows; l += P[t].n_lines; } }
+        for (int t = 0; t < T; t++) { P[t].pass = pass; if (T == 1 || pthread_create(&th[t], NULL, rmsk_worker, &P[t]) != 0) { rmsk_worker(&P[t]); th[t] = 0; } }
+        for (int t = 0; t < T; t++) if (th[t]) { pthread_join(th[t], NULL); th[t] = 0; }
+        if (timing) { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); fprintf(stderr, "[itx timing] index: rmsk pass %d done after %.0f ms (%d threads)\n", pass, (t1.tv_sec - tp0.tv_sec) * 1e3 + (t1.tv_nsec - tp0.tv_nsec) * 1e-6, T); }
+    }
+    int rc = ITX_OK;
+    for (int t = 0; t < T && rc == ITX_OK; t++) if (P[t].rc) { rc = P[t].rc; memcpy(err, P[t].err, ITX_ERRLEN); }      /* the first failure in file order */
+    long long total = 0, kept = 0, rows = 0;
+    for (int t = 0; t < T; t++) { total += P[t].nraw; kept += P[t].kept; rows += P[t].n_rows; }
+    raw_el *raw = NULL;
+    if (rc == ITX_OK) {
+        raw = (raw_el *)malloc(sizeof(raw_el) * (size_t)(total ? total : 1));
+        int32_t subcap = 0, famcap = 0, clacap = 0, chromcap = 0;
+        long long o = 0;
+        for (int t = 0; t < T; t++) {
+            rmsk_piece *Q = &P[t];
+            int32_t *mc = (int32_t *)malloc(sizeof(int32_t) * (size_t)(Q->chroms.n + 1)), *ms = (int32_t *)malloc(sizeof(int32_t) * (size_t)(Q->subs.n + 1));
+            int32_t *mf = (int32_t *)malloc(sizeof(int32_t) * (size_t)(Q->fams.n + 1)), *ml = (int32_t *)malloc(sizeof(int32_t) * (size_t)(Q->clas.n + 1));
+            for (int32_t k = 0; k < Q->chroms.n; k++) {
+                int32_t c = itx_strtab_find(&ix->chroms, Q->chroms.names[k]);
+                if (c < 0) {
+                    c = itx_strtab_add(&ix->chroms, Q->chroms.names[k]);
+                    if (c >= chromcap) { chromcap = chromcap ? chromcap * 2 : 64; ix->chrom_size = (int32_t *)realloc(ix->chrom_size, sizeof(int32_t) * (size_t)chromcap); }
+                    ix->chrom_size[c] = Q->chrom_size[k];
+                }
+                mc[k] = c;
+            }
+            for (int32_t k = 0; k < Q->clas.n; k++) { ml[k] = itx_strtab_intern(&ix->clas, Q->clas.names[k]); ix->cla = grow_groups(ix->cla, &clacap, ix->clas.n); }
+            for (int32_t k = 0; k < Q->fams.n; k++) {
+                const int32_t n0 = ix->fams.n; mf[k] = itx_strtab_intern(&ix->fams, Q->fams.names[k]); ix->fam = grow_groups(ix->fam, &famcap, ix->fams.n);
+                if (ix->fams.n != n0) ix->fam[mf[k]].first_cla = ml[Q->fam[k].first_cla];
+            }
+            for (int32_t k = 0; k < Q->subs.n; k++) {
+                const int32_t n0 = ix->subs.n; ms[k] = itx_strtab_intern(&ix->subs, Q->subs.names[k]); ix->sub = grow_groups(ix->sub, &subcap, ix->subs.n);
+                if (ix->subs.n != n0) { ix->sub[ms[k]].first_fam = mf[Q->sub[k].first_fam]; ix->sub[ms[k]].first_cla = ml[Q->sub[k].first_cla]; }
+            }
+            if (ix->stat_mode) {
+                for (int32_t k = 0; k < Q->subs.n; k++) { ix->sub[ms[k]].genome_count += Q->sub[k].genome_count; ix->sub[ms[k]].total_length += Q->sub[k].total_length; }
+                for (int32_t k = 0; k < Q->fams.n; k++) { ix->fam[mf[k]].genome_count += Q->fam[k].genome_count; ix->fam[mf[k]].total_length += Q->fam[k].total_length; }
+                for (int32_t k = 0; k < Q->clas.n; k++) { ix->cla[ml[k]].genome_count += Q->cla[k].genome_count; ix->cla[ml[k]].total_length += Q->cla[k].total_length; }
+            }
+            for (long long i = 0; i < Q->nraw; i++) {
+                raw_el el = Q->raw[i];
+                el.chrom = mc[el.chrom]; el.sub = ms[el.sub]; el.fam = mf[el.fam]; el.cla = ml[el.cla];
+                raw[o++] = el;
+            }
+            free(mc); free(ms); free(mf); free(ml);
+        }
+    }
+    for (int t = 0; t < T; t++) {
+        rmsk_piece *Q = &P[t];
+        if (Q->pass == 1 && (Q->chroms.slot)) { itx_strtab_free(&Q->chroms); itx_strtab_free(&Q->subs); itx_strtab_free(&Q->fams); itx_strtab_free(&Q->clas); }
+        free(Q->raw); free(Q->chrom_size); free(Q->sub); free(Q->fam); free(Q->cla);
+    }
+    free(P); free(th); free(buf);
+    *raw_out = raw; *nraw_out = total; *last_row = rows - 1; *kept_out = kept;
+    return rc;
+}
+
 int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const char *rep_sizes, const char *rmsk,
                         int filter_field, const char *filter_name, char err[ITX_ERRLEN]) {
     int rc;
@@ -176,70 +369,19 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
     if ((rc = load_name_int(rep_sizes, &ix->repsize, &ix->repsize_val, err))) return rc;
     if (filter_field != 0 && (filter_field < 0 || filter_field > 16 || !filter_name)) { snprintf(err, ITX_ERRLEN, "bad filter field %d", filter_field); return ITX_EARG; }
 
-    FILE *f = is_directory(rmsk) ? NULL : fopen(rmsk, "r");
-    if (!f) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", rmsk, strerror(errno)); return ITX_EIO; }
-    static const size_t IOBUF = 1 << 22; char *iobuf = (char *)malloc(IOBUF); setvbuf(f, iobuf, _IOFBF, IOBUF);
-    raw_el *raw = NULL; long long nraw = 0, rawcap = 0;
-    int32_t subcap = 0, famcap = 0, clacap = 0, chromcap = 0;
-    long long row = -1, kept = 0; long ln = 0;
-    char *line = NULL; size_t lc = 0;
-    rc = ITX_OK;
-    while (getline(&line, &lc, f) >= 0) {
-        ln++;
-        if (line[0] == '#') continue;
-        char *w[17]; int nw = split_white(line, w, 17);
-        if (nw == 0) continue;
-        if (nw < 17) { snprintf(err, ITX_ERRLEN, "Expecting 17 words line %ld of %s got %d", ln, rmsk, nw); rc = ITX_EFORMAT; break; }
-        row++;
-        if (filter_field != 0 && strcmp(filter_name, w[filter_field]) != 0) continue;
-        kept++;
-        raw_el e;
-        e.cs = (uint32_t)strtol(w[9][0] == '+' ? w[13] : w[15], NULL, 0);
-        e.ce = (uint32_t)strtol(w[14], NULL, 0);
-        e.start = (int32_t)(uint32_t)strtol(w[6], NULL, 0);
-        e.end = (int32_t)(uint32_t)strtol(w[7], NULL, 0);
-        e.row = (uint32_t)row;
-        int32_t c = itx_strtab_find(&ix->chroms, w[5]);
-        if (c < 0) {
-            int size = name_int_or(&ix->chromsize, ix->chromsize_val, w[5], 0);
-            if (size == 0) continue;                       /* chromosome not in the size file: row dropped */
-            if (size < 0) { snprintf(err, ITX_ERRLEN, "bad range %d,%d in binKeeperNew", 0, size); rc = ITX_EFORMAT; break; }
-            c = itx_strtab_add(&ix->chroms, w[5]);
-            if (c >= chromcap) { chromcap = chromcap ? chromcap * 2 : 64; ix->chrom_size = (int32_t *)realloc(ix->chrom_size, sizeof(int32_t) * (size_t)chromcap); }
-            ix->chrom_size[c] = size;
-        }
-        int32_t bin;
-        if (e.start < 0 || e.end > ix->chrom_size[c] || e.start > e.end) {
-            snprintf(err, ITX_ERRLEN, "(%d %d) out of range (%d %d) in binKeeperAdd", e.start, e.end, 0, ix->chrom_size[c]); rc = ITX_EFORMAT; break;
-        }
-        if (bin_level(e.start, e.end, &bin) < 0) { snprintf(err, ITX_ERRLEN, "start %d, end %d out of range in findBin (max is 2Gb)", e.start, e.end); rc = ITX_EFORMAT; break; }
-        e.chrom = c;
-        int32_t ns0 = ix->subs.n, nf0 = ix->fams.n, nc0 = ix->clas.n;
-        e.sub = itx_strtab_intern(&ix->subs, w[10]);
-        e.cla = itx_strtab_intern(&ix->clas, w[11]);
-        e.fam = itx_strtab_intern(&ix->fams, w[12]);
-        ix->sub = grow_groups(ix->sub, &subcap, ix->subs.n);
-        ix->fam = grow_groups(ix->fam, &famcap, ix->fams.n);
-        ix->cla = grow_groups(ix->cla, &clacap, ix->clas.n);
-        if (ix->subs.n != ns0) { ix->sub[e.sub].first_fam = e.fam; ix->sub[e.sub].first_cla = e.cla; }
-        if (ix->fams.n != nf0) { ix->fam[e.fam].first_cla = e.cla; }
-        (void)nc0;
-        if (ix->stat_mode) {
-            uint64_t len = (uint32_t)(e.end - e.start);
-            ix->sub[e.sub].genome_count++; ix->sub[e.sub].total_length += len;
-            ix->fam[e.fam].genome_count++; ix->fam[e.fam].total_length += len;
-            ix->cla[e.cla].genome_count++; ix->cla[e.cla].total_length += len;
-        }
-        if (nraw == rawcap) { rawcap = rawcap ? rawcap * 2 : (1 << 16); raw = (raw_el *)realloc(raw, sizeof(raw_el) * (size_t)rawcap); }
-        raw[nraw++] = e;
-    }
-    free(line); fclose(f); free(iobuf);
-    if (rc) { free(raw); return rc; }
+    /* the table is read whole and parsed by all host threads: the file is cut at line ends into one piece per thread,
+     * each piece is parsed into local tables (names in order of first appearance, counters, elements), and the pieces
+     * are merged in file order, which reproduces the ids a sequential pass would have given */
+    raw_el *raw = NULL; long long nraw = 0, row = -1, kept = 0;
+    const int timing = getenv("ITX_TIMING") != NULL; struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+#define ITX_LAP(what) do { if (timing) { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); fprintf(stderr, "[itx timing] index: %s at %.0f ms\n", what, (t1.tv_sec - ts0.tv_sec) * 1e3 + (t1.tv_nsec - ts0.tv_nsec) * 1e-6); } } while (0)
+    if ((rc = rmsk_parse_parallel(ix, rmsk, filter_field, filter_name, &raw, &nraw, &row, &kept, err))) { free(raw); return rc; }
     if (filter_field != 0 && kept <= 0) {
         snprintf(err, ITX_ERRLEN, "* No repeats found related to [%s], typo? or specify wrong repName/Class/Family filter?", filter_name);
         free(raw); return ITX_EFORMAT;
     }
     ix->n_rows = row + 1; ix->n_elem = nraw;
+    ITX_LAP("rmsk parsed and merged");
 
     /* order by (chrom, start, row) unless the file already is */
     int sorted = 1;
@@ -268,6 +410,7 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
         ix->row2el[e->row] = i;
     }
     free(raw);
+    ITX_LAP("sorted table laid out");
     if (nraw >= 0xffffffffLL) { snprintf(err, ITX_ERRLEN, "more than 2^32 rmsk rows are not supported"); return ITX_ENOTSUP; }
     /* position buckets: first element with start >= (b << ITX_BSH), per chromosome */
     ix->chrom_bucket = (long long *)calloc((size_t)nchrom + 1, sizeof(long long));
@@ -309,6 +452,7 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
         ix->cinfo[c].size = ix->chrom_size[c]; ix->cinfo[c].n = (uint32_t)(ix->chrom_off[c + 1] - ix->chrom_off[c]);
     }
     itx_strtab_free(&fold);
+    ITX_LAP("buckets and subfamily tables done");
     return ITX_OK;
 }
 
