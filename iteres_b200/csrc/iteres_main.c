@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <pthread.h>
 #include <unistd.h>
 #include "../../include/iteres_gpu.h"
 
@@ -83,8 +84,8 @@ static int cpgfilter_usage(void) { return print_usage("Filter CpG statistics on 
     "iteres cpgfilter [options] <chromosome size file> <repeat size file> <rmsk.txt> <CpG bedGraph file>", CPGFILTER_OPTS); }
 
 static void use_device(void) {
+    /* the device itself is first touched by itx_index_build (which fails with "no usable CUDA device" when there is none) */
     const char *d = getenv("ITERES_DEVICE");
-    if (itx_device_count() <= 0) die("no CUDA device found: this build of iteres runs its hot path on the GPU only");
     if (d && itx_set_device(atoi(d)) != ITX_OK) die("cannot use CUDA device %s", d);
 }
 static void done_in(time_t t0) { fprintf(stderr, "* Done, time used %.0f seconds.\n", difftime(time(NULL), t0)); }
@@ -99,7 +100,15 @@ static int pick_filter(char *name, char *cls, char *fam, char **subfam) {
     return field;
 }
 
+static double lap_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+static double g_t0;
+#define LAP(what) do { if (getenv("ITX_TIMING")) fprintf(stderr, "[itx timing] cli: %s at %.0f ms\n", what, lap_ms() - g_t0); } while (0)
+
+typedef struct { const char *wig, *sizes, *out; int rc; char err[ITX_ERRLEN]; } bw_job;
+static void *bw_run(void *arg) { bw_job *j = (bw_job *)arg; j->rc = itx_wig_to_bigwig(j->wig, j->sizes, j->out, j->err); return NULL; }
+
 static int main_stat(int argc, char **argv) {
+    g_t0 = lap_ms();
     itx_scan_opts o; itx_scan_opts_default(&o);
     int c, keep_wig = 0, sam = 0, bed = 0, bedu = 0; unsigned int norm = 0, norm2 = 0; char *prefix = NULL;
     time_t t0 = time(NULL);
@@ -141,22 +150,33 @@ static int main_stat(int argc, char **argv) {
     itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
     if (!ix) die("%s", err);
     fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    LAP("index built");
     fprintf(stderr, "* Parsing the SAM/BAM file\n");
     if (itx_scan_alignments(ix, bams, &o, cnt, err) != ITX_OK) die("%s", err);
+    LAP("alignments scanned");
     fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Writing stats and Wig file\n");
     char *wig = fmt_alloc("%s.iteres.wig", prefix), *wigu = fmt_alloc("%s.iteres.unique.wig", prefix);
     char *f_sub = fmt_alloc("%s.iteres.subfamily.stat", prefix), *f_fam = fmt_alloc("%s.iteres.family.stat", prefix), *f_cla = fmt_alloc("%s.iteres.class.stat", prefix);
+    LAP("counters on the host");
     if (itx_write_stat(ix, f_sub, wig, f_fam, f_cla, wigu, cnt[NIDX[norm]], cnt[NIDX2[norm2]]) != ITX_OK) die("Can't write the stat files for prefix %s", prefix);
+    LAP("tables and wiggles written");
     fprintf(stderr, "* Generating bigWig files\n");
-    if (itx_wig_to_bigwig(wig, rep_sizes, fmt_alloc("%s.iteres.bigWig", prefix), err) != ITX_OK) die("%s", err);
-    if (itx_wig_to_bigwig(wigu, rep_sizes, fmt_alloc("%s.iteres.unique.bigWig", prefix), err) != ITX_OK) die("%s", err);
+    {   /* the two conversions are independent: side by side */
+        bw_job ja = {wig, rep_sizes, fmt_alloc("%s.iteres.bigWig", prefix), 0, {0}}, jb = {wigu, rep_sizes, fmt_alloc("%s.iteres.unique.bigWig", prefix), 0, {0}};
+        pthread_t tb; const int threaded = pthread_create(&tb, NULL, bw_run, &jb) == 0;
+        bw_run(&ja);
+        if (threaded) pthread_join(tb, NULL); else bw_run(&jb);
+        if (ja.rc != ITX_OK) die("%s", ja.err);
+        if (jb.rc != ITX_OK) die("%s", jb.err);
+    }
+    LAP("bigWig files written");
     fprintf(stderr, "* Preparing report file\n");
     char *rep = fmt_alloc("%s.iteres.report", prefix);
     if (itx_write_report(rep, cnt, o.mapQ, "ALL") != ITX_OK) die("Can't open %s to write", rep);
     if (!keep_wig) { unlink(wig); unlink(wigu); }
-    itx_index_free(ix);
+    LAP("done");                          /* the process ends here: the index is not torn down piece by piece */
     done_in(t0);
     return 0;
 }

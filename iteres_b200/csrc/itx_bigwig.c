@@ -21,6 +21,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #define BW_SIG 0x888FFC26u
@@ -76,7 +78,16 @@ static void reduce_sections(const bw_section *sec, size_t nsec, const bw_chrom *
         const bw_section *S = &sec[i]; int start = (int)S->start;
         for (uint32_t k = 0; k < S->count; k++) {
             int size = (int)S->span; double val = S->val[k], sum = size * val, sq = sum * val;
-            sum_add(out, S->chrom_id, chroms[S->chrom_id].size, (uint32_t)start, (uint32_t)start + S->span, (uint32_t)size, val, val, sum, sq, reduction);
+            bw_sum *t = out->n ? &out->v[out->n - 1] : NULL;
+            const uint32_t a = (uint32_t)start, b = (uint32_t)start + S->span;
+            if (t && t->chrom_id == S->chrom_id && a >= t->start && b <= t->end && b <= chroms[S->chrom_id].size && a < b) {
+                /* the item lies inside the running summary: the same five updates sum_add makes, its overlap factor being exactly 1 */
+                t->valid = (uint32_t)(t->valid + 1.0 * (uint32_t)size);
+                if (t->minv > val) t->minv = (float)val;
+                if (t->maxv < val) t->maxv = (float)val;
+                t->sum = (float)(t->sum + 1.0 * sum);
+                t->sumsq = (float)(t->sumsq + 1.0 * sq);
+            } else sum_add(out, S->chrom_id, chroms[S->chrom_id].size, a, b, (uint32_t)size, val, val, sum, sq, reduction);
             start += (int)S->step;
         }
     }
@@ -224,6 +235,23 @@ static uint64_t write_summaries(FILE *f, bw_sumlist *L, uint32_t block, uint32_t
     return index_off;
 }
 
+typedef struct { bw_section *sec; size_t nsec; size_t next; uint8_t **out; uLongf *out_len; } bw_zjob;
+static void *bw_zworker(void *arg) {
+    bw_zjob *J = (bw_zjob *)arg;
+    for (;;) {
+        const size_t i0 = __atomic_fetch_add(&J->next, 16, __ATOMIC_RELAXED);
+        if (i0 >= J->nsec) break;
+        for (size_t i = i0; i < i0 + 16 && i < J->nsec; i++) {
+            const bw_section *S = &J->sec[i]; const uint32_t n = 24 + 4u * S->count; uint8_t *buf = (uint8_t *)malloc(n);
+            memcpy(buf, &S->chrom_id, 4); memcpy(buf + 4, &S->start, 4); memcpy(buf + 8, &S->end, 4); memcpy(buf + 12, &S->step, 4); memcpy(buf + 16, &S->span, 4);
+            buf[20] = 3; buf[21] = 0; memcpy(buf + 22, &S->count, 2); memcpy(buf + 24, S->val, 4u * S->count);      /* type 3 = fixedStep */
+            const uLong cap = (uLong)(1.001 * n + 13); uint8_t *cmp = (uint8_t *)malloc(cap + 64); uLongf cl = cap;
+            compress(cmp, &cl, buf, n);
+            J->out[i] = cmp; J->out_len[i] = cl; free(buf);
+        }
+    }
+    return NULL;
+}
 static int sec_cmp(const void *va, const void *vb) {
     const bw_section *a = (const bw_section *)va, *b = (const bw_section *)vb;
     int d = strcmp(a->chrom, b->chrom);
@@ -287,7 +315,12 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
         }
         if (!in_section) { snprintf(err, ITX_ERRLEN, "Unrecognized line %ld of %s:\n%s\n", lineno, wig_path, s); rc = ITX_EFORMAT; break; }
         char *w = s; while (*s && !is_space(*s)) s++; *s = 0;
-        char *endp; double v = strtod(w, &endp);
+        char *endp; double v;
+        {   /* wiggles of `stat` are plain counts: digits only take the short road, everything else strtod */
+            const char *q = w; uint64_t acc = 0; int nd = 0;
+            while (*q >= '0' && *q <= '9' && nd < 15) { acc = acc * 10 + (uint64_t)(*q - '0'); q++; nd++; }
+            if (nd && !*q) { v = (double)acc; endp = (char *)q; } else v = strtod(w, &endp);
+        }
         if (!*w || *endp) { snprintf(err, ITX_ERRLEN, "Expecting double field 1 line %ld of %s, got %s", lineno, wig_path, w); rc = ITX_EFORMAT; break; }
         if (pos + (uint32_t)nv * step + span > cs) {
             snprintf(err, ITX_ERRLEN, "line %ld of %s: chromosome %s has %u bases, but item ends at %u", lineno, wig_path, chrom, cs, pos + (uint32_t)nv * step + span);
@@ -381,15 +414,19 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
         write_chrom_tree(f, chroms, nchrom, nchrom < block ? nchrom : block, max_name);
         data_off = (uint64_t)ftell(f);
         { uint64_t sc = nsec; W(f, sc); }
-        for (size_t i = 0; i < nsec; i++) {
-            bw_section *S = &sec[i]; uint32_t n = 24 + 4u * S->count; uint8_t *buf = (uint8_t *)malloc(n), type = 3, res8 = 0;
-            S->file_off = (uint64_t)ftello(f);
-            memcpy(buf, &S->chrom_id, 4); memcpy(buf + 4, &S->start, 4); memcpy(buf + 8, &S->end, 4); memcpy(buf + 12, &S->step, 4); memcpy(buf + 16, &S->span, 4);
-            buf[20] = type; buf[21] = res8; memcpy(buf + 22, &S->count, 2); memcpy(buf + 24, S->val, 4u * S->count);
-            uLong cap = (uLong)(1.001 * n + 13); uint8_t *cmp = (uint8_t *)malloc(cap + 64); uLongf cl = cap;
-            compress(cmp, &cl, buf, n); fwrite(cmp, 1, cl, f);
-            if (n > unc_buf) unc_buf = n;
-            free(buf); free(cmp);
+        {   /* the sections are compressed by all host threads (each one is an independent zlib stream), then written in order */
+            bw_zjob J; J.sec = sec; J.nsec = nsec; J.next = 0; J.out = (uint8_t **)calloc(nsec, sizeof(uint8_t *)); J.out_len = (uLongf *)calloc(nsec, sizeof(uLongf));
+            int T = (int)sysconf(_SC_NPROCESSORS_ONLN); if (T < 1) T = 1; if (T > 32) T = 32; if (nsec < 64) T = 1;
+            pthread_t th[32]; int started = 0;
+            for (int t = 1; t < T; t++) if (pthread_create(&th[started], NULL, bw_zworker, &J) == 0) started++;
+            bw_zworker(&J);
+            for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+            for (size_t i = 0; i < nsec; i++) {
+                sec[i].file_off = (uint64_t)ftello(f);
+                fwrite(J.out[i], 1, J.out_len[i], f); free(J.out[i]);
+                const uint32_t n = 24 + 4u * sec[i].count; if (n > unc_buf) unc_buf = n;
+            }
+            free(J.out); free(J.out_len);
         }
         index_off = (uint64_t)ftello(f);
         {

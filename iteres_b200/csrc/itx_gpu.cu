@@ -71,7 +71,9 @@ static int g_device = 0;
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 extern "C" int itx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
-extern "C" int itx_set_device(int device) { g_device = device; return cudaSetDevice(device) == cudaSuccess ? ITX_OK : ITX_ENODEV; }
+/* only noted here: the device is first touched by itx_index_build, where the driver start-up overlaps the table parse */
+extern "C" int itx_set_device(int device) { if (device < 0) return ITX_EARG; g_device = device; return ITX_OK; }
+static void *cuda_warm_up(void *arg) { (void)arg; if (cudaSetDevice(g_device) == cudaSuccess) cudaFree(0); return NULL; }
 extern "C" void *itx_dev_alloc(uint64_t bytes) { void *p = NULL; cudaSetDevice(g_device); if (cudaMalloc(&p, bytes) != cudaSuccess) return NULL; return p; }
 extern "C" void itx_dev_free(void *p) { cudaFree(p); }
 extern "C" int itx_dev_upload(void *dst, const void *src, uint64_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? ITX_OK : ITX_ENODEV; }
@@ -145,7 +147,12 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
     err[0] = 0;
     itx_index *ix = (itx_index *)calloc(1, sizeof(itx_index));
-    if (itx_host_index_load(ix, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err) != ITX_OK) { itx_host_index_free(ix); free(ix); return NULL; }
+    /* the CUDA driver and context come up on a second thread while this one parses rmsk.txt */
+    pthread_t warm; const bool warming = pthread_create(&warm, NULL, cuda_warm_up, NULL) == 0;
+    const int host_rc = itx_host_index_load(ix, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err);
+    if (warming) pthread_join(warm, NULL);
+    cudaGetLastError();
+    if (host_rc != ITX_OK) { itx_host_index_free(ix); free(ix); return NULL; }
     itx_cuda *cu = (itx_cuda *)calloc(1, sizeof(itx_cuda));
     ix->cu = cu; ix->device = cu->device = g_device;
     {

@@ -525,6 +525,19 @@ static void ensure_orders(struct itx_index *ix) {
 }
 #define LLU(x) ((unsigned long long)(x))
 
+/* n lines "%u\n": millions of them per wiggle file, so the digits are laid down by hand into a block buffer */
+static void put_u32_lines(FILE *f, const uint32_t *v, uint32_t n) {
+    char buf[1 << 16]; size_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (w + 12 > sizeof buf) { fwrite(buf, 1, w, f); w = 0; }
+        uint32_t x = v[i]; char t[10]; int k = 0;
+        do { t[k++] = (char)('0' + x % 10u); x /= 10u; } while (x);
+        while (k) buf[w++] = t[--k];
+        buf[w++] = '\n';
+    }
+    if (w) fwrite(buf, 1, w, f);
+}
+
 int itx_write_stat(itx_index *ix, const char *subfam_stat, const char *wig, const char *fam_stat,
                    const char *class_stat, const char *wig_unique, uint64_t N, uint64_t NU) {
     if (!ix->stat_mode) return ITX_EARG;
@@ -544,7 +557,7 @@ int itx_write_stat(itx_index *ix, const char *subfam_stat, const char *wig, cons
             fprintf(fw, "fixedStep chrom=%s start=1 step=1 span=1\n", ix->subs.names[s]);
             fprintf(fu, "fixedStep chrom=%s start=1 step=1 span=1\n", ix->subs.names[s]);
             const uint32_t *a = ix->bp + ix->sub_bp_off[s], *u = ix->bp_u + ix->sub_bp_off[s];
-            for (uint32_t m = 0; m < L; m++) { fprintf(fw, "%u\n", a[m]); fprintf(fu, "%u\n", u[m]); }
+            put_u32_lines(fw, a, L); put_u32_lines(fu, u, L);           /* "%u\n" per consensus base */
         }
     }
     fclose(fw); fclose(fs); fclose(fu);

@@ -45,7 +45,7 @@ def test_no_device_means_error_not_fallback(tmp_path):
     cli = os.path.join(ROOT, "iteres_b200", "csrc", "iteres")
     p = subprocess.run([cli, "stat", "-o", str(tmp_path / "x")] + [os.path.join(gold, f) for f in ("chrom.sizes", "rep.sizes", "rmsk.txt", "reads.bam")],
                        capture_output=True, text=True)
-    assert p.returncode == 255 and "no CUDA device" in p.stderr
+    assert p.returncode == 255 and "no usable CUDA device" in p.stderr
 
 
 def test_product_never_touches_the_oracle():
