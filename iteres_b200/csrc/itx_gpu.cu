@@ -34,9 +34,11 @@ struct itx_cuda {
     void *d_cpg_u32; size_t n_cpg_u32;   /* grp_cpg, el_cpg */
     void *d_cpg_f64; size_t n_cpg_f64;   /* grp_cpg_score, bp_cpg, el_cpg_score */
     void *d_misc;                        /* tid_unknown_seen[ITX_MAX_TID_SEEN] + status[8] */
+    void *d_D;                           /* D itself in global memory, for the out-of-line device functions (the kernels read their by-value copy) */
     uint32_t *d_bp, *d_bp_u;             /* prefix-summed coverage (finalize output) */
     /* scan workspace */
-    uint32_t C, S; uint64_t cap_chunks;
+    uint32_t C, S; uint64_t cap_chunks;                      /* spans the tuple buffers hold (one launch group of the tuple path) */
+    uint64_t cap_log;                                         /* spans the entry / exit logs hold (one launch group of k_scan, >= cap_chunks) */
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
@@ -93,7 +95,7 @@ static void cuda_free_all(itx_cuda *cu) {
     cudaSetDevice(cu->device);
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
-                    cu->d_misc, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
+                    cu->d_misc, cu->d_D, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
@@ -214,6 +216,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         D.grp_cpg = (uint32_t *)cu->d_cpg_u32; D.el_cpg = D.grp_cpg + ng;
         D.grp_cpg_score = (double *)cu->d_cpg_f64; D.bp_cpg = D.grp_cpg_score + ng; D.el_cpg_score = D.bp_cpg + ix->bp_len;
         D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
+        CKN(cudaMalloc(&cu->d_D, sizeof D)); CKN(cudaMemcpy(cu->d_D, &D, sizeof D, cudaMemcpyHostToDevice));
         if (zero_counters(ix, err)) goto fail;
     }
     ix->tune_chunk = 65536; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
@@ -272,17 +275,21 @@ extern "C" void itx_bam_header_free(itx_bam_header *h) {
 }
 
 /* ------------------------------------------------------------------ scan machinery */
-static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
+/* window_bytes: the largest launch group of the tuple path (16 bytes of tuple per 36 bytes of stream); log_bytes: the
+ * largest launch group of k_scan, which only needs the spans' entry / exit logs and so can cover a whole resident stream */
+static int ensure_work(itx_index *ix, uint64_t window_bytes, uint64_t log_bytes, char *err) {
     itx_cuda *cu = ix->cu;
     uint32_t C = ix->tune_chunk, S = C / 36 + 1;
     uint64_t need = window_bytes / C + 2;
+    uint64_t need_log = (log_bytes > window_bytes ? log_bytes : window_bytes) / C + 2;
     bool want_trace = ix->trace_cap != 0 || cu->ord_cap != 0;
     const uint64_t trace_need = ix->trace_cap > cu->ord_cap ? ix->trace_cap : cu->ord_cap;
-    if (cu->d_tuples && cu->C == C && cu->cap_chunks >= need && (!want_trace || cu->d_rec_base) && (!cu->want_sel || cu->d_sel)) goto trace;
+    if (cu->d_tuples && cu->C == C && cu->cap_chunks >= need && cu->cap_log >= need_log && (!want_trace || cu->d_rec_base) && (!cu->want_sel || cu->d_sel)) goto trace;
     cudaFree(cu->d_tuples); cudaFree(cu->d_entry); cudaFree(cu->d_exit); cudaFree(cu->d_nrec); cudaFree(cu->d_rec_base); cudaFree(cu->d_sel);
     cu->d_tuples = NULL; cu->d_entry = cu->d_exit = cu->d_rec_base = NULL; cu->d_nrec = NULL; cu->d_sel = NULL;
-    cu->C = C; cu->S = S; cu->cap_chunks = need;
+    cu->C = C; cu->S = S; cu->cap_chunks = need; cu->cap_log = need_log;
     CK(cudaMalloc((void **)&cu->d_tuples, need * S * sizeof(itx_tuple)));
+    need = need_log;                                          /* the per-span arrays below are sized for the logs */
     CK(cudaMalloc((void **)&cu->d_entry, need * 8)); CK(cudaMalloc((void **)&cu->d_exit, need * 8)); CK(cudaMalloc((void **)&cu->d_nrec, need * 4));
     {
         CK(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_DECODE_SMEM));
@@ -291,7 +298,7 @@ static int ensure_work(itx_index *ix, uint64_t window_bytes, char *err) {
         cu->decode_ctas = nb > 0 ? nb : 1;
     }
     if (want_trace) CK(cudaMalloc((void **)&cu->d_rec_base, need * 8));
-    if (cu->want_sel) CK(cudaMalloc((void **)&cu->d_sel, need * S * sizeof(long long)));
+    if (cu->want_sel) CK(cudaMalloc((void **)&cu->d_sel, cu->cap_chunks * S * sizeof(long long)));
 trace:
     if (want_trace && (!cu->d_trace || cu->trace_cap < trace_need)) {
         cudaFree(cu->d_trace); cu->d_trace = NULL;
@@ -410,7 +417,10 @@ static int ordered_drain(scan_ctx *sc, uint64_t avail, char *err) {
     return ITX_OK;
 }
 
-static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err) {
+/* window: bytes per launch group; resident != 0: the whole stream is already on the device, so k_scan (which writes no
+ * tuples) takes it in ONE launch group unless itx_tune set a window -- one tail instead of one per GiB */
+#define ITX_DEFAULT_WINDOW (1ull << 30)
+static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err, int resident = 0) {
     itx_cuda *cu = ix->cu;
     memset(sc, 0, sizeof *sc);
     sc->ix = ix; sc->h = h; sc->b = d_bam; sc->len = len; sc->o = dev_opts(o);
@@ -422,7 +432,9 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
         if (window > (256ull << 20)) window = 256ull << 20;         /* the host pass buffers one launch group */
         cu->ord_cap = window / 37 + (uint64_t)ix->tune_chunk / 37 * 4 + 4096;    /* a record is at least 37 bytes long */
     } else cu->ord_cap = 0;
-    int rc = ensure_work(ix, window, err); if (rc) return rc;
+    uint64_t log_window = window;
+    if (resident && !sc->ordered && ix->tune_window == ITX_DEFAULT_WINDOW && len > window) log_window = len < (1ull << 40) ? len : (1ull << 40);
+    int rc = ensure_work(ix, window, log_window, err); if (rc) return rc;
     if (sc->ordered && (rc = ordered_begin(sc, o, err))) return rc;
     sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
     sc->k_next = sc->k_first;
@@ -501,14 +513,16 @@ static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t ava
 /* the fused path: ONE kernel per launch group (k_scan); sign -1 takes a group's counts back */
 static bool fused_smem_hist(const scan_ctx *sc) {
     const itx_cuda *cu = sc->ix->cu;
-    return (sc->o.filter == 0 && cu->D.stat_mode) && ITX_DECODE_SMEM + hist_bytes(cu) + 1024 <= cu->smem_optin;
+    return (sc->o.filter == 0 && cu->D.stat_mode) && ITX_SCAN_SMEM_BASE + hist_bytes(cu) + 1024 <= cu->smem_optin;
 }
 static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, int sign) {
     itx_cuda *cu = sc->ix->cu;
-    itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len); P.D = cu->D; P.sign = sign; P.window = window;
+    itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len); P.D = cu->D; P.Dg = (const itx_dev_index *)cu->d_D; P.sign = sign; P.window = window;
     P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused; P.ticket = cu->d_fused + 1;
     const bool sh = fused_smem_hist(sc);
-    const size_t smem = ITX_DECODE_SMEM + (sh ? hist_bytes(cu) : 0);
+    const size_t smem = ITX_SCAN_SMEM_BASE + (sh ? hist_bytes(cu) : 0);
+    P.flags = ITX_SCAN_DEFAULT;
+    { const char *v = getenv("ITX_SCAN_FLAGS"); if (v) P.flags = (uint32_t)strtoul(v, NULL, 0); }      /* A/B switches: the counts do not depend on them */
     if (!cu->scan_ctas[sh]) {
         if (sh) { cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
         else { cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
@@ -526,7 +540,8 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
 static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
     while (sc->k_next < k_hi) {
-        uint64_t n64 = k_hi - sc->k_next; if (n64 > cu->cap_chunks - 1) n64 = cu->cap_chunks - 1;
+        const uint64_t cap = (sc->fused ? cu->cap_log : cu->cap_chunks) - 1;
+        uint64_t n64 = k_hi - sc->k_next; if (n64 > cap) n64 = cap;
         uint32_t n = (uint32_t)n64;
         if (sc->fused && sc->n_win >= ITX_MAX_WINDOWS) { snprintf(err, ITX_ERRLEN, "more than %d launch groups in one scan: raise the window with itx_tune", ITX_MAX_WINDOWS); return ITX_ENOTSUP; }
         if (sc->fused) {
@@ -554,7 +569,11 @@ static int fused_replay(scan_ctx *sc, uint32_t first, char *err) {
     itx_cuda *cu = sc->ix->cu;
     for (uint32_t w = first; w < sc->n_win; w++) launch_fused(sc, w, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, -1);
     CK(cudaMemcpyAsync(cu->d_carry, cu->d_carry_log + first, 8, cudaMemcpyDeviceToDevice, cu->stream));
-    for (uint32_t w = first; w < sc->n_win; w++) { int rc = launch_tuple_path(sc, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, err); if (rc) return rc; }
+    for (uint32_t w = first; w < sc->n_win; w++)              /* a k_scan launch group may be larger than the tuple buffers: in pieces */
+        for (uint64_t d = 0; d < sc->wins[w].n; d += cu->cap_chunks - 1) {
+            const uint64_t n = sc->wins[w].n - d < cu->cap_chunks - 1 ? sc->wins[w].n - d : cu->cap_chunks - 1;
+            int rc = launch_tuple_path(sc, sc->wins[w].k0 + d, (uint32_t)n, sc->wins[w].avail, sc->wins[w].len, err); if (rc) return rc;
+        }
     return ITX_OK;
 }
 static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
@@ -623,7 +642,7 @@ extern "C" int itx_scan_bam_device(itx_index *ix, const itx_bam_header *h, const
     CK(cudaSetDevice(ix->cu->device));
     memset(&ix->prof, 0, sizeof ix->prof);
     scan_ctx sc;
-    if ((rc = scan_begin(&sc, ix, h, (const uint8_t *)d_bam, len, o, ix->tune_window < len ? ix->tune_window : len, err))) return rc;
+    if ((rc = scan_begin(&sc, ix, h, (const uint8_t *)d_bam, len, o, ix->tune_window < len ? ix->tune_window : len, err, 1))) return rc;
     if ((rc = scan_window(&sc, sc.k_end, len, err))) return rc;
     return scan_end(&sc, cnt, err);
 }

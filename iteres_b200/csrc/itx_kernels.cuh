@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
             const uint32_t chrom = info & ITX_CHROM_MASK;
             if (live && chrom != ITX_CHROM_NONE) {
                 int32_t nhit; float tcov;
-                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov, &e);
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
                 if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
                     const unsigned long long p = lo + T.rec_off;
@@ -497,13 +497,35 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
 struct itx_scan_args {
     itx_decode_args A;                   /* stream, spans, reference table, options, entry / exit logs, carry, status, work[2] */
     itx_dev_index D;
+    const itx_dev_index *Dg;             /* the same in global memory: what the out-of-line functions are handed, so that D stays in the parameter bank */
     int32_t sign;                        /* +1: count; -1: take back what the same call counted */
     uint32_t window;                     /* index of this launch in the scan */
     unsigned long long *carry_log;       /* [window] the carry the window started from (the undo pass starts from it too) */
     uint32_t *first_bad;                 /* smallest window index whose chain check failed */
     uint32_t *ticket;                    /* CTAs done */
+    uint32_t flags;                      /* ITX_SCAN_* (A/B switches; every combination gives the same counts) */
 };
-#define ITX_SCAN_SMEM_BASE ITX_DECODE_SMEM
+#define ITX_SCAN_PREFETCH 1u             /* the next stage's bytes are asked into L2 while this stage is worked on */
+#define ITX_SCAN_DOMSIZE  2u             /* chain walk predicts with the span's dominant record size, so an odd record costs one step, not two */
+#define ITX_SCAN_WINDOW   4u             /* the 32 table entries under the warp's highest bucket end are staged in shared memory, metadata included */
+#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW)
+#define ITX_WIN 32u                      /* table entries per warp window */
+#define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
+#define ITX_SCAN_SMEM_BASE (ITX_DECODE_SMEM + ITX_DW * ITX_WIN_BYTES)
+
+__device__ __forceinline__ void itx_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+/* table loads of a walk: the warp's window when the index falls into it, global memory otherwise (same values either way) */
+struct itx_iv_window {
+    const itx_dev_index &D; const int4 *win; uint32_t base, n;
+    __device__ __forceinline__ itx_iv operator()(uint32_t i) const {
+        const uint32_t d = i - base;
+        if (d < n) { const int4 v = win[d]; itx_iv e; e.start = v.x; e.end = v.y; e.pmax = v.z; e.row = (uint32_t)v.w; return e; }
+        return itx_ld_iv(D, i);
+    }
+};
+
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
@@ -516,6 +538,9 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
     uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * STG) + w * ITX_POS_SLOTS;
     const uint32_t buf_s = itx_smem_addr(buf);
     const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * STG + ITX_DW * ITX_POS_SLOTS * 2u) + w * 8;
+    int4 *win_iv = reinterpret_cast<int4 *>(itx_smem + ITX_DECODE_SMEM + w * ITX_WIN_BYTES);
+    uint4 *win_meta = reinterpret_cast<uint4 *>(win_iv + ITX_WIN);
+    int2 *win_meta2 = reinterpret_cast<int2 *>(win_meta + ITX_WIN);
     uint32_t *sh_hist = reinterpret_cast<uint32_t *>(itx_smem + ITX_SCAN_SMEM_BASE);
     const uint32_t nh = SMEM_HIST ? 2u * (uint32_t)(D.n_sub + D.n_fam + D.n_cla) : 0u;
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
@@ -526,11 +551,12 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
     const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
     const unsigned long long one64 = neg ? ~0ull : 1ull;
     const bool stat = A.o.filter == 0 && D.stat_mode;
+    const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
+    itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for after the selection, for the reads that are counted */
     uint32_t c[13];
 #pragma unroll
     for (int k = 0; k < 13; k++) c[k] = 0;
     uint32_t parity = 0;
-    const itx_src_global G{A.b};
     bool dead = false;
     for (;;) {
         uint32_t i = 0;
@@ -539,34 +565,70 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
         if (i >= A.nchunks || dead) break;
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
         unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-        unsigned long long p;
-        if (i == 0) {
+        /* the span's first record start: known for the window's first span; otherwise guessed out of the span's first
+         * stage, which is needed in shared memory anyway */
+        unsigned long long p = ITX_OFF_NONE;
+        bool guess = i != 0;
+        if (!guess) {
             if (neg) p = P.carry_log[P.window];
             else { p = *A.carry; if (lane == 0) P.carry_log[P.window] = p; }
-        } else {
-            p = ITX_OFF_NONE;
-            for (unsigned long long base = lo; base < hi; base += 32) {
-                const unsigned long long q = base + lane;
-                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
-            }
+            if (lane == 0) A.entry[i] = p;
         }
-        if (lane == 0) A.entry[i] = p;
-        while (p < hi) {
-            const unsigned long long c_lo = lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
+        unsigned long long staged = ITX_OFF_NONE;             /* stream offset of the stage now in shared memory */
+        uint32_t nb = 0;
+        uint32_t szd = 0;                                      /* the span's dominant record size (0: none yet) */
+        for (;;) {
+            if (guess ? !(lo < hi) : !(p < hi)) { if (guess && lane == 0) A.entry[i] = p; break; }
+            const unsigned long long c_lo = guess ? lo : lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
             unsigned long long c_hi = c_lo + ITX_STAGE; if (c_hi > hi) c_hi = hi;
-            const unsigned long long rest = A.len - c_lo;
-            const uint32_t nb = rest > STG ? STG : (uint32_t)rest;
-            const uint32_t bytes = (nb + 15u) & ~15u;
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                itx_mbar_expect_tx(bar_s, bytes);
-                itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+            if (staged != c_lo) {
+                /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream) */
+                const unsigned long long rest = A.len - c_lo;
+                nb = rest > STG ? STG : (uint32_t)rest;
+                const uint32_t bytes = (nb + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */
+                __syncwarp();                                  /* every lane is done reading the previous stage */
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    itx_mbar_expect_tx(bar_s, bytes);
+                    itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+                    /* what the span's next stage adds to this one, on its way into L2 meanwhile */
+                    if (f_prefetch && c_lo + ITX_STAGE < hi && c_lo + STG + ITX_STAGE <= A.len) itx_prefetch_l2(A.b + c_lo + STG, ITX_STAGE);
+                }
+                if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
+                parity ^= 1u;
+                staged = c_lo;
             }
-            if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
-            parity ^= 1u;
+            if (guess) {
+                /* itx_plausible2's test, 32 offsets per step: the core of every offset comes out of the stage with plain
+                 * shared-memory loads and is tested without branches; the second record is looked at for the survivors */
+                const itx_src_stage S0{buf, A.b, lo, nb};
+                for (unsigned long long base = lo; base < hi; base += 32) {
+                    const unsigned long long q = base + lane;
+                    bool ok = false;
+                    if (q < hi && q + 36 <= A.len) {
+                        const uint32_t d = (uint32_t)(q - lo);
+                        uint32_t x[9], lq; uint64_t nx, nx2;
+                        if (base - lo + 32u + 40u <= nb) {                /* warp-uniform: every lane's core lies in the stage */
+                            const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
+                            uint32_t wv[10];
+#pragma unroll
+                            for (int k = 0; k < 10; k++) wv[k] = wq[k];
+#pragma unroll
+                            for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
+                        } else S0.core(q, x);
+                        ok = itx_plausible_core(x, q, A.len, A.n_ref, &lq, &nx);
+                        if (ok) ok = S0.u8(q + 36 + lq - 1) == 0 && (nx == A.len || itx_plausible(S0, nx, A.len, A.n_ref, &nx2));
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                    if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
+                }
+                if (lane == 0) A.entry[i] = p;
+                guess = false;
+                continue;
+            }
+            /* the chain of this stage, out of shared memory.  Lane 0 holds the record at q; lane k >= 1 looks where record k
+             * would start if records 1.. had the dominant size, and the run of lanes that find that size there is accepted
+             * in one step (each accepted start is the previous record's start + its verified size: the exact chain). */
             uint32_t n = 0, ended = 0;
             uint32_t q = (uint32_t)(p - c_lo);
             {
@@ -578,19 +640,21 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                     if (q + 36u > room32) { ended = 1; break; }
                     const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
                     const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
-                    const uint32_t sz = bs0 + 4u;
-                    if ((int32_t)bs0 < 32 || q + sz < q || q + sz > room32) { ended = 1; break; }
-                    const unsigned long long pk = (unsigned long long)q + (unsigned long long)lane * sz;
-                    bool same = false;
-                    if (pk < qh && pk + sz <= room32) {
+                    const uint32_t sz0 = bs0 + 4u;
+                    if ((int32_t)bs0 < 32 || q + sz0 < q || q + sz0 > room32) { ended = 1; break; }
+                    const uint32_t szp = szd ? szd : sz0;
+                    const unsigned long long pk = lane == 0 ? (unsigned long long)q : (unsigned long long)q + sz0 + (unsigned long long)(lane - 1u) * szp;
+                    bool same = lane == 0;
+                    if (lane != 0 && pk < qh && pk + szp <= room32) {
                         const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + ((uint32_t)pk & ~3u));
-                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) == bs0;
+                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) + 4u == szp;
                     }
-                    const uint32_t m = __ballot_sync(0xffffffffu, same);
+                    const uint32_t m = __ballot_sync(0xffffffffu, same);           /* bit 0 is always set */
                     const uint32_t run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     if (lane < run && n + lane < ITX_POS_SLOTS) pos[n + lane] = (uint16_t)pk;
                     n += run;
-                    q += run * sz;
+                    q += sz0 + (run - 1u) * szp;
+                    szd = (f_dom && run >= 2u) ? szp : 0u;
                     if (q > av32 && lane == 0) atomicOr(&A.status[0], 2u);
                 }
             }
@@ -600,10 +664,11 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                 const uint32_t j = j0 + lane; const bool valid = j < n;
                 itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
                 unsigned long long rp = 0;
+                uint32_t x[9];
                 if (valid) {
                     rp = c_lo + pos[j];
-                    uint32_t x[9]; S.core(rp, x);
-                    T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, A.o);
+                    S.core(rp, x);
+                    T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, o_dec);
                 }
                 const uint32_t info = T.info;
                 const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
@@ -619,15 +684,37 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                 if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
                 long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
                 const uint32_t chrom = info & ITX_CHROM_MASK;
-                if (frag && chrom != ITX_CHROM_NONE) {
-                    int32_t nhit; float tcov;
-                    sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nhit, &tcov, &e);
+                itx_query Q; Q.fs = Q.fe = 0; Q.lo = Q.top = 0;
+                const bool q_ok = frag && chrom != ITX_CHROM_NONE && itx_query_open(D, (int32_t)chrom, T.start, T.end, &Q);
+                /* the table window of this round: the ITX_WIN entries below the highest bucket end any lane starts from
+                 * (coordinate-sorted reads walk the same few entries), loaded once, coalesced, with their metadata */
+                uint32_t wbase = 0, wn = 0;
+                if (f_win) {
+                    const uint32_t tmax = __reduce_max_sync(0xffffffffu, q_ok ? Q.top : 0u);
+                    if (tmax) {
+                        wbase = tmax > ITX_WIN ? tmax - ITX_WIN : 0u; wn = tmax - wbase;
+                        __syncwarp();                          /* the previous round's readers are done */
+                        if (lane < wn) {
+                            win_iv[lane] = __ldg(reinterpret_cast<const int4 *>(D.iv + wbase + lane));
+                            if (stat) {
+                                win_meta[lane] = __ldg(reinterpret_cast<const uint4 *>(D.meta + wbase + lane));
+                                win_meta2[lane] = __ldg(reinterpret_cast<const int2 *>(D.meta2 + wbase + lane));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (q_ok) {
+                    int32_t nhit = 0; float tcov = 0.0f;
+                    sel = itx_select_walk(D, *P.Dg, Q, itx_iv_window{D, win_iv, wbase, wn}, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
                     if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-                    if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
-                        uint32_t x[9]; S.core(rp, x);
-                        uint32_t bad = 0;
-                        if (itx_mapped_to_diff_subfam(D, S, rp, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
-                        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+                    if (sel >= 0 && A.o.diffSubfam) {
+                        uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
+                        if (itx_aux_find(S, a0, aend, 'X', 'A')) {
+                            uint32_t bad = 0;
+                            if (itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                            if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+                        }
                     }
                 }
                 const bool counted = sel >= 0 && !diffsub;
@@ -636,8 +723,12 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                 c[9] += __popc(m_cnt); c[10] += __popc(m_cnt & m_uniq);
                 if (counted) {
                     if (stat) {
-                        const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
-                        const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+                        const uint32_t wd = (uint32_t)sel - wbase;
+                        uint4 mv; int2 m2v;
+                        if (wd < wn) { mv = win_meta[wd]; m2v = win_meta2[wd]; }
+                        else { mv = __ldg(reinterpret_cast<const uint4 *>(D.meta + sel)); m2v = __ldg(reinterpret_cast<const int2 *>(D.meta2 + sel)); }
+                        itx_meta m; m.cons_start = mv.x; m.cons_end = mv.y; m.row = mv.z; m.sub = mv.w;
+                        const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2v.x), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2v.y);
                         if (SMEM_HIST) {
                             atomicAdd(&sh_hist[hs], 1u); atomicAdd(&sh_hist[hf], 1u); atomicAdd(&sh_hist[hc], 1u);
                             if (uniq) { atomicAdd(&sh_hist[hs + 1], 1u); atomicAdd(&sh_hist[hf + 1], 1u); atomicAdd(&sh_hist[hc + 1], 1u); }
@@ -735,7 +826,7 @@ __global__ void k_query(const itx_dev_index D, int32_t chrom, const uint32_t *st
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int32_t nh; float tcov; itx_iv e; e.row = 0;
-    long long sel = itx_find_select(D, chrom, start[i], end[i], &nh, &tcov, &e);
+    long long sel = itx_find_select(D, chrom, start[i], end[i], min_cov, &nh, &tcov, &e);
     if (sel >= 0 && tcov < min_cov) sel = -1;
     sel_row[i] = sel >= 0 ? (int32_t)e.row : -1;
     if (n_hits) n_hits[i] = nh;

@@ -132,6 +132,20 @@ ITX_HD bool itx_plausible(const Src &S, uint64_t p, uint64_t len, int32_t n_ref,
     *next = p + 4 + bs;
     return true;
 }
+/* The same test on a core that is already in registers (x as S.core() gives it): no early exits, so a warp that tests 32
+ * offsets at once stays converged; only the qname terminator is left to the caller (it needs one more byte: *lq_out). */
+ITX_HD bool itx_plausible_core(const uint32_t x[9], uint64_t p, uint64_t len, int32_t n_ref, uint32_t *lq_out, uint64_t *next) {
+    const uint32_t bs = x[0];
+    const int32_t tid = (int32_t)x[1], pos = (int32_t)x[2], ls = (int32_t)x[5], mtid = (int32_t)x[6], mpos = (int32_t)x[7];
+    const uint32_t lq = x[3] & 0xff, nc = x[4] & 0xffff;
+    const uint64_t need = 32ull + lq + 4ull * nc + (uint64_t)((ls + 1) / 2) + (uint64_t)ls;
+    bool ok = bs >= 33u && bs <= (1u << 26);
+    ok = ok && p + 4 + (uint64_t)bs <= len;
+    ok = ok && tid >= -1 && tid < n_ref && pos >= -1 && lq != 0 && ls >= 0 && mtid >= -1 && mtid < n_ref && mpos >= -1;
+    ok = ok && need <= bs;
+    *lq_out = lq; *next = p + 4 + bs;
+    return ok;
+}
 /* a record start followed by another one (or by the end of the stream) */
 template <class Src>
 ITX_HD bool itx_plausible2(const Src &S, uint64_t p, uint64_t len, int32_t n_ref) {
@@ -323,7 +337,8 @@ ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
 /* n > 1 hits: walk the list in binKeeper order (key ascending) without materialising it -- once per list
  * position the candidates are re-walked for the smallest key above the previous one -- and apply the
  * "last ascent" rule.  Rare (nested / abutting repeats), so it is kept out of line. */
-ITX_HDN long long itx_select_multi(const itx_dev_index &D, const itx_query &Q, uint32_t start, uint32_t end, int32_t n, float *tcov) {
+struct itx_sel_cov { long long sel; float cov; };             /* by value: nothing of the caller's goes through local memory */
+ITX_HDN itx_sel_cov itx_select_multi(const itx_dev_index &D, const itx_query Q, uint32_t start, uint32_t end, int32_t n) {
     const int32_t fs = Q.fs, fe = Q.fe;
     uint64_t prev_key = 0; bool have_prev = false; float prev_cov = 0.0f, best_cov = 0.0f; long long sel = -1;
     for (int32_t k = 0; k < n; k++) {
@@ -341,31 +356,47 @@ ITX_HDN long long itx_select_multi(const itx_dev_index &D, const itx_query &Q, u
         if (cov > prev_cov) { sel = bi; best_cov = cov; }
         prev_cov = cov; prev_key = bk; have_prev = true;
     }
-    *tcov = best_cov;
-    return sel;
+    itx_sel_cov r; r.sel = sel; r.cov = best_cov;
+    return r;
 }
 /* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.  Returns the
- * sorted-table index of the selected element or -1; *n_hits = length of binKeeperFind's hit list, *tcov =
- * coverage of the selected element, *sel_iv = the element.  Up to four hits are kept in registers and
- * visited in list order (order key ascending); longer lists take itx_select_multi.  Exact for any n. */
-ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
-    *n_hits = 0; *tcov = 0.0f;
-    itx_query Q;
-    if (!itx_query_open(D, c, start, end, &Q)) return -1;
+ * sorted-table index of the selected element or -1; *n_hits = length of binKeeperFind's hit list, *sel_iv = the
+ * element.  The first two hits are kept in registers (list order = order key ascending); longer lists (nested
+ * repeats, rare) take itx_select_multi.  Exact for any n.
+ * *tcov: every caller only asks `*tcov < thr` (generic.c:961), so *tcov is the selected element's coverage OR, when a
+ * single hit covers at least 2^-12 of the fragment and thr <= 2^-13, just 2^-13: the same side of thr, without the
+ * float division (the float quotient of the two rounded floats is then >= 2^-12 * (1 - 2^-22) > 2^-13 >= thr). */
+/* the table loads of a walk: straight from global memory, or (k_scan) through a warp's shared-memory window of the table */
+struct itx_iv_global {
+    const itx_dev_index &D;
+    ITX_HDM itx_iv operator()(uint32_t i) const { return itx_ld_iv(D, i); }
+};
+#define ITX_COV_FLOOR 0.0001220703125f       /* 2^-13 */
+/* D_out is what the out-of-line long-list path is handed (k_scan: the copy of D in global memory) */
+template <class LdIv>
+ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_out, const itx_query &Q, const LdIv &ld, uint32_t start, uint32_t end,
+                                 float thr, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     const int32_t fs = Q.fs, fe = Q.fe;
-    int32_t n = 0; uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-    itx_iv e0, e1, e2, e3; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0; e2 = e0; e3 = e0;
+    int32_t n = 0; uint32_t i0 = 0, i1 = 0;
+    itx_iv e0, e1; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0;
     for (uint32_t i = Q.top; i-- > Q.lo;) {
-        const itx_iv e = itx_ld_iv(D, i);
+        const itx_iv e = ld(i);
         if (!(e.pmax > fs)) break;
         if (e.end > fs && e.start < fe && e.start < e.end) {
-            if (n == 0) { i0 = i; e0 = e; } else if (n == 1) { i1 = i; e1 = e; } else if (n == 2) { i2 = i; e2 = e; } else if (n == 3) { i3 = i; e3 = e; }
+            if (n == 0) { i0 = i; e0 = e; } else { i1 = i; e1 = e; }
             n++;
         }
     }
     *n_hits = n;
     if (n == 0) return -1;
-    if (n == 1) { *tcov = itx_cov(start, end, e0.start, e0.end); *sel_iv = e0; return (long long)i0; }
+    if (n == 1) {
+        const int32_t s = (int32_t)start > e0.start ? (int32_t)start : e0.start, t = (int32_t)end < e0.end ? (int32_t)end : e0.end;
+        const uint32_t r = t - s > 0 ? (uint32_t)(t - s) : 0u, den = end - start;
+        if (thr <= ITX_COV_FLOOR && den != 0 && ((uint64_t)r << 12) >= (uint64_t)den) *tcov = ITX_COV_FLOOR;
+        else *tcov = itx_cov(start, end, e0.start, e0.end);
+        *sel_iv = e0;
+        return (long long)i0;
+    }
     if (n == 2) {
         /* list order = key order; the second is taken only if it covers more than the first */
         const bool first0 = itx_order_key(e0.start, e0.end, e0.row) < itx_order_key(e1.start, e1.end, e1.row);
@@ -377,32 +408,16 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
         *sel_iv = pick0 ? e0 : e1;
         return (long long)(pick0 ? i0 : i1);
     }
-    if (n > 4) {
-        const long long sel = itx_select_multi(D, Q, start, end, n, tcov);
-        if (sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)sel);
-        return sel;
-    }
-    const uint64_t NOKEY = ~0ull;
-    uint64_t k0 = itx_order_key(e0.start, e0.end, e0.row), k1 = itx_order_key(e1.start, e1.end, e1.row);
-    uint64_t k2 = itx_order_key(e2.start, e2.end, e2.row), k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
-    const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
-    const float c2 = itx_cov(start, end, e2.start, e2.end), c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
-    float prev = 0.0f, best = 0.0f; int32_t sel = -1;
-    for (int32_t step = 0; step < n; step++) {
-        /* the unvisited hit with the smallest key */
-        int32_t j = 0; uint64_t km = k0;
-        if (k1 < km) { km = k1; j = 1; }
-        if (k2 < km) { km = k2; j = 2; }
-        if (k3 < km) { km = k3; j = 3; }
-        const float cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
-        if (cj > prev) { sel = j; best = cj; }
-        prev = cj;
-        if (j == 0) k0 = NOKEY; else if (j == 1) k1 = NOKEY; else if (j == 2) k2 = NOKEY; else k3 = NOKEY;
-    }
-    *tcov = best;
-    if (sel < 0) return -1;
-    *sel_iv = sel == 0 ? e0 : (sel == 1 ? e1 : (sel == 2 ? e2 : e3));
-    return (long long)(sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3)));
+    const itx_sel_cov r = itx_select_multi(D_out, Q, start, end, n);
+    *tcov = r.cov;
+    if (r.sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)r.sel);
+    return r.sel;
+}
+ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, float thr, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
+    *n_hits = 0; *tcov = 0.0f;
+    itx_query Q;
+    if (!itx_query_open(D, c, start, end, &Q)) return -1;
+    return itx_select_walk(D, D, Q, itx_iv_global{D}, start, end, thr, n_hits, tcov, sel_iv);
 }
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
 ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
@@ -478,9 +493,8 @@ ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t 
 /* record at p (core x) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start.
  * *malformed counts alternates without 4 comma separated fields (the reference asserts there). */
 template <class Src>
-ITX_HDN bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const Src &S, uint64_t p, const uint32_t x[9],
-                                       int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
-    uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+ITX_HDN bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src &S, uint64_t a0, uint64_t aend,
+                                           int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
     uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
     if (!xa || xa >= aend) return false;
     uint8_t ty = S.u8(xa);
@@ -523,6 +537,13 @@ ITX_HDN bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const Src &S, uin
         s = pe + 1;
     }
     return false;
+}
+
+template <class Src>
+ITX_HD bool itx_mapped_to_diff_subfam(const itx_dev_index &D, const Src &S, uint64_t p, const uint32_t x[9],
+                                      int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
+    uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+    return itx_mapped_to_diff_subfam_aux(D, S, a0, aend, sel_fold, qlen, malformed);
 }
 
 /* ------------------------------------------------------------------ consensus coverage range */

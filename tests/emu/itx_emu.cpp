@@ -242,7 +242,7 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
             const uint32_t chrom = info & ITX_CHROM_MASK;
             if (live && chrom != ITX_CHROM_NONE) {
                 int32_t nh; float tcov;
-                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, &nh, &tcov, &e);
+                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, o.minCoverage, &nh, &tcov, &e);
                 if (sel >= 0 && tcov < o.minCoverage) sel = -1;
                 if (sel >= 0 && o.diffSubfam && (info & ITX_F_HASXA)) {
                     const uint64_t p = lo + T.rec_off; uint32_t x[9]; G.core(p, x); uint32_t bad = 0;
@@ -328,7 +328,7 @@ uint64_t emu_tile_entry_miss(emu_index *E) { return E->tile_entry_miss; }
 int32_t emu_query(emu_index *E, const char *chrom, uint32_t start, uint32_t end, float min_cov, int32_t *n_hits) {
     int32_t c = itx_strtab_find(&E->ix.chroms, chrom); if (n_hits) *n_hits = 0;
     if (c < 0) return -1;
-    int32_t nh; float tcov; itx_iv e; e.row = 0; long long sel = itx_find_select(E->D, c, start, end, &nh, &tcov, &e);
+    int32_t nh; float tcov; itx_iv e; e.row = 0; long long sel = itx_find_select(E->D, c, start, end, min_cov, &nh, &tcov, &e);
     if (n_hits) *n_hits = nh;
     if (sel >= 0 && tcov < min_cov) sel = -1;
     return sel >= 0 ? (int32_t)e.row : -1;

@@ -165,3 +165,62 @@ def test_records_of_every_size(chunk, tmp_path):
         assert tc > 0 and tm == 0                 # entry misses (te) are allowed here: records longer than a chunk
         ora.close()
         emu.close()
+
+
+def _nested_world(d):
+    """a hand-made chromosome: stacks of 2..7 nested / staggered elements (hit lists longer than the two kept in
+    registers), elements that straddle 128 kb and 1 Mb bin edges, and long fragments that touch an element by a few bases"""
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chrN\t4000000\n")
+    rng = np.random.default_rng(11)
+    rows, subs = [], ["S%d" % i for i in range(12)]
+    open(rs, "w").write("".join("%s\t%d\n" % (s, 3000) for s in subs))
+    pos = 5000
+    while pos < 3900000:
+        depth = int(rng.integers(1, 8))
+        a, b = pos, pos + int(rng.integers(200, 4000))
+        for k in range(depth):
+            rows.append((a, b))
+            a += int(rng.integers(0, 60)); b -= int(rng.integers(-40, 60))
+            if b <= a + 5:
+                break
+        pos = b + int(rng.integers(1, 30000))
+    for k in range(1, 30):
+        rows.append((k * 131072 - 40, k * 131072 + 70))
+    rows.append((1048576 - 300, 1048576 + 300))
+    rows.sort()
+    with open(rm, "w") as f:
+        for i, (a, b) in enumerate(rows):
+            sub = subs[i % len(subs)]
+            f.write("\t".join(["585", "1000", "0", "0", "0", "chrN", str(a), str(b), "-1", "+", sub, "CLS%d" % (i % 3), "FAM%d" % (i % 5),
+                               "1", str(min(3000, b - a)), "0", str(i)]) + "\n")
+    return cs, rs, rm, rows
+
+
+def test_emu_query_matches_oracle_on_nested_table(tmp_path):
+    """overlap + "last ascent" selection + minCoverage of the device logic against the oracle's binKeeper restatement:
+    hit lists of every length (the long-list path included) and coverages on both sides of every threshold"""
+    cs, rs, rm, rows = _nested_world(str(tmp_path))
+    ora = O.OracleIndex(cs, rs, rm)
+    emu = emu_lib.EmuIndex(cs, rs, rm)
+    rng = np.random.default_rng(3)
+    q = []
+    for (a, b) in rows:
+        for _ in range(6):
+            st = max(0, a + int(rng.integers(-120, 120)))
+            q.append((st, st + int(rng.integers(1, 300))))
+        q.append((a, b)); q.append((a + 1, b - 1)); q.append((max(0, a - 1), b + 1))
+        for ov in (1, 2, 3, 4, 5, 9):                 # a long fragment that touches the element by ov bases: coverage ov / length
+            for length in (ov * 4095, ov * 4096, ov * 4097, ov * 8191, ov * 8192, ov * 8193, ov * 9999, ov * 10000, ov * 10001):
+                st = b - ov
+                q.append((st, st + length))
+    seen = set()
+    for mc in (1e-4, 0.0, 2.0 ** -13, 0.00012, 0.5):
+        for (st, en) in q:
+            ws, hits = ora.find_select("chrN", st, en, mc)
+            sel, nh = emu.query("chrN", st, en, mc)
+            assert (sel, nh) == (ws, len(hits)), (st, en, mc)
+            seen.add(min(nh, 5))
+    assert seen >= {0, 1, 2, 3, 4, 5}
+    ora.close()
+    emu.close()

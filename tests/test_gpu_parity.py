@@ -372,6 +372,34 @@ def test_overlap_kernel_property(worlds):
     ix.close()
 
 
+def test_overlap_kernel_on_nested_table(tmp_path):
+    """hit lists of every length (the long-list path included) and coverages on both sides of every threshold: k_query
+    against the oracle's binKeeper restatement"""
+    from test_emu_synth import _nested_world
+    cs, rs, rm, rows = _nested_world(str(tmp_path))
+    ora = O.OracleIndex(cs, rs, rm)
+    ix = capi.Index(cs, rs, rm)
+    rng = np.random.default_rng(3)
+    q = []
+    for (a, b) in rows:
+        for _ in range(6):
+            st = max(0, a + int(rng.integers(-120, 120)))
+            q.append((st, st + int(rng.integers(1, 300))))
+        q += [(a, b), (a + 1, b - 1), (max(0, a - 1), b + 1)]
+        for ov in (1, 2, 3, 5):
+            for length in (ov * 4095, ov * 4096, ov * 4097, ov * 8191, ov * 8192, ov * 8193, ov * 9999, ov * 10000, ov * 10001):
+                q.append((b - ov, b - ov + length))
+    st = np.array([x[0] for x in q], dtype=np.uint32)
+    en = np.array([x[1] for x in q], dtype=np.uint32)
+    for mc in (1e-4, 0.0, 2.0 ** -13, 0.00012, 0.5):
+        sel, nh = ix.query_select("chrN", st, en, mc)
+        for i in range(len(q)):
+            ws, hits = ora.find_select("chrN", int(st[i]), int(en[i]), mc)
+            assert (sel[i], nh[i]) == (ws, len(hits)), (q[i], mc)
+    ora.close()
+    ix.close()
+
+
 def test_cpg_matches_oracle(worlds, tmp_path):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bg = str(tmp_path / "cpg.bedGraph")
