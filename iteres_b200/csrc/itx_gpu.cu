@@ -42,7 +42,7 @@ struct itx_cuda {
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
-    int scan_ctas[2];                                         /* resident CTAs per SM of k_scan<false>, k_scan<true> */
+    int scan_ctas[4];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
     int decode_ctas;                        /* resident CTAs per SM of k_decode_span */
     itx_trace *d_trace; uint64_t trace_cap;
@@ -511,28 +511,38 @@ static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t ava
     return ITX_OK;
 }
 /* the fused path: ONE kernel per launch group (k_scan); sign -1 takes a group's counts back */
+static int scan_warps(void) {                /* warps per k_scan CTA: 14 (two CTAs per SM, 72 registers) unless ITX_SCAN_WARPS=8 (three CTAs, 80 registers) */
+    const char *v = getenv("ITX_SCAN_WARPS");
+    return (v && atoi(v) == 8) ? 8 : ITX_SCAN_NW;
+}
 static bool fused_smem_hist(const scan_ctx *sc) {
     const itx_cuda *cu = sc->ix->cu;
-    return (sc->o.filter == 0 && cu->D.stat_mode) && ITX_SCAN_SMEM_BASE + hist_bytes(cu) + 1024 <= cu->smem_optin;
+    return (sc->o.filter == 0 && cu->D.stat_mode) && (scan_warps() == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + hist_bytes(cu) + 1024 <= cu->smem_optin;
+}
+template <bool SH, int NW>
+static void launch_scan_kernel(itx_cuda *cu, const itx_scan_args &P, uint32_t n, size_t smem, int *ctas) {
+    if (!*ctas) {
+        cudaFuncSetAttribute(k_scan<SH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_scan<SH, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<SH, NW>, NW * 32, smem);
+        *ctas = nb > 0 ? nb : 1;
+    }
+    const uint32_t want = (n + NW - 1) / NW, most = (uint32_t)(cu->sm_count * *ctas);
+    k_scan<SH, NW><<<want < most ? want : most, NW * 32, smem, cu->stream>>>(P);
 }
 static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, int sign) {
     itx_cuda *cu = sc->ix->cu;
     itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len); P.D = cu->D; P.Dg = (const itx_dev_index *)cu->d_D; P.sign = sign; P.window = window;
     P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused; P.ticket = cu->d_fused + 1;
     const bool sh = fused_smem_hist(sc);
-    const size_t smem = ITX_SCAN_SMEM_BASE + (sh ? hist_bytes(cu) : 0);
+    const int nw = scan_warps();
+    const size_t smem = (nw == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + (sh ? hist_bytes(cu) : 0);
     P.flags = ITX_SCAN_DEFAULT;
     { const char *v = getenv("ITX_SCAN_FLAGS"); if (v) P.flags = (uint32_t)strtoul(v, NULL, 0); }      /* A/B switches: the counts do not depend on them */
-    if (!cu->scan_ctas[sh]) {
-        if (sh) { cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
-        else { cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
-        int nb = 0;
-        if (sh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<true>, ITX_DW * 32, smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<false>, ITX_DW * 32, smem);
-        cu->scan_ctas[sh] = nb > 0 ? nb : 1;
-    }
-    const uint32_t want = (n + ITX_DW - 1) / ITX_DW, most = (uint32_t)(cu->sm_count * cu->scan_ctas[sh]);
-    const uint32_t grid = want < most ? want : most;
-    if (sh) k_scan<true><<<grid, ITX_DW * 32, smem, cu->stream>>>(P); else k_scan<false><<<grid, ITX_DW * 32, smem, cu->stream>>>(P);
+    int *ctas = &cu->scan_ctas[(nw == 8 ? 2 : 0) + (sh ? 1 : 0)];
+    if (nw == 8) { if (sh) launch_scan_kernel<true, 8>(cu, P, n, smem, ctas); else launch_scan_kernel<false, 8>(cu, P, n, smem, ctas); }
+    else { if (sh) launch_scan_kernel<true, ITX_SCAN_NW>(cu, P, n, smem, ctas); else launch_scan_kernel<false, ITX_SCAN_NW>(cu, P, n, smem, ctas); }
     sc->n_launch++;
     return ITX_OK;
 }

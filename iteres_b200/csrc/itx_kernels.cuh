@@ -130,6 +130,16 @@ struct itx_src_stage {
     }
 };
 
+/* the same bytes when the caller knows that everything it will read lies inside the staged bytes: no bounds tests */
+struct itx_src_flat {
+    const uint8_t *buf; unsigned long long base;
+    __device__ __forceinline__ uint8_t u8(uint64_t off) const { return buf[(uint32_t)off - (uint32_t)base]; }
+    __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(buf + ((uint32_t)aligned_off - (uint32_t)base)); }
+    __device__ __forceinline__ uint32_t u32(uint64_t off) const {
+        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
+        return itx_funnel_r(w32(a), w32(a + 4), sh);
+    }
+};
 /* A warp per span (= "chunk" of the bookkeeping, A.C bytes, a multiple of ITX_STAGE).  Only the span's first
  * record start is GUESSED (warp-wide structural test, checked against the previous span by k_verify / k_fixup);
  * inside the span the chain is carried from one 4 KiB stage to the next.  Each stage (+1 KiB margin) arrives
@@ -508,11 +518,19 @@ struct itx_scan_args {
 #define ITX_SCAN_PREFETCH 1u             /* the next stage's bytes are asked into L2 while this stage is worked on */
 #define ITX_SCAN_DOMSIZE  2u             /* chain walk predicts with the span's dominant record size, so an odd record costs one step, not two */
 #define ITX_SCAN_WINDOW   4u             /* the 32 table entries under the warp's highest bucket end are staged in shared memory, metadata included */
-#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW)
+#define ITX_SCAN_WINAHEAD 8u             /* the window the NEXT round will most likely need is fetched with cp.async while this round's tail and the next stage's
+                                          * copy, chain walk and decode go on (coordinate-sorted reads move up the table a few entries per round) */
+#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD)
 #define ITX_WIN 32u                      /* table entries per warp window */
+#define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
 #define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
-#define ITX_SCAN_SMEM_BASE (ITX_DECODE_SMEM + ITX_DW * ITX_WIN_BYTES)
+/* shared memory of a k_scan CTA of NW warps: stages, record-start slots, mbarriers, table windows; the histogram follows */
+#define ITX_SCAN_SMEM_BASE(NW) ((NW) * (ITX_STAGE + ITX_MARGIN) + (NW) * ITX_POS_SLOTS * 2u + (NW) * 8u + (NW) * ITX_WIN_BYTES)
+#define ITX_SCAN_CTAS(NW) ((NW) <= 8 ? 3 : 2)          /* 8 warps x 3 CTAs (80 registers) or 14 warps x 2 CTAs (72 registers) per SM */
 
+__device__ __forceinline__ void itx_cp_async16(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void itx_cp_async8(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void itx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void itx_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
@@ -526,8 +544,8 @@ struct itx_iv_window {
     }
 };
 
-template <bool SMEM_HIST>
-__global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) {
+template <bool SMEM_HIST, int NW>
+__global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
     __shared__ unsigned long long sh_cnt[13];
     __shared__ uint32_t sh_last;
@@ -535,13 +553,13 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr uint32_t STG = ITX_STAGE + ITX_MARGIN;
     uint8_t *buf = itx_smem + w * STG;
-    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + ITX_DW * STG) + w * ITX_POS_SLOTS;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + NW * STG) + w * ITX_POS_SLOTS;
     const uint32_t buf_s = itx_smem_addr(buf);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + ITX_DW * STG + ITX_DW * ITX_POS_SLOTS * 2u) + w * 8;
-    int4 *win_iv = reinterpret_cast<int4 *>(itx_smem + ITX_DECODE_SMEM + w * ITX_WIN_BYTES);
+    const uint32_t bar_s = itx_smem_addr(itx_smem + NW * STG + NW * ITX_POS_SLOTS * 2u) + w * 8;
+    int4 *win_iv = reinterpret_cast<int4 *>(itx_smem + NW * STG + NW * ITX_POS_SLOTS * 2u + NW * 8u + w * ITX_WIN_BYTES);
     uint4 *win_meta = reinterpret_cast<uint4 *>(win_iv + ITX_WIN);
     int2 *win_meta2 = reinterpret_cast<int2 *>(win_meta + ITX_WIN);
-    uint32_t *sh_hist = reinterpret_cast<uint32_t *>(itx_smem + ITX_SCAN_SMEM_BASE);
+    uint32_t *sh_hist = reinterpret_cast<uint32_t *>(itx_smem + ITX_SCAN_SMEM_BASE(NW));
     const uint32_t nh = SMEM_HIST ? 2u * (uint32_t)(D.n_sub + D.n_fam + D.n_cla) : 0u;
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
     if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
@@ -552,6 +570,9 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
     const unsigned long long one64 = neg ? ~0ull : 1ull;
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
+    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD);
+    const uint32_t n_elem32 = D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem;
+    uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
     itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for after the selection, for the reads that are counted */
     uint32_t c[13];
 #pragma unroll
@@ -688,20 +709,26 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                 const bool q_ok = frag && chrom != ITX_CHROM_NONE && itx_query_open(D, (int32_t)chrom, T.start, T.end, &Q);
                 /* the table window of this round: the ITX_WIN entries below the highest bucket end any lane starts from
                  * (coordinate-sorted reads walk the same few entries), loaded once, coalesced, with their metadata */
-                uint32_t wbase = 0, wn = 0;
+                uint32_t wbase = 0, wn = 0, tmax = 0;
                 if (f_win) {
-                    const uint32_t tmax = __reduce_max_sync(0xffffffffu, q_ok ? Q.top : 0u);
+                    tmax = __reduce_max_sync(0xffffffffu, q_ok ? Q.top : 0u);
                     if (tmax) {
-                        wbase = tmax > ITX_WIN ? tmax - ITX_WIN : 0u; wn = tmax - wbase;
-                        __syncwarp();                          /* the previous round's readers are done */
-                        if (lane < wn) {
-                            win_iv[lane] = __ldg(reinterpret_cast<const int4 *>(D.iv + wbase + lane));
-                            if (stat) {
-                                win_meta[lane] = __ldg(reinterpret_cast<const uint4 *>(D.meta + wbase + lane));
-                                win_meta2[lane] = __ldg(reinterpret_cast<const int2 *>(D.meta2 + wbase + lane));
+                        if (wspec != 0xffffffffu) itx_cp_async_wait_all();
+                        __syncwarp();                          /* the window fetched ahead has landed; the previous round's readers are done */
+                        if (wspec != 0xffffffffu && tmax >= wspec + 8u && tmax <= wspec + ITX_WIN) {
+                            wbase = wspec; wn = n_elem32 - wspec < ITX_WIN ? n_elem32 - wspec : ITX_WIN;     /* it covers this round */
+                        } else {
+                            wbase = tmax > ITX_WIN ? tmax - ITX_WIN : 0u; wn = tmax - wbase;
+                            if (lane < wn) {
+                                win_iv[lane] = __ldg(reinterpret_cast<const int4 *>(D.iv + wbase + lane));
+                                if (stat) {
+                                    win_meta[lane] = __ldg(reinterpret_cast<const uint4 *>(D.meta + wbase + lane));
+                                    win_meta2[lane] = __ldg(reinterpret_cast<const int2 *>(D.meta2 + wbase + lane));
+                                }
                             }
+                            wspec = 0xffffffffu;
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
                 if (q_ok) {
@@ -712,7 +739,9 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                         uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
                         if (itx_aux_find(S, a0, aend, 'X', 'A')) {
                             uint32_t bad = 0;
-                            if (itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                            const int32_t fold = D.sinfo[D.meta[sel].sub].fold, qlen = (int32_t)(T.end - T.start);
+                            if (aend + 4 <= c_lo + nb ? itx_mapped_to_diff_subfam_aux(*P.Dg, itx_src_flat{buf, c_lo}, a0, aend, fold, qlen, &bad)
+                                                      : itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, fold, qlen, &bad)) diffsub = true;
                             if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
                         }
                     }
@@ -749,12 +778,23 @@ __global__ void __launch_bounds__(ITX_DW * 32, 3) k_scan(const itx_scan_args P) 
                         if (uniq) itx_red_u32(&D.el_cnt_u[sel], one);
                     }
                 }
+                /* the next round's window, unless the one in place still has room above this round's highest entry */
+                if (f_ahead && tmax && !(wspec != 0xffffffffu && tmax + 8u <= wspec + ITX_WIN)) {
+                    const uint32_t nbase = tmax > 20u ? tmax - 20u : 0u;
+                    __syncwarp();                              /* this round's readers are done */
+                    if (nbase + lane < n_elem32) {
+                        itx_cp_async16(win_iv + lane, D.iv + nbase + lane);
+                        if (stat) { itx_cp_async16(win_meta + lane, D.meta + nbase + lane); itx_cp_async8(win_meta2 + lane, D.meta2 + nbase + lane); }
+                    }
+                    wspec = nbase;
+                }
             }
             if (ended) { p = ITX_OFF_END; break; }
             p = c_lo + q;
         }
         if (lane == 0) A.exit_[i] = p;
     }
+    itx_cp_async_wait_all();                                   /* a window fetched ahead and never used */
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 13; k++) if (c[k]) atomicAdd(&sh_cnt[k], (unsigned long long)c[k]);

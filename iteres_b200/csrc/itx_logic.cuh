@@ -361,8 +361,8 @@ ITX_HDN itx_sel_cov itx_select_multi(const itx_dev_index &D, const itx_query Q, 
 }
 /* Overlap + "last ascent" selection for the fragment [start, end) on rmsk chromosome c.  Returns the
  * sorted-table index of the selected element or -1; *n_hits = length of binKeeperFind's hit list, *sel_iv = the
- * element.  The first two hits are kept in registers (list order = order key ascending); longer lists (nested
- * repeats, rare) take itx_select_multi.  Exact for any n.
+ * element.  Up to four hits are kept in registers (the newest with its element, the others by index) and visited in
+ * list order (order key ascending); longer lists take itx_select_multi.  Exact for any n.
  * *tcov: every caller only asks `*tcov < thr` (generic.c:961), so *tcov is the selected element's coverage OR, when a
  * single hit covers at least 2^-12 of the fragment and thr <= 2^-13, just 2^-13: the same side of thr, without the
  * float division (the float quotient of the two rounded floats is then >= 2^-12 * (1 - 2^-22) > 2^-13 >= thr). */
@@ -377,15 +377,13 @@ template <class LdIv>
 ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_out, const itx_query &Q, const LdIv &ld, uint32_t start, uint32_t end,
                                  float thr, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     const int32_t fs = Q.fs, fe = Q.fe;
-    int32_t n = 0; uint32_t i0 = 0, i1 = 0;
-    itx_iv e0, e1; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0; e1 = e0;
+    /* the last four hits: the newest with its element, the others by index (a hit shifts them down: eight moves) */
+    int32_t n = 0; uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    itx_iv e0; e0.start = e0.end = 0; e0.pmax = 0; e0.row = 0;
     for (uint32_t i = Q.top; i-- > Q.lo;) {
         const itx_iv e = ld(i);
         if (!(e.pmax > fs)) break;
-        if (e.end > fs && e.start < fe && e.start < e.end) {
-            if (n == 0) { i0 = i; e0 = e; } else { i1 = i; e1 = e; }
-            n++;
-        }
+        if (e.end > fs && e.start < fe && e.start < e.end) { i3 = i2; i2 = i1; i1 = i0; i0 = i; e0 = e; n++; }
     }
     *n_hits = n;
     if (n == 0) return -1;
@@ -397,6 +395,13 @@ ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_
         *sel_iv = e0;
         return (long long)i0;
     }
+    if (n > 4) {
+        const itx_sel_cov r = itx_select_multi(D_out, Q, start, end, n);
+        *tcov = r.cov;
+        if (r.sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)r.sel);
+        return r.sel;
+    }
+    const itx_iv e1 = ld(i1);
     if (n == 2) {
         /* list order = key order; the second is taken only if it covers more than the first */
         const bool first0 = itx_order_key(e0.start, e0.end, e0.row) < itx_order_key(e1.start, e1.end, e1.row);
@@ -408,10 +413,30 @@ ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_
         *sel_iv = pick0 ? e0 : e1;
         return (long long)(pick0 ? i0 : i1);
     }
-    const itx_sel_cov r = itx_select_multi(D_out, Q, start, end, n);
-    *tcov = r.cov;
-    if (r.sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)r.sel);
-    return r.sel;
+    /* three or four hits: visited in key order, "last ascent" */
+    const itx_iv e2 = ld(i2);
+    itx_iv e3 = e0; if (n > 3) e3 = ld(i3);
+    const uint64_t NOKEY = ~0ull;
+    uint64_t k0 = itx_order_key(e0.start, e0.end, e0.row), k1 = itx_order_key(e1.start, e1.end, e1.row);
+    uint64_t k2 = itx_order_key(e2.start, e2.end, e2.row), k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
+    const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
+    const float c2 = itx_cov(start, end, e2.start, e2.end), c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
+    float prev = 0.0f, best = 0.0f; int32_t sel = -1;
+    for (int32_t step = 0; step < n; step++) {
+        /* the unvisited hit with the smallest key */
+        int32_t j = 0; uint64_t km = k0;
+        if (k1 < km) { km = k1; j = 1; }
+        if (k2 < km) { km = k2; j = 2; }
+        if (k3 < km) { km = k3; j = 3; }
+        const float cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+        if (cj > prev) { sel = j; best = cj; }
+        prev = cj;
+        if (j == 0) k0 = NOKEY; else if (j == 1) k1 = NOKEY; else if (j == 2) k2 = NOKEY; else k3 = NOKEY;
+    }
+    *tcov = best;
+    if (sel < 0) return -1;
+    *sel_iv = sel == 0 ? e0 : (sel == 1 ? e1 : (sel == 2 ? e2 : e3));
+    return (long long)(sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3)));
 }
 ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, float thr, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     *n_hits = 0; *tcov = 0.0f;
@@ -492,8 +517,9 @@ ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t 
 }
 /* record at p (core x) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start.
  * *malformed counts alternates without 4 comma separated fields (the reference asserts there). */
+/* S by value: an out-of-line function handed a reference would read the source's fields back from local memory at every byte */
 template <class Src>
-ITX_HDN bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src &S, uint64_t a0, uint64_t aend,
+ITX_HDN bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src S, uint64_t a0, uint64_t aend,
                                            int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
     uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
     if (!xa || xa >= aend) return false;

@@ -2,7 +2,7 @@
 # A/B of k_scan's switches on the bench workload (device-resident stream, kernels only).  usage: tools/ab_scan.sh <tag>
 tag=${1:-ab}
 mkdir -p gpurun_out
-run() { # name, env..., -- bench args
+run() { # name, env...
     name=$1; shift
     env "$@" python bench.py --no-e2e --no-cpu-baseline --steps 20 --warmup 3 $EXTRA > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.log
     python - "$name" gpurun_out/${tag}_${name}.json <<'PY'
@@ -15,11 +15,8 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
+run f15 ITX_SCAN_FLAGS=15
 run f7 ITX_SCAN_FLAGS=7
-run f0 ITX_SCAN_FLAGS=0
-run f1 ITX_SCAN_FLAGS=1
-run f2 ITX_SCAN_FLAGS=2
-run f4 ITX_SCAN_FLAGS=4
-EXTRA="--chunk 32768" run f7_c32k ITX_SCAN_FLAGS=7
-EXTRA="--chunk 16384" run f7_c16k ITX_SCAN_FLAGS=7
-EXTRA="--window 1073741825" run f7_w1g ITX_SCAN_FLAGS=7
+run f15_w8 ITX_SCAN_FLAGS=15 ITX_SCAN_WARPS=8
+EXTRA="--mode 2 --reads 25000000" run f15_pe ITX_SCAN_FLAGS=15
+EXTRA="--mode 1 --reads 30000000" run f15_xa ITX_SCAN_FLAGS=15
