@@ -100,15 +100,17 @@ __device__ __forceinline__ bool itx_mbar_wait(uint32_t bar, uint32_t parity, uin
     return itx_mbar_wait_slow(bar, parity, status);
 }
 /* stream bytes [base, base + nb) staged linearly in shared memory; anything beyond comes from global memory */
+/* Offsets are taken relative to the stage in 32 bits: a record is shorter than 2^31 bytes and starts inside the stage,
+ * so the true distance always fits, and anything at or past nb goes to global memory. */
 struct itx_src_stage {
     const uint8_t *buf; const uint8_t *g; unsigned long long base; uint32_t nb;
     __device__ __forceinline__ uint8_t u8(uint64_t off) const {
-        const unsigned long long d = off - base;
-        return d < nb ? buf[(uint32_t)d] : __ldg(g + off);
+        const uint32_t d = (uint32_t)off - (uint32_t)base;
+        return d < nb ? buf[d] : __ldg(g + off);
     }
     __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const {
-        const unsigned long long d = aligned_off - base;
-        return d + 4 <= nb ? *reinterpret_cast<const uint32_t *>(buf + (uint32_t)d) : __ldg(reinterpret_cast<const uint32_t *>(g + aligned_off));
+        const uint32_t d = (uint32_t)aligned_off - (uint32_t)base;
+        return d < (nb > 3u ? nb - 3u : 0u) ? *reinterpret_cast<const uint32_t *>(buf + d) : __ldg(reinterpret_cast<const uint32_t *>(g + aligned_off));
     }
     __device__ __forceinline__ uint32_t u32(uint64_t off) const {
         const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
@@ -116,9 +118,10 @@ struct itx_src_stage {
     }
     __device__ __forceinline__ void core(uint64_t p, uint32_t x[9]) const {
         const uint64_t a = p & ~3ull; const uint32_t sh = (uint32_t)(p & 3) * 8;
+        const uint32_t d = (uint32_t)a - (uint32_t)base;
         uint32_t w[10];
-        if (a - base + 40 <= nb) {
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(buf + (uint32_t)(a - base));
+        if (d < (nb > 39u ? nb - 39u : 0u)) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(buf + d);
 #pragma unroll
             for (int i = 0; i < 10; i++) w[i] = q[i];
         } else {
@@ -129,7 +132,6 @@ struct itx_src_stage {
         for (int j = 0; j < 9; j++) x[j] = itx_funnel_r(w[j], w[j + 1], sh);
     }
 };
-
 /* the same bytes when the caller knows that everything it will read lies inside the staged bytes: no bounds tests */
 struct itx_src_flat {
     const uint8_t *buf; unsigned long long base;
@@ -525,7 +527,9 @@ struct itx_scan_args {
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
 #define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
 /* shared memory of a k_scan CTA of NW warps: stages, record-start slots, mbarriers, table windows; the histogram follows */
-#define ITX_SCAN_SMEM_BASE(NW) ((NW) * (ITX_STAGE + ITX_MARGIN) + (NW) * ITX_POS_SLOTS * 2u + (NW) * 8u + (NW) * ITX_WIN_BYTES)
+/* one contiguous block per warp (every pointer is the warp's base plus a constant) */
+#define ITX_SCAN_WARP_BYTES (ITX_STAGE + ITX_MARGIN + ITX_POS_SLOTS * 2u + 16u + ITX_WIN_BYTES)
+#define ITX_SCAN_SMEM_BASE(NW) ((NW) * ITX_SCAN_WARP_BYTES)
 #define ITX_SCAN_CTAS(NW) ((NW) <= 8 ? 3 : 2)          /* 8 warps x 3 CTAs (80 registers) or 14 warps x 2 CTAs (72 registers) per SM */
 
 __device__ __forceinline__ void itx_cp_async16(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
@@ -552,11 +556,11 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     const itx_decode_args &A = P.A; const itx_dev_index &D = P.D;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr uint32_t STG = ITX_STAGE + ITX_MARGIN;
-    uint8_t *buf = itx_smem + w * STG;
-    uint16_t *pos = reinterpret_cast<uint16_t *>(itx_smem + NW * STG) + w * ITX_POS_SLOTS;
+    uint8_t *buf = itx_smem + w * ITX_SCAN_WARP_BYTES;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(buf + STG);
     const uint32_t buf_s = itx_smem_addr(buf);
-    const uint32_t bar_s = itx_smem_addr(itx_smem + NW * STG + NW * ITX_POS_SLOTS * 2u) + w * 8;
-    int4 *win_iv = reinterpret_cast<int4 *>(itx_smem + NW * STG + NW * ITX_POS_SLOTS * 2u + NW * 8u + w * ITX_WIN_BYTES);
+    const uint32_t bar_s = buf_s + STG + ITX_POS_SLOTS * 2u;
+    int4 *win_iv = reinterpret_cast<int4 *>(buf + STG + ITX_POS_SLOTS * 2u + 16u);
     uint4 *win_meta = reinterpret_cast<uint4 *>(win_iv + ITX_WIN);
     int2 *win_meta2 = reinterpret_cast<int2 *>(win_meta + ITX_WIN);
     uint32_t *sh_hist = reinterpret_cast<uint32_t *>(itx_smem + ITX_SCAN_SMEM_BASE(NW));
@@ -649,35 +653,41 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             }
             /* the chain of this stage, out of shared memory.  Lane 0 holds the record at q; lane k >= 1 looks where record k
              * would start if records 1.. had the dominant size, and the run of lanes that find that size there is accepted
-             * in one step (each accepted start is the previous record's start + its verified size: the exact chain). */
+             * in one step (each accepted start is the previous record's start + its verified size: the exact chain).
+             * Offsets are stage-relative and 32 bits wide; records of 64 KiB and more are stepped over one at a time. */
             uint32_t n = 0, ended = 0;
             uint32_t q = (uint32_t)(p - c_lo);
             {
                 const uint32_t qh = (uint32_t)(c_hi - c_lo);
                 const unsigned long long room = A.len - c_lo;
                 const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
-                const uint32_t av32 = A.avail > c_lo ? (A.avail - c_lo > 0x7fffffffull ? 0x7fffffffu : (uint32_t)(A.avail - c_lo)) : 0u;
                 while (q < qh) {
                     if (q + 36u > room32) { ended = 1; break; }
                     const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
                     const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
                     const uint32_t sz0 = bs0 + 4u;
-                    if ((int32_t)bs0 < 32 || q + sz0 < q || q + sz0 > room32) { ended = 1; break; }
+                    if ((int32_t)bs0 < 32 || sz0 > room32 - q) { ended = 1; break; }
                     const uint32_t szp = szd ? szd : sz0;
-                    const unsigned long long pk = lane == 0 ? (unsigned long long)q : (unsigned long long)q + sz0 + (unsigned long long)(lane - 1u) * szp;
-                    bool same = lane == 0;
-                    if (lane != 0 && pk < qh && pk + szp <= room32) {
-                        const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + ((uint32_t)pk & ~3u));
-                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) + 4u == szp;
+                    uint32_t run = 1u, pk = q;
+                    if ((sz0 | szp) < 0x10000u) {                                  /* warp-uniform */
+                        pk = lane ? q + sz0 + (lane - 1u) * szp : q;
+                        bool same = true;
+                        if (lane) {
+                            same = false;
+                            if (pk < qh && pk + szp <= room32) {
+                                const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + (pk & ~3u));
+                                same = itx_funnel_r(wk[0], wk[1], (pk & 3u) * 8u) + 4u == szp;
+                            }
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, same);       /* bit 0 is always set */
+                        run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     }
-                    const uint32_t m = __ballot_sync(0xffffffffu, same);           /* bit 0 is always set */
-                    const uint32_t run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     if (lane < run && n + lane < ITX_POS_SLOTS) pos[n + lane] = (uint16_t)pk;
                     n += run;
                     q += sz0 + (run - 1u) * szp;
                     szd = (f_dom && run >= 2u) ? szp : 0u;
-                    if (q > av32 && lane == 0) atomicOr(&A.status[0], 2u);
                 }
+                if (lane == 0 && A.avail < c_lo + q) atomicOr(&A.status[0], 2u);   /* a record longer than the staged window */
             }
             __syncwarp();
             const itx_src_stage S{buf, A.b, c_lo, nb};
@@ -737,7 +747,8 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
                     if (sel >= 0 && A.o.diffSubfam) {
                         uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
-                        if (itx_aux_find(S, a0, aend, 'X', 'A')) {
+                        /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
+                        if (aend - a0 >= 5 && itx_aux_find(S, a0, aend, 'X', 'A')) {
                             uint32_t bad = 0;
                             const int32_t fold = D.sinfo[D.meta[sel].sub].fold, qlen = (int32_t)(T.end - T.start);
                             if (aend + 4 <= c_lo + nb ? itx_mapped_to_diff_subfam_aux(*P.Dg, itx_src_flat{buf, c_lo}, a0, aend, fold, qlen, &bad)

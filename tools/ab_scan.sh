@@ -15,8 +15,6 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run f15 ITX_SCAN_FLAGS=15
-run f7 ITX_SCAN_FLAGS=7
-run f15_w8 ITX_SCAN_FLAGS=15 ITX_SCAN_WARPS=8
-EXTRA="--mode 2 --reads 25000000" run f15_pe ITX_SCAN_FLAGS=15
-EXTRA="--mode 1 --reads 30000000" run f15_xa ITX_SCAN_FLAGS=15
+run w14 ITX_SCAN_WARPS=14
+run w8 ITX_SCAN_WARPS=8
+EXTRA="--mode 2 --reads 25000000" run w14_pe ITX_SCAN_WARPS=14
