@@ -578,9 +578,28 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     const uint32_t n_elem32 = D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem;
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
     itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for after the selection, for the reads that are counted */
-    uint32_t c[13];
-#pragma unroll
-    for (int k = 0; k < 13; k++) c[k] = 0;
+    /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no
+     * popcounts); the fields are summed over the warp and added to the CTA's totals before any of them can reach 256 */
+    uint32_t pa = 0, pb = 0, pc = 0, n_rounds = 0;
+#define ITX_SCAN_FLUSH_COUNTERS() do { \
+        const uint32_t a0_ = __reduce_add_sync(0xffffffffu, pa & 0x00ff00ffu), a1_ = __reduce_add_sync(0xffffffffu, (pa >> 8) & 0x00ff00ffu); \
+        const uint32_t b0_ = __reduce_add_sync(0xffffffffu, pb & 0x00ff00ffu), b1_ = __reduce_add_sync(0xffffffffu, (pb >> 8) & 0x00ff00ffu); \
+        const uint32_t c0_ = __reduce_add_sync(0xffffffffu, pc & 0x00ff00ffu), c1_ = __reduce_add_sync(0xffffffffu, (pc >> 8) & 0x00ff00ffu); \
+        if (lane == 0) { \
+            if (a0_ & 0xffffu) atomicAdd(&sh_cnt[0], (unsigned long long)(a0_ & 0xffffu)); \
+            if (a1_ & 0xffffu) atomicAdd(&sh_cnt[1], (unsigned long long)(a1_ & 0xffffu)); \
+            if (a0_ >> 16) atomicAdd(&sh_cnt[2], (unsigned long long)(a0_ >> 16)); \
+            if (a1_ >> 16) atomicAdd(&sh_cnt[3], (unsigned long long)(a1_ >> 16)); \
+            if (b0_ & 0xffffu) atomicAdd(&sh_cnt[4], (unsigned long long)(b0_ & 0xffffu)); \
+            if (b1_ & 0xffffu) atomicAdd(&sh_cnt[5], (unsigned long long)(b1_ & 0xffffu)); \
+            if (b0_ >> 16) atomicAdd(&sh_cnt[6], (unsigned long long)(b0_ >> 16)); \
+            if (b1_ >> 16) { atomicAdd(&sh_cnt[7], (unsigned long long)(b1_ >> 16)); atomicAdd(&sh_cnt[11], (unsigned long long)(b1_ >> 16)); } \
+            if (c0_ & 0xffffu) atomicAdd(&sh_cnt[9], (unsigned long long)(c0_ & 0xffffu)); \
+            if (c1_ & 0xffffu) atomicAdd(&sh_cnt[10], (unsigned long long)(c1_ & 0xffffu)); \
+            if (c0_ >> 16) atomicAdd(&sh_cnt[12], (unsigned long long)(c0_ >> 16)); \
+        } \
+        pa = pb = pc = 0; n_rounds = 0; \
+    } while (0)
     uint32_t parity = 0;
     bool dead = false;
     for (;;) {
@@ -702,16 +721,12 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, o_dec);
                 }
                 const uint32_t info = T.info;
-                const bool slot2 = info & ITX_F_SLOT2, frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
-                const uint32_t m_valid = __ballot_sync(0xffffffffu, valid), m_slot2 = __ballot_sync(0xffffffffu, slot2);
-                const uint32_t m_map = __ballot_sync(0xffffffffu, info & ITX_F_MAPPED), m_used = __ballot_sync(0xffffffffu, info & ITX_F_USED);
-                const uint32_t m_frag = __ballot_sync(0xffffffffu, frag), m_uniq = __ballot_sync(0xffffffffu, uniq);
-                c[0] += __popc(m_valid & ~m_slot2); c[1] += __popc(m_slot2);
-                c[2] += __popc(m_map & ~m_slot2);   c[3] += __popc(m_map & m_slot2);
-                c[4] += __popc(m_used & ~m_slot2);  c[5] += __popc(m_used & m_slot2);
-                c[6] += __popc(m_frag);
-                const uint32_t mu = __popc(m_frag & m_uniq);
-                c[7] += mu; c[11] += mu;
+                const bool frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
+                {   /* read_end1/2, *_mapped, *_used, reads_mapped, reads_mapped_unique (= reads_nonredundant_unique without -R) */
+                    const uint32_t s2 = (info >> 28) & 1u, ns2 = s2 ^ 1u, mp = (info >> 29) & 1u, us = (info >> 30) & 1u, fr = (info >> 24) & 1u, uq = (info >> 25) & 1u;
+                    pa += ((valid ? 1u : 0u) & ns2) | (s2 << 8) | ((mp & ns2) << 16) | ((mp & s2) << 24);
+                    pb += (us & ns2) | ((us & s2) << 8) | (fr << 16) | ((fr & uq) << 24);
+                }
                 if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
                 long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
                 const uint32_t chrom = info & ITX_CHROM_MASK;
@@ -758,9 +773,8 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     }
                 }
                 const bool counted = sel >= 0 && !diffsub;
-                const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
-                c[12] += __popc(__ballot_sync(0xffffffffu, diffsub));
-                c[9] += __popc(m_cnt); c[10] += __popc(m_cnt & m_uniq);
+                pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
+                if (++n_rounds == 255u) ITX_SCAN_FLUSH_COUNTERS();
                 if (counted) {
                     if (stat) {
                         const uint32_t wd = (uint32_t)sel - wbase;
@@ -806,10 +820,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         if (lane == 0) A.exit_[i] = p;
     }
     itx_cp_async_wait_all();                                   /* a window fetched ahead and never used */
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 13; k++) if (c[k]) atomicAdd(&sh_cnt[k], (unsigned long long)c[k]);
-    }
+    ITX_SCAN_FLUSH_COUNTERS();
     __syncthreads();
     if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], neg ? 0ull - sh_cnt[threadIdx.x] : sh_cnt[threadIdx.x]);
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) itx_red_u64(&D.grp[t], neg ? 0ull - (unsigned long long)v : (unsigned long long)v); }

@@ -334,6 +334,22 @@ ITX_HD float itx_cov(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
     float den = (float)(end - start);
     return den == 0.0f ? 0.0f : (float)r / den;
 }
+/* the overlap of [start, end) with [es, ee) as getCov's numerator takes it (generic.c:296-301) */
+ITX_HD uint32_t itx_ovl(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
+    const int32_t s = (int32_t)start > es ? (int32_t)start : es, e = (int32_t)end < ee ? (int32_t)end : ee;
+    const int32_t r = e - s;
+    return r > 0 ? (uint32_t)r : 0u;
+}
+#define ITX_COV_FLOOR 0.0001220703125f       /* 2^-13 */
+/* Coverage r / den for a caller that only asks `cov < thr` (generic.c:961): the float quotient itx_cov forms, or -- when
+ * the overlap is at least 2^-12 of the fragment and thr <= 2^-13 -- just 2^-13, which lies on the same side of thr
+ * (the quotient of the two rounded floats is then >= 2^-12 * (1 - 2^-22) > 2^-13 >= thr): no division. */
+ITX_HD float itx_cov_thr(uint32_t r, uint32_t den, float thr) {
+    if (r != 0 && r == den) return 1.0f;
+    if (thr <= ITX_COV_FLOOR && den != 0 && ((uint64_t)r << 12) >= (uint64_t)den) return ITX_COV_FLOOR;
+    const float d = (float)den;
+    return d == 0.0f ? 0.0f : (float)(int32_t)r / d;
+}
 /* n > 1 hits: walk the list in binKeeper order (key ascending) without materialising it -- once per list
  * position the candidates are re-walked for the smallest key above the previous one -- and apply the
  * "last ascent" rule.  Rare (nested / abutting repeats), so it is kept out of line. */
@@ -371,7 +387,6 @@ struct itx_iv_global {
     const itx_dev_index &D;
     ITX_HDM itx_iv operator()(uint32_t i) const { return itx_ld_iv(D, i); }
 };
-#define ITX_COV_FLOOR 0.0001220703125f       /* 2^-13 */
 /* D_out is what the out-of-line long-list path is handed (k_scan: the copy of D in global memory) */
 template <class LdIv>
 ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_out, const itx_query &Q, const LdIv &ld, uint32_t start, uint32_t end,
@@ -387,54 +402,62 @@ ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_
     }
     *n_hits = n;
     if (n == 0) return -1;
-    if (n == 1) {
-        const int32_t s = (int32_t)start > e0.start ? (int32_t)start : e0.start, t = (int32_t)end < e0.end ? (int32_t)end : e0.end;
-        const uint32_t r = t - s > 0 ? (uint32_t)(t - s) : 0u, den = end - start;
-        if (thr <= ITX_COV_FLOOR && den != 0 && ((uint64_t)r << 12) >= (uint64_t)den) *tcov = ITX_COV_FLOOR;
-        else *tcov = itx_cov(start, end, e0.start, e0.end);
-        *sel_iv = e0;
-        return (long long)i0;
-    }
+    const uint32_t den = end - start;
+    if (n == 1) { *tcov = itx_cov_thr(itx_ovl(start, end, e0.start, e0.end), den, thr); *sel_iv = e0; return (long long)i0; }
     if (n > 4) {
         const itx_sel_cov r = itx_select_multi(D_out, Q, start, end, n);
         *tcov = r.cov;
         if (r.sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)r.sel);
         return r.sel;
     }
+    /* Two to four hits, visited in list order (key ascending), "last ascent" on the coverage.  All coverages share the
+     * denominator, and for fragments shorter than 2^23 bases the float quotients order exactly like the overlaps
+     * (both operands convert exactly, two quotients differ by at least 1 / den > 2^-23, more than one unit in the last
+     * place anywhere in (0, 1]): the overlaps are compared as integers and no quotient is formed.  Longer fragments
+     * take the float comparison itself. */
+    const bool by_int = den != 0 && den < (1u << 23);
     const itx_iv e1 = ld(i1);
     if (n == 2) {
-        /* list order = key order; the second is taken only if it covers more than the first */
         const bool first0 = itx_order_key(e0.start, e0.end, e0.row) < itx_order_key(e1.start, e1.end, e1.row);
-        const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
-        const float ca = first0 ? c0 : c1, cb = first0 ? c1 : c0;
-        const bool take_b = cb > ca;                        /* ca > 0 always, so the first is taken before */
+        const uint32_t r0 = itx_ovl(start, end, e0.start, e0.end), r1 = itx_ovl(start, end, e1.start, e1.end);
+        bool take_b;                                        /* the second is taken only if it covers more than the first (which covers > 0) */
+        if (by_int) take_b = first0 ? r1 > r0 : r0 > r1;
+        else {
+            const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
+            take_b = first0 ? c1 > c0 : c0 > c1;
+        }
         const bool pick0 = first0 != take_b;
-        *tcov = take_b ? cb : ca;
+        *tcov = itx_cov_thr(pick0 ? r0 : r1, den, thr);
         *sel_iv = pick0 ? e0 : e1;
         return (long long)(pick0 ? i0 : i1);
     }
-    /* three or four hits: visited in key order, "last ascent" */
     const itx_iv e2 = ld(i2);
     itx_iv e3 = e0; if (n > 3) e3 = ld(i3);
     const uint64_t NOKEY = ~0ull;
     uint64_t k0 = itx_order_key(e0.start, e0.end, e0.row), k1 = itx_order_key(e1.start, e1.end, e1.row);
     uint64_t k2 = itx_order_key(e2.start, e2.end, e2.row), k3 = n > 3 ? itx_order_key(e3.start, e3.end, e3.row) : NOKEY;
-    const float c0 = itx_cov(start, end, e0.start, e0.end), c1 = itx_cov(start, end, e1.start, e1.end);
-    const float c2 = itx_cov(start, end, e2.start, e2.end), c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
-    float prev = 0.0f, best = 0.0f; int32_t sel = -1;
+    const uint32_t r0 = itx_ovl(start, end, e0.start, e0.end), r1 = itx_ovl(start, end, e1.start, e1.end);
+    const uint32_t r2 = itx_ovl(start, end, e2.start, e2.end), r3 = n > 3 ? itx_ovl(start, end, e3.start, e3.end) : 0u;
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+    if (!by_int) {
+        c0 = itx_cov(start, end, e0.start, e0.end); c1 = itx_cov(start, end, e1.start, e1.end);
+        c2 = itx_cov(start, end, e2.start, e2.end); c3 = n > 3 ? itx_cov(start, end, e3.start, e3.end) : 0.0f;
+    }
+    float prev = 0.0f; uint32_t prev_r = 0; int32_t sel = -1;
     for (int32_t step = 0; step < n; step++) {
         /* the unvisited hit with the smallest key */
         int32_t j = 0; uint64_t km = k0;
         if (k1 < km) { km = k1; j = 1; }
         if (k2 < km) { km = k2; j = 2; }
         if (k3 < km) { km = k3; j = 3; }
+        const uint32_t rj = j == 0 ? r0 : (j == 1 ? r1 : (j == 2 ? r2 : r3));
         const float cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
-        if (cj > prev) { sel = j; best = cj; }
-        prev = cj;
+        if (by_int ? rj > prev_r : cj > prev) sel = j;
+        prev = cj; prev_r = rj;
         if (j == 0) k0 = NOKEY; else if (j == 1) k1 = NOKEY; else if (j == 2) k2 = NOKEY; else k3 = NOKEY;
     }
-    *tcov = best;
-    if (sel < 0) return -1;
+    if (sel < 0) { *tcov = 0.0f; return -1; }
+    *tcov = itx_cov_thr(sel == 0 ? r0 : (sel == 1 ? r1 : (sel == 2 ? r2 : r3)), den, thr);
     *sel_iv = sel == 0 ? e0 : (sel == 1 ? e1 : (sel == 2 ? e2 : e3));
     return (long long)(sel == 0 ? i0 : (sel == 1 ? i1 : (sel == 2 ? i2 : i3)));
 }

@@ -214,6 +214,8 @@ def test_emu_query_matches_oracle_on_nested_table(tmp_path):
             for length in (ov * 4095, ov * 4096, ov * 4097, ov * 8191, ov * 8192, ov * 8193, ov * 9999, ov * 10000, ov * 10001):
                 st = b - ov
                 q.append((st, st + length))
+    for (a, b) in rows[-12:]:                         # fragments of 2^23 bases and more (float comparison of the coverages) over the last few stacks
+        q += [(max(0, a - 3), a - 3 + 9000000), (a + 1, a + 1 + (1 << 23)), (b - 2, b - 2 + 20000000)]
     seen = set()
     for mc in (1e-4, 0.0, 2.0 ** -13, 0.00012, 0.5):
         for (st, en) in q:

@@ -389,6 +389,8 @@ def test_overlap_kernel_on_nested_table(tmp_path):
         for ov in (1, 2, 3, 5):
             for length in (ov * 4095, ov * 4096, ov * 4097, ov * 8191, ov * 8192, ov * 8193, ov * 9999, ov * 10000, ov * 10001):
                 q.append((b - ov, b - ov + length))
+    for (a, b) in rows[-12:]:                         # fragments of 2^23 bases and more (float comparison of the coverages) over the last few stacks
+        q += [(max(0, a - 3), a - 3 + 9000000), (a + 1, a + 1 + (1 << 23)), (b - 2, b - 2 + 20000000)]
     st = np.array([x[0] for x in q], dtype=np.uint32)
     en = np.array([x[1] for x in q], dtype=np.uint32)
     for mc in (1e-4, 0.0, 2.0 ** -13, 0.00012, 0.5):
