@@ -607,36 +607,40 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         if (lane == 0) i = atomicAdd(&A.work[2], 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= A.nchunks || dead) break;
+        /* Inside a span everything is kept relative to its first byte, in 32 bits (a span is at most 1 MiB and a record
+         * shorter than 2^31 bytes); the two chain sentinels keep their low words (0xfffffffe ended, 0xffffffff none). */
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+        const uint32_t hi = A.len - lo < A.C ? (uint32_t)(A.len - lo) : A.C;
         /* the span's first record start: known for the window's first span; otherwise guessed out of the span's first
          * stage, which is needed in shared memory anyway */
-        unsigned long long p = ITX_OFF_NONE;
+        uint32_t p = 0xffffffffu;
         bool guess = i != 0;
         if (!guess) {
-            if (neg) p = P.carry_log[P.window];
-            else { p = *A.carry; if (lane == 0) P.carry_log[P.window] = p; }
-            if (lane == 0) A.entry[i] = p;
+            unsigned long long p0;
+            if (neg) p0 = P.carry_log[P.window];
+            else { p0 = *A.carry; if (lane == 0) P.carry_log[P.window] = p0; }
+            if (lane == 0) A.entry[i] = p0;
+            p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
         }
-        unsigned long long staged = ITX_OFF_NONE;             /* stream offset of the stage now in shared memory */
+        uint32_t staged = 0xffffffffu;                         /* span offset of the stage now in shared memory */
         uint32_t nb = 0;
         uint32_t szd = 0;                                      /* the span's dominant record size (0: none yet) */
         for (;;) {
-            if (guess ? !(lo < hi) : !(p < hi)) { if (guess && lane == 0) A.entry[i] = p; break; }
-            const unsigned long long c_lo = guess ? lo : lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
-            unsigned long long c_hi = c_lo + ITX_STAGE; if (c_hi > hi) c_hi = hi;
+            if (guess ? hi == 0u : !(p < hi)) { if (guess && lane == 0) A.entry[i] = ITX_OFF_NONE; break; }
+            const uint32_t c_lo = guess ? 0u : p & ~(ITX_STAGE - 1u);
+            const uint32_t c_hi = c_lo + ITX_STAGE < hi ? c_lo + ITX_STAGE : hi;
+            const unsigned long long rest = A.len - lo - c_lo;                 /* bytes of the stream from this stage on */
             if (staged != c_lo) {
                 /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream) */
-                const unsigned long long rest = A.len - c_lo;
                 nb = rest > STG ? STG : (uint32_t)rest;
                 const uint32_t bytes = (nb + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */
                 __syncwarp();                                  /* every lane is done reading the previous stage */
                 if (lane == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     itx_mbar_expect_tx(bar_s, bytes);
-                    itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+                    itx_bulk_g2s(buf_s, A.b + lo + c_lo, bytes, bar_s);
                     /* what the span's next stage adds to this one, on its way into L2 meanwhile */
-                    if (f_prefetch && c_lo + ITX_STAGE < hi && c_lo + STG + ITX_STAGE <= A.len) itx_prefetch_l2(A.b + c_lo + STG, ITX_STAGE);
+                    if (f_prefetch && c_lo + ITX_STAGE < hi && rest >= STG + ITX_STAGE) itx_prefetch_l2(A.b + lo + c_lo + STG, ITX_STAGE);
                 }
                 if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
                 parity ^= 1u;
@@ -646,13 +650,13 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 /* itx_plausible2's test, 32 offsets per step: the core of every offset comes out of the stage with plain
                  * shared-memory loads and is tested without branches; the second record is looked at for the survivors */
                 const itx_src_stage S0{buf, A.b, lo, nb};
-                for (unsigned long long base = lo; base < hi; base += 32) {
-                    const unsigned long long q = base + lane;
+                for (uint32_t base = 0; base < hi; base += 32) {
+                    const uint32_t d = base + lane;
+                    const unsigned long long q = lo + d;
                     bool ok = false;
-                    if (q < hi && q + 36 <= A.len) {
-                        const uint32_t d = (uint32_t)(q - lo);
+                    if (d < hi && q + 36 <= A.len) {
                         uint32_t x[9], lq; uint64_t nx, nx2;
-                        if (base - lo + 32u + 40u <= nb) {                /* warp-uniform: every lane's core lies in the stage */
+                        if (base + 32u + 40u <= nb) {                     /* warp-uniform: every lane's core lies in the stage */
                             const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
                             uint32_t wv[10];
 #pragma unroll
@@ -666,26 +670,28 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
                 }
-                if (lane == 0) A.entry[i] = p;
+                if (lane == 0) A.entry[i] = p == 0xffffffffu ? ITX_OFF_NONE : lo + p;
                 guess = false;
                 continue;
             }
             /* the chain of this stage, out of shared memory.  Lane 0 holds the record at q; lane k >= 1 looks where record k
              * would start if records 1.. had the dominant size, and the run of lanes that find that size there is accepted
              * in one step (each accepted start is the previous record's start + its verified size: the exact chain).
-             * Offsets are stage-relative and 32 bits wide; records of 64 KiB and more are stepped over one at a time. */
-            uint32_t n = 0, ended = 0;
-            uint32_t q = (uint32_t)(p - c_lo);
+             * Offsets are stage-relative and 32 bits wide; records of 64 KiB and more are stepped over one at a time.
+             * q ends as the offset of the next stage's first record, or as 0xffffffff when the chain ends here. */
+            uint32_t n = 0;
+            uint32_t q = p - c_lo;
             {
-                const uint32_t qh = (uint32_t)(c_hi - c_lo);
-                const unsigned long long room = A.len - c_lo;
-                const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
+                const uint32_t qh = c_hi - c_lo;
+                const uint32_t room32 = rest > 0x7fffffffull ? 0x7fffffffu : (uint32_t)rest;
+                uint32_t q_end = q;                                                /* where the last whole record of the stage ends */
                 while (q < qh) {
-                    if (q + 36u > room32) { ended = 1; break; }
+                    q_end = q;
+                    if (q + 36u > room32) { q = 0xffffffffu; break; }
                     const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
                     const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
                     const uint32_t sz0 = bs0 + 4u;
-                    if ((int32_t)bs0 < 32 || sz0 > room32 - q) { ended = 1; break; }
+                    if ((int32_t)bs0 < 32 || sz0 > room32 - q) { q = 0xffffffffu; break; }
                     const uint32_t szp = szd ? szd : sz0;
                     uint32_t run = 1u, pk = q;
                     if ((sz0 | szp) < 0x10000u) {                                  /* warp-uniform */
@@ -706,17 +712,20 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     q += sz0 + (run - 1u) * szp;
                     szd = (f_dom && run >= 2u) ? szp : 0u;
                 }
-                if (lane == 0 && A.avail < c_lo + q) atomicOr(&A.status[0], 2u);   /* a record longer than the staged window */
+                if (q != 0xffffffffu) q_end = q;
+                if (lane == 0 && A.avail < lo + c_lo + q_end) atomicOr(&A.status[0], 2u);                  /* a record longer than the staged window */
             }
             __syncwarp();
-            const itx_src_stage S{buf, A.b, c_lo, nb};
+            const unsigned long long c_lo64 = lo + c_lo;
+            const itx_src_stage S{buf, A.b, c_lo64, nb};
+            uint32_t tmax_last = 0;                            /* highest table entry any round of this stage started from */
             for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                 const uint32_t j = j0 + lane; const bool valid = j < n;
                 itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
                 unsigned long long rp = 0;
                 uint32_t x[9];
                 if (valid) {
-                    rp = c_lo + pos[j];
+                    rp = c_lo64 + pos[j];
                     S.core(rp, x);
                     T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, o_dec);
                 }
@@ -756,21 +765,28 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                         }
                     }
                 }
-                if (q_ok) {
-                    int32_t nhit = 0; float tcov = 0.0f;
-                    sel = itx_select_walk(D, *P.Dg, Q, itx_iv_window{D, win_iv, wbase, wn}, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
-                    if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-                    if (sel >= 0 && A.o.diffSubfam) {
-                        uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
-                        /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
-                        if (aend - a0 >= 5 && itx_aux_find(S, a0, aend, 'X', 'A')) {
-                            uint32_t bad = 0;
-                            const int32_t fold = D.sinfo[D.meta[sel].sub].fold, qlen = (int32_t)(T.end - T.start);
-                            if (aend + 4 <= c_lo + nb ? itx_mapped_to_diff_subfam_aux(*P.Dg, itx_src_flat{buf, c_lo}, a0, aend, fold, qlen, &bad)
-                                                      : itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, fold, qlen, &bad)) diffsub = true;
-                            if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
-                        }
-                    }
+                int32_t nhit = 0; float tcov = 0.0f;
+                if (q_ok) sel = itx_select_walk(D, Q, itx_iv_window{D, win_iv, wbase, wn}, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+                /* the out-of-line paths (hit lists longer than four, XA alternates) sit in regions of their own: a call inside
+                 * the region above would make every lane that leaves it wait for a spilled convergence barrier */
+                if (sel == ITX_SEL_LONG) {
+                    const itx_sel_cov r = itx_select_multi(*P.Dg, Q, T.start, T.end, nhit);
+                    sel = r.sel; tcov = r.cov;
+                    if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
+                }
+                if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
+                uint64_t a0 = 0, aend = 0; bool has_xa = false;
+                if (sel >= 0 && A.o.diffSubfam) {
+                    itx_aux_range(rp, x, &a0, &aend);
+                    /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
+                    has_xa = aend - a0 >= 5 && itx_aux_find(S, a0, aend, 'X', 'A');
+                }
+                if (has_xa) {
+                    uint32_t bad = 0;
+                    const int32_t fold = D.sinfo[D.meta[sel].sub].fold, qlen = (int32_t)(T.end - T.start);
+                    if (aend + 4 <= c_lo64 + nb ? itx_mapped_to_diff_subfam_aux(*P.Dg, itx_src_flat{buf, c_lo64}, a0, aend, fold, qlen, &bad)
+                                                : itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, fold, qlen, &bad)) diffsub = true;
+                    if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
                 }
                 const bool counted = sel >= 0 && !diffsub;
                 pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
@@ -803,21 +819,24 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                         if (uniq) itx_red_u32(&D.el_cnt_u[sel], one);
                     }
                 }
-                /* the next round's window, unless the one in place still has room above this round's highest entry */
-                if (f_ahead && tmax && !(wspec != 0xffffffffu && tmax + 8u <= wspec + ITX_WIN)) {
-                    const uint32_t nbase = tmax > 20u ? tmax - 20u : 0u;
-                    __syncwarp();                              /* this round's readers are done */
-                    if (nbase + lane < n_elem32) {
-                        itx_cp_async16(win_iv + lane, D.iv + nbase + lane);
-                        if (stat) { itx_cp_async16(win_meta + lane, D.meta + nbase + lane); itx_cp_async8(win_meta2 + lane, D.meta2 + nbase + lane); }
-                    }
-                    wspec = nbase;
-                }
+                if (tmax) tmax_last = tmax;
             }
-            if (ended) { p = ITX_OFF_END; break; }
+            /* the window the next stage will most likely need, unless the one in place still has room above this stage's
+             * highest entry (issued out here, after the rounds: a spilled register reloaded right behind these copies
+             * would wait for them) */
+            if (f_ahead && tmax_last && !(wspec != 0xffffffffu && tmax_last + 8u <= wspec + ITX_WIN)) {
+                const uint32_t nbase = tmax_last > 20u ? tmax_last - 20u : 0u;
+                __syncwarp();                                  /* the last round's readers are done */
+                if (nbase + lane < n_elem32) {
+                    itx_cp_async16(win_iv + lane, D.iv + nbase + lane);
+                    if (stat) { itx_cp_async16(win_meta + lane, D.meta + nbase + lane); itx_cp_async8(win_meta2 + lane, D.meta2 + nbase + lane); }
+                }
+                wspec = nbase;
+            }
+            if (q == 0xffffffffu) { p = 0xfffffffeu; break; }
             p = c_lo + q;
         }
-        if (lane == 0) A.exit_[i] = p;
+        if (lane == 0) A.exit_[i] = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
     }
     itx_cp_async_wait_all();                                   /* a window fetched ahead and never used */
     ITX_SCAN_FLUSH_COUNTERS();

@@ -387,9 +387,10 @@ struct itx_iv_global {
     const itx_dev_index &D;
     ITX_HDM itx_iv operator()(uint32_t i) const { return itx_ld_iv(D, i); }
 };
-/* D_out is what the out-of-line long-list path is handed (k_scan: the copy of D in global memory) */
+/* More than four hits: ITX_SEL_LONG is returned and the caller runs itx_select_multi (out of line, in a region of its own). */
+#define ITX_SEL_LONG (-2ll)
 template <class LdIv>
-ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_out, const itx_query &Q, const LdIv &ld, uint32_t start, uint32_t end,
+ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_query &Q, const LdIv &ld, uint32_t start, uint32_t end,
                                  float thr, int32_t *n_hits, float *tcov, itx_iv *sel_iv) {
     const int32_t fs = Q.fs, fe = Q.fe;
     /* the last four hits: the newest with its element, the others by index (a hit shifts them down: eight moves) */
@@ -404,12 +405,7 @@ ITX_HD long long itx_select_walk(const itx_dev_index &D, const itx_dev_index &D_
     if (n == 0) return -1;
     const uint32_t den = end - start;
     if (n == 1) { *tcov = itx_cov_thr(itx_ovl(start, end, e0.start, e0.end), den, thr); *sel_iv = e0; return (long long)i0; }
-    if (n > 4) {
-        const itx_sel_cov r = itx_select_multi(D_out, Q, start, end, n);
-        *tcov = r.cov;
-        if (r.sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)r.sel);
-        return r.sel;
-    }
+    if (n > 4) return ITX_SEL_LONG;
     /* Two to four hits, visited in list order (key ascending), "last ascent" on the coverage.  All coverages share the
      * denominator, and for fragments shorter than 2^23 bases the float quotients order exactly like the overlaps
      * (both operands convert exactly, two quotients differ by at least 1 / den > 2^-23, more than one unit in the last
@@ -465,7 +461,13 @@ ITX_HD long long itx_find_select(const itx_dev_index &D, int32_t c, uint32_t sta
     *n_hits = 0; *tcov = 0.0f;
     itx_query Q;
     if (!itx_query_open(D, c, start, end, &Q)) return -1;
-    return itx_select_walk(D, D, Q, itx_iv_global{D}, start, end, thr, n_hits, tcov, sel_iv);
+    long long sel = itx_select_walk(D, Q, itx_iv_global{D}, start, end, thr, n_hits, tcov, sel_iv);
+    if (sel == ITX_SEL_LONG) {
+        const itx_sel_cov r = itx_select_multi(D, Q, start, end, *n_hits);
+        *tcov = r.cov; sel = r.sel;
+        if (sel >= 0) *sel_iv = itx_ld_iv(D, (uint32_t)sel);
+    }
+    return sel;
 }
 /* head of binKeeperFind's list (cpgBedGraphOverlapRepeat, generic.c:1086-1089) */
 ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start, uint32_t end, itx_iv *sel_iv) {
