@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
 #define ITX_DW 8                           /* warps per CTA */
 #define ITX_CLAIM 8u                       /* work units claimed per atomic on the work counters */
 #define ITX_PART 128u                      /* tuple slots per k_overlap work unit */
+#ifndef ITX_MARGIN
 #define ITX_MARGIN 1024u                   /* bytes staged past the chunk end for records that straddle it */
+#endif
 #define ITX_DECODE_SMEM 0
 
 __device__ __forceinline__ uint32_t itx_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +90,12 @@ __device__ __forceinline__ bool itx_mbar_try_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
+}
+__device__ __forceinline__ void itx_cp_async16(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void itx_cp_async8(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void itx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void itx_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 /* bounded wait with back-off: a copy that never lands sets status bit 4 instead of hanging the device */
 __device__ __noinline__ bool itx_mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t *status) {
@@ -168,88 +176,114 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
     __syncwarp();
     if (blockIdx.x == 0 && threadIdx.x == 0) *A.winbad = 0;
     uint32_t parity = 0;
-    const itx_src_global G{A.b};
     bool dead = false;
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(&A.work[0], 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= A.nchunks || dead) break;
+        /* span-relative 32-bit offsets, sentinels 0xfffffffe (chain ended) / 0xffffffff (no guess), as in k_scan */
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
-        /* the span's first record start: known for the window's first span, guessed otherwise */
-        unsigned long long p;
-        if (i == 0) p = *A.carry;
-        else {
-            p = ITX_OFF_NONE;
-            for (unsigned long long base = lo; base < hi; base += 32) {
-                const unsigned long long q = base + lane;
-                const bool ok = q < hi && itx_plausible2(G, q, A.len, A.n_ref);
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
-            }
+        const uint32_t hi = A.len - lo < A.C ? (uint32_t)(A.len - lo) : A.C;
+        uint32_t p = 0xffffffffu;
+        bool guess = i != 0;
+        if (!guess) {
+            const unsigned long long p0 = *A.carry;
+            if (lane == 0) A.entry[i] = p0;
+            p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
         }
-        if (lane == 0) A.entry[i] = p;
         itx_tuple *out = A.tuples + (size_t)i * A.S;
-        uint32_t n_out = 0;
-        while (p < hi) {                                   /* ITX_OFF_END / ITX_OFF_NONE are above any hi */
-            const unsigned long long c_lo = lo + ((p - lo) & ~(unsigned long long)(ITX_STAGE - 1));
-            unsigned long long c_hi = c_lo + ITX_STAGE; if (c_hi > hi) c_hi = hi;
-            const unsigned long long rest = A.len - c_lo;
-            const uint32_t nb = rest > STG ? STG : (uint32_t)rest;
-            const uint32_t bytes = (nb + 15u) & ~15u;      /* the buffer's 64 bytes of slack cover the round-up */
-            __syncwarp();                                  /* every lane is done reading the previous stage */
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                itx_mbar_expect_tx(bar_s, bytes);
-                itx_bulk_g2s(buf_s, A.b + c_lo, bytes, bar_s);
+        uint32_t n_out = 0, staged = 0xffffffffu, nb = 0, szd = 0;
+        for (;;) {
+            if (guess ? hi == 0u : !(p < hi)) { if (guess && lane == 0) A.entry[i] = ITX_OFF_NONE; break; }
+            const uint32_t c_lo = guess ? 0u : p & ~(ITX_STAGE - 1u);
+            const uint32_t c_hi = c_lo + ITX_STAGE < hi ? c_lo + ITX_STAGE : hi;
+            const unsigned long long rest = A.len - lo - c_lo;
+            if (staged != c_lo) {
+                nb = rest > STG ? STG : (uint32_t)rest;
+                const uint32_t bytes = (nb + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */
+                __syncwarp();                                  /* every lane is done reading the previous stage */
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    itx_mbar_expect_tx(bar_s, bytes);
+                    itx_bulk_g2s(buf_s, A.b + lo + c_lo, bytes, bar_s);
+                    if (c_lo + ITX_STAGE < hi && rest >= STG + ITX_STAGE) itx_prefetch_l2(A.b + lo + c_lo + STG, ITX_STAGE);
+                }
+                if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
+                parity ^= 1u;
+                staged = c_lo;
             }
-            if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
-            parity ^= 1u;
-            /* the chain of this stage, out of shared memory.  Reads usually have one length, so instead of one
-             * record per step the warp tests 32 predicted starts at once: lane k looks at q + k * size and the run
-             * of lanes that find the same block_size there is accepted in one step (a run of 1 is the plain walk).
-             * Every block_size word read lies inside the staged bytes (the margin is larger than a core). */
-            uint32_t n = 0, ended = 0;
-            uint32_t q = (uint32_t)(p - c_lo);
+            if (guess) {
+                /* the span's first record start, guessed out of its first stage: itx_plausible2's test on 32 offsets per step */
+                const itx_src_stage S0{buf, A.b, lo, nb};
+                for (uint32_t base = 0; base < hi; base += 32) {
+                    const uint32_t d = base + lane;
+                    const unsigned long long q = lo + d;
+                    bool ok = false;
+                    if (d < hi && q + 36 <= A.len) {
+                        uint32_t x[9], lq; uint64_t nx, nx2;
+                        S0.core(q, x);
+                        ok = itx_plausible_core(x, q, A.len, A.n_ref, &lq, &nx);
+                        if (ok) ok = S0.u8(q + 36 + lq - 1) == 0 && (nx == A.len || itx_plausible(S0, nx, A.len, A.n_ref, &nx2));
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                    if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
+                }
+                if (lane == 0) A.entry[i] = p == 0xffffffffu ? ITX_OFF_NONE : lo + p;
+                guess = false;
+                continue;
+            }
+            /* the chain of this stage (see k_scan): run prediction with the span's dominant record size */
+            uint32_t n = 0;
+            uint32_t q = p - c_lo;
             {
-                const uint32_t qh = (uint32_t)(c_hi - c_lo);
-                const unsigned long long room = A.len - c_lo;                     /* a record must end at or before room */
-                const uint32_t room32 = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
-                const uint32_t av32 = A.avail > c_lo ? (A.avail - c_lo > 0x7fffffffull ? 0x7fffffffu : (uint32_t)(A.avail - c_lo)) : 0u;
+                const uint32_t qh = c_hi - c_lo;
+                const uint32_t room32 = rest > 0x7fffffffull ? 0x7fffffffu : (uint32_t)rest;
+                uint32_t q_end = q;
                 while (q < qh) {
-                    if (q + 36u > room32) { ended = 1; break; }
+                    q_end = q;
+                    if (q + 36u > room32) { q = 0xffffffffu; break; }
                     const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
                     const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
-                    const uint32_t sz = bs0 + 4u;
-                    if ((int32_t)bs0 < 32 || q + sz < q || q + sz > room32) { ended = 1; break; }
-                    const unsigned long long pk = (unsigned long long)q + (unsigned long long)lane * sz;
-                    bool same = false;
-                    if (pk < qh && pk + sz <= room32) {
-                        const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + ((uint32_t)pk & ~3u));
-                        same = itx_funnel_r(wk[0], wk[1], ((uint32_t)pk & 3u) * 8u) == bs0;
+                    const uint32_t sz0 = bs0 + 4u;
+                    if ((int32_t)bs0 < 32 || sz0 > room32 - q) { q = 0xffffffffu; break; }
+                    const uint32_t szp = szd ? szd : sz0;
+                    uint32_t run = 1u, pk = q;
+                    if ((sz0 | szp) < 0x10000u) {
+                        pk = lane ? q + sz0 + (lane - 1u) * szp : q;
+                        bool same = true;
+                        if (lane) {
+                            same = false;
+                            if (pk < qh && pk + szp <= room32) {
+                                const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + (pk & ~3u));
+                                same = itx_funnel_r(wk[0], wk[1], (pk & 3u) * 8u) + 4u == szp;
+                            }
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, same);
+                        run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     }
-                    const uint32_t m = __ballot_sync(0xffffffffu, same);           /* bit 0 is always set */
-                    const uint32_t run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     if (lane < run && n + lane < ITX_POS_SLOTS) pos[n + lane] = (uint16_t)pk;
                     n += run;
-                    q += run * sz;
-                    if (q > av32 && lane == 0) atomicOr(&A.status[0], 2u);         /* record longer than the staged window */
+                    q += sz0 + (run - 1u) * szp;
+                    szd = run >= 2u ? szp : 0u;
                 }
+                if (q != 0xffffffffu) q_end = q;
+                if (lane == 0 && A.avail < lo + c_lo + q_end) atomicOr(&A.status[0], 2u);
             }
             __syncwarp();
-            const itx_src_stage S{buf, A.b, c_lo, nb};
+            const unsigned long long c_lo64 = lo + c_lo;
+            const itx_src_stage S{buf, A.b, c_lo64, nb};
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t ro = pos[j];
-                uint32_t x[9]; S.core(c_lo + ro, x);
-                const itx_tuple T = itx_decode_record(S, c_lo + ro, x, (uint32_t)(c_lo - lo) + ro, A.tid, A.n_ref, A.o);
+                uint32_t x[9]; S.core(c_lo64 + ro, x);
+                const itx_tuple T = itx_decode_record(S, c_lo64 + ro, x, c_lo + ro, A.tid, A.n_ref, A.o);
                 if (n_out + j < A.S) __stcs(reinterpret_cast<uint4 *>(out + n_out + j), make_uint4(T.start, T.end, T.info, T.rec_off));
             }
             n_out += n;
-            if (ended) { p = ITX_OFF_END; break; }
+            if (q == 0xffffffffu) { p = 0xfffffffeu; break; }
             p = c_lo + q;
         }
-        if (lane == 0) { A.exit_[i] = p; A.nrec[i] = n_out < A.S ? n_out : A.S; }
+        if (lane == 0) { A.exit_[i] = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p; A.nrec[i] = n_out < A.S ? n_out : A.S; }
     }
 }
 
@@ -524,7 +558,9 @@ struct itx_scan_args {
                                           * copy, chain walk and decode go on (coordinate-sorted reads move up the table a few entries per round) */
 #define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD)
 #define ITX_WIN 32u                      /* table entries per warp window */
+#ifndef ITX_SCAN_NW
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
+#endif
 #define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
 /* shared memory of a k_scan CTA of NW warps: stages, record-start slots, mbarriers, table windows; the histogram follows */
 /* one contiguous block per warp (every pointer is the warp's base plus a constant) */
@@ -532,12 +568,6 @@ struct itx_scan_args {
 #define ITX_SCAN_SMEM_BASE(NW) ((NW) * ITX_SCAN_WARP_BYTES)
 #define ITX_SCAN_CTAS(NW) ((NW) <= 8 ? 3 : 2)          /* 8 warps x 3 CTAs (80 registers) or 14 warps x 2 CTAs (72 registers) per SM */
 
-__device__ __forceinline__ void itx_cp_async16(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void itx_cp_async8(void *smem_dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void itx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void itx_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 /* table loads of a walk: the warp's window when the index falls into it, global memory otherwise (same values either way) */
 struct itx_iv_window {
     const itx_dev_index &D; const int4 *win; uint32_t base, n;

@@ -17,4 +17,3 @@ PY
 }
 run w14 ITX_SCAN_WARPS=14
 run w8 ITX_SCAN_WARPS=8
-EXTRA="--mode 2 --reads 25000000" run w14_pe ITX_SCAN_WARPS=14
