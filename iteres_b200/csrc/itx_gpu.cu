@@ -41,6 +41,7 @@ struct itx_cuda {
     uint64_t cap_log;                                         /* spans the entry / exit logs hold (one launch group of k_scan, >= cap_chunks) */
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
+    unsigned long long *h_scratch;                            /* pinned: the small values a scan uploads (no wait for the copy) */
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
     int scan_ctas[4];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
@@ -56,6 +57,7 @@ struct itx_cuda {
     FILE *bed_f, *bed_uf; int bed_owner;             /* opened by the outermost entry point of the run */
     uint64_t ord_cap;                                /* trace entries one launch group may need (0: not in ordered mode) */
     itx_trace *h_ord_trace; uint64_t h_ord_trace_cap; uint8_t *h_ord_buf; uint64_t h_ord_buf_cap;
+    int dirty_el;                                    /* the per-locus block may hold another rank's counts (an allreduce covers the whole u32 block) */
     int used_el, used_cpg, used_cpg_el, host_el, host_cpg, host_cpg_el;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
@@ -99,6 +101,7 @@ static void cuda_free_all(itx_cuda *cu) {
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
+    if (cu->h_scratch) cudaFreeHost(cu->h_scratch);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
     if (cu->marks_made) for (int i = 0; i < 8; i++) cudaEventDestroy(cu->marks[i]);
     if (cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) { cudaStreamDestroy(cu->inf_stream[i]); cudaEventDestroy(cu->inf_done[i]); }
@@ -115,12 +118,17 @@ extern "C" void itx_index_free(itx_index *ix) {
     free(ix);
 }
 
-static int zero_counters(itx_index *ix, char *err) {
+/* all = 0: only the blocks a scan has touched since they were last zeroed (the per-locus and CpG blocks are large and
+ * most runs never write them) */
+static int zero_counters(itx_index *ix, char *err, int all) {
     itx_cuda *cu = ix->cu;
+    const size_t bp2 = 2 * (size_t)ix->bp_len;
     CK(cudaMemsetAsync(cu->d_u64, 0, cu->n_u64 * 8, cu->stream));
-    CK(cudaMemsetAsync(cu->d_u32, 0, cu->n_u32 * 4, cu->stream));
-    CK(cudaMemsetAsync(cu->d_cpg_u32, 0, cu->n_cpg_u32 * 4, cu->stream));
-    CK(cudaMemsetAsync(cu->d_cpg_f64, 0, cu->n_cpg_f64 * 8, cu->stream));
+    CK(cudaMemsetAsync(cu->d_u32, 0, ((all || cu->used_el || cu->dirty_el) ? cu->n_u32 : bp2) * 4, cu->stream));
+    if (all || cu->used_cpg || cu->used_cpg_el) {
+        CK(cudaMemsetAsync(cu->d_cpg_u32, 0, cu->n_cpg_u32 * 4, cu->stream));
+        CK(cudaMemsetAsync(cu->d_cpg_f64, 0, cu->n_cpg_f64 * 8, cu->stream));
+    }
     CK(cudaMemsetAsync(cu->d_misc, 0, (ITX_MAX_TID_SEEN + 8) * 4, cu->stream));
     CK(cudaStreamSynchronize(cu->stream));
     return ITX_OK;
@@ -129,8 +137,8 @@ static int zero_counters(itx_index *ix, char *err) {
 extern "C" void itx_index_reset_counts(itx_index *ix) {
     char err[ITX_ERRLEN];
     cudaSetDevice(ix->cu->device);
-    zero_counters(ix, err);
-    ix->cu->used_el = ix->cu->used_cpg = ix->cu->used_cpg_el = 0;
+    zero_counters(ix, err, 0);
+    ix->cu->used_el = ix->cu->used_cpg = ix->cu->used_cpg_el = ix->cu->dirty_el = 0;
     if (ix->cu->d_dup_keys) {        /* forget the reads of the previous run */
         cudaMemset(ix->cu->d_dup_keys, 0xff, ix->cu->dup_cap * sizeof(itx_k128)); cudaMemset(ix->cu->d_dup_ords, 0xff, ix->cu->dup_cap * 8);
         cudaMemset(ix->cu->d_dup_mins, 0xff, 16); cudaMemset(ix->cu->d_dup_mins + 2, 0, 8);
@@ -201,6 +209,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaMalloc((void **)&cu->d_carry_log, ITX_MAX_WINDOWS * 8)); CKN(cudaMalloc((void **)&cu->d_fused, 8));
+        CKN(cudaHostAlloc((void **)&cu->h_scratch, 64, cudaHostAllocDefault));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -217,7 +226,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         D.grp_cpg_score = (double *)cu->d_cpg_f64; D.bp_cpg = D.grp_cpg_score + ng; D.el_cpg_score = D.bp_cpg + ix->bp_len;
         D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
         CKN(cudaMalloc(&cu->d_D, sizeof D)); CKN(cudaMemcpy(cu->d_D, &D, sizeof D, cudaMemcpyHostToDevice));
-        if (zero_counters(ix, err)) goto fail;
+        if (zero_counters(ix, err, 1)) goto fail;
     }
     ix->tune_chunk = 65536; ix->tune_window = 1ull << 30; ix->tune_threads = 0;
     return ix;
@@ -438,8 +447,8 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     if (sc->ordered && (rc = ordered_begin(sc, o, err))) return rc;
     sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
     sc->k_next = sc->k_first;
-    unsigned long long carry = h->hdr_len;
-    CK(cudaMemcpyAsync(cu->d_carry, &carry, 8, cudaMemcpyHostToDevice, cu->stream));
+    cu->h_scratch[0] = h->hdr_len;              /* the previous scan ended with a synchronize: its copy out of the scratch is long done */
+    CK(cudaMemcpyAsync(cu->d_carry, cu->h_scratch, 8, cudaMemcpyHostToDevice, cu->stream));
     CK(cudaMemsetAsync(cu->d_work, 0, 16, cu->stream));
     CK(cudaMemsetAsync(cu->D.status, 0, 8 * sizeof(uint32_t), cu->stream));      /* per-scan flags and failure counts */
     {   /* ITX_DECODE_KERNEL=thread selects the one-thread-per-chunk kernel (A/B measurement); chunks that are not whole tiles use it too */
@@ -447,13 +456,13 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
         cu->decode_variant = ((v && strcmp(v, "thread") == 0) || (cu->C % ITX_STAGE) != 0 || cu->C > (1u << 20)) ? 1 : 0;
         if (((uintptr_t)d_bam & 15) != 0) cu->decode_variant = 1;
     }
-    if (ix->trace_cap || sc->ordered) { unsigned long long z = 0; CK(cudaMemcpyAsync(cu->d_running, &z, 8, cudaMemcpyHostToDevice, cu->stream)); }
+    if (ix->trace_cap || sc->ordered) CK(cudaMemsetAsync(cu->d_running, 0, 8, cu->stream));
     {   /* one fused kernel per launch group unless something needs the tuples (-R, the ordered outputs, traces, ITX_FUSED=0) */
         const char *v = getenv("ITX_FUSED");
         sc->fused = !(v && strcmp(v, "0") == 0) && cu->decode_variant == 0 && !sc->rmdup && !sc->ordered && !ix->trace_cap && !cu->want_sel;
         if (sc->fused) { CK(cudaMemsetAsync(cu->d_fused, 0xff, 4, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 1, 0, 4, cu->stream)); }
     }
-    CK(cudaStreamSynchronize(cu->stream));   /* the 8-byte sources live on this stack frame */
+    if (!resident) CK(cudaStreamSynchronize(cu->stream));      /* the streaming paths go on to use other streams (copies, inflate) that read the flags just reset */
     return ITX_OK;
 }
 static itx_decode_args decode_args(const scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len) {
@@ -589,22 +598,24 @@ static int fused_replay(scan_ctx *sc, uint32_t first, char *err) {
 static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
     ordered_end(sc);
+    /* one round trip for everything the host reads at the end of a scan: the chain verdict of k_scan, the 13 counters, the flags */
+    unsigned long long hc[16]; uint32_t st[8]; uint32_t first_bad = 0xffffffffu;
+    if (sc->fused) CK(cudaMemcpyAsync(&first_bad, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaStreamSynchronize(cu->stream));
     if (sc->fused) {
-        uint32_t first_bad = 0xffffffffu;
-        CK(cudaMemcpyAsync(&first_bad, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
-        CK(cudaStreamSynchronize(cu->stream));
         if (first_bad == 0xffffffffu && sc->n_win && getenv("ITX_FUSED_TEST_REPLAY")) first_bad = 0;      /* test hook: replay everything */
         if (first_bad != 0xffffffffu) {
             int rc = fused_replay(sc, first_bad, err);
             if (rc) { free(sc->wins); sc->wins = NULL; return rc; }
             ix->prof.n_replayed_windows = sc->n_win - first_bad;
+            CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
+            CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
+            CK(cudaStreamSynchronize(cu->stream));
         }
         free(sc->wins); sc->wins = NULL;
     }
-    unsigned long long hc[16]; uint32_t st[8];
-    CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
-    CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
-    CK(cudaStreamSynchronize(cu->stream));
     for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k];
     if (cnt) memcpy(cnt, ix->cnt, sizeof ix->cnt);
     itx_profile *P = &ix->prof;
@@ -1357,6 +1368,7 @@ extern "C" int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     int r = gs();
     if (!r) r = ar(cu->d_u64, cu->d_u64, cu->n_u64, ncclUint64, ncclSum, cu->nccl_comm, cu->stream);
     if (!r && cu->n_u32) r = ar(cu->d_u32, cu->d_u32, cu->n_u32, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
+    cu->dirty_el = 1;
     int r2 = ge(); if (!r) r = r2;
     if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclAllReduce failed (%d)", r); return ITX_ENODEV; }
     unsigned long long hc[16];

@@ -346,7 +346,7 @@ ITX_HD uint32_t itx_ovl(uint32_t start, uint32_t end, int32_t es, int32_t ee) {
  * (the quotient of the two rounded floats is then >= 2^-12 * (1 - 2^-22) > 2^-13 >= thr): no division. */
 ITX_HD float itx_cov_thr(uint32_t r, uint32_t den, float thr) {
     if (r != 0 && r == den) return 1.0f;
-    if (thr <= ITX_COV_FLOOR && den != 0 && ((uint64_t)r << 12) >= (uint64_t)den) return ITX_COV_FLOOR;
+    if (thr <= ITX_COV_FLOOR && den != 0 && r >= (den >> 12) + ((den & 0xfffu) ? 1u : 0u)) return ITX_COV_FLOOR;      /* r * 2^12 >= den */
     const float d = (float)den;
     return d == 0.0f ? 0.0f : (float)(int32_t)r / d;
 }
