@@ -417,7 +417,7 @@ def main():
         e2e_t = sum(times) / len(times)
         e2e = {"value": total_rec / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(pe["h2d_bytes"]), "d2h_bytes_per_step": int(pe["d2h_bytes"]),
                "s_per_step": e2e_t, "steps": len(times), "api": "itx_scan_alignments(BGZF .bam, deflate level 1) + itx_sync_counts",
-               "inflate": ("host zlib threads" if pe["inflate_threads"] else "device: k_inflate (Huffman pass, one thread per BGZF block) + k_lz_resolve (match copies, one CTA per block), groups of 8192 blocks on 8 streams"),
+               "inflate": ("host zlib threads" if pe["inflate_threads"] else "device: k_inflate (Huffman pass, one thread per BGZF block) + k_lz_resolve (match copies, one CTA per block), groups of 16384 blocks on 8 streams"),
                "inflate_threads": int(pe["inflate_threads"]), "inflate_ms": pe["inflate_ms"],
                "scan_stream_ms": pe["decode_ms"] + pe["overlap_ms"],      # event time on the scan stream: includes its waits on the inflate streams
                "bam_bytes": os.path.getsize(bam)}

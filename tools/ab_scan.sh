@@ -15,5 +15,6 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run w14 ITX_SCAN_WARPS=14
-run w8 ITX_SCAN_WARPS=8
+run f31 ITX_SCAN_FLAGS=31
+run f15 ITX_SCAN_FLAGS=15
+EXTRA="--mode 2 --reads 25000000" run f31_pe ITX_SCAN_FLAGS=31
