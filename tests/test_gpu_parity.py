@@ -291,6 +291,39 @@ def test_fused_and_tuple_paths_count_the_same(case, mode, worlds, monkeypatch):
     ix.close()
 
 
+@pytest.mark.parametrize("flags,warps", [(0, 14), (3, 14), (4, 14), (12, 14), (15, 8)])
+@pytest.mark.parametrize("case", [SYN[1], SYN[2], SYN[4]], ids=lambda c: c[0])
+def test_scan_kernel_switches_never_change_the_counts(case, flags, warps, worlds, monkeypatch):
+    """k_scan's A/B switches (L2 prefetch, dominant-size chain walk, table window, window look-ahead, warps per CTA) are
+    performance choices only: every combination gives the oracle's numbers, on a resident stream taken as ONE launch
+    group as well as through the host path"""
+    name, shape, n_rmsk, rmode, n_units, kw = case
+    monkeypatch.setenv("ITX_SCAN_FLAGS", str(flags))
+    monkeypatch.setenv("ITX_SCAN_WARPS", str(warps))
+    s, (cs, rs, rm), _ = worlds(shape, n_rmsk)
+    buf, n, nrec = s.stream(rmode, n_units)
+    raw = buf[:n].tobytes()
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_stream(raw, O.default_opts(**kw))
+    ix = capi.Index(cs, rs, rm)
+    ix.tune(chunk_bytes=4096)                                  # many spans per warp, one launch group
+    L = capi.lib()
+    a = np.frombuffer(raw + b"\0" * 64, dtype=np.uint8)
+    d = L.itx_dev_alloc(len(a))
+    assert d and L.itx_dev_upload(d, a.ctypes.data, len(a)) == 0
+    hdr = ix.header(a.ctypes.data, n)
+    assert ix.scan_bam_device(hdr, d, n, capi.default_opts(**kw)) == want
+    assert ix.profile()["fused"] == 1 and ix.profile()["n_launches"] == 1
+    assert_same_tables(ix, ora)
+    ix.reset()
+    assert ix.scan_stream(raw, capi.default_opts(**kw)) == want
+    assert_same_tables(ix, ora)
+    L.itx_bam_header_free(hdr)
+    L.itx_dev_free(d)
+    ora.close()
+    ix.close()
+
+
 def test_damaged_bgzf_block_is_reported(worlds, tmp_path, monkeypatch):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bam = str(tmp_path / "reads.bam")
