@@ -18,6 +18,8 @@
 
 #define ITX_SLACK 64
 #define ITX_MAX_EVENTS 4096
+#define ITX_SEEN_FAST 1024                 /* unknown-tid marks fetched with the end-of-scan report (BAM headers with more references take one more copy) */
+#define ITX_SCRATCH_BYTES (256 + ITX_SEEN_FAST * 4)
 #define ITX_MAX_WINDOWS 65536              /* launch groups of one scan that k_scan can log (more: the tuple path takes over) */
 #define ITX_INF_STREAMS 8                  /* inflate groups in flight: copy, Huffman pass, match pass and scan of different groups overlap */
 
@@ -41,7 +43,8 @@ struct itx_cuda {
     uint64_t cap_log;                                         /* spans the entry / exit logs hold (one launch group of k_scan, >= cap_chunks) */
     itx_tuple *d_tuples; unsigned long long *d_entry, *d_exit, *d_carry, *d_rec_base, *d_running; uint32_t *d_nrec, *d_winbad;
     long long *d_sel; int want_sel;
-    unsigned long long *h_scratch;                            /* pinned: the small values a scan uploads (no wait for the copy) */
+    unsigned long long *h_scratch;                            /* pinned: [0] the carry a scan uploads (no wait for the copy); from byte 64 the end-of-scan report:
+                                                               * cnt[16] u64, status[8] u32, first bad launch group u32, then (byte 256) the first ITX_SEEN_FAST unknown-tid marks */
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
     int scan_ctas[4];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
@@ -209,7 +212,7 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
         CKN(cudaMalloc((void **)&cu->d_carry_log, ITX_MAX_WINDOWS * 8)); CKN(cudaMalloc((void **)&cu->d_fused, 8));
-        CKN(cudaHostAlloc((void **)&cu->h_scratch, 64, cudaHostAllocDefault));
+        CKN(cudaHostAlloc((void **)&cu->h_scratch, ITX_SCRATCH_BYTES, cudaHostAllocDefault));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -598,20 +601,27 @@ static int fused_replay(scan_ctx *sc, uint32_t first, char *err) {
 static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
     ordered_end(sc);
-    /* one round trip for everything the host reads at the end of a scan: the chain verdict of k_scan, the 13 counters, the flags */
-    unsigned long long hc[16]; uint32_t st[8]; uint32_t first_bad = 0xffffffffu;
-    if (sc->fused) CK(cudaMemcpyAsync(&first_bad, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
-    CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
-    CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
+    /* one round trip for everything the host reads at the end of a scan -- the chain verdict of k_scan, the 13 counters, the
+     * flags, the unknown-tid marks -- into pinned memory, so the four copies queue up behind the kernels without a wait each */
+    unsigned long long *hc = cu->h_scratch + 8; uint32_t *st = (uint32_t *)(cu->h_scratch + 24); uint32_t *first_bad_p = st + 8;
+    uint32_t *seen_fast = (uint32_t *)((uint8_t *)cu->h_scratch + 256);
+    const int32_t nt = sc->h->n_ref < ITX_MAX_TID_SEEN ? sc->h->n_ref : ITX_MAX_TID_SEEN, nt_fast = nt < ITX_SEEN_FAST ? nt : ITX_SEEN_FAST;
+    *first_bad_p = 0xffffffffu;
+    if (sc->fused) CK(cudaMemcpyAsync(first_bad_p, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(hc, cu->D.cnt, 16 * 8, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(st, cu->D.status, 8 * 4, cudaMemcpyDeviceToHost, cu->stream));
+    if (nt_fast > 0) CK(cudaMemcpyAsync(seen_fast, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt_fast, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaStreamSynchronize(cu->stream));
+    uint32_t first_bad = *first_bad_p;
     if (sc->fused) {
         if (first_bad == 0xffffffffu && sc->n_win && getenv("ITX_FUSED_TEST_REPLAY")) first_bad = 0;      /* test hook: replay everything */
         if (first_bad != 0xffffffffu) {
             int rc = fused_replay(sc, first_bad, err);
             if (rc) { free(sc->wins); sc->wins = NULL; return rc; }
             ix->prof.n_replayed_windows = sc->n_win - first_bad;
-            CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
-            CK(cudaMemcpyAsync(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost, cu->stream));
+            CK(cudaMemcpyAsync(hc, cu->D.cnt, 16 * 8, cudaMemcpyDeviceToHost, cu->stream));
+            CK(cudaMemcpyAsync(st, cu->D.status, 8 * 4, cudaMemcpyDeviceToHost, cu->stream));
+            if (nt_fast > 0) CK(cudaMemcpyAsync(seen_fast, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt_fast, cudaMemcpyDeviceToHost, cu->stream));
             CK(cudaStreamSynchronize(cu->stream));
         }
         free(sc->wins); sc->wins = NULL;
@@ -628,29 +638,33 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     if (sc->ev_n >= 3) { float t = 0; cudaEventElapsedTime(&t, cu->ev[0], cu->ev[sc->ev_n - 1]); P->total_ms = t; }
     P->n_records = ix->cnt[0] + ix->cnt[1]; P->n_fragments = ix->cnt[6]; P->stream_bytes = sc->len;
     P->n_launches = (uint64_t)sc->n_launch; P->n_bad_chunks = st[1]; P->fused = sc->fused;
-    P->d2h_bytes = sizeof hc + sizeof st;
+    P->d2h_bytes = 16 * 8 + 8 * 4 + sizeof(uint32_t) * (size_t)nt;
     if (sc->rmdup) cu->dup_ord_base += (sc->k_end + 1) * (uint64_t)cu->S;           /* the next file's reads come after this file's */
     if (st[4]) { snprintf(err, ITX_ERRLEN, "the -R key table overflowed"); return ITX_ENOMEM; }
     if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA bulk copy never completed (device-side time-out in k_decode_span)"); return ITX_ENODEV; }
     if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
     /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */
-    if (sc->h->n_ref > 0) {
-        int32_t nt = sc->h->n_ref < ITX_MAX_TID_SEEN ? sc->h->n_ref : ITX_MAX_TID_SEEN;
-        uint32_t *seen = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nt);
-        if (cudaMemcpy(seen, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt, cudaMemcpyDeviceToHost) == cudaSuccess) {
-            for (int32_t t = 0; t < nt; t++) if (seen[t]) {
-                char nm[600]; const char *raw = sc->h->names[t];
-                if (sc->h->addChr && strcasecmp(raw, "MT") == 0) snprintf(nm, sizeof nm, "chrM");
-                else if (sc->h->addChr && strncmp(raw, "chr", 3) != 0) snprintf(nm, sizeof nm, "chr%s", raw);
-                else snprintf(nm, sizeof nm, "%s", raw);
-                if (itx_strtab_find(&ix->warned, nm) < 0) {
-                    itx_strtab_add(&ix->warned, nm);
-                    fprintf(stderr, "* Warning: read ends mapped to chromosome %s will be discarded as %s not existed in the chromosome size file\n", nm, nm);
-                }
-            }
-            cudaMemsetAsync(cu->D.tid_unknown_seen, 0, sizeof(uint32_t) * (size_t)nt, cu->stream);
+    if (nt > 0) {
+        uint32_t *seen = seen_fast, *big = NULL;
+        if (nt > nt_fast) {
+            big = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nt);
+            if (!big || cudaMemcpy(big, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt, cudaMemcpyDeviceToHost) != cudaSuccess) { free(big); big = NULL; }
+            seen = big;
         }
-        free(seen);
+        bool any = false;
+        if (seen) for (int32_t t = 0; t < nt; t++) if (seen[t]) {
+            any = true;
+            char nm[600]; const char *raw = sc->h->names[t];
+            if (sc->h->addChr && strcasecmp(raw, "MT") == 0) snprintf(nm, sizeof nm, "chrM");
+            else if (sc->h->addChr && strncmp(raw, "chr", 3) != 0) snprintf(nm, sizeof nm, "chr%s", raw);
+            else snprintf(nm, sizeof nm, "%s", raw);
+            if (itx_strtab_find(&ix->warned, nm) < 0) {
+                itx_strtab_add(&ix->warned, nm);
+                fprintf(stderr, "* Warning: read ends mapped to chromosome %s will be discarded as %s not existed in the chromosome size file\n", nm, nm);
+            }
+        }
+        if (any) cudaMemsetAsync(cu->D.tid_unknown_seen, 0, sizeof(uint32_t) * (size_t)nt, cu->stream);
+        free(big);
     }
     return ITX_OK;
 }
