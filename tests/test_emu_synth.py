@@ -226,3 +226,60 @@ def test_emu_query_matches_oracle_on_nested_table(tmp_path):
     assert seen >= {0, 1, 2, 3, 4, 5}
     ora.close()
     emu.close()
+
+
+XA_ODD = [
+    "chr1,+5101,36M,1;",                                  # plain: another subfamily at 5101 -> discarded
+    "chr1,+5101,36M,1",                                   # no trailing separator
+    "chr1,+5101,36M,2;",                                  # nm2 > NM: ignored
+    "",                                                   # empty string: no pieces
+    ";",                                                  # one empty piece
+    ";;chr1,+5101,36M,1;;",                               # empty pieces around a real one
+    "chr1,+5101,36M;",                                    # three fields: malformed, skipped
+    "chr1,+5101;chr1,+5101,36M,1;",                       # malformed first, real second
+    "chr1,+5101,36M,1,extra,more;",                       # the fourth field stops at the next comma
+    "chr1,+5101,36M,;",                                   # empty fourth field: strtol("") = 0 <= NM
+    "chr1,,36M,1;",                                       # empty position: 0
+    ",+5101,36M,1;",                                      # empty chromosome name: unknown
+    "chrQ,+5101,36M,1;chr1,-5101,36M,0;",                 # unknown chromosome, then a hit on the minus strand
+    "chr1,0x13ed,36M,1;",                                 # strtol base 0: hexadecimal 5101
+    "chr1,011755,36M,01;",                                # octal 5101, octal 1
+    "chr1, +5101,36M, 1;",                                # leading white space is strtol's
+    "chr1,+5101x,36M,1z;",                                # trailing garbage stops the parse
+    "chr1,+1101,36M,0;",                                  # the same subfamily: kept
+    "chr1,+99999999999,36M,1;",                           # overflow saturates, (int) keeps the low word
+    "chr1,+5101,36M,1;" * 99 + "chr1,+1101,36M,0;",       # 100 pieces, the last one harmless... but an earlier one hits
+    "chr1,+1101,36M,0;" * 100 + "chr1,+5101,36M,1;",      # the 101st piece is never looked at
+    "chr1,+1101,36M,0;" * 99 + "chr1,+5101,36M,1;",       # the 100th is
+]
+
+
+def test_xa_strings_of_every_shape(tmp_path):
+    """mapped2diffSubfam (generic.c:303-341) on alternate lists that chopByChar / strtol treat in their own ways: the
+    device logic's single pass over the string against the oracle, read by read"""
+    import bamio
+    import kats
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
+    reads = []
+    for k, xa in enumerate(XA_ODD):
+        for ty in ("Z", "H"):
+            reads.append(kats.se("x%d%s" % (k, ty), 0, 1050, 0, aux=[("NM", "i", 1), ("XA", ty, xa)]))
+    reads.append(kats.se("xi", 0, 1050, 0, aux=[("NM", "i", 1), ("XA", "i", 7)]))          # XA that is not a string
+    reads.append(kats.se("xnm", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,0;")]))      # no NM: 0
+    raw = bamio.encode_header([("chr1", 1000000)]) + b"".join(bamio.encode_record(r) for r in reads)
+    ora = O.OracleIndex(cs, rs, rm)
+    cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(), trace=True)
+    for chunk in (256, 4096):
+        emu = emu_lib.EmuIndex(cs, rs, rm, chunk=chunk)
+        cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(), trace=True)
+        assert cnt_e == cnt_o
+        mask = ~np.uint32(8 | 64)
+        bad = np.nonzero((tr_e["flags"] & mask) != (tr_o["flags"] & mask))[0]
+        assert len(bad) == 0, [reads[i]["qname"] for i in bad]
+        emu.close()
+    assert 0 < cnt_o[12] < len(reads)
+    ora.close()
