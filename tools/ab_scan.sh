@@ -15,6 +15,11 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run f31 ITX_SCAN_FLAGS=31
-run f15 ITX_SCAN_FLAGS=15
-EXTRA="--mode 2 --reads 25000000" run f31_pe ITX_SCAN_FLAGS=31
+run all ITX_SCAN_FLAGS=15
+run none ITX_SCAN_FLAGS=0
+run prefetch ITX_SCAN_FLAGS=1
+run domsize ITX_SCAN_FLAGS=2
+run window ITX_SCAN_FLAGS=4
+run window_ahead ITX_SCAN_FLAGS=12
+run all_w8 ITX_SCAN_FLAGS=15 ITX_SCAN_WARPS=8
+EXTRA="--mode 2 --reads 25000000" run all_pe ITX_SCAN_FLAGS=15
