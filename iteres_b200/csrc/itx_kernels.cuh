@@ -1,22 +1,31 @@
 /* itx_kernels.cuh -- the sm_100a kernels of the iteres hot path.
  *
- *   k_decode_span K1  record boundaries + bam1_core_t unpack + fragment logic in ONE streaming pass.  The stream
- *                    is cut into spans; a warp takes a span, GUESSES its first record start with a warp-wide
- *                    structural test, then carries the block_size chain through the span stage by stage: each
- *                    4 KiB stage (+1 KiB margin) lands in shared memory through one 1-D TMA bulk copy
- *                    (cp.async.bulk + mbarrier), lane 0 walks the chain of the stage out of shared memory, and
- *                    every lane decodes one record per round and the warp stores 32 tuples with one coalesced
- *                    512-byte store.                           replaces bam_read1 / bam_calend / bam_aux_get
+ *   k_scan      K1+K2+K3  the product path: record boundaries, bam1_core_t unpack, fragment logic, interval overlap,
+ *                    "last ascent" selection, XA:Z alternate test and accumulation in ONE pass; nothing but counters
+ *                    is written.  The stream is cut into spans; a warp takes a span, GUESSES its first record start
+ *                    out of the span's first staged bytes (32 offsets per step, branch-free structural test), then
+ *                    carries the block_size chain through the span stage by stage: each 4 KiB stage (+1 KiB margin)
+ *                    lands in the warp's shared memory through one 1-D TMA bulk copy (cp.async.bulk + mbarrier) while
+ *                    the next stage's bytes are asked into L2; the chain of a stage is walked with run prediction on
+ *                    the span's dominant record size; every lane then decodes one record per round and looks its
+ *                    fragment up in a 32-entry window of the interval table that sits in shared memory (fetched a
+ *                    stage ahead with cp.async).  The spans' entries and exits are logged and checked by the last
+ *                    CTA; a failed guess is undone exactly (sign = -1) and replayed through the tuple path.
+ *                                                              replaces bam_read1 / bam_calend / bam_aux_get /
+ *                                                              binKeeperFind / getCov / mapped2diffSubfam / the counters
+ *   k_decode_span K1  the same front half writing 16-byte tuples (one coalesced 512-byte store per 32 records): the
+ *                    tuple path, taken when something needs the tuples (-R, ordered outputs, traces).
  *   k_verify / k_fixup  the entry a span assumed must equal the chain exit of the previous span; otherwise the
  *                    span is re-walked from its true entry.  The tuples are therefore exactly the sequential
  *                    chain, whatever the guesses were.
  *   k_decode         the same contract, one thread per chunk reading global memory (A/B measurement, odd sizes).
- *   k_overlap   K2+K3  one lane per tuple: position bucket + short lower_bound + bounded backward walk in
- *                    place of binKeeperFind, "last ascent" selection, XA:Z alternate test, then warp-aggregated
- *                    counters, a shared-memory subfamily/family/class histogram per CTA flushed with u64
- *                    reductions, and two u32 reductions per coverage difference array.
+ *   k_overlap   K2+K3  one lane per tuple: position bucket + bounded backward walk in place of binKeeperFind,
+ *                    "last ascent" selection, XA:Z alternate test, then warp-aggregated counters, a shared-memory
+ *                    subfamily/family/class histogram per CTA flushed with u64 reductions, and two u32 reductions
+ *                    per coverage difference array.
+ *   k_dedup     -R: 128-bit key table, smallest file-order ordinal per key.
  *   k_finalize  prefix sums of the coverage difference arrays (one warp per subfamily).
- *   k_cpg       K4  CpG bedGraph rows against the same table (cpgBedGraphOverlapRepeat).
+ *   k_bedgraph / k_cpg  K4  CpG bedGraph text parsed on the device, rows against the same table (cpgBedGraphOverlapRepeat).
  *   k_query     overlap + selection for explicit queries (property tests).
  */
 #ifndef ITX_KERNELS_CUH
@@ -151,11 +160,11 @@ struct itx_src_flat {
     }
 };
 /* A warp per span (= "chunk" of the bookkeeping, A.C bytes, a multiple of ITX_STAGE).  Only the span's first
- * record start is GUESSED (warp-wide structural test, checked against the previous span by k_verify / k_fixup);
+ * record start is GUESSED (out of the span's first stage, checked against the previous span by k_verify / k_fixup);
  * inside the span the chain is carried from one 4 KiB stage to the next.  Each stage (+1 KiB margin) arrives
- * in shared memory through one TMA bulk copy; lane 0 walks the block_size chain of the stage out of shared
- * memory (11 instructions per record), then every lane decodes one record per round out of shared memory and
- * the warp stores 32 tuples with one coalesced 512-byte store. */
+ * in shared memory through one TMA bulk copy; the warp walks the block_size chain of the stage out of shared
+ * memory with run prediction, then every lane decodes one record per round out of shared memory and the warp
+ * stores 32 tuples with one coalesced 512-byte store. */
 #define ITX_STAGE 4096u
 #define ITX_POS_SLOTS 128u                 /* > ITX_STAGE / 36 record starts per stage */
 #undef ITX_DECODE_SMEM
