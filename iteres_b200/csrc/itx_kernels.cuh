@@ -230,10 +230,9 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
                     const unsigned long long q = lo + d;
                     bool ok = false;
                     if (d < hi && q + 36 <= A.len) {
-                        uint32_t x[9], lq; uint64_t nx, nx2;
+                        uint32_t x[9];
                         S0.core(q, x);
-                        ok = itx_plausible_core(x, q, A.len, A.n_ref, &lq, &nx);
-                        if (ok) ok = S0.u8(q + 36 + lq - 1) == 0 && (nx == A.len || itx_plausible(S0, nx, A.len, A.n_ref, &nx2));
+                        ok = itx_plausible2_core(S0, x, q, A.len, A.n_ref);
                     }
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
@@ -252,22 +251,13 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
                 while (q < qh) {
                     q_end = q;
                     if (q + 36u > room32) { q = 0xffffffffu; break; }
-                    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
-                    const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
+                    const uint32_t bs0 = itx_buf_u32(buf, q);
                     const uint32_t sz0 = bs0 + 4u;
                     if ((int32_t)bs0 < 32 || sz0 > room32 - q) { q = 0xffffffffu; break; }
                     const uint32_t szp = szd ? szd : sz0;
                     uint32_t run = 1u, pk = q;
                     if ((sz0 | szp) < 0x10000u) {
-                        pk = lane ? q + sz0 + (lane - 1u) * szp : q;
-                        bool same = true;
-                        if (lane) {
-                            same = false;
-                            if (pk < qh && pk + szp <= room32) {
-                                const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + (pk & ~3u));
-                                same = itx_funnel_r(wk[0], wk[1], (pk & 3u) * 8u) + 4u == szp;
-                            }
-                        }
+                        const bool same = itx_chain_lane(buf, q, sz0, szp, lane, qh, room32, &pk);
                         const uint32_t m = __ballot_sync(0xffffffffu, same);
                         run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     }
@@ -694,7 +684,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     const unsigned long long q = lo + d;
                     bool ok = false;
                     if (d < hi && q + 36 <= A.len) {
-                        uint32_t x[9], lq; uint64_t nx, nx2;
+                        uint32_t x[9];
                         if (base + 32u + 40u <= nb) {                     /* warp-uniform: every lane's core lies in the stage */
                             const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
                             uint32_t wv[10];
@@ -703,8 +693,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
 #pragma unroll
                             for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
                         } else S0.core(q, x);
-                        ok = itx_plausible_core(x, q, A.len, A.n_ref, &lq, &nx);
-                        if (ok) ok = S0.u8(q + 36 + lq - 1) == 0 && (nx == A.len || itx_plausible(S0, nx, A.len, A.n_ref, &nx2));
+                        ok = itx_plausible2_core(S0, x, q, A.len, A.n_ref);
                     }
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
@@ -727,22 +716,13 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 while (q < qh) {
                     q_end = q;
                     if (q + 36u > room32) { q = 0xffffffffu; break; }
-                    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
-                    const uint32_t bs0 = itx_funnel_r(w0[0], w0[1], (q & 3u) * 8u);
+                    const uint32_t bs0 = itx_buf_u32(buf, q);
                     const uint32_t sz0 = bs0 + 4u;
                     if ((int32_t)bs0 < 32 || sz0 > room32 - q) { q = 0xffffffffu; break; }
                     const uint32_t szp = szd ? szd : sz0;
                     uint32_t run = 1u, pk = q;
                     if ((sz0 | szp) < 0x10000u) {                                  /* warp-uniform */
-                        pk = lane ? q + sz0 + (lane - 1u) * szp : q;
-                        bool same = true;
-                        if (lane) {
-                            same = false;
-                            if (pk < qh && pk + szp <= room32) {
-                                const uint32_t *wk = reinterpret_cast<const uint32_t *>(buf + (pk & ~3u));
-                                same = itx_funnel_r(wk[0], wk[1], (pk & 3u) * 8u) + 4u == szp;
-                            }
-                        }
+                        const bool same = itx_chain_lane(buf, q, sz0, szp, lane, qh, room32, &pk);
                         const uint32_t m = __ballot_sync(0xffffffffu, same);       /* bit 0 is always set */
                         run = m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
                     }

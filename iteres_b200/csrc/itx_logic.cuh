@@ -146,6 +146,34 @@ ITX_HD bool itx_plausible_core(const uint32_t x[9], uint64_t p, uint64_t len, in
     *lq_out = lq; *next = p + 4 + bs;
     return ok;
 }
+/* itx_plausible2's verdict through the core-first test: what the span kernels ask about 32 offsets per step */
+template <class Src>
+ITX_HD bool itx_plausible2_core(const Src &S, const uint32_t x[9], uint64_t p, uint64_t len, int32_t n_ref) {
+    uint32_t lq; uint64_t nx, nx2;
+    bool ok = itx_plausible_core(x, p, len, n_ref, &lq, &nx);
+    if (ok) ok = S.u8(p + 36 + lq - 1) == 0 && (nx == len || itx_plausible(S, nx, len, n_ref, &nx2));
+    return ok;
+}
+/* The chain walk of a staged piece of the stream (k_scan / k_decode_span), one step, one lane.  `buf` holds the stage,
+ * offsets are relative to it; the record at q has size sz0 (already validated), records after it are predicted to have
+ * size szp.  Lane 0 stands for the record at q; lane k >= 1 looks where record k would start under the prediction and
+ * reports whether a record of exactly the predicted size starts there (inside [0, qh) and ending within room32).  The run
+ * of lanes 0..r-1 that report true is accepted by the caller: each accepted start is the previous start plus a verified
+ * size, i.e. the exact chain. */
+ITX_HD uint32_t itx_buf_u32(const uint8_t *buf, uint32_t q) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(buf + (q & ~3u));
+    return itx_funnel_r(w[0], w[1], (q & 3u) * 8u);
+}
+ITX_HD bool itx_chain_lane(const uint8_t *buf, uint32_t q, uint32_t sz0, uint32_t szp, uint32_t lane, uint32_t qh, uint32_t room32, uint32_t *pk_out) {
+    const uint32_t pk = lane ? q + sz0 + (lane - 1u) * szp : q;
+    bool same = true;
+    if (lane) {
+        same = false;
+        if (pk < qh && pk + szp <= room32) same = itx_buf_u32(buf, pk) + 4u == szp;
+    }
+    *pk_out = pk;
+    return same;
+}
 /* a record start followed by another one (or by the end of the stream) */
 template <class Src>
 ITX_HD bool itx_plausible2(const Src &S, uint64_t p, uint64_t len, int32_t n_ref) {

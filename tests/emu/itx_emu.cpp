@@ -114,49 +114,59 @@ static void walk_chunk(emu_index *E, const uint8_t *b, uint64_t len, uint64_t lo
     *exit_ = p;
 }
 
-/* The lane-parallel chain resolution of k_decode_tile, simulated: 32 sub-ranges of a chunk each guess their
- * first record start and walk their piece; pieces are chained with the kernel's synchronous update rule
- * (transparent lanes, own guess behind an all-transparent prefix).  Returns the record starts and the exit. */
-static void sub_walk(const itx_src_global &G, uint64_t len, uint64_t p, uint64_t s1, std::vector<uint64_t> *out, uint64_t *x) {
-    if (out) out->clear();
-    if (p < ITX_OFF_END) {
-        while (p < s1) {
-            if (p + 36 > len) { p = ITX_OFF_END; break; }
-            const uint32_t bs = G.u32(p); const uint64_t e = p + 4 + (uint64_t)bs;
-            if ((int32_t)bs < 32 || e > len) { p = ITX_OFF_END; break; }
-            if (out) out->push_back(p);
-            p = e;
-        }
-    }
-    *x = p;
-}
-static void tile_chain(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, int32_t n_ref, bool first, uint64_t carry,
+/* The span kernels' chain (k_scan / k_decode_span), simulated lane by lane with the very functions the kernels call
+ * (itx_plausible2_core for the span guess, itx_buf_u32 / itx_chain_lane for a step of the walk): the span's first record
+ * start is guessed 32 offsets per step out of the span's first bytes, then the chain is carried stage by stage
+ * (ITX_EMU_STAGE bytes, as the kernels' ITX_STAGE) with run prediction on the span's dominant record size.  Offsets are
+ * span-relative and 32 bits wide, sentinels 0xfffffffe (chain ended) / 0xffffffff (no guess) as in the kernels.
+ * Returns the entry, the record starts and the exit, to be compared with the sequential chain. */
+#define ITX_EMU_STAGE 4096u
+static void span_chain(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, int32_t n_ref, bool first, uint64_t carry,
                        uint64_t *entry0, std::vector<uint64_t> *starts, uint64_t *exitX) {
     const itx_src_global G{b};
-    uint64_t hi = lo + C; if (hi > len) hi = len;
-    const uint32_t B = C / 32;
-    uint64_t guess[32], cand[32], X[32], Xg[32], s1v[32];
-    for (uint32_t l = 0; l < 32; l++) {
-        uint64_t s0 = lo + (uint64_t)l * B, s1 = s0 + B; if (s1 > hi) s1 = hi;
-        s1v[l] = s1;
-        uint64_t c = ITX_OFF_NONE;
-        if (first && l == 0) c = carry; else if (s0 < s1) c = itx_speculate_entry(G, s0, s1, len, n_ref);
-        guess[l] = cand[l] = c;
-        sub_walk(G, len, c, s1, NULL, &Xg[l]); X[l] = Xg[l];
+    const uint32_t hi = len - lo < C ? (uint32_t)(len - lo) : C;
+    uint32_t p = 0xffffffffu;
+    if (first) p = carry >= ITX_OFF_END ? (uint32_t)carry : (carry - lo < 0xfffffff0ull ? (uint32_t)(carry - lo) : 0xfffffffeu);
+    else {
+        for (uint32_t base = 0; base < hi && p == 0xffffffffu; base += 32) {
+            uint32_t m = 0;
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                const uint32_t d = base + lane; const uint64_t q = lo + d;
+                bool ok = false;
+                if (d < hi && q + 36 <= len) { uint32_t x[9]; G.core(q, x); ok = itx_plausible2_core(G, x, q, len, n_ref); }
+                if (ok) m |= 1u << lane;
+            }
+            if (m) p = base + (uint32_t)__builtin_ctz(m);
+        }
     }
-    for (int it = 0; it < 34; it++) {
-        uint64_t want[32]; bool any = false;
-        for (uint32_t l = 0; l < 32; l++) { const uint64_t prev = l ? X[l - 1] : 0; want[l] = (l == 0 || prev == ITX_OFF_NONE) ? guess[l] : prev; if (want[l] != cand[l]) any = true; }
-        if (!any) break;
-        uint64_t nX[32];
-        for (uint32_t l = 0; l < 32; l++) { nX[l] = X[l]; if (want[l] != cand[l]) { cand[l] = want[l]; if (want[l] == guess[l]) nX[l] = Xg[l]; else sub_walk(G, len, cand[l], s1v[l], NULL, &nX[l]); } }
-        for (uint32_t l = 0; l < 32; l++) X[l] = nX[l];
-    }
-    *entry0 = ITX_OFF_NONE;
-    for (uint32_t l = 0; l < 32; l++) if (cand[l] != ITX_OFF_NONE) { *entry0 = cand[l]; break; }
+    *entry0 = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
     starts->clear();
-    for (uint32_t l = 0; l < 32; l++) { std::vector<uint64_t> v; uint64_t x; sub_walk(G, len, cand[l], s1v[l], &v, &x); starts->insert(starts->end(), v.begin(), v.end()); }
-    *exitX = X[31];
+    uint32_t szd = 0;
+    while (p < hi) {
+        const uint32_t c_lo = p & ~(ITX_EMU_STAGE - 1u), c_hi = c_lo + ITX_EMU_STAGE < hi ? c_lo + ITX_EMU_STAGE : hi;
+        const uint64_t rest = len - lo - c_lo;
+        const uint8_t *buf = b + lo + c_lo;
+        uint32_t q = p - c_lo;
+        const uint32_t qh = c_hi - c_lo, room32 = rest > 0x7fffffffull ? 0x7fffffffu : (uint32_t)rest;
+        while (q < qh) {
+            if (q + 36u > room32) { q = 0xffffffffu; break; }
+            const uint32_t bs0 = itx_buf_u32(buf, q), sz0 = bs0 + 4u;
+            if ((int32_t)bs0 < 32 || sz0 > room32 - q) { q = 0xffffffffu; break; }
+            const uint32_t szp = szd ? szd : sz0;
+            uint32_t run = 1u, pks[32]; pks[0] = q;
+            if ((sz0 | szp) < 0x10000u) {
+                uint32_t m = 0;
+                for (uint32_t lane = 0; lane < 32; lane++) if (itx_chain_lane(buf, q, sz0, szp, lane, qh, room32, &pks[lane])) m |= 1u << lane;
+                run = m == 0xffffffffu ? 32u : (uint32_t)__builtin_ctz(~m);
+            }
+            for (uint32_t lane = 0; lane < run; lane++) starts->push_back(lo + c_lo + pks[lane]);
+            q += sz0 + (run - 1u) * szp;
+            szd = run >= 2u ? szp : 0u;
+        }
+        if (q == 0xffffffffu) { p = 0xfffffffeu; break; }
+        p = c_lo + q;
+    }
+    *exitX = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
 }
 
 /* bam: uncompressed stream with >= 64 readable bytes after len.  want_trace: keep a per-record trace. */
@@ -183,11 +193,11 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
         entry[i] = exit_[i - 1];
         walk_chunk(E, bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
     }
-    /* the warp kernel's lane-parallel chain, chunk by chunk, against the sequential chain */
-    if ((C & 127u) == 0 && C >= 2048u) {
+    /* the span kernels' chain (staged guess, run-predicted walk), span by span, against the sequential chain */
+    if ((C % ITX_EMU_STAGE) == 0 && C <= (1u << 20)) {
         for (uint64_t i = 0; i < n; i++) {
             uint64_t e0, ex; std::vector<uint64_t> st;
-            tile_chain(bam, len, (k0 + i) * C, C, h.n_ref, i == 0, h.hdr_len, &e0, &st, &ex);
+            span_chain(bam, len, (k0 + i) * C, C, h.n_ref, i == 0, i == 0 ? h.hdr_len : 0, &e0, &st, &ex);
             E->tile_checked++;
             if (e0 != entry[i]) { E->tile_entry_miss++; continue; }     /* a wrong chunk guess: the repair path's business */
             bool same = ex == exit_[i] && st.size() == tup[i].size();

@@ -57,14 +57,14 @@ def test_emu_matches_oracle(case, worlds):
     raw = buf[:n].tobytes()
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
-    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=2048)
+    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
     cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
     assert cnt_e == cnt_o
     assert cnt_o[0] + cnt_o[1] == nrec and cnt_o[9] > 0
     checked, mism = emu.ring_check()
     assert checked >= nrec and mism == 0          # ring addressing decodes every record identically
     tc, tm, te = emu.tile_check()
-    assert tc > 0 and tm == 0 and te == emu.n_bad()   # k_decode_tile's lane-parallel chain == the sequential chain
+    assert tc > 0 and tm == 0 and te == emu.n_bad()   # the span kernels' chain (staged guess, run-predicted walk) == the sequential chain
     assert len(tr_e) == len(tr_o) == nrec
     for f in ("start", "end", "tid", "sel_row"):
         assert np.array_equal(tr_e[f], tr_o[f]), f
@@ -145,7 +145,7 @@ def test_reference_binary_matches_oracle_on_synthetic_bam(mode, n_units, args, w
         assert filecmp.cmp(str(rd / fn), str(od / fn), shallow=False), fn
 
 
-@pytest.mark.parametrize("chunk", [2048, 32768])
+@pytest.mark.parametrize("chunk", [4096, 32768])
 def test_records_of_every_size(chunk, tmp_path):
     """records from 60 bytes to 70 KB (longer than a chunk and than the decode ring): same counters and trace"""
     import mixed_records
