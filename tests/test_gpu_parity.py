@@ -505,8 +505,9 @@ def test_filter_mode_counts_per_locus(worlds):
 
 @pytest.mark.parametrize("chunk,window", [(1024, 1 << 18), (4096, 1 << 18), (32768, 1 << 30), (65536, 1 << 20)])
 def test_records_of_every_size(chunk, window, tmp_path):
-    """records from 60 bytes to 70 KB: longer than a chunk (chunks without any record start), than the
-    decode ring (global-memory path inside k_decode_tiles, ring restart after the jump) and straddling windows"""
+    """records from 60 bytes to 70 KB: longer than a span (spans without any record start), than a stage and its
+    margin (the global-memory fall-back of the staged source), of 64 KiB and more (stepped over one at a time by the
+    chain walk) and straddling launch groups"""
     import mixed_records
     tabs = mixed_records.tables(str(tmp_path))
     raw, nrec = mixed_records.make()
