@@ -14,6 +14,7 @@
 #include <string.h>
 #include <map>
 #include <vector>
+#include <cmath>
 
 struct emu_index {
     itx_index ix;
@@ -334,6 +335,53 @@ uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }
 uint64_t emu_tile_checked(emu_index *E) { return E->tile_checked; }
 uint64_t emu_tile_mismatch(emu_index *E) { return E->tile_mismatch; }
 uint64_t emu_tile_entry_miss(emu_index *E) { return E->tile_entry_miss; }
+
+/* The two arithmetic shortcuts of itx_select_walk, checked against the float arithmetic they stand for (getCov,
+ * generic.c:296-301, and the comparisons at generic.c:950-962):
+ *   (1) for den < 2^23 and ra, rb <= den, (float)ra / (float)den > (float)rb / (float)den  <=>  ra > rb;
+ *   (2) itx_cov_thr(r, den, thr) < thr  <=>  the float quotient < thr, for any thr.
+ * Random cases plus the edges (overlaps around den / 4096, den around 2^23 and 2^24, thresholds next to 2^-13).
+ * Returns the number of violations. */
+static float exact_cov(uint32_t r, uint32_t den) {
+    if (r != 0 && r == den) return 1.0f;
+    volatile float d = (float)den, n = (float)(int32_t)r;      /* volatile: plain float division, no contraction */
+    return d == 0.0f ? 0.0f : n / d;
+}
+uint64_t emu_check_cov_rules(uint64_t n, uint64_t seed) {
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    const float thr_fixed[] = {1e-4f, ITX_COV_FLOOR, std::nextafterf(ITX_COV_FLOOR, 0.0f), std::nextafterf(ITX_COV_FLOOR, 1.0f), 0.0f, 0.00012f,
+                               0.000244140625f, 0.5f, 1.0f, 2.0f, -1.0f, 1e-30f};
+    for (uint64_t k = 0; k < n; k++) {
+        uint32_t den;
+        switch (rnd() % 6) {
+            case 0: den = 1 + (uint32_t)(rnd() % 400); break;                        /* reads */
+            case 1: den = 1 + (uint32_t)(rnd() % 100000); break;                     /* fragments */
+            case 2: den = (1u << 23) - 1 - (uint32_t)(rnd() % 64); break;            /* just below the integer-comparison limit */
+            case 3: den = (1u << 23) + (uint32_t)(rnd() % (1u << 24)); break;        /* above it: only rule (2) applies */
+            case 4: den = 4096u * (1 + (uint32_t)(rnd() % 5000)) + (uint32_t)(rnd() % 3) - 1; break;   /* around multiples of 2^12 */
+            default: den = 1 + (uint32_t)(rnd() % ((1u << 23) - 1)); break;
+        }
+        uint32_t ra, rb;
+        switch (rnd() % 4) {
+            case 0: ra = (uint32_t)(rnd() % ((uint64_t)den + 1)); rb = (uint32_t)(rnd() % ((uint64_t)den + 1)); break;
+            case 1: ra = (uint32_t)(rnd() % ((uint64_t)den + 1)); rb = ra ? ra - 1 : 0; break;              /* neighbours */
+            case 2: ra = den - (uint32_t)(rnd() % (den < 4 ? den : 4)); rb = den - (uint32_t)(rnd() % (den < 4 ? den : 4)); break;   /* near full coverage */
+            default: ra = (den >> 12) + (uint32_t)(rnd() % 3); rb = (den >> 12) + (uint32_t)(rnd() % 3); if (ra > den) ra = den; if (rb > den) rb = den; break;   /* around den / 4096 */
+        }
+        if (den < (1u << 23)) {
+            const bool fa = exact_cov(ra, den) > exact_cov(rb, den);
+            if (fa != (ra > rb)) bad++;
+        }
+        for (float thr : thr_fixed) {
+            if ((itx_cov_thr(ra, den, thr) < thr) != (exact_cov(ra, den) < thr)) bad++;
+        }
+        union { uint32_t u; float f; } t; t.u = (uint32_t)rnd() & 0x7fffffffu;               /* any non-negative float, NaN and inf included */
+        if ((itx_cov_thr(ra, den, t.f) < t.f) != (exact_cov(ra, den) < t.f)) bad++;
+        if (itx_cov(100u, 100u + den, 100 + (int32_t)(den - ra), 100 + (int32_t)den) != exact_cov(ra, den) && den < (1u << 30)) bad++;   /* itx_cov is getCov */
+    }
+    return bad;
+}
 
 int32_t emu_query(emu_index *E, const char *chrom, uint32_t start, uint32_t end, float min_cov, int32_t *n_hits) {
     int32_t c = itx_strtab_find(&E->ix.chroms, chrom); if (n_hits) *n_hits = 0;

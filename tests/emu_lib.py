@@ -33,6 +33,8 @@ def lib():
         for f in ("emu_ring_checked", "emu_ring_mismatch", "emu_tile_checked", "emu_tile_mismatch", "emu_tile_entry_miss"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [vp]
+        L.emu_check_cov_rules.restype = C.c_uint64
+        L.emu_check_cov_rules.argtypes = [C.c_uint64, C.c_uint64]
         L.emu_query.restype = C.c_int32
         L.emu_query.argtypes = [vp, cp, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_int32)]
         L.emu_inflate.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int]

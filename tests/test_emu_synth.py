@@ -283,3 +283,10 @@ def test_xa_strings_of_every_shape(tmp_path):
         emu.close()
     assert 0 < cnt_o[12] < len(reads)
     ora.close()
+
+
+def test_coverage_shortcuts_are_the_float_arithmetic():
+    """itx_select_walk compares overlaps as integers (fragments shorter than 2^23 bases) and forms the coverage quotient
+    only when it can fall below the threshold: both rules against the float arithmetic of getCov, on two million cases
+    that include the edges the proofs in itx_logic.cuh lean on"""
+    assert emu_lib.lib().emu_check_cov_rules(2_000_000, 12345) == 0
