@@ -49,6 +49,26 @@ def tables_equal(a, b):
         assert a.table(which) == b.table(which)
 
 
+def assert_group_tables_and_coverage(emu, ora):
+    """subfamily / family / class rows (names in Kent hash order, read counts, unique counts, lengths, genome counts) and
+    the per-base coverage vectors, all and unique"""
+    import ctypes as C
+    L = O.lib()
+    c4 = (C.c_uint64 * 4)()
+    for which, nfun in ((0, L.ora_n_subfam), (1, L.ora_n_fam), (2, L.ora_n_class)):
+        got = emu.table(which)
+        assert len(got) == nfun(ora.h)
+        for i, row in enumerate(got):
+            L.ora_counts(ora.h, which, i, c4)
+            assert row == (L.ora_name(ora.h, which, i).decode(),) + tuple(c4)
+    for i in range(L.ora_n_subfam(ora.h)):
+        ln = L.ora_subfam_length(ora.h, i)
+        if ln:
+            for u in (0, 1):
+                want = np.ctypeslib.as_array(L.ora_subfam_bp(ora.h, i, u), shape=(ln,))
+                assert np.array_equal(emu.coverage(i, u), want)
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_emu_matches_oracle(case, worlds):
     name, shape, n_rmsk, mode, n_units, kw = case
@@ -72,22 +92,7 @@ def test_emu_matches_oracle(case, worlds):
     assert np.array_equal(tr_e["flags"] & mask, tr_o["flags"] & mask)
     if kw.get("diffSubfam", 1) and mode == 1:
         assert cnt_o[12] > 0
-    # group tables and coverage
-    L = O.lib()
-    import ctypes as C
-    c4 = (C.c_uint64 * 4)()
-    for which, nfun in ((0, L.ora_n_subfam), (1, L.ora_n_fam), (2, L.ora_n_class)):
-        got = emu.table(which)
-        assert len(got) == nfun(ora.h)
-        for i, row in enumerate(got):
-            L.ora_counts(ora.h, which, i, c4)
-            assert row == (L.ora_name(ora.h, which, i).decode(),) + tuple(c4)
-    for i in range(L.ora_n_subfam(ora.h)):
-        ln = L.ora_subfam_length(ora.h, i)
-        if ln:
-            for u in (0, 1):
-                want = np.ctypeslib.as_array(L.ora_subfam_bp(ora.h, i, u), shape=(ln,))
-                assert np.array_equal(emu.coverage(i, u), want)
+    assert_group_tables_and_coverage(emu, ora)
     ora.close()
     emu.close()
 
@@ -290,3 +295,78 @@ def test_coverage_shortcuts_are_the_float_arithmetic():
     only when it can fall below the threshold: both rules against the float arithmetic of getCov, on two million cases
     that include the edges the proofs in itx_logic.cuh lean on"""
     assert emu_lib.lib().emu_check_cov_rules(2_000_000, 12345) == 0
+
+
+def _adversarial_records(rng, n, n_ref):
+    """records whose fields sit on the edges the fragment logic branches on (generic.c:748-905): positions at 0, at and
+    past the chromosome end, negative; reference ids at and past n_ref; isize 0, +-iSize, +-(iSize+1), INT_MIN-ish;
+    every flag combination; CIGARs with and without reference-consuming ops; no CIGAR; reads longer than the chromosome"""
+    import kats
+    recs = []
+    sizes = {0: 1000000, 1: 16571}
+    for i in range(n):
+        tid = int(rng.choice([0, 0, 0, 1, 1, 2, n_ref, n_ref + 3, -1, -2]))
+        size = sizes.get(tid, 5000)
+        pos = int(rng.choice([0, 1, 35, 36, 1000, 1050, 1299, 1300, 5000, 5880, 5999, 6099, size - 37, size - 36, size - 1, size, size + 100,
+                              -1, 2 ** 31 - 40, int(rng.integers(0, 7000))]))
+        flag = int(rng.choice([0, 16, 4, 1, 1 | 64, 1 | 128, 1 | 64 | 8, 1 | 128 | 8, 99, 147, 83, 163, 73, 133, 69, 137, 1 | 2 | 64 | 16 | 32, 1024, 256 | 16, 2048,
+                               int(rng.integers(0, 4096))]))
+        L = int(rng.choice([1, 20, 36, 50, 100, 400]))
+        cigar = str(rng.choice(["%dM" % L, "*", "5S%dM" % max(1, L - 5), "10M5D%dM" % max(1, L - 10), "10M200N%dM" % max(1, L - 10), "%d=" % L, "3I%dX" % max(1, L - 3),
+                                "1M" * 0 + "%dM2D3N4M" % L, "20000M"]))
+        isize = int(rng.choice([0, 1, -1, 36, 200, -200, 499, 500, 501, -499, -500, -501, 100000, -100000, 2 ** 31 - 1, -(2 ** 31)]))
+        mpos = int(rng.choice([0, pos, max(0, pos - 300), pos + 300 if pos < 2 ** 31 - 400 else pos, size - 10, size + 50, -1]))
+        mtid = int(rng.choice([tid, tid, 0, -1, 1]))
+        aux = [("NM", "C", int(rng.integers(0, 3)))]
+        if rng.random() < 0.3:
+            aux.append(("XA", "Z", str(rng.choice(["chr1,+5101,36M,1;", "chr1,-1101,36M,0;", "chrM,+200,36M,2;chr1,+5950,36M,0;", "chr9,+5,36M,0;"]))))
+        recs.append(dict(qname="a%d" % i, flag=flag, tid=tid, pos=pos, mapq=int(rng.choice([0, 9, 10, 11, 29, 30, 31, 60, 255])), cigar=cigar,
+                         mtid=mtid, mpos=mpos, isize=isize, seq="A" * L, qual="I" * L, aux=aux))
+    return recs
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_adversarial_records_match_oracle(seed, tmp_path):
+    """fragment logic, bam_calend, clamping, strand / extension arithmetic with unsigned wrap-around, -C renaming, the unknown-
+    chromosome path and the counters, on records built to sit on every branch -- the device logic against the oracle, record
+    by record, under several option sets"""
+    import bamio
+    import kats
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\nchrM\t16571\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    rows = kats.ANNOT1 + [kats.rmsk_row("chrM", 100, 400, "+", "AluY", "SINE", "Alu", 1, 300, 0),
+                          kats.rmsk_row("chr1", 999900, 1000000, "-", "L1PA2", "LINE", "L1", -100, 5900, 5800),
+                          kats.rmsk_row("chr1", 0, 40, "+", "MIR", "SINE", "MIR", 1, 41, 0)]
+    open(rm, "w").write("\n".join(rows) + "\n")
+    rng = np.random.default_rng(seed)
+    refs = [("chr1", 1000000), ("chrM", 16571), ("chrUn_x", 5000)]
+    reads = _adversarial_records(rng, 1500, len(refs))
+    import struct
+
+    def enc(r):                                   # the bin field is not on the path: encode with a tame position, then put the real one in
+        b = bytearray(bamio.encode_record(dict(r, pos=min(max(r["pos"], 0), 1 << 28))))
+        b[8:12] = struct.pack("<i", r["pos"])
+        return bytes(b)
+    raw = bamio.encode_header(refs) + b"".join(enc(r) for r in reads)
+    option_sets = [dict(), dict(extension=0), dict(extension=1000), dict(treat=1), dict(discardWrongEnd=1, iSize=200), dict(iSize=0),
+                   dict(mapQ=30, minCoverage=0.5), dict(mapQ=0, minCoverage=0.0), dict(diffSubfam=0, extension=36), dict(filter=1), dict(addChr=1)]
+    for kw in option_sets:
+        ora = O.OracleIndex(cs, rs, rm)
+        cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
+        emu = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
+        cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
+        assert cnt_e == cnt_o, kw
+        assert cnt_o[6] > 200 and cnt_o[9] > 20 and cnt_o[4] + cnt_o[5] < cnt_o[2] + cnt_o[3] < len(reads), cnt_o     # every stage of the funnel drops some
+        assert len(tr_e) == len(tr_o) == len(reads)
+        for f in ("start", "end", "tid", "sel_row"):
+            bad = np.nonzero(tr_e[f] != tr_o[f])[0]
+            assert len(bad) == 0, (kw, f, [reads[i] for i in bad[:3]])
+        mask = ~np.uint32(8 | 64)
+        bad = np.nonzero((tr_e["flags"] & mask) != (tr_o["flags"] & mask))[0]
+        assert len(bad) == 0, (kw, [reads[i] for i in bad[:3]])
+        if not kw.get("filter"):
+            assert_group_tables_and_coverage(emu, ora)
+        ora.close()
+        emu.close()
