@@ -466,6 +466,43 @@ def test_xa_strings_of_every_shape(fused, tmp_path, monkeypatch):
     ix.close()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_adversarial_records_match_oracle(fused, tmp_path, monkeypatch):
+    """records built to sit on every branch of the fragment logic (positions at and past chromosome ends, reference ids
+    past n_ref, isize edges, every flag mix) under several option sets: k_scan and the tuple path against the oracle"""
+    import struct
+    import bamio
+    from test_emu_synth import _adversarial_records
+    monkeypatch.setenv("ITX_FUSED", str(fused))
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\nchrM\t16571\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    rows = kats.ANNOT1 + [kats.rmsk_row("chrM", 100, 400, "+", "AluY", "SINE", "Alu", 1, 300, 0),
+                          kats.rmsk_row("chr1", 999900, 1000000, "-", "L1PA2", "LINE", "L1", -100, 5900, 5800),
+                          kats.rmsk_row("chr1", 0, 40, "+", "MIR", "SINE", "MIR", 1, 41, 0)]
+    open(rm, "w").write("\n".join(rows) + "\n")
+    refs = [("chr1", 1000000), ("chrM", 16571), ("chrUn_x", 5000)]
+    reads = _adversarial_records(np.random.default_rng(4), 3000, len(refs))
+
+    def enc(r):
+        b = bytearray(bamio.encode_record(dict(r, pos=min(max(r["pos"], 0), 1 << 28))))
+        b[8:12] = struct.pack("<i", r["pos"])
+        return bytes(b)
+    raw = bamio.encode_header(refs) + b"".join(enc(r) for r in reads)
+    for kw in (dict(), dict(extension=0), dict(extension=1000), dict(treat=1), dict(discardWrongEnd=1, iSize=200), dict(mapQ=30, minCoverage=0.5),
+               dict(mapQ=0, minCoverage=0.0), dict(addChr=1)):
+        ora = O.OracleIndex(cs, rs, rm)
+        want = ora.scan_stream(raw, O.default_opts(**kw))
+        ix = capi.Index(cs, rs, rm)
+        ix.tune(chunk_bytes=4096)
+        assert ix.scan_stream(raw, capi.default_opts(**kw)) == want, kw
+        assert ix.profile()["fused"] == fused
+        assert_same_tables(ix, ora)
+        ora.close()
+        ix.close()
+
+
 def test_cpg_matches_oracle(worlds, tmp_path):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bg = str(tmp_path / "cpg.bedGraph")
