@@ -370,3 +370,47 @@ def test_adversarial_records_match_oracle(seed, tmp_path):
             assert_group_tables_and_coverage(emu, ora)
         ora.close()
         emu.close()
+
+
+def decoy_stream():
+    """records that carry, inside a byte-array aux field, back-to-back copies of a perfectly valid record: a span that begins
+    inside such a field GUESSES one of the copies as its first record (the copies pass every structural test, next record
+    included), so the chain check must catch it and the span must be walked again from where the previous one really ended"""
+    import struct
+    import bamio
+    import kats
+    small = bamio.encode_record(kats.se("decoy", 0, 5100, 37))
+    payload = small * 90                                   # ~ 9 KB: longer than two 4 KiB spans
+    carrier_aux = [("NM", "C", 0), ("ZB", "B", b"C" + struct.pack("<i", len(payload)) + payload)]
+    reads = []
+    for k in range(12):
+        reads.append(kats.se("carrier%d" % k, 0, 1050 + k, 37, aux=carrier_aux))
+        for j in range(25):
+            reads.append(kats.se("r%d_%d" % (k, j), 16 if j % 2 else 0, 1000 + 7 * j, 30 + j % 3, aux=[("NM", "C", 1)]))
+    raw = bamio.encode_header([("chr1", 1000000)]) + b"".join(bamio.encode_record(r) for r in reads)
+    return raw, len(reads)
+
+
+def test_wrong_span_guesses_are_caught_and_repaired(tmp_path):
+    import kats
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
+    raw, nrec = decoy_stream()
+    ora = O.OracleIndex(cs, rs, rm)
+    cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(), trace=True)
+    assert cnt_o[0] == nrec and cnt_o[9] > 0
+    for chunk in (4096, 8192):
+        emu = emu_lib.EmuIndex(cs, rs, rm, chunk=chunk)
+        cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(), trace=True)
+        assert emu.n_bad() > 0                                  # decoys were taken for record starts ...
+        assert cnt_e == cnt_o                                   # ... and it made no difference
+        for f in ("start", "end", "tid", "sel_row"):
+            assert np.array_equal(tr_e[f], tr_o[f]), f
+        tc, tm, te = emu.tile_check()
+        assert tc > 0 and tm == 0 and te > 0                    # the span kernels' guess falls for them too; their walks otherwise agree
+        assert_group_tables_and_coverage(emu, ora)
+        emu.close()
+    ora.close()

@@ -503,6 +503,33 @@ def test_adversarial_records_match_oracle(fused, tmp_path, monkeypatch):
         ix.close()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_wrong_span_guesses_are_caught_and_repaired(fused, tmp_path, monkeypatch):
+    """valid-looking records inside byte-array aux fields are taken for record starts by the span guess: k_scan's chain
+    check must notice, take back what it counted (sign -1) and count again through the tuple path, whose k_fixup repairs
+    the guesses -- without the test hook, on wrong guesses the kernels really make"""
+    from test_emu_synth import decoy_stream
+    monkeypatch.setenv("ITX_FUSED", str(fused))
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
+    raw, nrec = decoy_stream()
+    ora = O.OracleIndex(cs, rs, rm)
+    want = ora.scan_stream(raw, O.default_opts())
+    assert want[0] == nrec and want[9] > 0
+    ix = capi.Index(cs, rs, rm)
+    ix.tune(chunk_bytes=4096)
+    assert ix.scan_stream(raw, capi.default_opts()) == want
+    pr = ix.profile()
+    assert pr["fused"] == fused
+    assert pr["n_replayed_windows"] > 0 if fused else pr["n_bad_chunks"] > 0
+    assert_same_tables(ix, ora)
+    ora.close()
+    ix.close()
+
+
 def test_cpg_matches_oracle(worlds, tmp_path):
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bg = str(tmp_path / "cpg.bedGraph")
