@@ -503,8 +503,9 @@ def test_adversarial_records_match_oracle(fused, tmp_path, monkeypatch):
         ix.close()
 
 
+@pytest.mark.parametrize("window", [0, 1 << 16])
 @pytest.mark.parametrize("fused", [1, 0])
-def test_wrong_span_guesses_are_caught_and_repaired(fused, tmp_path, monkeypatch):
+def test_wrong_span_guesses_are_caught_and_repaired(fused, window, tmp_path, monkeypatch):
     """valid-looking records inside byte-array aux fields are taken for record starts by the span guess: k_scan's chain
     check must notice, take back what it counted (sign -1) and count again through the tuple path, whose k_fixup repairs
     the guesses -- without the test hook, on wrong guesses the kernels really make"""
@@ -520,7 +521,7 @@ def test_wrong_span_guesses_are_caught_and_repaired(fused, tmp_path, monkeypatch
     want = ora.scan_stream(raw, O.default_opts())
     assert want[0] == nrec and want[9] > 0
     ix = capi.Index(cs, rs, rm)
-    ix.tune(chunk_bytes=4096)
+    ix.tune(chunk_bytes=4096, window_bytes=window)              # one launch group, or several: the undo restarts from a logged carry
     assert ix.scan_stream(raw, capi.default_opts()) == want
     pr = ix.profile()
     assert pr["fused"] == fused
