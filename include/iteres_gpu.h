@@ -69,6 +69,10 @@ void itx_index_reset_counts(itx_index *ix);  /* zero every counter on the device
  *      itx_index_reset_counts.  cnt[13] as generic.c:1048-1060. ---- */
 int itx_scan_alignments(itx_index *ix, const char *bam_list, const itx_scan_opts *o,
                         uint64_t cnt[13], char err[ITX_ERRLEN]);
+/* the single-file twin samFile2nodupRepbedFileNew (generic.h:73; generic.c:343-697), what `iteres filter` calls: `path` is ONE
+ * file name and is not split at commas */
+int itx_scan_alignment_file(itx_index *ix, const char *path, const itx_scan_opts *o,
+                            uint64_t cnt[13], char err[ITX_ERRLEN]);
 /* same path, the BGZF file image already in host memory */
 int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t len, const itx_scan_opts *o,
                          uint64_t cnt[13], char err[ITX_ERRLEN]);
@@ -120,6 +124,9 @@ int32_t itx_n_subfam(const itx_index *ix);
 int32_t itx_n_fam(const itx_index *ix);
 int32_t itx_n_class(const itx_index *ix);
 int64_t itx_n_elem(const itx_index *ix);
+/* repeat_num of rmsk2binKeeperHash (generic.c:1593, 1697-1701): rows that passed the -n/-c/-f filter, counted BEFORE the rows on
+ * chromosomes missing from the size file are dropped -- the number the reference prints in "* Total N repeats found." */
+int64_t itx_n_repeats_parsed(const itx_index *ix);
 int32_t itx_n_chrom(const itx_index *ix);
 const char *itx_name(const itx_index *ix, int which, int32_t i);
 void itx_counts(const itx_index *ix, int which, int32_t i, uint64_t out[4] /* read_count, unique, total_length, genome_count */);
@@ -179,6 +186,40 @@ int itx_comm_init(itx_index *ix, const uint8_t id[ITX_NCCL_ID_BYTES], int rank, 
 int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]);   /* afterwards itx_get_counters returns the global sums */
 void itx_get_counters(const itx_index *ix, uint64_t cnt[13]);
 void itx_comm_destroy(itx_index *ix);
+
+/* ---- ONE BAM file across the ranks ("split the BAM into G contiguous ranges of BGZF blocks"; the reference reads
+ *      its files in one loop, generic.c:700-745, block by block, cussamtools/bgzf.c:471-521).  Rank r owns the BGZF blocks that
+ *      START in the r-th share of the file's bytes and the records that start in those blocks; it guesses its first record start
+ *      out of the bytes (no .bai needed) and reads past its last block until the straddling record is whole.  The ranks then
+ *      compare notes: a rank whose guess is not where the chain of the ranks before it arrives scans its part again from the
+ *      right place, so the counts are those of one pass over the file, bit for bit.  -R, -B/-V and filter -r (file-order
+ *      outputs) and SAM text are not sharded (ITX_ENOTSUP). ---- */
+#define ITX_SHARD_GUESS 0xfffffffffffffffdULL
+#define ITX_SHARD_END   0xfffffffffffffffeULL   /* the record chain ended (a cut record): nothing after it counts */
+#define ITX_SHARD_NONE  0xffffffffffffffffULL   /* no record start */
+typedef struct itx_shard_report {
+    uint64_t entry_rel;        /* first record start the rank settled on, as an offset into its own uncompressed bytes */
+    uint64_t exit_rel;         /* where the chain left the part, as an offset into the NEXT rank's bytes */
+    uint64_t own_bytes;        /* uncompressed size of the rank's own blocks */
+} itx_shard_report;
+/* one rank, one file; entry = ITX_SHARD_GUESS or what itx_shard_chain_check handed back */
+int itx_scan_shard_file(itx_index *ix, const char *path, const itx_scan_opts *o, int rank, int nranks, uint64_t entry,
+                        itx_shard_report *rep, uint64_t cnt[13], char err[ITX_ERRLEN]);
+/* the reports of all ranks -> first rank that must scan again (and from where), or -1.  Pure host arithmetic. */
+int itx_shard_chain_check(int nranks, const itx_shard_report *rep, uint64_t *forced_entry);
+/* the whole protocol for a comma separated list of files, rank and size taken from itx_comm_init: scan, all-gather the
+ * reports (NCCL), scan again where the check says so.  Afterwards every rank holds the counts of ITS parts;
+ * itx_comm_allreduce_counts makes them the job's. */
+int itx_scan_alignments_shard(itx_index *ix, const char *bam_list, const itx_scan_opts *o, uint64_t cnt[13], char err[ITX_ERRLEN]);
+/* cpgBedGraphOverlapRepeat over the rank-th of nranks parts of the bedGraph (cut at line ends); the u32 counts and f64 score
+ * sums are merged by itx_comm_allreduce_counts (1e-9 relative on the sums), the line totals by itx_get_cpg_totals after it */
+int itx_scan_cpg_shard(itx_index *ix, const char *bedgraph, int filter, int rank, int nranks, uint32_t *n_lines, uint32_t *n_in_repeat,
+                       char err[ITX_ERRLEN]);
+void itx_get_cpg_totals(const itx_index *ix, uint64_t *n_lines, uint64_t *n_in_repeat);
+int itx_comm_rank(const itx_index *ix, int *rank, int *nranks);
+/* like itx_set_device + itx_index_build in one call (several indexes, one per device, can be built from threads of one process) */
+itx_index *itx_index_build_on(int device, const char *chrom_sizes, const char *rep_sizes, const char *rmsk,
+                              int filter_field, const char *filter_name, char err[ITX_ERRLEN]);
 
 /* ---- raw device helpers for benchmarks (so a harness needs no other CUDA binding) ---- */
 void *itx_dev_alloc(uint64_t bytes);

@@ -50,12 +50,13 @@ def default_opts(**kw):
 
 # every symbol include/iteres_gpu.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = """itx_scan_opts_default itx_device_count itx_set_device itx_version itx_index_build itx_index_free
-itx_index_reset_counts itx_scan_alignments itx_scan_bgzf_memory itx_scan_bam_host itx_bam_header_parse
+itx_index_reset_counts itx_scan_alignments itx_scan_alignment_file itx_scan_bgzf_memory itx_scan_bam_host itx_bam_header_parse
 itx_bam_header_len itx_bam_header_free itx_scan_bam_device itx_scan_cpg itx_sync_counts itx_write_stat
 itx_write_report itx_write_filter itx_write_cpg_stat itx_write_cpg_filter itx_n_subfam itx_n_fam itx_n_class
-itx_n_elem itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
+itx_n_elem itx_n_repeats_parsed itx_n_chrom itx_name itx_counts itx_subfam_length itx_subfam_bp itx_n_rows itx_elem_counts_by_row
 itx_trace_enable itx_trace_fetch itx_query_select itx_last_profile itx_mark itx_elapsed_ms itx_tune itx_comm_unique_id itx_comm_init
-itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
+itx_comm_allreduce_counts itx_get_counters itx_comm_destroy itx_scan_shard_file itx_shard_chain_check
+itx_scan_alignments_shard itx_scan_cpg_shard itx_get_cpg_totals itx_comm_rank itx_index_build_on itx_dev_alloc itx_dev_free itx_dev_upload itx_host_alloc_pinned
 itx_host_free_pinned itx_dev_flush_l2 itx_dev_sync itx_stream_fetch itx_wig_to_bigwig itx_sam_to_bam itx_free""".split()
 
 _lib = None
@@ -72,7 +73,7 @@ def bind(L):
     for f in ("itx_n_subfam", "itx_n_fam", "itx_n_class", "itx_n_chrom"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_int32
-    for f in ("itx_n_elem", "itx_n_rows"):
+    for f in ("itx_n_elem", "itx_n_rows", "itx_n_repeats_parsed"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_int64
     L.itx_name.restype = cp

@@ -149,7 +149,7 @@ static int main_stat(int argc, char **argv) {
     fprintf(stderr, "* Parsing the rmsk file\n");
     itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
     if (!ix) die("%s", err);
-    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     LAP("index built");
     fprintf(stderr, "* Parsing the SAM/BAM file\n");
     if (itx_scan_alignments(ix, bams, &o, cnt, err) != ITX_OK) die("%s", err);
@@ -220,10 +220,10 @@ static int main_filter(int argc, char **argv) {
     fprintf(stderr, "* Start to parse the rmsk file\n");
     itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
     if (!ix) die("%s", err);
-    if (field) fprintf(stderr, "* Total %lld repeats for [%s].\n", (long long)itx_n_elem(ix), subfam);
-    else fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    if (field) fprintf(stderr, "* Total %lld repeats for [%s].\n", (long long)itx_n_repeats_parsed(ix), subfam);
+    else fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     fprintf(stderr, "* Start to parse the SAM/BAM file\n");
-    if (itx_scan_alignments(ix, bam, &o, cnt, err) != ITX_OK) die("%s", err);
+    if (itx_scan_alignment_file(ix, bam, &o, cnt, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Preparing the output file\n");
@@ -254,7 +254,7 @@ static int main_cpgstat(int argc, char **argv) {
     fprintf(stderr, "* Start to parse the rmsk file\n");
     itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
     if (!ix) die("%s", err);
-    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_elem(ix));
+    fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     fprintf(stderr, "* Start to parse the bedGraph file\n");
     if (itx_scan_cpg(ix, bg, 0, &lines, &inrep, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Processed CpG sites: %u\n* CpG sites in Repeats: %u\n", lines, inrep);

@@ -22,6 +22,26 @@ int itx_bgzf_header_ok(const uint8_t *h) {
     return h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
 }
 
+/* First BGZF block boundary in buf[0, n): an offset whose header checks out and whose BSIZE leads to another good header --
+ * twice over when the bytes are there -- or exactly to the end of the file (at_eof).  What a reader that is dropped into the
+ * middle of a file does instead of consulting a .bai (the sharded scan: every rank but the first).  Returns -1 if there is none. */
+int64_t itx_bgzf_find_block(const uint8_t *buf, uint64_t n, int at_eof) {
+    for (uint64_t i = 0; i + 18 <= n; i++) {
+        if (buf[i] != 31 || !itx_bgzf_header_ok(buf + i)) continue;
+        uint64_t o = i; int good = 0;
+        for (int hop = 0; hop < 3; hop++) {
+            if (o + 18 > n) { good = hop > 0 || (at_eof && o == n); break; }
+            if (!itx_bgzf_header_ok(buf + o)) { good = 0; break; }
+            const uint32_t bsize = ((uint32_t)buf[o + 16] | (uint32_t)buf[o + 17] << 8) + 1;
+            if (bsize < 26) { good = 0; break; }
+            o += bsize; good = 1;
+            if (at_eof && o == n) break;
+        }
+        if (good) return (int64_t)i;
+    }
+    return -1;
+}
+
 int itx_bgzf_scan(const uint8_t *file, uint64_t len, itx_bgzf_block **blocks, uint64_t *n_blocks, uint64_t *total_u, char err[ITX_ERRLEN]) {
     uint64_t cap = len / 16384 + 64, n = 0, off = 0, u = 0;
     itx_bgzf_block *b = (itx_bgzf_block *)malloc(sizeof(itx_bgzf_block) * cap);

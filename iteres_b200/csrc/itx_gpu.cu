@@ -15,12 +15,15 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <vector>
 
 #define ITX_SLACK 64
 #define ITX_MAX_EVENTS 4096
 #define ITX_SEEN_FAST 1024                 /* unknown-tid marks fetched with the end-of-scan report (BAM headers with more references take one more copy) */
 #define ITX_SCRATCH_BYTES (256 + ITX_SEEN_FAST * 4)
 #define ITX_MAX_WINDOWS 65536              /* launch groups of one scan that k_scan can log (more: the tuple path takes over) */
+#define ITX_INF_LANES_DEFAULT 32           /* blocks per k_inflate warp (ITX_INF_LANES), and for the last groups of a file (ITX_INF_TAIL_LANES) */
+#define ITX_INF_TAIL_LANES_DEFAULT 8
 #define ITX_INF_STREAMS 8                  /* inflate groups in flight: copy, Huffman pass, match pass and scan of different groups overlap */
 
 struct itx_cuda {
@@ -60,13 +63,19 @@ struct itx_cuda {
     FILE *bed_f, *bed_uf; int bed_owner;             /* opened by the outermost entry point of the run */
     uint64_t ord_cap;                                /* trace entries one launch group may need (0: not in ordered mode) */
     itx_trace *h_ord_trace; uint64_t h_ord_trace_cap; uint8_t *h_ord_buf; uint64_t h_ord_buf_cap;
-    int dirty_el;                                    /* the per-locus block may hold another rank's counts (an allreduce covers the whole u32 block) */
+    int l2_persist_on;
+    int used_bp;                                     /* a stat-mode scan has run since the last reset (the coverage difference arrays may be non-zero) */
+    void *d_snap; size_t snap_cap;                   /* counter snapshot of a sharded scan (counters_snapshot) */
+    unsigned long long *d_shard;                     /* sharded scan: this rank's report + everybody's (NCCL all-gather) */
     int used_el, used_cpg, used_cpg_el, host_el, host_cpg, host_cpg_el;   /* per-locus / CpG counters touched on the device since the last reset; host copies not all zero */
     cudaStream_t inf_stream[ITX_INF_STREAMS]; cudaEvent_t inf_done[ITX_INF_STREAMS]; int inf_made;
     uint8_t *h_stage[2]; uint64_t h_stage_cap;
+    uint8_t *h_ring[4]; uint64_t h_ring_cap;          /* pinned slots of the compressed-window reader (ITX_RD_SLOTS) */
     void *d_flush;
     cudaEvent_t ev[ITX_MAX_EVENTS]; int n_ev_made;
     cudaEvent_t marks[8]; int marks_made;
+    cudaEvent_t grp_ev[64];                          /* one per inflate group in flight (the compressed ring's overwrite protection) */
+    cudaEvent_t *inf_ev; int inf_ev_made;            /* ITX_TIMING / profile: launch and end of every inflate group (events of THIS device) */
     /* NCCL (dlopen) */
     void *nccl_lib; void *nccl_comm; int nranks, rank;
 };
@@ -75,12 +84,13 @@ struct itx_cuda {
 #define CKN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
 
 static int g_device = 0;
+static int env_int_early(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 extern "C" int itx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 /* only noted here: the device is first touched by itx_index_build, where the driver start-up overlaps the table parse */
 extern "C" int itx_set_device(int device) { if (device < 0) return ITX_EARG; g_device = device; return ITX_OK; }
-static void *cuda_warm_up(void *arg) { (void)arg; if (cudaSetDevice(g_device) == cudaSuccess) cudaFree(0); return NULL; }
+static void *cuda_warm_up(void *arg) { if (cudaSetDevice((int)(intptr_t)arg) == cudaSuccess) cudaFree(0); return NULL; }
 extern "C" void *itx_dev_alloc(uint64_t bytes) { void *p = NULL; cudaSetDevice(g_device); if (cudaMalloc(&p, bytes) != cudaSuccess) return NULL; return p; }
 extern "C" void itx_dev_free(void *p) { cudaFree(p); }
 extern "C" int itx_dev_upload(void *dst, const void *src, uint64_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? ITX_OK : ITX_ENODEV; }
@@ -101,12 +111,16 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_D, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused, cu->d_snap, cu->d_shard};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
+    for (int i = 0; i < 4; i++) if (cu->h_ring[i]) cudaFreeHost(cu->h_ring[i]);
     if (cu->h_scratch) cudaFreeHost(cu->h_scratch);
     for (int i = 0; i < cu->n_ev_made; i++) cudaEventDestroy(cu->ev[i]);
     if (cu->marks_made) for (int i = 0; i < 8; i++) cudaEventDestroy(cu->marks[i]);
+    for (int i = 0; i < cu->inf_ev_made; i++) cudaEventDestroy(cu->inf_ev[i]);
+    for (int i = 0; i < 64; i++) if (cu->grp_ev[i]) cudaEventDestroy(cu->grp_ev[i]);
+    free(cu->inf_ev);
     if (cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) { cudaStreamDestroy(cu->inf_stream[i]); cudaEventDestroy(cu->inf_done[i]); }
     if (cu->stream) cudaStreamDestroy(cu->stream);
     if (cu->copy_stream) cudaStreamDestroy(cu->copy_stream);
@@ -127,7 +141,7 @@ static int zero_counters(itx_index *ix, char *err, int all) {
     itx_cuda *cu = ix->cu;
     const size_t bp2 = 2 * (size_t)ix->bp_len;
     CK(cudaMemsetAsync(cu->d_u64, 0, cu->n_u64 * 8, cu->stream));
-    CK(cudaMemsetAsync(cu->d_u32, 0, ((all || cu->used_el || cu->dirty_el) ? cu->n_u32 : bp2) * 4, cu->stream));
+    CK(cudaMemsetAsync(cu->d_u32, 0, ((all || cu->used_el) ? cu->n_u32 : bp2) * 4, cu->stream));
     if (all || cu->used_cpg || cu->used_cpg_el) {
         CK(cudaMemsetAsync(cu->d_cpg_u32, 0, cu->n_cpg_u32 * 4, cu->stream));
         CK(cudaMemsetAsync(cu->d_cpg_f64, 0, cu->n_cpg_f64 * 8, cu->stream));
@@ -141,7 +155,8 @@ extern "C" void itx_index_reset_counts(itx_index *ix) {
     char err[ITX_ERRLEN];
     cudaSetDevice(ix->cu->device);
     zero_counters(ix, err, 0);
-    ix->cu->used_el = ix->cu->used_cpg = ix->cu->used_cpg_el = ix->cu->dirty_el = 0;
+    ix->cu->used_el = ix->cu->used_cpg = ix->cu->used_cpg_el = ix->cu->used_bp = 0;
+    ix->cpg_lines = ix->cpg_in_repeat = 0;
     if (ix->cu->d_dup_keys) {        /* forget the reads of the previous run */
         cudaMemset(ix->cu->d_dup_keys, 0xff, ix->cu->dup_cap * sizeof(itx_k128)); cudaMemset(ix->cu->d_dup_ords, 0xff, ix->cu->dup_cap * 8);
         cudaMemset(ix->cu->d_dup_mins, 0xff, 16); cudaMemset(ix->cu->d_dup_mins + 2, 0, 8);
@@ -157,11 +172,16 @@ extern "C" void itx_index_reset_counts(itx_index *ix) {
 
 extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk,
                                       int filter_field, const char *filter_name, char err[ITX_ERRLEN]) {
+    return itx_index_build_on(g_device, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err);
+}
+extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, const char *rep_sizes, const char *rmsk,
+                                         int filter_field, const char *filter_name, char err[ITX_ERRLEN]) {
+    const int g_device = device;               /* shadows the process-wide default: this index lives on `device` */
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
     err[0] = 0;
     itx_index *ix = (itx_index *)calloc(1, sizeof(itx_index));
     /* the CUDA driver and context come up on a second thread while this one parses rmsk.txt */
-    pthread_t warm; const bool warming = pthread_create(&warm, NULL, cuda_warm_up, NULL) == 0;
+    pthread_t warm; const bool warming = pthread_create(&warm, NULL, cuda_warm_up, (void *)(intptr_t)g_device) == 0;
     const int host_rc = itx_host_index_load(ix, chrom_sizes, rep_sizes, rmsk, filter_field, filter_name, err);
     if (warming) pthread_join(warm, NULL);
     cudaGetLastError();
@@ -211,10 +231,9 @@ extern "C" itx_index *itx_index_build(const char *chrom_sizes, const char *rep_s
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
-        CKN(cudaMalloc((void **)&cu->d_carry_log, ITX_MAX_WINDOWS * 8)); CKN(cudaMalloc((void **)&cu->d_fused, 8));
+        CKN(cudaMalloc((void **)&cu->d_carry_log, ITX_MAX_WINDOWS * 8)); CKN(cudaMalloc((void **)&cu->d_fused, 32)); CKN(cudaMemset(cu->d_fused, 0, 32));
         CKN(cudaHostAlloc((void **)&cu->h_scratch, ITX_SCRATCH_BYTES, cudaHostAllocDefault));
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CKN(cudaFuncSetAttribute(k_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
         D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
@@ -364,7 +383,10 @@ typedef struct scan_ctx_s {
     int n_launch;
     int rmdup;
     /* fused mode: k_scan instead of the tuple path; the windows are logged so that a failed chain check can be replayed */
-    int fused; uint32_t n_win, wins_cap; struct scan_win { uint64_t k0; uint32_t n; uint64_t avail, len; } *wins;
+    int fused; uint32_t n_win, wins_cap; struct scan_win { uint64_t k0; uint32_t n; uint64_t avail, len, own; } *wins;
+    /* a scan that is one rank's shard of a stream: record starts at or past `own` are the next rank's; the first record start is
+     * guessed (carry0 == ITX_OFF_GUESS) or handed in; what the chain did at both ends comes back in entry_out / carry_out */
+    uint64_t own, carry0, entry_out, carry_out;
     /* ordered mode */
     int ordered, names; uint32_t mapQ; uint64_t p_cur; char **tname;
 } scan_ctx;
@@ -432,11 +454,15 @@ static int ordered_drain(scan_ctx *sc, uint64_t avail, char *err) {
 /* window: bytes per launch group; resident != 0: the whole stream is already on the device, so k_scan (which writes no
  * tuples) takes it in ONE launch group unless itx_tune set a window -- one tail instead of one per GiB */
 #define ITX_DEFAULT_WINDOW (1ull << 30)
-static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err, int resident = 0) {
+static void l2_persist_window(itx_index *ix);
+#define ITX_CARRY_HEADER (~0ull)          /* scan_begin: the chain starts right after the BAM header (a scan from the start of a stream) */
+static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, const uint8_t *d_bam, uint64_t len, const itx_scan_opts *o, uint64_t window, char *err, int resident = 0,
+                      uint64_t carry0 = ITX_CARRY_HEADER) {
     itx_cuda *cu = ix->cu;
     memset(sc, 0, sizeof *sc);
     sc->ix = ix; sc->h = h; sc->b = d_bam; sc->len = len; sc->o = dev_opts(o);
-    if (o->filter) cu->used_el = 1;
+    sc->own = ~0ull; sc->carry0 = carry0 == ITX_CARRY_HEADER ? h->hdr_len : carry0; sc->entry_out = sc->carry_out = ITX_OFF_NONE;
+    if (o->filter) cu->used_el = 1; else if (ix->stat_mode) cu->used_bp = 1;
     sc->rmdup = o->rmDup != 0;
     cu->want_sel = 0;
     sc->ordered = (o->outbed || o->outbed_unique || o->readNames) ? 1 : 0; sc->names = o->readNames != 0; sc->mapQ = o->mapQ;
@@ -448,9 +474,12 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     if (resident && !sc->ordered && ix->tune_window == ITX_DEFAULT_WINDOW && len > window) log_window = len < (1ull << 40) ? len : (1ull << 40);
     int rc = ensure_work(ix, window, log_window, err); if (rc) return rc;
     if (sc->ordered && (rc = ordered_begin(sc, o, err))) return rc;
-    sc->k_first = h->hdr_len / cu->C; sc->k_end = len > h->hdr_len ? (len + cu->C - 1) / cu->C : sc->k_first;
+    {
+        const uint64_t first = sc->carry0 >= ITX_OFF_GUESS ? 0 : sc->carry0;
+        sc->k_first = first / cu->C; sc->k_end = len > first ? (len + cu->C - 1) / cu->C : sc->k_first;
+    }
     sc->k_next = sc->k_first;
-    cu->h_scratch[0] = h->hdr_len;              /* the previous scan ended with a synchronize: its copy out of the scratch is long done */
+    cu->h_scratch[0] = sc->carry0;              /* the previous scan ended with a synchronize: its copy out of the scratch is long done */
     CK(cudaMemcpyAsync(cu->d_carry, cu->h_scratch, 8, cudaMemcpyHostToDevice, cu->stream));
     CK(cudaMemsetAsync(cu->d_work, 0, 16, cu->stream));
     CK(cudaMemsetAsync(cu->D.status, 0, 8 * sizeof(uint32_t), cu->stream));      /* per-scan flags and failure counts */
@@ -463,15 +492,39 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     {   /* one fused kernel per launch group unless something needs the tuples (-R, the ordered outputs, traces, ITX_FUSED=0) */
         const char *v = getenv("ITX_FUSED");
         sc->fused = !(v && strcmp(v, "0") == 0) && cu->decode_variant == 0 && !sc->rmdup && !sc->ordered && !ix->trace_cap && !cu->want_sel;
-        if (sc->fused) { CK(cudaMemsetAsync(cu->d_fused, 0xff, 4, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 1, 0, 4, cu->stream)); }
+        if (sc->carry0 == ITX_OFF_GUESS && (sc->rmdup || sc->ordered)) { snprintf(err, ITX_ERRLEN, "-R, -B / -V and filter -r follow the reads in file order: they are not available in a sharded scan"); return ITX_ENOTSUP; }
+        if (sc->fused) { CK(cudaMemsetAsync(cu->d_fused, 0xff, 4, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 1, 0, 12, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 4, 0xff, 8, cu->stream)); }
     }
+    l2_persist_window(ix);
     if (!resident) CK(cudaStreamSynchronize(cu->stream));      /* the streaming paths go on to use other streams (copies, inflate) that read the flags just reset */
     return ITX_OK;
 }
-static itx_decode_args decode_args(const scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len) {
+/* A/B switch ITX_L2_PERSIST=1: the coverage difference arrays (the target of k_scan's scattered reductions) are asked to stay in L2
+ * (persisting access-policy window on the scan stream) while the stream bytes pass through */
+static void l2_persist_window(itx_index *ix) {
+    itx_cuda *cu = ix->cu;
+    const int want = env_int_early("ITX_L2_PERSIST", 0) ? 1 : 0;
+    if (want == cu->l2_persist_on) return;
+    cudaStreamAttrValue v; memset(&v, 0, sizeof v);
+    if (want) {
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cu->device);
+        size_t bytes = 2 * (size_t)ix->bp_len * 4;
+        if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+        size_t lim = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim);
+        v.accessPolicyWindow.base_ptr = cu->d_u32; v.accessPolicyWindow.num_bytes = bytes; v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    cudaStreamSetAttribute(cu->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    if (!want) cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+    cu->l2_persist_on = want;
+}
+static itx_decode_args decode_args(const scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, uint64_t own) {
     itx_cuda *cu = sc->ix->cu;
     itx_decode_args A;
     A.b = sc->b; A.len = len; A.avail = avail; A.k0 = k0; A.nchunks = n; A.C = cu->C; A.S = cu->S;
+    A.own = own < len ? own : len;
     A.tid = sc->h->d_tid; A.n_ref = sc->h->n_ref; A.o = sc->o;
     A.tuples = cu->d_tuples; A.entry = cu->d_entry; A.exit_ = cu->d_exit; A.nrec = cu->d_nrec;
     A.carry = cu->d_carry; A.winbad = cu->d_winbad; A.status = cu->D.status; A.work = cu->d_work;
@@ -479,9 +532,9 @@ static itx_decode_args decode_args(const scan_ctx *sc, uint64_t k0, uint32_t n, 
 }
 static size_t hist_bytes(const itx_cuda *cu) { return 2ull * (size_t)(cu->D.n_sub + cu->D.n_fam + cu->D.n_cla) * 4; }
 /* the tuple path for chunks [k0, k0 + n): k_decode_span (or k_decode) -> k_verify -> k_fixup -> [k_dedup x2] -> k_overlap */
-static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, char *err) {
+static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, uint64_t own, char *err) {
     itx_index *ix = sc->ix; itx_cuda *cu = ix->cu;
-    const itx_decode_args A = decode_args(sc, k0, n, avail, len);
+    const itx_decode_args A = decode_args(sc, k0, n, avail, len, own);
     bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
     if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
     if (cu->decode_variant == 0) {
@@ -543,10 +596,10 @@ static void launch_scan_kernel(itx_cuda *cu, const itx_scan_args &P, uint32_t n,
     const uint32_t want = (n + NW - 1) / NW, most = (uint32_t)(cu->sm_count * *ctas);
     k_scan<SH, NW><<<want < most ? want : most, NW * 32, smem, cu->stream>>>(P);
 }
-static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, int sign) {
+static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, uint64_t own, int sign) {
     itx_cuda *cu = sc->ix->cu;
-    itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len); P.D = cu->D; P.Dg = (const itx_dev_index *)cu->d_D; P.sign = sign; P.window = window;
-    P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused; P.ticket = cu->d_fused + 1;
+    itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len, own); P.D = cu->D; P.Dg = (const itx_dev_index *)cu->d_D; P.sign = sign; P.window = window;
+    P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused;
     const bool sh = fused_smem_hist(sc);
     const int nw = scan_warps();
     const size_t smem = (nw == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + (sh ? hist_bytes(cu) : 0);
@@ -568,14 +621,14 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
         if (sc->fused && sc->n_win >= ITX_MAX_WINDOWS) { snprintf(err, ITX_ERRLEN, "more than %d launch groups in one scan: raise the window with itx_tune", ITX_MAX_WINDOWS); return ITX_ENOTSUP; }
         if (sc->fused) {
             if (sc->n_win == sc->wins_cap) { sc->wins_cap = sc->wins_cap ? sc->wins_cap * 2 : 64; sc->wins = (scan_ctx::scan_win *)realloc(sc->wins, sc->wins_cap * sizeof(*sc->wins)); }
-            sc->wins[sc->n_win].k0 = sc->k_next; sc->wins[sc->n_win].n = n; sc->wins[sc->n_win].avail = avail; sc->wins[sc->n_win].len = sc->len;
+            sc->wins[sc->n_win].k0 = sc->k_next; sc->wins[sc->n_win].n = n; sc->wins[sc->n_win].avail = avail; sc->wins[sc->n_win].len = sc->len; sc->wins[sc->n_win].own = sc->own;
             bool timed = sc->ev_n + 3 <= ITX_MAX_EVENTS;
             if (timed) cudaEventRecord(get_event(cu, sc->ev_n), cu->stream);
-            launch_fused(sc, sc->n_win, sc->k_next, n, avail, sc->len, +1);
+            launch_fused(sc, sc->n_win, sc->k_next, n, avail, sc->len, sc->own, +1);
             if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 1), cu->stream); cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
             sc->n_win++;
         } else {
-            int rc = launch_tuple_path(sc, sc->k_next, n, avail, sc->len, err); if (rc) return rc;
+            int rc = launch_tuple_path(sc, sc->k_next, n, avail, sc->len, sc->own, err); if (rc) return rc;
         }
         sc->windows++;
         sc->k_next += n;
@@ -589,12 +642,12 @@ static int scan_window(scan_ctx *sc, uint64_t k_hi, uint64_t avail, char *err) {
  * what k_scan counted from that window on and count those windows again through the tuple path, which repairs guesses */
 static int fused_replay(scan_ctx *sc, uint32_t first, char *err) {
     itx_cuda *cu = sc->ix->cu;
-    for (uint32_t w = first; w < sc->n_win; w++) launch_fused(sc, w, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, -1);
+    for (uint32_t w = first; w < sc->n_win; w++) launch_fused(sc, w, sc->wins[w].k0, sc->wins[w].n, sc->wins[w].avail, sc->wins[w].len, sc->wins[w].own, -1);
     CK(cudaMemcpyAsync(cu->d_carry, cu->d_carry_log + first, 8, cudaMemcpyDeviceToDevice, cu->stream));
     for (uint32_t w = first; w < sc->n_win; w++)              /* a k_scan launch group may be larger than the tuple buffers: in pieces */
         for (uint64_t d = 0; d < sc->wins[w].n; d += cu->cap_chunks - 1) {
             const uint64_t n = sc->wins[w].n - d < cu->cap_chunks - 1 ? sc->wins[w].n - d : cu->cap_chunks - 1;
-            int rc = launch_tuple_path(sc, sc->wins[w].k0 + d, (uint32_t)n, sc->wins[w].avail, sc->wins[w].len, err); if (rc) return rc;
+            int rc = launch_tuple_path(sc, sc->wins[w].k0 + d, (uint32_t)n, sc->wins[w].avail, sc->wins[w].len, sc->wins[w].own, err); if (rc) return rc;
         }
     return ITX_OK;
 }
@@ -607,7 +660,11 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     uint32_t *seen_fast = (uint32_t *)((uint8_t *)cu->h_scratch + 256);
     const int32_t nt = sc->h->n_ref < ITX_MAX_TID_SEEN ? sc->h->n_ref : ITX_MAX_TID_SEEN, nt_fast = nt < ITX_SEEN_FAST ? nt : ITX_SEEN_FAST;
     *first_bad_p = 0xffffffffu;
+    unsigned long long *carry_p = cu->h_scratch + 29, *entry_p = cu->h_scratch + 30;      /* bytes 232 and 240 of the report */
+    *entry_p = ITX_OFF_NONE;
     if (sc->fused) CK(cudaMemcpyAsync(first_bad_p, cu->d_fused, 4, cudaMemcpyDeviceToHost, cu->stream));
+    if (sc->fused && sc->carry0 == ITX_OFF_GUESS) CK(cudaMemcpyAsync(entry_p, cu->d_fused + 4, 8, cudaMemcpyDeviceToHost, cu->stream));
+    CK(cudaMemcpyAsync(carry_p, cu->d_carry, 8, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaMemcpyAsync(hc, cu->D.cnt, 16 * 8, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaMemcpyAsync(st, cu->D.status, 8 * 4, cudaMemcpyDeviceToHost, cu->stream));
     if (nt_fast > 0) CK(cudaMemcpyAsync(seen_fast, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt_fast, cudaMemcpyDeviceToHost, cu->stream));
@@ -621,6 +678,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
             ix->prof.n_replayed_windows = sc->n_win - first_bad;
             CK(cudaMemcpyAsync(hc, cu->D.cnt, 16 * 8, cudaMemcpyDeviceToHost, cu->stream));
             CK(cudaMemcpyAsync(st, cu->D.status, 8 * 4, cudaMemcpyDeviceToHost, cu->stream));
+            CK(cudaMemcpyAsync(carry_p, cu->d_carry, 8, cudaMemcpyDeviceToHost, cu->stream));
             if (nt_fast > 0) CK(cudaMemcpyAsync(seen_fast, cu->D.tid_unknown_seen, sizeof(uint32_t) * (size_t)nt_fast, cudaMemcpyDeviceToHost, cu->stream));
             CK(cudaStreamSynchronize(cu->stream));
         }
@@ -628,6 +686,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     }
     for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k];
     if (cnt) memcpy(cnt, ix->cnt, sizeof ix->cnt);
+    sc->carry_out = *carry_p; sc->entry_out = sc->carry0 == ITX_OFF_GUESS ? *entry_p : sc->carry0;
     itx_profile *P = &ix->prof;
     P->decode_ms = P->overlap_ms = 0; P->total_ms = 0;
     for (int i = 0; i + 2 < sc->ev_n + 1 && i + 2 < ITX_MAX_EVENTS; i += 3) {
@@ -766,52 +825,256 @@ static int grow_device(itx_cuda *cu, void **p, uint64_t *cap, uint64_t need, uin
     return ITX_OK;
 }
 
-/* BGZF -> HBM in ONE pass, the inflate on the device.  Host threads read the compressed file window by window
- * into pinned memory (two slots); the main thread walks the block headers of the window just read (BSIZE at byte
- * 16, ISIZE in the footer: bgzf.c:401-411, 471-521), which gives every block its place in the uncompressed stream,
- * and sends window and block table over PCIe on the copy stream.  Per group of about one resident wave of blocks
- * the scan stream runs k_inflate (Huffman decoding, literals, match lists), k_lz_resolve (match copies) and then
- * the scan kernels over everything that lies before the group.  The stream's total size is only known at the
- * end: the stream buffer is sized from the first window's compression ratio and grown if that was too small. */
-static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth) {
+/* ------------------------------------------------------------------ compressed windows: from the source towards the device */
+/* The compressed bytes cross PCIe window by window (Wc bytes).  A source that is pinned host memory is handed to the copy
+ * engine where it lies (no host copy at all); anything else -- a file descriptor, pageable memory -- goes through a ring of
+ * pinned slots that a reader thread keeps filled ahead of the consumer (pread / memcpy by the pool's threads), so that reading
+ * window w + 2 overlaps walking the block headers of window w + 1 and the DMA of window w.  A window ends in the middle of
+ * a block; the cut block's bytes are moved in front of the next slot (every slot has ITX_RD_HEAD bytes of room there), so the
+ * consumer always sees whole blocks without anything being read twice. */
+#define ITX_RD_SLOTS 4
+#define ITX_RD_HEAD 65536u
+typedef struct comp_reader {
+    const itx_bgzf_src *S; uint64_t begin, end, Wc; int nth, direct, device;
+    uint8_t *slot[ITX_RD_SLOTS]; cudaEvent_t freed[ITX_RD_SLOTS];
+    pthread_t th; int th_started; pthread_mutex_t mu; pthread_cond_t cv;
+    uint64_t produced, released; int failed, stop;
+} comp_reader;
+static void *comp_reader_main(void *arg) {
+    comp_reader *R = (comp_reader *)arg;
+    cudaSetDevice(R->device);
+    for (uint64_t w = 0;; w++) {
+        const uint64_t o0 = R->begin + w * R->Wc;
+        if (o0 >= R->end) break;
+        pthread_mutex_lock(&R->mu);
+        while (!R->stop && w >= R->released + ITX_RD_SLOTS) pthread_cond_wait(&R->cv, &R->mu);
+        const int stop = R->stop;
+        pthread_mutex_unlock(&R->mu);
+        if (stop) break;
+        const int sl = (int)(w % ITX_RD_SLOTS);
+        cudaEventSynchronize(R->freed[sl]);                         /* the copy out of this slot's previous window is done */
+        const uint64_t o1 = o0 + R->Wc < R->end ? o0 + R->Wc : R->end;
+        const int rc = src_read(R->S, o0, o1, R->slot[sl] + ITX_RD_HEAD, R->nth);
+        pthread_mutex_lock(&R->mu);
+        if (rc != ITX_OK) R->failed = 1;
+        R->produced = w + 1;
+        pthread_cond_broadcast(&R->cv);
+        pthread_mutex_unlock(&R->mu);
+        if (rc != ITX_OK) break;
+    }
+    return NULL;
+}
+static int comp_reader_open(comp_reader *R, itx_cuda *cu, const itx_bgzf_src *S, uint64_t begin, uint64_t end, uint64_t Wc, int nth, char *err) {
+    memset(R, 0, sizeof *R);
+    R->S = S; R->begin = begin; R->end = end; R->Wc = Wc; R->nth = nth; R->device = cu->device;
+    if (S->fd < 0) {
+        cudaPointerAttributes at;
+        R->direct = cudaPointerGetAttributes(&at, S->mem) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        { const char *v = getenv("ITX_PINNED_DIRECT"); if (v && atoi(v) == 0) R->direct = 0; }      /* A/B: stage even pinned memory */
+    }
+    if (R->direct) return ITX_OK;
+    if (cu->h_ring_cap < Wc + ITX_RD_HEAD + 64) {
+        for (int i = 0; i < ITX_RD_SLOTS; i++) { if (cu->h_ring[i]) cudaFreeHost(cu->h_ring[i]); cu->h_ring[i] = NULL; }
+        cu->h_ring_cap = 0;
+        for (int i = 0; i < ITX_RD_SLOTS; i++) CK(cudaHostAlloc((void **)&cu->h_ring[i], Wc + ITX_RD_HEAD + 64, cudaHostAllocDefault));
+        cu->h_ring_cap = Wc + ITX_RD_HEAD + 64;
+    }
+    for (int i = 0; i < ITX_RD_SLOTS; i++) { R->slot[i] = cu->h_ring[i]; CK(cudaEventCreateWithFlags(&R->freed[i], cudaEventDisableTiming)); }
+    pthread_mutex_init(&R->mu, NULL); pthread_cond_init(&R->cv, NULL);
+    if (pthread_create(&R->th, NULL, comp_reader_main, R) != 0) { snprintf(err, ITX_ERRLEN, "cannot start the reader thread"); return ITX_ENOMEM; }
+    R->th_started = 1;
+    return ITX_OK;
+}
+/* window w as the consumer sees it: *p points at file offset `cur` (<= the window's own first byte: what the window before
+ * left over lies in front), *n bytes are there */
+static int comp_reader_get(comp_reader *R, uint64_t w, uint64_t cur, const uint8_t **p, uint64_t *n) {
+    if (R->direct) { *p = R->S->mem + cur; *n = R->end - cur < R->Wc ? R->end - cur : R->Wc; return ITX_OK; }
+    const uint64_t o0 = R->begin + w * R->Wc;
+    if (o0 >= R->end) { *p = R->slot[w % ITX_RD_SLOTS] + ITX_RD_HEAD - (o0 - cur); *n = o0 - cur; return ITX_OK; }      /* only the leftover */
+    pthread_mutex_lock(&R->mu);
+    while (R->produced <= w && !R->failed) pthread_cond_wait(&R->cv, &R->mu);
+    const int failed = R->failed && R->produced <= w;
+    pthread_mutex_unlock(&R->mu);
+    if (failed) return ITX_EIO;
+    const uint64_t o1 = o0 + R->Wc < R->end ? o0 + R->Wc : R->end;
+    *p = R->slot[w % ITX_RD_SLOTS] + ITX_RD_HEAD - (o0 - cur); *n = o1 - cur;
+    return ITX_OK;
+}
+/* the consumer is done with window w: its DMA (if any) has been enqueued on `copy`; the bytes from `cur` on were not used and go in front of the next slot */
+static void comp_reader_release(comp_reader *R, uint64_t w, const uint8_t *p, uint64_t n, uint64_t used, cudaStream_t copy) {
+    if (R->direct) return;
+    const uint64_t left = n - used;
+    const int nx = (int)((w + 1) % ITX_RD_SLOTS);
+    if (left && left <= ITX_RD_HEAD) {
+        cudaEventSynchronize(R->freed[nx]);                         /* the DMA that read that slot's front (ITX_RD_SLOTS - 1 windows ago) is done */
+        memmove(R->slot[nx] + ITX_RD_HEAD - left, p + used, left);
+    }
+    cudaEventRecord(R->freed[w % ITX_RD_SLOTS], copy);
+    pthread_mutex_lock(&R->mu);
+    R->released = w + 1;
+    pthread_cond_broadcast(&R->cv);
+    pthread_mutex_unlock(&R->mu);
+}
+static void comp_reader_close(comp_reader *R) {
+    if (R->th_started) {
+        pthread_mutex_lock(&R->mu); R->stop = 1; pthread_cond_broadcast(&R->cv); pthread_mutex_unlock(&R->mu);
+        pthread_join(R->th, NULL);
+        pthread_mutex_destroy(&R->mu); pthread_cond_destroy(&R->cv);
+    }
+    if (!R->direct) for (int i = 0; i < ITX_RD_SLOTS; i++) if (R->freed[i]) { cudaEventSynchronize(R->freed[i]); cudaEventDestroy(R->freed[i]); }
+}
+
+/* the BAM header of a BGZF source, parsed on the host out of the file's first blocks (whatever part of the file the caller goes on to scan) */
+static itx_bam_header *bam_header_from_src(itx_index *ix, const itx_bgzf_src *S, int addChr, int nth, char *err) {
+    itx_bam_header *h = NULL; uint8_t *cbuf = NULL, *hb = NULL; itx_bgzf_block *blk = NULL;
+    char e2[ITX_ERRLEN]; e2[0] = 0;
+    for (uint64_t want = 1u << 20;; want *= 4) {
+        const uint64_t n = want < S->len ? want : S->len;
+        const uint8_t *c = S->mem;
+        if (S->fd >= 0) {
+            cbuf = (uint8_t *)realloc(cbuf, n + 64);
+            if (!cbuf || itx_parallel_pread(S->fd, 0, n, cbuf, nth) != ITX_OK) { snprintf(err, ITX_ERRLEN, "read error at the start of the BAM file"); break; }
+            c = cbuf;
+        }
+        uint64_t nblk = 0, total = 0;
+        free(blk); blk = NULL;
+        if (itx_bgzf_scan(c, n, &blk, &nblk, &total, e2) != ITX_OK) { snprintf(err, ITX_ERRLEN, "%s", e2); break; }
+        bool stop = nblk == 0;                                 /* not a BGZF file at all */
+        for (uint64_t nb = 1; nb <= nblk && !h && !stop; nb = nb < 4 ? nb + 1 : nb * 2) {
+            const uint64_t n1 = nb < nblk ? nb : nblk, ub = blk[n1 - 1].uoff + blk[n1 - 1].isize;
+            hb = (uint8_t *)realloc(hb, ub + 64);
+            if (!hb || itx_bgzf_inflate_range(c, blk, 0, n1, hb, nth, NULL) != ITX_OK) { snprintf(e2, ITX_ERRLEN, "BGZF inflate failed in the header blocks"); stop = true; break; }
+            h = itx_bam_header_parse(ix, hb, ub, addChr, e2);
+            if (!h && memcmp(hb, "BAM\1", 4) != 0) stop = true;
+            if (n1 == nblk) break;
+        }
+        if (h || stop || n == S->len) {
+            if (!h) snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : (nblk ? "truncated BAM header" : "invalid BAM binary header (this is not a BAM file)"));
+            break;
+        }
+    }
+    free(cbuf); free(hb); free(blk);
+    return h;
+}
+
+/* what one rank of a sharded scan is told and what it reports (itx_scan_shard_file) */
+typedef struct {
+    int rank, nranks;
+    uint64_t entry;            /* in: ITX_OFF_GUESS, or the rank-local offset of the first record (from the rank before) */
+    uint64_t margin;           /* in: uncompressed bytes read past the own range for the record that straddles its end */
+    uint64_t entry_rel;        /* out: the first record start the scan settled on (rank-local; NONE: it met none) */
+    uint64_t exit_rel;         /* out: where the chain left the own range, relative to its end (ITX_OFF_END: the chain ended) */
+    uint64_t own_bytes;        /* out: uncompressed bytes of the own blocks */
+    int more_after;            /* out: there was more of the file after what was read (a chain that ended may just have run out of margin) */
+} shard_io;
+
+/* BGZF -> HBM in ONE pass, the inflate on the device.  The compressed bytes arrive window by window (above); the main
+ * thread walks the block headers of each window (BSIZE at byte 16, ISIZE in the footer: bgzf.c:401-411, 471-521),
+ * which gives every block its place in the uncompressed stream, and sends window and block table over PCIe on the copy
+ * stream -- into a RING on the device when the file is larger than the ring (a window's place is recycled once the groups
+ * that read it are done).  Blocks are handed to the device in groups: one k_inflate (Huffman decoding, literals, match
+ * lists) + k_lz_resolve (match copies) pair per group on one of ITX_INF_STREAMS streams, and the scan kernels follow
+ * 64 MiB (the largest BAM record) behind the inflated front.  The stream's total size is only known at the end: the
+ * stream buffer is sized from the first window's compression ratio and grown if that was too small.
+ * sh != NULL: this is rank sh->rank of sh->nranks.  The rank owns the blocks that START in its share of the file's bytes
+ * (boundaries found by itx_bgzf_find_block), a record belongs to the rank in whose blocks it starts, and the scan reads
+ * on past the own range until the straddling record is whole. */
+template <uint32_t LG>
+static void launch_inflate(const itx_inflate_args &IA, cudaStream_t st) {
+    static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    if (!attr_set[LG]) { cudaFuncSetAttribute(k_inflate<LG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); attr_set[LG] = true; }
+    const uint64_t nb = (IA.nblk + (1u << LG) - 1) >> LG;
+    k_inflate<LG><<<(unsigned)nb, ITX_INF_THREADS, ITX_INF_SMEM(LG), st>>>(IA);
+}
+static int env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
+static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth, shard_io *sh) {
     itx_cuda *cu = ix->cu;
     const uint64_t flen = S->len;
     int rc = ITX_OK;
     const bool timing = getenv("ITX_TIMING") != NULL; const double tm0 = now_ms();
-    uint64_t Wc = 64ull << 20;                               /* compressed bytes per read / copy window */
+    uint64_t Wc = 64ull << 20;                               /* compressed bytes per window */
+    { const int mb = env_int("ITX_COMP_WINDOW_MB", 0); if (mb > 0) Wc = (uint64_t)mb << 20; }
     if (Wc > flen) Wc = flen;
     if (Wc < (1u << 20)) Wc = 1u << 20;
-    cudaEvent_t slot_free[2] = {NULL, NULL}, begin_ev = NULL;
-    enum { MAXW = 256 }; static cudaEvent_t wev[2 * MAXW]; static int wev_made = 0; int nw = 0;
-    itx_bgzf_block *blk = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;
+    cudaEvent_t copied = NULL, begin_ev = NULL;
+    enum { MAXW = 256 }; cudaEvent_t *wev = NULL; int nw = 0;
+    itx_bgzf_block *blk = NULL; uint64_t *foff = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;
     itx_bam_header *h = NULL;
     scan_ctx sc; bool begun = false;
+    comp_reader R; bool reader_open = false;
     double inflate_ms = 0, wall0 = now_ms();
+    /* launched groups, oldest first: where their compressed bytes start in the ring (absolute, ever-growing position) and the event slot that says they are done */
+    enum { GQ = 64 }; uint64_t g_abs[GQ]; uint64_t g_waited = 0;
     do {
-        if ((rc = ensure_stage(cu, Wc + 65536, err))) break;
-        if ((rc = grow_device(cu, (void **)&cu->d_comp, &cu->d_comp_cap, flen + ITX_SLACK, 0, "the compressed image", err))) break;
-        for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming);
+        /* ---- this rank's share of the file */
+        uint64_t r_begin = 0, r_end = flen;
+        const bool sharded = sh && sh->nranks > 1;
+        if (sh) { sh->entry_rel = ITX_OFF_NONE; sh->exit_rel = ITX_OFF_NONE; sh->own_bytes = 0; sh->more_after = 0; }
+        if (sharded) {
+            r_begin = flen / (uint64_t)sh->nranks * (uint64_t)sh->rank; r_end = sh->rank + 1 == sh->nranks ? flen : flen / (uint64_t)sh->nranks * (uint64_t)(sh->rank + 1);
+            if (sh->rank > 0) {
+                /* the first block that starts at or after r_begin (a block is at most 64 KiB long) */
+                uint64_t probe = 3u << 16; int64_t at = -1;
+                uint8_t *pb = NULL;
+                for (; at < 0; probe *= 4) {
+                    const uint64_t n = flen - r_begin < probe ? flen - r_begin : probe;
+                    const uint8_t *c = S->mem ? S->mem + r_begin : NULL;
+                    if (S->fd >= 0) { pb = (uint8_t *)realloc(pb, n + 64); if (!pb || itx_parallel_pread(S->fd, r_begin, r_begin + n, pb, nth) != ITX_OK) { rc = ITX_EIO; break; } c = pb; }
+                    at = itx_bgzf_find_block(c, n, r_begin + n == flen);
+                    if (at < 0 && (r_begin + n == flen || probe > (64u << 20))) break;
+                }
+                free(pb);
+                if (rc) { snprintf(err, ITX_ERRLEN, "read error in the BAM file at offset %llu", (unsigned long long)r_begin); break; }
+                r_begin = at < 0 ? flen : r_begin + (uint64_t)at;          /* no block starts in the rest of the file: nothing to own */
+            }
+            if (r_end < r_begin) r_end = r_begin;
+        }
+        if (!(h = bam_header_from_src(ix, S, o->addChr, nth, err))) { rc = ITX_EFORMAT; break; }
+        if ((rc = comp_reader_open(&R, cu, S, r_begin, flen, Wc, nth, err))) break;
+        reader_open = true;
+        /* the compressed bytes on the device: the whole range when it fits the ring, else a ring */
+        uint64_t ring_cap = (uint64_t)env_int("ITX_COMP_RING_MB", 8192) << 20;
+        if (ring_cap < 4 * (Wc + ITX_RD_HEAD)) ring_cap = 4 * (Wc + ITX_RD_HEAD);
+        { const uint64_t whole = flen - r_begin + ITX_RD_HEAD; if (!sharded && whole < ring_cap) ring_cap = whole; else if (sharded && (r_end - r_begin) + (sh->margin + (4u << 20)) * 2 + ITX_RD_HEAD < ring_cap) ring_cap = (r_end - r_begin) + (sh->margin + (4u << 20)) * 2 + ITX_RD_HEAD; }
+        if ((rc = grow_device(cu, (void **)&cu->d_comp, &cu->d_comp_cap, ring_cap + ITX_SLACK, 0, "the compressed bytes", err))) break;
+        ring_cap = cu->d_comp_cap - ITX_SLACK;                /* a larger buffer left by an earlier scan is used whole */
+        cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&begin_ev, cudaEventDisableTiming);
-        if (!wev_made) { for (int i = 0; i < 2 * MAXW; i++) cudaEventCreate(&wev[i]); wev_made = 1; }
+        if (!cu->inf_ev) {
+            cu->inf_ev = (cudaEvent_t *)calloc(2 * MAXW, sizeof(cudaEvent_t));
+            for (int i = 0; cu->inf_ev && i < 2 * MAXW; i++) { if (cudaEventCreate(&cu->inf_ev[i]) != cudaSuccess) break; cu->inf_ev_made = i + 1; }
+            cudaGetLastError();
+        }
+        wev = cu->inf_ev;
         /* a group = a run of consecutive blocks handed to the device as one k_inflate + k_lz_resolve pair on one of
-         * ITX_INF_STREAMS streams.  A thread needs tens of milliseconds for its block whatever the launch size, so groups
-         * are kept to a fraction of the resident threads and several are in flight: the file's copy, the two inflate
-         * passes and the scan of successive groups overlap. */
+         * ITX_INF_STREAMS streams.  A thread needs milliseconds for its block whatever the launch size, so groups are kept
+         * to a fraction of the resident threads and several are in flight: the file's copy, the two inflate passes and the
+         * scan of successive groups overlap.  Towards the end of the file nothing is left to hide that latency behind:
+         * the last groups are smaller and run fewer blocks per warp (shorter rounds). */
         if (!cu->inf_made) {
             for (int i = 0; i < ITX_INF_STREAMS; i++) { cudaStreamCreateWithFlags(&cu->inf_stream[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&cu->inf_done[i], cudaEventDisableTiming); }
             cu->inf_made = 1;
         }
         uint64_t GROUP = 16384;                    /* 151 ms per 3.4 GB file against 158 ms at 8192 and 173 ms at 4096 (B200, round 1) */
-        { const char *v = getenv("ITX_INF_GROUP"); if (v && atoll(v) >= 32) GROUP = (uint64_t)atoll(v) / 32 * 32; }
+        { const int v = env_int("ITX_INF_GROUP", 0); if (v >= 32) GROUP = (uint64_t)v / 32 * 32; }
         {   /* small files: no more slots than the file can have blocks (should a file beat the estimate, groups simply close earlier) */
-            const uint64_t est = flen / 2048 + 64;
+            const uint64_t est = (flen - r_begin) / 2048 + 64;
             if (GROUP > est) GROUP = (est + 31) / 32 * 32;
         }
-        if (!cu->d_tabs || cu->d_tabs_threads < GROUP * ITX_INF_STREAMS) {
+        uint64_t TAIL_GROUP = GROUP / 4 < 32 ? 32 : GROUP / 4 / 32 * 32;
+        { const int v = env_int("ITX_INF_TAIL_GROUP", 0); if (v >= 32) TAIL_GROUP = (uint64_t)v / 32 * 32; if (TAIL_GROUP > GROUP) TAIL_GROUP = GROUP; }
+        const int LANES = env_int("ITX_INF_LANES", ITX_INF_LANES_DEFAULT), TAIL_LANES = env_int("ITX_INF_TAIL_LANES", ITX_INF_TAIL_LANES_DEFAULT);
+        const uint64_t min_lanes = (uint64_t)(LANES < TAIL_LANES ? LANES : TAIL_LANES) >= 8 ? (uint64_t)(LANES < TAIL_LANES ? LANES : TAIL_LANES) : 8;
+        const uint64_t tab_warps = (GROUP + min_lanes - 1) / min_lanes * ITX_INF_STREAMS;       /* warps whose long-code symbol arrays may be live at once */
+        if (!cu->d_tabs || cu->d_tabs_threads < tab_warps * 32) {
+            cudaStreamSynchronize(cu->stream);
             cudaFree(cu->d_tabs); cu->d_tabs = NULL;
-            if (cudaMalloc((void **)&cu->d_tabs, GROUP * ITX_INF_STREAMS * ITX_T_CELLS * 2) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
-            cu->d_tabs_threads = GROUP * ITX_INF_STREAMS;
+            if (cudaMalloc((void **)&cu->d_tabs, tab_warps * 32 * ITX_T_CELLS * 2) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate the inflate tables"); rc = ITX_ENOMEM; break; }
+            cu->d_tabs_threads = tab_warps * 32;
         }
+        const uint64_t tab_stride = cu->d_tabs_threads / ITX_INF_STREAMS * ITX_T_CELLS;           /* cells per stream */
         int lz_ctas = 1;
         cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ_SMEM);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_ctas, k_lz_resolve, ITX_LZ_THREADS, ITX_LZ_SMEM);
@@ -824,18 +1087,46 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 cudaMalloc((void **)&cu->d_mn, ns * 4) != cudaSuccess) { cudaGetLastError(); snprintf(err, ITX_ERRLEN, "cannot allocate the match lists (%llu blocks)", (unsigned long long)ns); rc = ITX_ENOMEM; break; }
             cu->d_m_slots = ns;
         }
-        uint64_t fo = 0, gb0 = 0, n_groups = 0; int slot = 0; bool ended = false;
+        const uint64_t m_stride = cu->d_m_slots / ITX_INF_STREAMS;
         const uint64_t MARGIN = (64ull << 20) + 65536;      /* a record is at most 2^26 bytes long: chunks this far behind the inflated front are safe to scan */
-        while (!ended && rc == ITX_OK) {
-            const uint64_t n = flen - fo < Wc ? flen - fo : Wc;
-            const bool more_in_file = fo + n < flen;
-            cudaEventSynchronize(slot_free[slot]);                             /* the previous copy out of this slot is done */
-            uint8_t *hs = cu->h_stage[slot];
-            if (n && src_read(S, fo, fo + n, hs, nth) != ITX_OK) { snprintf(err, ITX_ERRLEN, "read error in the BAM file at offset %llu", (unsigned long long)fo); rc = ITX_EIO; break; }
+        uint64_t cur = r_begin, gb0 = 0, n_groups = 0, cabs = 0, g_abs0 = 0, own_total = ~0ull, typical_group_bytes = GROUP * 24576ull;
+        bool ended = false, own_closed = false, g_open_has_abs = false;
+        /* hand blocks [gb0, upto) to the device; everything they need has been enqueued on the copy stream before `copied` was recorded */
+        auto launch_group = [&](uint64_t upto, bool tail) {
+            const int gs = (int)(n_groups % ITX_INF_STREAMS); cudaStream_t st = cu->inf_stream[gs];
+            cudaStreamWaitEvent(st, copied, 0);
+            if (n_groups == 0) cudaStreamWaitEvent(st, begin_ev, 0);           /* the status words are zeroed on the scan stream */
+            itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = upto - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
+            IA.tabs = cu->d_tabs + (size_t)gs * tab_stride;
+            IA.m_pl = cu->d_mpl + (size_t)gs * m_stride * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * m_stride * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * m_stride; IA.m_cap = ITX_M_WORST;
+            const bool ev_ok = 2 * nw + 1 < cu->inf_ev_made;
+            if (ev_ok) cudaEventRecord(wev[2 * nw], st);
+            const int lanes = tail ? TAIL_LANES : LANES;
+            if (lanes <= 8) launch_inflate<3>(IA, st); else if (lanes <= 16) launch_inflate<4>(IA, st); else launch_inflate<5>(IA, st);
+            uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
+            k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
+            if (ev_ok) { cudaEventRecord(wev[2 * nw + 1], st); nw++; }
+            cudaEventRecord(cu->inf_done[gs], st);
+            cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0);          /* the scan stream has now waited for every group so far */
+            sc.n_launch += 2;
+            {   /* an event of its own per group (GQ of them, reused round robin) for the ring: a window may only land on bytes whose groups are done */
+                const int gi = (int)(n_groups % GQ);
+                if (!cu->grp_ev[gi]) cudaEventCreateWithFlags(&cu->grp_ev[gi], cudaEventDisableTiming);
+                else if (n_groups >= GQ) cudaEventSynchronize(cu->grp_ev[gi]);           /* GQ groups back: long done */
+                cudaEventRecord(cu->grp_ev[gi], st);
+                g_abs[gi] = g_abs0;
+            }
+            gb0 = upto; n_groups++; g_open_has_abs = false;
+        };
+        for (uint64_t w = 0; !ended && rc == ITX_OK; w++) {
+            const uint8_t *hs = NULL; uint64_t n = 0;
+            if (comp_reader_get(&R, w, cur, &hs, &n) != ITX_OK) { snprintf(err, ITX_ERRLEN, "read error in the BAM file at offset %llu", (unsigned long long)cur); rc = ITX_EIO; break; }
+            const bool more_in_file = cur + n < flen;
             /* the blocks that lie completely inside this window */
             const uint64_t nb_before = nblk; uint64_t off = 0;
+            std::vector<uint64_t> closes;                                              /* groups that fill up inside this window end at these block counts */
+            uint64_t g_first = gb0;                                                    /* first block of the group being filled */
             for (;;) {
-                if (nblk - gb0 >= GROUP) break;                                        /* the group is full: the rest is read again for the next one */
                 if (off + 18 > n) { if (!more_in_file) ended = true; break; }
                 const uint8_t *hd = hs + off;
                 if (!itx_bgzf_header_ok(hd)) { ended = true; break; }                  /* a bad header ends the stream silently (bgzf_read) */
@@ -844,27 +1135,23 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 if (off + bsize > n) { if (!more_in_file) ended = true; break; }      /* continues in the next window, or the file is cut short */
                 uint32_t isize; memcpy(&isize, hd + bsize - 4, 4);
                 if (isize == 0 || isize > 65536) { ended = true; break; }              /* an empty block ends the data (bgzf.c:539-546) */
-                if (nblk == blk_cap) { blk_cap = blk_cap ? blk_cap * 2 : 4096; blk = (itx_bgzf_block *)realloc(blk, sizeof(itx_bgzf_block) * blk_cap); }
-                blk[nblk].coff = fo + off; blk[nblk].csize = bsize; blk[nblk].isize = isize; blk[nblk].uoff = total;
+                if (sharded && !own_closed && cur + off >= r_end) { own_closed = true; own_total = total; }
+                if (own_closed && total - own_total >= sh->margin) { ended = true; sh->more_after = 1; break; }      /* the straddling record has its room */
+                if (nblk == blk_cap) { blk_cap = blk_cap ? blk_cap * 2 : 4096; blk = (itx_bgzf_block *)realloc(blk, sizeof(itx_bgzf_block) * blk_cap); foff = (uint64_t *)realloc(foff, 8 * blk_cap); }
+                blk[nblk].coff = off; blk[nblk].csize = bsize; blk[nblk].isize = isize; blk[nblk].uoff = total; foff[nblk] = cur + off;
                 nblk++; total += isize; off += bsize;
+                /* near the end of the file (or of the own range) groups close early */
+                const uint64_t left_c = (sharded && !own_closed ? r_end : flen) - (cur + off < (sharded && !own_closed ? r_end : flen) ? cur + off : (sharded && !own_closed ? r_end : flen));
+                const uint64_t G = left_c < typical_group_bytes ? TAIL_GROUP : GROUP;
+                if (nblk - g_first >= G) { closes.push_back(nblk); g_first = nblk; }
             }
-            if (off == 0 && nblk - gb0 < GROUP) ended = true;                          /* no progress is possible */
+            if (off == 0 && !ended && n >= Wc) ended = true;                           /* no progress is possible */
             if (!begun) {
-                /* the BAM header is parsed on the host out of the first blocks of the first window */
-                uint8_t *hb = NULL; char e2[ITX_ERRLEN]; e2[0] = 0;
-                for (uint64_t nb = 1; nb <= nblk && !h; nb = nb < 4 ? nb + 1 : nb * 2) {
-                    const uint64_t n1 = nb < nblk ? nb : nblk, ub = blk[n1 - 1].uoff + blk[n1 - 1].isize;
-                    hb = (uint8_t *)realloc(hb, ub + 64);
-                    if (itx_bgzf_inflate_range(hs, blk, 0, n1, hb, nth, NULL) != ITX_OK) { snprintf(e2, ITX_ERRLEN, "BGZF inflate failed in the header blocks"); break; }
-                    h = itx_bam_header_parse(ix, hb, ub, o->addChr, e2);
-                    if (!h && (n1 == nblk || memcmp(hb, "BAM\1", 4) != 0)) break;
-                }
-                free(hb);
-                if (!h) { snprintf(err, ITX_ERRLEN, "%s", e2[0] ? e2 : (nblk ? "truncated BAM header" : "invalid BAM binary header (this is not a BAM file)")); rc = ITX_EFORMAT; break; }
-                /* first guess of the stream size: this window's ratio over the whole file, with a margin */
+                /* first guess of the stream size: this window's ratio over this rank's share of the file, with a margin */
                 uint64_t guess = total;
                 if (!ended) {
-                    guess = (uint64_t)((double)flen * ((double)total / (double)off) * 1.08) + (64ull << 20);
+                    const uint64_t share = (sharded ? r_end : flen) - r_begin;
+                    guess = (uint64_t)((double)share * ((double)total / (double)(off ? off : 1)) * 1.08) + (64ull << 20) + (sharded ? sh->margin + (1u << 20) : 0);
                     if (!(cu->d_stream && cu->d_stream_cap >= guess + ITX_SLACK)) {
                         size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
                         const uint64_t room = (uint64_t)fr + (cu->d_stream ? cu->d_stream_cap : 0);      /* the old buffer is released first */
@@ -873,15 +1160,17 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 }
                 if (!(cu->d_stream && cu->d_stream_cap >= guess + ITX_SLACK)) { cudaStreamSynchronize(cu->stream); cudaFree(cu->d_stream); cu->d_stream = NULL; cu->d_stream_cap = 0; }
                 if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, guess + ITX_SLACK, 0, "the uncompressed stream", err))) break;
-                if ((rc = scan_begin(&sc, ix, h, cu->d_stream, 1ull << 62, o, guess < ix->tune_window ? guess : ix->tune_window, err))) break;
+                const uint64_t carry0 = (sharded && sh->rank > 0) ? sh->entry : ITX_CARRY_HEADER;
+                if ((rc = scan_begin(&sc, ix, h, cu->d_stream, 1ull << 62, o, guess < ix->tune_window ? guess : ix->tune_window, err, 0, carry0))) break;
                 begun = true;
                 cudaEventRecord(begin_ev, cu->stream);
+                if (off) typical_group_bytes = (uint64_t)((double)GROUP * (double)off / (double)(nblk ? nblk : 1));
                 if (timing) fprintf(stderr, "[itx timing] first window read, header parsed, buffers ready at %.1f ms\n", now_ms() - tm0);
             }
             if (total + ITX_SLACK > cu->d_stream_cap) {
                 /* the guess was too small: grow, keeping what has been inflated (everything before the open group) */
                 const uint64_t want = total + total / 2 + (256ull << 20);
-                if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, want + ITX_SLACK, blk[gb0].uoff, "the uncompressed stream", err))) break;
+                if ((rc = grow_device(cu, (void **)&cu->d_stream, &cu->d_stream_cap, want + ITX_SLACK, gb0 < nblk ? blk[gb0].uoff : total, "the uncompressed stream", err))) break;
                 sc.b = cu->d_stream;
             }
             if (nblk > cu->d_blk_cap) {
@@ -892,38 +1181,43 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 if (rc) break;
             }
             if (off) {
-                if (cudaMemcpyAsync(cu->d_comp + fo, hs, off, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess ||
-                    cudaMemcpyAsync(cu->d_blk + nb_before, blk + nb_before, (nblk - nb_before) * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
-            }
-            cudaEventRecord(slot_free[slot], cu->copy_stream);
-            fo += off;
-            if (nblk > gb0 && (nblk - gb0 >= GROUP || ended)) {
-                const int gs = (int)(n_groups % ITX_INF_STREAMS); cudaStream_t st = cu->inf_stream[gs];
-                cudaStreamWaitEvent(st, slot_free[slot], 0);                   /* copies are in order: the last one covers the group */
-                if (n_groups == 0) cudaStreamWaitEvent(st, begin_ev, 0);       /* the status words are zeroed on the scan stream */
-                itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = nblk - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
-                IA.tabs = cu->d_tabs + (size_t)gs * GROUP * ITX_T_CELLS;
-                IA.m_pl = cu->d_mpl + (size_t)gs * GROUP * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * GROUP * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * GROUP; IA.m_cap = ITX_M_WORST;
-                const uint64_t nb = (IA.nblk + ITX_INF_THREADS - 1) / ITX_INF_THREADS;
-                if (nw < MAXW) cudaEventRecord(wev[2 * nw], st);
-                k_inflate<<<(unsigned)nb, ITX_INF_THREADS, ITX_INF_SMEM, st>>>(IA);
-                uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
-                k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
-                if (nw < MAXW) { cudaEventRecord(wev[2 * nw + 1], st); nw++; }
-                cudaEventRecord(cu->inf_done[gs], st);
-                cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0);          /* the scan stream has now waited for every group so far */
-                sc.n_launch += 2;
-                gb0 = nblk; n_groups++;
-                if (!ended) {
-                    const uint64_t k_hi = total > MARGIN ? (total - MARGIN) / cu->C : 0;
-                    if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, total, err);
+                /* the window's place in the ring; whatever lies there belongs to groups that must be done first */
+                if (cabs % ring_cap + off > ring_cap) cabs += ring_cap - cabs % ring_cap;          /* not across the ring's end */
+                if (!g_open_has_abs) { g_abs0 = cabs; g_open_has_abs = true; }
+                if (cabs + off > ring_cap) {
+                    const uint64_t low = cabs + off - ring_cap;                                      /* absolute positions below this one are overwritten */
+                    if (gb0 < nb_before && g_abs0 < low) launch_group(nb_before, false);             /* the open group itself is in the way: out it goes */
+                    if (!g_open_has_abs) { g_abs0 = cabs; g_open_has_abs = true; }
+                    if (g_waited + GQ < n_groups) g_waited = n_groups - GQ;                         /* older ones were waited for on the host */
+                    while (g_waited < n_groups && g_abs[g_waited % GQ] < low) { cudaStreamWaitEvent(cu->copy_stream, cu->grp_ev[g_waited % GQ], 0); g_waited++; }
                 }
+                const uint64_t cpos = cabs % ring_cap;
+                for (uint64_t k = nb_before; k < nblk; k++) blk[k].coff += cpos;
+                if (cudaMemcpyAsync(cu->d_comp + cpos, hs, off, cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess ||
+                    cudaMemcpyAsync(cu->d_blk + nb_before, blk + nb_before, (nblk - nb_before) * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
+                cabs += off;
             }
-            slot ^= 1;
+            cudaEventRecord(copied, cu->copy_stream);
+            comp_reader_release(&R, w, hs, n, off, cu->copy_stream);
+            cur += off;
+            if (own_closed) sc.own = own_total;
+            for (size_t k = 0; k < closes.size(); k++) if (closes[k] > gb0) launch_group(closes[k], closes[k] - gb0 < GROUP);
+            if (ended && nblk > gb0) launch_group(nblk, true);
+            if (!closes.empty() && !ended) {
+                const uint64_t front = gb0 ? blk[gb0 - 1].uoff + blk[gb0 - 1].isize : 0;          /* what the groups launched so far inflate */
+                uint64_t k_hi = front > MARGIN ? (front - MARGIN) / cu->C : 0;
+                if (own_closed) { const uint64_t k_own = (own_total + cu->C - 1) / cu->C; if (k_hi > k_own) k_hi = k_own; }
+                if (k_hi > sc.k_next) rc = scan_window(&sc, k_hi, front, err);
+            }
         }
         if (rc != ITX_OK) break;
         if (!begun) { snprintf(err, ITX_ERRLEN, "invalid BAM binary header (this is not a BAM file)"); rc = ITX_EFORMAT; break; }
-        sc.len = total; sc.k_end = total > h->hdr_len ? (total + cu->C - 1) / cu->C : sc.k_first;
+        if (!own_closed) own_total = total;
+        sc.len = total; sc.own = own_total;
+        {
+            const uint64_t first = sc.carry0 >= ITX_OFF_GUESS ? 0 : sc.carry0;
+            sc.k_end = own_total > first ? (own_total + cu->C - 1) / cu->C : sc.k_first;
+        }
         if (sc.k_next < sc.k_end) rc = scan_window(&sc, sc.k_end, total, err);
         if (timing) fprintf(stderr, "[itx timing] file read, copies and kernels enqueued at %.1f ms (%llu blocks, %llu bytes)\n", now_ms() - tm0, (unsigned long long)nblk, (unsigned long long)total);
         if (rc == ITX_OK) rc = scan_end(&sc, cnt, err);
@@ -931,20 +1225,26 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         if (rc == ITX_OK) {
             uint32_t st[8];
             if (cudaMemcpy(st, cu->D.status, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[5]) {
-                snprintf(err, ITX_ERRLEN, "BGZF inflate failed on %u block(s), e.g. block %u at compressed offset %llu", st[5], st[6], (unsigned long long)(st[6] < nblk ? blk[st[6]].coff : 0));
+                snprintf(err, ITX_ERRLEN, "BGZF inflate failed on %u block(s), e.g. block %u at compressed offset %llu", st[5], st[6], (unsigned long long)(st[6] < nblk ? foff[st[6]] : 0));
                 rc = ITX_EFORMAT;
             }
+        }
+        if (rc == ITX_OK && sh) {
+            sh->own_bytes = own_total;
+            sh->entry_rel = sc.k_first == sc.k_end && sc.carry0 == ITX_OFF_GUESS ? ITX_OFF_NONE : sc.entry_out;
+            sh->exit_rel = sc.carry_out >= ITX_OFF_GUESS ? (sc.carry_out == ITX_OFF_GUESS ? ITX_OFF_NONE : sc.carry_out) : (sc.carry_out >= own_total ? sc.carry_out - own_total : 0);
         }
         if (timing) for (int i = 0; i < nw; i++) { float a = 0, b = 0; cudaEventElapsedTime(&a, wev[0], wev[2 * i]); cudaEventElapsedTime(&b, wev[0], wev[2 * i + 1]); fprintf(stderr, "[itx timing] inflate group %d: %.1f .. %.1f ms after the first launch\n", i, a, b); }
         /* groups overlap: report the span from the first group's launch to the last group's end */
         for (int i = 0; i < nw; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, wev[0], wev[2 * i + 1]) == cudaSuccess && ms > inflate_ms) inflate_ms = ms; }
     } while (0);
     if (rc != ITX_OK) { cudaStreamSynchronize(cu->stream); cudaStreamSynchronize(cu->copy_stream); if (!err[0]) snprintf(err, ITX_ERRLEN, "CUDA error while streaming: %s", cudaGetErrorString(cudaGetLastError())); }
-    ix->prof.h2d_bytes = flen; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time, first k_inflate launch to last k_lz_resolve end */
+    ix->prof.h2d_bytes = reader_open ? (nblk ? foff[nblk - 1] + blk[nblk - 1].csize - foff[0] : 0) : 0; ix->prof.h2d_ms = now_ms() - wall0; ix->prof.inflate_ms = inflate_ms; ix->prof.inflate_threads = 0;   /* 0 threads: inflate_ms is device time, first k_inflate launch to last k_lz_resolve end */
     if (rc != ITX_OK && cu->inf_made) for (int i = 0; i < ITX_INF_STREAMS; i++) cudaStreamSynchronize(cu->inf_stream[i]);
-    for (int i = 0; i < 2; i++) if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    if (reader_open) { cudaStreamSynchronize(cu->copy_stream); comp_reader_close(&R); }
+    if (copied) cudaEventDestroy(copied);
     if (begin_ev) cudaEventDestroy(begin_ev);
-    free(blk);
+    free(blk); free(foff);
     itx_bam_header_free(h);
     return rc;
 }
@@ -969,7 +1269,7 @@ extern "C" int itx_scan_bgzf_memory(itx_index *ix, const uint8_t *bgzf, uint64_t
     const int nth = inflate_thread_count(ix);
     if (inflate_on_host()) return scan_bgzf_host_inflate(ix, bgzf, flen, o, cnt, err, nth);
     itx_bgzf_src S; S.fd = -1; S.mem = bgzf; S.len = flen;
-    return scan_bgzf_device_inflate(ix, &S, o, cnt, err, nth);
+    return scan_bgzf_device_inflate(ix, &S, o, cnt, err, nth, NULL);
 }
 
 /* the A/B path: block table from a walk over the whole image, zlib on the host threads, uncompressed windows over PCIe */
@@ -1054,8 +1354,21 @@ static int scan_one_file(itx_index *ix, const char *path, const itx_scan_opts *o
     memset(&ix->prof, 0, sizeof ix->prof);
     posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
     itx_bgzf_src S; S.fd = fd; S.mem = NULL; S.len = (uint64_t)st.st_size;
-    rc = scan_bgzf_device_inflate(ix, &S, o, cnt, err, inflate_thread_count(ix));
+    rc = scan_bgzf_device_inflate(ix, &S, o, cnt, err, inflate_thread_count(ix), NULL);
     close(fd);
+    return rc;
+}
+
+/* the single-file twin (samFile2nodupRepbedFileNew, generic.c:343: what `filter` calls): the argument is ONE path, commas and all */
+extern "C" int itx_scan_alignment_file(itx_index *ix, const char *path, const itx_scan_opts *o, uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    int rc = ITX_OK;
+    if ((o->outbed || o->outbed_unique) && (rc = ordered_open_files(ix->cu, o, err))) return rc;
+    ix->cu->bed_owner = (o->outbed || o->outbed_unique) ? 1 : 0;
+    rc = scan_one_file(ix, path, o, cnt, err);
+    ix->prof.n_records = ix->cnt[0] + ix->cnt[1]; ix->prof.n_fragments = ix->cnt[6];
+    ordered_close_files(ix->cu);
     return rc;
 }
 
@@ -1220,7 +1533,30 @@ static int cpg_parse_line_host(itx_index *ix, const char *s, const char *e, cpg_
  * the lines, parses them and accumulates.  The host only sees what the device hands back: the first line with fewer
  * than four fields (an error, as in the reference) and the rare lines whose score needs the full strtod.
  * ITX_CPG_PARSE=host keeps the whole parse on the host (A/B). */
+/* first line start at or after `at` (0 stays 0): the byte after the first line feed at or after at - 1; flen if there is none */
+static int cpg_line_start(int fd, uint64_t flen, uint64_t at, uint64_t *out) {
+    if (at == 0) { *out = 0; return ITX_OK; }
+    char buf[65536];
+    for (uint64_t o = at - 1; o < flen;) {
+        const ssize_t r = pread(fd, buf, sizeof buf, (off_t)o);
+        if (r <= 0) return ITX_EIO;
+        const char *nl = (const char *)memchr(buf, '\n', (size_t)r);
+        if (nl) { *out = o + (uint64_t)(nl - buf) + 1; return ITX_OK; }
+        o += (uint64_t)r;
+    }
+    *out = flen;
+    return ITX_OK;
+}
+static int scan_cpg_part(itx_index *ix, const char *bedgraph, int filter, int rank, int nranks, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]);
 extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]) {
+    return scan_cpg_part(ix, bedgraph, filter, 0, 1, n_lines, n_in_repeat, err);
+}
+/* a rank owns the lines that START in its share of the file's bytes */
+extern "C" int itx_scan_cpg_shard(itx_index *ix, const char *bedgraph, int filter, int rank, int nranks, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]) {
+    if (rank < 0 || nranks < 1 || rank >= nranks) { if (err) snprintf(err, ITX_ERRLEN, "bad rank %d of %d", rank, nranks); return ITX_EARG; }
+    return scan_cpg_part(ix, bedgraph, filter, rank, nranks, n_lines, n_in_repeat, err);
+}
+static int scan_cpg_part(itx_index *ix, const char *bedgraph, int filter, int rank, int nranks, uint32_t *n_lines, uint32_t *n_in_repeat, char err[ITX_ERRLEN]) {
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
     err[0] = 0;
     itx_cuda *cu = ix->cu;
@@ -1231,7 +1567,13 @@ extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uin
     int fd = (stat(bedgraph, &st) == 0 && S_ISDIR(st.st_mode)) ? -1 : open(bedgraph, O_RDONLY);
     if (fd < 0) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
     if (fstat(fd, &st) != 0) { close(fd); snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", bedgraph, strerror(errno)); return ITX_EIO; }
-    const uint64_t flen = (uint64_t)st.st_size;
+    uint64_t flen = (uint64_t)st.st_size, f_begin = 0;
+    if (nranks > 1) {
+        uint64_t a = 0, b = flen;
+        if (cpg_line_start(fd, flen, flen / (uint64_t)nranks * (uint64_t)rank, &a) != ITX_OK ||
+            (rank + 1 < nranks && cpg_line_start(fd, flen, flen / (uint64_t)nranks * (uint64_t)(rank + 1), &b) != ITX_OK)) { close(fd); snprintf(err, ITX_ERRLEN, "read error in %s", bedgraph); return ITX_EIO; }
+        f_begin = a; flen = b < a ? a : b;                     /* from here on `flen` is the end of this rank's part */
+    }
     const bool host_parse = getenv("ITX_CPG_PARSE") && strcmp(getenv("ITX_CPG_PARSE"), "host") == 0;
     const int nth = inflate_thread_count(ix);
     const uint64_t W = 64ull << 20, CAPW = 2 * W + 4096;                   /* a window holds a cut line of the previous one in front */
@@ -1275,7 +1617,7 @@ extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uin
         }
         return ITX_OK;
     };
-    uint64_t fo = 0, carry = 0; int slot = 0;
+    uint64_t fo = f_begin, carry = 0; int slot = 0;
     uint8_t *carrybuf = (uint8_t *)malloc(W + 64);
     const bool timing = getenv("ITX_TIMING") != NULL; double t_read = 0, t_settle = 0; const double t_all0 = now_ms();
     while (rc == ITX_OK && (fo < flen || carry)) {
@@ -1327,6 +1669,7 @@ extern "C" int itx_scan_cpg(itx_index *ix, const char *bedgraph, int filter, uin
     cudaFree(dcnt); cpg_rows_free(&R);
     if (n_lines) *n_lines = (uint32_t)lines;
     if (n_in_repeat) *n_in_repeat = (uint32_t)inrep;
+    if (rc == ITX_OK) { ix->cpg_lines += lines; ix->cpg_in_repeat += inrep; }
     return rc;
 }
 
@@ -1367,9 +1710,11 @@ extern "C" int itx_comm_init(itx_index *ix, const uint8_t id[ITX_NCCL_ID_BYTES],
     cu->nccl_lib = lib; cu->rank = rank; cu->nranks = nranks;
     return ITX_OK;
 }
-/* ONE grouped allreduce(sum) over the packed counter block: the u64 lanes (13 global counters and the
- * subfamily/family/class pairs) and the u32 lanes (coverage difference arrays and per-locus counts,
- * wrapping like the reference's unsigned int). */
+/* ONE grouped allreduce(sum) over the parts of the packed counter block that the scans since the last reset wrote: the u64
+ * lanes (13 global counters, CpG line totals, the subfamily/family/class pairs), the u32 lanes of the mode that ran (stat:
+ * coverage difference arrays; filter: per-locus counts -- wrapping like the reference's unsigned int) and, after a CpG scan,
+ * its u32 counts and f64 score sums (the one floating-point lane: the sum order differs from a single scan's, 1e-9 relative).
+ * Every rank must have run the same kinds of scan, so that the lanes match. */
 extern "C" int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     char lerr[ITX_ERRLEN]; if (!err) err = lerr;
     itx_cuda *cu = ix->cu;
@@ -1378,18 +1723,161 @@ extern "C" int itx_comm_allreduce_counts(itx_index *ix, char err[ITX_ERRLEN]) {
     fn_allreduce ar = (fn_allreduce)dlsym(cu->nccl_lib, "ncclAllReduce");
     fn_void gs = (fn_void)dlsym(cu->nccl_lib, "ncclGroupStart"), ge = (fn_void)dlsym(cu->nccl_lib, "ncclGroupEnd");
     if (!ar || !gs || !ge) { snprintf(err, ITX_ERRLEN, "NCCL symbols missing"); return ITX_ENOTSUP; }
-    const int ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0;
+    const int ncclUint32 = 3, ncclUint64 = 5, ncclFloat64 = 8, ncclSum = 0;
+    const size_t ne = (size_t)ix->n_elem, ng = (size_t)(ix->subs.n + ix->fams.n + ix->clas.n), bl = (size_t)ix->bp_len;
+    /* the CpG line totals ride in two spare u64 lanes */
+    unsigned long long tot[2] = {ix->cpg_lines, ix->cpg_in_repeat};
+    CK(cudaMemcpyAsync(cu->D.cnt + 13, tot, sizeof tot, cudaMemcpyHostToDevice, cu->stream));
     int r = gs();
     if (!r) r = ar(cu->d_u64, cu->d_u64, cu->n_u64, ncclUint64, ncclSum, cu->nccl_comm, cu->stream);
-    if (!r && cu->n_u32) r = ar(cu->d_u32, cu->d_u32, cu->n_u32, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
-    cu->dirty_el = 1;
+    if (!r && cu->used_bp && bl) r = ar(cu->D.bp_diff, cu->D.bp_diff, 2 * bl, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
+    if (!r && cu->used_el && ne) r = ar(cu->D.el_cnt, cu->D.el_cnt, 2 * ne, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
+    if (!r && cu->used_cpg) {
+        const size_t nu = ng + (cu->used_cpg_el ? ne : 0), nf = ng + bl + (cu->used_cpg_el ? ne : 0);
+        if (nu) r = ar(cu->d_cpg_u32, cu->d_cpg_u32, nu, ncclUint32, ncclSum, cu->nccl_comm, cu->stream);
+        if (!r && nf) r = ar(cu->d_cpg_f64, cu->d_cpg_f64, nf, ncclFloat64, ncclSum, cu->nccl_comm, cu->stream);
+    }
     int r2 = ge(); if (!r) r = r2;
     if (r != 0) { snprintf(err, ITX_ERRLEN, "ncclAllReduce failed (%d)", r); return ITX_ENODEV; }
     unsigned long long hc[16];
     CK(cudaMemcpyAsync(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost, cu->stream));
     CK(cudaStreamSynchronize(cu->stream));
     for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k];
+    ix->cpg_lines = hc[13]; ix->cpg_in_repeat = hc[14];
     return ITX_OK;
+}
+extern "C" void itx_get_cpg_totals(const itx_index *ix, uint64_t *n_lines, uint64_t *n_in_repeat) { if (n_lines) *n_lines = ix->cpg_lines; if (n_in_repeat) *n_in_repeat = ix->cpg_in_repeat; }
+extern "C" int itx_comm_rank(const itx_index *ix, int *rank, int *nranks) {
+    if (!ix->cu->nccl_comm) { if (rank) *rank = 0; if (nranks) *nranks = 1; return ITX_EARG; }
+    if (rank) *rank = ix->cu->rank;
+    if (nranks) *nranks = ix->cu->nranks;
+    return ITX_OK;
+}
+
+/* ------------------------------------------------------------------ ONE BAM file across the ranks */
+/* the touched counter blocks, saved before a rank scans its part of a file and put back if that part has to be scanned again
+ * from another first record (the rank before says where the chain really enters) */
+static int counters_snapshot(itx_index *ix, int restore, char *err) {
+    itx_cuda *cu = ix->cu;
+    const size_t b64 = cu->n_u64 * 8, b32 = ((cu->used_el ? cu->n_u32 : 2 * (size_t)ix->bp_len)) * 4, bm = (ITX_MAX_TID_SEEN + 8) * 4;
+    if (!cu->d_snap || cu->snap_cap < b64 + b32 + bm) {
+        if (restore) { snprintf(err, ITX_ERRLEN, "internal: no counter snapshot to restore"); return ITX_EARG; }
+        cudaFree(cu->d_snap); cu->d_snap = NULL;
+        CK(cudaMalloc(&cu->d_snap, b64 + b32 + bm)); cu->snap_cap = b64 + b32 + bm;
+    }
+    uint8_t *q = (uint8_t *)cu->d_snap;
+    if (!restore) {
+        CK(cudaMemcpyAsync(q, cu->d_u64, b64, cudaMemcpyDeviceToDevice, cu->stream));
+        CK(cudaMemcpyAsync(q + b64, cu->d_u32, b32, cudaMemcpyDeviceToDevice, cu->stream));
+        CK(cudaMemcpyAsync(q + b64 + b32, cu->d_misc, bm, cudaMemcpyDeviceToDevice, cu->stream));
+    } else {
+        CK(cudaMemcpyAsync(cu->d_u64, q, b64, cudaMemcpyDeviceToDevice, cu->stream));
+        CK(cudaMemcpyAsync(cu->d_u32, q + b64, b32, cudaMemcpyDeviceToDevice, cu->stream));
+        CK(cudaMemcpyAsync(cu->d_misc, q + b64 + b32, bm, cudaMemcpyDeviceToDevice, cu->stream));
+    }
+    CK(cudaStreamSynchronize(cu->stream));
+    return ITX_OK;
+}
+
+/* Rank `rank` of `nranks` scans its part of ONE BGZF file: the blocks that start in its share of the file's bytes, the records
+ * that start in those blocks.  entry = ITX_SHARD_GUESS: the first record start is guessed out of the bytes like any span's (rank 0
+ * starts behind the header whatever `entry` says); otherwise entry is the offset -- in the rank's own uncompressed bytes -- that
+ * itx_shard_chain_check handed back.  rep tells how the chain entered and left the part. */
+extern "C" int itx_scan_shard_file(itx_index *ix, const char *path, const itx_scan_opts *o, int rank, int nranks, uint64_t entry,
+                                   itx_shard_report *rep, uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    if (rank < 0 || nranks < 1 || rank >= nranks || !rep) { snprintf(err, ITX_ERRLEN, "bad rank %d of %d", rank, nranks); return ITX_EARG; }
+    if (o->isSam) { snprintf(err, ITX_ERRLEN, "SAM text cannot be split across ranks"); return ITX_ENOTSUP; }
+    if (nranks > 1 && (o->rmDup || o->outbed || o->outbed_unique || o->readNames)) { snprintf(err, ITX_ERRLEN, "-R, -B / -V and filter -r follow the reads in file order: they are not available in a sharded scan"); return ITX_ENOTSUP; }
+    itx_cuda *cu = ix->cu;
+    CK(cudaSetDevice(cu->device));
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { snprintf(err, ITX_ERRLEN, "Error\n[bam file %s: %s]", path, strerror(errno)); return ITX_EIO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); snprintf(err, ITX_ERRLEN, "Error\n[bam file %s is empty or unreadable]", path); return ITX_EIO; }
+    memset(&ix->prof, 0, sizeof ix->prof);
+    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    itx_bgzf_src S; S.fd = fd; S.mem = NULL; S.len = (uint64_t)st.st_size;
+    int rc = ITX_OK;
+    const bool retry_possible = nranks > 1 && rank + 1 < nranks;
+    if (retry_possible && (rc = counters_snapshot(ix, 0, err))) { close(fd); return rc; }
+    /* the record that straddles the end of the part needs bytes of the next rank's blocks: 1 MiB of them, more only if a longer record shows up */
+    for (uint64_t margin = 1u << 20;; margin = margin < (16u << 20) ? (16u << 20) : (64ull << 20) + 65536) {
+        shard_io sh; memset(&sh, 0, sizeof sh);
+        sh.rank = rank; sh.nranks = nranks; sh.entry = entry == ITX_SHARD_GUESS ? ITX_OFF_GUESS : entry; sh.margin = margin;
+        rc = scan_bgzf_device_inflate(ix, &S, o, cnt, err, inflate_thread_count(ix), &sh);
+        if (rc != ITX_OK) break;
+        rep->entry_rel = sh.entry_rel; rep->exit_rel = sh.exit_rel; rep->own_bytes = sh.own_bytes;
+        if (!(retry_possible && sh.exit_rel == ITX_OFF_END && sh.more_after && margin < (64ull << 20))) break;
+        if ((rc = counters_snapshot(ix, 1, err))) break;           /* the chain ran out of bytes, not out of records: again with more room */
+    }
+    close(fd);
+    return rc;
+}
+typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+extern "C" int itx_scan_alignments_shard(itx_index *ix, const char *bam_list, const itx_scan_opts *o, uint64_t cnt[13], char err[ITX_ERRLEN]) {
+    char lerr[ITX_ERRLEN]; if (!err) err = lerr;
+    err[0] = 0;
+    itx_cuda *cu = ix->cu;
+    if (!cu->nccl_comm) { snprintf(err, ITX_ERRLEN, "itx_comm_init has not been called"); return ITX_EARG; }
+    CK(cudaSetDevice(cu->device));
+    fn_allgather ag = (fn_allgather)dlsym(cu->nccl_lib, "ncclAllGather");
+    if (!ag) { snprintf(err, ITX_ERRLEN, "NCCL symbols missing"); return ITX_ENOTSUP; }
+    const int nr = cu->nranks, me = cu->rank, ncclUint64 = 5;
+    if (!cu->d_shard) CK(cudaMalloc((void **)&cu->d_shard, 4 * 8 * (size_t)(nr + 1)));
+    unsigned long long *all = (unsigned long long *)malloc(4 * 8 * (size_t)nr);
+    itx_shard_report *reps = (itx_shard_report *)malloc(sizeof(itx_shard_report) * (size_t)nr);
+    char *list = strdup(bam_list), *save = NULL; int rc = ITX_OK, nfile = 0;
+    itx_profile total; memset(&total, 0, sizeof total);
+    for (char *tok = strtok_r(list, ",", &save); tok && rc == ITX_OK; tok = strtok_r(NULL, ",", &save)) {
+        if (++nfile > 100) break;                       /* the reference's row[100] */
+        uint64_t entry = ITX_SHARD_GUESS;
+        if ((rc = counters_snapshot(ix, 0, err))) break;
+        itx_shard_report rep; memset(&rep, 0, sizeof rep);
+        bool need_scan = true;
+        /* rounds in lock step: whoever has to, scans; everybody all-gathers; everybody runs the same check on the same reports */
+        for (int round = 0; rc == ITX_OK; round++) {
+            char e1[ITX_ERRLEN]; e1[0] = 0; int rc1 = ITX_OK;
+            if (need_scan) {
+                if (round > 0) rc1 = counters_snapshot(ix, 1, e1);
+                if (rc1 == ITX_OK) rc1 = itx_scan_shard_file(ix, tok, o, me, nr, entry, &rep, cnt, e1);
+                need_scan = false;
+                if (round == 0) {
+                    total.decode_ms += ix->prof.decode_ms; total.overlap_ms += ix->prof.overlap_ms; total.total_ms += ix->prof.total_ms; total.h2d_ms += ix->prof.h2d_ms;
+                    total.inflate_ms += ix->prof.inflate_ms; total.stream_bytes += ix->prof.stream_bytes; total.h2d_bytes += ix->prof.h2d_bytes; total.d2h_bytes += ix->prof.d2h_bytes;
+                    total.n_launches += ix->prof.n_launches; total.fused = ix->prof.fused; total.n_replayed_windows += ix->prof.n_replayed_windows;
+                } else total.n_bad_chunks++;
+            }
+            unsigned long long mine[4] = {rep.entry_rel, rep.exit_rel, rep.own_bytes, (unsigned long long)(unsigned)(-rc1)};
+            if (cudaMemcpyAsync(cu->d_shard, mine, sizeof mine, cudaMemcpyHostToDevice, cu->stream) != cudaSuccess ||
+                ag(cu->d_shard, cu->d_shard + 4, 4, ncclUint64, cu->nccl_comm, cu->stream) != 0 ||
+                cudaMemcpyAsync(all, cu->d_shard + 4, 4 * 8 * (size_t)nr, cudaMemcpyDeviceToHost, cu->stream) != cudaSuccess ||
+                cudaStreamSynchronize(cu->stream) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "ncclAllGather of the shard reports failed"); rc = ITX_ENODEV; break; }
+            int failed = -1;
+            for (int k = 0; k < nr; k++) { reps[k].entry_rel = all[4 * k]; reps[k].exit_rel = all[4 * k + 1]; reps[k].own_bytes = all[4 * k + 2]; if (all[4 * k + 3] && failed < 0) failed = k; }
+            if (failed >= 0) {
+                rc = -(int)(unsigned)all[4 * failed + 3];
+                if (failed == me) snprintf(err, ITX_ERRLEN, "%s", e1); else snprintf(err, ITX_ERRLEN, "rank %d failed in %s (status %d)", failed, tok, rc);
+                break;
+            }
+            uint64_t forced = 0;
+            const int bad = itx_shard_chain_check(nr, reps, &forced);
+            if (bad < 0) break;                                    /* the parts chain: this file is done */
+            if (round > nr) { snprintf(err, ITX_ERRLEN, "internal: the parts of %s do not chain after %d rounds", tok, round); rc = ITX_EFORMAT; break; }
+            if (bad == me) { entry = forced; need_scan = true; }
+        }
+    }
+    /* this rank's counters as they stand */
+    if (rc == ITX_OK) {
+        unsigned long long hc[16];
+        if (cudaMemcpy(hc, cu->D.cnt, sizeof hc, cudaMemcpyDeviceToHost) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error reading the counters"); rc = ITX_ENODEV; }
+        else { for (int k = 0; k < 13; k++) ix->cnt[k] = hc[k]; if (cnt) memcpy(cnt, ix->cnt, sizeof ix->cnt); }
+    }
+    total.n_records = ix->cnt[0] + ix->cnt[1]; total.n_fragments = ix->cnt[6];
+    ix->prof = total;
+    free(list); free(all); free(reps);
+    return rc;
 }
 extern "C" void itx_get_counters(const itx_index *ix, uint64_t cnt[13]) { memcpy(cnt, ix->cnt, sizeof ix->cnt); }
 extern "C" void itx_comm_destroy(itx_index *ix) {

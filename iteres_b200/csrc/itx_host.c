@@ -380,7 +380,7 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
         snprintf(err, ITX_ERRLEN, "* No repeats found related to [%s], typo? or specify wrong repName/Class/Family filter?", filter_name);
         free(raw); return ITX_EFORMAT;
     }
-    ix->n_rows = row + 1; ix->n_elem = nraw;
+    ix->n_rows = row + 1; ix->n_elem = nraw; ix->n_kept = kept;
     ITX_LAP("rmsk parsed and merged");
 
     /* order by (chrom, start, row) unless the file already is */
@@ -695,12 +695,40 @@ int itx_write_cpg_filter(itx_index *ix, const char *path, double thr) {
     return ITX_OK;
 }
 
+/* ------------------------------------------------------------------ one BAM across ranks: the chain between the parts */
+/* Rank 0's chain starts behind the BAM header, so its report stands.  Every later rank guessed (or was told) where its first
+ * record starts; it is right when that is where the chain of the ranks before it arrives.  A part the chain runs over entirely
+ * (a record longer than the part) must have met no record start; a part without blocks is transparent; once the chain has ended
+ * (a cut record) nothing after it counts, as in the reference, whose loop stops there (generic.c:745).
+ * Returns the first rank whose entry is wrong and, in *forced_entry, the entry it has to scan again from -- or -1. */
+int itx_shard_chain_check(int nranks, const itx_shard_report *rep, uint64_t *forced_entry) {
+    if (nranks < 2) return -1;
+    uint64_t x = rep[0].exit_rel;                    /* where the chain stands, relative to the first own byte of the next rank with blocks */
+    for (int k = 1; k < nranks; k++) {
+        if (rep[k].own_bytes == 0) continue;
+        if (x == ITX_OFF_NONE) { x = rep[k].exit_rel; continue; }             /* nothing is known (no rank before this one had a record): its guess stands */
+        if (x == ITX_OFF_END) {
+            if (rep[k].entry_rel != ITX_OFF_END) { *forced_entry = ITX_OFF_END; return k; }
+            continue;
+        }
+        if (x >= rep[k].own_bytes) {                 /* the chain runs over the whole part */
+            if (rep[k].entry_rel != ITX_OFF_NONE && rep[k].entry_rel != x) { *forced_entry = x; return k; }
+            x -= rep[k].own_bytes;
+            continue;
+        }
+        if (rep[k].entry_rel != x) { *forced_entry = x; return k; }
+        x = rep[k].exit_rel;
+    }
+    return -1;
+}
+
 /* ------------------------------------------------------------------ accessors */
 int32_t itx_n_subfam(const itx_index *ix) { return ix->stat_mode ? ix->subs.n : 0; }
 int32_t itx_n_fam(const itx_index *ix) { return ix->stat_mode ? ix->fams.n : 0; }
 int32_t itx_n_class(const itx_index *ix) { return ix->stat_mode ? ix->clas.n : 0; }
 int64_t itx_n_elem(const itx_index *ix) { return ix->n_elem; }
 int64_t itx_n_rows(const itx_index *ix) { return ix->n_rows; }
+int64_t itx_n_repeats_parsed(const itx_index *ix) { return ix->n_kept; }
 int32_t itx_n_chrom(const itx_index *ix) { return ix->chroms.n; }
 static int32_t ordered(const itx_index *cix, int which, int32_t i) {
     struct itx_index *ix = (struct itx_index *)cix; ensure_orders(ix);

@@ -101,6 +101,7 @@ typedef struct { uint32_t start, end, info, rec_off; } itx_tuple;
 #define ITX_CHROM_MASK 0x007fffffu
 #define ITX_CHROM_NONE 0x007fffffu
 
+#define ITX_OFF_GUESS 0xfffffffffffffffdULL  /* carry of a scan that starts in the middle of a stream: the first record start is guessed like any span's */
 #define ITX_OFF_END  0xfffffffffffffffeULL   /* the record chain ended here (truncated / corrupt record) */
 #define ITX_OFF_NONE 0xffffffffffffffffULL   /* speculation found no plausible record start */
 
@@ -121,12 +122,14 @@ struct itx_index {
     itx_group *sub, *fam, *cla;                                          /* counters (stat_mode only) */
     uint32_t *sub_len; unsigned long long *sub_bp_off; int32_t *sub_fold; uint64_t bp_len;
     long long n_elem, n_rows;
+    long long n_kept;                    /* rows that passed the -n/-c/-f filter, before rows on chromosomes missing from the size file were dropped (repeat_num, generic.c:1593) */
     itx_iv *iv; itx_meta *meta; itx_meta2 *meta2; int32_t *el_chrom;   /* sorted order */
     uint32_t *bucket; long long *chrom_bucket; long long n_bucket;
     itx_chrominfo *cinfo; itx_subinfo *sinfo;
     long long *row2el;                   /* rmsk row -> sorted element index or -1 */
     /* host mirrors of the device results (filled by itx_sync_counts) */
     uint64_t cnt[13];
+    uint64_t cpg_lines, cpg_in_repeat;   /* totals of the CpG scans since the last reset (summed over the ranks by itx_comm_allreduce_counts) */
     uint32_t *bp, *bp_u;                 /* prefix-summed coverage, bp_len entries (entry len of each group unused) */
     double *bp_cpg;
     uint32_t *el_cnt, *el_cnt_u, *el_cpg; double *el_cpg_score;
@@ -163,6 +166,7 @@ int itx_bgzf_scan(const uint8_t *file, uint64_t len, itx_bgzf_block **blocks, ui
 int itx_parallel_copy(const uint8_t *file, uint64_t o0, uint64_t o1, uint8_t *dst, int nth);
 int itx_parallel_pread(int fd, uint64_t o0, uint64_t o1, uint8_t *dst, int nth);
 int itx_bgzf_header_ok(const uint8_t *h18);
+int64_t itx_bgzf_find_block(const uint8_t *buf, uint64_t n, int at_eof);
 int itx_bgzf_inflate_range(const uint8_t *file, const itx_bgzf_block *blocks, uint64_t b0, uint64_t b1,
                            uint8_t *dst, int nth, double *busy_ms);
 

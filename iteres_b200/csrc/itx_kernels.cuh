@@ -35,6 +35,7 @@
 
 struct itx_decode_args {
     const uint8_t *b; unsigned long long len, avail, k0;
+    unsigned long long own;             /* record starts at or past this offset are someone else's (<= len; = len unless the scan is one rank's shard of a stream) */
     uint32_t nchunks, C, S;
     const itx_tidinfo *tid; int32_t n_ref;
     itx_dev_opts o;
@@ -51,7 +52,7 @@ __device__ __forceinline__ void itx_red_u64(unsigned long long *p, unsigned long
 __device__ __forceinline__ void itx_walk_chunk(const itx_decode_args &A, uint32_t i, unsigned long long p) {
     const itx_src_global G{A.b};
     const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-    unsigned long long hi = lo + A.C; if (hi > A.len) hi = A.len;
+    unsigned long long hi = lo + A.C; if (hi > A.own) hi = A.own;
     itx_tuple *out = A.tuples + (size_t)i * A.S;
     uint32_t n = 0;
     if (p < ITX_OFF_END) {
@@ -72,10 +73,10 @@ __global__ void __launch_bounds__(128) k_decode(const itx_decode_args A) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.nchunks) return;
     unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C, hi = lo + A.C;
-    if (hi > A.len) hi = A.len;
-    unsigned long long p;
+    if (hi > A.own) hi = A.own;
+    unsigned long long p = ITX_OFF_GUESS;
     if (i == 0) { p = *A.carry; *A.winbad = 0; }
-    else p = itx_speculate_entry(itx_src_global{A.b}, lo, hi, A.len, A.n_ref);
+    if (p == ITX_OFF_GUESS) p = itx_speculate_entry(itx_src_global{A.b}, lo, hi, A.len, A.n_ref);
     A.entry[i] = p;
     itx_walk_chunk(A, i, p);
 }
@@ -193,13 +194,16 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
         if (i >= A.nchunks || dead) break;
         /* span-relative 32-bit offsets, sentinels 0xfffffffe (chain ended) / 0xffffffff (no guess), as in k_scan */
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        const uint32_t hi = A.len - lo < A.C ? (uint32_t)(A.len - lo) : A.C;
+        const uint32_t hi = A.own - lo < A.C ? (uint32_t)(A.own - lo) : A.C;
         uint32_t p = 0xffffffffu;
         bool guess = i != 0;
         if (!guess) {
             const unsigned long long p0 = *A.carry;
-            if (lane == 0) A.entry[i] = p0;
-            p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
+            if (p0 == ITX_OFF_GUESS) guess = true;             /* the scan starts in the middle of a stream (a rank's shard) */
+            else {
+                if (lane == 0) A.entry[i] = p0;
+                p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
+            }
         }
         itx_tuple *out = A.tuples + (size_t)i * A.S;
         uint32_t n_out = 0, staged = 0xffffffffu, nb = 0, szd = 0;
@@ -286,10 +290,25 @@ __global__ void __launch_bounds__(ITX_DW * 32) k_decode_span(const itx_decode_ar
     }
 }
 
+/* The exit that counts for span i is that of the last span before it that holds a record start (a span a long record runs
+ * over logs NONE for entry and exit); NONE all the way down means that nothing is known yet (a scan that starts in the
+ * middle of a stream and has not met a record start so far). */
+__device__ __forceinline__ unsigned long long itx_prev_exit(const unsigned long long *exit_, uint32_t j) {
+    unsigned long long x = exit_[j];
+    while (x == ITX_OFF_NONE && j > 0) { j--; x = exit_[j]; }
+    return x;
+}
+__device__ __forceinline__ bool itx_span_consistent(const itx_decode_args &A, uint32_t i) {
+    const unsigned long long en = A.entry[i], ex = itx_prev_exit(A.exit_, i - 1);
+    if (en == ex || ex == ITX_OFF_NONE) return true;
+    if (en != ITX_OFF_NONE) return false;
+    const unsigned long long span_end = (A.k0 + i) * (unsigned long long)A.C + A.C;
+    return ex == ITX_OFF_END || (ex < ITX_OFF_GUESS && ex >= (span_end < A.own ? span_end : A.own));
+}
 __global__ void k_verify(const itx_decode_args A) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 || i >= A.nchunks) return;
-    if (A.entry[i] != A.exit_[i - 1]) atomicAdd(A.winbad, 1u);
+    if (!itx_span_consistent(A, i)) atomicAdd(A.winbad, 1u);
 }
 
 /* one warp; a no-op when every guess was right */
@@ -299,12 +318,12 @@ __global__ void k_fixup(const itx_decode_args A) {
         uint32_t i = 1;
         while (i < n) {
             uint32_t idx = i + lane;
-            bool bad = idx < n && A.entry[idx] != A.exit_[idx - 1];
+            bool bad = idx < n && !itx_span_consistent(A, idx);
             uint32_t m = __ballot_sync(0xffffffffu, bad);
             if (!m) { i += 32; continue; }
             uint32_t j = i + (uint32_t)__ffs((int)m) - 1;
             if (lane == 0) {
-                unsigned long long e = A.exit_[j - 1];
+                unsigned long long e = itx_prev_exit(A.exit_, j - 1);
                 A.entry[j] = e;
                 itx_walk_chunk(A, j, e);
                 atomicAdd(&A.status[1], 1u);
@@ -315,7 +334,11 @@ __global__ void k_fixup(const itx_decode_args A) {
         }
     }
     __syncwarp();
-    if (lane == 0) { *A.carry = A.exit_[n - 1]; A.work[0] = 0; A.work[1] = 0; }
+    if (lane == 0) {
+        unsigned long long x = itx_prev_exit(A.exit_, n - 1);
+        if (x == ITX_OFF_NONE && *A.carry == ITX_OFF_GUESS) x = ITX_OFF_GUESS;      /* still no record start met */
+        *A.carry = x; A.work[0] = 0; A.work[1] = 0;
+    }
 }
 
 /* ------------------------------------------------------------------ -R: duplicate removal */
@@ -535,10 +558,11 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
  * straight into overlap / selection / accumulation, so no tuple ever leaves the SM: the stream is read once and
  * nothing but counters is written.  A span's first record start is still a guess, and a wrong guess would by now
  * have been counted; so the spans' entries and exits are logged, the LAST CTA to finish checks the chain
- * (entry[i] == exit[i-1]) and notes the first window that fails, and the host -- at the end of the scan, when it
- * reads the counters anyway -- replays every window from the first bad one with sign = -1 (the same guesses, the
- * same additions, negated: integer sums, so the undo is exact) and runs the tuple path (k_decode_span, k_verify,
- * k_fixup, k_overlap) over them instead.  No guess has failed on any stream tested; the path exists for exactness. */
+ * (entry[i] == the exit of the last span before it that held a record start) and notes the first window that fails,
+ * and the host -- at the end of the scan, when it reads the counters anyway -- replays every window from the first bad
+ * one with sign = -1 (the same guesses, the same additions, negated: integer sums, so the undo is exact) and runs the
+ * tuple path (k_decode_span, k_verify, k_fixup, k_overlap) over them instead.  No guess has failed on any generated or
+ * converted stream; the path exists for exactness. */
 struct itx_scan_args {
     itx_decode_args A;                   /* stream, spans, reference table, options, entry / exit logs, carry, status, work[2] */
     itx_dev_index D;
@@ -546,8 +570,9 @@ struct itx_scan_args {
     int32_t sign;                        /* +1: count; -1: take back what the same call counted */
     uint32_t window;                     /* index of this launch in the scan */
     unsigned long long *carry_log;       /* [window] the carry the window started from (the undo pass starts from it too) */
-    uint32_t *first_bad;                 /* smallest window index whose chain check failed */
-    uint32_t *ticket;                    /* CTAs done */
+    uint32_t *first_bad;                 /* smallest window index whose chain check failed; [1] CTAs done; [2] status bits of this launch (folded into
+                                          * status[0] by the last CTA only when the launch will not be replayed: what a wrongly guessed span reports is garbage);
+                                          * [4..5] (u64) the first record start a scan that began mid-stream settled on */
     uint32_t flags;                      /* ITX_SCAN_* (A/B switches; every combination gives the same counts) */
 };
 #define ITX_SCAN_PREFETCH 1u             /* the next stage's bytes are asked into L2 while this stage is worked on */
@@ -555,7 +580,12 @@ struct itx_scan_args {
 #define ITX_SCAN_WINDOW   4u             /* the 32 table entries under the warp's highest bucket end are staged in shared memory, metadata included */
 #define ITX_SCAN_WINAHEAD 8u             /* the window the NEXT round will most likely need is fetched with cp.async while this round's tail and the next stage's
                                           * copy, chain walk and decode go on (coordinate-sorted reads move up the table a few entries per round) */
-#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD)
+#define ITX_SCAN_EARLY    16u            /* the next stage's bulk copy is issued as soon as the last round of this stage has taken what it needs out of the
+                                          * staged bytes (core, CIGAR, aux tags): it flies while the warp does the table walk, selection and accumulation */
+#define ITX_SCAN_EVICT    32u            /* stream bytes carry an L2 evict-first hint: they are used once, the interval table and the counters are not */
+#define ITX_SCAN_XACOOP   64u            /* XA:Z alternates are tested one LANE per alternate (all alternates of a round side by side) instead of one lane per read */
+#define ITX_SCAN_EVICT_PF 128u           /* the evict-first hint on the L2 prefetches too */
+#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
 #define ITX_WIN 32u                      /* table entries per warp window */
 #ifndef ITX_SCAN_NW
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
@@ -567,6 +597,18 @@ struct itx_scan_args {
 #define ITX_SCAN_SMEM_BASE(NW) ((NW) * ITX_SCAN_WARP_BYTES)
 #define ITX_SCAN_CTAS(NW) ((NW) <= 8 ? 3 : 2)          /* 8 warps x 3 CTAs (80 registers) or 14 warps x 2 CTAs (72 registers) per SM */
 
+__device__ __forceinline__ unsigned long long itx_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void itx_bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void itx_prefetch_l2_hint(const void *src, uint32_t bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+
 /* table loads of a walk: the warp's window when the index falls into it, global memory otherwise (same values either way) */
 struct itx_iv_window {
     const itx_dev_index &D; const int4 *win; uint32_t base, n;
@@ -576,6 +618,16 @@ struct itx_iv_window {
         return itx_ld_iv(D, i);
     }
 };
+
+/* The chain check of a launch group, by its last CTA (k_scan) -- also what the sharded scan's host side applies between ranks.
+ * A span that holds no record start at all (a record longer than a span runs over it) logs NONE for both its entry and its exit:
+ * the exit that counts for span i is that of the last span before it which has one.  Span i is consistent when its guessed entry
+ * IS that exit -- or, if it found no plausible start, when the chain does run over it entirely (or had already ended). */
+__device__ __forceinline__ unsigned long long itx_effective_exit(const unsigned long long *exit_, uint32_t j) {
+    unsigned long long x = __ldcg(exit_ + j);
+    while (x == ITX_OFF_NONE && j > 0) { j--; x = __ldcg(exit_ + j); }
+    return x;
+}
 
 template <bool SMEM_HIST, int NW>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
@@ -603,10 +655,13 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     const unsigned long long one64 = neg ? ~0ull : 1ull;
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
-    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD);
+    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = P.flags & ITX_SCAN_EARLY, f_xacoop = P.flags & ITX_SCAN_XACOOP;
+    const bool f_evict = P.flags & ITX_SCAN_EVICT, f_evict_pf = P.flags & ITX_SCAN_EVICT_PF;
+    unsigned long long pol = 0;
+    if (f_evict || f_evict_pf) pol = itx_policy_evict_first();
     const uint32_t n_elem32 = D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem;
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
-    itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for after the selection, for the reads that are counted */
+    itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for right after the decode, by this kernel itself */
     /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no
      * popcounts); the fields are summed over the warp and added to the CTA's totals before any of them can reach 256 */
     uint32_t pa = 0, pb = 0, pc = 0, n_rounds = 0;
@@ -629,6 +684,21 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         } \
         pa = pb = pc = 0; n_rounds = 0; \
     } while (0)
+    /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream), and what
+     * the stage after it adds on its way into L2 meanwhile; the caller has made sure that every lane is done with the old bytes */
+#define ITX_SCAN_ISSUE(c_lo_, rest_, nb_out_) do { \
+        nb_out_ = (rest_) > STG ? STG : (uint32_t)(rest_); \
+        __syncwarp(); \
+        if (lane == 0) { \
+            const uint32_t bytes_ = (nb_out_ + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */ \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
+            itx_mbar_expect_tx(bar_s, bytes_); \
+            if (f_evict) itx_bulk_g2s_hint(buf_s, A.b + lo + (c_lo_), bytes_, bar_s, pol); else itx_bulk_g2s(buf_s, A.b + lo + (c_lo_), bytes_, bar_s); \
+            if (f_prefetch && (c_lo_) + ITX_STAGE < hi && (rest_) >= STG + ITX_STAGE) { \
+                if (f_evict_pf) itx_prefetch_l2_hint(A.b + lo + (c_lo_) + STG, ITX_STAGE, pol); else itx_prefetch_l2(A.b + lo + (c_lo_) + STG, ITX_STAGE); \
+            } \
+        } \
+    } while (0)
     uint32_t parity = 0;
     bool dead = false;
     for (;;) {
@@ -639,20 +709,25 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         /* Inside a span everything is kept relative to its first byte, in 32 bits (a span is at most 1 MiB and a record
          * shorter than 2^31 bytes); the two chain sentinels keep their low words (0xfffffffe ended, 0xffffffff none). */
         const unsigned long long lo = (A.k0 + i) * (unsigned long long)A.C;
-        const uint32_t hi = A.len - lo < A.C ? (uint32_t)(A.len - lo) : A.C;
-        /* the span's first record start: known for the window's first span; otherwise guessed out of the span's first
-         * stage, which is needed in shared memory anyway */
+        /* record starts at or past A.own belong to whoever scans the stream from there on (the next rank of a sharded scan) */
+        const uint32_t hi = A.own - lo < A.C ? (uint32_t)(A.own - lo) : A.C;
+        /* the span's first record start: known for the window's first span (unless the scan starts in the middle of a stream:
+         * ITX_OFF_GUESS); otherwise guessed out of the span's first stage, which is needed in shared memory anyway */
         uint32_t p = 0xffffffffu;
         bool guess = i != 0;
         if (!guess) {
             unsigned long long p0;
             if (neg) p0 = P.carry_log[P.window];
             else { p0 = *A.carry; if (lane == 0) P.carry_log[P.window] = p0; }
-            if (lane == 0) A.entry[i] = p0;
-            p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
+            if (p0 == ITX_OFF_GUESS) guess = true;
+            else {
+                if (lane == 0) A.entry[i] = p0;
+                p = p0 >= ITX_OFF_END ? (uint32_t)p0 : (p0 - lo < 0xfffffff0ull ? (uint32_t)(p0 - lo) : 0xfffffffeu);
+            }
         }
         uint32_t staged = 0xffffffffu;                         /* span offset of the stage now in shared memory */
-        uint32_t nb = 0;
+        uint32_t inflight = 0xffffffffu;                       /* span offset of the stage whose copy was issued early (none) */
+        uint32_t nb = 0, nb_next = 0;
         uint32_t szd = 0;                                      /* the span's dominant record size (0: none yet) */
         for (;;) {
             if (guess ? hi == 0u : !(p < hi)) { if (guess && lane == 0) A.entry[i] = ITX_OFF_NONE; break; }
@@ -660,20 +735,11 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             const uint32_t c_hi = c_lo + ITX_STAGE < hi ? c_lo + ITX_STAGE : hi;
             const unsigned long long rest = A.len - lo - c_lo;                 /* bytes of the stream from this stage on */
             if (staged != c_lo) {
-                /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream) */
-                nb = rest > STG ? STG : (uint32_t)rest;
-                const uint32_t bytes = (nb + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */
-                __syncwarp();                                  /* every lane is done reading the previous stage */
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    itx_mbar_expect_tx(bar_s, bytes);
-                    itx_bulk_g2s(buf_s, A.b + lo + c_lo, bytes, bar_s);
-                    /* what the span's next stage adds to this one, on its way into L2 meanwhile */
-                    if (f_prefetch && c_lo + ITX_STAGE < hi && rest >= STG + ITX_STAGE) itx_prefetch_l2(A.b + lo + c_lo + STG, ITX_STAGE);
-                }
+                if (inflight == c_lo) nb = nb_next;            /* on its way since the last round of the previous stage */
+                else ITX_SCAN_ISSUE(c_lo, rest, nb);         /* (the macro's __syncwarp: every lane is done reading the previous stage) */
                 if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
                 parity ^= 1u;
-                staged = c_lo;
+                staged = c_lo; inflight = 0xffffffffu;
             }
             if (guess) {
                 /* itx_plausible2's test, 32 offsets per step: the core of every offset comes out of the stage with plain
@@ -732,7 +798,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     szd = (f_dom && run >= 2u) ? szp : 0u;
                 }
                 if (q != 0xffffffffu) q_end = q;
-                if (lane == 0 && A.avail < lo + c_lo + q_end) atomicOr(&A.status[0], 2u);                  /* a record longer than the staged window */
+                if (lane == 0 && A.avail < lo + c_lo + q_end) atomicOr(P.first_bad + 2, 2u);              /* a record longer than the staged window */
             }
             __syncwarp();
             const unsigned long long c_lo64 = lo + c_lo;
@@ -740,13 +806,32 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             uint32_t tmax_last = 0;                            /* highest table entry any round of this stage started from */
             for (uint32_t j0 = 0; j0 < n; j0 += 32) {
                 const uint32_t j = j0 + lane; const bool valid = j < n;
+                /* ---- everything this round needs out of the staged bytes: core, CIGAR, the XA / NM tags */
                 itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
-                unsigned long long rp = 0;
-                uint32_t x[9];
+                uint32_t xa_rel = 0, aend_rel = 0; int32_t xa_nm = 0;             /* stage-relative offsets of the XA type byte (0: no XA) and of the record's end */
                 if (valid) {
-                    rp = c_lo64 + pos[j];
+                    const unsigned long long rp = c_lo64 + pos[j];
+                    uint32_t x[9];
                     S.core(rp, x);
                     T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, o_dec);
+                    if (A.o.diffSubfam && (T.info & ITX_F_FRAG) && (T.info & ITX_CHROM_MASK) != ITX_CHROM_NONE) {
+                        uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
+                        /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
+                        if (aend - a0 >= 5) {
+                            const uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
+                            if (xa && xa < aend) {
+                                xa_rel = (uint32_t)(xa - c_lo64); aend_rel = (uint32_t)(aend - c_lo64);
+                                xa_nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
+                            }
+                        }
+                    }
+                }
+                /* the last round of a stage whose reads carry no XA lists is done with the staged bytes: the next stage's copy starts now */
+                if (f_early && j0 + 32u >= n && q != 0xffffffffu && c_lo + q < hi && !__any_sync(0xffffffffu, xa_rel != 0u)) {
+                    const uint32_t c_nx = (c_lo + q) & ~(ITX_STAGE - 1u);
+                    const unsigned long long rest_nx = A.len - lo - c_nx;
+                    ITX_SCAN_ISSUE(c_nx, rest_nx, nb_next);
+                    inflight = c_nx;
                 }
                 const uint32_t info = T.info;
                 const bool frag = info & ITX_F_FRAG, uniq = info & ITX_F_UNIQ;
@@ -755,7 +840,8 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     pa += ((valid ? 1u : 0u) & ns2) | (s2 << 8) | ((mp & ns2) << 16) | ((mp & s2) << 24);
                     pb += (us & ns2) | ((us & s2) << 8) | (fr << 16) | ((fr & uq) << 24);
                 }
-                if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
+                /* a count, not a mark: the undo pass takes back what a wrongly guessed span left here too */
+                if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) itx_red_u32(&D.tid_unknown_seen[T.start], one);
                 long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
                 const uint32_t chrom = info & ITX_CHROM_MASK;
                 itx_query Q; Q.fs = Q.fe = 0; Q.lo = Q.top = 0;
@@ -794,18 +880,64 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
                 }
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-                uint64_t a0 = 0, aend = 0; bool has_xa = false;
-                if (sel >= 0 && A.o.diffSubfam) {
-                    itx_aux_range(rp, x, &a0, &aend);
-                    /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
-                    has_xa = aend - a0 >= 5 && itx_aux_find(S, a0, aend, 'X', 'A');
-                }
-                if (has_xa) {
-                    uint32_t bad = 0;
-                    const int32_t fold = D.sinfo[D.meta[sel].sub].fold, qlen = (int32_t)(T.end - T.start);
-                    if (aend + 4 <= c_lo64 + nb ? itx_mapped_to_diff_subfam_aux(*P.Dg, itx_src_flat{buf, c_lo64}, a0, aend, fold, qlen, &bad)
-                                                : itx_mapped_to_diff_subfam_aux(*P.Dg, S, a0, aend, fold, qlen, &bad)) diffsub = true;
-                    if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+                /* ---- XA:Z alternates (mapped2diffSubfam), for the reads that are about to be counted */
+                const bool xa_go = sel >= 0 && xa_rel != 0u;
+                if (__any_sync(0xffffffffu, xa_go)) {
+                    int32_t fold = 0;
+                    if (xa_go) fold = D.sinfo[D.meta[sel].sub].fold;
+                    const int32_t qlen = (int32_t)(T.end - T.start);
+                    /* the lane-per-alternate walk reads the staged bytes without bounds tests: only for records that lie inside them */
+                    const bool coop = f_xacoop && xa_go && aend_rel + 4u <= nb;
+                    if (__any_sync(0xffffffffu, coop)) {
+                        const itx_src_flat F{buf, c_lo64};
+                        /* every owner counts the pieces of its own list; the pieces of the whole round are numbered across the warp */
+                        uint32_t np = 0; uint32_t zs = 0, ze = 0;
+                        if (coop) {
+                            const uint8_t ty = buf[xa_rel];
+                            if (ty == 'Z' || ty == 'H') {
+                                uint64_t ze64; zs = xa_rel + 1u;
+                                np = itx_xa_count(F, c_lo64 + zs, c_lo64 + aend_rel, &ze64); ze = (uint32_t)(ze64 - c_lo64);
+                            }
+                        }
+                        uint32_t incl = np;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+                        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
+                        bool found = false; uint32_t n_bad = 0;
+                        for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
+                            const uint32_t g = b0 + lane;                  /* this lane's piece of the round */
+                            /* its owner: the first lane whose running count exceeds g (the counts never decrease along the warp) */
+                            uint32_t ow = 0;
+#pragma unroll
+                            for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= g) ow += st; }
+                            ow &= 31u;
+                            const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow), o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
+                            const int32_t o_nm = __shfl_sync(0xffffffffu, xa_nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
+                            bool hit = false, mal = false;
+                            if (g < total) {
+                                uint64_t ps, pe;
+                                itx_xa_kth(F, c_lo64 + o_zs, c_lo64 + o_ze, g - o_base, &ps, &pe);
+                                if (pe > ps) hit = itx_xa_piece(D, F, ps, pe, o_nm, o_qlen, o_fold, &mal);
+                            }
+                            const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
+                            /* back to the owners: the first alternate that answers yes ends the walk, malformed ones before it are counted */
+                            if (np && !found && base < b0 + 32u && incl > b0) {
+                                const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
+                                const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
+                                const uint32_t h = m_hit & range;
+                                if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
+                                else n_bad += (uint32_t)__popc(m_mal & range);
+                            }
+                        }
+                        if (found) diffsub = true;
+                        if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
+                    }
+                    if (xa_go && !coop) {
+                        uint32_t bad = 0;
+                        if (aend_rel + 4u <= nb ? itx_xa_walk(*P.Dg, itx_src_flat{buf, c_lo64}, c_lo64 + xa_rel, c_lo64 + aend_rel, xa_nm, fold, qlen, &bad)
+                                                : itx_xa_walk(*P.Dg, S, c_lo64 + xa_rel, c_lo64 + aend_rel, xa_nm, fold, qlen, &bad)) diffsub = true;
+                        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+                    }
                 }
                 const bool counted = sel >= 0 && !diffsub;
                 pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
@@ -865,19 +997,39 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     /* the last CTA out checks the chain of the whole window and hands the carry on */
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) sh_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) sh_last = atomicAdd(P.first_bad + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (sh_last) {
         __threadfence();
         uint32_t bad = 0;
-        for (uint32_t i = 1 + threadIdx.x; i < A.nchunks; i += blockDim.x) bad |= __ldcg(A.entry + i) != __ldcg(A.exit_ + i - 1) ? 1u : 0u;
+        for (uint32_t i = 1 + threadIdx.x; i < A.nchunks; i += blockDim.x) {
+            const unsigned long long en = __ldcg(A.entry + i), ex = itx_effective_exit(A.exit_, i - 1);
+            bool ok = en == ex || ex == ITX_OFF_NONE;          /* NONE all the way down: a scan that starts mid-stream has met no record start yet */
+            if (!ok && en == ITX_OFF_NONE) {                   /* the span found no record start: right if the chain runs over it, or has ended */
+                const unsigned long long span_end = (A.k0 + i) * (unsigned long long)A.C + A.C;
+                ok = ex == ITX_OFF_END || (ex < ITX_OFF_GUESS && ex >= (span_end < A.own ? span_end : A.own));
+            }
+            bad |= ok ? 0u : 1u;
+        }
         bad = __syncthreads_or((int)bad) ? 1u : 0u;
         if (threadIdx.x == 0) {
             if (!neg) {
                 if (bad) atomicMin(P.first_bad, P.window);
-                *A.carry = __ldcg(A.exit_ + A.nchunks - 1);
+                unsigned long long x = itx_effective_exit(A.exit_, A.nchunks - 1);
+                if (x == ITX_OFF_NONE && __ldcg(P.carry_log + P.window) == ITX_OFF_GUESS) x = ITX_OFF_GUESS;
+                *A.carry = x;
+                /* what this launch reported about the stream counts only if the launch stands (windows are launched in order, so
+                 * first_bad is final for every window up to this one) */
+                const uint32_t st = __ldcg(P.first_bad + 2);
+                if (st && __ldcg(P.first_bad) == 0xffffffffu) atomicOr(&A.status[0], st);
             }
-            A.work[2] = 0; *P.ticket = 0;
+            if (!neg && P.window == 0 && __ldcg(P.carry_log) == ITX_OFF_GUESS) {
+                /* a scan that started mid-stream: the record start it settled on (the caller checks it against the scan before) */
+                unsigned long long fe = ITX_OFF_NONE;
+                for (uint32_t i = 0; i < A.nchunks && fe == ITX_OFF_NONE; i++) fe = __ldcg(A.entry + i);
+                *reinterpret_cast<unsigned long long *>(P.first_bad + 4) = fe;
+            }
+            A.work[2] = 0; P.first_bad[1] = 0; P.first_bad[2] = 0;
         }
     }
 }
@@ -1060,43 +1212,48 @@ __global__ void __launch_bounds__(256) k_bedgraph(const itx_bedgraph_args A) {
 }
 
 /* ------------------------------------------------------------------ BGZF inflate on the device */
-/* One thread per BGZF block, one warp per CTA, the warp's 32 blocks decoded in lock step.  A thread's look-up
- * tables (ITX_LUT_CELLS 16-bit cells) live in shared memory as 32-bit words interleaved across the lanes -- word
- * w of lane l at index w * 32 + l -- so every lane owns a bank whatever cell it reads; 20 KiB per warp, ten warps
- * per SM.  The symbol arrays of the long codes live in global memory, interleaved the same way (cell j of lane l
- * at tabs[warp][j * 32 + l]).  A warp takes the groups of 32 blocks blockIdx.x, blockIdx.x + gridDim.x, ... */
+/* One thread per BGZF block, one warp per CTA, 2^LG of the warp's lanes decoding 2^LG blocks in lock step (the others idle).
+ * A thread's look-up tables (ITX_LUT_CELLS 16-bit cells) live in shared memory as 32-bit words interleaved across the
+ * active lanes -- word w of lane l at index w * 2^LG + l -- so every lane owns a bank whatever cell it reads; 20 KiB per
+ * warp of 32 blocks.  The symbol arrays of the long codes live in global memory, interleaved by 32 (cell j of lane l at
+ * tabs[warp][j * 32 + l]).  A warp takes the groups of 2^LG blocks blockIdx.x, blockIdx.x + gridDim.x, ...
+ * Fewer blocks per warp = fewer ways for a round to diverge = a shorter round: 32 blocks per warp is the densest packing,
+ * 8 the lowest latency per block (what the last groups of a file want: nothing hides their latency). */
+template <uint32_t LG>
 struct itx_tab_dev {
     uint16_t *g, *s;
     __device__ __forceinline__ uint16_t operator()(uint32_t j) const { return g[j * 32u]; }
     __device__ __forceinline__ void set(uint32_t j, uint16_t v) const { g[j * 32u] = v; }
-    __device__ __forceinline__ uint16_t lut(uint32_t j) const { return s[((j >> 1) << 6) | (j & 1u)]; }
-    __device__ __forceinline__ void lut_set(uint32_t j, uint16_t v) const { s[((j >> 1) << 6) | (j & 1u)] = v; }
+    __device__ __forceinline__ uint16_t lut(uint32_t j) const { return s[((j >> 1) << (LG + 1u)) | (j & 1u)]; }
+    __device__ __forceinline__ void lut_set(uint32_t j, uint16_t v) const { s[((j >> 1) << (LG + 1u)) | (j & 1u)] = v; }
 };
 struct itx_inflate_args {
-    const uint8_t *file;                 /* the compressed file image on the device */
+    const uint8_t *file;                 /* the compressed bytes on the device (a ring: coff is an offset into it, not into the file) */
     const itx_bgzf_block *blk;           /* coff, csize, isize, uoff per block */
     unsigned long long b0, nblk;         /* blocks [b0, b0 + nblk) */
     uint8_t *out;                        /* uncompressed stream: block b goes to out + blk[b].uoff */
     uint32_t *status;                    /* [5] number of blocks that failed, [6] index of one of them */
-    uint16_t *tabs;                      /* ITX_T_CELLS cells per thread of the grid */
+    uint16_t *tabs;                      /* 32 * ITX_T_CELLS cells per warp of the grid */
     /* deferred matches: block g0 of the launch owns m_pl[g0 * m_cap ..] / m_d[g0 * m_cap ..]; m_n[g0] = entries or ITX_M_NONE */
     uint32_t *m_pl; uint16_t *m_d; uint32_t *m_n; uint32_t m_cap;
 };
 #define ITX_INF_THREADS 32
-#define ITX_INF_SMEM (ITX_LUT_CELLS * 2u * ITX_INF_THREADS)
+#define ITX_INF_SMEM(LG) (ITX_LUT_CELLS * 2u * (1u << (LG)))
 /* First pass over every block of the launch: Huffman decoding, literals stored, matches listed (m_cap != 0) or
  * copied in line (m_cap == 0).  The host sizes the lists for the worst case (ITX_M_WORST entries: a match is at
  * least three bytes long), so a list cannot overflow. */
 #define ITX_M_WORST 21848u
-__global__ void __launch_bounds__(ITX_INF_THREADS, 10) k_inflate(const itx_inflate_args A) {
+template <uint32_t LG>
+__global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(const itx_inflate_args A) {
     extern __shared__ __align__(16) uint8_t itx_inf_smem[];
+    constexpr uint32_t NL = 1u << LG;
     const uint32_t lane = threadIdx.x;
-    itx_inflater<itx_tab_dev> I;
+    itx_inflater<itx_tab_dev<LG> > I;
     I.tab.g = A.tabs + (size_t)blockIdx.x * (32u * ITX_T_CELLS) + lane;
-    I.tab.s = reinterpret_cast<uint16_t *>(itx_inf_smem) + lane * 2u;
-    for (unsigned long long g0 = (unsigned long long)blockIdx.x * 32u; g0 < A.nblk; g0 += (unsigned long long)gridDim.x * 32u) {
+    I.tab.s = reinterpret_cast<uint16_t *>(itx_inf_smem) + (lane & (NL - 1u)) * 2u;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * NL; g0 < A.nblk; g0 += (unsigned long long)gridDim.x * NL) {
         const unsigned long long g = g0 + lane, b = A.b0 + g;
-        const bool mine = g < A.nblk;
+        const bool mine = lane < NL && g < A.nblk;
         I.state = ITX_ST_DONE; I.err = ITX_INF_OK; I.m_cap = 0; I.n_match = 0;
         if (mine) {
             const itx_bgzf_block B = A.blk[b];
@@ -1104,7 +1261,7 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, 10) k_inflate(const itx_infla
             if (A.m_cap) { I.m_cap = A.m_cap; I.m_pl = A.m_pl + g * A.m_cap; I.m_d = A.m_d + g * A.m_cap; }
             I.begin(A.file + B.coff + 18, B.csize - 18 - 8, B.isize);          /* header 18, footer CRC32 + ISIZE */
         }
-        /* the warp's 32 blocks step together, one round (a few symbols, or a header with its table build) per lane per
+        /* the warp's blocks step together, one round (a few symbols, or a header with its table build) per lane per
          * iteration.  A table build is thousands of instructions: a lane that reaches a header waits there until most
          * of the others have reached theirs, so that the builds run side by side instead of one after the other
          * (blocks written by the same compressor change tables after about the same number of symbols). */
@@ -1112,7 +1269,7 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, 10) k_inflate(const itx_infla
             const bool run = I.running(), hdr = run && I.state == ITX_ST_HEADER;
             const uint32_t m_run = __ballot_sync(0xffffffffu, run), m_hdr = __ballot_sync(0xffffffffu, hdr);
             if (!m_run) break;
-            const bool hdr_go = m_hdr == m_run || __popc(m_hdr) >= 24;
+            const bool hdr_go = m_hdr == m_run || (uint32_t)__popc(m_hdr) >= (3u * NL) / 4u;
             if (run && (!hdr || hdr_go)) I.advance();
         }
         if (mine) {

@@ -288,6 +288,10 @@ ITX_HD itx_tuple itx_decode_record(const Src &S, uint64_t p, const uint32_t x[9]
             /* bam_calend is only observable when the end survives the extension step */
             if (o.extension == 0 || minus) {
                 uint64_t cp = p + 36 + lq;
+                /* only the CIGAR words that lie inside the record: an n_cigar that overstates what the record holds (a corrupt
+                 * file, or the garbage a wrongly guessed span walks) must not send the loop past the record's own end */
+                const uint64_t rec_end = p + 4 + (uint64_t)x[0];
+                if (cp + 4ull * nc > rec_end) nc = rec_end > cp ? (uint32_t)((rec_end - cp) >> 2) : 0u;
                 for (uint32_t k = 0; k < nc; k++) {
                     uint32_t cg = S.u32(cp + 4ull * k), op = cg & 0xf;
                     if (op == 0 || op == 2 || op == 3) tmpend += cg >> 4;
@@ -324,7 +328,7 @@ ITX_HD uint64_t itx_order_key(int32_t s, int32_t e, uint32_t row) {
     const uint32_t x = ((uint32_t)s ^ (uint32_t)(e - 1)) >> 17;
     uint32_t l = (32u - itx_clz32(x) + 2u) / 3u;
     if (l > 5u) l = 5u;
-    const uint32_t a = (uint32_t)s >> (17u + 3u * l);
+    const uint32_t a = l >= 5u ? 0u : (uint32_t)s >> (17u + 3u * l);      /* a shift by 32 is undefined; level 5 has one bin */
     return ((uint64_t)(5u - l) << 48) | ((uint64_t)(0xffffu - a) << 32) | (uint64_t)row;
 }
 ITX_HD itx_iv itx_ld_iv(const itx_dev_index &D, uint32_t i) {
@@ -568,17 +572,62 @@ ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t 
         i = (i + 1) & m;
     }
 }
-/* record at p (core x) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start.
- * *malformed counts alternates without 4 comma separated fields (the reference asserts there). */
+/* ---- the pieces of mapped2diffSubfam (generic.c:303-341), shared by the one-lane walk and k_scan's lane-per-alternate walk ----
+ * The value of XA:Z is chopped at ';' into at most 100 pieces (chopByChar(..., 100)); piece k is what lies between the k-th and the
+ * (k+1)-th ';' (the string's start / end standing in for the missing ones), an empty piece is skipped, and every other piece is
+ * chopped at ',' into chr, pos, cigar, nm (the reference asserts on anything but four fields: counted in *malformed here). */
+/* one piece [ps, pe), ps < pe: does this alternate (nm2 <= nm) touch an element of another folded subfamily? */
+template <class Src>
+ITX_HD bool itx_xa_piece(const itx_dev_index &D, const Src &S, uint64_t ps, uint64_t pe, int32_t nm, int32_t qlen, int32_t sel_fold, bool *malformed) {
+    /* up to 4 comma separated fields (chr, pos, cigar, nm); the 4th stops at the next comma */
+    uint64_t f0s = 0, f0e = 0, f1s = 0, f1e = 0, f3s = 0, f3e = 0, q = ps; int nf = 0; bool more = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (more) {
+            const uint64_t b0 = q;
+            while (q < pe && S.u8(q) != ',') q++;
+            if (k == 0) { f0s = b0; f0e = q; } else if (k == 1) { f1s = b0; f1e = q; } else if (k == 3) { f3s = b0; f3e = q; }
+            nf++;
+            if (q >= pe) more = false; else q++;
+        }
+    }
+    *malformed = nf != 4;
+    if (nf != 4) return false;
+    const int32_t nm2 = itx_strtol_int(S, f3s, f3e);
+    if (nm2 > nm) return false;
+    int32_t st = itx_strtol_int(S, f1s, f1e);
+    if (st < 0) st = (int32_t)(0u - (uint32_t)st);
+    const int32_t en = (int32_t)((uint32_t)st + (uint32_t)qlen);
+    const int32_t c = itx_chrom_by_name(D, S, f0s, f0e);
+    return c >= 0 && itx_any_other_subfam(D, c, st, en, sel_fold);
+}
+/* the value string that starts at zs (the byte after the type byte): *ze = its terminator (or aend), returns the number of
+ * pieces the reference visits (0 for the empty string: chopByChar on "" gives none) */
+template <class Src>
+ITX_HD uint32_t itx_xa_count(const Src &S, uint64_t zs, uint64_t aend, uint64_t *ze) {
+    uint64_t z = zs; uint32_t semis = 0;
+    while (z < aend) { const uint8_t c = S.u8(z); if (c == 0) break; semis += c == ';' ? 1u : 0u; z++; }
+    *ze = z;
+    if (z == zs) return 0;
+    return semis + 1u < 100u ? semis + 1u : 100u;
+}
+/* bounds of piece k (k < itx_xa_count) */
+template <class Src>
+ITX_HD void itx_xa_kth(const Src &S, uint64_t zs, uint64_t ze, uint32_t k, uint64_t *ps, uint64_t *pe) {
+    uint64_t z = zs;
+    for (uint32_t seen = 0; seen < k && z < ze; z++) if (S.u8(z) == ';') seen++;
+    *ps = z;
+    while (z < ze && S.u8(z) != ';') z++;
+    *pe = z;
+}
+/* the one-lane walk over the alternates: xa = offset of the type byte of XA (0: no such tag), nm = bam_aux2i of NM.
+ * *malformed counts alternates without 4 comma separated fields met before the verdict. */
 /* S by value: an out-of-line function handed a reference would read the source's fields back from local memory at every byte */
 template <class Src>
-ITX_HDN bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src S, uint64_t a0, uint64_t aend,
-                                           int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
-    uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
+ITX_HDN bool itx_xa_walk(const itx_dev_index &D, const Src S, uint64_t xa, uint64_t aend, int32_t nm, int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
     if (!xa || xa >= aend) return false;
-    uint8_t ty = S.u8(xa);
+    const uint8_t ty = S.u8(xa);
     if (ty != 'Z' && ty != 'H') return false;
-    int32_t nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
     uint64_t s = xa + 1, zend = s;
     while (zend < aend && S.u8(zend) != 0) zend++;
     if (s == zend) return false;                                  /* chopByChar on "" gives no pieces */
@@ -588,34 +637,23 @@ ITX_HDN bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src S, 
         while (pe < zend && S.u8(pe) != ';') pe++;
         pieces++;
         if (pe > s) {
-            /* up to 4 comma separated fields (chr, pos, cigar, nm); the 4th stops at the next comma */
-            uint64_t f0s = 0, f0e = 0, f1s = 0, f1e = 0, f3s = 0, f3e = 0, q = s; int nf = 0; bool more = true;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (more) {
-                    const uint64_t b0 = q;
-                    while (q < pe && S.u8(q) != ',') q++;
-                    if (k == 0) { f0s = b0; f0e = q; } else if (k == 1) { f1s = b0; f1e = q; } else if (k == 3) { f3s = b0; f3e = q; }
-                    nf++;
-                    if (q >= pe) more = false; else q++;
-                }
-            }
-            if (nf != 4) { if (malformed) (*malformed)++; }
-            else {
-                int32_t nm2 = itx_strtol_int(S, f3s, f3e);
-                if (nm2 <= nm) {
-                    int32_t st = itx_strtol_int(S, f1s, f1e);
-                    if (st < 0) st = (int32_t)(0u - (uint32_t)st);
-                    int32_t en = (int32_t)((uint32_t)st + (uint32_t)qlen);
-                    int32_t c = itx_chrom_by_name(D, S, f0s, f0e);
-                    if (c >= 0 && itx_any_other_subfam(D, c, st, en, sel_fold)) return true;
-                }
-            }
+            bool mal;
+            if (itx_xa_piece(D, S, s, pe, nm, qlen, sel_fold, &mal)) return true;
+            if (mal && malformed) (*malformed)++;
         }
         if (pe >= zend) break;
         s = pe + 1;
     }
     return false;
+}
+/* record's aux area [a0, aend) carries XA; sel_fold = folded subfamily of the selected element; qlen = end - start */
+template <class Src>
+ITX_HD bool itx_mapped_to_diff_subfam_aux(const itx_dev_index &D, const Src &S, uint64_t a0, uint64_t aend,
+                                          int32_t sel_fold, int32_t qlen, uint32_t *malformed) {
+    const uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
+    if (!xa || xa >= aend) return false;
+    const int32_t nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
+    return itx_xa_walk(D, S, xa, aend, nm, sel_fold, qlen, malformed);
 }
 
 template <class Src>

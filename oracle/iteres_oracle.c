@@ -481,7 +481,11 @@ int ora_scan_bam_stream(ora_index *ix, const uint8_t *bam, uint64_t len, const o
                 c[6]++; if (uniq) c[7]++;
                 start = (unsigned int)pos;
                 int tmpend;
-                if (n_cigar) { uint32_t e2 = (uint32_t)pos; for (uint32_t k = 0; k < n_cigar; k++) { uint32_t cg; memcpy(&cg, cigar_p + k, 4); int op = cg & 0xf; if (op == 0 || op == 2 || op == 3) e2 += cg >> 4; } tmpend = (int)e2; }
+                /* CIGAR words past the record's own end are not read (the reference would read whatever follows in its
+                 * buffer: undefined); the device path clamps the same way */
+                uint32_t n_cig_in = n_cigar;
+                { const int64_t room = (int64_t)block_len - 32 - (int64_t)l_qname; if (room < 4 * (int64_t)n_cigar) n_cig_in = room > 0 ? (uint32_t)(room / 4) : 0; }
+                if (n_cigar) { uint32_t e2 = (uint32_t)pos; for (uint32_t k = 0; k < n_cig_in; k++) { uint32_t cg; memcpy(&cg, cigar_p + k, 4); int op = cg & 0xf; if (op == 0 || op == 2 || op == 3) e2 += cg >> 4; } tmpend = (int)e2; }
                 else tmpend = pos + l_qseq;
                 end = umin(cend, (unsigned int)tmpend);
                 strand = (flag & 16) ? '-' : '+';

@@ -23,6 +23,7 @@ struct emu_index {
     std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
     std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
     std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch, tile_checked, tile_mismatch, tile_entry_miss;
+    uint64_t xa_checked = 0, xa_mismatch = 0;             /* reads with XA put through the lane-per-alternate decomposition of k_scan; verdicts that differed from the one-lane walk */
     /* -R: smallest ordinal per key, of the unique and of the other fragments; persists across the files of a run */
     std::map<std::pair<unsigned long long, unsigned long long>, unsigned long long> dup_first;
     unsigned long long dup_min_unique = ~0ull, dup_min_other = ~0ull, dup_ord_base = 0;
@@ -39,7 +40,7 @@ void emu_reset(emu_index *E) {
     std::fill(E->el_cpg_score.begin(), E->el_cpg_score.end(), 0.0);
     std::fill(E->status.begin(), E->status.end(), 0u);
     E->dup_first.clear(); E->dup_min_unique = E->dup_min_other = ~0ull; E->dup_ord_base = 0;
-    E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0;
+    E->trace.clear(); E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0; E->xa_checked = E->xa_mismatch = 0;
 }
 
 emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char *rmsk, int filter_field, const char *filter_name, char *err) {
@@ -79,12 +80,12 @@ itx_index *emu_host_index(emu_index *E) { return &E->ix; }
 /* the ring the TMA decode kernel reads records from: 4 tiles of 2 KiB addressed by (offset & 8191) */
 static const uint32_t EMU_TILE = 2048, EMU_RING = 8192;
 static void walk_chunk(emu_index *E, const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, uint64_t p, const itx_bam_header &h, const itx_dev_opts &o,
-                       std::vector<itx_tuple> &out, uint64_t *exit_) {
+                       std::vector<itx_tuple> &out, uint64_t *exit_, uint64_t own = ~0ull) {
     const itx_src_global G{b};
     alignas(16) static thread_local uint8_t ring[EMU_RING];
     const itx_src_ring R{ring, EMU_RING - 1};
     uint64_t ring_t0 = ~0ull;
-    uint64_t hi = lo + C; if (hi > len) hi = len;
+    uint64_t hi = lo + C; if (hi > len) hi = len; if (hi > own) hi = own;
     out.clear();
     if (p < ITX_OFF_END) {
         while (p < hi) {
@@ -170,32 +171,93 @@ static void span_chain(const uint8_t *b, uint64_t len, uint64_t lo, uint32_t C, 
     *exitX = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
 }
 
+/* k_scan's XA walk for ONE read, composed exactly as the kernel composes it: the pieces are counted (itx_xa_count), handed out
+ * 32 at a time -- one per lane -- each lane finds its piece (itx_xa_kth) and tests it (itx_xa_piece); the first alternate that
+ * answers yes ends the walk and the malformed ones before it are counted. */
+static bool xa_lanes(const itx_dev_index &D, const itx_src_global &G, uint64_t p, const uint32_t x[9], int32_t fold, int32_t qlen, uint32_t *malformed) {
+    uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+    if (aend - a0 < 5) return false;
+    const uint64_t xa = itx_aux_find(G, a0, aend, 'X', 'A');
+    if (!xa || xa >= aend) return false;
+    const int32_t nm = itx_aux2i(G, itx_aux_find(G, a0, aend, 'N', 'M'), aend);
+    const uint8_t ty = G.u8(xa);
+    if (ty != 'Z' && ty != 'H') return false;
+    uint64_t ze; const uint64_t zs = xa + 1;
+    const uint32_t np = itx_xa_count(G, zs, aend, &ze);
+    bool found = false;
+    for (uint32_t b0 = 0; b0 < np && !found; b0 += 32) {
+        uint32_t m_hit = 0, m_mal = 0;
+        for (uint32_t lane = 0; lane < 32 && b0 + lane < np; lane++) {
+            uint64_t ps, pe; bool mal = false, hit = false;
+            itx_xa_kth(G, zs, ze, b0 + lane, &ps, &pe);
+            if (pe > ps) hit = itx_xa_piece(D, G, ps, pe, nm, qlen, fold, &mal);
+            if (hit) m_hit |= 1u << lane;
+            if (mal) m_mal |= 1u << lane;
+        }
+        if (m_hit) { found = true; *malformed += (uint32_t)__builtin_popcount(m_mal & ((1u << __builtin_ctz(m_hit)) - 1u)); }
+        else *malformed += (uint32_t)__builtin_popcount(m_mal);
+    }
+    return found;
+}
+
+/* the chain rule of the kernels (itx_span_consistent): the exit that counts for span i is that of the last span before it
+ * that holds a record start; a span that met none is right when the chain runs over it or has ended */
+static uint64_t prev_exit(const std::vector<uint64_t> &exit_, uint64_t j) { uint64_t x = exit_[j]; while (x == ITX_OFF_NONE && j > 0) { j--; x = exit_[j]; } return x; }
+static bool span_consistent(const std::vector<uint64_t> &entry, const std::vector<uint64_t> &exit_, uint64_t i, uint64_t span_end, uint64_t own) {
+    const uint64_t en = entry[i], ex = prev_exit(exit_, i - 1);
+    if (en == ex || ex == ITX_OFF_NONE) return true;
+    if (en != ITX_OFF_NONE) return false;
+    return ex == ITX_OFF_END || (ex < ITX_OFF_GUESS && ex >= (span_end < own ? span_end : own));
+}
+
 /* bam: uncompressed stream with >= 64 readable bytes after len.  want_trace: keep a per-record trace. */
+static int emu_scan_core(emu_index *E, const uint8_t *hdr_bam, uint64_t hdr_bytes, const uint8_t *bam, uint64_t len, uint64_t own, uint64_t carry0, const itx_scan_opts *so,
+                         uint32_t chunk, int want_trace, uint64_t cnt[13], uint64_t *entry_out, uint64_t *exit_out, char *err);
 int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_scan_opts *so, uint32_t chunk, int want_trace, uint64_t cnt[13], char *err) {
+    return emu_scan_core(E, bam, len, bam, len, ~0ull, ~0ull, so, chunk, want_trace, cnt, NULL, NULL, err);
+}
+/* one rank's part of a stream (itx_scan_shard_file on the device): `bam` holds the rank's own bytes [0, own) plus a margin up to len
+ * and no header (that comes from hdr_bam, the start of the file); carry0 = ITX_OFF_GUESS or the forced entry */
+int emu_scan_shard(emu_index *E, const uint8_t *hdr_bam, uint64_t hdr_bytes, const uint8_t *bam, uint64_t len, uint64_t own, uint64_t carry0, const itx_scan_opts *so,
+                   uint32_t chunk, uint64_t cnt[13], uint64_t *entry_rel, uint64_t *exit_rel, char *err) {
+    uint64_t en = ITX_OFF_NONE, ex = ITX_OFF_NONE;
+    int rc = emu_scan_core(E, hdr_bam, hdr_bytes, bam, len, own, carry0, so, chunk, 0, cnt, &en, &ex, err);
+    if (rc) return rc;
+    *entry_rel = en;
+    *exit_rel = ex >= ITX_OFF_GUESS ? (ex == ITX_OFF_GUESS ? ITX_OFF_NONE : ex) : (ex >= own ? ex - own : 0);
+    return ITX_OK;
+}
+static int emu_scan_core(emu_index *E, const uint8_t *hdr_bam, uint64_t hdr_bytes, const uint8_t *bam, uint64_t len, uint64_t own, uint64_t carry0, const itx_scan_opts *so,
+                         uint32_t chunk, int want_trace, uint64_t cnt[13], uint64_t *entry_out, uint64_t *exit_out, char *err) {
     itx_index &ix = E->ix; itx_dev_index &D = E->D;
     itx_bam_header h;
-    if (itx_host_parse_bam_header(&ix, bam, len, so->addChr, &h, err) != ITX_OK) return ITX_EFORMAT;
+    if (itx_host_parse_bam_header(&ix, hdr_bam, hdr_bytes, so->addChr, &h, err) != ITX_OK) return ITX_EFORMAT;
+    if (own > len) own = len;
+    if (carry0 == ~0ull) carry0 = h.hdr_len;
+    const uint64_t first_byte = carry0 >= ITX_OFF_GUESS ? 0 : carry0;
     itx_dev_opts o; o.mapQ = so->mapQ; o.iSize = so->iSize; o.extension = so->extension; o.minCoverage = so->minCoverage;
     o.filter = so->filter; o.discardWrongEnd = so->discardWrongEnd; o.treat = so->treat; o.diffSubfam = so->diffSubfam;
     const uint32_t C = chunk;
-    const uint64_t k0 = h.hdr_len / C, k1 = len > h.hdr_len ? (len + C - 1) / C : k0, n = k1 - k0;
+    const uint64_t k0 = first_byte / C, k1 = own > first_byte ? (own + C - 1) / C : k0, n = k1 - k0;
     std::vector<std::vector<itx_tuple>> tup(n);
     std::vector<uint64_t> entry(n), exit_(n);
-    /* K1: every chunk guesses its entry independently (chunk 0 knows it) */
+    /* K1: every chunk guesses its entry independently (chunk 0 knows it, unless the scan starts in the middle of a stream) */
     for (uint64_t i = 0; i < n; i++) {
-        uint64_t lo = (k0 + i) * C, hi = lo + C; if (hi > len) hi = len;
-        uint64_t p = i == 0 ? h.hdr_len : itx_speculate_entry(itx_src_global{bam}, lo, hi, len, h.n_ref);
+        uint64_t lo = (k0 + i) * C, hi = lo + C; if (hi > own) hi = own;
+        uint64_t p = (i == 0 && carry0 != ITX_OFF_GUESS) ? carry0 : itx_speculate_entry(itx_src_global{bam}, lo, hi, len, h.n_ref);
         entry[i] = p;
-        walk_chunk(E, bam, len, lo, C, p, h, o, tup[i], &exit_[i]);
+        walk_chunk(E, bam, len, lo, C, p, h, o, tup[i], &exit_[i], own);
     }
-    /* verify + repair */
-    for (uint64_t i = 1; i < n; i++) if (entry[i] != exit_[i - 1]) {
+    /* verify + repair (k_verify / k_fixup) */
+    for (uint64_t i = 1; i < n; i++) if (!span_consistent(entry, exit_, i, (k0 + i) * C + C, own)) {
         E->n_bad++;
-        entry[i] = exit_[i - 1];
-        walk_chunk(E, bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i]);
+        entry[i] = prev_exit(exit_, i - 1);
+        walk_chunk(E, bam, len, (k0 + i) * C, C, entry[i], h, o, tup[i], &exit_[i], own);
     }
+    if (entry_out) { *entry_out = ITX_OFF_NONE; if (carry0 != ITX_OFF_GUESS) *entry_out = carry0; else for (uint64_t i = 0; i < n && *entry_out == ITX_OFF_NONE; i++) *entry_out = entry[i]; }
+    if (exit_out) { *exit_out = n ? prev_exit(exit_, n - 1) : carry0; if (*exit_out == ITX_OFF_NONE && carry0 == ITX_OFF_GUESS) *exit_out = ITX_OFF_GUESS; }
     /* the span kernels' chain (staged guess, run-predicted walk), span by span, against the sequential chain */
-    if ((C % ITX_EMU_STAGE) == 0 && C <= (1u << 20)) {
+    if ((C % ITX_EMU_STAGE) == 0 && C <= (1u << 20) && own == len && carry0 == h.hdr_len) {
         for (uint64_t i = 0; i < n; i++) {
             uint64_t e0, ex; std::vector<uint64_t> st;
             span_chain(bam, len, (k0 + i) * C, C, h.n_ref, i == 0, i == 0 ? h.hdr_len : 0, &e0, &st, &ex);
@@ -259,6 +321,10 @@ int emu_scan_stream(emu_index *E, const uint8_t *bam, uint64_t len, const itx_sc
                     const uint64_t p = lo + T.rec_off; uint32_t x[9]; G.core(p, x); uint32_t bad = 0;
                     if (itx_mapped_to_diff_subfam(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
                     D.status[2] += bad;
+                    uint32_t bad2 = 0;
+                    const bool d2 = xa_lanes(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad2);
+                    E->xa_checked++;
+                    if (d2 != diffsub || bad2 != bad) E->xa_mismatch++;
                 }
             }
             if (diffsub) c[12]++;
@@ -330,6 +396,8 @@ uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
     return E->trace.size();
 }
 uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
+uint64_t emu_xa_checked(emu_index *E) { return E->xa_checked; }
+uint64_t emu_xa_mismatch(emu_index *E) { return E->xa_mismatch; }
 uint64_t emu_ring_checked(emu_index *E) { return E->ring_checked; }
 uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }
 uint64_t emu_tile_checked(emu_index *E) { return E->tile_checked; }

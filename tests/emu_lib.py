@@ -30,7 +30,8 @@ def lib():
         L.emu_trace.argtypes = [vp, vp, u64]
         L.emu_n_bad.restype = u64
         L.emu_n_bad.argtypes = [vp]
-        for f in ("emu_ring_checked", "emu_ring_mismatch", "emu_tile_checked", "emu_tile_mismatch", "emu_tile_entry_miss"):
+        L.emu_scan_shard.argtypes = [vp, vp, u64, vp, u64, u64, u64, C.POINTER(capi.ScanOpts), C.c_uint32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), cp]
+        for f in ("emu_ring_checked", "emu_ring_mismatch", "emu_tile_checked", "emu_tile_mismatch", "emu_tile_entry_miss", "emu_xa_checked", "emu_xa_mismatch"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [vp]
         L.emu_check_cov_rules.restype = C.c_uint64
@@ -85,6 +86,24 @@ class EmuIndex(capi.IndexBase):
             k = self.L.emu_trace(self.e, C.cast(t, C.c_void_p), cap)
             return list(self.cnt), (np.ctypeslib.as_array(t)[:k].copy() if k else np.zeros(0, dtype=np.dtype(capi.Trace)))
         return list(self.cnt)
+
+    def scan_shard(self, header_buf, part, own, carry0, opts):
+        """one rank's part of a stream: `part` = the rank's own bytes [0, own) followed by its margin; header_buf = the start of the
+        whole stream (for the BAM header); carry0 = GUESS or a forced entry.  Returns (counters, entry_rel, exit_rel)."""
+        hb = np.frombuffer(bytes(header_buf) + b"\0" * 64, dtype=np.uint8)
+        a = np.frombuffer(bytes(part) + b"\0" * 64, dtype=np.uint8)
+        err = C.create_string_buffer(256)
+        en, ex = C.c_uint64(0), C.c_uint64(0)
+        self._dirty = True
+        rc = self.L.emu_scan_shard(self.e, hb.ctypes.data, len(hb) - 64, a.ctypes.data, len(a) - 64, own, carry0, C.byref(opts), self.chunk, self.cnt,
+                                   C.byref(en), C.byref(ex), err)
+        if rc:
+            raise capi.ItxError(rc, err.value.decode())
+        return list(self.cnt), en.value, ex.value
+
+    def xa_check(self):
+        """(reads with XA put through k_scan's lane-per-alternate decomposition, verdicts that differed from the one-lane walk)"""
+        return self.L.emu_xa_checked(self.e), self.L.emu_xa_mismatch(self.e)
 
     def n_bad(self):
         return self.L.emu_n_bad(self.e)
