@@ -146,7 +146,7 @@ static int zero_counters(itx_index *ix, char *err, int all) {
         CK(cudaMemsetAsync(cu->d_cpg_u32, 0, cu->n_cpg_u32 * 4, cu->stream));
         CK(cudaMemsetAsync(cu->d_cpg_f64, 0, cu->n_cpg_f64 * 8, cu->stream));
     }
-    CK(cudaMemsetAsync(cu->d_misc, 0, (ITX_MAX_TID_SEEN + 8) * 4, cu->stream));
+    CK(cudaMemsetAsync(cu->d_misc, 0, (2 * ITX_MAX_TID_SEEN + 8) * 4, cu->stream));
     CK(cudaStreamSynchronize(cu->stream));
     return ITX_OK;
 }
@@ -227,7 +227,7 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         cu->n_cpg_u32 = ng + ne; cu->n_cpg_f64 = ng + (size_t)ix->bp_len + ne;
         CKN(cudaMalloc(&cu->d_u64, (cu->n_u64 ? cu->n_u64 : 1) * 8)); CKN(cudaMalloc(&cu->d_u32, (cu->n_u32 ? cu->n_u32 : 1) * 4));
         CKN(cudaMalloc(&cu->d_cpg_u32, (cu->n_cpg_u32 ? cu->n_cpg_u32 : 1) * 4)); CKN(cudaMalloc(&cu->d_cpg_f64, (cu->n_cpg_f64 ? cu->n_cpg_f64 : 1) * 8));
-        CKN(cudaMalloc(&cu->d_misc, (ITX_MAX_TID_SEEN + 8) * 4));
+        CKN(cudaMalloc(&cu->d_misc, (2 * ITX_MAX_TID_SEEN + 8) * 4));      /* unknown-tid marks of the scan, of the running k_scan launch, status words */
         CKN(cudaMalloc((void **)&cu->d_bp, ((size_t)ix->bp_len + 1) * 4)); CKN(cudaMalloc((void **)&cu->d_bp_u, ((size_t)ix->bp_len + 1) * 4));
         CKN(cudaMalloc((void **)&cu->d_carry, 8)); CKN(cudaMalloc((void **)&cu->d_running, 8)); CKN(cudaMalloc((void **)&cu->d_winbad, 4));
         CKN(cudaMalloc((void **)&cu->d_work, 16)); CKN(cudaMemset(cu->d_work, 0, 16));
@@ -246,7 +246,7 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         D.bp_diff = (uint32_t *)cu->d_u32; D.bp_diff_u = D.bp_diff + ix->bp_len; D.el_cnt = D.bp_diff_u + ix->bp_len; D.el_cnt_u = D.el_cnt + ne;
         D.grp_cpg = (uint32_t *)cu->d_cpg_u32; D.el_cpg = D.grp_cpg + ng;
         D.grp_cpg_score = (double *)cu->d_cpg_f64; D.bp_cpg = D.grp_cpg_score + ng; D.el_cpg_score = D.bp_cpg + ix->bp_len;
-        D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + ITX_MAX_TID_SEEN;
+        D.tid_unknown_seen = (uint32_t *)cu->d_misc; D.status = D.tid_unknown_seen + 2 * ITX_MAX_TID_SEEN;
         CKN(cudaMalloc(&cu->d_D, sizeof D)); CKN(cudaMemcpy(cu->d_D, &D, sizeof D, cudaMemcpyHostToDevice));
         if (zero_counters(ix, err, 1)) goto fail;
     }
@@ -1759,7 +1759,7 @@ extern "C" int itx_comm_rank(const itx_index *ix, int *rank, int *nranks) {
  * from another first record (the rank before says where the chain really enters) */
 static int counters_snapshot(itx_index *ix, int restore, char *err) {
     itx_cuda *cu = ix->cu;
-    const size_t b64 = cu->n_u64 * 8, b32 = ((cu->used_el ? cu->n_u32 : 2 * (size_t)ix->bp_len)) * 4, bm = (ITX_MAX_TID_SEEN + 8) * 4;
+    const size_t b64 = cu->n_u64 * 8, b32 = ((cu->used_el ? cu->n_u32 : 2 * (size_t)ix->bp_len)) * 4, bm = (2 * ITX_MAX_TID_SEEN + 8) * 4;
     if (!cu->d_snap || cu->snap_cap < b64 + b32 + bm) {
         if (restore) { snprintf(err, ITX_ERRLEN, "internal: no counter snapshot to restore"); return ITX_EARG; }
         cudaFree(cu->d_snap); cu->d_snap = NULL;

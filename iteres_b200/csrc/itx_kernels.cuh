@@ -629,6 +629,78 @@ __device__ __forceinline__ unsigned long long itx_effective_exit(const unsigned 
     return x;
 }
 
+/* The XA:Z walk of one round of k_scan, the whole warp at once (every lane calls it; go = this lane's read carries XA and is about
+ * to be counted).  buf holds the stage [c_lo64, c_lo64 + nb) of the stream g; rec_rel = the lane's record start, xa_rel = the type
+ * byte of its XA tag, both relative to the stage.  Lane-per-alternate (coop): every owner counts the pieces of its own list, the
+ * pieces of the whole round are numbered across the warp and handed out 32 at a time, one per lane -- whichever read they belong
+ * to -- so that all alternates of a round are parsed, looked up and walked side by side; the verdicts go back to the owners with
+ * two ballots.  Records that do not lie inside the staged bytes take the one-lane walk.  Returns mapped2diffSubfam's verdict. */
+__device__ __noinline__ bool itx_xa_warp(const itx_dev_index *Dg, const uint8_t *buf, const uint8_t *g, unsigned long long c_lo64, uint32_t nb, uint32_t rec_rel,
+                                         bool go, uint32_t xa_rel, int32_t fold, int32_t qlen, bool f_coop, bool neg) {
+    const itx_dev_index &D = *Dg;
+    const uint32_t lane = threadIdx.x & 31;
+    const itx_src_stage S{buf, g, c_lo64, nb};
+    /* the record's aux area again (the core sits in the stage: the record starts there), and NM */
+    uint64_t a0 = 0, aend = 0; int32_t nm = 0;
+    if (go) {
+        uint32_t x[9]; S.core(c_lo64 + rec_rel, x);
+        itx_aux_range(c_lo64 + rec_rel, x, &a0, &aend);
+        nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
+    }
+    const uint32_t aend_rel = (uint32_t)(aend - c_lo64);
+    bool diffsub = false;
+    const bool coop = f_coop && go && aend_rel + 4u <= nb;          /* no bounds tests on the staged bytes: only for records that lie inside them */
+    if (__any_sync(0xffffffffu, coop)) {
+        const itx_src_flat F{buf, c_lo64};
+        uint32_t np = 0, zs = 0, ze = 0;
+        if (coop) {
+            const uint8_t ty = buf[xa_rel];
+            if (ty == 'Z' || ty == 'H') {
+                uint64_t ze64; zs = xa_rel + 1u;
+                np = itx_xa_count(F, c_lo64 + zs, c_lo64 + aend_rel, &ze64); ze = (uint32_t)(ze64 - c_lo64);
+            }
+        }
+        uint32_t incl = np;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
+        bool found = false; uint32_t n_bad = 0;
+        for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
+            const uint32_t gi = b0 + lane;                 /* this lane's piece of the round */
+            /* its owner: the first lane whose running count exceeds gi (the counts never decrease along the warp) */
+            uint32_t ow = 0;
+#pragma unroll
+            for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= gi) ow += st; }
+            ow &= 31u;
+            const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow), o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
+            const int32_t o_nm = __shfl_sync(0xffffffffu, nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
+            bool hit = false, mal = false;
+            if (gi < total) {
+                uint64_t ps, pe;
+                itx_xa_kth(F, c_lo64 + o_zs, c_lo64 + o_ze, gi - o_base, &ps, &pe);
+                if (pe > ps) hit = itx_xa_piece(D, F, ps, pe, o_nm, o_qlen, o_fold, &mal);
+            }
+            const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
+            /* back to the owners: the first alternate that answers yes ends the walk, malformed ones before it are counted */
+            if (np && !found && base < b0 + 32u && incl > b0) {
+                const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
+                const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
+                const uint32_t h = m_hit & range;
+                if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
+                else n_bad += (uint32_t)__popc(m_mal & range);
+            }
+        }
+        if (found) diffsub = true;
+        if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
+    }
+    if (go && !coop) {
+        uint32_t bad = 0;
+        if (itx_xa_walk(D, S, c_lo64 + xa_rel, aend, nm, fold, qlen, &bad)) diffsub = true;
+        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+    }
+    return diffsub;
+}
+
 template <bool SMEM_HIST, int NW>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
@@ -808,7 +880,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 const uint32_t j = j0 + lane; const bool valid = j < n;
                 /* ---- everything this round needs out of the staged bytes: core, CIGAR, the XA / NM tags */
                 itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
-                uint32_t xa_rel = 0, aend_rel = 0; int32_t xa_nm = 0;             /* stage-relative offsets of the XA type byte (0: no XA) and of the record's end */
+                uint32_t xa_rel = 0;                                               /* stage-relative offset of the XA tag's type byte (0: the read carries no XA) */
                 if (valid) {
                     const unsigned long long rp = c_lo64 + pos[j];
                     uint32_t x[9];
@@ -819,10 +891,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                         /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
                         if (aend - a0 >= 5) {
                             const uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
-                            if (xa && xa < aend) {
-                                xa_rel = (uint32_t)(xa - c_lo64); aend_rel = (uint32_t)(aend - c_lo64);
-                                xa_nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
-                            }
+                            if (xa && xa < aend) xa_rel = (uint32_t)(xa - c_lo64);
                         }
                     }
                 }
@@ -840,8 +909,9 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     pa += ((valid ? 1u : 0u) & ns2) | (s2 << 8) | ((mp & ns2) << 16) | ((mp & s2) << 24);
                     pb += (us & ns2) | ((us & s2) << 8) | (fr << 16) | ((fr & uq) << 24);
                 }
-                /* a count, not a mark: the undo pass takes back what a wrongly guessed span left here too */
-                if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) itx_red_u32(&D.tid_unknown_seen[T.start], one);
+                /* marks of THIS launch: the last CTA folds them into the scan's marks only if the launch stands (a plain store: every
+                 * read of such a chromosome hits the same word, and reductions on one address serialise in L2) */
+                if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[ITX_MAX_TID_SEEN + T.start] = 1u;
                 long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
                 const uint32_t chrom = info & ITX_CHROM_MASK;
                 itx_query Q; Q.fs = Q.fe = 0; Q.lo = Q.top = 0;
@@ -880,64 +950,12 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
                 }
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-                /* ---- XA:Z alternates (mapped2diffSubfam), for the reads that are about to be counted */
+                /* ---- XA:Z alternates (mapped2diffSubfam), for the reads that are about to be counted: out of line, the whole warp at once */
                 const bool xa_go = sel >= 0 && xa_rel != 0u;
                 if (__any_sync(0xffffffffu, xa_go)) {
                     int32_t fold = 0;
                     if (xa_go) fold = D.sinfo[D.meta[sel].sub].fold;
-                    const int32_t qlen = (int32_t)(T.end - T.start);
-                    /* the lane-per-alternate walk reads the staged bytes without bounds tests: only for records that lie inside them */
-                    const bool coop = f_xacoop && xa_go && aend_rel + 4u <= nb;
-                    if (__any_sync(0xffffffffu, coop)) {
-                        const itx_src_flat F{buf, c_lo64};
-                        /* every owner counts the pieces of its own list; the pieces of the whole round are numbered across the warp */
-                        uint32_t np = 0; uint32_t zs = 0, ze = 0;
-                        if (coop) {
-                            const uint8_t ty = buf[xa_rel];
-                            if (ty == 'Z' || ty == 'H') {
-                                uint64_t ze64; zs = xa_rel + 1u;
-                                np = itx_xa_count(F, c_lo64 + zs, c_lo64 + aend_rel, &ze64); ze = (uint32_t)(ze64 - c_lo64);
-                            }
-                        }
-                        uint32_t incl = np;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-                        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
-                        bool found = false; uint32_t n_bad = 0;
-                        for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
-                            const uint32_t g = b0 + lane;                  /* this lane's piece of the round */
-                            /* its owner: the first lane whose running count exceeds g (the counts never decrease along the warp) */
-                            uint32_t ow = 0;
-#pragma unroll
-                            for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= g) ow += st; }
-                            ow &= 31u;
-                            const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow), o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
-                            const int32_t o_nm = __shfl_sync(0xffffffffu, xa_nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
-                            bool hit = false, mal = false;
-                            if (g < total) {
-                                uint64_t ps, pe;
-                                itx_xa_kth(F, c_lo64 + o_zs, c_lo64 + o_ze, g - o_base, &ps, &pe);
-                                if (pe > ps) hit = itx_xa_piece(D, F, ps, pe, o_nm, o_qlen, o_fold, &mal);
-                            }
-                            const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
-                            /* back to the owners: the first alternate that answers yes ends the walk, malformed ones before it are counted */
-                            if (np && !found && base < b0 + 32u && incl > b0) {
-                                const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
-                                const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
-                                const uint32_t h = m_hit & range;
-                                if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
-                                else n_bad += (uint32_t)__popc(m_mal & range);
-                            }
-                        }
-                        if (found) diffsub = true;
-                        if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
-                    }
-                    if (xa_go && !coop) {
-                        uint32_t bad = 0;
-                        if (aend_rel + 4u <= nb ? itx_xa_walk(*P.Dg, itx_src_flat{buf, c_lo64}, c_lo64 + xa_rel, c_lo64 + aend_rel, xa_nm, fold, qlen, &bad)
-                                                : itx_xa_walk(*P.Dg, S, c_lo64 + xa_rel, c_lo64 + aend_rel, xa_nm, fold, qlen, &bad)) diffsub = true;
-                        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
-                    }
+                    diffsub = itx_xa_warp(P.Dg, buf, A.b, c_lo64, nb, valid ? (uint32_t)pos[j] : 0u, xa_go, xa_rel, fold, (int32_t)(T.end - T.start), f_xacoop, neg);
                 }
                 const bool counted = sel >= 0 && !diffsub;
                 pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
@@ -1012,6 +1030,13 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             bad |= ok ? 0u : 1u;
         }
         bad = __syncthreads_or((int)bad) ? 1u : 0u;
+        {   /* this launch's unknown-chromosome marks: kept if the launch stands, dropped with it otherwise (the replay marks for itself) */
+            const bool stands = !neg && !bad && __ldcg(P.first_bad) == 0xffffffffu;
+            const uint32_t nt = (uint32_t)(A.n_ref < ITX_MAX_TID_SEEN ? A.n_ref : ITX_MAX_TID_SEEN);
+            for (uint32_t t = threadIdx.x; t < nt; t += blockDim.x)
+                if (__ldcg(D.tid_unknown_seen + ITX_MAX_TID_SEEN + t)) { if (stands) D.tid_unknown_seen[t] = 1u; D.tid_unknown_seen[ITX_MAX_TID_SEEN + t] = 0u; }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
             if (!neg) {
                 if (bad) atomicMin(P.first_bad, P.window);

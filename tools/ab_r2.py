@@ -89,6 +89,14 @@ if what == "scan":
     scan_variants("SE-50", 0, reads, V_SCAN)
     scan_variants("PE-100", 2, reads // 2, [V_SCAN[0], V_SCAN[2], V_SCAN[3], V_SCAN[6]])
     scan_variants("SE-75+XA", 1, reads * 3 // 5, [("r1 (15)", {"ITX_SCAN_FLAGS": "15"}), ("early,serial XA (31)", {"ITX_SCAN_FLAGS": "31"}), ("default (95)", {})], steps=5)
+elif what == "ncu1":
+    # ONE launch of k_scan (after two warm-up launches) on the stream AB_MODE / AB_READS name, with the environment as it is
+    mode = int(os.environ.get("AB_MODE", "0"))
+    hbuf, n, nrec, _ = make_stream(mode, reads)
+    dbuf, h = resident(hbuf, n)
+    for _ in range(3):
+        ix.reset(); cnt = ix.scan_bam_device(h, dbuf, n, opts)
+    print("mode", mode, "records", nrec, "bytes", n, "counters", cnt, flush=True)
 elif what == "ncu":
     hbuf, n, nrec, _ = make_stream(0, reads)
     dbuf, h = resident(hbuf, n)
