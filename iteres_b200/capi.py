@@ -25,6 +25,24 @@ class ScanOpts(C.Structure):
                 ("readNames", C.c_int32), ("isSam", C.c_int32), ("outbed", C.c_char_p), ("outbed_unique", C.c_char_p)]
 
 
+class ShardReport(C.Structure):
+    """itx_shard_report: how the record chain entered and left one rank's part of a file"""
+    _fields_ = [("entry_rel", C.c_uint64), ("exit_rel", C.c_uint64), ("own_bytes", C.c_uint64)]
+
+
+SHARD_GUESS, SHARD_END, SHARD_NONE = 0xfffffffffffffffd, 0xfffffffffffffffe, 0xffffffffffffffff
+
+
+def shard_chain_check(reports, L=None):
+    """itx_shard_chain_check on a list of (entry_rel, exit_rel, own_bytes): (first rank that must scan again or -1, its entry)"""
+    L = L or lib()
+    arr = (ShardReport * len(reports))(*[ShardReport(*r) for r in reports])
+    forced = C.c_uint64(0)
+    L.itx_shard_chain_check.argtypes = [C.c_int, C.POINTER(ShardReport), C.POINTER(C.c_uint64)]
+    bad = L.itx_shard_chain_check(len(reports), arr, C.byref(forced))
+    return bad, forced.value
+
+
 class Trace(C.Structure):
     _fields_ = [("start", C.c_uint32), ("end", C.c_uint32), ("tid", C.c_int32), ("sel_row", C.c_int32),
                 ("flags", C.c_uint32)]
@@ -104,6 +122,15 @@ def lib():
         L.itx_index_reset_counts.argtypes = [vp]
         L.itx_scan_alignments.argtypes = [vp, cp, C.POINTER(ScanOpts), C.POINTER(u64), cp]
         L.itx_scan_bgzf_memory.argtypes = [vp, vp, u64, C.POINTER(ScanOpts), C.POINTER(u64), cp]
+        L.itx_scan_alignment_file.argtypes = [vp, cp, C.POINTER(ScanOpts), C.POINTER(u64), cp]
+        L.itx_scan_shard_file.argtypes = [vp, cp, C.POINTER(ScanOpts), C.c_int, C.c_int, u64, C.POINTER(ShardReport), C.POINTER(u64), cp]
+        L.itx_shard_chain_check.argtypes = [C.c_int, C.POINTER(ShardReport), C.POINTER(u64)]
+        L.itx_scan_alignments_shard.argtypes = [vp, cp, C.POINTER(ScanOpts), C.POINTER(u64), cp]
+        L.itx_scan_cpg_shard.argtypes = [vp, cp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), cp]
+        L.itx_get_cpg_totals.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.itx_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.itx_index_build_on.restype = vp
+        L.itx_index_build_on.argtypes = [C.c_int, cp, cp, cp, C.c_int, cp, cp]
         L.itx_scan_bam_host.argtypes = [vp, vp, u64, C.POINTER(ScanOpts), C.POINTER(u64), cp]
         L.itx_bam_header_parse.restype = vp
         L.itx_bam_header_parse.argtypes = [vp, vp, u64, C.c_int, cp]
@@ -219,11 +246,13 @@ class Index(IndexBase):
 
     def __init__(self, chrom_sizes, rep_sizes, rmsk, filter_field=0, filter_name="ALL", device=None):
         self.L = lib()
-        if device is not None:
-            self.L.itx_set_device(device)
         err = C.create_string_buffer(ERRLEN)
-        self.h = self.L.itx_index_build(chrom_sizes.encode(), rep_sizes.encode(), rmsk.encode(), filter_field,
-                                        filter_name.encode(), err)
+        if device is not None:
+            self.h = self.L.itx_index_build_on(device, chrom_sizes.encode(), rep_sizes.encode(), rmsk.encode(), filter_field,
+                                               filter_name.encode(), err)
+        else:
+            self.h = self.L.itx_index_build(chrom_sizes.encode(), rep_sizes.encode(), rmsk.encode(), filter_field,
+                                            filter_name.encode(), err)
         if not self.h:
             raise ItxError(-1, err.value.decode())
         self.cnt = (C.c_uint64 * 13)()
@@ -252,6 +281,36 @@ class Index(IndexBase):
         err = C.create_string_buffer(ERRLEN)
         self._ck(self.L.itx_scan_alignments(self.h, bam_list.encode(), C.byref(opts), self.cnt, err), err)
         return list(self.cnt)
+
+    def scan_alignment_file(self, path, opts):
+        """the single-file twin (what `iteres filter` calls): the path is not split at commas"""
+        err = C.create_string_buffer(ERRLEN)
+        self._ck(self.L.itx_scan_alignment_file(self.h, path.encode(), C.byref(opts), self.cnt, err), err)
+        return list(self.cnt)
+
+    def scan_shard_file(self, path, opts, rank, nranks, entry=SHARD_GUESS):
+        """rank `rank` of `nranks` scans its block range of ONE file -> (counters so far, (entry_rel, exit_rel, own_bytes))"""
+        err = C.create_string_buffer(ERRLEN)
+        rep = ShardReport()
+        self._ck(self.L.itx_scan_shard_file(self.h, path.encode(), C.byref(opts), rank, nranks, entry, C.byref(rep), self.cnt, err), err)
+        return list(self.cnt), (rep.entry_rel, rep.exit_rel, rep.own_bytes)
+
+    def scan_alignments_shard(self, bam_list, opts):
+        """the whole protocol (scan, NCCL all-gather of the reports, re-scan where the chain check says so); rank / size from comm_init"""
+        err = C.create_string_buffer(ERRLEN)
+        self._ck(self.L.itx_scan_alignments_shard(self.h, bam_list.encode(), C.byref(opts), self.cnt, err), err)
+        return list(self.cnt)
+
+    def scan_cpg_shard(self, path, rank, nranks, filter=0):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        err = C.create_string_buffer(ERRLEN)
+        self._ck(self.L.itx_scan_cpg_shard(self.h, path.encode(), filter, rank, nranks, C.byref(a), C.byref(b), err), err)
+        return a.value, b.value
+
+    def cpg_totals(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.L.itx_get_cpg_totals(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def scan_bgzf_memory(self, ptr, nbytes, opts):
         err = C.create_string_buffer(ERRLEN)

@@ -48,6 +48,7 @@ struct itx_cuda {
     long long *d_sel; int want_sel;
     unsigned long long *h_scratch;                            /* pinned: [0] the carry a scan uploads (no wait for the copy); from byte 64 the end-of-scan report:
                                                                * cnt[16] u64, status[8] u32, first bad launch group u32, then (byte 256) the first ITX_SEEN_FAST unknown-tid marks */
+    unsigned long long *d_xa_q; uint64_t xa_cap; uint32_t *d_xa_n;      /* k_scan -> k_xa: record offsets of the reads whose XA:Z alternates have to be looked at */
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
     int scan_ctas[4];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
@@ -111,7 +112,7 @@ static void cuda_free_all(itx_cuda *cu) {
     void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_D, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
-                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused, cu->d_snap, cu->d_shard};
+                    cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused, cu->d_snap, cu->d_shard, cu->d_xa_q, cu->d_xa_n};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     for (int i = 0; i < 2; i++) if (cu->h_stage[i]) cudaFreeHost(cu->h_stage[i]);
     for (int i = 0; i < 4; i++) if (cu->h_ring[i]) cudaFreeHost(cu->h_ring[i]);
@@ -308,6 +309,18 @@ extern "C" void itx_bam_header_free(itx_bam_header *h) {
 /* ------------------------------------------------------------------ scan machinery */
 /* window_bytes: the largest launch group of the tuple path (16 bytes of tuple per 36 bytes of stream); log_bytes: the
  * largest launch group of k_scan, which only needs the spans' entry / exit logs and so can cover a whole resident stream */
+/* the queue k_scan hands its XA:Z reads to k_xa in: one entry per 42 bytes of a launch group (no record that carries an XA list is
+ * shorter), so it cannot overflow.  0: no room on the device -- the caller takes the tuple path, which looks at XA in line. */
+static int ensure_xa_queue(itx_cuda *cu, uint64_t group_bytes) {
+    const uint64_t need = group_bytes / 42 + 1024;
+    if (!cu->d_xa_n) { if (cudaMalloc((void **)&cu->d_xa_n, 8) != cudaSuccess || cudaMemset(cu->d_xa_n, 0, 8) != cudaSuccess) { cudaGetLastError(); return 0; } }
+    if (cu->d_xa_q && cu->xa_cap >= need) return 1;
+    cudaStreamSynchronize(cu->stream);
+    cudaFree(cu->d_xa_q); cu->d_xa_q = NULL; cu->xa_cap = 0;
+    if (cudaMalloc((void **)&cu->d_xa_q, need * 8) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cu->xa_cap = need;
+    return 1;
+}
 static int ensure_work(itx_index *ix, uint64_t window_bytes, uint64_t log_bytes, char *err) {
     itx_cuda *cu = ix->cu;
     uint32_t C = ix->tune_chunk, S = C / 36 + 1;
@@ -492,6 +505,11 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     {   /* one fused kernel per launch group unless something needs the tuples (-R, the ordered outputs, traces, ITX_FUSED=0) */
         const char *v = getenv("ITX_FUSED");
         sc->fused = !(v && strcmp(v, "0") == 0) && cu->decode_variant == 0 && !sc->rmdup && !sc->ordered && !ix->trace_cap && !cu->want_sel;
+        if (sc->fused && sc->o.diffSubfam) {
+            /* a k_scan launch group covers at most cap_log spans */
+            const uint64_t group = (cu->cap_log) * (uint64_t)cu->C;
+            if (!ensure_xa_queue(cu, group < len + cu->C ? group : len + cu->C)) sc->fused = 0;
+        }
         if (sc->carry0 == ITX_OFF_GUESS && (sc->rmdup || sc->ordered)) { snprintf(err, ITX_ERRLEN, "-R, -B / -V and filter -r follow the reads in file order: they are not available in a sharded scan"); return ITX_ENOTSUP; }
         if (sc->fused) { CK(cudaMemsetAsync(cu->d_fused, 0xff, 4, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 1, 0, 12, cu->stream)); CK(cudaMemsetAsync(cu->d_fused + 4, 0xff, 8, cu->stream)); }
     }
@@ -600,6 +618,7 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
     itx_cuda *cu = sc->ix->cu;
     itx_scan_args P; P.A = decode_args(sc, k0, n, avail, len, own); P.D = cu->D; P.Dg = (const itx_dev_index *)cu->d_D; P.sign = sign; P.window = window;
     P.carry_log = cu->d_carry_log; P.first_bad = cu->d_fused;
+    P.xa_q = cu->d_xa_q; P.xa_n = cu->d_xa_n; P.xa_cap = sc->o.diffSubfam ? cu->xa_cap : 0;
     const bool sh = fused_smem_hist(sc);
     const int nw = scan_warps();
     const size_t smem = (nw == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + (sh ? hist_bytes(cu) : 0);
@@ -609,6 +628,16 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
     if (nw == 8) { if (sh) launch_scan_kernel<true, 8>(cu, P, n, smem, ctas); else launch_scan_kernel<false, 8>(cu, P, n, smem, ctas); }
     else { if (sh) launch_scan_kernel<true, ITX_SCAN_NW>(cu, P, n, smem, ctas); else launch_scan_kernel<false, ITX_SCAN_NW>(cu, P, n, smem, ctas); }
     sc->n_launch++;
+    if (sc->o.diffSubfam) {
+        /* the reads k_scan queued (XA:Z alternates): mapped2diffSubfam and their accumulation, with the launch's sign */
+        itx_xa_args X; X.D = cu->D; X.Dg = (const itx_dev_index *)cu->d_D; X.b = sc->b; X.tid = sc->h->d_tid; X.n_ref = sc->h->n_ref; X.o = sc->o;
+        X.q = cu->d_xa_q; X.q_n = cu->d_xa_n; X.q_cap = cu->xa_cap; X.sign = sign; X.flags = P.flags;
+        uint64_t blocks = ((uint64_t)n * cu->C / 42 + 255) / 256, most = (uint64_t)cu->sm_count * 8;
+        if (blocks > most) blocks = most;
+        if (blocks < 1) blocks = 1;
+        k_xa<<<(unsigned)blocks, 256, 0, cu->stream>>>(X);
+        sc->n_launch++;
+    }
     return ITX_OK;
 }
 /* launch the kernels for chunks [k_next, k_hi) (k_hi <= k_end); avail = bytes valid on the device */
@@ -700,6 +729,7 @@ static int scan_end(scan_ctx *sc, uint64_t cnt[13], char *err) {
     P->d2h_bytes = 16 * 8 + 8 * 4 + sizeof(uint32_t) * (size_t)nt;
     if (sc->rmdup) cu->dup_ord_base += (sc->k_end + 1) * (uint64_t)cu->S;           /* the next file's reads come after this file's */
     if (st[4]) { snprintf(err, ITX_ERRLEN, "the -R key table overflowed"); return ITX_ENOMEM; }
+    if (st[0] & 8u) { snprintf(err, ITX_ERRLEN, "internal: the XA queue overflowed"); return ITX_ENOMEM; }
     if (st[0] & 4u) { snprintf(err, ITX_ERRLEN, "a TMA bulk copy never completed (device-side time-out in k_decode_span)"); return ITX_ENODEV; }
     if (st[0] & 2u) { snprintf(err, ITX_ERRLEN, "a BAM record is longer than the staged window (%llu bytes); raise the window with itx_tune", (unsigned long long)ix->tune_window); return ITX_ENOTSUP; }
     /* chromosomes absent from the size file: the reference warns once per name (generic.c:796-801) */

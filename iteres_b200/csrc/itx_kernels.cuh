@@ -574,6 +574,9 @@ struct itx_scan_args {
                                           * status[0] by the last CTA only when the launch will not be replayed: what a wrongly guessed span reports is garbage);
                                           * [4..5] (u64) the first record start a scan that began mid-stream settled on */
     uint32_t flags;                      /* ITX_SCAN_* (A/B switches; every combination gives the same counts) */
+    /* reads that carry XA:Z and are about to be counted are not decided here: their record offsets are queued for k_xa, which
+     * tests the alternates (mapped2diffSubfam) and does their accumulation.  xa_n[0] = entries so far (k_xa zeroes it) */
+    unsigned long long *xa_q; uint32_t *xa_n; unsigned long long xa_cap;
 };
 #define ITX_SCAN_PREFETCH 1u             /* the next stage's bytes are asked into L2 while this stage is worked on */
 #define ITX_SCAN_DOMSIZE  2u             /* chain walk predicts with the span's dominant record size, so an odd record costs one step, not two */
@@ -629,78 +632,6 @@ __device__ __forceinline__ unsigned long long itx_effective_exit(const unsigned 
     return x;
 }
 
-/* The XA:Z walk of one round of k_scan, the whole warp at once (every lane calls it; go = this lane's read carries XA and is about
- * to be counted).  buf holds the stage [c_lo64, c_lo64 + nb) of the stream g; rec_rel = the lane's record start, xa_rel = the type
- * byte of its XA tag, both relative to the stage.  Lane-per-alternate (coop): every owner counts the pieces of its own list, the
- * pieces of the whole round are numbered across the warp and handed out 32 at a time, one per lane -- whichever read they belong
- * to -- so that all alternates of a round are parsed, looked up and walked side by side; the verdicts go back to the owners with
- * two ballots.  Records that do not lie inside the staged bytes take the one-lane walk.  Returns mapped2diffSubfam's verdict. */
-__device__ __noinline__ bool itx_xa_warp(const itx_dev_index *Dg, const uint8_t *buf, const uint8_t *g, unsigned long long c_lo64, uint32_t nb, uint32_t rec_rel,
-                                         bool go, uint32_t xa_rel, int32_t fold, int32_t qlen, bool f_coop, bool neg) {
-    const itx_dev_index &D = *Dg;
-    const uint32_t lane = threadIdx.x & 31;
-    const itx_src_stage S{buf, g, c_lo64, nb};
-    /* the record's aux area again (the core sits in the stage: the record starts there), and NM */
-    uint64_t a0 = 0, aend = 0; int32_t nm = 0;
-    if (go) {
-        uint32_t x[9]; S.core(c_lo64 + rec_rel, x);
-        itx_aux_range(c_lo64 + rec_rel, x, &a0, &aend);
-        nm = itx_aux2i(S, itx_aux_find(S, a0, aend, 'N', 'M'), aend);
-    }
-    const uint32_t aend_rel = (uint32_t)(aend - c_lo64);
-    bool diffsub = false;
-    const bool coop = f_coop && go && aend_rel + 4u <= nb;          /* no bounds tests on the staged bytes: only for records that lie inside them */
-    if (__any_sync(0xffffffffu, coop)) {
-        const itx_src_flat F{buf, c_lo64};
-        uint32_t np = 0, zs = 0, ze = 0;
-        if (coop) {
-            const uint8_t ty = buf[xa_rel];
-            if (ty == 'Z' || ty == 'H') {
-                uint64_t ze64; zs = xa_rel + 1u;
-                np = itx_xa_count(F, c_lo64 + zs, c_lo64 + aend_rel, &ze64); ze = (uint32_t)(ze64 - c_lo64);
-            }
-        }
-        uint32_t incl = np;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
-        bool found = false; uint32_t n_bad = 0;
-        for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
-            const uint32_t gi = b0 + lane;                 /* this lane's piece of the round */
-            /* its owner: the first lane whose running count exceeds gi (the counts never decrease along the warp) */
-            uint32_t ow = 0;
-#pragma unroll
-            for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= gi) ow += st; }
-            ow &= 31u;
-            const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow), o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
-            const int32_t o_nm = __shfl_sync(0xffffffffu, nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
-            bool hit = false, mal = false;
-            if (gi < total) {
-                uint64_t ps, pe;
-                itx_xa_kth(F, c_lo64 + o_zs, c_lo64 + o_ze, gi - o_base, &ps, &pe);
-                if (pe > ps) hit = itx_xa_piece(D, F, ps, pe, o_nm, o_qlen, o_fold, &mal);
-            }
-            const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
-            /* back to the owners: the first alternate that answers yes ends the walk, malformed ones before it are counted */
-            if (np && !found && base < b0 + 32u && incl > b0) {
-                const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
-                const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
-                const uint32_t h = m_hit & range;
-                if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
-                else n_bad += (uint32_t)__popc(m_mal & range);
-            }
-        }
-        if (found) diffsub = true;
-        if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
-    }
-    if (go && !coop) {
-        uint32_t bad = 0;
-        if (itx_xa_walk(D, S, c_lo64 + xa_rel, aend, nm, fold, qlen, &bad)) diffsub = true;
-        if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
-    }
-    return diffsub;
-}
-
 template <bool SMEM_HIST, int NW>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
@@ -723,17 +654,15 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     if (lane == 0) { itx_mbar_init(bar_s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     const bool neg = P.sign < 0;
-    const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
-    const unsigned long long one64 = neg ? ~0ull : 1ull;
+#define one (neg ? 0xffffffffu : 1u)
+#define minus_one (neg ? 1u : 0xffffffffu)
+#define one64 (neg ? ~0ull : 1ull)
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
-    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = P.flags & ITX_SCAN_EARLY, f_xacoop = P.flags & ITX_SCAN_XACOOP;
+    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = P.flags & ITX_SCAN_EARLY;
     const bool f_evict = P.flags & ITX_SCAN_EVICT, f_evict_pf = P.flags & ITX_SCAN_EVICT_PF;
-    unsigned long long pol = 0;
-    if (f_evict || f_evict_pf) pol = itx_policy_evict_first();
-    const uint32_t n_elem32 = D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem;
+#define n_elem32 (D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem)
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
-    itx_dev_opts o_dec = A.o; o_dec.diffSubfam = 0;            /* XA is looked for right after the decode, by this kernel itself */
     /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no
      * popcounts); the fields are summed over the warp and added to the CTA's totals before any of them can reach 256 */
     uint32_t pa = 0, pb = 0, pc = 0, n_rounds = 0;
@@ -765,9 +694,9 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             const uint32_t bytes_ = (nb_out_ + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */ \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
             itx_mbar_expect_tx(bar_s, bytes_); \
-            if (f_evict) itx_bulk_g2s_hint(buf_s, A.b + lo + (c_lo_), bytes_, bar_s, pol); else itx_bulk_g2s(buf_s, A.b + lo + (c_lo_), bytes_, bar_s); \
+            if (f_evict) itx_bulk_g2s_hint(buf_s, A.b + lo + (c_lo_), bytes_, bar_s, itx_policy_evict_first()); else itx_bulk_g2s(buf_s, A.b + lo + (c_lo_), bytes_, bar_s); \
             if (f_prefetch && (c_lo_) + ITX_STAGE < hi && (rest_) >= STG + ITX_STAGE) { \
-                if (f_evict_pf) itx_prefetch_l2_hint(A.b + lo + (c_lo_) + STG, ITX_STAGE, pol); else itx_prefetch_l2(A.b + lo + (c_lo_) + STG, ITX_STAGE); \
+                if (f_evict_pf) itx_prefetch_l2_hint(A.b + lo + (c_lo_) + STG, ITX_STAGE, itx_policy_evict_first()); else itx_prefetch_l2(A.b + lo + (c_lo_) + STG, ITX_STAGE); \
             } \
         } \
     } while (0)
@@ -799,7 +728,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         }
         uint32_t staged = 0xffffffffu;                         /* span offset of the stage now in shared memory */
         uint32_t inflight = 0xffffffffu;                       /* span offset of the stage whose copy was issued early (none) */
-        uint32_t nb = 0, nb_next = 0;
+        uint32_t nb = 0;
         uint32_t szd = 0;                                      /* the span's dominant record size (0: none yet) */
         for (;;) {
             if (guess ? hi == 0u : !(p < hi)) { if (guess && lane == 0) A.entry[i] = ITX_OFF_NONE; break; }
@@ -807,7 +736,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             const uint32_t c_hi = c_lo + ITX_STAGE < hi ? c_lo + ITX_STAGE : hi;
             const unsigned long long rest = A.len - lo - c_lo;                 /* bytes of the stream from this stage on */
             if (staged != c_lo) {
-                if (inflight == c_lo) nb = nb_next;            /* on its way since the last round of the previous stage */
+                if (inflight == c_lo) nb = rest > STG ? STG : (uint32_t)rest;      /* on its way since the last round of the previous stage */
                 else ITX_SCAN_ISSUE(c_lo, rest, nb);         /* (the macro's __syncwarp: every lane is done reading the previous stage) */
                 if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
                 parity ^= 1u;
@@ -885,7 +814,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     const unsigned long long rp = c_lo64 + pos[j];
                     uint32_t x[9];
                     S.core(rp, x);
-                    T = itx_decode_record(S, rp, x, 0u, A.tid, A.n_ref, o_dec);
+                    T = itx_decode_record<itx_src_stage, false>(S, rp, x, 0u, A.tid, A.n_ref, A.o);      /* XA is looked for right here, below */
                     if (A.o.diffSubfam && (T.info & ITX_F_FRAG) && (T.info & ITX_CHROM_MASK) != ITX_CHROM_NONE) {
                         uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
                         /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
@@ -895,11 +824,13 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                         }
                     }
                 }
-                /* the last round of a stage whose reads carry no XA lists is done with the staged bytes: the next stage's copy starts now */
-                if (f_early && j0 + 32u >= n && q != 0xffffffffu && c_lo + q < hi && !__any_sync(0xffffffffu, xa_rel != 0u)) {
+                /* the last round of a stage is done with the staged bytes: the next stage's copy starts now */
+                if (f_early && j0 + 32u >= n && q != 0xffffffffu && c_lo + q < hi) {
                     const uint32_t c_nx = (c_lo + q) & ~(ITX_STAGE - 1u);
                     const unsigned long long rest_nx = A.len - lo - c_nx;
-                    ITX_SCAN_ISSUE(c_nx, rest_nx, nb_next);
+                    uint32_t nb_nx;
+                    ITX_SCAN_ISSUE(c_nx, rest_nx, nb_nx);
+                    (void)nb_nx;
                     inflight = c_nx;
                 }
                 const uint32_t info = T.info;
@@ -912,7 +843,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 /* marks of THIS launch: the last CTA folds them into the scan's marks only if the launch stands (a plain store: every
                  * read of such a chromosome hits the same word, and reductions on one address serialise in L2) */
                 if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[ITX_MAX_TID_SEEN + T.start] = 1u;
-                long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
+                long long sel = -1; const bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
                 const uint32_t chrom = info & ITX_CHROM_MASK;
                 itx_query Q; Q.fs = Q.fe = 0; Q.lo = Q.top = 0;
                 const bool q_ok = frag && chrom != ITX_CHROM_NONE && itx_query_open(D, (int32_t)chrom, T.start, T.end, &Q);
@@ -950,12 +881,19 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
                 }
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-                /* ---- XA:Z alternates (mapped2diffSubfam), for the reads that are about to be counted: out of line, the whole warp at once */
-                const bool xa_go = sel >= 0 && xa_rel != 0u;
-                if (__any_sync(0xffffffffu, xa_go)) {
-                    int32_t fold = 0;
-                    if (xa_go) fold = D.sinfo[D.meta[sel].sub].fold;
-                    diffsub = itx_xa_warp(P.Dg, buf, A.b, c_lo64, nb, valid ? (uint32_t)pos[j] : 0u, xa_go, xa_rel, fold, (int32_t)(T.end - T.start), f_xacoop, neg);
+                /* ---- reads with XA:Z alternates that are about to be counted go to k_xa (mapped2diffSubfam + their accumulation) */
+                {
+                    const bool xa_go = sel >= 0 && xa_rel != 0u;
+                    const uint32_t m_xa = __ballot_sync(0xffffffffu, xa_go);
+                    if (m_xa) {
+                        uint32_t qb = 0;
+                        if (lane == 0) qb = atomicAdd(P.xa_n, (uint32_t)__popc(m_xa));
+                        qb = __shfl_sync(0xffffffffu, qb, 0) + (uint32_t)__popc(m_xa & ((1u << lane) - 1u));
+                        if (xa_go) {
+                            if (qb < P.xa_cap) P.xa_q[qb] = c_lo64 + pos[j]; else atomicOr(&A.status[0], 8u);      /* cannot happen: the queue holds one entry per 42 bytes of stream */
+                            sel = -1;
+                        }
+                    }
                 }
                 const bool counted = sel >= 0 && !diffsub;
                 pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
@@ -1056,6 +994,132 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             }
             A.work[2] = 0; P.first_bad[1] = 0; P.first_bad[2] = 0;
         }
+    }
+#undef one
+#undef minus_one
+#undef one64
+#undef n_elem32
+}
+
+/* ------------------------------------------------------------------ XA:Z alternates (mapped2diffSubfam) */
+/* k_xa: the reads k_scan queued -- they carry XA:Z and were about to be counted.  One lane per read re-derives its fragment and
+ * the selected element (the same functions, out of global memory), then the warp walks the alternates of its 32 reads one LANE
+ * per ALTERNATE: every owner counts the pieces of its own list, the pieces of the 32 reads are numbered across the warp and handed
+ * out 32 at a time -- whichever read they belong to -- so that parsing, chromosome lookup and the table walk of all alternates
+ * run side by side; the verdicts go back to the owners with two ballots (the first alternate that answers yes ends a read's
+ * walk; malformed ones before it are counted).  Reads that stay are accumulated here, with the sign of the k_scan launch. */
+struct itx_xa_args {
+    itx_dev_index D; const itx_dev_index *Dg;                                  /* Dg: the same in global memory, for the out-of-line one-lane walk */
+    const uint8_t *b; const itx_tidinfo *tid; int32_t n_ref; itx_dev_opts o;
+    const unsigned long long *q; uint32_t *q_n; unsigned long long q_cap;      /* q_n: [0] entries, [1] CTAs done (the last one zeroes both) */
+    int32_t sign; uint32_t flags;
+};
+__global__ void __launch_bounds__(256, 2) k_xa(const itx_xa_args A) {
+    const itx_dev_index &D = A.D;
+    __shared__ uint32_t sh_c[3];
+    if (threadIdx.x < 3) sh_c[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long n = __ldcg(A.q_n) < A.q_cap ? __ldcg(A.q_n) : A.q_cap;
+    const bool neg = A.sign < 0, stat = A.o.filter == 0 && D.stat_mode, coop = A.flags & ITX_SCAN_XACOOP;
+    const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
+    const unsigned long long one64 = neg ? ~0ull : 1ull;
+    const itx_src_global G{A.b};
+    uint32_t c_rep = 0, c_rep_u = 0, c_diff = 0;
+    const unsigned long long w0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i0 = w0 * 32ull; i0 < n; i0 += nw * 32ull) {
+        const unsigned long long idx = i0 + lane;
+        bool go = idx < n;
+        itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
+        long long sel = -1; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
+        uint64_t xa = 0, aend = 0; int32_t nm = 0, fold = 0;
+        if (go) {
+            const unsigned long long rp = __ldcs(A.q + idx);
+            uint32_t x[9]; G.core(rp, x);
+            T = itx_decode_record<itx_src_global, false>(G, rp, x, 0u, A.tid, A.n_ref, A.o);
+            int32_t nhit; float tcov;
+            sel = itx_find_select(D, (int32_t)(T.info & ITX_CHROM_MASK), T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+            if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
+            uint64_t a0; itx_aux_range(rp, x, &a0, &aend);
+            xa = itx_aux_find(G, a0, aend, 'X', 'A');
+            go = sel >= 0 && xa && xa < aend;                      /* always true: k_scan queued the read for exactly this */
+            if (go) { nm = itx_aux2i(G, itx_aux_find(G, a0, aend, 'N', 'M'), aend); fold = D.sinfo[D.meta[sel].sub].fold; }
+        }
+        const int32_t qlen = (int32_t)(T.end - T.start);
+        bool diffsub = false;
+        if (coop) {
+            /* every owner counts the pieces of its own list; the pieces of the 32 reads are numbered across the warp */
+            uint32_t np = 0; uint64_t zs = 0, ze = 0;
+            if (go) { const uint8_t ty = G.u8(xa); if (ty == 'Z' || ty == 'H') { zs = xa + 1; np = itx_xa_count(G, zs, aend, &ze); } }
+            uint32_t incl = np;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
+            bool found = false; uint32_t n_bad = 0;
+            for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
+                const uint32_t gi = b0 + lane;                 /* this lane's piece of the batch */
+                /* its owner: the first lane whose running count exceeds gi (the counts never decrease along the warp) */
+                uint32_t ow = 0;
+#pragma unroll
+                for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= gi) ow += st; }
+                ow &= 31u;
+                const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow);
+                const uint64_t o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
+                const int32_t o_nm = __shfl_sync(0xffffffffu, nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
+                bool hit = false, mal = false;
+                if (gi < total) {
+                    uint64_t ps, pe;
+                    itx_xa_kth(G, o_zs, o_ze, gi - o_base, &ps, &pe);
+                    if (pe > ps) hit = itx_xa_piece(D, G, ps, pe, o_nm, o_qlen, o_fold, &mal);
+                }
+                const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
+                if (np && !found && base < b0 + 32u && incl > b0) {
+                    const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
+                    const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
+                    const uint32_t h = m_hit & range;
+                    if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
+                    else n_bad += (uint32_t)__popc(m_mal & range);
+                }
+            }
+            diffsub = found;
+            if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
+        } else if (go) {
+            uint32_t bad = 0;
+            diffsub = itx_xa_walk(*A.Dg, G, xa, aend, nm, fold, qlen, &bad);
+            if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+        }
+        const bool uniq = T.info & ITX_F_UNIQ, counted = go && !diffsub;
+        const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
+        c_diff += (uint32_t)__popc(__ballot_sync(0xffffffffu, go && diffsub));
+        c_rep += (uint32_t)__popc(m_cnt); c_rep_u += (uint32_t)__popc(m_cnt & __ballot_sync(0xffffffffu, uniq));
+        if (counted) {
+            if (stat) {
+                const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
+                const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
+                itx_red_u64(&D.grp[hs], one64); itx_red_u64(&D.grp[hf], one64); itx_red_u64(&D.grp[hc], one64);
+                if (uniq) { itx_red_u64(&D.grp[hs + 1], one64); itx_red_u64(&D.grp[hf + 1], one64); itx_red_u64(&D.grp[hc + 1], one64); }
+                const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(D.sinfo + m.sub));
+                const uint32_t L = sv.x;
+                uint32_t ja, jb;
+                if (L && itx_cov_range(T.start, T.end - T.start, e.start, e.end, m.cons_start, m.cons_end, L, &ja, &jb)) {
+                    const unsigned long long off = (unsigned long long)sv.z | ((unsigned long long)sv.w << 32);
+                    itx_red_u32(&D.bp_diff[off + ja], one); itx_red_u32(&D.bp_diff[off + jb], minus_one);
+                    if (uniq) { itx_red_u32(&D.bp_diff_u[off + ja], one); itx_red_u32(&D.bp_diff_u[off + jb], minus_one); }
+                }
+            } else if (A.o.filter) {
+                itx_red_u32(&D.el_cnt[sel], one);
+                if (uniq) itx_red_u32(&D.el_cnt_u[sel], one);
+            }
+        }
+    }
+    if (lane == 0) { if (c_rep) atomicAdd(&sh_c[0], c_rep); if (c_rep_u) atomicAdd(&sh_c[1], c_rep_u); if (c_diff) atomicAdd(&sh_c[2], c_diff); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh_c[0]) itx_red_u64(&D.cnt[9], neg ? 0ull - sh_c[0] : (unsigned long long)sh_c[0]);
+        if (sh_c[1]) itx_red_u64(&D.cnt[10], neg ? 0ull - sh_c[1] : (unsigned long long)sh_c[1]);
+        if (sh_c[2]) itx_red_u64(&D.cnt[12], neg ? 0ull - sh_c[2] : (unsigned long long)sh_c[2]);
+        __threadfence();
+        if (atomicAdd(A.q_n + 1, 1u) == gridDim.x - 1) { A.q_n[0] = 0; A.q_n[1] = 0; }      /* every CTA has read the count: the queue is empty again */
     }
 }
 

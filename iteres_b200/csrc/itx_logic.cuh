@@ -251,7 +251,8 @@ ITX_HD void itx_aux_range(uint64_t p, const uint32_t x[9], uint64_t *a0, uint64_
 /* ------------------------------------------------------------------ one BAM record -> tuple */
 ITX_HD uint32_t itx_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-template <class Src>
+/* WANT_XA = false: the caller looks for the XA tag itself (k_scan), whatever o.diffSubfam says */
+template <class Src, bool WANT_XA = true>
 ITX_HD itx_tuple itx_decode_record(const Src &S, uint64_t p, const uint32_t x[9], uint32_t rec_off,
                                    const itx_tidinfo *tidtab, int32_t n_ref, const itx_dev_opts &o) {
     itx_tuple T; T.start = 0; T.end = 0; T.info = ITX_CHROM_NONE; T.rec_off = rec_off;
@@ -307,7 +308,7 @@ ITX_HD itx_tuple itx_decode_record(const Src &S, uint64_t p, const uint32_t x[9]
     T.start = start; T.end = end;
     T.info = (T.info & ~ITX_CHROM_MASK) | ITX_F_FRAG | (uniq ? ITX_F_UNIQ : 0u) | (minus ? ITX_F_MINUS : 0u) |
              (ti.chrom < 0 ? ITX_CHROM_NONE : (uint32_t)ti.chrom);
-    if (o.diffSubfam && ti.chrom >= 0) {
+    if (WANT_XA && o.diffSubfam && ti.chrom >= 0) {
         uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
         if (itx_aux_find(S, a0, aend, 'X', 'A')) T.info |= ITX_F_HASXA;
     }
@@ -601,23 +602,53 @@ ITX_HD bool itx_xa_piece(const itx_dev_index &D, const Src &S, uint64_t ps, uint
     const int32_t c = itx_chrom_by_name(D, S, f0s, f0e);
     return c >= 0 && itx_any_other_subfam(D, c, st, en, sel_fold);
 }
+/* four bytes at a time: 0x80 in every byte of w that equals the byte replicated in c4 (exact, no carries between bytes) */
+ITX_HD uint32_t itx_eq4(uint32_t w, uint32_t c4) {
+    const uint32_t x = w ^ c4;
+    return ~((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x)) & 0x80808080u;
+}
+ITX_HD uint32_t itx_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
 /* the value string that starts at zs (the byte after the type byte): *ze = its terminator (or aend), returns the number of
- * pieces the reference visits (0 for the empty string: chopByChar on "" gives none) */
+ * pieces the reference visits (0 for the empty string: chopByChar on "" gives none).  Aligned words once the first odd bytes are
+ * done (reads may touch up to 3 bytes past aend, inside the word that holds aend - 1: stream buffers carry slack). */
 template <class Src>
 ITX_HD uint32_t itx_xa_count(const Src &S, uint64_t zs, uint64_t aend, uint64_t *ze) {
-    uint64_t z = zs; uint32_t semis = 0;
-    while (z < aend) { const uint8_t c = S.u8(z); if (c == 0) break; semis += c == ';' ? 1u : 0u; z++; }
+    uint64_t z = zs; uint32_t semis = 0; bool open = true;
+    while (open && z < aend && (z & 3)) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { semis += c == ';' ? 1u : 0u; z++; } }
+    while (open && z + 4 <= aend) {
+        const uint32_t w = S.w32(z);
+        if (itx_eq4(w, 0u)) break;                               /* the terminator is in this word: the byte loop finds it */
+        semis += itx_popc32(itx_eq4(w, 0x3b3b3b3bu));
+        z += 4;
+    }
+    while (open && z < aend) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { semis += c == ';' ? 1u : 0u; z++; } }
     *ze = z;
     if (z == zs) return 0;
     return semis + 1u < 100u ? semis + 1u : 100u;
 }
-/* bounds of piece k (k < itx_xa_count) */
+/* bounds of piece k (k < itx_xa_count): [*ps, *pe) lies between the k-th and the (k+1)-th ';' of [zs, ze) */
 template <class Src>
 ITX_HD void itx_xa_kth(const Src &S, uint64_t zs, uint64_t ze, uint32_t k, uint64_t *ps, uint64_t *pe) {
-    uint64_t z = zs;
-    for (uint32_t seen = 0; seen < k && z < ze; z++) if (S.u8(z) == ';') seen++;
+    uint64_t z = zs; uint32_t seen = 0;
+    while (seen < k && z < ze && (z & 3)) { if (S.u8(z) == ';') seen++; z++; }
+    while (seen < k && z + 4 <= ze) {
+        const uint32_t n = itx_popc32(itx_eq4(S.w32(z), 0x3b3b3b3bu));
+        if (seen + n >= k) break;                                /* the k-th ';' is in this word */
+        seen += n; z += 4;
+    }
+    while (seen < k && z < ze) { if (S.u8(z) == ';') seen++; z++; }
     *ps = z;
-    while (z < ze && S.u8(z) != ';') z++;
+    while (z < ze && (z & 3) && S.u8(z) != ';') z++;
+    if (z < ze && !(z & 3)) {
+        while (z + 4 <= ze && !itx_eq4(S.w32(z), 0x3b3b3b3bu)) z += 4;
+        while (z < ze && S.u8(z) != ';') z++;
+    }
     *pe = z;
 }
 /* the one-lane walk over the alternates: xa = offset of the type byte of XA (0: no such tag), nm = bam_aux2i of NM.
