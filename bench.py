@@ -844,6 +844,7 @@ def extra_configs(a, L, ix, world_s, tables, wd, opts, peak, ncpu, parity):
             times.append(time.perf_counter() - t1)
     gd1 = os.path.join(wd, "x_cfg1_gpu")
     gpu_tables(ix1, "stat", gd1, opts)
+    w1.seed = 4241                                             # the reads of cfg1.bam
     R1 = Resident(L, ix1, w1, 0, 1_000_000, threads=ncpu)
     ks, stp, c1r, _ = timed_resident(ix1, R1, opts, 20, 3)
     assert c1r == c1

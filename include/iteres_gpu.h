@@ -168,6 +168,7 @@ typedef struct itx_profile {
     int32_t inflate_threads;
     int32_t fused;         /* 1: the launch groups ran as one k_scan each (its time is decode_ms; overlap_ms is 0) */
     uint64_t n_replayed_windows;   /* launch groups counted again through the tuple path after a failed chain check */
+    double cpg_kernel_ms;          /* itx_scan_cpg: device time of the k_bedgraph launches (sum) */
 } itx_profile;
 void itx_last_profile(const itx_index *ix, itx_profile *p);
 /* device-side stopwatch on the scan stream: itx_mark records CUDA event `slot` (0..7) after everything

@@ -53,7 +53,8 @@ class Profile(C.Structure):
                 ("total_ms", C.c_double), ("h2d_ms", C.c_double), ("inflate_ms", C.c_double),
                 ("n_records", C.c_uint64), ("n_fragments", C.c_uint64), ("stream_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint64),
-                ("n_bad_chunks", C.c_uint64), ("inflate_threads", C.c_int32), ("fused", C.c_int32), ("n_replayed_windows", C.c_uint64)]
+                ("n_bad_chunks", C.c_uint64), ("inflate_threads", C.c_int32), ("fused", C.c_int32), ("n_replayed_windows", C.c_uint64),
+                ("cpg_kernel_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1622,10 +1622,13 @@ static int scan_cpg_part(itx_index *ix, const char *bedgraph, int filter, int ra
     unsigned long long *d_inrep_rows = dcnt ? dcnt + 8 : NULL;             /* k_cpg's own counter */
     if (rc == ITX_OK) cudaMemsetAsync(d_inrep_rows, 0, 8, cu->stream);
     /* what window `i` left for the host: its counters, the malformed line, the lines with a hard score */
+    cudaEvent_t kev[4]; for (int i = 0; i < 4; i++) cudaEventCreate(&kev[i]);
+    double kernel_ms = 0;
     auto settle = [&](int i) -> int {
         if (!inflight[i]) return ITX_OK;
         inflight[i] = false;
         unsigned long long c[4];
+        { float ms = 0; if (cudaEventSynchronize(kev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, kev[2 * i], kev[2 * i + 1]) == cudaSuccess) kernel_ms += ms; }
         if (cudaEventSynchronize(done[i]) != cudaSuccess || cudaMemcpy(c, dcnt + 4 * i, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) { snprintf(err, ITX_ERRLEN, "CUDA error in the bedGraph kernel: %s", cudaGetErrorString(cudaGetLastError())); return ITX_ENODEV; }
         lines += c[0]; inrep += c[1];
         const char *tb = (const char *)hbuf[i];
@@ -1682,7 +1685,9 @@ static int scan_cpg_part(itx_index *ix, const char *bedgraph, int filter, int ra
                 cudaMemcpyAsync(dbuf[slot], hb, use, cudaMemcpyHostToDevice, cu->stream);
                 cudaMemsetAsync(dcnt + 4 * slot, 0, 32, cu->stream); cudaMemsetAsync(dcnt + 4 * slot + 2, 0xff, 8, cu->stream);
                 itx_bedgraph_args A; A.D = cu->D; A.text = dbuf[slot]; A.n = use; A.filter = filter; A.counts = dcnt + 4 * slot; A.fallback = dfall[slot]; A.fallback_cap = fall_cap;
+                cudaEventRecord(kev[2 * slot], cu->stream);
                 k_bedgraph<<<(unsigned)((use + ITX_BG_TILE - 1) / ITX_BG_TILE), 256, 0, cu->stream>>>(A);
+                cudaEventRecord(kev[2 * slot + 1], cu->stream);
                 cudaEventRecord(done[slot], cu->stream);
                 inflight[slot] = true;
             }
@@ -1700,6 +1705,8 @@ static int scan_cpg_part(itx_index *ix, const char *bedgraph, int filter, int ra
     if (n_lines) *n_lines = (uint32_t)lines;
     if (n_in_repeat) *n_in_repeat = (uint32_t)inrep;
     if (rc == ITX_OK) { ix->cpg_lines += lines; ix->cpg_in_repeat += inrep; }
+    for (int i = 0; i < 4; i++) cudaEventDestroy(kev[i]);
+    ix->prof.cpg_kernel_ms = kernel_ms; ix->prof.h2d_bytes = flen - f_begin;
     return rc;
 }
 

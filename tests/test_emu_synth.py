@@ -420,3 +420,43 @@ def test_wrong_span_guesses_are_caught_and_repaired(tmp_path):
         assert_group_tables_and_coverage(emu, ora)
         emu.close()
     ora.close()
+
+
+def inconsistent_cigar_stream():
+    """records whose n_cigar overstates what the record holds (a corrupt file -- or the garbage a wrongly guessed span walks): the
+    CIGAR walk of bam_calend must stop at the record's own end.  The last record of the stream is one of them: an unclamped walk
+    would read past the end of the buffer (the reference itself reads whatever follows in its malloc'ed block: undefined)."""
+    import struct
+    import bamio
+    import kats
+    good = [bamio.encode_record(kats.se("g%d" % j, 16 if j % 2 else 0, 1000 + 11 * j, 37, aux=[("NM", "C", 1)])) for j in range(40)]
+
+    def broken(qname, flag, pos, n_cigar_claimed, n_cigar_present, l_seq=0):
+        q = qname.encode() + b"\0"
+        cig = b"".join(struct.pack("<I", (20 << 4) | 0) for _ in range(n_cigar_present))
+        core = struct.pack("<iiIIiiii", 0, pos, (4680 << 16) | (37 << 8) | len(q), (flag << 16) | n_cigar_claimed, l_seq, -1, -1, 0)
+        data = core + q + cig
+        return struct.pack("<i", len(data)) + data
+    recs = good[:20] + [broken("b1", 16, 1040, 9, 2), broken("b2", 0, 1060, 65535, 0), broken("b3", 16, 5100, 3, 3)] + good[20:] + [broken("last", 16, 1100, 60000, 1)]
+    return bamio.encode_header([("chr1", 1000000)]) + b"".join(recs), len(recs)
+
+
+def test_n_cigar_beyond_the_record_is_not_followed(tmp_path):
+    import kats
+    d = str(tmp_path)
+    cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
+    open(cs, "w").write("chr1\t1000000\n")
+    open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
+    open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
+    raw, nrec = inconsistent_cigar_stream()
+    for ext in (0, 150):                                        # -E 0: every read's end comes from the CIGAR; -E 150: only the minus strand's
+        ora = O.OracleIndex(cs, rs, rm)
+        cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(extension=ext), trace=True)
+        assert cnt_o[0] == nrec and cnt_o[9] > 0
+        emu = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
+        cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(extension=ext), trace=True)
+        assert cnt_e == cnt_o
+        for f in ("start", "end", "tid", "sel_row"):
+            assert np.array_equal(tr_e[f], tr_o[f]), f
+        ora.close()
+        emu.close()
