@@ -8,7 +8,8 @@ ERRLEN = 256
 
 
 def lib_path():
-    return os.path.join(HERE, "csrc", "libiteres_gpu.so")
+    # ITX_LIB: another build of the same library (A/B measurements of compile-time variants)
+    return os.environ.get("ITX_LIB") or os.path.join(HERE, "csrc", "libiteres_gpu.so")
 
 
 class ItxError(RuntimeError):

@@ -88,6 +88,60 @@ static void use_device(void) {
     const char *d = getenv("ITERES_DEVICE");
     if (d && itx_set_device(atoi(d)) != ITX_OK) die("cannot use CUDA device %s", d);
 }
+/* ITERES_GPUS=N: the job is split over N devices (ITERES_DEVICE, ITERES_DEVICE + 1, ...), one host thread and one index per device.
+ * Alignments: ONE file list, every rank scans its BGZF block range of every file (itx_scan_alignments_shard); CpG: every rank its part of
+ * the bedGraph's lines; then ONE allreduce of the counter block, and rank 0 writes the tables -- the same bytes as a single device writes
+ * (integer sums; CpG score sums within 1e-9 relative).  Options that follow the reads in file order (-R, -B, -V, -r) and SAM text run
+ * on one device. */
+typedef struct {
+    int rank, n, dev0; const char *cs, *rs, *rm; int field; const char *fname; const uint8_t *uid;
+    int cpg, cpg_filter; const char *input; const itx_scan_opts *o;
+    itx_index *ix; uint64_t cnt[13]; int rc; char err[ITX_ERRLEN];
+} gpu_rank;
+static void *gpu_rank_main(void *arg) {
+    gpu_rank *g = (gpu_rank *)arg;
+    g->rc = ITX_OK; g->err[0] = 0;
+    g->ix = itx_index_build_on(g->dev0 + g->rank, g->cs, g->rs, g->rm, g->field, g->fname, g->err);
+    if (!g->ix) { g->rc = ITX_EFORMAT; return NULL; }
+    if ((g->rc = itx_comm_init(g->ix, g->uid, g->rank, g->n, g->err))) return NULL;
+    if (g->cpg) { uint32_t a = 0, b = 0; g->rc = itx_scan_cpg_shard(g->ix, g->input, g->cpg_filter, g->rank, g->n, &a, &b, g->err); }
+    else g->rc = itx_scan_alignments_shard(g->ix, g->input, g->o, g->cnt, g->err);
+    if (g->rc) return NULL;
+    g->rc = itx_comm_allreduce_counts(g->ix, g->err);
+    if (g->rc == ITX_OK) itx_get_counters(g->ix, g->cnt);
+    return NULL;
+}
+static int n_gpus_wanted(void) {
+    const char *v = getenv("ITERES_GPUS");
+    int n = v ? atoi(v) : 1;
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return n;
+}
+/* the whole multi-device run; returns rank 0's index, holding the job's counters (cnt filled for alignment scans) */
+static itx_index *run_on_gpus(int n, const char *cs, const char *rs, const char *rm, int field, const char *fname, int cpg, int cpg_filter,
+                              const char *input, const itx_scan_opts *o, uint64_t cnt[13]) {
+    static uint8_t uid[ITX_NCCL_ID_BYTES];
+    char err[ITX_ERRLEN];
+    if (itx_device_count() < n) die("ITERES_GPUS=%d, but only %d CUDA device(s) are visible", n, itx_device_count());
+    if (itx_comm_unique_id(uid, err) != ITX_OK) die("%s", err);
+    const char *d0 = getenv("ITERES_DEVICE");
+    gpu_rank *g = (gpu_rank *)calloc((size_t)n, sizeof(gpu_rank));
+    pthread_t *th = (pthread_t *)calloc((size_t)n, sizeof(pthread_t));
+    for (int r = 0; r < n; r++) {
+        g[r].rank = r; g[r].n = n; g[r].dev0 = d0 ? atoi(d0) : 0; g[r].cs = cs; g[r].rs = rs; g[r].rm = rm; g[r].field = field; g[r].fname = fname; g[r].uid = uid;
+        g[r].cpg = cpg; g[r].cpg_filter = cpg_filter; g[r].input = input; g[r].o = o;
+        if (pthread_create(&th[r], NULL, gpu_rank_main, &g[r]) != 0) die("cannot start the thread of device %d", r);
+    }
+    for (int r = 0; r < n; r++) pthread_join(th[r], NULL);
+    for (int r = 0; r < n; r++) if (g[r].rc != ITX_OK) die("%s", g[r].err[0] ? g[r].err : "a device failed");
+    if (cnt) memcpy(cnt, g[0].cnt, sizeof g[0].cnt);
+    itx_index *ix = g[0].ix;
+    for (int r = 1; r < n; r++) itx_index_free(g[r].ix);
+    free(th); free(g);
+    return ix;
+}
+
 static void done_in(time_t t0) { fprintf(stderr, "* Done, time used %.0f seconds.\n", difftime(time(NULL), t0)); }
 
 /* which of -n / -c / -f was given -> (rmsk column, name) as filter.c:93-113 */
@@ -146,13 +200,21 @@ static int main_stat(int argc, char **argv) {
     if (bedu) o.outbed_unique = fmt_alloc("%s.iteres.unique.bed", prefix);
     use_device();
     char err[ITX_ERRLEN]; uint64_t cnt[13];
+    itx_index *ix;
+    const int ngpu = (o.rmDup || bed || bedu || sam) ? 1 : n_gpus_wanted();
+    if (ngpu != n_gpus_wanted()) fprintf(stderr, "* -R, -B, -V and -S follow the reads in file order: running on one GPU\n");
     fprintf(stderr, "* Parsing the rmsk file\n");
-    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
+    if (ngpu > 1) {
+        ix = run_on_gpus(ngpu, chrom_sizes, rep_sizes, rmsk, 0, "ALL", 0, 0, bams, &o, cnt);
+        fprintf(stderr, "* Total %lld repeats found.\n* Parsing the SAM/BAM file\n", (long long)itx_n_repeats_parsed(ix));
+    } else {
+    ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
     if (!ix) die("%s", err);
     fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     LAP("index built");
     fprintf(stderr, "* Parsing the SAM/BAM file\n");
     if (itx_scan_alignments(ix, bams, &o, cnt, err) != ITX_OK) die("%s", err);
+    }
     LAP("alignments scanned");
     fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
@@ -217,13 +279,19 @@ static int main_filter(int argc, char **argv) {
     o.readNames = readlist;
     use_device();
     char err[ITX_ERRLEN]; uint64_t cnt[13];
+    itx_index *ix;
+    const int ngpu = (o.rmDup || readlist || sam || strchr(bam, ',')) ? 1 : n_gpus_wanted();
+    if (ngpu != n_gpus_wanted()) fprintf(stderr, "* -R, -r and -S follow the reads in file order: running on one GPU\n");
     fprintf(stderr, "* Start to parse the rmsk file\n");
-    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
-    if (!ix) die("%s", err);
+    if (ngpu > 1) ix = run_on_gpus(ngpu, chrom_sizes, rep_sizes, rmsk, field, subfam, 0, 0, bam, &o, cnt);
+    else {
+        ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
+        if (!ix) die("%s", err);
+    }
     if (field) fprintf(stderr, "* Total %lld repeats for [%s].\n", (long long)itx_n_repeats_parsed(ix), subfam);
     else fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     fprintf(stderr, "* Start to parse the SAM/BAM file\n");
-    if (itx_scan_alignment_file(ix, bam, &o, cnt, err) != ITX_OK) die("%s", err);
+    if (ngpu == 1 && itx_scan_alignment_file(ix, bam, &o, cnt, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "\r* Processed read ends: %llu\n", (unsigned long long)(cnt[0] + cnt[1]));
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Preparing the output file\n");
@@ -252,11 +320,18 @@ static int main_cpgstat(int argc, char **argv) {
     use_device();
     char err[ITX_ERRLEN]; uint32_t lines = 0, inrep = 0;
     fprintf(stderr, "* Start to parse the rmsk file\n");
-    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
-    if (!ix) die("%s", err);
+    itx_index *ix;
+    const int ngpu = n_gpus_wanted();
+    if (ngpu > 1) {
+        ix = run_on_gpus(ngpu, chrom_sizes, rep_sizes, rmsk, 0, "ALL", 1, 0, bg, NULL, NULL);
+        uint64_t a = 0, b = 0; itx_get_cpg_totals(ix, &a, &b); lines = (uint32_t)a; inrep = (uint32_t)b;
+    } else {
+        ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, 0, "ALL", err);
+        if (!ix) die("%s", err);
+    }
     fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     fprintf(stderr, "* Start to parse the bedGraph file\n");
-    if (itx_scan_cpg(ix, bg, 0, &lines, &inrep, err) != ITX_OK) die("%s", err);
+    if (ngpu == 1 && itx_scan_cpg(ix, bg, 0, &lines, &inrep, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Processed CpG sites: %u\n* CpG sites in Repeats: %u\n", lines, inrep);
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Writing stats and Wig file\n");
@@ -291,10 +366,19 @@ static int main_cpgfilter(int argc, char **argv) {
     use_device();
     char err[ITX_ERRLEN]; uint32_t lines = 0, inrep = 0;
     fprintf(stderr, "* Start to parse the rmsk file\n");
-    itx_index *ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
-    if (!ix) die("%s", err);
+    itx_index *ix;
+    const int ngpu = n_gpus_wanted();
+    if (ngpu > 1) {
+        ix = run_on_gpus(ngpu, chrom_sizes, rep_sizes, rmsk, field, subfam, 1, 1, bg, NULL, NULL);
+        uint64_t a = 0, b = 0; itx_get_cpg_totals(ix, &a, &b); lines = (uint32_t)a; inrep = (uint32_t)b;
+    } else {
+        ix = itx_index_build(chrom_sizes, rep_sizes, rmsk, field, subfam, err);
+        if (!ix) die("%s", err);
+    }
+    if (field) fprintf(stderr, "* Total %lld repeats for [%s].\n", (long long)itx_n_repeats_parsed(ix), subfam);
+    else fprintf(stderr, "* Total %lld repeats found.\n", (long long)itx_n_repeats_parsed(ix));
     fprintf(stderr, "* Start to parse the bedGraph file\n");
-    if (itx_scan_cpg(ix, bg, 1, &lines, &inrep, err) != ITX_OK) die("%s", err);
+    if (ngpu == 1 && itx_scan_cpg(ix, bg, 1, &lines, &inrep, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Processed CpG sites: %u\n* CpG sites in Repeats: %u\n", lines, inrep);
     if (itx_sync_counts(ix, err) != ITX_OK) die("%s", err);
     fprintf(stderr, "* Preparing the output file\n");

@@ -659,8 +659,18 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
 #define one64 (neg ? ~0ull : 1ull)
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
+#ifdef ITX_NO_EARLY
+    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = false;
+#else
     const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = P.flags & ITX_SCAN_EARLY;
+#endif
+#ifdef ITX_NO_HINTS
+    const bool f_evict = false, f_evict_pf = false;
+#elif defined(ITX_ALWAYS_EVICT)
+    const bool f_evict = true, f_evict_pf = false;
+#else
     const bool f_evict = P.flags & ITX_SCAN_EVICT, f_evict_pf = P.flags & ITX_SCAN_EVICT_PF;
+#endif
 #define n_elem32 (D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem)
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
     /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no

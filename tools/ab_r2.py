@@ -106,6 +106,20 @@ elif what == "ncu":
         os.environ.update(env)
         ix.reset(); ix.scan_bam_device(h, dbuf, n, opts)
         print("launched", tag, flush=True)
+elif what == "e2e1":
+    # ONE BGZF scan from a pinned image (for ncu on k_inflate / k_lz_resolve); AB_READS sizes the file
+    hbuf, n, nrec, hl = make_stream(0, reads)
+    bam = os.path.join(wd, "reads1.bam")
+    assert S.lib().synth_write_bam(bam.encode(), hbuf, hl, hbuf + hl, n - hl, 1, ncpu) == 0
+    L.itx_host_free_pinned(hbuf)
+    fsz = os.path.getsize(bam)
+    pin = L.itx_host_alloc_pinned(fsz + 64)
+    with open(bam, "rb") as f:
+        assert f.readinto((C.c_char * fsz).from_address(pin)) == fsz
+    for i in range(2):
+        t = time.perf_counter()
+        ix.reset(); got = ix.scan_bgzf_memory(pin, fsz, opts)
+        print("scan %d: %.1f ms, %d records" % (i, 1e3 * (time.perf_counter() - t), got[0] + got[1]), flush=True)
 elif what == "e2e":
     hbuf, n, nrec, hl = make_stream(0, reads)
     bam = os.path.join(wd, "reads.bam")
