@@ -50,7 +50,7 @@ struct itx_cuda {
                                                                * cnt[16] u64, status[8] u32, first bad launch group u32, then (byte 256) the first ITX_SEEN_FAST unknown-tid marks */
     unsigned long long *d_xa_q; uint64_t xa_cap; uint32_t *d_xa_n;      /* k_scan -> k_xa: record offsets of the reads whose XA:Z alternates have to be looked at */
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
-    int scan_ctas[4];                                         /* resident CTAs per SM of the k_scan instances */
+    int scan_ctas[6];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
     int decode_ctas;                        /* resident CTAs per SM of k_decode_span */
     itx_trace *d_trace; uint64_t trace_cap;
@@ -602,17 +602,17 @@ static bool fused_smem_hist(const scan_ctx *sc) {
     const itx_cuda *cu = sc->ix->cu;
     return (sc->o.filter == 0 && cu->D.stat_mode) && (scan_warps() == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + hist_bytes(cu) + 1024 <= cu->smem_optin;
 }
-template <bool SH, int NW>
+template <bool SH, int NW, bool AB>
 static void launch_scan_kernel(itx_cuda *cu, const itx_scan_args &P, uint32_t n, size_t smem, int *ctas) {
     if (!*ctas) {
-        cudaFuncSetAttribute(k_scan<SH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_scan<SH, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_scan<SH, NW, AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_scan<SH, NW, AB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<SH, NW>, NW * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<SH, NW, AB>, NW * 32, smem);
         *ctas = nb > 0 ? nb : 1;
     }
     const uint32_t want = (n + NW - 1) / NW, most = (uint32_t)(cu->sm_count * *ctas);
-    k_scan<SH, NW><<<want < most ? want : most, NW * 32, smem, cu->stream>>>(P);
+    k_scan<SH, NW, AB><<<want < most ? want : most, NW * 32, smem, cu->stream>>>(P);
 }
 static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, uint64_t avail, uint64_t len, uint64_t own, int sign) {
     itx_cuda *cu = sc->ix->cu;
@@ -622,11 +622,16 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
     const bool sh = fused_smem_hist(sc);
     const int nw = scan_warps();
     const size_t smem = (nw == 8 ? ITX_SCAN_SMEM_BASE(8) : ITX_SCAN_SMEM_BASE(ITX_SCAN_NW)) + (sh ? hist_bytes(cu) : 0);
-    P.flags = ITX_SCAN_DEFAULT;
-    { const char *v = getenv("ITX_SCAN_FLAGS"); if (v) P.flags = (uint32_t)strtoul(v, NULL, 0); }      /* A/B switches: the counts do not depend on them */
-    int *ctas = &cu->scan_ctas[(nw == 8 ? 2 : 0) + (sh ? 1 : 0)];
-    if (nw == 8) { if (sh) launch_scan_kernel<true, 8>(cu, P, n, smem, ctas); else launch_scan_kernel<false, 8>(cu, P, n, smem, ctas); }
-    else { if (sh) launch_scan_kernel<true, ITX_SCAN_NW>(cu, P, n, smem, ctas); else launch_scan_kernel<false, ITX_SCAN_NW>(cu, P, n, smem, ctas); }
+    /* the product kernel has its switches compiled in; ITX_SCAN_FLAGS / ITX_SCAN_WARPS select the kernel that reads them at run time
+     * (tests, A/B measurements: the counts do not depend on them) */
+    P.flags = ITX_SCAN_PRODUCT;
+    const char *fv = getenv("ITX_SCAN_FLAGS");
+    const bool ab = fv != NULL || nw == 8;
+    if (fv) P.flags = (uint32_t)strtoul(fv, NULL, 0);
+    int *ctas = &cu->scan_ctas[(ab ? (nw == 8 ? 4 : 2) : 0) + (sh ? 1 : 0)];
+    if (!ab) { if (sh) launch_scan_kernel<true, ITX_SCAN_NW, false>(cu, P, n, smem, ctas); else launch_scan_kernel<false, ITX_SCAN_NW, false>(cu, P, n, smem, ctas); }
+    else if (nw == 8) { if (sh) launch_scan_kernel<true, 8, true>(cu, P, n, smem, ctas); else launch_scan_kernel<false, 8, true>(cu, P, n, smem, ctas); }
+    else { if (sh) launch_scan_kernel<true, ITX_SCAN_NW, true>(cu, P, n, smem, ctas); else launch_scan_kernel<false, ITX_SCAN_NW, true>(cu, P, n, smem, ctas); }
     sc->n_launch++;
     if (sc->o.diffSubfam) {
         /* the reads k_scan queued (XA:Z alternates): mapped2diffSubfam and their accumulation, with the launch's sign */
@@ -1093,7 +1098,10 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             const uint64_t est = (flen - r_begin) / 2048 + 64;
             if (GROUP > est) GROUP = (est + 31) / 32 * 32;
         }
-        uint64_t TAIL_GROUP = GROUP / 4 < 32 ? 32 : GROUP / 4 / 32 * 32;
+        /* smaller groups towards the end of the file were measured too (ITX_INF_TAIL_GROUP): 153 ms against 147.5 ms without them -- the
+         * throughput of the inflate passes, not the latency of the last group, bounds a large file.  A group that is small anyway (a
+         * small file, the last blocks of a large one) runs 8 blocks per warp: shorter rounds, lower latency per block. */
+        uint64_t TAIL_GROUP = GROUP;
         { const int v = env_int("ITX_INF_TAIL_GROUP", 0); if (v >= 32) TAIL_GROUP = (uint64_t)v / 32 * 32; if (TAIL_GROUP > GROUP) TAIL_GROUP = GROUP; }
         const int LANES = env_int("ITX_INF_LANES", ITX_INF_LANES_DEFAULT), TAIL_LANES = env_int("ITX_INF_TAIL_LANES", ITX_INF_TAIL_LANES_DEFAULT);
         const uint64_t min_lanes = (uint64_t)(LANES < TAIL_LANES ? LANES : TAIL_LANES) >= 8 ? (uint64_t)(LANES < TAIL_LANES ? LANES : TAIL_LANES) : 8;
@@ -1106,6 +1114,11 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         }
         const uint64_t tab_stride = cu->d_tabs_threads / ITX_INF_STREAMS * ITX_T_CELLS;           /* cells per stream */
         int lz_ctas = 1;
+        /* ITX_LZ=1: k_lz_jump (pointer jumping, every thread busy, 192 KiB of shared memory per block in flight); default: k_lz_resolve
+         * (ordered batches, 64 KiB).  Measured on the B200 (3.4 GB file): the same 151 ms end to end -- k_lz_jump is several times
+         * faster per block, but its CTA needs a whole SM's shared memory, so it waits for every k_inflate warp there to finish */
+        const bool lz_jump = env_int("ITX_LZ", 0) != 0;
+        cudaFuncSetAttribute(k_lz_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ2_SMEM);
         cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ_SMEM);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_ctas, k_lz_resolve, ITX_LZ_THREADS, ITX_LZ_SMEM);
         if (lz_ctas < 1) lz_ctas = 1;
@@ -1133,8 +1146,13 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             if (ev_ok) cudaEventRecord(wev[2 * nw], st);
             const int lanes = tail ? TAIL_LANES : LANES;
             if (lanes <= 8) launch_inflate<3>(IA, st); else if (lanes <= 16) launch_inflate<4>(IA, st); else launch_inflate<5>(IA, st);
-            uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
-            k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
+            if (lz_jump) {
+                uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count; if (lzb > lzmax) lzb = lzmax;
+                k_lz_jump<<<(unsigned)lzb, ITX_LZ2_THREADS, ITX_LZ2_SMEM, st>>>(IA);
+            } else {
+                uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
+                k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
+            }
             if (ev_ok) { cudaEventRecord(wev[2 * nw + 1], st); nw++; }
             cudaEventRecord(cu->inf_done[gs], st);
             cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0);          /* the scan stream has now waited for every group so far */
@@ -1231,8 +1249,8 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             comp_reader_release(&R, w, hs, n, off, cu->copy_stream);
             cur += off;
             if (own_closed) sc.own = own_total;
-            for (size_t k = 0; k < closes.size(); k++) if (closes[k] > gb0) launch_group(closes[k], closes[k] - gb0 < GROUP);
-            if (ended && nblk > gb0) launch_group(nblk, true);
+            for (size_t k = 0; k < closes.size(); k++) if (closes[k] > gb0) launch_group(closes[k], closes[k] - gb0 <= 4096);
+            if (ended && nblk > gb0) launch_group(nblk, nblk - gb0 <= 4096);
             if (!closes.empty() && !ended) {
                 const uint64_t front = gb0 ? blk[gb0 - 1].uoff + blk[gb0 - 1].isize : 0;          /* what the groups launched so far inflate */
                 uint64_t k_hi = front > MARGIN ? (front - MARGIN) / cu->C : 0;

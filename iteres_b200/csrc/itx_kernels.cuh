@@ -632,7 +632,70 @@ __device__ __forceinline__ unsigned long long itx_effective_exit(const unsigned 
     return x;
 }
 
-template <bool SMEM_HIST, int NW>
+/* A span's first record start, guessed out of its first staged bytes (itx_plausible2's test, 32 offsets per step: the core of every
+ * offset comes out of the stage with plain shared-memory loads and is tested without branches; the second record is looked at for
+ * the survivors).  Once per span, so it is kept out of line: the stage loop is bound by instruction fetch as much as by issue, and
+ * these few hundred instructions are not part of it.  Returns the span-relative offset or 0xffffffff. */
+__device__ __noinline__ uint32_t itx_guess_span(const uint8_t *buf, const uint8_t *g, unsigned long long lo, uint32_t hi, uint32_t nb, unsigned long long len, int32_t n_ref) {
+    const uint32_t lane = threadIdx.x & 31;
+    const itx_src_stage S0{buf, g, lo, nb};
+    uint32_t p = 0xffffffffu;
+    for (uint32_t base = 0; base < hi; base += 32) {
+        const uint32_t d = base + lane;
+        const unsigned long long q = lo + d;
+        bool ok = false;
+        if (d < hi && q + 36 <= len) {
+            uint32_t x[9];
+            if (base + 32u + 40u <= nb) {                     /* warp-uniform: every lane's core lies in the stage */
+                const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
+                uint32_t wv[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++) wv[k] = wq[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
+            } else S0.core(q, x);
+            ok = itx_plausible2_core(S0, x, q, len, n_ref);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
+    }
+    return p;
+}
+/* the XA tag of one record (its type byte, relative to the stage; 0: none): bam_aux_get's walk over the aux area, out of line --
+ * only records whose aux area can hold a list at all get here */
+__device__ __noinline__ uint32_t itx_find_xa_tag(const uint8_t *buf, const uint8_t *g, unsigned long long c_lo64, uint32_t nb, uint32_t rec_rel, uint32_t aux_rel, uint32_t rec_bytes) {
+    const itx_src_stage S{buf, g, c_lo64, nb};
+    const uint64_t rp = c_lo64 + rec_rel, a0 = rp + aux_rel, aend = rp + rec_bytes;
+    const uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
+    return (xa && xa < aend) ? (uint32_t)(xa - c_lo64) : 0u;
+}
+/* the 13 report counters of a warp (8-bit fields of three registers per lane) into the CTA's totals: every 255 rounds, out of line */
+__device__ __noinline__ void itx_flush_counters(uint32_t pa, uint32_t pb, uint32_t pc, unsigned long long *sh_cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t a0_ = __reduce_add_sync(0xffffffffu, pa & 0x00ff00ffu), a1_ = __reduce_add_sync(0xffffffffu, (pa >> 8) & 0x00ff00ffu);
+    const uint32_t b0_ = __reduce_add_sync(0xffffffffu, pb & 0x00ff00ffu), b1_ = __reduce_add_sync(0xffffffffu, (pb >> 8) & 0x00ff00ffu);
+    const uint32_t c0_ = __reduce_add_sync(0xffffffffu, pc & 0x00ff00ffu), c1_ = __reduce_add_sync(0xffffffffu, (pc >> 8) & 0x00ff00ffu);
+    if (lane == 0) {
+        if (a0_ & 0xffffu) atomicAdd(&sh_cnt[0], (unsigned long long)(a0_ & 0xffffu));
+        if (a1_ & 0xffffu) atomicAdd(&sh_cnt[1], (unsigned long long)(a1_ & 0xffffu));
+        if (a0_ >> 16) atomicAdd(&sh_cnt[2], (unsigned long long)(a0_ >> 16));
+        if (a1_ >> 16) atomicAdd(&sh_cnt[3], (unsigned long long)(a1_ >> 16));
+        if (b0_ & 0xffffu) atomicAdd(&sh_cnt[4], (unsigned long long)(b0_ & 0xffffu));
+        if (b1_ & 0xffffu) atomicAdd(&sh_cnt[5], (unsigned long long)(b1_ & 0xffffu));
+        if (b0_ >> 16) atomicAdd(&sh_cnt[6], (unsigned long long)(b0_ >> 16));
+        if (b1_ >> 16) { atomicAdd(&sh_cnt[7], (unsigned long long)(b1_ >> 16)); atomicAdd(&sh_cnt[11], (unsigned long long)(b1_ >> 16)); }
+        if (c0_ & 0xffffu) atomicAdd(&sh_cnt[9], (unsigned long long)(c0_ & 0xffffu));
+        if (c1_ & 0xffffu) atomicAdd(&sh_cnt[10], (unsigned long long)(c1_ & 0xffffu));
+        if (c0_ >> 16) atomicAdd(&sh_cnt[12], (unsigned long long)(c0_ >> 16));
+    }
+}
+/* AB = false: the product build -- the switches above are compile-time constants (ITX_SCAN_PRODUCT), so the paths they would
+ * select between are not in the loop at all (the loop is bound by instruction issue AND fetch: every instruction that is not
+ * there helps); AB = true: the switches are read from P.flags (tests and measurements: every combination gives the same counts) */
+#ifndef ITX_SCAN_PRODUCT
+#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT)
+#endif
+template <bool SMEM_HIST, int NW, bool AB>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
     extern __shared__ __align__(128) uint8_t itx_smem[];
     __shared__ unsigned long long sh_cnt[13];
@@ -658,43 +721,15 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
 #define minus_one (neg ? 1u : 0xffffffffu)
 #define one64 (neg ? ~0ull : 1ull)
     const bool stat = A.o.filter == 0 && D.stat_mode;
-    const bool f_prefetch = P.flags & ITX_SCAN_PREFETCH, f_dom = P.flags & ITX_SCAN_DOMSIZE, f_win = P.flags & ITX_SCAN_WINDOW;
-#ifdef ITX_NO_EARLY
-    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = false;
-#else
-    const bool f_ahead = f_win && (P.flags & ITX_SCAN_WINAHEAD), f_early = P.flags & ITX_SCAN_EARLY;
-#endif
-#ifdef ITX_NO_HINTS
-    const bool f_evict = false, f_evict_pf = false;
-#elif defined(ITX_ALWAYS_EVICT)
-    const bool f_evict = true, f_evict_pf = false;
-#else
-    const bool f_evict = P.flags & ITX_SCAN_EVICT, f_evict_pf = P.flags & ITX_SCAN_EVICT_PF;
-#endif
+    const uint32_t flags = AB ? P.flags : (uint32_t)ITX_SCAN_PRODUCT;
+    const bool f_prefetch = flags & ITX_SCAN_PREFETCH, f_dom = flags & ITX_SCAN_DOMSIZE, f_win = flags & ITX_SCAN_WINDOW;
+    const bool f_ahead = f_win && (flags & ITX_SCAN_WINAHEAD), f_early = flags & ITX_SCAN_EARLY;
+    const bool f_evict = flags & ITX_SCAN_EVICT, f_evict_pf = flags & ITX_SCAN_EVICT_PF;
 #define n_elem32 (D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem)
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
     /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no
      * popcounts); the fields are summed over the warp and added to the CTA's totals before any of them can reach 256 */
     uint32_t pa = 0, pb = 0, pc = 0, n_rounds = 0;
-#define ITX_SCAN_FLUSH_COUNTERS() do { \
-        const uint32_t a0_ = __reduce_add_sync(0xffffffffu, pa & 0x00ff00ffu), a1_ = __reduce_add_sync(0xffffffffu, (pa >> 8) & 0x00ff00ffu); \
-        const uint32_t b0_ = __reduce_add_sync(0xffffffffu, pb & 0x00ff00ffu), b1_ = __reduce_add_sync(0xffffffffu, (pb >> 8) & 0x00ff00ffu); \
-        const uint32_t c0_ = __reduce_add_sync(0xffffffffu, pc & 0x00ff00ffu), c1_ = __reduce_add_sync(0xffffffffu, (pc >> 8) & 0x00ff00ffu); \
-        if (lane == 0) { \
-            if (a0_ & 0xffffu) atomicAdd(&sh_cnt[0], (unsigned long long)(a0_ & 0xffffu)); \
-            if (a1_ & 0xffffu) atomicAdd(&sh_cnt[1], (unsigned long long)(a1_ & 0xffffu)); \
-            if (a0_ >> 16) atomicAdd(&sh_cnt[2], (unsigned long long)(a0_ >> 16)); \
-            if (a1_ >> 16) atomicAdd(&sh_cnt[3], (unsigned long long)(a1_ >> 16)); \
-            if (b0_ & 0xffffu) atomicAdd(&sh_cnt[4], (unsigned long long)(b0_ & 0xffffu)); \
-            if (b1_ & 0xffffu) atomicAdd(&sh_cnt[5], (unsigned long long)(b1_ & 0xffffu)); \
-            if (b0_ >> 16) atomicAdd(&sh_cnt[6], (unsigned long long)(b0_ >> 16)); \
-            if (b1_ >> 16) { atomicAdd(&sh_cnt[7], (unsigned long long)(b1_ >> 16)); atomicAdd(&sh_cnt[11], (unsigned long long)(b1_ >> 16)); } \
-            if (c0_ & 0xffffu) atomicAdd(&sh_cnt[9], (unsigned long long)(c0_ & 0xffffu)); \
-            if (c1_ & 0xffffu) atomicAdd(&sh_cnt[10], (unsigned long long)(c1_ & 0xffffu)); \
-            if (c0_ >> 16) atomicAdd(&sh_cnt[12], (unsigned long long)(c0_ >> 16)); \
-        } \
-        pa = pb = pc = 0; n_rounds = 0; \
-    } while (0)
     /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream), and what
      * the stage after it adds on its way into L2 meanwhile; the caller has made sure that every lane is done with the old bytes */
 #define ITX_SCAN_ISSUE(c_lo_, rest_, nb_out_) do { \
@@ -753,28 +788,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 staged = c_lo; inflight = 0xffffffffu;
             }
             if (guess) {
-                /* itx_plausible2's test, 32 offsets per step: the core of every offset comes out of the stage with plain
-                 * shared-memory loads and is tested without branches; the second record is looked at for the survivors */
-                const itx_src_stage S0{buf, A.b, lo, nb};
-                for (uint32_t base = 0; base < hi; base += 32) {
-                    const uint32_t d = base + lane;
-                    const unsigned long long q = lo + d;
-                    bool ok = false;
-                    if (d < hi && q + 36 <= A.len) {
-                        uint32_t x[9];
-                        if (base + 32u + 40u <= nb) {                     /* warp-uniform: every lane's core lies in the stage */
-                            const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
-                            uint32_t wv[10];
-#pragma unroll
-                            for (int k = 0; k < 10; k++) wv[k] = wq[k];
-#pragma unroll
-                            for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
-                        } else S0.core(q, x);
-                        ok = itx_plausible2_core(S0, x, q, A.len, A.n_ref);
-                    }
-                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                    if (m) { p = base + (uint32_t)__ffs((int)m) - 1; break; }
-                }
+                p = itx_guess_span(buf, A.b, lo, hi, nb, A.len, A.n_ref);
                 if (lane == 0) A.entry[i] = p == 0xffffffffu ? ITX_OFF_NONE : lo + p;
                 guess = false;
                 continue;
@@ -823,15 +837,22 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 if (valid) {
                     const unsigned long long rp = c_lo64 + pos[j];
                     uint32_t x[9];
-                    S.core(rp, x);
+                    {   /* the chain walk has made sure that the 36 bytes of the core lie inside the stream, and a record starts inside the
+                         * stage: they are in the staged bytes -- no bounds test, no path to global memory */
+                        const uint32_t d = pos[j];
+                        const uint32_t *wq = reinterpret_cast<const uint32_t *>(buf + (d & ~3u)); const uint32_t sh = (d & 3u) * 8u;
+                        uint32_t wv[10];
+#pragma unroll
+                        for (int k = 0; k < 10; k++) wv[k] = wq[k];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
+                    }
                     T = itx_decode_record<itx_src_stage, false>(S, rp, x, 0u, A.tid, A.n_ref, A.o);      /* XA is looked for right here, below */
                     if (A.o.diffSubfam && (T.info & ITX_F_FRAG) && (T.info & ITX_CHROM_MASK) != ITX_CHROM_NONE) {
-                        uint64_t a0, aend; itx_aux_range(rp, x, &a0, &aend);
                         /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
-                        if (aend - a0 >= 5) {
-                            const uint64_t xa = itx_aux_find(S, a0, aend, 'X', 'A');
-                            if (xa && xa < aend) xa_rel = (uint32_t)(xa - c_lo64);
-                        }
+                        const uint32_t lq = x[3] & 0xffu, nc = x[4] & 0xffffu; const int32_t ls = (int32_t)x[5];
+                        const int64_t fixed = 36ll + lq + 4ll * nc + (int64_t)ls + (int64_t)((ls + 1) / 2);
+                        if (fixed >= 36 && fixed + 5 <= 4ll + (int64_t)x[0]) xa_rel = itx_find_xa_tag(buf, A.b, c_lo64, nb, pos[j], (uint32_t)fixed, x[0] + 4u);
                     }
                 }
                 /* the last round of a stage is done with the staged bytes: the next stage's copy starts now */
@@ -907,7 +928,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                 }
                 const bool counted = sel >= 0 && !diffsub;
                 pc += (counted ? 1u : 0u) | ((counted && uniq ? 1u : 0u) << 8) | ((diffsub ? 1u : 0u) << 16);      /* reads_repeat, reads_repeat_unique, reads_diff_subfam */
-                if (++n_rounds == 255u) ITX_SCAN_FLUSH_COUNTERS();
+                if (++n_rounds == 255u) { itx_flush_counters(pa, pb, pc, sh_cnt); pa = pb = pc = 0; n_rounds = 0; }
                 if (counted) {
                     if (stat) {
                         const uint32_t wd = (uint32_t)sel - wbase;
@@ -956,7 +977,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         if (lane == 0) A.exit_[i] = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
     }
     itx_cp_async_wait_all();                                   /* a window fetched ahead and never used */
-    ITX_SCAN_FLUSH_COUNTERS();
+    itx_flush_counters(pa, pb, pc, sh_cnt);
     __syncthreads();
     if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], neg ? 0ull - sh_cnt[threadIdx.x] : sh_cnt[threadIdx.x]);
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) { const uint32_t v = sh_hist[t]; if (v) itx_red_u64(&D.grp[t], neg ? 0ull - (unsigned long long)v : (unsigned long long)v); }
@@ -1452,6 +1473,61 @@ __global__ void __launch_bounds__(ITX_LZ_THREADS) k_lz_resolve(const itx_inflate
         for (uint32_t i = tid * 16u; i < span; i += ITX_LZ_THREADS * 16u) {
             if (i >= lo && i + 16u <= hi) *reinterpret_cast<uint4 *>(const_cast<uint8_t *>(a0) + i) = *reinterpret_cast<const uint4 *>(itx_lz_buf + i);
             else for (uint32_t j = 0; j < 16u; j++) if (i + j >= lo && i + j < hi) const_cast<uint8_t *>(a0)[i + j] = itx_lz_buf[i + j];
+        }
+        __syncthreads();
+    }
+}
+
+/* Second pass, data-parallel: a CTA per block, EVERY thread busy.  A byte of the block is either a literal (already in place) or
+ * belongs to a listed match, i.e. it is a copy of the byte `dist` before it -- which may itself be a copy.  src[i] = where byte i comes
+ * from (itself for a literal); following src to its fixed point names the literal every byte finally equals, and the chains are
+ * shortened by pointer jumping (src[i] = src[src[i]], all bytes at once), so the number of passes is the LOGARITHM of the longest
+ * chain -- a handful for BAM blocks, 16 at worst (a run of one byte repeated through the whole block).  No ordering between matches
+ * is ever needed, so nothing waits: the block is in and out of shared memory in tens of microseconds.
+ * Shared memory: the block (64 KiB + alignment slack) and src as 16-bit indices (128 KiB): one CTA per SM. */
+#define ITX_LZ2_THREADS 512
+#define ITX_LZ2_SMEM (65536u + 32u + 131072u)
+__global__ void __launch_bounds__(ITX_LZ2_THREADS, 1) k_lz_jump(const itx_inflate_args A) {
+    extern __shared__ __align__(16) uint8_t itx_lz_buf[];
+    uint8_t *data = itx_lz_buf;
+    uint16_t *src = reinterpret_cast<uint16_t *>(itx_lz_buf + 65536u + 32u);
+    const uint32_t tid = threadIdx.x;
+    for (unsigned long long g = blockIdx.x; g < A.nblk; g += gridDim.x) {
+        const uint32_t n = A.m_n[g];
+        if (n == ITX_M_NONE || n == 0) continue;                       /* failed (reported by k_inflate) or nothing to copy */
+        const itx_bgzf_block B = A.blk[A.b0 + g];
+        uint8_t *base = A.out + B.uoff;
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 15u);
+        const uint8_t *a0 = base - skew;                               /* 16-byte aligned; never before the stream buffer */
+        const uint32_t span = (skew + B.isize + 15u) & ~15u;           /* <= 65536 + 16; the stream buffer carries slack past its end */
+        const uint32_t isize = B.isize;
+        const uint32_t *pl = A.m_pl + g * A.m_cap; const uint16_t *md = A.m_d + g * A.m_cap;
+        for (uint32_t i = tid * 16u; i < span; i += ITX_LZ2_THREADS * 16u) *reinterpret_cast<uint4 *>(data + i) = __ldcs(reinterpret_cast<const uint4 *>(a0 + i));
+        for (uint32_t i = tid * 2u; i < isize; i += ITX_LZ2_THREADS * 2u) *reinterpret_cast<uint32_t *>(src + i) = i | ((i + 1u) << 16);      /* every byte its own source */
+        __syncthreads();
+        /* the listed matches: byte pos + j comes from pos + j - dist (a match that overlaps itself chains through its own bytes) */
+        for (uint32_t k = tid; k < n; k += ITX_LZ2_THREADS) {
+            const uint32_t e = __ldcs(pl + k), d = (uint32_t)__ldcs(md + k);
+            const uint32_t pos = e & 0xffffu, len = e >> 16;
+            for (uint32_t j = 0; j < len; j++) src[pos + j] = (uint16_t)(pos + j - d);
+        }
+        __syncthreads();
+        /* pointer jumping until every byte points at a literal */
+        for (;;) {
+            bool changed = false;
+            for (uint32_t i = tid; i < isize; i += ITX_LZ2_THREADS) {
+                const uint32_t s = src[i];
+                if (s != i) { const uint32_t ss = src[s]; if (ss != s) { src[i] = (uint16_t)ss; changed = true; } }
+            }
+            if (!__syncthreads_or(changed ? 1 : 0)) break;
+        }
+        uint8_t *sm = data + skew;
+        for (uint32_t i = tid; i < isize; i += ITX_LZ2_THREADS) { const uint32_t s = src[i]; if (s != i) sm[i] = sm[s]; }      /* a literal is never written here */
+        __syncthreads();
+        const uint32_t lo = skew, hi = skew + isize;
+        for (uint32_t i = tid * 16u; i < span; i += ITX_LZ2_THREADS * 16u) {
+            if (i >= lo && i + 16u <= hi) *reinterpret_cast<uint4 *>(const_cast<uint8_t *>(a0) + i) = *reinterpret_cast<const uint4 *>(data + i);
+            else for (uint32_t j = 0; j < 16u; j++) if (i + j >= lo && i + j < hi) const_cast<uint8_t *>(a0)[i + j] = data[i + j];
         }
         __syncthreads();
     }

@@ -521,7 +521,21 @@ int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_c
     const uint32_t rc = I.run(padded.data() + 4 + skew, in_len, expect);
     if (produced) *produced = I.out_pos;
     if (I.state == ITX_ST_OVERFLOW) return 99;
-    if (defer && rc == ITX_INF_OK) {
+    if (defer == 2 && rc == ITX_INF_OK) {
+        /* k_lz_jump: src[i] = where byte i comes from, pointer jumping until every byte points at a literal, then one gather */
+        const uint32_t n = I.n_match, isize = I.out_pos;
+        std::vector<uint16_t> src(65536 + 2);
+        for (uint32_t i = 0; i < isize; i++) src[i] = (uint16_t)i;
+        for (uint32_t k = 0; k < n; k++) { const uint32_t pos = mpl[k] & 0xffffu, len = mpl[k] >> 16, d = md[k]; for (uint32_t j = 0; j < len; j++) src[pos + j] = (uint16_t)(pos + j - d); }
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (uint32_t i = isize; i-- > 0;) {               /* any order gives the same fixed point; backwards is the least favourable for an in-place sweep */
+                const uint32_t sidx = src[i];
+                if (sidx != i) { const uint32_t ss = src[sidx]; if (ss != sidx) { src[i] = (uint16_t)ss; changed = true; } }
+            }
+        }
+        for (uint32_t i = 0; i < isize && i < out_cap; i++) if (src[i] != i) out[i] = out[src[i]];
+    } else if (defer && rc == ITX_INF_OK) {
         const uint32_t n = I.n_match;
         for (uint32_t k0 = 0; k0 < n; k0 += 32) {
             uint32_t undone = 0;

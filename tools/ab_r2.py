@@ -133,12 +133,10 @@ elif what == "e2e":
         mv = (C.c_char * fsz).from_address(pin)
         assert f.readinto(mv) == fsz
     print("BGZF %.2f GB written and pinned" % (fsz / 1e9), flush=True)
-    variants = [("lanes32 tail8", {}), ("lanes32 tail32 (r1)", {"ITX_INF_TAIL_LANES": "32", "ITX_INF_TAIL_GROUP": "16384"}),
-                ("lanes16 tail8", {"ITX_INF_LANES": "16"}), ("lanes8 tail8", {"ITX_INF_LANES": "8"}),
-                ("lanes16 g8192", {"ITX_INF_LANES": "16", "ITX_INF_GROUP": "8192"}), ("lanes8 g8192", {"ITX_INF_LANES": "8", "ITX_INF_GROUP": "8192"}),
-                ("lanes8 g4096", {"ITX_INF_LANES": "8", "ITX_INF_GROUP": "4096"})]
+    variants = [("lz_jump (default)", {}), ("lz_batches (r1)", {"ITX_LZ": "0"}), ("lz_jump tail32", {"ITX_INF_TAIL_LANES": "32", "ITX_INF_TAIL_GROUP": "16384"}),
+                ("lz_jump g8192", {"ITX_INF_GROUP": "8192"}), ("lz_jump g32768", {"ITX_INF_GROUP": "32768"})]
     for tag, env in variants:
-        for k in ("ITX_INF_LANES", "ITX_INF_TAIL_LANES", "ITX_INF_GROUP", "ITX_INF_TAIL_GROUP", "ITX_TIMING"):
+        for k in ("ITX_INF_LANES", "ITX_INF_TAIL_LANES", "ITX_INF_GROUP", "ITX_INF_TAIL_GROUP", "ITX_TIMING", "ITX_LZ"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for api in ("pinned", "file"):
