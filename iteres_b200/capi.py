@@ -250,6 +250,7 @@ class Index(IndexBase):
         self.L = lib()
         err = C.create_string_buffer(ERRLEN)
         if device is not None:
+            self.L.itx_set_device(device)      # the process-wide default too: itx_dev_alloc / itx_host_alloc_pinned follow it
             self.h = self.L.itx_index_build_on(device, chrom_sizes.encode(), rep_sizes.encode(), rmsk.encode(), filter_field,
                                                filter_name.encode(), err)
         else:

@@ -661,6 +661,13 @@ __device__ __noinline__ uint32_t itx_guess_span(const uint8_t *buf, const uint8_
     }
     return p;
 }
+/* a record that runs past the staged bytes (longer than the margin): decoded with the bounds-tested source, out of line */
+__device__ __noinline__ itx_tuple itx_decode_long(const uint8_t *buf, const uint8_t *g, unsigned long long c_lo64, uint32_t nb, uint32_t rec_rel,
+                                                  const itx_tidinfo *tid, int32_t n_ref, const itx_dev_opts o) {
+    const itx_src_stage S{buf, g, c_lo64, nb};
+    uint32_t x[9]; S.core(c_lo64 + rec_rel, x);
+    return itx_decode_record<itx_src_stage, false>(S, c_lo64 + rec_rel, x, 0u, tid, n_ref, o);
+}
 /* the XA tag of one record (its type byte, relative to the stage; 0: none): bam_aux_get's walk over the aux area, out of line --
  * only records whose aux area can hold a list at all get here */
 __device__ __noinline__ uint32_t itx_find_xa_tag(const uint8_t *buf, const uint8_t *g, unsigned long long c_lo64, uint32_t nb, uint32_t rec_rel, uint32_t aux_rel, uint32_t rec_bytes) {
@@ -847,7 +854,10 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
 #pragma unroll
                         for (int k = 0; k < 9; k++) x[k] = itx_funnel_r(wv[k], wv[k + 1], sh);
                     }
-                    T = itx_decode_record<itx_src_stage, false>(S, rp, x, 0u, A.tid, A.n_ref, A.o);      /* XA is looked for right here, below */
+                    /* a record that lies inside the staged bytes (all but the ones longer than the margin) is read without bounds
+                     * tests; XA is looked for right here, below */
+                    if (pos[j] + 4u + x[0] <= nb) T = itx_decode_record<itx_src_flat, false>(itx_src_flat{buf, c_lo64}, rp, x, 0u, A.tid, A.n_ref, A.o);
+                    else T = itx_decode_long(buf, A.b, c_lo64, nb, pos[j], A.tid, A.n_ref, A.o);
                     if (A.o.diffSubfam && (T.info & ITX_F_FRAG) && (T.info & ITX_CHROM_MASK) != ITX_CHROM_NONE) {
                         /* "XA" + type + at least one character + NUL: a shorter aux area cannot hold a list of alternates */
                         const uint32_t lq = x[3] & 0xffu, nc = x[4] & 0xffffu; const int32_t ls = (int32_t)x[5];
