@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs / strong scaling (A/B runs)")
-    ap.add_argument("--strong-pairs", type=int, default=50_000_000, help="PE-100 pairs in the ONE file of the strong-scaling pass (N > 1)")
+    ap.add_argument("--strong-pairs", type=int, default=40_000_000, help="PE-100 pairs in the ONE file of the strong-scaling pass (N > 1)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--keep", action="store_true")
@@ -706,8 +706,8 @@ def main():
     strong = None
     if not a.no_extra and world == 1:
         extra = extra_configs(a, L, ix, world_s, tables, wd, opts, peak, ncpu, parity)
-    if not a.no_extra and world > 1:
-        strong = strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, max_over_ranks, ncpu)
+    if not a.no_extra:
+        strong = strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, max_over_ranks, ncpu, sum_over_ranks)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -873,40 +873,46 @@ def extra_configs(a, L, ix, world_s, tables, wd, opts, peak, ncpu, parity):
 
 
 # ------------------------------------------------------------------------------------------ ONE PE-100 file over N GPUs
-def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, max_over_ranks, ncpu):
+def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, max_over_ranks, ncpu, sum_over_ranks):
     import synth as S
     bam = os.path.join(wd, "strong_pe100.bam")
     t0 = time.perf_counter()
-    total_rec = 0
-    if rank == 0:
-        # generated and written in slices so that the host never holds more than a few GB of it
-        hdr = world_s.header()
-        nch = world_s.n_chunks(a.strong_pairs)
-        with open(bam, "wb"):
-            pass
-        per = max(1, nch // 16)
-        import numpy as np
-        first = True
-        tmp = bam + ".part"
-        for c0 in range(0, nch, per):
-            c1 = min(nch, c0 + per)
-            sz, nrec = world_s.records_size(2, a.strong_pairs, c0, c1, ncpu)
+    # ONE coordinate-sorted file, written once: every rank generates and compresses its slice of the generator's chunks (the header goes
+    # into the first part only; BGZF parts concatenate once the empty end-of-file block of all but the last is dropped), rank 0 joins them
+    import numpy as np
+    hdr = world_s.header()
+    nch = world_s.n_chunks(a.strong_pairs)
+    c0, c1 = rank * nch // world, (rank + 1) * nch // world
+    gth = max(1, ncpu // world)
+    part = "%s.part%d" % (bam, rank)
+    my_rec = 0
+    with open(part, "wb") as fpart:
+        per = max(1, (c1 - c0 + 3) // 4)                   # in a few slices, so that no rank holds more than a couple of GB at a time
+        tmp = part + ".tmp"
+        for k0 in range(c0, c1, per):
+            k1 = min(c1, k0 + per)
+            sz, nrec = world_s.records_size(2, a.strong_pairs, k0, k1, gth)
             buf = np.zeros(sz + 64, dtype=np.uint8)
-            assert world_s.records_into(buf.ctypes.data, 2, a.strong_pairs, c0, c1, ncpu) == sz
-            # the header goes into the first slice only; BGZF files concatenate (every slice ends on a block boundary) once the
-            # empty end-of-file block of all but the last slice is dropped
-            rc = S.lib().synth_write_bam(tmp.encode(), hdr.ctypes.data, len(hdr) if first else 0, buf.ctypes.data, sz, 1, ncpu)
+            assert world_s.records_into(buf.ctypes.data, 2, a.strong_pairs, k0, k1, gth) == sz
+            rc = S.lib().synth_write_bam(tmp.encode(), hdr.ctypes.data, len(hdr) if k0 == 0 else 0, buf.ctypes.data, sz, 1, gth)
             assert rc == 0
             with open(tmp, "rb") as f:
                 data = f.read()
-            if c1 < nch and data.endswith(BGZF_EOF):
+            if k1 < nch and data.endswith(BGZF_EOF):
                 data = data[:-len(BGZF_EOF)]
-            with open(bam, "ab") as f:
-                f.write(data)
-            total_rec += nrec
-            first = False
-        os.unlink(tmp)
+            fpart.write(data)
+            my_rec += nrec
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+    barrier()
+    if rank == 0:
+        with open(bam, "wb") as out:
+            for r in range(world):
+                with open("%s.part%d" % (bam, r), "rb") as f:
+                    shutil.copyfileobj(f, out, 64 << 20)
+                os.unlink("%s.part%d" % (bam, r))
         log("strong scaling: ONE PE-100 file, %d M pairs, %.2f GB BGZF (%.1f s)" % (a.strong_pairs // 1_000_000, os.path.getsize(bam) / 1e9, time.perf_counter() - t0))
+    total_rec = int(sum_over_ranks(my_rec))
     barrier()
     times = []
     got = None
@@ -914,8 +920,11 @@ def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, ma
         barrier()
         t1 = time.perf_counter()
         ix.reset()
-        ix.scan_alignments_shard(bam, opts)
-        got = ix.allreduce_counts()
+        if world > 1:
+            ix.scan_alignments_shard(bam, opts)
+            got = ix.allreduce_counts()
+        else:
+            got = ix.scan_alignments(bam, opts)              # the 1-GPU point of the same curve: the whole file, one device
         ix._dirty = True
         ix.sync()
         dt = max_over_ranks(time.perf_counter() - t1)
@@ -929,7 +938,8 @@ def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, ma
     return {"workload": "iteres stat on ONE coordinate-sorted PE-100 BGZF file, %d M pairs (%d M records, %.2f GB; BASELINE names 500 M: bounded by the bench's time budget), the same file at every N" % (
                 a.strong_pairs // 1_000_000, total_rec // 1_000_000, os.path.getsize(bam) / 1e9),
             "scaling": "strong", "n_gpus": world, "value": total_rec / t, "unit": "read ends/s", "s_per_step": t, "steps": len(times),
-            "api": "itx_scan_alignments_shard (BGZF block ranges, guessed first records, NCCL all-gather chain check) + itx_comm_allreduce_counts + itx_sync_counts",
+            "api": ("itx_scan_alignments_shard (BGZF block ranges, guessed first records, NCCL all-gather chain check) + itx_comm_allreduce_counts + itx_sync_counts"
+                    if world > 1 else "itx_scan_alignments + itx_sync_counts (one device: the whole file)"),
             "file": "on tmpfs / page-cache resident", "ranks_rescanned_after_chain_check": int(pr["n_bad_chunks"]),
             "counters": {"records": int(got[0] + got[1]), "fragments": int(got[6]), "in_repeats": int(got[9])}}
 
