@@ -1028,6 +1028,8 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     itx_cuda *cu = ix->cu;
     const uint64_t flen = S->len;
     int rc = ITX_OK;
+    /* every stream / event call of the pipeline is checked where it is made: a failure is reported with its line, not as a later launch error */
+#define EV(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess && rc == ITX_OK) { snprintf(err, ITX_ERRLEN, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); rc = ITX_ENODEV; } } while (0)
     const bool timing = getenv("ITX_TIMING") != NULL; const double tm0 = now_ms();
     uint64_t Wc = 64ull << 20;                               /* compressed bytes per window */
     { const int mb = env_int("ITX_COMP_WINDOW_MB", 0); if (mb > 0) Wc = (uint64_t)mb << 20; }
@@ -1137,15 +1139,16 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         /* hand blocks [gb0, upto) to the device; everything they need has been enqueued on the copy stream before `copied` was recorded */
         auto launch_group = [&](uint64_t upto, bool tail) {
             const int gs = (int)(n_groups % ITX_INF_STREAMS); cudaStream_t st = cu->inf_stream[gs];
-            cudaStreamWaitEvent(st, copied, 0);
-            if (n_groups == 0) cudaStreamWaitEvent(st, begin_ev, 0);           /* the status words are zeroed on the scan stream */
+            EV(cudaStreamWaitEvent(st, copied, 0));
+            if (n_groups == 0) EV(cudaStreamWaitEvent(st, begin_ev, 0));           /* the status words are zeroed on the scan stream */
             itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = upto - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
             IA.tabs = cu->d_tabs + (size_t)gs * tab_stride;
             IA.m_pl = cu->d_mpl + (size_t)gs * m_stride * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * m_stride * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * m_stride; IA.m_cap = ITX_M_WORST;
             const bool ev_ok = 2 * nw + 1 < cu->inf_ev_made;
-            if (ev_ok) cudaEventRecord(wev[2 * nw], st);
+            if (ev_ok) EV(cudaEventRecord(wev[2 * nw], st));
             const int lanes = tail ? TAIL_LANES : LANES;
             if (lanes <= 8) launch_inflate<3>(IA, st); else if (lanes <= 16) launch_inflate<4>(IA, st); else launch_inflate<5>(IA, st);
+            EV(cudaGetLastError());
             if (lz_jump) {
                 uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count; if (lzb > lzmax) lzb = lzmax;
                 k_lz_jump<<<(unsigned)lzb, ITX_LZ2_THREADS, ITX_LZ2_SMEM, st>>>(IA);
@@ -1153,15 +1156,16 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count * (uint64_t)lz_ctas; if (lzb > lzmax) lzb = lzmax;
                 k_lz_resolve<<<(unsigned)lzb, ITX_LZ_THREADS, ITX_LZ_SMEM, st>>>(IA);
             }
-            if (ev_ok) { cudaEventRecord(wev[2 * nw + 1], st); nw++; }
-            cudaEventRecord(cu->inf_done[gs], st);
-            cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0);          /* the scan stream has now waited for every group so far */
+            EV(cudaGetLastError());
+            if (ev_ok) { EV(cudaEventRecord(wev[2 * nw + 1], st)); nw++; }
+            EV(cudaEventRecord(cu->inf_done[gs], st));
+            EV(cudaStreamWaitEvent(cu->stream, cu->inf_done[gs], 0));          /* the scan stream has now waited for every group so far */
             sc.n_launch += 2;
             {   /* an event of its own per group (GQ of them, reused round robin) for the ring: a window may only land on bytes whose groups are done */
                 const int gi = (int)(n_groups % GQ);
                 if (!cu->grp_ev[gi]) cudaEventCreateWithFlags(&cu->grp_ev[gi], cudaEventDisableTiming);
                 else if (n_groups >= GQ) cudaEventSynchronize(cu->grp_ev[gi]);           /* GQ groups back: long done */
-                cudaEventRecord(cu->grp_ev[gi], st);
+                EV(cudaEventRecord(cu->grp_ev[gi], st));
                 g_abs[gi] = g_abs0;
             }
             gb0 = upto; n_groups++; g_open_has_abs = false;
@@ -1211,7 +1215,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 const uint64_t carry0 = (sharded && sh->rank > 0) ? sh->entry : ITX_CARRY_HEADER;
                 if ((rc = scan_begin(&sc, ix, h, cu->d_stream, 1ull << 62, o, guess < ix->tune_window ? guess : ix->tune_window, err, 0, carry0))) break;
                 begun = true;
-                cudaEventRecord(begin_ev, cu->stream);
+                EV(cudaEventRecord(begin_ev, cu->stream));
                 if (off) typical_group_bytes = (uint64_t)((double)GROUP * (double)off / (double)(nblk ? nblk : 1));
                 if (timing) fprintf(stderr, "[itx timing] first window read, header parsed, buffers ready at %.1f ms\n", now_ms() - tm0);
             }
@@ -1237,7 +1241,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                     if (gb0 < nb_before && g_abs0 < low) launch_group(nb_before, false);             /* the open group itself is in the way: out it goes */
                     if (!g_open_has_abs) { g_abs0 = cabs; g_open_has_abs = true; }
                     if (g_waited + GQ < n_groups) g_waited = n_groups - GQ;                         /* older ones were waited for on the host */
-                    while (g_waited < n_groups && g_abs[g_waited % GQ] < low) { cudaStreamWaitEvent(cu->copy_stream, cu->grp_ev[g_waited % GQ], 0); g_waited++; }
+                    while (g_waited < n_groups && g_abs[g_waited % GQ] < low) { EV(cudaStreamWaitEvent(cu->copy_stream, cu->grp_ev[g_waited % GQ], 0)); g_waited++; }
                 }
                 const uint64_t cpos = cabs % ring_cap;
                 for (uint64_t k = nb_before; k < nblk; k++) blk[k].coff += cpos;
@@ -1245,7 +1249,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                     cudaMemcpyAsync(cu->d_blk + nb_before, blk + nb_before, (nblk - nb_before) * sizeof(itx_bgzf_block), cudaMemcpyHostToDevice, cu->copy_stream) != cudaSuccess) { rc = ITX_ENODEV; break; }
                 cabs += off;
             }
-            cudaEventRecord(copied, cu->copy_stream);
+            EV(cudaEventRecord(copied, cu->copy_stream));
             comp_reader_release(&R, w, hs, n, off, cu->copy_stream);
             cur += off;
             if (own_closed) sc.own = own_total;
@@ -1296,6 +1300,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     itx_bam_header_free(h);
     return rc;
 }
+#undef EV
 
 static bool inflate_on_host(void) { const char *m = getenv("ITX_INFLATE"); return m && strcmp(m, "host") == 0; }   /* A/B switch: zlib on the host threads */
 static int scan_bgzf_host_inflate(itx_index *ix, const uint8_t *bgzf, uint64_t flen, const itx_scan_opts *o, uint64_t cnt[13], char *err, int nth);

@@ -238,3 +238,38 @@ def test_cpg_parts_sum_to_the_whole(tmp_path):
     for ix in ixs + [whole]:
         ix.close()
     s.close()
+
+
+@pytest.mark.parametrize("api", ["file", "pinned"])
+def test_compressed_ring_wraps(api, tmp_path, monkeypatch):
+    """a compressed ring much smaller than the file (1 MiB windows, 4 MiB ring, groups of 64 blocks): windows land on bytes whose
+    inflate groups are done, open groups that are in the way are closed early -- and the stream, the counts and the tables are
+    those of the unbounded run"""
+    d = str(tmp_path)
+    s = synth.Synth(1, 60000, seed=24)
+    tabs = s.write_tables(d)
+    bam = os.path.join(d, "reads.bam")
+    n, nrec = s.write_bam(bam, 2, 150000, level=1, threads=4)
+    assert os.path.getsize(bam) > 12 << 20
+    whole = capi.Index(*tabs)
+    want = whole.scan_alignments(bam, capi.default_opts())
+    stream_want = whole.stream_fetch(n)
+    monkeypatch.setenv("ITX_COMP_WINDOW_MB", "1")
+    monkeypatch.setenv("ITX_COMP_RING_MB", "4")
+    monkeypatch.setenv("ITX_INF_GROUP", "64")
+    ix = capi.Index(*tabs)
+    if api == "file":
+        got = ix.scan_alignments(bam, capi.default_opts())
+    else:
+        L = capi.lib()
+        fsz = os.path.getsize(bam)
+        pin = L.itx_host_alloc_pinned(fsz + 64)
+        with open(bam, "rb") as f:
+            assert f.readinto((C.c_char * fsz).from_address(pin)) == fsz
+        got = ix.scan_bgzf_memory(pin, fsz, capi.default_opts())
+        L.itx_host_free_pinned(pin)
+    assert got == want and got[0] + got[1] == nrec
+    assert ix.stream_fetch(n) == stream_want                    # what the device inflated, byte for byte
+    for which in range(3):
+        assert ix.table(which) == whole.table(which)
+    ix.close(); whole.close(); s.close()
