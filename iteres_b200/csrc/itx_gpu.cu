@@ -1037,7 +1037,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     if (Wc < (1u << 20)) Wc = 1u << 20;
     cudaEvent_t copied = NULL, begin_ev = NULL;
     enum { MAXW = 256 }; cudaEvent_t *wev = NULL; int nw = 0;
-    itx_bgzf_block *blk = NULL; uint64_t *foff = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;
+    itx_bgzf_block *blk = NULL; uint64_t *foff = NULL, *babs = NULL; uint64_t nblk = 0, blk_cap = 0, total = 0;      /* per block: file offset, absolute (ever-growing) ring position */
     itx_bam_header *h = NULL;
     scan_ctx sc; bool begun = false;
     comp_reader R; bool reader_open = false;
@@ -1134,8 +1134,8 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         }
         const uint64_t m_stride = cu->d_m_slots / ITX_INF_STREAMS;
         const uint64_t MARGIN = (64ull << 20) + 65536;      /* a record is at most 2^26 bytes long: chunks this far behind the inflated front are safe to scan */
-        uint64_t cur = r_begin, gb0 = 0, n_groups = 0, cabs = 0, g_abs0 = 0, own_total = ~0ull, typical_group_bytes = GROUP * 24576ull;
-        bool ended = false, own_closed = false, g_open_has_abs = false;
+        uint64_t cur = r_begin, gb0 = 0, n_groups = 0, cabs = 0, own_total = ~0ull, typical_group_bytes = GROUP * 24576ull;
+        bool ended = false, own_closed = false;
         /* hand blocks [gb0, upto) to the device; everything they need has been enqueued on the copy stream before `copied` was recorded */
         auto launch_group = [&](uint64_t upto, bool tail) {
             const int gs = (int)(n_groups % ITX_INF_STREAMS); cudaStream_t st = cu->inf_stream[gs];
@@ -1166,9 +1166,9 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 if (!cu->grp_ev[gi]) cudaEventCreateWithFlags(&cu->grp_ev[gi], cudaEventDisableTiming);
                 else if (n_groups >= GQ) cudaEventSynchronize(cu->grp_ev[gi]);           /* GQ groups back: long done */
                 EV(cudaEventRecord(cu->grp_ev[gi], st));
-                g_abs[gi] = g_abs0;
+                g_abs[gi] = babs[gb0];                                      /* where the group's first block lies */
             }
-            gb0 = upto; n_groups++; g_open_has_abs = false;
+            gb0 = upto; n_groups++;
         };
         for (uint64_t w = 0; !ended && rc == ITX_OK; w++) {
             const uint8_t *hs = NULL; uint64_t n = 0;
@@ -1189,7 +1189,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
                 if (isize == 0 || isize > 65536) { ended = true; break; }              /* an empty block ends the data (bgzf.c:539-546) */
                 if (sharded && !own_closed && cur + off >= r_end) { own_closed = true; own_total = total; }
                 if (own_closed && total - own_total >= sh->margin) { ended = true; sh->more_after = 1; break; }      /* the straddling record has its room */
-                if (nblk == blk_cap) { blk_cap = blk_cap ? blk_cap * 2 : 4096; blk = (itx_bgzf_block *)realloc(blk, sizeof(itx_bgzf_block) * blk_cap); foff = (uint64_t *)realloc(foff, 8 * blk_cap); }
+                if (nblk == blk_cap) { blk_cap = blk_cap ? blk_cap * 2 : 4096; blk = (itx_bgzf_block *)realloc(blk, sizeof(itx_bgzf_block) * blk_cap); foff = (uint64_t *)realloc(foff, 8 * blk_cap); babs = (uint64_t *)realloc(babs, 8 * blk_cap); }
                 blk[nblk].coff = off; blk[nblk].csize = bsize; blk[nblk].isize = isize; blk[nblk].uoff = total; foff[nblk] = cur + off;
                 nblk++; total += isize; off += bsize;
                 /* near the end of the file (or of the own range) groups close early */
@@ -1235,11 +1235,10 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             if (off) {
                 /* the window's place in the ring; whatever lies there belongs to groups that must be done first */
                 if (cabs % ring_cap + off > ring_cap) cabs += ring_cap - cabs % ring_cap;          /* not across the ring's end */
-                if (!g_open_has_abs) { g_abs0 = cabs; g_open_has_abs = true; }
+                for (uint64_t k = nb_before; k < nblk; k++) babs[k] = cabs + blk[k].coff;           /* (coff is still relative to the window) */
                 if (cabs + off > ring_cap) {
                     const uint64_t low = cabs + off - ring_cap;                                      /* absolute positions below this one are overwritten */
-                    if (gb0 < nb_before && g_abs0 < low) launch_group(nb_before, false);             /* the open group itself is in the way: out it goes */
-                    if (!g_open_has_abs) { g_abs0 = cabs; g_open_has_abs = true; }
+                    if (gb0 < nb_before && babs[gb0] < low) launch_group(nb_before, false);          /* the open group itself is in the way: out it goes */
                     if (g_waited + GQ < n_groups) g_waited = n_groups - GQ;                         /* older ones were waited for on the host */
                     while (g_waited < n_groups && g_abs[g_waited % GQ] < low) { EV(cudaStreamWaitEvent(cu->copy_stream, cu->grp_ev[g_waited % GQ], 0)); g_waited++; }
                 }
@@ -1296,7 +1295,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
     if (reader_open) { cudaStreamSynchronize(cu->copy_stream); comp_reader_close(&R); }
     if (copied) cudaEventDestroy(copied);
     if (begin_ev) cudaEventDestroy(begin_ev);
-    free(blk); free(foff);
+    free(blk); free(foff); free(babs);
     itx_bam_header_free(h);
     return rc;
 }
