@@ -605,7 +605,9 @@ static bool fused_smem_hist(const scan_ctx *sc) {
 template <bool SH, int NW, bool AB>
 static void launch_scan_kernel(itx_cuda *cu, const itx_scan_args &P, uint32_t n, size_t smem, int *ctas) {
     if (!*ctas) {
-        cudaFuncSetAttribute(k_scan<SH, NW, AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        /* the device's opt-in maximum, not this index's need: the attribute belongs to the function, and another index of the
+         * same process (other table sizes, another histogram) must not find it lowered */
+        cudaFuncSetAttribute(k_scan<SH, NW, AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cu->smem_optin - 1024);       /* (the kernel has a little static shared memory too) */
         cudaFuncSetAttribute(k_scan<SH, NW, AB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan<SH, NW, AB>, NW * 32, smem);

@@ -666,3 +666,23 @@ def test_bedgraph_text_oddities(parse, worlds, tmp_path, monkeypatch):
         ix.scan_cpg(bad, 0)
     assert "At least 4 fields required, got 3" in str(e.value)
     ix.close()
+
+
+def test_two_indexes_of_different_sizes_in_one_process(worlds):
+    """the scan kernels' shared-memory attribute belongs to the function, not to an index: an index with a larger histogram must
+    still launch after a smaller one has been used (a process that holds several indexes: the bench, a multi-device caller)"""
+    s_big, tabs_big, _ = worlds(1, 60000)          # 1395 subfamilies
+    s_small, tabs_small, _ = worlds(0, 20000)      # 1200 subfamilies
+    buf, n, nrec = s_big.stream(0, 30000)
+    raw_big = buf[:n].tobytes()
+    buf, n, nrec = s_small.stream(0, 30000)
+    raw_small = buf[:n].tobytes()
+    a, b = capi.Index(*tabs_big), capi.Index(*tabs_small)
+    want_a = a.scan_stream(raw_big, capi.default_opts())
+    want_b = b.scan_stream(raw_small, capi.default_opts())
+    a.reset(); b.reset()
+    assert a.scan_stream(raw_big, capi.default_opts()) == want_a
+    assert b.scan_stream(raw_small, capi.default_opts()) == want_b
+    a.reset()
+    assert a.scan_stream(raw_big, capi.default_opts()) == want_a
+    a.close(); b.close()
