@@ -610,6 +610,7 @@ def main():
         k2_bytes = 16 * R_ + 16 * F_ + 28 * H_ + 8 * HU_
         os.environ["ITX_FUSED"] = "0"
         d2 = o2 = 0.0
+        ix.reset(); ix.scan_bam_device(R.h, R.dbuf, n, opts)        # untimed: the first launch of these kernels loads them
         for _ in range(5):
             ix.reset(); ix.scan_bam_device(R.h, R.dbuf, n, opts)
             p2 = ix.profile()

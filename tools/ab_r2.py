@@ -106,6 +106,21 @@ elif what == "ncu":
         os.environ.update(env)
         ix.reset(); ix.scan_bam_device(h, dbuf, n, opts)
         print("launched", tag, flush=True)
+elif what == "tuple":
+    # the tuple path (ITX_FUSED=0) at several sizes: decode / overlap device time per scan
+    os.environ["ITX_FUSED"] = "0"
+    for nr in (10_000_000, 20_000_000, 50_000_000):
+        hbuf, n, nrec, _ = make_stream(0, nr)
+        dbuf, h = resident(hbuf, n)
+        L.itx_host_free_pinned(hbuf)
+        for _ in range(2):
+            ix.reset(); ix.scan_bam_device(h, dbuf, n, opts)
+        d = o = 0.0
+        for _ in range(5):
+            ix.reset(); cnt = ix.scan_bam_device(h, dbuf, n, opts)
+            pr = ix.profile(); d += pr["decode_ms"] / 5; o += pr["overlap_ms"] / 5
+        print("tuple path %d M reads: decode %.3f ms overlap %.3f ms launches %d" % (nr // 1_000_000, d, o, pr["n_launches"]), flush=True)
+        L.itx_bam_header_free(h); L.itx_dev_free(dbuf)
 elif what == "e2e1":
     # ONE BGZF scan from a pinned image (for ncu on k_inflate / k_lz_resolve); AB_READS sizes the file
     hbuf, n, nrec, hl = make_stream(0, reads)
