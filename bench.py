@@ -932,6 +932,8 @@ def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, ma
         if i:
             times.append(dt)
     pr = ix.profile()
+    dev_ms = max_over_ranks(pr["total_ms"])                 # device side of the slowest rank: first to last scan launch on its stream
+    inf_ms = max_over_ranks(pr["inflate_ms"])
     if rank != 0:
         return None
     assert got[0] + got[1] == total_rec, (got, total_rec)
@@ -941,7 +943,9 @@ def strong_scaling(a, L, ix, world_s, tables, wd, opts, rank, world, barrier, ma
             "scaling": "strong", "n_gpus": world, "value": total_rec / t, "unit": "read ends/s", "s_per_step": t, "steps": len(times),
             "api": ("itx_scan_alignments_shard (BGZF block ranges, guessed first records, NCCL all-gather chain check) + itx_comm_allreduce_counts + itx_sync_counts"
                     if world > 1 else "itx_scan_alignments + itx_sync_counts (one device: the whole file)"),
-            "file": "on tmpfs / page-cache resident", "ranks_rescanned_after_chain_check": int(pr["n_bad_chunks"]),
+            "file": "on tmpfs / page-cache resident: every rank pread()s its block range into pinned slots with %d host threads (the box's %d cores are shared by the ranks)" % (max(2, ncpu // world), ncpu),
+            "device_ms_slowest_rank": {"inflate_first_launch_to_last_end": inf_ms, "scan_stream_first_to_last_launch": dev_ms},
+            "ranks_rescanned_after_chain_check": int(pr["n_bad_chunks"]),
             "counters": {"records": int(got[0] + got[1]), "fragments": int(got[6]), "in_repeats": int(got[9])}}
 
 
