@@ -1078,8 +1078,16 @@ __global__ void __launch_bounds__(256, 2) k_xa(const itx_xa_args A) {
             const unsigned long long rp = __ldcs(A.q + idx);
             uint32_t x[9]; G.core(rp, x);
             T = itx_decode_record<itx_src_global, false>(G, rp, x, 0u, A.tid, A.n_ref, A.o);
-            int32_t nhit; float tcov;
-            sel = itx_find_select(D, (int32_t)(T.info & ITX_CHROM_MASK), T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+            int32_t nhit = 0; float tcov = 0.0f;
+            itx_query Q;
+            if (itx_query_open(D, (int32_t)(T.info & ITX_CHROM_MASK), T.start, T.end, &Q)) {
+                sel = itx_select_walk(D, Q, itx_iv_global{D}, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+                if (sel == ITX_SEL_LONG) {                       /* out of line, on the copy of the index in global memory (no local copy of D) */
+                    const itx_sel_cov r = itx_select_multi(*A.Dg, Q, T.start, T.end, nhit);
+                    sel = r.sel; tcov = r.cov;
+                    if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
+                }
+            }
             if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
             uint64_t a0; itx_aux_range(rp, x, &a0, &aend);
             xa = itx_aux_find(G, a0, aend, 'X', 'A');
@@ -1090,8 +1098,11 @@ __global__ void __launch_bounds__(256, 2) k_xa(const itx_xa_args A) {
         bool diffsub = false;
         if (coop) {
             /* every owner counts the pieces of its own list; the pieces of the 32 reads are numbered across the warp */
-            uint32_t np = 0; uint64_t zs = 0, ze = 0;
-            if (go) { const uint8_t ty = G.u8(xa); if (ty == 'Z' || ty == 'H') { zs = xa + 1; np = itx_xa_count(G, zs, aend, &ze); } }
+            uint32_t np = 0, sp0 = 0, sp1 = 0, packed = 0; uint64_t zs = 0, ze = 0;
+            if (go) {
+                const uint8_t ty = G.u8(xa);
+                if (ty == 'Z' || ty == 'H') { uint32_t sp[2]; bool pk; zs = xa + 1; np = itx_xa_count_pack(G, zs, aend, &ze, sp, &pk); sp0 = sp[0]; sp1 = sp[1]; packed = pk ? 1u : 0u; }
+            }
             uint32_t incl = np;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
@@ -1107,10 +1118,14 @@ __global__ void __launch_bounds__(256, 2) k_xa(const itx_xa_args A) {
                 const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow);
                 const uint64_t o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
                 const int32_t o_nm = __shfl_sync(0xffffffffu, nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
+                const uint32_t o_np = __shfl_sync(0xffffffffu, np, (int)ow), o_packed = __shfl_sync(0xffffffffu, packed, (int)ow);
+                uint32_t o_sp[2]; o_sp[0] = __shfl_sync(0xffffffffu, sp0, (int)ow); o_sp[1] = __shfl_sync(0xffffffffu, sp1, (int)ow);
                 bool hit = false, mal = false;
                 if (gi < total) {
                     uint64_t ps, pe;
-                    itx_xa_kth(G, o_zs, o_ze, gi - o_base, &ps, &pe);
+                    const uint32_t k = gi - o_base;
+                    if (o_packed && k < 8u) itx_xa_piece_bounds(o_zs, o_ze, o_np, o_sp, k, &ps, &pe);      /* the owner noted where its first ';' are */
+                    else itx_xa_kth(G, o_zs, o_ze, k, &ps, &pe);
                     if (pe > ps) hit = itx_xa_piece(D, G, ps, pe, o_nm, o_qlen, o_fold, &mal);
                 }
                 const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);

@@ -549,7 +549,8 @@ ITX_HD int32_t itx_strtol_int(const Src &S, uint64_t s, uint64_t e) {
         uint8_t c = S.u8(s); uint32_t d;
         if (c >= '0' && c <= '9') d = c - '0'; else if ((c | 32) >= 'a' && (c | 32) <= 'z') d = (uint32_t)((c | 32) - 'a') + 10; else break;
         if (d >= base) break;
-        if (acc > (0xffffffffffffffffull - d) / base) sat = true; else acc = acc * base + d;
+        /* the exact overflow test needs a 64-bit division: only once the value is within a factor 36 of 2^64 */
+        if (acc >= (1ull << 58) && acc > (0xffffffffffffffffull - d) / base) sat = true; else acc = acc * base + d;
         s++;
     }
     /* LONG_MIN / LONG_MAX on overflow, like glibc; the caller's (int) cast keeps the low 32 bits */
@@ -631,6 +632,39 @@ ITX_HD uint32_t itx_xa_count(const Src &S, uint64_t zs, uint64_t aend, uint64_t 
     *ze = z;
     if (z == zs) return 0;
     return semis + 1u < 100u ? semis + 1u : 100u;
+}
+/* itx_xa_count that also notes where the first eight ';' are: their offsets from zs, eight bits each, in sp[0..1] (*packed = false if
+ * one of them does not fit eight bits) -- the lanes that take the pieces then need not scan the string again (itx_xa_piece_bounds) */
+template <class Src>
+ITX_HD uint32_t itx_xa_count_pack(const Src &S, uint64_t zs, uint64_t aend, uint64_t *ze, uint32_t sp[2], bool *packed) {
+    uint64_t z = zs; uint32_t semis = 0; bool open = true, ok = true;
+    sp[0] = sp[1] = 0;
+#define ITX_XA_NOTE(pos_) do { const uint64_t o_ = (pos_) - zs; if (semis < 8u) { if (o_ < 256u) sp[semis >> 2] |= (uint32_t)o_ << (8u * (semis & 3u)); else ok = false; } semis++; } while (0)
+    while (open && z < aend && (z & 3)) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { if (c == ';') ITX_XA_NOTE(z); z++; } }
+    while (open && z + 4 <= aend) {
+        const uint32_t w = S.w32(z);
+        if (itx_eq4(w, 0u)) break;                               /* the terminator is in this word: the byte loop finds it */
+        uint32_t m = itx_eq4(w, 0x3b3b3b3bu);
+        while (m) {                                              /* lowest set byte first: bytes are in memory order (little endian) */
+            const uint32_t low = m & (0u - m);
+            const uint32_t b = low == 0x80u ? 0u : (low == 0x8000u ? 1u : (low == 0x800000u ? 2u : 3u));
+            ITX_XA_NOTE(z + b);
+            m &= m - 1u;
+        }
+        z += 4;
+    }
+    while (open && z < aend) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { if (c == ';') ITX_XA_NOTE(z); z++; } }
+#undef ITX_XA_NOTE
+    *ze = z; *packed = ok;
+    if (z == zs) return 0;
+    return semis + 1u < 100u ? semis + 1u : 100u;
+}
+/* bounds of piece k out of the packed offsets (k < 8, packed); np = itx_xa_count_pack's result */
+ITX_HD void itx_xa_piece_bounds(uint64_t zs, uint64_t ze, uint32_t np, const uint32_t sp[2], uint32_t k, uint64_t *ps, uint64_t *pe) {
+    const uint32_t prev = k ? ((k - 1u) < 4u ? sp[0] >> (8u * (k - 1u)) : sp[1] >> (8u * (k - 5u))) & 0xffu : 0u;
+    const uint32_t cur = (k < 4u ? sp[0] >> (8u * k) : sp[1] >> (8u * (k - 4u))) & 0xffu;
+    *ps = k ? zs + prev + 1u : zs;
+    *pe = k + 1u < np ? zs + cur : ze;                          /* the last piece runs to the end of the string */
 }
 /* bounds of piece k (k < itx_xa_count): [*ps, *pe) lies between the k-th and the (k+1)-th ';' of [zs, ze) */
 template <class Src>

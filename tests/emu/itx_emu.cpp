@@ -182,14 +182,22 @@ static bool xa_lanes(const itx_dev_index &D, const itx_src_global &G, uint64_t p
     const int32_t nm = itx_aux2i(G, itx_aux_find(G, a0, aend, 'N', 'M'), aend);
     const uint8_t ty = G.u8(xa);
     if (ty != 'Z' && ty != 'H') return false;
-    uint64_t ze; const uint64_t zs = xa + 1;
-    const uint32_t np = itx_xa_count(G, zs, aend, &ze);
+    uint64_t ze, ze2; const uint64_t zs = xa + 1;
+    uint32_t sp[2]; bool packed;
+    const uint32_t np = itx_xa_count_pack(G, zs, aend, &ze, sp, &packed);
+    if (np != itx_xa_count(G, zs, aend, &ze2) || ze != ze2) return !*malformed && false;      /* (never: the two counters agree) */
     bool found = false;
     for (uint32_t b0 = 0; b0 < np && !found; b0 += 32) {
         uint32_t m_hit = 0, m_mal = 0;
         for (uint32_t lane = 0; lane < 32 && b0 + lane < np; lane++) {
             uint64_t ps, pe; bool mal = false, hit = false;
-            itx_xa_kth(G, zs, ze, b0 + lane, &ps, &pe);
+            const uint32_t k = b0 + lane;
+            if (packed && k < 8u) {                              /* as k_xa: bounds out of the owner's notes, checked here against the scan */
+                uint64_t ps2, pe2;
+                itx_xa_piece_bounds(zs, ze, np, sp, k, &ps, &pe);
+                itx_xa_kth(G, zs, ze, k, &ps2, &pe2);
+                if (ps != ps2 || pe != pe2) { *malformed += 1000000u; }
+            } else itx_xa_kth(G, zs, ze, k, &ps, &pe);
             if (pe > ps) hit = itx_xa_piece(D, G, ps, pe, nm, qlen, fold, &mal);
             if (hit) m_hit |= 1u << lane;
             if (mal) m_mal |= 1u << lane;
