@@ -100,7 +100,10 @@ elif what == "ncu1":
 elif what == "ncu":
     hbuf, n, nrec, _ = make_stream(0, reads)
     dbuf, h = resident(hbuf, n)
-    for tag, env in V_SCAN[:7]:
+    V_NCU = [("all switches (127)", {"ITX_SCAN_FLAGS": "127"}), ("no L2 prefetch (126)", {"ITX_SCAN_FLAGS": "126"}), ("no evict-first hint (95)", {"ITX_SCAN_FLAGS": "95"}),
+             ("no early copy (111)", {"ITX_SCAN_FLAGS": "111"}), ("no table window (115)", {"ITX_SCAN_FLAGS": "115"}), ("evict hint on the prefetch too (255)", {"ITX_SCAN_FLAGS": "255"}),
+             ("persisting window on the coverage arrays", {"ITX_SCAN_FLAGS": "127", "ITX_L2_PERSIST": "1"})]
+    for tag, env in V_NCU:
         for k in ("ITX_SCAN_FLAGS", "ITX_SCAN_WARPS", "ITX_L2_PERSIST"):
             os.environ.pop(k, None)
         os.environ.update(env)
