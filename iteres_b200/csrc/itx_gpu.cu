@@ -517,11 +517,11 @@ static int scan_begin(scan_ctx *sc, itx_index *ix, const itx_bam_header *h, cons
     if (!resident) CK(cudaStreamSynchronize(cu->stream));      /* the streaming paths go on to use other streams (copies, inflate) that read the flags just reset */
     return ITX_OK;
 }
-/* A/B switch ITX_L2_PERSIST=1: the coverage difference arrays (the target of k_scan's scattered reductions) are asked to stay in L2
+/* ITX_L2_PERSIST (default 1; 0 switches it off): the coverage difference arrays (the target of k_scan's scattered reductions) are asked to stay in L2
  * (persisting access-policy window on the scan stream) while the stream bytes pass through */
 static void l2_persist_window(itx_index *ix) {
     itx_cuda *cu = ix->cu;
-    const int want = env_int_early("ITX_L2_PERSIST", 0) ? 1 : 0;
+    const int want = env_int_early("ITX_L2_PERSIST", 1) ? 1 : 0;      /* default on: DRAM writes of a 50 M read k_scan 0.31 GB -> 0.01 GB, reads -0.3 GB (profiles/r02_k_scan_traffic_attribution.txt) */
     if (want == cu->l2_persist_on) return;
     cudaStreamAttrValue v; memset(&v, 0, sizeof v);
     if (want) {

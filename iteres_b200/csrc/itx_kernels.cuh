@@ -588,7 +588,8 @@ struct itx_scan_args {
 #define ITX_SCAN_EVICT    32u            /* stream bytes carry an L2 evict-first hint: they are used once, the interval table and the counters are not */
 #define ITX_SCAN_XACOOP   64u            /* XA:Z alternates are tested one LANE per alternate (all alternates of a round side by side) instead of one lane per read */
 #define ITX_SCAN_EVICT_PF 128u           /* the evict-first hint on the L2 prefetches too */
-#define ITX_SCAN_DEFAULT  (ITX_SCAN_PREFETCH | ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
+#define ITX_SCAN_CARRY    256u           /* the margin of the stage in place becomes the head of the next one inside shared memory: it is not fetched twice */
+#define ITX_SCAN_DEFAULT  (ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
 #define ITX_WIN 32u                      /* table entries per warp window */
 #ifndef ITX_SCAN_NW
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     const uint32_t flags = AB ? P.flags : (uint32_t)ITX_SCAN_PRODUCT;
     const bool f_prefetch = flags & ITX_SCAN_PREFETCH, f_dom = flags & ITX_SCAN_DOMSIZE, f_win = flags & ITX_SCAN_WINDOW;
     const bool f_ahead = f_win && (flags & ITX_SCAN_WINAHEAD), f_early = flags & ITX_SCAN_EARLY;
-    const bool f_evict = flags & ITX_SCAN_EVICT, f_evict_pf = flags & ITX_SCAN_EVICT_PF;
+    const bool f_evict = flags & ITX_SCAN_EVICT, f_evict_pf = flags & ITX_SCAN_EVICT_PF, f_carry = flags & ITX_SCAN_CARRY;
 #define n_elem32 (D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem)
     uint32_t wspec = 0xffffffffu;                               /* first table entry of the window fetched ahead (none yet) */
     /* the 13 report counters: every lane counts its own records in 8-bit fields of three registers (no votes, no
@@ -739,14 +740,22 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     uint32_t pa = 0, pb = 0, pc = 0, n_rounds = 0;
     /* one stage into shared memory: a TMA bulk copy of ITX_STAGE + ITX_MARGIN bytes (less at the end of the stream), and what
      * the stage after it adds on its way into L2 meanwhile; the caller has made sure that every lane is done with the old bytes */
-#define ITX_SCAN_ISSUE(c_lo_, rest_, nb_out_) do { \
+#define ITX_SCAN_ISSUE(c_lo_, rest_, nb_out_, carry_) do { \
         nb_out_ = (rest_) > STG ? STG : (uint32_t)(rest_); \
+        /* the stage that follows the one in place begins with that one's margin: those bytes are moved inside shared memory (32 per \
+         * lane) and only the rest comes over from L2 / HBM -- the margin is not fetched twice */ \
+        const bool carry__ = f_carry && (carry_) && nb_out_ > ITX_MARGIN; \
+        if (carry__) { \
+            const uint4 t0_ = *reinterpret_cast<const uint4 *>(buf + ITX_STAGE + lane * 32u), t1_ = *reinterpret_cast<const uint4 *>(buf + ITX_STAGE + lane * 32u + 16u); \
+            *reinterpret_cast<uint4 *>(buf + lane * 32u) = t0_; *reinterpret_cast<uint4 *>(buf + lane * 32u + 16u) = t1_; \
+        } \
         __syncwarp(); \
         if (lane == 0) { \
-            const uint32_t bytes_ = (nb_out_ + 15u) & ~15u;     /* the buffer's 64 bytes of slack cover the round-up */ \
+            const uint32_t skip_ = carry__ ? ITX_MARGIN : 0u; \
+            const uint32_t bytes_ = ((nb_out_ + 15u) & ~15u) - skip_;     /* the buffer's 64 bytes of slack cover the round-up */ \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
             itx_mbar_expect_tx(bar_s, bytes_); \
-            if (f_evict) itx_bulk_g2s_hint(buf_s, A.b + lo + (c_lo_), bytes_, bar_s, itx_policy_evict_first()); else itx_bulk_g2s(buf_s, A.b + lo + (c_lo_), bytes_, bar_s); \
+            if (f_evict) itx_bulk_g2s_hint(buf_s + skip_, A.b + lo + (c_lo_) + skip_, bytes_, bar_s, itx_policy_evict_first()); else itx_bulk_g2s(buf_s + skip_, A.b + lo + (c_lo_) + skip_, bytes_, bar_s); \
             if (f_prefetch && (c_lo_) + ITX_STAGE < hi && (rest_) >= STG + ITX_STAGE) { \
                 if (f_evict_pf) itx_prefetch_l2_hint(A.b + lo + (c_lo_) + STG, ITX_STAGE, itx_policy_evict_first()); else itx_prefetch_l2(A.b + lo + (c_lo_) + STG, ITX_STAGE); \
             } \
@@ -789,7 +798,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
             const unsigned long long rest = A.len - lo - c_lo;                 /* bytes of the stream from this stage on */
             if (staged != c_lo) {
                 if (inflight == c_lo) nb = rest > STG ? STG : (uint32_t)rest;      /* on its way since the last round of the previous stage */
-                else ITX_SCAN_ISSUE(c_lo, rest, nb);         /* (the macro's __syncwarp: every lane is done reading the previous stage) */
+                else ITX_SCAN_ISSUE(c_lo, rest, nb, staged + ITX_STAGE == c_lo && nb == STG);      /* (every lane is done reading the previous stage: the macro's __syncwarp ... */
                 if (!itx_mbar_wait(bar_s, parity, A.status)) { dead = true; break; }
                 parity ^= 1u;
                 staged = c_lo; inflight = 0xffffffffu;
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     const uint32_t c_nx = (c_lo + q) & ~(ITX_STAGE - 1u);
                     const unsigned long long rest_nx = A.len - lo - c_nx;
                     uint32_t nb_nx;
-                    ITX_SCAN_ISSUE(c_nx, rest_nx, nb_nx);
+                    ITX_SCAN_ISSUE(c_nx, rest_nx, nb_nx, c_nx == c_lo + ITX_STAGE && nb == STG);
                     (void)nb_nx;
                     inflight = c_nx;
                 }
