@@ -701,7 +701,7 @@ __device__ __noinline__ void itx_flush_counters(uint32_t pa, uint32_t pb, uint32
  * select between are not in the loop at all (the loop is bound by instruction issue AND fetch: every instruction that is not
  * there helps); AB = true: the switches are read from P.flags (tests and measurements: every combination gives the same counts) */
 #ifndef ITX_SCAN_PRODUCT
-#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT)
+#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT | ITX_SCAN_CARRY)
 #endif
 template <bool SMEM_HIST, int NW, bool AB>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
