@@ -1121,7 +1121,8 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         /* ITX_LZ=1: k_lz_jump (pointer jumping, every thread busy, 192 KiB of shared memory per block in flight); default: k_lz_resolve
          * (ordered batches, 64 KiB).  Measured on the B200 (3.4 GB file): the same 151 ms end to end -- k_lz_jump is several times
          * faster per block, but its CTA needs a whole SM's shared memory, so it waits for every k_inflate warp there to finish */
-        const bool lz_jump = env_int("ITX_LZ", 0) != 0;
+        const int lz_mode = env_int("ITX_LZ", 2);
+        const bool lz_jump = lz_mode == 1, lz_fused = lz_mode == 2;
         cudaFuncSetAttribute(k_lz_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ2_SMEM);
         cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ_SMEM);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_ctas, k_lz_resolve, ITX_LZ_THREADS, ITX_LZ_SMEM);
@@ -1145,13 +1146,14 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             if (n_groups == 0) EV(cudaStreamWaitEvent(st, begin_ev, 0));           /* the status words are zeroed on the scan stream */
             itx_inflate_args IA; IA.file = cu->d_comp; IA.blk = cu->d_blk; IA.b0 = gb0; IA.nblk = upto - gb0; IA.out = cu->d_stream; IA.status = cu->D.status;
             IA.tabs = cu->d_tabs + (size_t)gs * tab_stride;
-            IA.m_pl = cu->d_mpl + (size_t)gs * m_stride * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * m_stride * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * m_stride; IA.m_cap = ITX_M_WORST;
+            IA.m_pl = cu->d_mpl + (size_t)gs * m_stride * ITX_M_WORST; IA.m_d = cu->d_md + (size_t)gs * m_stride * ITX_M_WORST; IA.m_n = cu->d_mn + (size_t)gs * m_stride; IA.m_cap = ITX_M_WORST; IA.fuse_lz = lz_fused ? 1u : 0u;
             const bool ev_ok = 2 * nw + 1 < cu->inf_ev_made;
             if (ev_ok) EV(cudaEventRecord(wev[2 * nw], st));
             const int lanes = tail ? TAIL_LANES : LANES;
             if (lanes <= 8) launch_inflate<3>(IA, st); else if (lanes <= 16) launch_inflate<4>(IA, st); else launch_inflate<5>(IA, st);
             EV(cudaGetLastError());
-            if (lz_jump) {
+            if (lz_fused) {
+            } else if (lz_jump) {
                 uint64_t lzb = IA.nblk, lzmax = (uint64_t)cu->sm_count; if (lzb > lzmax) lzb = lzmax;
                 k_lz_jump<<<(unsigned)lzb, ITX_LZ2_THREADS, ITX_LZ2_SMEM, st>>>(IA);
             } else {

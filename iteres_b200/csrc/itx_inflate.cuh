@@ -418,4 +418,26 @@ ITX_HD void itx_lz_copy(uint8_t *o, uint32_t len, uint32_t d) {
 ITX_HD bool itx_lz_ready(uint32_t pos, uint32_t len, uint32_t dist, bool is_first_unfinished, uint32_t first_unfinished_pos) {
     return is_first_unfinished || pos - dist + len <= first_unfinished_pos;
 }
+/* ---- the second pass INSIDE the decoding warp: windows of W bytes.  src[i - w0] = where byte i of the window comes from (itself for
+ * a literal); the chains that stay inside the window are shortened by pointer jumping, and a source before the window is final
+ * because the windows of a block are resolved in order.  Only the src cells live in shared memory (the warp's look-up tables, dead by
+ * then): literals and history are read where they lie.  The per-lane pieces are here so that the host test can step them lane by
+ * lane; the device driver is itx_lzw_resolve (itx_kernels.cuh). */
+ITX_HD void itx_lzw_init(uint16_t *src, uint32_t w0, uint32_t cnt, uint32_t lane) {
+    for (uint32_t i = lane; i < cnt; i += 32u) src[i] = (uint16_t)(w0 + i);
+}
+/* the part of match (pos, len, dist) that lies in [w0, w1) */
+ITX_HD void itx_lzw_scatter(uint16_t *src, uint32_t w0, uint32_t w1, uint32_t pos, uint32_t len, uint32_t dist) {
+    const uint32_t a = pos > w0 ? pos : w0, b = pos + len < w1 ? pos + len : w1;
+    for (uint32_t j = a; j < b; j++) src[j - w0] = (uint16_t)(j - dist);
+}
+/* one pass over the lane's cells (lane, lane + 32, ...): true = something moved */
+ITX_HD bool itx_lzw_jump(uint16_t *src, uint32_t w0, uint32_t cnt, uint32_t lane) {
+    bool changed = false;
+    for (uint32_t i = lane; i < cnt; i += 32u) {
+        const uint32_t sv = src[i];
+        if (sv >= w0 && sv != w0 + i) { const uint32_t ss = src[sv - w0]; if (ss != sv) { src[i] = (uint16_t)ss; changed = true; } }
+    }
+    return changed;
+}
 #endif

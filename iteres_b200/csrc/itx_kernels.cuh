@@ -1390,6 +1390,7 @@ struct itx_inflate_args {
     uint16_t *tabs;                      /* 32 * ITX_T_CELLS cells per warp of the grid */
     /* deferred matches: block g0 of the launch owns m_pl[g0 * m_cap ..] / m_d[g0 * m_cap ..]; m_n[g0] = entries or ITX_M_NONE */
     uint32_t *m_pl; uint16_t *m_d; uint32_t *m_n; uint32_t m_cap;
+    uint32_t fuse_lz;                    /* the decoding warp resolves the matches of its own blocks (itx_lzw_resolve): no second kernel */
 };
 #define ITX_INF_THREADS 32
 #define ITX_INF_SMEM(LG) (ITX_LUT_CELLS * 2u * (1u << (LG)))
@@ -1397,6 +1398,42 @@ struct itx_inflate_args {
  * copied in line (m_cap == 0).  The host sizes the lists for the worst case (ITX_M_WORST entries: a match is at
  * least three bytes long), so a list cannot overflow. */
 #define ITX_M_WORST 21848u
+/* The second pass of one block by the 32 lanes of the warp that decoded it: windows of W bytes, W 16-bit src cells in the warp's
+ * shared memory (its look-up tables, dead once the batch is decoded).  The list is in output order and its matches do not overlap,
+ * so the entries of a window are a run of the list; an entry cut by a window's end is visited by both windows.  Bytes are read with
+ * ld.cg (they were stored by other lanes of this warp: L2 is where stores land) and the gather runs four loads ahead of its stores
+ * (a position that is read is a literal or lies before the window: nothing in this loop writes it). */
+template <uint32_t W>
+__device__ __forceinline__ void itx_lzw_resolve(uint8_t *out, uint32_t isize, const uint32_t *pl, const uint16_t *md, uint32_t n, uint16_t *src, uint32_t lane) {
+    uint32_t k0 = 0;
+    for (uint32_t w0 = 0; w0 < isize && k0 < n; w0 += W) {
+        const uint32_t w1 = w0 + W < isize ? w0 + W : isize, cnt = w1 - w0;
+        if ((__ldcg(pl + k0) & 0xffffu) >= w1) continue;                    /* nothing but literals in this window */
+        itx_lzw_init(src, w0, cnt, lane);
+        __syncwarp();
+        for (uint32_t k = k0;; k += 32u) {
+            const bool in = k + lane < n;
+            const uint32_t e = in ? __ldcg(pl + k + lane) : 0xffffu;
+            const uint32_t pos = e & 0xffffu, len = e >> 16;
+            if (in && pos < w1) itx_lzw_scatter(src, w0, w1, pos, len, (uint32_t)__ldcg(md + k + lane));
+            const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, in && pos + len <= w1));       /* finished for good: a prefix of the batch */
+            k0 = k + c;
+            if (c < 32u) break;
+        }
+        __syncwarp();
+        while (__any_sync(0xffffffffu, itx_lzw_jump(src, w0, cnt, lane))) { }
+        for (uint32_t i0 = lane; i0 < cnt; i0 += 128u) {
+            uint32_t sv[4]; uint8_t b[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) { const uint32_t i = i0 + 32u * u; sv[u] = i < cnt ? (uint32_t)src[i] : w0 + i; }
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) b[u] = sv[u] != w0 + i0 + 32u * u ? __ldcg(out + sv[u]) : (uint8_t)0;
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) if (sv[u] != w0 + i0 + 32u * u) out[w0 + i0 + 32u * u] = b[u];
+        }
+        __syncwarp();
+    }
+}
 template <uint32_t LG>
 __global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(const itx_inflate_args A) {
     extern __shared__ __align__(16) uint8_t itx_inf_smem[];
@@ -1431,6 +1468,19 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(
             if (I.state != ITX_ST_DONE) { atomicAdd(&A.status[5], 1u); A.status[6] = (uint32_t)b; }
         }
         __syncwarp();
+        if (A.fuse_lz && A.m_cap) {
+            /* the warp's blocks one after the other, all 32 lanes on each */
+            constexpr uint32_t W = LG == 5 ? 8192u : (LG == 4 ? 4096u : 2048u);             /* 2 W bytes of the warp's 640 << LG */
+            const uint32_t nm = mine && I.state == ITX_ST_DONE ? I.n_match : 0u;
+            const unsigned long long op = reinterpret_cast<unsigned long long>(I.out);
+            for (uint32_t l = 0; l < NL; l++) {
+                const uint32_t n_l = __shfl_sync(0xffffffffu, nm, (int)l);
+                if (!n_l) continue;
+                const uint32_t isz = __shfl_sync(0xffffffffu, I.out_pos, (int)l);
+                uint8_t *o_l = reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, op, (int)l));
+                itx_lzw_resolve<W>(o_l, isz, A.m_pl + (g0 + l) * A.m_cap, A.m_d + (g0 + l) * A.m_cap, n_l, reinterpret_cast<uint16_t *>(itx_inf_smem), lane);
+            }
+        }
     }
 }
 

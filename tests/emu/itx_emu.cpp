@@ -529,7 +529,30 @@ int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_c
     const uint32_t rc = I.run(padded.data() + 4 + skew, in_len, expect);
     if (produced) *produced = I.out_pos;
     if (I.state == ITX_ST_OVERFLOW) return 99;
-    if (defer == 2 && rc == ITX_INF_OK) {
+    if (defer >= 3 && rc == ITX_INF_OK) {
+        /* itx_lzw_resolve (k_inflate's own second pass), lane by lane: windows of W bytes, the same per-lane pieces as the device */
+        const uint32_t W = defer == 3 ? 8192u : (defer == 4 ? 2048u : 64u), n = I.n_match, isize = I.out_pos;
+        std::vector<uint16_t> src(W);
+        uint32_t k0 = 0;
+        for (uint32_t w0 = 0; w0 < isize && k0 < n; w0 += W) {
+            const uint32_t w1 = w0 + W < isize ? w0 + W : isize, cnt = w1 - w0;
+            if ((mpl[k0] & 0xffffu) >= w1) continue;
+            for (uint32_t l = 0; l < 32; l++) itx_lzw_init(src.data(), w0, cnt, l);
+            for (uint32_t k = k0;; k += 32) {
+                uint32_t c = 0;
+                for (int l = 31; l >= 0; l--) {                    /* any lane order: the matches of a list do not overlap */
+                    const bool in = k + (uint32_t)l < n;
+                    const uint32_t e = in ? mpl[k + l] : 0xffffu, pos = e & 0xffffu, len = e >> 16;
+                    if (in && pos < w1) itx_lzw_scatter(src.data(), w0, w1, pos, len, md[k + l]);
+                    if (in && pos + len <= w1) c++;
+                }
+                k0 = k + c;
+                if (c < 32) break;
+            }
+            for (bool any = true; any;) { any = false; for (int l = 31; l >= 0; l--) if (itx_lzw_jump(src.data(), w0, cnt, (uint32_t)l)) any = true; }
+            for (uint32_t i = 0; i < cnt; i++) if (src[i] != (uint16_t)(w0 + i)) out[w0 + i] = out[src[i]];
+        }
+    } else if (defer == 2 && rc == ITX_INF_OK) {
         /* k_lz_jump: src[i] = where byte i comes from, pointer jumping until every byte points at a literal, then one gather */
         const uint32_t n = I.n_match, isize = I.out_pos;
         std::vector<uint16_t> src(65536 + 2);

@@ -43,7 +43,7 @@ def samples():
 SAMPLES = samples()
 
 
-@pytest.mark.parametrize("defer", [0, 1, 2])
+@pytest.mark.parametrize("defer", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("level", [0, 1, 6, 9])
 @pytest.mark.parametrize("name", sorted(SAMPLES))
 def test_matches_zlib(name, level, defer):

@@ -151,13 +151,15 @@ elif what == "e2e":
         mv = (C.c_char * fsz).from_address(pin)
         assert f.readinto(mv) == fsz
     print("BGZF %.2f GB written and pinned" % (fsz / 1e9), flush=True)
-    variants = [("lz_jump (default)", {}), ("lz_batches (r1)", {"ITX_LZ": "0"}), ("lz_jump tail32", {"ITX_INF_TAIL_LANES": "32", "ITX_INF_TAIL_GROUP": "16384"}),
-                ("lz_jump g8192", {"ITX_INF_GROUP": "8192"}), ("lz_jump g32768", {"ITX_INF_GROUP": "32768"})]
+    variants = [("in-warp windows (2)", {}), ("k_lz_resolve (0)", {"ITX_LZ": "0"}), ("windows, tail 4096x8", {"ITX_INF_TAIL_GROUP": "4096"}),
+                ("windows, 16 lanes", {"ITX_INF_LANES": "16"}), ("windows, g8192", {"ITX_INF_GROUP": "8192"}), ("windows, g8192 tail 2048", {"ITX_INF_GROUP": "8192", "ITX_INF_TAIL_GROUP": "2048"})]
+    if os.environ.get("AB_E2E_VARIANTS"):
+        variants = [(v, dict(kv.split("=") for kv in v.split(",") if kv)) for v in os.environ["AB_E2E_VARIANTS"].split(";")]
     for tag, env in variants:
         for k in ("ITX_INF_LANES", "ITX_INF_TAIL_LANES", "ITX_INF_GROUP", "ITX_INF_TAIL_GROUP", "ITX_TIMING", "ITX_LZ"):
             os.environ.pop(k, None)
         os.environ.update(env)
-        for api in ("pinned", "file"):
+        for api in (("pinned", "file") if tag == variants[0][0] else ("pinned",)):
             ts = []
             for i in range(4):
                 if i == 3 and api == "pinned":
