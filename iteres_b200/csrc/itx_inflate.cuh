@@ -26,12 +26,14 @@
 #define ITX_INF_EDATA 1        /* invalid deflate data */
 #define ITX_INF_ESIZE 2        /* output is not the ISIZE the BGZF footer promised */
 
-#define ITX_LB 8u              /* index bits of the literal/length table */
+#ifndef ITX_LB
+#define ITX_LB 8u              /* index bits of the literal/length table (>= 7: the cells hold the code-length code's 7-bit table while a header is read) */
+#endif
 #define ITX_DB 6u              /* index bits of the distance table */
 /* shared cells of one thread (16 bit): entry = symbol << 4 | code length, 0 = "longer than the index" */
 #define ITX_LUT_L 0u           /* [256] literal/length table; while a header is read: [0,128) the code-length code's table */
-#define ITX_LUT_D 256u         /* [64]  distance table; while a header is read: the 256 literal code lengths, four per cell */
-#define ITX_LUT_CELLS 320u
+#define ITX_LUT_D (1u << ITX_LB)   /* [64]  distance table; while a header is read: the 256 literal code lengths, four per cell */
+#define ITX_LUT_CELLS (ITX_LUT_D + 64u)
 /* global cells of one thread (16 bit) */
 #define ITX_T_LSYM 0u          /* [288] literal/length symbols in canonical order */
 #define ITX_T_DSYM 288u        /* [30]  distance symbols in canonical order */
@@ -43,8 +45,6 @@
 #define ITX_ST_ERROR 3u
 #define ITX_ST_COPY 4u         /* a match is being copied, ITX_COPY_STEP bytes per round (in-line mode only) */
 #define ITX_ST_OVERFLOW 5u     /* deferred mode: the block has more matches than its list holds */
-#define ITX_ST_LPEND 6u        /* a long literal/length code: its symbol is on its way from the symbol array */
-#define ITX_ST_DPEND 7u        /* the same for a long distance code (the match length waits in pend_len) */
 #define ITX_COPY_STEP 8u
 #define ITX_BURST 3u           /* literals decoded ahead of the general symbol of a round */
 #define ITX_M_NONE 0xffffffffu /* match count of a block that overflowed or failed */
@@ -72,8 +72,7 @@ struct itx_inflater {
     Tab tab;
     uint32_t err;
     uint32_t state, last, expect;
-    uint32_t pend_len, pend_dist;          /* ITX_ST_COPY, ITX_ST_DPEND */
-    uint32_t pend_sym;                     /* ITX_ST_LPEND / ITX_ST_DPEND: the symbol loaded in the previous round */
+    uint32_t pend_len, pend_dist;          /* ITX_ST_COPY */
     /* deferred mode (m_cap != 0): literals go to their final place, matches are only LISTED -- entry k is
      * (output position | length << 16, distance) -- and a second pass (k_lz_resolve) copies them while the block's
      * history is cache resident; a decoder that copies in line waits on a DRAM read of its own history every round */
@@ -173,8 +172,7 @@ struct itx_inflater {
         return left;
     }
     /* codes longer than the table index: canonical bit-serial walk from length `from` + 1.  Returns the slot of
-     * the symbol in the (global-memory) symbol array, or -1; the caller loads it and uses it one round later, so
-     * that the load's latency is spent on the other lanes' next symbols instead of stalling the warp. */
+     * the symbol in the (global-memory) symbol array, or -1. */
     ITX_HDM int32_t walk_long(const uint32_t c[8], uint32_t from, uint32_t first0, uint32_t index0) {
         uint32_t buf = (uint32_t)bitbuf;
         int32_t code = (int32_t)((itx_brev32(buf) >> (32 - from)) << 1), first = (int32_t)first0, index = (int32_t)index0;
@@ -215,13 +213,14 @@ struct itx_inflater {
         out_pos += n; pend_len -= n;
         state = pend_len ? ITX_ST_COPY : ITX_ST_SYMBOL;
     }
-    /* One round of the symbol states.  The phases are written so that the lanes of a warp re-converge before each
-     * of them: (1) a literal/length symbol -- out of the table, or the one a long code asked for in the previous
-     * round; (2) what the symbol means, down to the distance symbol; (3) the match.  false = invalid data. */
+    /* One round of the symbol state: up to ITX_BURST short-code literals, then one general symbol down to its match.  Written
+     * without early exits, as nested phases, so that the lanes of a warp (32 different blocks, each somewhere else in this code)
+     * re-converge after every phase instead of running the tail once per path.  A code longer than the table index is finished by
+     * the canonical walk and its symbol fetched from the (global-memory) symbol array on the spot.  false = invalid data. */
     ITX_HDM bool symbol_round() {
-        uint32_t s = 0, d = 0, len = 0; bool have_s = false, have_d = false;
-        if (state == ITX_ST_SYMBOL) {
-            if (out_pos > out_cap || overrun()) return false;
+        bool ok = !(out_pos > out_cap || overrun());
+        uint32_t s = 0x7fffffffu;                                          /* no symbol */
+        if (ok) {
             refill();
             uint32_t e = tab.lut(ITX_LUT_L + ((uint32_t)bitbuf & ((1u << ITX_LB) - 1u)));
             /* most symbols of a BAM stream are literals with short codes: up to ITX_BURST of them go out right here,
@@ -234,43 +233,40 @@ struct itx_inflater {
                 }
             }
             refill();                                                      /* only adds high bits: e stays valid */
-            if (e & 15u) { consume(e & 15u); s = e >> 4; have_s = true; }
+            if (e & 15u) { consume(e & 15u); s = e >> 4; }
             else {
                 const int32_t slot = walk_long(lc, ITX_LB, lfirst, lindex);
-                if (slot < 0) return false;
-                pend_sym = tab(ITX_T_LSYM + (uint32_t)slot); state = ITX_ST_LPEND;
+                if (slot < 0) ok = false; else s = tab(ITX_T_LSYM + (uint32_t)slot);
             }
-        } else if (state == ITX_ST_LPEND) { s = pend_sym; have_s = true; state = ITX_ST_SYMBOL; }
-        else if (state == ITX_ST_DPEND) { d = pend_sym; len = pend_len; have_d = true; state = ITX_ST_SYMBOL; }
-        if (have_s) {
-            if (s < 256) put((uint8_t)s);
-            else if (s == 256) state = last ? ITX_ST_DONE : ITX_ST_HEADER;
+        }
+        if (s < 256u) put((uint8_t)s);
+        else if (s == 256u) state = last ? ITX_ST_DONE : ITX_ST_HEADER;
+        else if (s != 0x7fffffffu) {
+            s -= 257u;
+            if (s >= 29u) ok = false;
             else {
-                s -= 257;
-                if (s >= 29) return false;
-                len = lbase(s) + take(lext(s));                            /* <= 15 + 5 of the >= 32 bits are gone */
+                const uint32_t len = lbase(s) + take(lext(s));             /* <= 15 + 5 of the >= 32 bits are gone */
                 refill();
                 const uint32_t e = tab.lut(ITX_LUT_D + ((uint32_t)bitbuf & ((1u << ITX_DB) - 1u)));
-                if (e & 15u) { consume(e & 15u); d = e >> 4; have_d = true; }
+                uint32_t d = 0xffffffffu;
+                if (e & 15u) { consume(e & 15u); d = e >> 4; }
                 else {
                     const int32_t slot = walk_long(dc, ITX_DB, dfirst, dindex);
-                    if (slot < 0) return false;
-                    pend_sym = tab(ITX_T_DSYM + (uint32_t)slot); pend_len = len; state = ITX_ST_DPEND;
+                    if (slot >= 0) d = tab(ITX_T_DSYM + (uint32_t)slot);
+                }
+                if (d >= 30u) ok = false;
+                else {
+                    const uint32_t dist = dbase(d) + take(dext(d));        /* <= 15 + 13 of the >= 32 bits */
+                    if (dist > out_pos) ok = false;
+                    else if (out_pos + len > out_cap) { out_pos += len; ok = false; }
+                    else if (m_cap) {
+                        if (n_match >= m_cap) state = ITX_ST_OVERFLOW;
+                        else { m_pl[n_match] = out_pos | (len << 16); m_d[n_match] = (uint16_t)dist; n_match++; out_pos += len; }
+                    } else { pend_len = len; pend_dist = dist; copy_step(); }
                 }
             }
         }
-        if (have_d) {
-            if (d >= 30) return false;
-            const uint32_t dist = dbase(d) + take(dext(d));                /* <= 15 + 13 of the >= 32 bits */
-            if (dist > out_pos) return false;
-            if (out_pos + len > out_cap) { out_pos += len; return false; }
-            if (m_cap) {
-                if (n_match >= m_cap) { state = ITX_ST_OVERFLOW; return true; }
-                m_pl[n_match] = out_pos | (len << 16); m_d[n_match] = (uint16_t)dist; n_match++;
-                out_pos += len;
-            } else { pend_len = len; pend_dist = dist; copy_step(); }
-        }
-        return true;
+        return ok;
     }
     ITX_HDM bool stored() {
         consume(bitcnt & 7);                                          /* to the next byte boundary */
@@ -347,7 +343,7 @@ struct itx_inflater {
      * one symbol, or one step of a long match copy -- and the kernel re-converges the warp between calls. */
     ITX_HDM void begin(const uint8_t *in, uint32_t in_len, uint32_t expect_) {
         set_input(in, in_len);
-        out_pos = 0; state = ITX_ST_HEADER; last = 0; expect = expect_; err = ITX_INF_OK; pend_len = pend_dist = 0; pend_sym = 0; n_match = 0;
+        out_pos = 0; state = ITX_ST_HEADER; last = 0; expect = expect_; err = ITX_INF_OK; pend_len = pend_dist = 0; n_match = 0;
         lfirst = lindex = dfirst = dindex = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) { lc[k] = 0; dc[k] = 0; }
@@ -355,7 +351,7 @@ struct itx_inflater {
     }
     ITX_HDM bool running() const { return state != ITX_ST_DONE && state != ITX_ST_ERROR && state != ITX_ST_OVERFLOW; }
     ITX_HDM void advance() {
-        if (state == ITX_ST_SYMBOL || state == ITX_ST_LPEND || state == ITX_ST_DPEND) {
+        if (state == ITX_ST_SYMBOL) {
             if (!symbol_round()) { state = ITX_ST_ERROR; err = ITX_INF_EDATA; }
         } else if (state == ITX_ST_COPY) {
             copy_step();
@@ -424,19 +420,36 @@ ITX_HD bool itx_lz_ready(uint32_t pos, uint32_t len, uint32_t dist, bool is_firs
  * then): literals and history are read where they lie.  The per-lane pieces are here so that the host test can step them lane by
  * lane; the device driver is itx_lzw_resolve (itx_kernels.cuh). */
 ITX_HD void itx_lzw_init(uint16_t *src, uint32_t w0, uint32_t cnt, uint32_t lane) {
-    for (uint32_t i = lane; i < cnt; i += 32u) src[i] = (uint16_t)(w0 + i);
+    /* up to the next multiple of 256 cells (the windows are multiples of 256): the passes below run without bound tests, and a cell
+     * past the window's end is its own source like a literal (positions past 65535 wrap: such cells are never read as a source) */
+    const uint32_t cnt_r = (cnt + 255u) & ~255u;
+    for (uint32_t i = lane; i < cnt_r; i += 32u) src[i] = (uint16_t)(w0 + i);
 }
-/* the part of match (pos, len, dist) that lies in [w0, w1) */
+/* the part of match (pos, len, dist) that lies in [w0, w1).  A match that overlaps itself (dist < len: a run) points every byte
+ * straight at the period before the match, so the chain through its own bytes never has to be followed */
 ITX_HD void itx_lzw_scatter(uint16_t *src, uint32_t w0, uint32_t w1, uint32_t pos, uint32_t len, uint32_t dist) {
     const uint32_t a = pos > w0 ? pos : w0, b = pos + len < w1 ? pos + len : w1;
-    for (uint32_t j = a; j < b; j++) src[j - w0] = (uint16_t)(j - dist);
+    if (dist >= len) {
+        for (uint32_t j = a; j < b; j++) src[j - w0] = (uint16_t)(j - dist);
+    } else {
+        uint32_t r = (a - pos) % dist;
+        for (uint32_t j = a; j < b; j++) { src[j - w0] = (uint16_t)(pos - dist + r); r = r + 1u == dist ? 0u : r + 1u; }
+    }
 }
-/* one pass over the lane's cells (lane, lane + 32, ...): true = something moved */
+/* one pass over the lane's cells (lane, lane + 32, ...), eight cells at a time: all loads of a batch before its stores, so a pass
+ * costs a few shared-memory latencies, not one per cell.  A literal looks itself up and stays; a source before the window is
+ * final.  true = something moved */
 ITX_HD bool itx_lzw_jump(uint16_t *src, uint32_t w0, uint32_t cnt, uint32_t lane) {
     bool changed = false;
-    for (uint32_t i = lane; i < cnt; i += 32u) {
-        const uint32_t sv = src[i];
-        if (sv >= w0 && sv != w0 + i) { const uint32_t ss = src[sv - w0]; if (ss != sv) { src[i] = (uint16_t)ss; changed = true; } }
+    const uint32_t cnt_r = (cnt + 255u) & ~255u;
+    for (uint32_t i0 = lane; i0 < cnt_r; i0 += 256u) {
+        uint32_t sv[8], ss[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) sv[u] = (uint32_t)src[i0 + 32u * u];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) ss[u] = sv[u] >= w0 ? (uint32_t)src[sv[u] - w0] : sv[u];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) if (ss[u] != sv[u]) { src[i0 + 32u * u] = (uint16_t)ss[u]; changed = true; }
     }
     return changed;
 }

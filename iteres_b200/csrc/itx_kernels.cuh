@@ -1398,17 +1398,22 @@ struct itx_inflate_args {
  * copied in line (m_cap == 0).  The host sizes the lists for the worst case (ITX_M_WORST entries: a match is at
  * least three bytes long), so a list cannot overflow. */
 #define ITX_M_WORST 21848u
-/* The second pass of one block by the 32 lanes of the warp that decoded it: windows of W bytes, W 16-bit src cells in the warp's
- * shared memory (its look-up tables, dead once the batch is decoded).  The list is in output order and its matches do not overlap,
- * so the entries of a window are a run of the list; an entry cut by a window's end is visited by both windows.  Bytes are read with
- * ld.cg (they were stored by other lanes of this warp: L2 is where stores land) and the gather runs four loads ahead of its stores
- * (a position that is read is a literal or lies before the window: nothing in this loop writes it). */
+/* The second pass of one block by the 32 lanes of the warp that decoded it: windows of W bytes; W 16-bit src cells and the window's
+ * bytes in the warp's shared memory (its look-up tables, dead once the batch is decoded).  The list is in output order and its matches
+ * do not overlap, so the entries of a window are a run of the list; an entry cut by a window's end is visited by both windows.
+ * A window comes in with 16-byte loads (ld.cg: the bytes were stored by other lanes of this warp, L2 is where stores land), bytes whose
+ * source lies before the window are gathered from L2 eight loads at a time per lane, the others out of shared memory, and the window
+ * goes back with 16-byte stores. */
 template <uint32_t W>
-__device__ __forceinline__ void itx_lzw_resolve(uint8_t *out, uint32_t isize, const uint32_t *pl, const uint16_t *md, uint32_t n, uint16_t *src, uint32_t lane) {
+__device__ __forceinline__ void itx_lzw_resolve(uint8_t *out, uint32_t isize, const uint32_t *pl, const uint16_t *md, uint32_t n, uint16_t *src, uint8_t *data, uint32_t lane) {
     uint32_t k0 = 0;
     for (uint32_t w0 = 0; w0 < isize && k0 < n; w0 += W) {
         const uint32_t w1 = w0 + W < isize ? w0 + W : isize, cnt = w1 - w0;
         if ((__ldcg(pl + k0) & 0xffffu) >= w1) continue;                    /* nothing but literals in this window */
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(out + w0) & 15u);
+        uint8_t *a0 = out + w0 - skew;                                       /* 16-byte aligned; the stream buffer has slack on both sides */
+        const uint32_t span = (skew + cnt + 15u) & ~15u;
+        for (uint32_t i = lane * 16u; i < span; i += 512u) *reinterpret_cast<uint4 *>(data + i) = __ldcg(reinterpret_cast<const uint4 *>(a0 + i));
         itx_lzw_init(src, w0, cnt, lane);
         __syncwarp();
         for (uint32_t k = k0;; k += 32u) {
@@ -1422,20 +1427,38 @@ __device__ __forceinline__ void itx_lzw_resolve(uint8_t *out, uint32_t isize, co
         }
         __syncwarp();
         while (__any_sync(0xffffffffu, itx_lzw_jump(src, w0, cnt, lane))) { }
-        for (uint32_t i0 = lane; i0 < cnt; i0 += 128u) {
-            uint32_t sv[4]; uint8_t b[4];
+        uint8_t *dw = data + skew;
+        const uint32_t cnt_r = (cnt + 255u) & ~255u;                        /* cells past the window's end are their own sources (itx_lzw_init) */
+        for (uint32_t i0 = lane; i0 < cnt_r; i0 += 256u) {
+            uint32_t sv[8]; uint8_t b[8];
 #pragma unroll
-            for (uint32_t u = 0; u < 4u; u++) { const uint32_t i = i0 + 32u * u; sv[u] = i < cnt ? (uint32_t)src[i] : w0 + i; }
+            for (uint32_t u = 0; u < 8u; u++) sv[u] = (uint32_t)src[i0 + 32u * u];
 #pragma unroll
-            for (uint32_t u = 0; u < 4u; u++) b[u] = sv[u] != w0 + i0 + 32u * u ? __ldcg(out + sv[u]) : (uint8_t)0;
+            for (uint32_t u = 0; u < 8u; u++) b[u] = sv[u] < w0 ? __ldcg(out + sv[u]) : dw[sv[u] - w0];       /* a literal reads itself; a literal of the window is never changed here */
 #pragma unroll
-            for (uint32_t u = 0; u < 4u; u++) if (sv[u] != w0 + i0 + 32u * u) out[w0 + i0 + 32u * u] = b[u];
+            for (uint32_t u = 0; u < 8u; u++) dw[i0 + 32u * u] = b[u];
+        }
+        __syncwarp();
+        for (uint32_t i = lane * 16u; i < span; i += 512u) {
+            if (i >= skew && i + 16u <= skew + cnt) *reinterpret_cast<uint4 *>(a0 + i) = *reinterpret_cast<const uint4 *>(data + i);
+            else for (uint32_t j = 0; j < 16u; j++) if (i + j >= skew && i + j < skew + cnt) a0[i + j] = data[i + j];
         }
         __syncwarp();
     }
 }
+#ifndef ITX_LZW_W5
+#define ITX_LZW_W5 6144u
+#define ITX_LZW_W4 3072u
+#define ITX_LZW_W3 1536u
+#endif
+#ifndef ITX_INF_OCC4
+#define ITX_INF_OCC4 16
+#endif
+#ifndef ITX_INF_OCC5
+#define ITX_INF_OCC5 10
+#endif
 template <uint32_t LG>
-__global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(const itx_inflate_args A) {
+__global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? ITX_INF_OCC5 : ITX_INF_OCC4) k_inflate(const itx_inflate_args A) {
     extern __shared__ __align__(16) uint8_t itx_inf_smem[];
     constexpr uint32_t NL = 1u << LG;
     const uint32_t lane = threadIdx.x;
@@ -1470,7 +1493,7 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(
         __syncwarp();
         if (A.fuse_lz && A.m_cap) {
             /* the warp's blocks one after the other, all 32 lanes on each */
-            constexpr uint32_t W = LG == 5 ? 8192u : (LG == 4 ? 4096u : 2048u);             /* 2 W bytes of the warp's 640 << LG */
+            constexpr uint32_t W = LG == 5 ? ITX_LZW_W5 : (LG == 4 ? ITX_LZW_W4 : ITX_LZW_W3);      /* 2 W bytes of cells + W + 32 bytes of data in the warp's 640 << LG */
             const uint32_t nm = mine && I.state == ITX_ST_DONE ? I.n_match : 0u;
             const unsigned long long op = reinterpret_cast<unsigned long long>(I.out);
             for (uint32_t l = 0; l < NL; l++) {
@@ -1478,7 +1501,7 @@ __global__ void __launch_bounds__(ITX_INF_THREADS, LG == 5 ? 10 : 16) k_inflate(
                 if (!n_l) continue;
                 const uint32_t isz = __shfl_sync(0xffffffffu, I.out_pos, (int)l);
                 uint8_t *o_l = reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, op, (int)l));
-                itx_lzw_resolve<W>(o_l, isz, A.m_pl + (g0 + l) * A.m_cap, A.m_d + (g0 + l) * A.m_cap, n_l, reinterpret_cast<uint16_t *>(itx_inf_smem), lane);
+                itx_lzw_resolve<W>(o_l, isz, A.m_pl + (g0 + l) * A.m_cap, A.m_d + (g0 + l) * A.m_cap, n_l, reinterpret_cast<uint16_t *>(itx_inf_smem), itx_inf_smem + 2u * W, lane);
             }
         }
     }

@@ -531,7 +531,7 @@ int emu_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_c
     if (I.state == ITX_ST_OVERFLOW) return 99;
     if (defer >= 3 && rc == ITX_INF_OK) {
         /* itx_lzw_resolve (k_inflate's own second pass), lane by lane: windows of W bytes, the same per-lane pieces as the device */
-        const uint32_t W = defer == 3 ? 8192u : (defer == 4 ? 2048u : 64u), n = I.n_match, isize = I.out_pos;
+        const uint32_t W = defer == 3 ? 8192u : (defer == 4 ? 2048u : 256u), n = I.n_match, isize = I.out_pos;       /* multiples of 256 (itx_lzw_init) */
         std::vector<uint16_t> src(W);
         uint32_t k0 = 0;
         for (uint32_t w0 = 0; w0 < isize && k0 < n; w0 += W) {
