@@ -7,7 +7,7 @@ counters back on the host.
 
   value        reads/s with the uncompressed BAM stream already resident in HBM (kernels only)
   e2e          the same metric through the C-ABI call a caller makes with HOST buffers: itx_scan_bgzf_memory() on the BGZF
-               .bam image in pinned host memory -> cudaMemcpyAsync windows -> k_inflate + k_lz_resolve (BGZF blocks inflated
+               .bam image in pinned host memory -> cudaMemcpyAsync windows -> k_inflate (BGZF blocks inflated
                on the device) -> k_scan -> counter tables back on the host (itx_sync_counts), all inside the timed region
   e2e_file     the same from a FILE through itx_scan_alignments() (what the `iteres` command line does): a reader thread
                pread()s the file into a ring of pinned slots first.  The file lives on tmpfs / in the page cache (/dev/shm)
@@ -667,7 +667,7 @@ def main():
             log("e2e %s: %s ms" % (tag, " ".join("%.1f" % (1e3 * x) for x in times)))
             return {"value": total_rec / t, "unit": UNIT, "h2d_bytes_per_step": int(pe["h2d_bytes"]), "d2h_bytes_per_step": int(pe["d2h_bytes"]),
                     "s_per_step": t, "steps": len(times), "inflate_ms": pe["inflate_ms"], "bam_bytes": fsz,
-                    "inflate": "device: k_inflate (Huffman pass, one thread per BGZF block) + k_lz_resolve (match copies, one CTA per block), groups on 8 streams"}
+                    "inflate": "device: k_inflate (one thread per BGZF block decodes literals and lists matches, 16 blocks per warp; the warp then copies the matches of its blocks in shared-memory windows), launch groups on 8 streams"}
         e2e = run_e2e(lambda: ix.scan_bgzf_memory(pin, fsz, opts), "pinned image")
         e2e["api"] = "itx_scan_bgzf_memory(BGZF image in pinned host memory, deflate level 1) + itx_sync_counts"
         e2e_file = run_e2e(lambda: ix.scan_alignments(bam, opts), "file")

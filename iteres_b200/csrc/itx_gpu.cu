@@ -22,7 +22,7 @@
 #define ITX_SEEN_FAST 1024                 /* unknown-tid marks fetched with the end-of-scan report (BAM headers with more references take one more copy) */
 #define ITX_SCRATCH_BYTES (256 + ITX_SEEN_FAST * 4)
 #define ITX_MAX_WINDOWS 65536              /* launch groups of one scan that k_scan can log (more: the tuple path takes over) */
-#define ITX_INF_LANES_DEFAULT 32           /* blocks per k_inflate warp (ITX_INF_LANES), and for the last groups of a file (ITX_INF_TAIL_LANES) */
+#define ITX_INF_LANES_DEFAULT 16           /* blocks per k_inflate warp (ITX_INF_LANES), and for the last groups of a file (ITX_INF_TAIL_LANES) */
 #define ITX_INF_TAIL_LANES_DEFAULT 8
 #define ITX_INF_STREAMS 8                  /* inflate groups in flight: copy, Huffman pass, match pass and scan of different groups overlap */
 
@@ -1011,7 +1011,7 @@ typedef struct {
  * which gives every block its place in the uncompressed stream, and sends window and block table over PCIe on the copy
  * stream -- into a RING on the device when the file is larger than the ring (a window's place is recycled once the groups
  * that read it are done).  Blocks are handed to the device in groups: one k_inflate (Huffman decoding, literals, match
- * lists) + k_lz_resolve (match copies) pair per group on one of ITX_INF_STREAMS streams, and the scan kernels follow
+ * lists, then the match copies by the same warp) per group on one of ITX_INF_STREAMS streams, and the scan kernels follow
  * 64 MiB (the largest BAM record) behind the inflated front.  The stream's total size is only known at the end: the
  * stream buffer is sized from the first window's compression ratio and grown if that was too small.
  * sh != NULL: this is rank sh->rank of sh->nranks.  The rank owns the blocks that START in its share of the file's bytes
@@ -1087,9 +1087,9 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             cudaGetLastError();
         }
         wev = cu->inf_ev;
-        /* a group = a run of consecutive blocks handed to the device as one k_inflate + k_lz_resolve pair on one of
+        /* a group = a run of consecutive blocks handed to the device as one k_inflate launch on one of
          * ITX_INF_STREAMS streams.  A thread needs milliseconds for its block whatever the launch size, so groups are kept
-         * to a fraction of the resident threads and several are in flight: the file's copy, the two inflate passes and the
+         * to a fraction of the resident threads and several are in flight: the file's copy, the inflate passes and the
          * scan of successive groups overlap.  Towards the end of the file nothing is left to hide that latency behind:
          * the last groups are smaller and run fewer blocks per warp (shorter rounds). */
         if (!cu->inf_made) {
@@ -1118,9 +1118,11 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         }
         const uint64_t tab_stride = cu->d_tabs_threads / ITX_INF_STREAMS * ITX_T_CELLS;           /* cells per stream */
         int lz_ctas = 1;
-        /* ITX_LZ=1: k_lz_jump (pointer jumping, every thread busy, 192 KiB of shared memory per block in flight); default: k_lz_resolve
-         * (ordered batches, 64 KiB).  Measured on the B200 (3.4 GB file): the same 151 ms end to end -- k_lz_jump is several times
-         * faster per block, but its CTA needs a whole SM's shared memory, so it waits for every k_inflate warp there to finish */
+        /* the second pass (match copies).  ITX_LZ=2, the default: inside k_inflate, by the warp that decoded the blocks (itx_lzw_resolve:
+         * windows of the block in the warp's own shared memory, no second kernel).  ITX_LZ=0: k_lz_resolve, a CTA per block with the
+         * whole block in 64 KiB of shared memory -- its CTAs displace the decoding warps (20 KiB each), so the two passes ran one after
+         * the other in effect (140 ms per 3.4 GB file against 113 ms).  ITX_LZ=1: k_lz_jump (pointer jumping over the whole block,
+         * 192 KiB per CTA: it waits for every k_inflate warp of an SM to finish) */
         const int lz_mode = env_int("ITX_LZ", 2);
         const bool lz_jump = lz_mode == 1, lz_fused = lz_mode == 2;
         cudaFuncSetAttribute(k_lz_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_LZ2_SMEM);

@@ -46,7 +46,9 @@
 #define ITX_ST_COPY 4u         /* a match is being copied, ITX_COPY_STEP bytes per round (in-line mode only) */
 #define ITX_ST_OVERFLOW 5u     /* deferred mode: the block has more matches than its list holds */
 #define ITX_COPY_STEP 8u
+#ifndef ITX_BURST
 #define ITX_BURST 3u           /* literals decoded ahead of the general symbol of a round */
+#endif
 #define ITX_M_NONE 0xffffffffu /* match count of a block that overflowed or failed */
 
 ITX_HD uint32_t itx_brev32(uint32_t x) {
@@ -74,7 +76,7 @@ struct itx_inflater {
     uint32_t state, last, expect;
     uint32_t pend_len, pend_dist;          /* ITX_ST_COPY */
     /* deferred mode (m_cap != 0): literals go to their final place, matches are only LISTED -- entry k is
-     * (output position | length << 16, distance) -- and a second pass (k_lz_resolve) copies them while the block's
+     * (output position | length << 16, distance) -- and a second pass copies them while the block's
      * history is cache resident; a decoder that copies in line waits on a DRAM read of its own history every round */
     uint32_t *m_pl; uint16_t *m_d; uint32_t n_match, m_cap;
     uint32_t lc[8], dc[8];                 /* per-length code counts, two 16-bit counts per register */

@@ -1452,7 +1452,7 @@ __device__ __forceinline__ void itx_lzw_resolve(uint8_t *out, uint32_t isize, co
 #define ITX_LZW_W3 1536u
 #endif
 #ifndef ITX_INF_OCC4
-#define ITX_INF_OCC4 16
+#define ITX_INF_OCC4 18             /* 96 registers: 18 warps of 16 blocks per SM measured 4 % faster end to end than 16 warps at 112 */
 #endif
 #ifndef ITX_INF_OCC5
 #define ITX_INF_OCC5 10
