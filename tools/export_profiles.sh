@@ -21,3 +21,4 @@ for f in bench_full; do [ -f gpurun_out/${tag}_$f.json ] && cp gpurun_out/${tag}
     tools/sass_md5.sh
 } > $out/${tag}_sass.txt
 ls -la $out | grep ${tag}_
+[ -f $out/${tag}_launches.csv ] && python tools/launch_shares.py $out/${tag}_launches.csv > $out/${tag}_launch_shares.txt
