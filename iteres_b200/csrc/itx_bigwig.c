@@ -210,28 +210,56 @@ static void write_chrom_tree(FILE *f, const bw_chrom *chroms, uint32_t n, uint32
     free(key);
 }
 
-/* ---- compressed summary blocks + index (bbiWrite.c:478-536) */
-static uint64_t write_summaries(FILE *f, bw_sumlist *L, uint32_t block, uint32_t per_slot) {
-    uint32_t count = (uint32_t)L->n; W(f, count);
-    uLong cap = (uLong)(1.001 * (32.0 * per_slot) + 13);
-    uint8_t *unc = (uint8_t *)malloc(32 * (size_t)per_slot), *cmp = (uint8_t *)malloc(cap + 64);
-    size_t ix = 0;
-    while (ix < L->n) {
-        size_t m = L->n - ix < per_slot ? L->n - ix : per_slot; uint8_t *w = unc; uint64_t pos = (uint64_t)ftello(f);
-        for (size_t i = 0; i < m; i++, ix++) {
-            bw_sum *s = &L->v[ix];
+/* ---- compressed summary blocks + index (bbiWrite.c:478-536): the blocks (per_slot summaries each, independent zlib streams) are
+ * compressed by all host threads, then written in order */
+typedef struct { const bw_sumlist *L; uint32_t per_slot; size_t nblk, next; uint8_t **out; uLongf *out_len; } bw_sjob;
+static void *bw_sworker(void *arg) {
+    bw_sjob *J = (bw_sjob *)arg;
+    const uLong cap = (uLong)(1.001 * (32.0 * J->per_slot) + 13);
+    uint8_t *unc = (uint8_t *)malloc(32 * (size_t)J->per_slot);
+    for (;;) {
+        const size_t b = __atomic_fetch_add(&J->next, 1, __ATOMIC_RELAXED);
+        if (b >= J->nblk) break;
+        const size_t i0 = b * J->per_slot, m = J->L->n - i0 < J->per_slot ? J->L->n - i0 : J->per_slot; uint8_t *w = unc;
+        for (size_t i = 0; i < m; i++) {
+            const bw_sum *s = &J->L->v[i0 + i];
             memcpy(w, &s->chrom_id, 4); memcpy(w + 4, &s->start, 4); memcpy(w + 8, &s->end, 4); memcpy(w + 12, &s->valid, 4);
             memcpy(w + 16, &s->minv, 4); memcpy(w + 20, &s->maxv, 4); memcpy(w + 24, &s->sum, 4); memcpy(w + 28, &s->sumsq, 4);
-            w += 32; s->file_off = pos;
+            w += 32;
         }
-        uLongf cl = cap; compress(cmp, &cl, unc, (uLong)(w - unc));
-        fwrite(cmp, 1, cl, f);
+        uint8_t *cmp = (uint8_t *)malloc(cap + 64); uLongf cl = cap;
+        compress(cmp, &cl, unc, (uLong)(w - unc));
+        J->out[b] = cmp; J->out_len[b] = cl;
     }
+    free(unc);
+    return NULL;
+}
+static int bw_threads(size_t njobs) {
+    int T = (int)sysconf(_SC_NPROCESSORS_ONLN); if (T < 1) T = 1; if (T > 32) T = 32; if (njobs < 8) T = 1;
+    return T;
+}
+static uint64_t write_summaries(FILE *f, bw_sumlist *L, uint32_t block, uint32_t per_slot) {
+    uint32_t count = (uint32_t)L->n; W(f, count);
+    bw_sjob J; J.L = L; J.per_slot = per_slot; J.nblk = (L->n + per_slot - 1) / per_slot; J.next = 0;
+    J.out = (uint8_t **)calloc(J.nblk ? J.nblk : 1, sizeof(uint8_t *)); J.out_len = (uLongf *)calloc(J.nblk ? J.nblk : 1, sizeof(uLongf));
+    {
+        const int T = bw_threads(J.nblk); pthread_t th[32]; int started = 0;
+        for (int t = 1; t < T; t++) if (pthread_create(&th[started], NULL, bw_sworker, &J) == 0) started++;
+        bw_sworker(&J);
+        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    }
+    for (size_t b = 0; b < J.nblk; b++) {
+        const uint64_t pos = (uint64_t)ftello(f);
+        const size_t i0 = b * per_slot, m = L->n - i0 < per_slot ? L->n - i0 : per_slot;
+        for (size_t i = 0; i < m; i++) L->v[i0 + i].file_off = pos;
+        fwrite(J.out[b], 1, J.out_len[b], f); free(J.out[b]);
+    }
+    free(J.out); free(J.out_len);
     uint64_t index_off = (uint64_t)ftello(f);
     rkey *keys = (rkey *)malloc(sizeof(rkey) * (L->n ? L->n : 1));
     for (size_t i = 0; i < L->n; i++) { keys[i].chrom = L->v[i].chrom_id; keys[i].start = L->v[i].start; keys[i].end = L->v[i].end; keys[i].off = L->v[i].file_off; }
     write_rtree(f, keys, L->n, block, per_slot, index_off);
-    free(keys); free(unc); free(cmp);
+    free(keys);
     return index_off;
 }
 
@@ -263,10 +291,25 @@ static int is_space(int c) { return c == ' ' || (c >= 9 && c <= 13); }
 /* chrom_size(ctx, name) gives the chromosome size the reference would find in its size file, or -1 */
 int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, const char *name), void *ctx, const char *out_path, char err[ITX_ERRLEN]) {
     const uint32_t block = 256, per_slot = 1024;
+    const int timing = getenv("ITX_TIMING") != NULL; struct timespec bw_t0; clock_gettime(CLOCK_MONOTONIC, &bw_t0);
+#define BW_LAP(what) do { if (timing) { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); fprintf(stderr, "[itx timing] bigWig %s: %s at %.0f ms\n", out_path, what, (t1.tv_sec - bw_t0.tv_sec) * 1e3 + (t1.tv_nsec - bw_t0.tv_nsec) / 1e6); } } while (0)
     FILE *in = fopen(wig_path, "r");
     if (!in) { snprintf(err, ITX_ERRLEN, "Couldn't open %s , %s", wig_path, strerror(errno)); return ITX_EIO; }
+    /* the whole text in memory (a wiggle of `stat` is a few tens of MB: one number per consensus base), lines cut in place */
+    char *text = NULL; size_t tlen = 0;
+    {
+        size_t cap = 1u << 20; text = (char *)malloc(cap + 1);
+        for (;;) {
+            if (tlen == cap) { cap *= 2; text = (char *)realloc(text, cap + 1); }
+            const size_t r = fread(text + tlen, 1, cap - tlen, in);
+            if (!r) break;
+            tlen += r;
+        }
+        text[tlen] = 0;
+    }
+    fclose(in);
     bw_section *sec = NULL; size_t nsec = 0, csec = 0;
-    char *line = NULL; size_t lcap = 0; long lineno = 0; int rc = ITX_OK;
+    char *line = NULL, *next_line = text; long lineno = 0; int rc = ITX_OK;
     char *chrom = NULL; uint32_t cs = 0, span = 0, step = 0, pos = 0; float *vals = NULL; size_t nv = 0, cv = 0;
     int in_section = 0;
     /* one fixedStep declaration's values -> sections of <= per_slot values (bwgCreate.c:226-262) */
@@ -277,8 +320,24 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
             bw_section *S = &sec[nsec++]; S->chrom = chrom; S->start = st; st += (uint32_t)m * step; S->end = st - step + span; S->step = step; S->span = span; \
             S->count = (uint16_t)m; S->val = (float *)malloc(sizeof(float) * m); memcpy(S->val, vals + k, sizeof(float) * m); k += m; S->chrom_id = 0; S->file_off = 0; } \
         nv = 0; } while (0)
-    while (rc == ITX_OK && getline(&line, &lcap, in) >= 0) {
+    while (rc == ITX_OK && next_line < text + tlen) {
+        line = next_line;
         lineno++;
+        if (in_section && *line >= '0' && *line <= '9') {
+            /* the line every wiggle of `stat` is made of: a plain count and a newline */
+            const char *q = line; uint64_t acc = 0; int nd = 0;
+            while (*q >= '0' && *q <= '9' && nd < 15) { acc = acc * 10 + (uint64_t)(*q - '0'); q++; nd++; }
+            if (*q == '\n' && pos + (uint32_t)nv * step + span <= cs) {
+                if (nv == cv) { cv = cv ? cv * 2 : 4096; vals = (float *)realloc(vals, cv * sizeof(float)); }
+                vals[nv++] = (float)(double)acc;
+                next_line = (char *)q + 1;
+                continue;
+            }
+        }
+        {   /* any other line: cut at its end, then word by word as before */
+            char *nl = (char *)memchr(line, '\n', (size_t)(text + tlen - line));
+            if (nl) { *nl = 0; next_line = nl + 1; } else next_line = text + tlen;
+        }
         char *s = line; while (is_space(*s)) s++;
         if (!*s || *s == '#') continue;
         if (!in_section && nsec == 0 && (strncmp(s, "browser", 7) == 0 || strncmp(s, "track", 5) == 0)) continue;
@@ -331,7 +390,8 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
     }
     if (rc == ITX_OK && in_section) FLUSH();
 #undef FLUSH
-    free(line); fclose(in); free(vals);
+    BW_LAP("wig text parsed");
+    free(text); free(vals);
     if (rc == ITX_OK && nsec == 0) { snprintf(err, ITX_ERRLEN, "%s is empty of data", wig_path); rc = ITX_EFORMAT; }
     if (rc != ITX_OK) { for (size_t i = 0; i < nsec; i++) free(sec[i].val); free(sec); return rc; }
 
@@ -393,6 +453,7 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
             if (items <= nchrom) break;
         }
     }
+    BW_LAP("sections sorted, zoom levels reduced");
     FILE *f = fopen(out_path, "wb");
     if (!f) { snprintf(err, ITX_ERRLEN, "Can't open %s to write: %s", out_path, strerror(errno)); rc = ITX_EIO; goto done; }
     {
@@ -428,6 +489,7 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
             }
             free(J.out); free(J.out_len);
         }
+        BW_LAP("sections compressed and written");
         index_off = (uint64_t)ftello(f);
         {
             rkey *keys = (rkey *)malloc(sizeof(rkey) * nsec);
@@ -436,6 +498,7 @@ int itx_bigwig_from_wig(const char *wig_path, long (*chrom_size)(void *ctx, cons
             free(keys);
         }
         for (int i = 0; i < nzoom; i++) { zoom_data[i] = (uint64_t)ftello(f); zoom_index[i] = write_summaries(f, &zoom[i], block, per_slot); }
+        BW_LAP("index and zoom summaries written");
         if (zoom[0].n) {
             const bw_sum *s = &zoom[0].v[0];
             uint64_t vc = s->valid; double mn = s->minv, mx = s->maxv, sd = s->sum, sq = s->sumsq;

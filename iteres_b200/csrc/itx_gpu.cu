@@ -1072,6 +1072,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         }
         if (!(h = bam_header_from_src(ix, S, o->addChr, nth, err))) { rc = ITX_EFORMAT; break; }
         if ((rc = comp_reader_open(&R, cu, S, r_begin, flen, Wc, nth, err))) break;
+        if (timing) fprintf(stderr, "[itx timing] header parsed, reader open (pinned slots) at %.1f ms\n", now_ms() - tm0);
         reader_open = true;
         /* the compressed bytes on the device: the whole range when it fits the ring, else a ring */
         uint64_t ring_cap = (uint64_t)env_int("ITX_COMP_RING_MB", 8192) << 20;
@@ -1079,6 +1080,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
         { const uint64_t whole = flen - r_begin + ITX_RD_HEAD; if (!sharded && whole < ring_cap) ring_cap = whole; else if (sharded && (r_end - r_begin) + (sh->margin + (4u << 20)) * 2 + ITX_RD_HEAD < ring_cap) ring_cap = (r_end - r_begin) + (sh->margin + (4u << 20)) * 2 + ITX_RD_HEAD; }
         if ((rc = grow_device(cu, (void **)&cu->d_comp, &cu->d_comp_cap, ring_cap + ITX_SLACK, 0, "the compressed bytes", err))) break;
         ring_cap = cu->d_comp_cap - ITX_SLACK;                /* a larger buffer left by an earlier scan is used whole */
+        if (timing) fprintf(stderr, "[itx timing] compressed ring on the device (%.2f GB) at %.1f ms\n", (double)cu->d_comp_cap / 1e9, now_ms() - tm0);
         cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&begin_ev, cudaEventDisableTiming);
         if (!cu->inf_ev) {
@@ -1138,6 +1140,7 @@ static int scan_bgzf_device_inflate(itx_index *ix, const itx_bgzf_src *S, const 
             cu->d_m_slots = ns;
         }
         const uint64_t m_stride = cu->d_m_slots / ITX_INF_STREAMS;
+        if (timing) fprintf(stderr, "[itx timing] inflate tables and match lists (%.2f GB) at %.1f ms\n", (double)cu->d_m_slots * ITX_M_WORST * 6 / 1e9, now_ms() - tm0);
         const uint64_t MARGIN = (64ull << 20) + 65536;      /* a record is at most 2^26 bytes long: chunks this far behind the inflated front are safe to scan */
         uint64_t cur = r_begin, gb0 = 0, n_groups = 0, cabs = 0, own_total = ~0ull, typical_group_bytes = GROUP * 24576ull;
         bool ended = false, own_closed = false;

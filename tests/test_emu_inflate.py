@@ -30,6 +30,8 @@ def samples():
         "ramp": bytes(range(256)) * 250,
         "short_periods": b"".join(bytes([65 + i % 26]) * (3 + i % 7) + b"xyz" * (2 + i % 5) + b"abcdefg" * 3 for i in range(2500))[:65000],
         "triples": bytes(rnd.choice(b"ab") for _ in range(65000)),       # dense 3..6-byte matches: long match lists
+        # the largest block BGZF allows (ISIZE 65536: positions fill 16 bits, the last window of the match copies is cut short)
+        "max_block": (b"".join(bytes([65 + i % 26]) * (3 + i % 7) + b"xyz" * (2 + i % 5) + bytes(rnd.randrange(256) for _ in range(i % 11)) for i in range(4000)))[:65536],
     }
     s = synth.Synth(0, 2000, seed=5)
     for mode in (0, 1, 2):

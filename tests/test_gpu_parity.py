@@ -193,9 +193,34 @@ def test_device_inflate_matches_host_inflate(level, worlds, tmp_path, monkeypatc
     ora.close()
 
 
+@pytest.mark.parametrize("lz", ["2", "0", "1"])
+@pytest.mark.parametrize("block", [65536, 0xff00, 6144 + 1, 3072, 257, 40])
+def test_bgzf_blocks_of_every_size_and_every_match_copy_pass(block, lz, worlds, tmp_path, monkeypatch):
+    """BGZF blocks from the largest the format allows (ISIZE 65536: positions fill 16 bits) down to a few bytes, cut at the edges of
+    the match-copy windows, through the three second passes (ITX_LZ=2 inside k_inflate, 0 k_lz_resolve, 1 k_lz_jump): the stream on
+    the device is the stream that was compressed, byte for byte"""
+    import bamio
+    monkeypatch.delenv("ITX_INFLATE", raising=False)
+    monkeypatch.setenv("ITX_LZ", lz)
+    s, (cs, rs, rm), _ = worlds(1, 60000)
+    buf, n, _ = s.stream(1, 6000 if block >= 3072 else 600)
+    raw = buf[:n].tobytes()
+    bam = str(tmp_path / "reads.bam")
+    with open(bam, "wb") as f:
+        for i in range(0, n, block):
+            f.write(bamio.bgzf_block(raw[i:i + block], 6 if (i // block) % 3 else 1))
+        f.write(bamio.EOF_BLOCK)
+    ix = capi.Index(cs, rs, rm)
+    want = ix.scan_bam_host(buf.ctypes.data, n, capi.default_opts())
+    ix.reset()
+    assert ix.scan_alignments(bam, capi.default_opts()) == want
+    assert ix.stream_fetch(n + 100) == raw
+    ix.close()
+
+
 @pytest.mark.parametrize("mode,level", [(0, 1), (1, 6), (2, 9), (2, 0)])
 def test_device_inflate_reproduces_the_stream_byte_for_byte(mode, level, worlds, tmp_path, monkeypatch):
-    """k_inflate + k_lz_resolve against the bytes the generator compressed (file entry and memory-image entry)"""
+    """k_inflate (decoding and match copies) against the bytes the generator compressed (file entry and memory-image entry)"""
     monkeypatch.delenv("ITX_INFLATE", raising=False)
     s, (cs, rs, rm), _ = worlds(1, 60000)
     bam = str(tmp_path / "reads.bam")

@@ -34,7 +34,8 @@ def main():
     t, p = run(ours, ["stat", "-o", "o_small"] + tables + [small], d)
     out["ours_small"] = {"reads": a.ref_reads, "wall_s": t, "rc": p.returncode}
     t, p = run(ours, ["stat", "-o", "o_big"] + tables + [big], d)
-    out["ours_big"] = {"reads": a.reads, "wall_s": t, "rc": p.returncode, "bam_bytes": os.path.getsize(big)}
+    out["ours_big"] = {"reads": a.reads, "wall_s": t, "rc": p.returncode, "bam_bytes": os.path.getsize(big),
+                       "timeline": [l.replace("[itx timing] ", "") for l in p.stderr.splitlines() if l.startswith("[itx timing]") and "inflate group" not in l]}    # with ITX_TIMING=1
     if os.path.exists(ref):
         t, p = run(ref, ["stat", "-o", "r_small"] + tables + [small], d)
         out["reference_small"] = {"reads": a.ref_reads, "wall_s": t, "rc": p.returncode}
