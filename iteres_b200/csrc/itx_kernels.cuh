@@ -1064,7 +1064,10 @@ struct itx_xa_args {
     const unsigned long long *q; uint32_t *q_n; unsigned long long q_cap;      /* q_n: [0] entries, [1] CTAs done (the last one zeroes both) */
     int32_t sign; uint32_t flags;
 };
-__global__ void __launch_bounds__(256, 2) k_xa(const itx_xa_args A) {
+#ifndef ITX_XA_OCC
+#define ITX_XA_OCC 4                 /* 64 registers, 32 warps per SM: the kernel waits on scattered table and record reads (11.2 -> 9.3 ms per 30 M reads of cfg 3 against 24 warps at 80 registers; 48 registers spill and lose again) */
+#endif
+__global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
     const itx_dev_index &D = A.D;
     __shared__ uint32_t sh_c[3];
     if (threadIdx.x < 3) sh_c[threadIdx.x] = 0;

@@ -89,6 +89,9 @@ if what == "scan":
     scan_variants("SE-50", 0, reads, V_SCAN)
     scan_variants("PE-100", 2, reads // 2, [V_SCAN[0], V_SCAN[2], V_SCAN[3], V_SCAN[6]])
     scan_variants("SE-75+XA", 1, reads * 3 // 5, [("r1 (15)", {"ITX_SCAN_FLAGS": "15"}), ("early,serial XA (31)", {"ITX_SCAN_FLAGS": "31"}), ("default (95)", {})], steps=5)
+elif what == "xa":
+    # the SE-75 + XA:Z stream (cfg 3's shape) through the product kernels: k_scan + k_xa per step
+    scan_variants("SE-75+XA", 1, reads * 3 // 5, [("product", {})], steps=10)
 elif what == "ncu1":
     # ONE launch of k_scan (after two warm-up launches) on the stream AB_MODE / AB_READS name, with the environment as it is
     mode = int(os.environ.get("AB_MODE", "0"))
@@ -159,7 +162,7 @@ elif what == "e2e":
         for k in ("ITX_INF_LANES", "ITX_INF_TAIL_LANES", "ITX_INF_GROUP", "ITX_INF_TAIL_GROUP", "ITX_TIMING", "ITX_LZ"):
             os.environ.pop(k, None)
         os.environ.update(env)
-        for api in (("pinned", "file") if tag == variants[0][0] else ("pinned",)):
+        for api in (("pinned", "file") if tag == variants[0][0] or os.environ.get("AB_E2E_FILE") else ("pinned",)):
             ts = []
             for i in range(4):
                 if i == 3 and api == "pinned":
