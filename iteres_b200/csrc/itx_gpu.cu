@@ -31,7 +31,7 @@ struct itx_cuda {
     int sm_count; size_t smem_optin;
     /* index */
     itx_dev_index D;
-    void *d_iv, *d_bucket, *d_chrom_bucket, *d_cinfo, *d_sinfo, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
+    void *d_iv, *d_ivf, *d_bucket, *d_chrom_bucket, *d_cinfo, *d_sinfo, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
     void *d_sub_len, *d_sub_bp_off, *d_sub_fold;
     /* counter block */
     void *d_u64; size_t n_u64;           /* cnt[16] + grp */
@@ -48,7 +48,7 @@ struct itx_cuda {
     long long *d_sel; int want_sel;
     unsigned long long *h_scratch;                            /* pinned: [0] the carry a scan uploads (no wait for the copy); from byte 64 the end-of-scan report:
                                                                * cnt[16] u64, status[8] u32, first bad launch group u32, then (byte 256) the first ITX_SEEN_FAST unknown-tid marks */
-    unsigned long long *d_xa_q; uint64_t xa_cap; uint32_t *d_xa_n;      /* k_scan -> k_xa: record offsets of the reads whose XA:Z alternates have to be looked at */
+    unsigned long long *d_xa_q; uint64_t xa_cap; uint32_t *d_xa_n; int xa_attr;      /* k_scan -> k_xa: record offsets of the reads whose XA:Z alternates have to be looked at */
     unsigned long long *d_carry_log; uint32_t *d_fused;      /* k_scan: carry per window; [0] first bad window, [1] CTA ticket */
     int scan_ctas[6];                                         /* resident CTAs per SM of the k_scan instances */
     uint32_t *d_work; int decode_variant;   /* 0: k_decode_span (TMA staged stages, chain carried inside a span), 1: k_decode (thread per chunk) */
@@ -109,7 +109,7 @@ template <typename T> static int upload(void **dst, const T *src, size_t n, char
 static void cuda_free_all(itx_cuda *cu) {
     if (!cu) return;
     cudaSetDevice(cu->device);
-    void *ptrs[] = {cu->d_iv, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
+    void *ptrs[] = {cu->d_iv, cu->d_ivf, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
                     cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_D, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused, cu->d_snap, cu->d_shard, cu->d_xa_q, cu->d_xa_n};
@@ -201,7 +201,7 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         CKN(cudaStreamCreateWithFlags(&cu->stream, cudaStreamNonBlocking));
         CKN(cudaStreamCreateWithFlags(&cu->copy_stream, cudaStreamNonBlocking));
         const size_t ne = (size_t)ix->n_elem; const int32_t nc = ix->chroms.n, ns = ix->subs.n, nf = ix->fams.n, ncl = ix->clas.n;
-        if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_bucket, ix->bucket, (size_t)ix->n_bucket, err) ||
+        if (upload(&cu->d_iv, ix->iv, ne, err) || upload(&cu->d_ivf, ix->ivf, ne, err) || upload(&cu->d_bucket, ix->bucket, (size_t)ix->n_bucket, err) ||
             upload(&cu->d_chrom_bucket, ix->chrom_bucket, (size_t)nc + 1, err) || upload(&cu->d_cinfo, ix->cinfo, (size_t)nc, err) ||
             upload(&cu->d_sinfo, ix->sinfo, (size_t)ns, err) || upload(&cu->d_meta, ix->meta, ne, err) ||
             upload(&cu->d_meta2, ix->meta2, ne, err) || upload(&cu->d_chrom_off, ix->chrom_off, (size_t)nc + 1, err) ||
@@ -237,7 +237,7 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         CKN(cudaFuncSetAttribute(k_decode_span, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CKN(cudaFuncSetAttribute(k_lz_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         itx_dev_index &D = cu->D;
-        D.iv = (const itx_iv *)cu->d_iv; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
+        D.iv = (const itx_iv *)cu->d_iv; D.ivf = (const itx_iv *)cu->d_ivf; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
         D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool;
@@ -642,7 +642,8 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
         uint64_t blocks = ((uint64_t)n * cu->C / 42 + 255) / 256, most = (uint64_t)cu->sm_count * 8;
         if (blocks > most) blocks = most;
         if (blocks < 1) blocks = 1;
-        k_xa<<<(unsigned)blocks, 256, 0, cu->stream>>>(X);
+        if (!cu->xa_attr) { cudaFuncSetAttribute(k_xa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_XA_SMEM); cu->xa_attr = 1; }
+        k_xa<<<(unsigned)blocks, 256, ITX_XA_SMEM, cu->stream>>>(X);
         sc->n_launch++;
     }
     return ITX_OK;

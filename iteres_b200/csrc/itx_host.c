@@ -445,6 +445,9 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
     ix->sub_bp_off[ns] = off; ix->bp_len = off;
     ix->sinfo = (itx_subinfo *)calloc((size_t)(ns ? ns : 1), sizeof(itx_subinfo));
     for (int32_t s = 0; s < ns; s++) { ix->sinfo[s].len = ix->sub_len[s]; ix->sinfo[s].fold = ix->sub_fold[s]; ix->sinfo[s].bp_off = ix->sub_bp_off[s]; }
+    /* what the walk of an XA:Z alternate looks at (generic.c:318-334: overlap, then sameWord on the subfamily names), 16 bytes per element */
+    ix->ivf = (itx_iv *)malloc(sizeof(itx_iv) * ne);
+    for (long long i = 0; i < nraw; i++) { ix->ivf[i] = ix->iv[i]; ix->ivf[i].row = (uint32_t)ix->sub_fold[ix->meta[i].sub]; }
     if (ix->n_bucket >= 0xffffffffLL) { snprintf(err, ITX_ERRLEN, "genome too large for the position buckets"); return ITX_ENOTSUP; }
     ix->cinfo = (itx_chrominfo *)calloc((size_t)(nchrom ? nchrom : 1), sizeof(itx_chrominfo));
     for (int32_t c = 0; c < nchrom; c++) {
@@ -466,7 +469,7 @@ void itx_host_index_free(struct itx_index *ix) {
     }
     itx_strtab_free(&ix->subs); itx_strtab_free(&ix->fams); itx_strtab_free(&ix->clas); itx_strtab_free(&ix->warned);
     free(ix->sub); free(ix->fam); free(ix->cla); free(ix->sub_len); free(ix->sub_bp_off); free(ix->sub_fold);
-    free(ix->iv); free(ix->bucket); free(ix->chrom_bucket); free(ix->cinfo); free(ix->sinfo); free(ix->meta); free(ix->meta2); free(ix->el_chrom); free(ix->row2el);
+    free(ix->iv); free(ix->ivf); free(ix->bucket); free(ix->chrom_bucket); free(ix->cinfo); free(ix->sinfo); free(ix->meta); free(ix->meta2); free(ix->el_chrom); free(ix->row2el);
     free(ix->bp); free(ix->bp_u); free(ix->bp_cpg); free(ix->el_cnt); free(ix->el_cnt_u); free(ix->el_cpg); free(ix->el_cpg_score);
     free(ix->row_cnt); free(ix->row_cnt_u);
     free(ix->sub_order); free(ix->fam_order); free(ix->cla_order);

@@ -47,6 +47,7 @@ typedef struct { uint32_t len; int32_t fold; unsigned long long bp_off; } itx_su
 
 typedef struct {
     const itx_iv *iv; const itx_meta *meta; const itx_meta2 *meta2;
+    const itx_iv *ivf;                   /* iv with the element's case-folded subfamily id in place of its row: all the walk of an XA:Z alternate needs, in one load */
     const itx_chrominfo *cinfo; const itx_subinfo *sinfo;
     const uint32_t *bucket; const long long *chrom_bucket;   /* bucket[chrom_bucket[c] + (pos >> ITX_BSH)], (size >> ITX_BSH) + 2 entries per chromosome */
     const long long *chrom_off;          /* n_chrom + 1 */
@@ -124,6 +125,7 @@ struct itx_index {
     long long n_elem, n_rows;
     long long n_kept;                    /* rows that passed the -n/-c/-f filter, before rows on chromosomes missing from the size file were dropped (repeat_num, generic.c:1593) */
     itx_iv *iv; itx_meta *meta; itx_meta2 *meta2; int32_t *el_chrom;   /* sorted order */
+    itx_iv *ivf;                         /* iv with sub_fold[meta.sub] in place of the row (mapped2diffSubfam's walks) */
     uint32_t *bucket; long long *chrom_bucket; long long n_bucket;
     itx_chrominfo *cinfo; itx_subinfo *sinfo;
     long long *row2el;                   /* rmsk row -> sorted element index or -1 */

@@ -150,16 +150,6 @@ struct itx_src_stage {
         for (int j = 0; j < 9; j++) x[j] = itx_funnel_r(w[j], w[j + 1], sh);
     }
 };
-/* the same bytes when the caller knows that everything it will read lies inside the staged bytes: no bounds tests */
-struct itx_src_flat {
-    const uint8_t *buf; unsigned long long base;
-    __device__ __forceinline__ uint8_t u8(uint64_t off) const { return buf[(uint32_t)off - (uint32_t)base]; }
-    __device__ __forceinline__ uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(buf + ((uint32_t)aligned_off - (uint32_t)base)); }
-    __device__ __forceinline__ uint32_t u32(uint64_t off) const {
-        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
-        return itx_funnel_r(w32(a), w32(a + 4), sh);
-    }
-};
 /* A warp per span (= "chunk" of the bookkeeping, A.C bytes, a multiple of ITX_STAGE).  Only the span's first
  * record start is GUESSED (out of the span's first stage, checked against the previous span by k_verify / k_fixup);
  * inside the span the chain is carried from one 4 KiB stage to the next.  Each stage (+1 KiB margin) arrives
@@ -1067,12 +1057,24 @@ struct itx_xa_args {
 #ifndef ITX_XA_OCC
 #define ITX_XA_OCC 4                 /* 64 registers, 32 warps per SM: the kernel waits on scattered table and record reads (11.2 -> 9.3 ms per 30 M reads of cfg 3 against 24 warps at 80 registers; 48 registers spill and lose again) */
 #endif
+#ifndef ITX_XA_POOL
+#define ITX_XA_POOL 6144u            /* bytes of shared memory per warp for the aux areas of its 32 reads (192 per read; what does not fit waits for the next pass) */
+#endif
+#define ITX_XA_SMEM (8u * ITX_XA_POOL)
+__device__ __forceinline__ void itx_cp_async16_cg(void *smem_dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
+/* The aux areas are parsed out of SHARED memory.  Round 2's first k_xa read them byte by byte with __ldg (1.4 G sector requests
+ * and 2.9 G warp-instructions per 9 M reads, most of them waiting on L1): here the warp first brings the aux areas of its reads
+ * over with 16-byte cp.async -- packed one behind the other in the warp's pool, as many reads per pass as fit -- and every parser
+ * (tag walk, piece count, field split, strtol, chromosome name) then runs on itx_src_flat, without bounds tests and without a
+ * global load.  An aux area larger than the pool takes the one-lane walk over global memory. */
 __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
+    extern __shared__ __align__(16) uint8_t itx_xa_smem[];
     const itx_dev_index &D = A.D;
     __shared__ uint32_t sh_c[3];
     if (threadIdx.x < 3) sh_c[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
+    uint8_t *pool = itx_xa_smem + (threadIdx.x >> 5) * ITX_XA_POOL;
     const unsigned long long n = __ldcg(A.q_n) < A.q_cap ? __ldcg(A.q_n) : A.q_cap;
     const bool neg = A.sign < 0, stat = A.o.filter == 0 && D.stat_mode, coop = A.flags & ITX_SCAN_XACOOP;
     const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
         bool go = idx < n;
         itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
         long long sel = -1; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
-        uint64_t xa = 0, aend = 0; int32_t nm = 0, fold = 0;
+        uint64_t a0 = 0, aend = 0; int32_t fold = 0;
         if (go) {
             const unsigned long long rp = __ldcs(A.q + idx);
             uint32_t x[9]; G.core(rp, x);
@@ -1101,61 +1103,95 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
                 }
             }
             if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
-            uint64_t a0; itx_aux_range(rp, x, &a0, &aend);
-            xa = itx_aux_find(G, a0, aend, 'X', 'A');
-            go = sel >= 0 && xa && xa < aend;                      /* always true: k_scan queued the read for exactly this */
-            if (go) { nm = itx_aux2i(G, itx_aux_find(G, a0, aend, 'N', 'M'), aend); fold = D.sinfo[D.meta[sel].sub].fold; }
+            itx_aux_range(rp, x, &a0, &aend);
+            go = sel >= 0 && a0 < aend;                            /* always true: k_scan queued the read because it is counted and carries XA */
+            if (go) fold = (int32_t)__ldg(&D.ivf[sel].row);
         }
         const int32_t qlen = (int32_t)(T.end - T.start);
-        bool diffsub = false;
-        if (coop) {
-            /* every owner counts the pieces of its own list; the pieces of the 32 reads are numbered across the warp */
-            uint32_t np = 0, sp0 = 0, sp1 = 0, packed = 0; uint64_t zs = 0, ze = 0;
-            if (go) {
-                const uint8_t ty = G.u8(xa);
-                if (ty == 'Z' || ty == 'H') { uint32_t sp[2]; bool pk; zs = xa + 1; np = itx_xa_count_pack(G, zs, aend, &ze, sp, &pk); sp0 = sp[0]; sp1 = sp[1]; packed = pk ? 1u : 0u; }
+        /* the aux area, 16-byte granules around it (stream buffers are 16-byte aligned and carry 64 bytes of slack) */
+        const uint64_t base = a0 & ~15ull;
+        const uint32_t need = go ? (uint32_t)((aend - base + 15ull) & ~15ull) : 0u;
+        /* inside the pool offsets are 32 bits wide and relative to `base` (the parsers do half the work per byte of a 64-bit walk) */
+        const uint32_t a0r = (uint32_t)(a0 - base), aendr = go ? (uint32_t)(aend - base) : 0u;
+        bool big = go && (!coop || aend - base > (uint64_t)(ITX_XA_POOL - 16u));
+        bool pending = go && !big, diffsub = false;
+        uint32_t n_bad = 0;
+        while (__any_sync(0xffffffffu, pending)) {
+            /* this pass: the pending reads whose aux areas fit the pool, in lane order */
+            const uint32_t nd = pending ? need : 0u;
+            uint32_t incl_b = nd;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl_b, d); if (lane >= (uint32_t)d) incl_b += t; }
+            const bool in = pending && incl_b <= ITX_XA_POOL;
+            const uint32_t off = incl_b - nd;
+            __syncwarp();                                          /* the readers of the previous pass are done with the pool */
+            for (uint32_t m = __ballot_sync(0xffffffffu, in); m; m &= m - 1u) {
+                const int r = __ffs((int)m) - 1;
+                const uint64_t b_r = __shfl_sync(0xffffffffu, base, r);
+                const uint32_t nd_r = __shfl_sync(0xffffffffu, nd, r), off_r = __shfl_sync(0xffffffffu, off, r);
+                for (uint32_t c = lane * 16u; c < nd_r; c += 512u) itx_cp_async16_cg(pool + off_r + c, A.b + b_r + c);
             }
+            itx_cp_async_wait_all();
+            __syncwarp();
+            /* every owner: XA and NM (bam_aux_get), the pieces of its list counted */
+            uint32_t np = 0, sp0 = 0, sp1 = 0, packed = 0, zs = 0, ze = 0; int32_t nm = 0;
+            if (in) {
+                const itx_src_flat S{pool + off, 0ull};
+                const uint32_t xa = itx_aux_find(S, a0r, aendr, 'X', 'A');
+                const uint32_t nmo = xa == 0xffffffffu ? xa : itx_aux_find(S, a0r, aendr, 'N', 'M');
+                if (xa == 0xffffffffu || nmo == 0xffffffffu) big = true;   /* a corrupt array count in the aux area: the 64-bit walk over global memory decides */
+                else if (xa && xa < aendr) {
+                    nm = itx_aux2i(S, nmo, aendr);
+                    const uint8_t ty = S.u8(xa);
+                    if (ty == 'Z' || ty == 'H') { uint32_t sp[2]; bool pk; zs = xa + 1u; np = itx_xa_count_pack(S, zs, aendr, &ze, sp, &pk); sp0 = sp[0]; sp1 = sp[1]; packed = pk ? 1u : 0u; }
+                } else go = false;                                 /* (never: k_scan saw the tag) */
+            }
+            /* the pieces of the pass are numbered across the warp and handed out 32 at a time, one lane per alternate */
             uint32_t incl = np;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), base = incl - np;
-            bool found = false; uint32_t n_bad = 0;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), pbase = incl - np;
+            bool found = false;
             for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
-                const uint32_t gi = b0 + lane;                 /* this lane's piece of the batch */
+                const uint32_t gi = b0 + lane;                     /* this lane's piece of the batch */
                 /* its owner: the first lane whose running count exceeds gi (the counts never decrease along the warp) */
                 uint32_t ow = 0;
 #pragma unroll
                 for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + st - 1u)); if (v <= gi) ow += st; }
                 ow &= 31u;
-                const uint32_t o_base = __shfl_sync(0xffffffffu, base, (int)ow);
-                const uint64_t o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
+                const uint32_t o_base = __shfl_sync(0xffffffffu, pbase, (int)ow), o_off = __shfl_sync(0xffffffffu, off, (int)ow);
+                const uint32_t o_zs = __shfl_sync(0xffffffffu, zs, (int)ow), o_ze = __shfl_sync(0xffffffffu, ze, (int)ow);
                 const int32_t o_nm = __shfl_sync(0xffffffffu, nm, (int)ow), o_fold = __shfl_sync(0xffffffffu, fold, (int)ow), o_qlen = __shfl_sync(0xffffffffu, qlen, (int)ow);
                 const uint32_t o_np = __shfl_sync(0xffffffffu, np, (int)ow), o_packed = __shfl_sync(0xffffffffu, packed, (int)ow);
                 uint32_t o_sp[2]; o_sp[0] = __shfl_sync(0xffffffffu, sp0, (int)ow); o_sp[1] = __shfl_sync(0xffffffffu, sp1, (int)ow);
                 bool hit = false, mal = false;
                 if (gi < total) {
-                    uint64_t ps, pe;
+                    const itx_src_flat So{pool + o_off, 0ull};
+                    uint32_t ps, pe;
                     const uint32_t k = gi - o_base;
                     if (o_packed && k < 8u) itx_xa_piece_bounds(o_zs, o_ze, o_np, o_sp, k, &ps, &pe);      /* the owner noted where its first ';' are */
-                    else itx_xa_kth(G, o_zs, o_ze, k, &ps, &pe);
-                    if (pe > ps) hit = itx_xa_piece(D, G, ps, pe, o_nm, o_qlen, o_fold, &mal);
+                    else itx_xa_kth(So, o_zs, o_ze, k, &ps, &pe);
+                    if (pe > ps) hit = itx_xa_piece(D, So, ps, pe, o_nm, o_qlen, o_fold, &mal);
                 }
                 const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
-                if (np && !found && base < b0 + 32u && incl > b0) {
-                    const uint32_t lo_b = base > b0 ? base - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
+                if (np && !found && pbase < b0 + 32u && incl > b0) {
+                    const uint32_t lo_b = pbase > b0 ? pbase - b0 : 0u, hi_b = incl - b0 < 32u ? incl - b0 : 32u;
                     const uint32_t range = (hi_b >= 32u ? 0xffffffffu : (1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
                     const uint32_t h = m_hit & range;
                     if (h) { found = true; n_bad += (uint32_t)__popc(m_mal & range & ((1u << ((uint32_t)__ffs((int)h) - 1u)) - 1u)); }
                     else n_bad += (uint32_t)__popc(m_mal & range);
                 }
             }
-            diffsub = found;
-            if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
-        } else if (go) {
-            uint32_t bad = 0;
-            diffsub = itx_xa_walk(*A.Dg, G, xa, aend, nm, fold, qlen, &bad);
-            if (bad) atomicAdd(&D.status[2], neg ? 0u - bad : bad);
+            if (in) { diffsub = found; pending = false; }
         }
+        if (big && go) {                                           /* an aux area that does not fit the pool (or the A/B switch): one lane, global memory */
+            const uint64_t xa = itx_aux_find(G, a0, aend, 'X', 'A');
+            if (xa && xa < aend) {
+                const int32_t nm = itx_aux2i(G, itx_aux_find(G, a0, aend, 'N', 'M'), aend);
+                diffsub = itx_xa_walk(*A.Dg, G, xa, aend, nm, fold, qlen, &n_bad);
+            } else go = false;
+        }
+        if (n_bad) atomicAdd(&D.status[2], neg ? 0u - n_bad : n_bad);
         const bool uniq = T.info & ITX_F_UNIQ, counted = go && !diffsub;
         const uint32_t m_cnt = __ballot_sync(0xffffffffu, counted);
         c_diff += (uint32_t)__popc(__ballot_sync(0xffffffffu, go && diffsub));

@@ -104,6 +104,18 @@ struct itx_src_ring {
     }
 };
 
+/* Bytes staged linearly (shared memory on the device) when the caller knows that everything it will read lies inside the staged
+ * bytes: buf[0] is the byte at offset `base`; no bounds tests */
+struct itx_src_flat {
+    const uint8_t *buf; unsigned long long base;
+    ITX_HDM uint8_t u8(uint64_t off) const { return buf[(uint32_t)off - (uint32_t)base]; }
+    ITX_HDM uint32_t w32(uint64_t aligned_off) const { return *reinterpret_cast<const uint32_t *>(buf + ((uint32_t)aligned_off - (uint32_t)base)); }
+    ITX_HDM uint32_t u32(uint64_t off) const {
+        const uint64_t a = off & ~3ull; const uint32_t sh = (uint32_t)(off & 3) * 8;
+        return itx_funnel_r(w32(a), w32(a + 4), sh);
+    }
+};
+
 /* ------------------------------------------------------------------ record chain */
 /* Cheap structural test used ONLY to guess where a chunk's first record starts; the guess is checked
  * against the real chain afterwards (k_verify / k_fixup), so a wrong answer costs time, not exactness. */
@@ -205,8 +217,10 @@ ITX_HD uint64_t itx_speculate_entry(const Src &S, uint64_t lo, uint64_t hi, uint
 /* bam_aux_get: returns the offset of the type byte of `tag`, or 0.  Faithful to the reference's skip
  * rule, including its quirk that the type is upper-cased before its size is looked up (so 'f' and
  * 'd' values are skipped as size 0).  Reads are bounded by aend. */
-template <class Src>
-ITX_HD uint64_t itx_aux_find(const Src &S, uint64_t s, uint64_t aend, uint8_t t0, uint8_t t1) {
+/* Off: the type offsets are kept in -- uint64_t stream offsets, or uint32_t offsets into a staged copy (k_xa: half the
+ * instructions per byte of a 64-bit walk) */
+template <class Src, class Off>
+ITX_HD Off itx_aux_find(const Src &S, Off s, Off aend, uint8_t t0, uint8_t t1) {
     while (s + 1 < aend) {
         uint8_t c0 = S.u8(s), c1 = S.u8(s + 1);
         s += 2;
@@ -221,18 +235,21 @@ ITX_HD uint64_t itx_aux_find(const Src &S, uint64_t s, uint64_t aend, uint8_t t0
             uint8_t sub = S.u8(s);
             uint32_t sz = (sub == 'C' || sub == 'c' || sub == 'A') ? 1u : (sub == 'S' || sub == 's') ? 2u : (sub == 'I' || sub == 'i' || sub == 'f') ? 4u : 0u;
             uint32_t n = (uint32_t)S.u8(s + 1) | (uint32_t)S.u8(s + 2) << 8 | (uint32_t)S.u8(s + 3) << 16 | (uint32_t)S.u8(s + 4) << 24;
-            s += 5 + (uint64_t)sz * (uint64_t)(int64_t)(int32_t)n;
+            const uint64_t step = 5 + (uint64_t)sz * (uint64_t)(int64_t)(int32_t)n;
+            /* a step that leaves the aux area (a corrupt count) wraps differently in 32 bits: the caller repeats the walk with 64-bit offsets */
+            if (sizeof(Off) < 8 && step > (uint64_t)(aend - s)) return (Off) ~(Off)0;
+            s += (Off)step;
         } else s += (ty == 'C' || ty == 'A') ? 1u : (ty == 'S') ? 2u : (ty == 'I') ? 4u : 0u;
     }
     return 0;
 }
 /* bam_aux2i on the value whose type byte sits at offset s (0 -> 0) */
-template <class Src>
-ITX_HD int32_t itx_aux2i(const Src &S, uint64_t s, uint64_t aend) {
+template <class Src, class Off>
+ITX_HD int32_t itx_aux2i(const Src &S, Off s, Off aend) {
     if (!s || s >= aend) return 0;
     uint8_t ty = S.u8(s); s++;
     uint32_t v = 0;
-    for (int i = 0; i < 4; i++) if (s + (uint64_t)i < aend) v |= (uint32_t)S.u8(s + i) << (8 * i);
+    for (int i = 0; i < 4; i++) if (s + (Off)i < aend) v |= (uint32_t)S.u8(s + (Off)i) << (8 * i);
     if (ty == 'c') return (int32_t)(int8_t)(v & 0xff);
     if (ty == 'C') return (int32_t)(v & 0xff);
     if (ty == 's') return (int32_t)(int16_t)(v & 0xffff);
@@ -524,17 +541,24 @@ ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, i
     if (!itx_query_open(D, c, (uint32_t)s, (uint32_t)e, &Q)) return false;
     const int32_t fs = Q.fs, fe = Q.fe;
     for (uint32_t i = Q.top; i-- > Q.lo;) {
-        const itx_iv v = itx_ld_iv(D, i);
+        /* ivf: the interval with its folded subfamily id beside it -- one load per candidate instead of three dependent ones
+         * (iv, meta, sinfo), and a third of the bytes: the alternates land anywhere in the table, every load is a miss */
+#if defined(__CUDA_ARCH__)
+        const int4 w = __ldg(reinterpret_cast<const int4 *>(D.ivf + i));
+        itx_iv v; v.start = w.x; v.end = w.y; v.pmax = w.z; v.row = (uint32_t)w.w;
+#else
+        const itx_iv v = D.ivf[i];
+#endif
         if (!(v.pmax > fs)) break;
-        if (v.end > fs && v.start < fe && v.start < v.end && D.sinfo[D.meta[i].sub].fold != fold) return true;
+        if (v.end > fs && v.start < fe && v.start < v.end && (int32_t)v.row != fold) return true;
     }
     return false;
 }
 
 /* ------------------------------------------------------------------ XA:Z alternates (mapped2diffSubfam) */
 /* strtol(s, 0, 0) over the bytes [s, e): white space, sign, 0x / 0 prefixes, saturating; returned as (int) */
-template <class Src>
-ITX_HD int32_t itx_strtol_int(const Src &S, uint64_t s, uint64_t e) {
+template <class Src, class Off>
+ITX_HD int32_t itx_strtol_int(const Src &S, Off s, Off e) {
     while (s < e) { uint8_t c = S.u8(s); if (c == ' ' || (c >= 9 && c <= 13)) s++; else break; }
     bool neg = false;
     if (s < e) { uint8_t c = S.u8(s); if (c == '-') { neg = true; s++; } else if (c == '+') s++; }
@@ -543,6 +567,12 @@ ITX_HD int32_t itx_strtol_int(const Src &S, uint64_t s, uint64_t e) {
         uint8_t c1 = s + 1 < e ? S.u8(s + 1) : 0, c2 = s + 2 < e ? S.u8(s + 2) : 0;
         bool hex2 = (c2 >= '0' && c2 <= '9') || ((c2 | 32) >= 'a' && (c2 | 32) <= 'f');
         if ((c1 == 'x' || c1 == 'X') && hex2) { base = 16; s += 2; } else base = 8;
+    }
+    if (base == 10) {
+        /* the usual case -- at most nine decimal digits -- in 32 bits; a tenth digit goes to the general loop below, from the start */
+        uint32_t a32 = 0, nd = 0; Off t = s;
+        while (t < e && nd < 9u) { const uint32_t d = (uint32_t)S.u8(t) - (uint32_t)'0'; if (d > 9u) break; a32 = a32 * 10u + d; t++; nd++; }
+        if (!(t < e && (uint32_t)S.u8(t) - (uint32_t)'0' <= 9u)) return neg ? (int32_t)(0u - a32) : (int32_t)a32;
     }
     uint64_t acc = 0; bool sat = false;
     while (s < e) {
@@ -559,16 +589,16 @@ ITX_HD int32_t itx_strtol_int(const Src &S, uint64_t s, uint64_t e) {
     else v = (sat || acc > 0x7fffffffffffffffull) ? 0x7fffffffffffffffull : acc;
     return (int32_t)(uint32_t)v;
 }
-template <class Src>
-ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t s, uint64_t e) {
+template <class Src, class Off>
+ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, Off s, Off e) {
     uint32_t h = 2166136261u;
-    for (uint64_t i = s; i < e; i++) { h ^= S.u8(i); h *= 16777619u; }
+    for (Off i = s; i < e; i++) { h ^= S.u8(i); h *= 16777619u; }
     uint32_t m = D.cname_nslot - 1, i = h & m;
     for (;;) {
         uint32_t v = D.cname_slot[i];
         if (!v) return -1;
         const char *nm = D.cname_pool + D.cname_off[v - 1];
-        uint64_t k = 0; bool same = true;
+        Off k = 0; bool same = true;
         for (; s + k < e; k++) if ((uint8_t)nm[k] != S.u8(s + k) || nm[k] == 0) { same = false; break; }
         if (same && nm[k] == 0) return (int32_t)(v - 1);
         i = (i + 1) & m;
@@ -579,14 +609,14 @@ ITX_HD int32_t itx_chrom_by_name(const itx_dev_index &D, const Src &S, uint64_t 
  * (k+1)-th ';' (the string's start / end standing in for the missing ones), an empty piece is skipped, and every other piece is
  * chopped at ',' into chr, pos, cigar, nm (the reference asserts on anything but four fields: counted in *malformed here). */
 /* one piece [ps, pe), ps < pe: does this alternate (nm2 <= nm) touch an element of another folded subfamily? */
-template <class Src>
-ITX_HD bool itx_xa_piece(const itx_dev_index &D, const Src &S, uint64_t ps, uint64_t pe, int32_t nm, int32_t qlen, int32_t sel_fold, bool *malformed) {
+template <class Src, class Off>
+ITX_HD bool itx_xa_piece(const itx_dev_index &D, const Src &S, Off ps, Off pe, int32_t nm, int32_t qlen, int32_t sel_fold, bool *malformed) {
     /* up to 4 comma separated fields (chr, pos, cigar, nm); the 4th stops at the next comma */
-    uint64_t f0s = 0, f0e = 0, f1s = 0, f1e = 0, f3s = 0, f3e = 0, q = ps; int nf = 0; bool more = true;
+    Off f0s = 0, f0e = 0, f1s = 0, f1e = 0, f3s = 0, f3e = 0, q = ps; int nf = 0; bool more = true;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (more) {
-            const uint64_t b0 = q;
+            const Off b0 = q;
             while (q < pe && S.u8(q) != ',') q++;
             if (k == 0) { f0s = b0; f0e = q; } else if (k == 1) { f1s = b0; f1e = q; } else if (k == 3) { f3s = b0; f3e = q; }
             nf++;
@@ -618,9 +648,9 @@ ITX_HD uint32_t itx_popc32(uint32_t x) {
 /* the value string that starts at zs (the byte after the type byte): *ze = its terminator (or aend), returns the number of
  * pieces the reference visits (0 for the empty string: chopByChar on "" gives none).  Aligned words once the first odd bytes are
  * done (reads may touch up to 3 bytes past aend, inside the word that holds aend - 1: stream buffers carry slack). */
-template <class Src>
-ITX_HD uint32_t itx_xa_count(const Src &S, uint64_t zs, uint64_t aend, uint64_t *ze) {
-    uint64_t z = zs; uint32_t semis = 0; bool open = true;
+template <class Src, class Off>
+ITX_HD uint32_t itx_xa_count(const Src &S, Off zs, Off aend, Off *ze) {
+    Off z = zs; uint32_t semis = 0; bool open = true;
     while (open && z < aend && (z & 3)) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { semis += c == ';' ? 1u : 0u; z++; } }
     while (open && z + 4 <= aend) {
         const uint32_t w = S.w32(z);
@@ -635,11 +665,11 @@ ITX_HD uint32_t itx_xa_count(const Src &S, uint64_t zs, uint64_t aend, uint64_t 
 }
 /* itx_xa_count that also notes where the first eight ';' are: their offsets from zs, eight bits each, in sp[0..1] (*packed = false if
  * one of them does not fit eight bits) -- the lanes that take the pieces then need not scan the string again (itx_xa_piece_bounds) */
-template <class Src>
-ITX_HD uint32_t itx_xa_count_pack(const Src &S, uint64_t zs, uint64_t aend, uint64_t *ze, uint32_t sp[2], bool *packed) {
-    uint64_t z = zs; uint32_t semis = 0; bool open = true, ok = true;
+template <class Src, class Off>
+ITX_HD uint32_t itx_xa_count_pack(const Src &S, Off zs, Off aend, Off *ze, uint32_t sp[2], bool *packed) {
+    Off z = zs; uint32_t semis = 0; bool open = true, ok = true;
     sp[0] = sp[1] = 0;
-#define ITX_XA_NOTE(pos_) do { const uint64_t o_ = (pos_) - zs; if (semis < 8u) { if (o_ < 256u) sp[semis >> 2] |= (uint32_t)o_ << (8u * (semis & 3u)); else ok = false; } semis++; } while (0)
+#define ITX_XA_NOTE(pos_) do { const Off o_ = (pos_) - zs; if (semis < 8u) { if (o_ < 256u) sp[semis >> 2] |= (uint32_t)o_ << (8u * (semis & 3u)); else ok = false; } semis++; } while (0)
     while (open && z < aend && (z & 3)) { const uint8_t c = S.u8(z); if (c == 0) open = false; else { if (c == ';') ITX_XA_NOTE(z); z++; } }
     while (open && z + 4 <= aend) {
         const uint32_t w = S.w32(z);
@@ -660,16 +690,17 @@ ITX_HD uint32_t itx_xa_count_pack(const Src &S, uint64_t zs, uint64_t aend, uint
     return semis + 1u < 100u ? semis + 1u : 100u;
 }
 /* bounds of piece k out of the packed offsets (k < 8, packed); np = itx_xa_count_pack's result */
-ITX_HD void itx_xa_piece_bounds(uint64_t zs, uint64_t ze, uint32_t np, const uint32_t sp[2], uint32_t k, uint64_t *ps, uint64_t *pe) {
+template <class Off>
+ITX_HD void itx_xa_piece_bounds(Off zs, Off ze, uint32_t np, const uint32_t sp[2], uint32_t k, Off *ps, Off *pe) {
     const uint32_t prev = k ? ((k - 1u) < 4u ? sp[0] >> (8u * (k - 1u)) : sp[1] >> (8u * (k - 5u))) & 0xffu : 0u;
     const uint32_t cur = (k < 4u ? sp[0] >> (8u * k) : sp[1] >> (8u * (k - 4u))) & 0xffu;
     *ps = k ? zs + prev + 1u : zs;
     *pe = k + 1u < np ? zs + cur : ze;                          /* the last piece runs to the end of the string */
 }
 /* bounds of piece k (k < itx_xa_count): [*ps, *pe) lies between the k-th and the (k+1)-th ';' of [zs, ze) */
-template <class Src>
-ITX_HD void itx_xa_kth(const Src &S, uint64_t zs, uint64_t ze, uint32_t k, uint64_t *ps, uint64_t *pe) {
-    uint64_t z = zs; uint32_t seen = 0;
+template <class Src, class Off>
+ITX_HD void itx_xa_kth(const Src &S, Off zs, Off ze, uint32_t k, Off *ps, Off *pe) {
+    Off z = zs; uint32_t seen = 0;
     while (seen < k && z < ze && (z & 3)) { if (S.u8(z) == ';') seen++; z++; }
     while (seen < k && z + 4 <= ze) {
         const uint32_t n = itx_popc32(itx_eq4(S.w32(z), 0x3b3b3b3bu));

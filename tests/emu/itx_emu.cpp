@@ -62,7 +62,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     E->u64.assign(16 + 2 * ng, 0); E->bp_diff.assign(ix.bp_len + 1, 0); E->bp_diff_u.assign(ix.bp_len + 1, 0);
     E->el_cnt.assign(ne + 1, 0); E->el_cnt_u.assign(ne + 1, 0); E->tid_seen.assign(ITX_MAX_TID_SEEN, 0); E->status.assign(8, 0);
     E->grp_cpg.assign(ng + 1, 0); E->el_cpg.assign(ne + 1, 0); E->grp_cpg_score.assign(ng + 1, 0.0); E->bp_cpg.assign(ix.bp_len + 1, 0.0); E->el_cpg_score.assign(ne + 1, 0.0);
-    D.iv = ix.iv; D.bucket = ix.bucket; D.chrom_bucket = ix.chrom_bucket; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
+    D.iv = ix.iv; D.ivf = ix.ivf; D.bucket = ix.bucket; D.chrom_bucket = ix.chrom_bucket; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
     D.n_chrom = nc; D.n_elem = ix.n_elem;
     D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data();
     D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix.stat_mode;
@@ -208,6 +208,62 @@ static bool xa_lanes(const itx_dev_index &D, const itx_src_global &G, uint64_t p
     return found;
 }
 
+/* k_xa as it is now: the aux area of the read is STAGED (16-byte granules around it, as the kernel's cp.async brings them into the
+ * warp's pool; everything else in the pool is poisoned here) and parsed with 32-bit pool-relative offsets through itx_src_flat; a
+ * read whose aux area does not fit, or whose tag walk meets an array count that leaves the area, takes the one-lane 64-bit walk
+ * over global memory -- the kernel's fallback.  Returns the verdict; *malformed as the kernel would count it. */
+static const uint32_t EMU_XA_POOL = 6144;
+static bool xa_staged(const itx_dev_index &D, const itx_src_global &G, uint64_t p, const uint32_t x[9], int32_t fold, int32_t qlen, uint32_t *malformed, uint32_t pool_off, bool *counted_go) {
+    uint64_t a0, aend; itx_aux_range(p, x, &a0, &aend);
+    *counted_go = a0 < aend;
+    if (!(a0 < aend)) return false;
+    const uint64_t base = a0 & ~15ull;
+    bool big = aend - base > (uint64_t)(EMU_XA_POOL - 16u);
+    bool diffsub = false;
+    if (!big) {
+        const uint32_t need = (uint32_t)((aend - base + 15ull) & ~15ull);
+        if (pool_off + need > EMU_XA_POOL) pool_off = 0;
+        alignas(16) static thread_local uint8_t pool[EMU_XA_POOL];
+        memset(pool, 0xA5, sizeof pool);
+        memcpy(pool + pool_off, G.b + base, need);
+        const uint32_t a0r = (uint32_t)(a0 - base), aendr = (uint32_t)(aend - base);
+        const itx_src_flat S{pool + pool_off, 0ull};
+        const uint32_t xa = itx_aux_find(S, a0r, aendr, (uint8_t)'X', (uint8_t)'A');
+        const uint32_t nmo = xa == 0xffffffffu ? xa : itx_aux_find(S, a0r, aendr, (uint8_t)'N', (uint8_t)'M');
+        if (xa == 0xffffffffu || nmo == 0xffffffffu) big = true;
+        else if (xa && xa < aendr) {
+            const int32_t nm = itx_aux2i(S, nmo, aendr);
+            const uint8_t ty = S.u8(xa);
+            uint32_t np = 0, zs = 0, ze = 0, sp[2] = {0, 0}; bool packed = false;
+            if (ty == 'Z' || ty == 'H') { zs = xa + 1u; np = itx_xa_count_pack(S, zs, aendr, &ze, sp, &packed); }
+            bool found = false;
+            for (uint32_t b0 = 0; b0 < np && !found; b0 += 32) {
+                uint32_t m_hit = 0, m_mal = 0;
+                for (uint32_t lane = 0; lane < 32 && b0 + lane < np; lane++) {
+                    uint32_t ps, pe; bool mal = false, hit = false;
+                    const uint32_t k = b0 + lane;
+                    if (packed && k < 8u) itx_xa_piece_bounds(zs, ze, np, sp, k, &ps, &pe);
+                    else itx_xa_kth(S, zs, ze, k, &ps, &pe);
+                    if (pe > ps) hit = itx_xa_piece(D, S, ps, pe, nm, qlen, fold, &mal);
+                    if (hit) m_hit |= 1u << lane;
+                    if (mal) m_mal |= 1u << lane;
+                }
+                if (m_hit) { found = true; *malformed += (uint32_t)__builtin_popcount(m_mal & ((1u << __builtin_ctz(m_hit)) - 1u)); }
+                else *malformed += (uint32_t)__builtin_popcount(m_mal);
+            }
+            diffsub = found;
+        } else *counted_go = false;
+    }
+    if (big) {
+        const uint64_t xa = itx_aux_find(G, a0, aend, (uint8_t)'X', (uint8_t)'A');
+        if (xa && xa < aend) {
+            const int32_t nm = itx_aux2i(G, itx_aux_find(G, a0, aend, (uint8_t)'N', (uint8_t)'M'), aend);
+            diffsub = itx_xa_walk(D, G, xa, aend, nm, fold, qlen, malformed);
+        } else *counted_go = false;
+    }
+    return diffsub;
+}
+
 /* the chain rule of the kernels (itx_span_consistent): the exit that counts for span i is that of the last span before it
  * that holds a record start; a span that met none is right when the chain runs over it or has ended */
 static uint64_t prev_exit(const std::vector<uint64_t> &exit_, uint64_t j) { uint64_t x = exit_[j]; while (x == ITX_OFF_NONE && j > 0) { j--; x = exit_[j]; } return x; }
@@ -333,6 +389,10 @@ static int emu_scan_core(emu_index *E, const uint8_t *hdr_bam, uint64_t hdr_byte
                     const bool d2 = xa_lanes(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad2);
                     E->xa_checked++;
                     if (d2 != diffsub || bad2 != bad) E->xa_mismatch++;
+                    /* and k_xa's staged 32-bit walk, at a pool offset that moves from read to read */
+                    uint32_t bad3 = 0; bool go3 = false;
+                    const bool d3 = xa_staged(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad3, (uint32_t)((E->xa_checked * 48u) % EMU_XA_POOL) & ~15u, &go3);
+                    if (d3 != diffsub || bad3 != bad || !go3) E->xa_mismatch++;
                 }
             }
             if (diffsub) c[12]++;

@@ -261,6 +261,28 @@ XA_ODD = [
 ]
 
 
+def xa_odd_reads():
+    """the reads of test_xa_strings_of_every_shape (shared with the device test of the same name)"""
+    import kats
+    reads = []
+    for k, xa in enumerate(XA_ODD):
+        for ty in ("Z", "H"):
+            reads.append(kats.se("x%d%s" % (k, ty), 0, 1050, 0, aux=[("NM", "i", 1), ("XA", ty, xa)]))
+    reads.append(kats.se("xi", 0, 1050, 0, aux=[("NM", "i", 1), ("XA", "i", 7)]))          # XA that is not a string
+    reads.append(kats.se("xnm", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,0;")]))      # no NM: 0
+    # k_xa parses the aux area out of a staged copy with 32-bit offsets: an aux area larger than its 6 KiB pool, byte arrays in front of
+    # the tags, and an array count that leaves the aux area between XA and NM (NM is then not found: 0) take its fall-backs
+    import struct
+    big = b"C" + struct.pack("<i", 7000) + bytes(7000)          # (the reference copies the list into char[2000]: the LIST stays short)
+    reads.append(kats.se("xbig_hit", 0, 1050, 0, aux=[("ZB", "B", big), ("NM", "i", 1), ("XA", "Z", "chr1,+1101,36M,0;chr1,+5101,36M,1;")]))
+    reads.append(kats.se("xbig_keep", 0, 1050, 0, aux=[("NM", "i", 1), ("XA", "Z", "chr1,+1101,36M,0;"), ("ZB", "B", big)]))
+    arr = b"C" + struct.pack("<i", 40) + bytes(range(40))
+    reads.append(kats.se("xarr", 0, 1050, 0, aux=[("ZB", "B", arr), ("NM", "i", 1), ("ZC", "B", b"s" + struct.pack("<i", 3) + bytes(6)), ("XA", "Z", "chr1,+5101,36M,1;")]))
+    reads.append(kats.se("xarr_bad", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,0;"), ("ZB", "B", b"I" + struct.pack("<I", 0x40000000)), ("NM", "i", 1)]))
+    reads.append(kats.se("xarr_bad2", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,1;"), ("ZB", "B", b"I" + struct.pack("<I", 0x40000000)), ("NM", "i", 1)]))
+    return reads
+
+
 def test_xa_strings_of_every_shape(tmp_path):
     """mapped2diffSubfam (generic.c:303-341) on alternate lists that chopByChar / strtol treat in their own ways: the
     device logic's single pass over the string against the oracle, read by read"""
@@ -271,12 +293,7 @@ def test_xa_strings_of_every_shape(tmp_path):
     open(cs, "w").write("chr1\t1000000\n")
     open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
     open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
-    reads = []
-    for k, xa in enumerate(XA_ODD):
-        for ty in ("Z", "H"):
-            reads.append(kats.se("x%d%s" % (k, ty), 0, 1050, 0, aux=[("NM", "i", 1), ("XA", ty, xa)]))
-    reads.append(kats.se("xi", 0, 1050, 0, aux=[("NM", "i", 1), ("XA", "i", 7)]))          # XA that is not a string
-    reads.append(kats.se("xnm", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,0;")]))      # no NM: 0
+    reads = xa_odd_reads()
     raw = bamio.encode_header([("chr1", 1000000)]) + b"".join(bamio.encode_record(r) for r in reads)
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(), trace=True)

@@ -465,21 +465,17 @@ def test_overlap_kernel_on_nested_table(tmp_path):
 @pytest.mark.parametrize("fused", [1, 0])
 def test_xa_strings_of_every_shape(fused, tmp_path, monkeypatch):
     """mapped2diffSubfam on alternate lists that chopByChar / strtol treat in their own ways (empty and malformed pieces,
-    more than 100 pieces, hexadecimal and octal numbers, XA of another type): k_scan and the tuple path against the oracle"""
+    more than 100 pieces, hexadecimal and octal numbers, XA of another type, aux areas larger than k_xa's pool, array counts that leave
+    the aux area): k_scan + k_xa and the tuple path against the oracle"""
     import bamio
-    from test_emu_synth import XA_ODD
+    from test_emu_synth import xa_odd_reads
     monkeypatch.setenv("ITX_FUSED", str(fused))
     d = str(tmp_path)
     cs, rs, rm = (os.path.join(d, n) for n in ("chrom.sizes", "rep.sizes", "rmsk.txt"))
     open(cs, "w").write("chr1\t1000000\n")
     open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
     open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
-    reads = []
-    for k, xa in enumerate(XA_ODD):
-        for ty in ("Z", "H"):
-            reads.append(kats.se("x%d%s" % (k, ty), 0, 1050, 0, aux=[("NM", "i", 1), ("XA", ty, xa)]))
-    reads.append(kats.se("xi", 0, 1050, 0, aux=[("NM", "i", 1), ("XA", "i", 7)]))
-    reads.append(kats.se("xnm", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,0;")]))
+    reads = xa_odd_reads()
     raw = bamio.encode_header([("chr1", 1000000)]) + b"".join(bamio.encode_record(r) for r in reads)
     ora = O.OracleIndex(cs, rs, rm)
     want = ora.scan_stream(raw, O.default_opts())
