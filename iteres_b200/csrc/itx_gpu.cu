@@ -31,7 +31,7 @@ struct itx_cuda {
     int sm_count; size_t smem_optin;
     /* index */
     itx_dev_index D;
-    void *d_iv, *d_ivf, *d_bucket, *d_chrom_bucket, *d_cinfo, *d_sinfo, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool;
+    void *d_iv, *d_ivf, *d_bucket, *d_chrom_bucket, *d_cinfo, *d_sinfo, *d_meta, *d_meta2, *d_chrom_off, *d_chrom_size, *d_cname_slot, *d_cname_off, *d_cname_pool, *d_cname32;
     void *d_sub_len, *d_sub_bp_off, *d_sub_fold;
     /* counter block */
     void *d_u64; size_t n_u64;           /* cnt[16] + grp */
@@ -110,7 +110,7 @@ static void cuda_free_all(itx_cuda *cu) {
     if (!cu) return;
     cudaSetDevice(cu->device);
     void *ptrs[] = {cu->d_iv, cu->d_ivf, cu->d_bucket, cu->d_chrom_bucket, cu->d_cinfo, cu->d_sinfo, cu->d_work, cu->d_meta, cu->d_meta2, cu->d_chrom_off, cu->d_chrom_size, cu->d_cname_slot, cu->d_cname_off,
-                    cu->d_cname_pool, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
+                    cu->d_cname_pool, cu->d_cname32, cu->d_sub_len, cu->d_sub_bp_off, cu->d_sub_fold, cu->d_u64, cu->d_u32, cu->d_cpg_u32, cu->d_cpg_f64,
                     cu->d_misc, cu->d_D, cu->d_bp, cu->d_bp_u, cu->d_tuples, cu->d_entry, cu->d_exit, cu->d_carry, cu->d_rec_base, cu->d_running,
                     cu->d_nrec, cu->d_winbad, cu->d_sel, cu->d_trace, cu->d_stream, cu->d_flush, cu->d_comp, cu->d_blk, cu->d_tabs, cu->d_mpl, cu->d_md, cu->d_mn, cu->d_dup_keys, cu->d_dup_ords, cu->d_dup_mins, cu->d_carry_log, cu->d_fused, cu->d_snap, cu->d_shard, cu->d_xa_q, cu->d_xa_n};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
@@ -222,6 +222,12 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         int r = upload(&cu->d_cname_slot, slot, nslot, err) || upload(&cu->d_cname_off, noff, (size_t)nc + 1, err) || upload(&cu->d_cname_pool, poolb, pool + 1, err);
         free(slot); free(noff); free(poolb);
         if (r) goto fail;
+        {
+            uint32_t *n32 = itx_names32(ix->chroms.names, nc);
+            r = upload(&cu->d_cname32, n32, (size_t)(nc > 0 ? nc : 1) * 8, err);
+            free(n32);
+            if (r) goto fail;
+        }
         /* counter block */
         const size_t ng = (size_t)(ns + nf + ncl);
         cu->n_u64 = 16 + 2 * ng; cu->n_u32 = 2 * (size_t)ix->bp_len + 2 * ne;
@@ -240,7 +246,7 @@ extern "C" itx_index *itx_index_build_on(int device, const char *chrom_sizes, co
         D.iv = (const itx_iv *)cu->d_iv; D.ivf = (const itx_iv *)cu->d_ivf; D.bucket = (const uint32_t *)cu->d_bucket; D.chrom_bucket = (const long long *)cu->d_chrom_bucket;
         D.cinfo = (const itx_chrominfo *)cu->d_cinfo; D.sinfo = (const itx_subinfo *)cu->d_sinfo; D.meta = (const itx_meta *)cu->d_meta; D.meta2 = (const itx_meta2 *)cu->d_meta2;
         D.chrom_off = (const long long *)cu->d_chrom_off; D.chrom_size = (const int32_t *)cu->d_chrom_size; D.n_chrom = nc; D.n_elem = ix->n_elem;
-        D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool;
+        D.cname_slot = (const uint32_t *)cu->d_cname_slot; D.cname_nslot = nslot; D.cname_off = (const uint32_t *)cu->d_cname_off; D.cname_pool = (const char *)cu->d_cname_pool; D.cname32 = (const uint32_t *)cu->d_cname32;
         D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix->stat_mode;
         D.sub_len = (const uint32_t *)cu->d_sub_len; D.sub_bp_off = (const unsigned long long *)cu->d_sub_bp_off; D.sub_fold = (const int32_t *)cu->d_sub_fold;
         D.cnt = (unsigned long long *)cu->d_u64; D.grp = D.cnt + 16;
@@ -664,8 +670,10 @@ static int launch_fused(scan_ctx *sc, uint32_t window, uint64_t k0, uint32_t n, 
         uint64_t blocks = ((uint64_t)n * cu->C / 42 + 255) / 256, most = (uint64_t)cu->sm_count * 8;
         if (blocks > most) blocks = most;
         if (blocks < 1) blocks = 1;
-        if (!cu->xa_attr) { cudaFuncSetAttribute(k_xa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_XA_SMEM); cu->xa_attr = 1; }
-        k_xa<<<(unsigned)blocks, 256, ITX_XA_SMEM, cu->stream>>>(X);
+        const size_t fc_bytes = 2 * (size_t)(cu->D.n_fam + cu->D.n_cla) * 4;
+        X.hist_fc = (sc->o.filter == 0 && cu->D.stat_mode && fc_bytes <= 4096) ? 1u : 0u;
+        if (!cu->xa_attr) { cudaFuncSetAttribute(k_xa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITX_XA_SMEM + 4096); cu->xa_attr = 1; }
+        k_xa<<<(unsigned)blocks, 256, ITX_XA_SMEM + (X.hist_fc ? fc_bytes : 0), cu->stream>>>(X);
         sc->n_launch++;
     }
     return ITX_OK;

@@ -459,6 +459,16 @@ int itx_host_index_load(struct itx_index *ix, const char *chrom_sizes, const cha
     return ITX_OK;
 }
 
+uint32_t *itx_names32(char *const *names, int32_t n) {
+    uint32_t *t = (uint32_t *)calloc((size_t)(n > 0 ? n : 1) * 8, 4);
+    for (int32_t c = 0; c < n; c++) {
+        const size_t l = strlen(names[c]);
+        if (l >= 32) memset(t + 8 * (size_t)c, 0xff, 32);
+        else memcpy(t + 8 * (size_t)c, names[c], l);            /* (little-endian host, like the device) */
+    }
+    return t;
+}
+
 void itx_host_index_free(struct itx_index *ix) {
     itx_strtab_free(&ix->chromsize); free(ix->chromsize_val);
     itx_strtab_free(&ix->repsize); free(ix->repsize_val);

@@ -23,6 +23,8 @@ int32_t itx_strtab_intern(itx_strtab *t, const char *name);        /* find or ad
 /* output-row order of a Kent hash holding these names (cuskent/hash.c:41-53, 136-140, 374-410, 511-551) */
 int32_t *itx_kent_order(const itx_strtab *t, int pow2_initial);
 uint32_t itx_fnv1a(const char *s, size_t n);
+/* n names as eight zero-padded little-endian words each (a name of 32 bytes and more: all ones, which no padded name equals); malloc'ed */
+uint32_t *itx_names32(char *const *names, int32_t n);
 
 /* ------------------------------------------------------------------ per-group counters (host copy) */
 typedef struct {
@@ -55,6 +57,7 @@ typedef struct {
     int32_t n_chrom; long long n_elem;
     /* chromosome names for XA lookups: open addressing (FNV-1a) -> chrom id + 1; names NUL-terminated in a pool */
     const uint32_t *cname_slot; uint32_t cname_nslot; const uint32_t *cname_off; const char *cname_pool;
+    const uint32_t *cname32;             /* the same names, eight zero-padded words each (all ones: a name of 32 bytes and more); NULL: not built */
     int32_t n_sub, n_fam, n_cla;
     int32_t stat_mode;                   /* 1 when the group tables exist (filter_field == 0) */
     const uint32_t *sub_len;             /* consensus length or 0 */

@@ -1119,6 +1119,7 @@ struct itx_xa_args {
     const uint8_t *b; const itx_tidinfo *tid; int32_t n_ref; itx_dev_opts o;
     const unsigned long long *q; uint32_t *q_n; unsigned long long q_cap;      /* q_n: [0] entries, [1] CTAs done (the last one zeroes both) */
     int32_t sign; uint32_t flags;
+    uint32_t hist_fc;                                                          /* 1: the CTA keeps the family / class counts in shared memory (behind the pools) */
 };
 #ifndef ITX_XA_OCC
 #define ITX_XA_OCC 4                 /* 64 registers, 32 warps per SM: the kernel waits on scattered table and record reads (11.2 -> 9.3 ms per 30 M reads of cfg 3 against 24 warps at 80 registers; 48 registers spill and lose again) */
@@ -1126,7 +1127,7 @@ struct itx_xa_args {
 #ifndef ITX_XA_POOL
 #define ITX_XA_POOL 6144u            /* bytes of shared memory per warp for the aux areas of its 32 reads (192 per read; what does not fit waits for the next pass) */
 #endif
-#define ITX_XA_SMEM (8u * ITX_XA_POOL)
+#define ITX_XA_SMEM (8u * ITX_XA_POOL + 64u)          /* + slack: itx_xa_piece_fast loads whole words up to 60 bytes past a piece's start */
 __device__ __forceinline__ void itx_cp_async16_cg(void *smem_dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(itx_smem_addr(smem_dst)), "l"(src) : "memory"); }
 /* The aux areas are parsed out of SHARED memory.  Round 2's first k_xa read them byte by byte with __ldg (1.4 G sector requests
  * and 2.9 G warp-instructions per 9 M reads, most of them waiting on L1): here the warp first brings the aux areas of its reads
@@ -1141,6 +1142,12 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     uint8_t *pool = itx_xa_smem + (threadIdx.x >> 5) * ITX_XA_POOL;
+    /* the family and class counters are a few dozen addresses that every counted read would hit: per CTA in shared memory, flushed once
+     * (reductions on one address queue up in L2); the subfamily counters -- a thousand and more addresses -- go straight to global memory */
+    uint32_t *sh_fc = reinterpret_cast<uint32_t *>(itx_xa_smem + ITX_XA_SMEM);
+    const uint32_t n_fc = A.hist_fc ? 2u * (uint32_t)(D.n_fam + D.n_cla) : 0u;
+    for (uint32_t t = threadIdx.x; t < n_fc; t += blockDim.x) sh_fc[t] = 0u;
+    __syncthreads();
     const unsigned long long n = __ldcg(A.q_n) < A.q_cap ? __ldcg(A.q_n) : A.q_cap;
     const bool neg = A.sign < 0, stat = A.o.filter == 0 && D.stat_mode, coop = A.flags & ITX_SCAN_XACOOP;
     const uint32_t one = neg ? 0xffffffffu : 1u, minus_one = neg ? 1u : 0xffffffffu;
@@ -1216,7 +1223,11 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
             uint32_t incl = np;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+#ifdef ITX_XA_EXPERIMENT                                         /* timing experiments only (tools/build_variant.sh): 1 = no alternate is looked at */
+            const uint32_t total = 0u, pbase = incl - np;
+#else
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), pbase = incl - np;
+#endif
             bool found = false;
             for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
                 const uint32_t gi = b0 + lane;                     /* this lane's piece of the batch */
@@ -1237,7 +1248,7 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
                     const uint32_t k = gi - o_base;
                     if (o_packed && k < 8u) itx_xa_piece_bounds(o_zs, o_ze, o_np, o_sp, k, &ps, &pe);      /* the owner noted where its first ';' are */
                     else itx_xa_kth(So, o_zs, o_ze, k, &ps, &pe);
-                    if (pe > ps) hit = itx_xa_piece(D, So, ps, pe, o_nm, o_qlen, o_fold, &mal);
+                    if (pe > ps) hit = itx_xa_piece_fast(D, So, ps, pe, o_nm, o_qlen, o_fold, &mal);
                 }
                 const uint32_t m_hit = __ballot_sync(0xffffffffu, hit), m_mal = __ballot_sync(0xffffffffu, mal);
                 if (np && !found && pbase < b0 + 32u && incl > b0) {
@@ -1266,8 +1277,16 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
             if (stat) {
                 const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
                 const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
-                itx_red_u64(&D.grp[hs], one64); itx_red_u64(&D.grp[hf], one64); itx_red_u64(&D.grp[hc], one64);
-                if (uniq) { itx_red_u64(&D.grp[hs + 1], one64); itx_red_u64(&D.grp[hf + 1], one64); itx_red_u64(&D.grp[hc + 1], one64); }
+                itx_red_u64(&D.grp[hs], one64);
+                if (uniq) itx_red_u64(&D.grp[hs + 1], one64);
+                if (n_fc) {
+                    const uint32_t lf = 2u * (uint32_t)m2.fam, lc = 2u * (uint32_t)(D.n_fam + m2.cla);
+                    atomicAdd(&sh_fc[lf], 1u); atomicAdd(&sh_fc[lc], 1u);
+                    if (uniq) { atomicAdd(&sh_fc[lf + 1], 1u); atomicAdd(&sh_fc[lc + 1], 1u); }
+                } else {
+                    itx_red_u64(&D.grp[hf], one64); itx_red_u64(&D.grp[hc], one64);
+                    if (uniq) { itx_red_u64(&D.grp[hf + 1], one64); itx_red_u64(&D.grp[hc + 1], one64); }
+                }
                 const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(D.sinfo + m.sub));
                 const uint32_t L = sv.x;
                 uint32_t ja, jb;
@@ -1284,6 +1303,7 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
     }
     if (lane == 0) { if (c_rep) atomicAdd(&sh_c[0], c_rep); if (c_rep_u) atomicAdd(&sh_c[1], c_rep_u); if (c_diff) atomicAdd(&sh_c[2], c_diff); }
     __syncthreads();
+    for (uint32_t t = threadIdx.x; t < n_fc; t += blockDim.x) { const uint32_t v = sh_fc[t]; if (v) itx_red_u64(&D.grp[2u * (uint32_t)D.n_sub + t], neg ? 0ull - (unsigned long long)v : (unsigned long long)v); }
     if (threadIdx.x == 0) {
         if (sh_c[0]) itx_red_u64(&D.cnt[9], neg ? 0ull - sh_c[0] : (unsigned long long)sh_c[0]);
         if (sh_c[1]) itx_red_u64(&D.cnt[10], neg ? 0ull - sh_c[1] : (unsigned long long)sh_c[1]);

@@ -645,6 +645,111 @@ ITX_HD uint32_t itx_popc32(uint32_t x) {
     return (uint32_t)__builtin_popcount(x);
 #endif
 }
+ITX_HD uint32_t itx_popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll((unsigned long long)x);
+#else
+    return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+ITX_HD uint32_t itx_ctz64(uint64_t x) {          /* x != 0 */
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffsll((long long)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+/* n decimal digits in the low bytes of (t0, t1, t2), as strtol(.., 0, 0) reads them when n is 1..9 and there is no leading zero (a
+ * leading zero means octal or hexadecimal there): *out = the value; false: not of that shape */
+ITX_HD bool itx_dec9(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t n, uint32_t *out) {
+    uint32_t v = 0; bool ok = n >= 1u && n <= 9u;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint32_t word = i < 4 ? t0 : (i < 8 ? t1 : t2);
+        const uint32_t d = ((word >> (8 * (i & 3))) & 0xffu) - (uint32_t)'0';
+        if ((uint32_t)i < n) { ok = ok && d <= 9u; v = v * 10u + d; }
+    }
+    if (n > 1u && (t0 & 0xffu) == (uint32_t)'0') ok = false;
+    *out = v;
+    return ok;
+}
+/* itx_xa_piece for a piece that lies in STAGED bytes (offsets 32 bits wide, words readable up to 47 bytes past ps): the usual
+ * shape -- at most 44 bytes, "name,[+-]digits,cigar,digits" with numbers of at most nine digits without leading zeros and a name of
+ * at most 31 bytes -- is taken in registers: the piece's words are loaded side by side (no load waits for the byte before it),
+ * the commas found four bytes at a time, the numbers read out of registers, the name compared eight words at a time with the
+ * zero-padded names of D.cname32.  Anything else is itx_xa_piece's business; the verdicts are the same by construction (and
+ * checked read by read in tests/emu). */
+#ifndef ITX_XA_FAST_NOTE
+#define ITX_XA_FAST_NOTE(i)              /* tests/emu counts how many pieces took the register path (0) and the general one (1) */
+#endif
+template <class Src>
+ITX_HD bool itx_xa_piece_fast(const itx_dev_index &D, const Src &S, uint32_t ps, uint32_t pe, int32_t nm, int32_t qlen, int32_t sel_fold, bool *malformed) {
+    const uint32_t len = pe - ps;
+    if (len <= 44u && D.cname32 != nullptr) {
+        const uint32_t a = ps & ~3u, sh = (ps & 3u) * 8u;
+        uint32_t r[12], w[11];
+#pragma unroll
+        for (int k = 0; k < 12; k++) r[k] = S.w32(a + 4u * (uint32_t)k);
+#pragma unroll
+        for (int k = 0; k < 11; k++) w[k] = itx_funnel_r(r[k], r[k + 1], sh);
+        uint64_t cm = 0;                                           /* bit i: byte i of the piece is a comma */
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const uint32_t x = itx_eq4(w[k], 0x2c2c2c2cu) >> 7;
+            cm |= (uint64_t)((x | x >> 7 | x >> 14 | x >> 21) & 0xfu) << (4 * k);
+        }
+        cm &= (1ull << len) - 1ull;
+        if (itx_popc64(cm) >= 3u) {
+            const uint32_t c1 = itx_ctz64(cm); cm &= cm - 1ull;
+            const uint32_t c2 = itx_ctz64(cm); cm &= cm - 1ull;
+            const uint32_t c3 = itx_ctz64(cm); cm &= cm - 1ull;
+            const uint32_t c4 = cm ? itx_ctz64(cm) : len;
+            /* the fourth field: the alternate's edit distance */
+            uint32_t nm2 = 0, st = 0;
+            const uint32_t f3 = ps + c3 + 1u, f3a = f3 & ~3u, f3s = (f3 & 3u) * 8u;
+            const uint32_t u0 = S.w32(f3a), u1 = S.w32(f3a + 4u);
+            bool ok = c4 - c3 - 1u <= 4u && itx_dec9(itx_funnel_r(u0, u1, f3s), 0u, 0u, c4 - c3 - 1u, &nm2);
+            /* the second: the position, with its strand sign (abs() drops it) */
+            const uint32_t f1 = ps + c1 + 1u, f1a = f1 & ~3u, f1s = (f1 & 3u) * 8u;
+            const uint32_t v0 = S.w32(f1a), v1 = S.w32(f1a + 4u), v2 = S.w32(f1a + 8u), v3 = S.w32(f1a + 12u);
+            uint32_t t0 = itx_funnel_r(v0, v1, f1s), t1 = itx_funnel_r(v1, v2, f1s), t2 = itx_funnel_r(v2, v3, f1s);
+            uint32_t n1 = c2 - c1 - 1u;
+            const uint32_t sg = t0 & 0xffu;
+            if (n1 >= 1u && (sg == (uint32_t)'+' || sg == (uint32_t)'-')) { t0 = itx_funnel_r(t0, t1, 8u); t1 = itx_funnel_r(t1, t2, 8u); t2 >>= 8; n1--; }
+            ok = ok && itx_dec9(t0, t1, t2, n1, &st);
+            ok = ok && c1 >= 1u && c1 <= 31u;
+            if (ok) {
+                ITX_XA_FAST_NOTE(0);
+                *malformed = false;
+                if ((int32_t)nm2 > nm) return false;
+                const int32_t en = (int32_t)(st + (uint32_t)qlen);
+                /* the first: the chromosome, by name */
+                uint32_t h = 2166136261u;
+#pragma unroll
+                for (int i = 0; i < 31; i++) { if ((uint32_t)i >= c1) break; h ^= (w[i >> 2] >> (8 * (i & 3))) & 0xffu; h *= 16777619u; }
+                uint32_t pw[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) pw[k] = c1 >= 4u * (uint32_t)k + 4u ? w[k] : (c1 > 4u * (uint32_t)k ? w[k] & ((1u << (8u * (c1 - 4u * (uint32_t)k))) - 1u) : 0u);
+                const uint32_t m = D.cname_nslot - 1u;
+                for (uint32_t i = h & m;; i = (i + 1u) & m) {
+                    const uint32_t v = D.cname_slot[i];
+                    if (!v) return false;                          /* no such chromosome */
+                    const uint32_t *nw = D.cname32 + 8u * (v - 1u);
+                    bool same = true;
+#if defined(__CUDA_ARCH__)
+                    const uint4 na = __ldg(reinterpret_cast<const uint4 *>(nw)), nb = __ldg(reinterpret_cast<const uint4 *>(nw) + 1);
+                    same = na.x == pw[0] && na.y == pw[1] && na.z == pw[2] && na.w == pw[3] && nb.x == pw[4] && nb.y == pw[5] && nb.z == pw[6] && nb.w == pw[7];
+#else
+                    for (int k = 0; k < 8; k++) same = same && nw[k] == pw[k];
+#endif
+                    if (same) return itx_any_other_subfam(D, (int32_t)(v - 1u), (int32_t)st, en, sel_fold);
+                }
+            }
+        }
+    }
+    ITX_XA_FAST_NOTE(1);
+    return itx_xa_piece(D, S, ps, pe, nm, qlen, sel_fold, malformed);
+}
 /* the value string that starts at zs (the byte after the type byte): *ze = its terminator (or aend), returns the number of
  * pieces the reference visits (0 for the empty string: chopByChar on "" gives none).  Aligned words once the first odd bytes are
  * done (reads may touch up to 3 bytes past aend, inside the word that holds aend - 1: stream buffers carry slack). */

@@ -6,6 +6,9 @@
  * the `-m "not gpu"` suite check the per-record logic against the oracle on a box without a GPU.
  * The product has no CPU path: nothing under iteres_b200/ links or loads this file.
  */
+#include <stdint.h>
+static uint64_t g_xa_fast[2];                              /* pieces of XA lists that took itx_xa_piece_fast's register path / the general one */
+#define ITX_XA_FAST_NOTE(i) (g_xa_fast[i]++)
 #include "../../iteres_b200/csrc/itx_logic.cuh"
 #include "../../iteres_b200/csrc/itx_inflate.cuh"
 #include "../../iteres_b200/csrc/itx_ordered.h"
@@ -23,6 +26,7 @@ struct emu_index {
     std::vector<unsigned long long> u64; std::vector<uint32_t> bp_diff, bp_diff_u, el_cnt, el_cnt_u, tid_seen, status;
     std::vector<uint32_t> grp_cpg, el_cpg; std::vector<double> grp_cpg_score, bp_cpg, el_cpg_score;
     std::vector<itx_trace> trace; uint64_t n_bad, ring_checked, ring_mismatch, tile_checked, tile_mismatch, tile_entry_miss;
+    uint32_t *cname32 = nullptr;
     uint64_t xa_checked = 0, xa_mismatch = 0;             /* reads with XA put through the lane-per-alternate decomposition of k_scan; verdicts that differed from the one-lane walk */
     /* -R: smallest ordinal per key, of the unique and of the other fragments; persists across the files of a run */
     std::map<std::pair<unsigned long long, unsigned long long>, unsigned long long> dup_first;
@@ -64,7 +68,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     E->grp_cpg.assign(ng + 1, 0); E->el_cpg.assign(ne + 1, 0); E->grp_cpg_score.assign(ng + 1, 0.0); E->bp_cpg.assign(ix.bp_len + 1, 0.0); E->el_cpg_score.assign(ne + 1, 0.0);
     D.iv = ix.iv; D.ivf = ix.ivf; D.bucket = ix.bucket; D.chrom_bucket = ix.chrom_bucket; D.meta = ix.meta; D.meta2 = ix.meta2; D.chrom_off = ix.chrom_off; D.chrom_size = ix.chrom_size;
     D.n_chrom = nc; D.n_elem = ix.n_elem;
-    D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data();
+    D.cname_slot = E->cname_slot.data(); D.cname_nslot = nslot; D.cname_off = E->cname_off.data(); D.cname_pool = E->cname_pool.data(); E->cname32 = itx_names32(ix.chroms.names, nc); D.cname32 = E->cname32;
     D.n_sub = ns; D.n_fam = nf; D.n_cla = ncl; D.stat_mode = ix.stat_mode;
     D.sub_len = ix.sub_len; D.sub_bp_off = ix.sub_bp_off; D.sub_fold = ix.sub_fold; D.cinfo = ix.cinfo; D.sinfo = ix.sinfo;
     D.cnt = E->u64.data(); D.grp = D.cnt + 16; D.bp_diff = E->bp_diff.data(); D.bp_diff_u = E->bp_diff_u.data();
@@ -74,7 +78,7 @@ emu_index *emu_build(const char *chrom_sizes, const char *rep_sizes, const char 
     E->n_bad = 0; E->ring_checked = E->ring_mismatch = 0; E->tile_checked = E->tile_mismatch = E->tile_entry_miss = 0;
     return E;
 }
-void emu_free(emu_index *E) { if (!E) return; itx_host_index_free(&E->ix); delete E; }
+void emu_free(emu_index *E) { if (!E) return; itx_host_index_free(&E->ix); free(E->cname32); delete E; }
 itx_index *emu_host_index(emu_index *E) { return &E->ix; }
 
 /* the ring the TMA decode kernel reads records from: 4 tiles of 2 KiB addressed by (offset & 8191) */
@@ -291,7 +295,7 @@ static bool xa_staged(const itx_dev_index &D, const itx_src_global &G, uint64_t 
     if (!big) {
         const uint32_t need = (uint32_t)((aend - base + 15ull) & ~15ull);
         if (pool_off + need > EMU_XA_POOL) pool_off = 0;
-        alignas(16) static thread_local uint8_t pool[EMU_XA_POOL];
+        alignas(16) static thread_local uint8_t pool[EMU_XA_POOL + 64];
         memset(pool, 0xA5, sizeof pool);
         memcpy(pool + pool_off, G.b + base, need);
         const uint32_t a0r = (uint32_t)(a0 - base), aendr = (uint32_t)(aend - base);
@@ -312,7 +316,7 @@ static bool xa_staged(const itx_dev_index &D, const itx_src_global &G, uint64_t 
                     const uint32_t k = b0 + lane;
                     if (packed && k < 8u) itx_xa_piece_bounds(zs, ze, np, sp, k, &ps, &pe);
                     else itx_xa_kth(S, zs, ze, k, &ps, &pe);
-                    if (pe > ps) hit = itx_xa_piece(D, S, ps, pe, nm, qlen, fold, &mal);
+                    if (pe > ps) hit = itx_xa_piece_fast(D, S, ps, pe, nm, qlen, fold, &mal);
                     if (hit) m_hit |= 1u << lane;
                     if (mal) m_mal |= 1u << lane;
                 }
@@ -540,6 +544,7 @@ uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
 }
 uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
 uint64_t emu_xa_checked(emu_index *E) { return E->xa_checked; }
+uint64_t emu_xa_fast(int which) { return g_xa_fast[which & 1]; }
 uint64_t emu_xa_mismatch(emu_index *E) { return E->xa_mismatch; }
 uint64_t emu_ring_checked(emu_index *E) { return E->ring_checked; }
 uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }

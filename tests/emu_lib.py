@@ -34,6 +34,8 @@ def lib():
         for f in ("emu_ring_checked", "emu_ring_mismatch", "emu_tile_checked", "emu_tile_mismatch", "emu_tile_entry_miss", "emu_xa_checked", "emu_xa_mismatch"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [vp]
+        L.emu_xa_fast.restype = u64
+        L.emu_xa_fast.argtypes = [C.c_int]
         L.emu_check_cov_rules.restype = C.c_uint64
         L.emu_check_cov_rules.argtypes = [C.c_uint64, C.c_uint64]
         L.emu_query.restype = C.c_int32
@@ -104,6 +106,10 @@ class EmuIndex(capi.IndexBase):
     def xa_check(self):
         """(reads with XA put through k_scan's lane-per-alternate decomposition, verdicts that differed from the one-lane walk)"""
         return self.L.emu_xa_checked(self.e), self.L.emu_xa_mismatch(self.e)
+
+    def xa_fast(self):
+        """(pieces of XA lists that took itx_xa_piece_fast's register path, pieces it handed to the general parser) -- process-wide"""
+        return self.L.emu_xa_fast(0), self.L.emu_xa_fast(1)
 
     def n_bad(self):
         return self.L.emu_n_bad(self.e)

@@ -78,6 +78,7 @@ def test_emu_matches_oracle(case, worlds):
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(**kw), trace=True)
     emu = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
+    fast0 = emu.xa_fast()
     cnt_e, tr_e = emu.scan_stream(raw, capi.default_opts(**kw), trace=True)
     assert cnt_e == cnt_o
     assert cnt_o[0] + cnt_o[1] == nrec and cnt_o[9] > 0
@@ -92,8 +93,11 @@ def test_emu_matches_oracle(case, worlds):
     assert np.array_equal(tr_e["flags"] & mask, tr_o["flags"] & mask)
     if kw.get("diffSubfam", 1) and mode == 1:
         assert cnt_o[12] > 0
+        f0, g0 = fast0
         checked, differed = emu.xa_check()              # the lane-per-alternate walk of k_scan against the one-lane walk
         assert checked > 0 and differed == 0
+        f1, g1 = emu.xa_fast()                          # ... whose pieces k_xa reads in registers when they have the usual shape: these do
+        assert f1 - f0 > 0 and f1 - f0 > 20 * (g1 - g0)
     assert_group_tables_and_coverage(emu, ora)
     ora.close()
     emu.close()
@@ -308,6 +312,8 @@ def test_xa_strings_of_every_shape(tmp_path):
         # ones before it counted): the same verdicts and the same malformed count as the one-lane walk, read by read
         checked, differed = emu.xa_check()
         assert checked > 0 and differed == 0
+        fast, general = emu.xa_fast()
+        assert fast > 0 and general > 0                 # the register path and the general parser both met these lists
         emu.close()
     assert 0 < cnt_o[12] < len(reads)
     ora.close()
