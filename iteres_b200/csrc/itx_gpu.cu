@@ -328,7 +328,7 @@ extern "C" void itx_bam_header_free(itx_bam_header *h) {
 /* the queue k_scan hands its XA:Z reads to k_xa in: one entry per 42 bytes of a launch group (no record that carries an XA list is
  * shorter), so it cannot overflow.  0: no room on the device -- the caller takes the tuple path, which looks at XA in line. */
 static int ensure_xa_queue(itx_cuda *cu, uint64_t group_bytes) {
-    const uint64_t need = group_bytes / 42 + 1024;
+    const uint64_t need = group_bytes / 42 + 1024 + 8192ull * ITX_XA_BLK;      /* + a block (reserved, perhaps never filled) per warp of the largest grid */
     if (!cu->d_xa_n) { if (cudaMalloc((void **)&cu->d_xa_n, 8) != cudaSuccess || cudaMemset(cu->d_xa_n, 0, 8) != cudaSuccess) { cudaGetLastError(); return 0; } }
     if (cu->d_xa_q && cu->xa_cap >= need) return 1;
     cudaStreamSynchronize(cu->stream);

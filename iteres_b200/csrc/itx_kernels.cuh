@@ -582,8 +582,14 @@ struct itx_scan_args {
 #define ITX_SCAN_PACK     512u           /* stages start AT a record (16-byte granule) instead of on a 4 KiB boundary and hold up to 32 whole records, one
                                           * round each: with 4 KiB of record starts per stage a 232-byte record (PE-100) fills 18 lanes of a round, packed it
                                           * fills 22; the tail of the buffer behind the last whole record is carried inside shared memory */
+#define ITX_SCAN_SERIAL   1024u          /* a span whose records keep defeating the size prediction (fewer than 2.5 records accepted per step: XA lists, long
+                                          * read names of every length) walks the rest of its stages record by record -- 18 instructions per record, all
+                                          * lanes alike, against 45 per step of the predicted walk */
 #define ITX_SCAN_DEFAULT  (ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
 #define ITX_WIN 32u                      /* table entries per warp window */
+#define ITX_XA_BLK 128u                  /* k_scan -> k_xa queue: a warp reserves this many entries at a time (one atomic on the queue's counter per block, not
+                                          * per round: a million and more same-address atomics per launch queued up in L2 and cost cfg 3 two milliseconds);
+                                          * what a warp leaves unused of its last block is marked empty (all ones) */
 #ifndef ITX_SCAN_NW
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
 #endif
@@ -694,7 +700,7 @@ __device__ __noinline__ void itx_flush_counters(uint32_t pa, uint32_t pb, uint32
  * select between are not in the loop at all (the loop is bound by instruction issue AND fetch: every instruction that is not
  * there helps); AB = true: the switches are read from P.flags (tests and measurements: every combination gives the same counts) */
 #ifndef ITX_SCAN_PRODUCT
-#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT | ITX_SCAN_CARRY)
+#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT | ITX_SCAN_CARRY | ITX_SCAN_SERIAL)
 #endif
 template <bool SMEM_HIST, int NW, bool AB, bool PACK = false>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
@@ -716,6 +722,8 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
     for (uint32_t t = threadIdx.x; t < nh; t += blockDim.x) sh_hist[t] = 0;
     if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
     if (lane == 0) { itx_mbar_init(bar_s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    uint32_t *xa_blk = reinterpret_cast<uint32_t *>(buf + STG + ITX_POS_SLOTS * 2u + 8u);      /* the warp's block of the XA queue: [0] first entry, [1] entries used (beside the mbarrier) */
+    if (lane == 0) { xa_blk[0] = 0u; xa_blk[1] = ITX_XA_BLK; }
     __syncthreads();
     const bool neg = P.sign < 0;
 #define one (neg ? 0xffffffffu : 1u)
@@ -723,7 +731,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
 #define one64 (neg ? ~0ull : 1ull)
     const bool stat = A.o.filter == 0 && D.stat_mode;
     const uint32_t flags = AB ? P.flags : (uint32_t)(ITX_SCAN_PRODUCT | (PACK ? ITX_SCAN_PACK : 0u));
-    const bool f_pack = flags & ITX_SCAN_PACK;
+    const bool f_pack = flags & ITX_SCAN_PACK, f_serial = flags & ITX_SCAN_SERIAL;
     const bool f_prefetch = flags & ITX_SCAN_PREFETCH, f_dom = flags & ITX_SCAN_DOMSIZE, f_win = flags & ITX_SCAN_WINDOW;
     const bool f_ahead = f_win && (flags & ITX_SCAN_WINAHEAD), f_early = flags & ITX_SCAN_EARLY;
     const bool f_evict = flags & ITX_SCAN_EVICT, f_evict_pf = flags & ITX_SCAN_EVICT_PF, f_carry = flags & ITX_SCAN_CARRY;
@@ -809,6 +817,7 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         uint32_t nb = 0;
         uint32_t szd = 0;                                      /* the span's dominant record size (0: none yet) */
         bool guessed = false;                                  /* packed geometry: the stage the guess was made in is kept for the first records */
+        bool ser = false;                                      /* the size prediction does badly in this span: walk record by record */
         for (;;) {
             if (guess ? hi == 0u : !(p < hi)) { if (guess && lane == 0) A.entry[i] = ITX_OFF_NONE; break; }
             /* packed: a stage starts at the 16-byte granule of its first record (the span's first stage, staged for the guess, is kept
@@ -872,9 +881,22 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                         n += run;
                         q += sz0 + (run - 1u) * szp;
                     }
-                } else
+                } else if (f_serial && ser) {
+                    /* record by record, every lane the same walk (the lane whose turn it is notes the start) */
+                    while (q < qh) {
+                        q_end = q;
+                        if (q + 36u > room32) { q = 0xffffffffu; break; }
+                        const uint32_t bs0 = itx_buf_u32(buf, q);
+                        if ((int32_t)bs0 < 32 || bs0 + 4u > room32 - q) { q = 0xffffffffu; break; }
+                        if ((n & 31u) == lane && n < ITX_POS_SLOTS) pos[n] = (uint16_t)q;
+                        n++;
+                        q += bs0 + 4u;
+                    }
+                } else {
+                uint32_t steps = 0;
                 while (q < qh) {
                     q_end = q;
+                    steps++;
                     if (q + 36u > room32) { q = 0xffffffffu; break; }
                     const uint32_t bs0 = itx_buf_u32(buf, q);
                     const uint32_t sz0 = bs0 + 4u;
@@ -890,6 +912,8 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     n += run;
                     q += sz0 + (run - 1u) * szp;
                     szd = (f_dom && run >= 2u) ? szp : 0u;
+                }
+                if (f_serial && n >= 8u && steps * 5u > n * 2u) ser = true;
                 }
                 if (q != 0xffffffffu) q_end = q;
                 if (lane == 0 && A.avail < lo + c_lo + q_end) atomicOr(P.first_bad + 2, 2u);              /* a record longer than the staged window */
@@ -992,13 +1016,21 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
                     const bool xa_go = sel >= 0 && xa_rel != 0u;
                     const uint32_t m_xa = __ballot_sync(0xffffffffu, xa_go);
                     if (m_xa) {
-                        uint32_t qb = 0;
-                        if (lane == 0) qb = atomicAdd(P.xa_n, (uint32_t)__popc(m_xa));
-                        qb = __shfl_sync(0xffffffffu, qb, 0) + (uint32_t)__popc(m_xa & ((1u << lane) - 1u));
+                        const uint32_t cnt = (uint32_t)__popc(m_xa);
+                        uint32_t qb = xa_blk[0], used = xa_blk[1];
+                        if (used + cnt > ITX_XA_BLK) {         /* the block cannot take this round: its rest is marked empty, the next one reserved */
+                            if (qb + ITX_XA_BLK <= P.xa_cap) for (uint32_t t = used + lane; t < ITX_XA_BLK; t += 32u) P.xa_q[qb + t] = ~0ull;
+                            if (lane == 0) qb = atomicAdd(P.xa_n, ITX_XA_BLK);
+                            qb = __shfl_sync(0xffffffffu, qb, 0); used = 0u;
+                        }
                         if (xa_go) {
-                            if (qb < P.xa_cap) P.xa_q[qb] = c_lo64 + pos[j]; else atomicOr(&A.status[0], 8u);      /* cannot happen: the queue holds one entry per 42 bytes of stream */
+                            if (qb + ITX_XA_BLK <= P.xa_cap) P.xa_q[qb + used + (uint32_t)__popc(m_xa & ((1u << lane) - 1u))] = c_lo64 + pos[j];
+                            else atomicOr(&A.status[0], 8u);       /* cannot happen: the queue holds one entry per 42 bytes of stream and a block per warp on top */
                             sel = -1;
                         }
+                        __syncwarp();
+                        if (lane == 0) { xa_blk[0] = qb; xa_blk[1] = used + cnt; }
+                        __syncwarp();
                     }
                 }
                 const bool counted = sel >= 0 && !diffsub;
@@ -1052,6 +1084,10 @@ __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_s
         if (lane == 0) A.exit_[i] = p >= 0xfffffffeu ? (0xffffffff00000000ull | p) : lo + p;
     }
     itx_cp_async_wait_all();                                   /* a window fetched ahead and never used */
+    {   /* what is left of the warp's block of the XA queue is marked empty */
+        const uint32_t qb = xa_blk[0], used = xa_blk[1];
+        if (used < ITX_XA_BLK && qb + ITX_XA_BLK <= P.xa_cap) for (uint32_t t = used + lane; t < ITX_XA_BLK; t += 32u) P.xa_q[qb + t] = ~0ull;
+    }
     itx_flush_counters(pa, pb, pc, sh_cnt);
     __syncthreads();
     if (threadIdx.x < 13 && sh_cnt[threadIdx.x]) itx_red_u64(&D.cnt[threadIdx.x], neg ? 0ull - sh_cnt[threadIdx.x] : sh_cnt[threadIdx.x]);
@@ -1161,8 +1197,9 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
         itx_tuple T; T.start = T.end = T.rec_off = 0; T.info = 0;
         long long sel = -1; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
         uint64_t a0 = 0, aend = 0; int32_t fold = 0;
+        unsigned long long rp = ~0ull;
+        if (go) { rp = __ldcs(A.q + idx); go = rp != ~0ull; }      /* all ones: an entry of a block that its warp did not fill */
         if (go) {
-            const unsigned long long rp = __ldcs(A.q + idx);
             uint32_t x[9]; G.core(rp, x);
             T = itx_decode_record<itx_src_global, false>(G, rp, x, 0u, A.tid, A.n_ref, A.o);
             int32_t nhit = 0; float tcov = 0.0f;
@@ -1198,12 +1235,9 @@ __global__ void __launch_bounds__(256, ITX_XA_OCC) k_xa(const itx_xa_args A) {
             const bool in = pending && incl_b <= ITX_XA_POOL;
             const uint32_t off = incl_b - nd;
             __syncwarp();                                          /* the readers of the previous pass are done with the pool */
-            for (uint32_t m = __ballot_sync(0xffffffffu, in); m; m &= m - 1u) {
-                const int r = __ffs((int)m) - 1;
-                const uint64_t b_r = __shfl_sync(0xffffffffu, base, r);
-                const uint32_t nd_r = __shfl_sync(0xffffffffu, nd, r), off_r = __shfl_sync(0xffffffffu, off, r);
-                for (uint32_t c = lane * 16u; c < nd_r; c += 512u) itx_cp_async16_cg(pool + off_r + c, A.b + b_r + c);
-            }
+            /* every lane brings its own read's aux area (16 bytes per copy: the sectors are the same however the lanes share them out, and a
+             * loop over the reads with the warp copying each one together cost a shuffle round per read) */
+            if (in) for (uint32_t c = 0; c < nd; c += 16u) itx_cp_async16_cg(pool + off + c, A.b + base + c);
             itx_cp_async_wait_all();
             __syncwarp();
             /* every owner: XA and NM (bam_aux_get), the pieces of its list counted */

@@ -695,6 +695,7 @@ ITX_HD bool itx_xa_piece_fast(const itx_dev_index &D, const Src &S, uint32_t ps,
         uint64_t cm = 0;                                           /* bit i: byte i of the piece is a comma */
 #pragma unroll
         for (int k = 0; k < 11; k++) {
+            if (4u * (uint32_t)k >= len) break;
             const uint32_t x = itx_eq4(w[k], 0x2c2c2c2cu) >> 7;
             cm |= (uint64_t)((x | x >> 7 | x >> 14 | x >> 21) & 0xfu) << (4 * k);
         }
@@ -727,21 +728,29 @@ ITX_HD bool itx_xa_piece_fast(const itx_dev_index &D, const Src &S, uint32_t ps,
                 uint32_t h = 2166136261u;
 #pragma unroll
                 for (int i = 0; i < 31; i++) { if ((uint32_t)i >= c1) break; h ^= (w[i >> 2] >> (8 * (i & 3))) & 0xffu; h *= 16777619u; }
-                uint32_t pw[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) pw[k] = c1 >= 4u * (uint32_t)k + 4u ? w[k] : (c1 > 4u * (uint32_t)k ? w[k] & ((1u << (8u * (c1 - 4u * (uint32_t)k))) - 1u) : 0u);
+                /* the words of the name: whole ones as they are, the last one cut to the name's bytes; the padded name in the table must
+                 * equal them and be all zeros from there on (its first word past them is: names hold no zero byte) */
+                const uint32_t nwd = (c1 + 3u) >> 2;               /* 1 .. 8 */
                 const uint32_t m = D.cname_nslot - 1u;
                 for (uint32_t i = h & m;; i = (i + 1u) & m) {
                     const uint32_t v = D.cname_slot[i];
                     if (!v) return false;                          /* no such chromosome */
                     const uint32_t *nw = D.cname32 + 8u * (v - 1u);
-                    bool same = true;
+                    uint32_t nv[8];
 #if defined(__CUDA_ARCH__)
                     const uint4 na = __ldg(reinterpret_cast<const uint4 *>(nw)), nb = __ldg(reinterpret_cast<const uint4 *>(nw) + 1);
-                    same = na.x == pw[0] && na.y == pw[1] && na.z == pw[2] && na.w == pw[3] && nb.x == pw[4] && nb.y == pw[5] && nb.z == pw[6] && nb.w == pw[7];
+                    nv[0] = na.x; nv[1] = na.y; nv[2] = na.z; nv[3] = na.w; nv[4] = nb.x; nv[5] = nb.y; nv[6] = nb.z; nv[7] = nb.w;
 #else
-                    for (int k = 0; k < 8; k++) same = same && nw[k] == pw[k];
+                    for (int k = 0; k < 8; k++) nv[k] = nw[k];
 #endif
+                    bool same = true;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if ((uint32_t)k > nwd) break;
+                        uint32_t want = 0u;                        /* k == nwd: the word behind the name */
+                        if ((uint32_t)k < nwd) want = 4u * (uint32_t)k + 4u <= c1 ? w[k] : w[k] & ((1u << (8u * (c1 & 3u))) - 1u);
+                        same = same && nv[k] == want;
+                    }
                     if (same) return itx_any_other_subfam(D, (int32_t)(v - 1u), (int32_t)st, en, sel_fold);
                 }
             }

@@ -326,11 +326,12 @@ def test_fused_and_tuple_paths_count_the_same(case, mode, worlds, monkeypatch, g
 
 @pytest.mark.parametrize("flags,warps", [(0, 14), (3, 14), (4, 14), (12, 14), (15, 8), (16, 14), (16 + 256, 14), (256, 14), (511, 14), (2 + 4 + 8 + 32 + 256, 8),
                                          (2 + 4 + 8 + 16 + 32 + 64 + 256, 14),
-                                         (512, 14), (512 + 16, 14), (512 + 2 + 4 + 8 + 16 + 32 + 64 + 256, 14), (512 + 2 + 4 + 8 + 16 + 256, 8), (512 + 1 + 2 + 4 + 256, 14)])
+                                         (512, 14), (512 + 16, 14), (512 + 2 + 4 + 8 + 16 + 32 + 64 + 256, 14), (512 + 2 + 4 + 8 + 16 + 256, 8), (512 + 1 + 2 + 4 + 256, 14),
+                                         (1024 + 2 + 4 + 8 + 16 + 32 + 64 + 256, 14), (1024 + 2, 14), (1024, 8), (1024 + 512 + 2 + 16 + 256, 14)])
 @pytest.mark.parametrize("case", [SYN[1], SYN[2], SYN[4]], ids=lambda c: c[0])
 def test_scan_kernel_switches_never_change_the_counts(case, flags, warps, worlds, monkeypatch):
     """k_scan's switches (L2 prefetch, dominant-size chain walk, table window, window look-ahead, early stage copy, evict-first hint,
-    lane-per-alternate XA walk, margin carry, packed stage geometry; warps per CTA) are performance choices only: every combination gives the oracle's numbers, on a resident stream taken as ONE launch
+    lane-per-alternate XA walk, margin carry, packed stage geometry, record-by-record chain walk; warps per CTA) are performance choices only: every combination gives the oracle's numbers, on a resident stream taken as ONE launch
     group as well as through the host path"""
     name, shape, n_rmsk, rmode, n_units, kw = case
     monkeypatch.setenv("ITX_SCAN_FLAGS", str(flags))

@@ -99,6 +99,12 @@ elif what == "geom":
     scan_variants("SE-50", 0, reads, V, steps=10)
     scan_variants("PE-100", 2, reads // 2, V, steps=10)
     scan_variants("SE-75+XA", 1, reads * 3 // 5, V, steps=6)
+elif what == "three":
+    # the product kernels on the three record shapes (ITX_LIB selects a variant library)
+    V = [("product", {})]
+    scan_variants("SE-50", 0, reads, V, steps=20)
+    scan_variants("PE-100", 2, reads // 2, V, steps=10)
+    scan_variants("SE-75+XA", 1, reads * 3 // 5, V, steps=6)
 elif what == "ncu1":
     # ONE launch of k_scan (after two warm-up launches) on the stream AB_MODE / AB_READS name, with the environment as it is
     mode = int(os.environ.get("AB_MODE", "0"))
