@@ -581,10 +581,12 @@ struct itx_scan_args {
 #define ITX_SCAN_CARRY    256u           /* the margin of the stage in place becomes the head of the next one inside shared memory: it is not fetched twice */
 #define ITX_SCAN_PACK     512u           /* stages start AT a record (16-byte granule) instead of on a 4 KiB boundary and hold up to 32 whole records, one
                                           * round each: with 4 KiB of record starts per stage a 232-byte record (PE-100) fills 18 lanes of a round, packed it
-                                          * fills 22; the tail of the buffer behind the last whole record is carried inside shared memory */
+                                          * fills 22; the tail of the buffer behind the last whole record is carried inside shared memory.  Measured SLOWER
+                                          * (SE-50 2.23 -> 2.53 ms, PE-100 3.16 -> 3.50 ms): kept as a switch (ITX_SCAN_PACK=1), not the product's choice */
 #define ITX_SCAN_SERIAL   1024u          /* a span whose records keep defeating the size prediction (fewer than 2.5 records accepted per step: XA lists, long
                                           * read names of every length) walks the rest of its stages record by record -- 18 instructions per record, all
-                                          * lanes alike, against 45 per step of the predicted walk */
+                                          * lanes alike, against 45 per step of the predicted walk.  A/B switch only: compiled into the product it gains the
+                                          * SE-75 + XA stream 3 % and costs SE-50 / PE-100 4 % (a register spilled, a longer loop) */
 #define ITX_SCAN_DEFAULT  (ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
 #define ITX_WIN 32u                      /* table entries per warp window */
 #define ITX_XA_BLK 128u                  /* k_scan -> k_xa queue: a warp reserves this many entries at a time (one atomic on the queue's counter per block, not
@@ -700,7 +702,7 @@ __device__ __noinline__ void itx_flush_counters(uint32_t pa, uint32_t pb, uint32
  * select between are not in the loop at all (the loop is bound by instruction issue AND fetch: every instruction that is not
  * there helps); AB = true: the switches are read from P.flags (tests and measurements: every combination gives the same counts) */
 #ifndef ITX_SCAN_PRODUCT
-#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT | ITX_SCAN_CARRY | ITX_SCAN_SERIAL)
+#define ITX_SCAN_PRODUCT (ITX_SCAN_DEFAULT | ITX_SCAN_EVICT | ITX_SCAN_CARRY)      /* not ITX_SCAN_PACK, not ITX_SCAN_SERIAL: measured slower */
 #endif
 template <bool SMEM_HIST, int NW, bool AB, bool PACK = false>
 __global__ void __launch_bounds__(NW * 32, ITX_SCAN_CTAS(NW)) k_scan(const itx_scan_args P) {
