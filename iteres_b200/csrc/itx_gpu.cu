@@ -591,20 +591,22 @@ static int launch_tuple_path(scan_ctx *sc, uint64_t k0, uint32_t n, uint64_t ava
     sc->n_launch += 3;
     itx_overlap_args B;
     B.D = cu->D; B.b = sc->b; B.k0 = k0; B.nchunks = n; B.C = cu->C; B.S = cu->S; B.tuples = cu->d_tuples; B.nrec = cu->d_nrec; B.o = sc->o;
-    B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1;
+    B.trace = NULL; B.trace_cap = 0; B.rec_base = NULL; B.sel_out = cu->want_sel ? cu->d_sel : NULL; B.work = cu->d_work + 1; B.Dg = (const itx_dev_index *)cu->d_D;
     if (ix->trace_cap || sc->ordered) {
         if (sc->ordered) cudaMemsetAsync(cu->d_running, 0, 8, cu->stream);          /* the group's records are traced from slot 0 */
         k_rec_base<<<1, 1024, 0, cu->stream>>>(cu->d_nrec, n, cu->d_rec_base, cu->d_running);
         B.trace = cu->d_trace; B.trace_cap = cu->trace_cap; B.rec_base = cu->d_rec_base; sc->n_launch++;
     }
     const size_t hist = hist_bytes(cu);
-    bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + 1024 <= cu->smem_optin && hist <= 160 * 1024;
+    bool smem = (sc->o.filter == 0 && cu->D.stat_mode) && hist + ITX_OVL_WIN_SMEM + 1024 <= cu->smem_optin && hist <= 160 * 1024;
     int blocks = cu->sm_count * (hist > 48 * 1024 ? 1 : (hist > 24 * 1024 ? 2 : 4));
     uint32_t need_blocks = (n * ((cu->S + ITX_PART - 1) / ITX_PART) + 7) / 8; if ((uint32_t)blocks > need_blocks) blocks = (int)need_blocks; if (blocks < 1) blocks = 1;
+    /* dynamic shared memory: the histogram (when it fits), then a table window per warp */
     if (smem) {
-        if (hist > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);
-        k_overlap<true><<<blocks, 256, hist, cu->stream>>>(B);
-    } else k_overlap<false><<<blocks, 256, 0, cu->stream>>>(B);
+        const size_t sm = ((hist + 15) & ~(size_t)15) + ITX_OVL_WIN_SMEM;
+        if (sm > 48 * 1024) cudaFuncSetAttribute(k_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        k_overlap<true><<<blocks, 256, sm, cu->stream>>>(B);
+    } else k_overlap<false><<<blocks, 256, ITX_OVL_WIN_SMEM, cu->stream>>>(B);
     sc->n_launch++;
     if (timed) { cudaEventRecord(get_event(cu, sc->ev_n + 2), cu->stream); sc->ev_n += 3; }
     return ITX_OK;

@@ -427,11 +427,24 @@ struct itx_overlap_args {
     itx_trace *trace; unsigned long long trace_cap; const unsigned long long *rec_base;   /* trace != 0: per-record trace */
     long long *sel_out;                                                                  /* != 0: selected element per tuple slot */
     uint32_t *work;
+    const itx_dev_index *Dg;                                                             /* D in global memory, for the out-of-line selection of long hit lists */
 };
 
+#define ITX_WIN 32u                      /* table entries per warp window */
+#define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
+/* table loads of a walk: the warp's window when the index falls into it, global memory otherwise (same values either way) */
+struct itx_iv_window {
+    const itx_dev_index &D; const int4 *win; uint32_t base, n;
+    __device__ __forceinline__ itx_iv operator()(uint32_t i) const {
+        const uint32_t d = i - base;
+        if (d < n) { const int4 v = win[d]; itx_iv e; e.start = v.x; e.end = v.y; e.pmax = v.z; e.row = (uint32_t)v.w; return e; }
+        return itx_ld_iv(D, i);
+    }
+};
+#define ITX_OVL_WIN_SMEM (8u * ITX_WIN_BYTES)          /* k_overlap: a table window per warp, behind the histogram */
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
-    extern __shared__ uint32_t sh_hist[];
+    extern __shared__ __align__(16) uint32_t sh_hist[];
     __shared__ unsigned long long sh_cnt[13];
     const itx_dev_index &D = A.D;
     const uint32_t nh = SMEM_HIST ? 2u * (uint32_t)(D.n_sub + D.n_fam + D.n_cla) : 0u;
@@ -439,6 +452,16 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
     if (threadIdx.x < 13) sh_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
+    /* the warp's table window (as k_scan's): tuples are in file order, so the 32 fragments of a round walk the same few table entries --
+     * the entries around the highest bucket end any lane starts from are loaded once, coalesced, with their metadata, and the walks and
+     * the accumulation read them out of shared memory (global memory outside the window: same values).  A window is kept while the
+     * rounds that follow still start inside it. */
+    uint8_t *win_b = reinterpret_cast<uint8_t *>(sh_hist) + ((nh * 4u + 15u) & ~15u) + (threadIdx.x >> 5) * ITX_WIN_BYTES;
+    int4 *win_iv = reinterpret_cast<int4 *>(win_b);
+    uint4 *win_meta = reinterpret_cast<uint4 *>(win_iv + ITX_WIN);
+    int2 *win_meta2 = reinterpret_cast<int2 *>(win_meta + ITX_WIN);
+    uint32_t wbase = 0, wn = 0;
+    const uint32_t n_elem32 = D.n_elem > 0xffffffffll ? 0xffffffffu : (uint32_t)D.n_elem;
     uint32_t c[13];
 #pragma unroll
     for (int k = 0; k < 13; k++) c[k] = 0;
@@ -478,15 +501,38 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
             if ((info & ITX_F_UNKNOWN) && T.start < ITX_MAX_TID_SEEN) D.tid_unknown_seen[T.start] = 1u;
             long long sel = -1; bool diffsub = false; itx_iv e; e.start = e.end = 0; e.pmax = 0; e.row = 0;
             const uint32_t chrom = info & ITX_CHROM_MASK;
-            if (live && chrom != ITX_CHROM_NONE) {
-                int32_t nhit; float tcov;
-                sel = itx_find_select(D, (int32_t)chrom, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+            itx_query Q; Q.fs = Q.fe = 0; Q.lo = Q.top = 0;
+            const bool q_ok = live && chrom != ITX_CHROM_NONE && itx_query_open(D, (int32_t)chrom, T.start, T.end, &Q);
+            {
+                const uint32_t tmax = __reduce_max_sync(0xffffffffu, q_ok ? Q.top : 0u);
+                if (tmax && !(wn && tmax >= wbase + 8u && tmax <= wbase + wn)) {
+                    __syncwarp();                              /* the previous rounds' readers are done */
+                    wbase = tmax > 24u ? tmax - 24u : 0u;
+                    wn = n_elem32 - wbase < ITX_WIN ? n_elem32 - wbase : ITX_WIN;
+                    if (lane < wn) {
+                        win_iv[lane] = __ldg(reinterpret_cast<const int4 *>(D.iv + wbase + lane));
+                        if (stat) {
+                            win_meta[lane] = __ldg(reinterpret_cast<const uint4 *>(D.meta + wbase + lane));
+                            win_meta2[lane] = __ldg(reinterpret_cast<const int2 *>(D.meta2 + wbase + lane));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (q_ok) {
+                int32_t nhit = 0; float tcov = 0.0f;
+                sel = itx_select_walk(D, Q, itx_iv_window{D, win_iv, wbase, wn}, T.start, T.end, A.o.minCoverage, &nhit, &tcov, &e);
+                if (sel == ITX_SEL_LONG) {
+                    const itx_sel_cov r = itx_select_multi(*A.Dg, Q, T.start, T.end, nhit);
+                    sel = r.sel; tcov = r.cov;
+                    if (sel >= 0) e = itx_ld_iv(D, (uint32_t)sel);
+                }
                 if (sel >= 0 && tcov < A.o.minCoverage) sel = -1;
                 if (sel >= 0 && A.o.diffSubfam && (info & ITX_F_HASXA)) {
                     const unsigned long long p = lo + T.rec_off;
                     uint32_t x[9]; G.core(p, x);
                     uint32_t bad = 0;
-                    if (itx_mapped_to_diff_subfam(D, G, p, x, D.sinfo[D.meta[sel].sub].fold, (int32_t)(T.end - T.start), &bad)) diffsub = true;
+                    if (itx_mapped_to_diff_subfam(*A.Dg, G, p, x, (int32_t)__ldg(&D.ivf[sel].row), (int32_t)(T.end - T.start), &bad)) diffsub = true;      /* (the index in global memory: an out-of-line walk handed the parameter copy would make every thread copy it to its stack) */
                     if (bad) atomicAdd(&D.status[2], bad);
                 }
             }
@@ -496,7 +542,12 @@ __global__ void __launch_bounds__(256, 4) k_overlap(const itx_overlap_args A) {
             c[9] += __popc(m_cnt); c[10] += __popc(m_cnt & m_uniq);
             if (counted) {
                 if (stat) {
-                    const itx_meta m = D.meta[sel]; const itx_meta2 m2 = D.meta2[sel];
+                    const uint32_t wd = (uint32_t)sel - wbase;
+                    uint4 mv; int2 m2v;
+                    if (wd < wn) { mv = win_meta[wd]; m2v = win_meta2[wd]; }
+                    else { mv = __ldg(reinterpret_cast<const uint4 *>(D.meta + sel)); m2v = __ldg(reinterpret_cast<const int2 *>(D.meta2 + sel)); }
+                    itx_meta m; m.cons_start = mv.x; m.cons_end = mv.y; m.row = mv.z; m.sub = mv.w;
+                    itx_meta2 m2; m2.fam = m2v.x; m2.cla = m2v.y;
                     const uint32_t hs = 2u * m.sub, hf = 2u * (uint32_t)(D.n_sub + m2.fam), hc = 2u * (uint32_t)(D.n_sub + D.n_fam + m2.cla);
                     if (SMEM_HIST) {
                         atomicAdd(&sh_hist[hs], 1u); atomicAdd(&sh_hist[hf], 1u); atomicAdd(&sh_hist[hc], 1u);
@@ -588,14 +639,12 @@ struct itx_scan_args {
                                           * lanes alike, against 45 per step of the predicted walk.  A/B switch only: compiled into the product it gains the
                                           * SE-75 + XA stream 3 % and costs SE-50 / PE-100 4 % (a register spilled, a longer loop) */
 #define ITX_SCAN_DEFAULT  (ITX_SCAN_DOMSIZE | ITX_SCAN_WINDOW | ITX_SCAN_WINAHEAD | ITX_SCAN_EARLY | ITX_SCAN_XACOOP)
-#define ITX_WIN 32u                      /* table entries per warp window */
 #define ITX_XA_BLK 128u                  /* k_scan -> k_xa queue: a warp reserves this many entries at a time (one atomic on the queue's counter per block, not
                                           * per round: a million and more same-address atomics per launch queued up in L2 and cost cfg 3 two milliseconds);
                                           * what a warp leaves unused of its last block is marked empty (all ones) */
 #ifndef ITX_SCAN_NW
 #define ITX_SCAN_NW 14                    /* warps per k_scan CTA */
 #endif
-#define ITX_WIN_BYTES (ITX_WIN * (16u + 16u + 8u))
 /* shared memory of a k_scan CTA of NW warps: stages, record-start slots, mbarriers, table windows; the histogram follows */
 /* one contiguous block per warp (every pointer is the warp's base plus a constant) */
 #define ITX_SCAN_WARP_BYTES (ITX_STAGE + ITX_MARGIN + ITX_POS_SLOTS * 2u + 16u + ITX_WIN_BYTES)
@@ -614,15 +663,6 @@ __device__ __forceinline__ void itx_prefetch_l2_hint(const void *src, uint32_t b
     asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
 }
 
-/* table loads of a walk: the warp's window when the index falls into it, global memory otherwise (same values either way) */
-struct itx_iv_window {
-    const itx_dev_index &D; const int4 *win; uint32_t base, n;
-    __device__ __forceinline__ itx_iv operator()(uint32_t i) const {
-        const uint32_t d = i - base;
-        if (d < n) { const int4 v = win[d]; itx_iv e; e.start = v.x; e.end = v.y; e.pmax = v.z; e.row = (uint32_t)v.w; return e; }
-        return itx_ld_iv(D, i);
-    }
-};
 
 /* The chain check of a launch group, by its last CTA (k_scan) -- also what the sharded scan's host side applies between ranks.
  * A span that holds no record start at all (a record longer than a span runs over it) logs NONE for both its entry and its exit:

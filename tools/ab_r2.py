@@ -128,7 +128,7 @@ elif what == "ncu":
 elif what == "tuple":
     # the tuple path (ITX_FUSED=0) at several sizes: decode / overlap device time per scan
     os.environ["ITX_FUSED"] = "0"
-    for nr in (10_000_000, 20_000_000, 50_000_000):
+    for nr in ((reads,) if os.environ.get("AB_TUPLE_ONE") else (10_000_000, 20_000_000, 50_000_000)):
         hbuf, n, nrec, _ = make_stream(0, nr)
         dbuf, h = resident(hbuf, n)
         L.itx_host_free_pinned(hbuf)
