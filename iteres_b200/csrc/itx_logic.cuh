@@ -536,7 +536,11 @@ ITX_HD long long itx_find_head(const itx_dev_index &D, int32_t c, uint32_t start
     return bi;
 }
 /* does [s, e) on chromosome c touch any element whose case-folded subfamily differs from `fold`? */
+#ifndef ITX_XA_WALK_NOTE
+#define ITX_XA_WALK_NOTE(c, s, e, fold)      /* tests/emu notes what the parsers of an alternate ask the table for */
+#endif
 ITX_HD bool itx_any_other_subfam(const itx_dev_index &D, int32_t c, int32_t s, int32_t e, int32_t fold) {
+    ITX_XA_WALK_NOTE(c, s, e, fold);
     itx_query Q;
     if (!itx_query_open(D, c, (uint32_t)s, (uint32_t)e, &Q)) return false;
     const int32_t fs = Q.fs, fe = Q.fe;

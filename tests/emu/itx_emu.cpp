@@ -9,6 +9,8 @@
 #include <stdint.h>
 static uint64_t g_xa_fast[2];                              /* pieces of XA lists that took itx_xa_piece_fast's register path / the general one */
 #define ITX_XA_FAST_NOTE(i) (g_xa_fast[i]++)
+static int64_t g_xa_walk[5];                               /* the last question an alternate's parser asked the table: chromosome, start, end, fold; [4] how many so far */
+#define ITX_XA_WALK_NOTE(c, s, e, fold) (g_xa_walk[0] = (c), g_xa_walk[1] = (s), g_xa_walk[2] = (e), g_xa_walk[3] = (fold), g_xa_walk[4]++)
 #include "../../iteres_b200/csrc/itx_logic.cuh"
 #include "../../iteres_b200/csrc/itx_inflate.cuh"
 #include "../../iteres_b200/csrc/itx_ordered.h"
@@ -17,6 +19,7 @@ static uint64_t g_xa_fast[2];                              /* pieces of XA lists
 #include <string.h>
 #include <map>
 #include <vector>
+#include <string>
 #include <cmath>
 
 struct emu_index {
@@ -545,6 +548,59 @@ uint64_t emu_trace(emu_index *E, itx_trace *out, uint64_t cap) {
 uint64_t emu_n_bad(emu_index *E) { return E->n_bad; }
 uint64_t emu_xa_checked(emu_index *E) { return E->xa_checked; }
 uint64_t emu_xa_fast(int which) { return g_xa_fast[which & 1]; }
+/* itx_xa_piece_fast against itx_xa_piece on generated alternates: names of the index, near misses, long and empty names; positions
+ * with and without signs, leading zeros, hexadecimal, white space, too many digits; any number of commas.  Returns the number of
+ * pieces on which verdict or malformed flag differ (0). */
+uint64_t emu_xa_fuzz(emu_index *E, uint64_t seed, uint64_t n) {
+    const itx_dev_index &D = E->D; const itx_index &ix = E->ix;
+    uint64_t st = seed * 6364136223846793005ull + 1442695040888963407ull, bad = 0;
+    auto rnd = [&](uint32_t m) { st = st * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)((st >> 33) % (m ? m : 1)); };
+    alignas(16) static thread_local uint8_t pool[512 + 64];
+    for (uint64_t it = 0; it < n; it++) {
+        std::string p;
+        /* name */
+        switch (rnd(8)) {
+        case 0: break;
+        case 1: { const int L = 1 + (int)rnd(40); for (int i = 0; i < L; i++) p.push_back((char)('a' + rnd(26))); break; }
+        case 2: { std::string nm = ix.chroms.n ? ix.chroms.names[rnd((uint32_t)ix.chroms.n)] : "chr1"; nm.push_back((char)('0' + rnd(10))); p += nm; break; }
+        case 3: { std::string nm = ix.chroms.n ? ix.chroms.names[rnd((uint32_t)ix.chroms.n)] : "chr1"; if (!nm.empty()) nm.pop_back(); p += nm; break; }
+        default: p += ix.chroms.n ? ix.chroms.names[rnd((uint32_t)ix.chroms.n)] : "chr1";
+        }
+        const uint32_t ncomma = rnd(10) < 7 ? 3u : rnd(6);
+        for (uint32_t f = 1; f <= ncomma; f++) {
+            p.push_back(',');
+            if (f == 1 || f == 3 || f > 3) {                       /* a number */
+                const uint32_t k = rnd(16);
+                if (k == 0) continue;
+                if (k == 1) p += " ";
+                if (k == 2) p += "0x";
+                if (k == 3) p += "0";
+                if (f == 1 && rnd(4)) p.push_back(rnd(2) ? '+' : '-');
+                if (k == 4) p.push_back('-');
+                const uint32_t nd = f == 1 ? (k == 5 ? 9 + rnd(12) : 1 + rnd(9)) : (k == 5 ? 1 + rnd(6) : 1);
+                for (uint32_t i = 0; i < nd; i++) p.push_back((char)('0' + ((i == 0 && k != 6) ? 1 + rnd(9) : rnd(10))));
+                if (k == 7) p.push_back('x');
+                if (k == 8) p += "  ";
+            } else { const int L = (int)rnd(8); for (int i = 0; i < L; i++) p.push_back("0123456789MIDNS"[rnd(15)]); }
+        }
+        if (p.empty() || p.size() > 400) continue;
+        const uint32_t off = 16u * rnd(4) + rnd(4);                /* every alignment of the piece inside its words */
+        memset(pool, 0xA5, sizeof pool);
+        memcpy(pool + off, p.data(), p.size());
+        const itx_src_flat S{pool, 0ull};
+        const int32_t nm = (int32_t)rnd(4), qlen = 30 + (int32_t)rnd(100), fold = (int32_t)rnd((uint32_t)(ix.subs.n ? ix.subs.n : 1));
+        bool m1 = false, m2 = false;
+        int64_t a1[5], a2[5];
+        memset(g_xa_walk, 0, sizeof g_xa_walk);
+        const bool h1 = itx_xa_piece_fast(D, S, off, off + (uint32_t)p.size(), nm, qlen, fold, &m1);
+        memcpy(a1, g_xa_walk, sizeof a1); memset(g_xa_walk, 0, sizeof g_xa_walk);
+        const bool h2 = itx_xa_piece(D, S, off, off + (uint32_t)p.size(), nm, qlen, fold, &m2);
+        memcpy(a2, g_xa_walk, sizeof a2);
+        /* the same verdict, the same malformed flag, and the same question to the table (chromosome, start, end) if one was asked */
+        if (h1 != h2 || m1 != m2 || memcmp(a1, a2, sizeof a1) != 0) { if (bad < 5) fprintf(stderr, "xa fuzz: '%s' fast %d/%d general %d/%d\n", p.c_str(), (int)h1, (int)m1, (int)h2, (int)m2); bad++; }
+    }
+    return bad;
+}
 uint64_t emu_xa_mismatch(emu_index *E) { return E->xa_mismatch; }
 uint64_t emu_ring_checked(emu_index *E) { return E->ring_checked; }
 uint64_t emu_ring_mismatch(emu_index *E) { return E->ring_mismatch; }

@@ -36,6 +36,8 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.emu_xa_fast.restype = u64
         L.emu_xa_fast.argtypes = [C.c_int]
+        L.emu_xa_fuzz.restype = u64
+        L.emu_xa_fuzz.argtypes = [vp, u64, u64]
         L.emu_check_cov_rules.restype = C.c_uint64
         L.emu_check_cov_rules.argtypes = [C.c_uint64, C.c_uint64]
         L.emu_query.restype = C.c_int32
@@ -110,6 +112,10 @@ class EmuIndex(capi.IndexBase):
     def xa_fast(self):
         """(pieces of XA lists that took itx_xa_piece_fast's register path, pieces it handed to the general parser) -- process-wide"""
         return self.L.emu_xa_fast(0), self.L.emu_xa_fast(1)
+
+    def xa_fuzz(self, seed, n):
+        """itx_xa_piece_fast against itx_xa_piece on n generated alternates: the number of pieces they disagree on"""
+        return self.L.emu_xa_fuzz(self.e, seed, n)
 
     def n_bad(self):
         return self.L.emu_n_bad(self.e)

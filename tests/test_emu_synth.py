@@ -319,6 +319,25 @@ def test_xa_strings_of_every_shape(tmp_path):
     ora.close()
 
 
+def test_register_parser_of_an_alternate_agrees_with_the_general_one(tmp_path):
+    """k_xa reads an alternate of the usual shape in registers (itx_xa_piece_fast) and hands anything else to the general parser
+    (itx_xa_piece: strtol(.., 0, 0), chopByChar): on generated pieces -- names of the table, near misses, long and empty names,
+    numbers with signs, leading zeros, hexadecimal, white space, too many digits, any number of commas, every alignment -- the two
+    give the same verdict, the same malformed flag and ask the interval table the same question (chromosome, start, end), and both
+    paths are taken"""
+    d = str(tmp_path)
+    s = synth.Synth(1, 20000, seed=11)
+    cs, rs, rm = s.write_tables(d)
+    emu = emu_lib.EmuIndex(cs, rs, rm, chunk=4096)
+    f0, g0 = emu.xa_fast()
+    for seed in range(1, 9):
+        assert emu.xa_fuzz(seed, 250_000) == 0
+    f1, g1 = emu.xa_fast()
+    assert f1 - f0 > 200_000 and g1 - g0 > 200_000
+    emu.close()
+    s.close()
+
+
 def test_coverage_shortcuts_are_the_float_arithmetic():
     """itx_select_walk compares overlaps as integers (fragments shorter than 2^23 bases) and forms the coverage quotient
     only when it can fall below the threshold: both rules against the float arithmetic of getCov, on two million cases
