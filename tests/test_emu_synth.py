@@ -298,6 +298,13 @@ def test_xa_strings_of_every_shape(tmp_path):
     open(rs, "w").write("AluY\t300\nL1PA2\t6000\n")
     open(rm, "w").write("\n".join(kats.ANNOT1) + "\n")
     reads = xa_odd_reads()
+    # (here only: array counts that are negative or of an unknown subtype -- the tag walk then steps backwards or into the count's own
+    # bytes, as bam_aux_get does; k_xa's 32-bit walk hands such a read to the 64-bit one)
+    import struct
+    reads.append(kats.se("neg_small", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,1;"), ("ZB", "B", b"C" + struct.pack("<i", -3) + b"NMC\x01xx"), ("NM", "i", 1)]))
+    reads.append(kats.se("neg_back", 0, 1050, 0, aux=[("NM", "i", 1), ("ZB", "B", b"I" + struct.pack("<i", -4)), ("XA", "Z", "chr1,+5101,36M,1;")]))
+    reads.append(kats.se("neg_back2", 0, 1050, 0, aux=[("XA", "Z", "chr1,+5101,36M,1;"), ("ZB", "B", b"I" + struct.pack("<i", -4)), ("NM", "i", 1)]))
+    reads.append(kats.se("zero_sub", 0, 1050, 0, aux=[("ZB", "B", b"?" + struct.pack("<i", 7)), ("NM", "i", 1), ("XA", "Z", "chr1,+5101,36M,1;")]))
     raw = bamio.encode_header([("chr1", 1000000)]) + b"".join(bamio.encode_record(r) for r in reads)
     ora = O.OracleIndex(cs, rs, rm)
     cnt_o, tr_o = ora.scan_stream(raw, O.default_opts(), trace=True)
